@@ -1,0 +1,48 @@
+"""Shared helpers for the parity tests."""
+import json
+import os
+
+import numpy as np
+
+from dpmn_b200.schema import PGRMConfig, cmm_schema, pgrm_schema
+from oracle import inputs as gen
+from oracle.params import synth_params
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel_err(a, ref):
+    """BASELINE.md tolerance metric: max|a - ref| / max|ref|."""
+    a = np.asarray(a, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    return z, meta
+
+
+def pgrm_case(meta):
+    """(cfg, params, x_q, x_kv, residuals) rebuilt from a golden fixture's seeds."""
+    cfg = PGRMConfig(embed_dim=meta["embed"], num_heads=meta["heads"], window_size=tuple(meta["window"]),
+                     iter=meta["iter"], mode=meta["mode"])
+    P = synth_params(pgrm_schema(cfg), meta["seed"])
+    B = meta["B"]
+    x_q = gen.prior_branch2(meta["seed"], B) if meta["mode"] else gen.prior_branch1(meta["seed"], B)
+    x_kv = gen.image_stream(meta["seed"], B)
+    res = gen.residuals(meta["seed"], B, meta["nres"])
+    return cfg, P, x_q, x_kv, res
+
+
+def cmm_case(meta):
+    P = synth_params(cmm_schema(3, meta["cnum"]), meta["seed"])
+    x1 = gen.image_stream(meta["seed"], meta["B"], tag=31)
+    x2 = gen.image_stream(meta["seed"], meta["B"], tag=32)
+    return P, x1, x2
+
+
+PGRM_GOLDEN = ["pgrm_i0_m0", "pgrm_i2_m0", "pgrm_i3_m1", "pgrm_i5_m1", "pgrm_w2", "pgrm_w4", "pgrm_w8",
+               "pgrm_w16_c192", "pgrm_w48_c96_h4"]
+CMM_GOLDEN = ["cmm_c8_eval", "cmm_c8_train", "cmm_c64_eval"]

@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- SR images/sec of the DPMN hot path (6 x PGRM + CMM forward, batch 48/GPU) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|fp16|bf16] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definitions of every key.
+  value          images/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e            images/s through the public module API from pinned HOST buffers, H2D + D2H inside the timed region
+  roofline       the dominant kernel class, timed per launch with CUDA events by the library's profile hook
+  cpu_baseline   the torch-CPU port of the reference (oracle/torch_ref.py) on this host's cores, bounded sample
+--impl reference times that same CPU port as the reference arm (the reference is pure PyTorch and
+/root/reference does not exist on the GPU box; oracle/torch_ref.py is pinned to its outputs).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BATCH = 48
+METRIC = "SR images/sec"
+WORKLOAD = "DPMN hot path forward: 6xPGRM cascade (b1=b2=3, win 2/4/8, dim 96, 6 heads) + CMM, 16x64 -> 32x128, " \
+           "batch 48/GPU, synthetic PSN output + priors (configs[1] without the frozen TATT backbone)"
+
+# algorithmic FLOPs per image (2*MAC, matmul/conv only; SURVEY.md 8d / BASELINE.md section 3)
+FLOPS_IMG = {"gemm": 6 * 2 * (56_623_104 + 25_165_824 + 460_062_720 - 7_077_888),   # q/kv + SK proj(+fold) + Mlp GEMMs
+             "window_attn": 6 * 2 * 11_010_048,
+             "conv": 4_459_069_440,
+             "total": 11_267_776_512}
+
+
+def synth_inputs(seed, B):
+    from oracle import inputs as gen
+    r = np.random.default_rng([seed, 99])
+    psn = r.uniform(0, 1, size=(B, 4, 32, 128)).astype(np.float32)
+    psn[:, 3] = (psn[:, 3] > 0.5)
+    p1 = [gen.prior_branch1(seed + k, B) for k in range(3)]
+    p2 = [gen.prior_branch2(seed + k, B) for k in range(3)]
+    return psn, p1, p2
+
+
+def synth_weights(seed):
+    """Deterministic non-trivial weights for the 6 PGRMs + CMM (random-init architecture, BASELINE `data`)."""
+    from dpmn_b200.schema import PGRMConfig, cmm_schema, pgrm_schema
+    from oracle.params import synth_params
+    pg = [synth_params(pgrm_schema(PGRMConfig(iter=k, mode=(k >= 3))), seed + k) for k in range(6)]
+    cm = synth_params(cmm_schema(3, 64), seed + 50)
+    return pg, cm
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_throughput(budget_s=20.0, steps=None, warmup=1):
+    """Time oracle/torch_ref.hot_path_forward on the host cores; returns (images/s, description, ms/step, sample B)."""
+    from oracle import torch_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    pg, cm = synth_weights(2)
+    pg = [{k: torch.from_numpy(np.asarray(v)) for k, v in p.items()} for p in pg]
+    cm = {k: torch.from_numpy(np.asarray(v)) for k, v in cm.items()}
+    Bs = 8   # bounded sample of the batch-48 workload (same per-image work; the path has no cross-image coupling)
+    psn, p1, p2 = synth_inputs(1, Bs)
+    args = (torch.from_numpy(psn), [torch.from_numpy(a) for a in p1], [torch.from_numpy(a) for a in p2])
+    times = []
+    with torch.no_grad():
+        for _ in range(warmup):
+            torch_ref.hot_path_forward(pg, cm, *args)
+        t_end = time.perf_counter() + budget_s
+        n = 0
+        while (steps is None and time.perf_counter() < t_end and n < 50) or (steps is not None and n < steps):
+            t0 = time.perf_counter()
+            torch_ref.hot_path_forward(pg, cm, *args)
+            times.append(time.perf_counter() - t0)
+            n += 1
+    med = float(np.median(times))
+    return Bs / med, f"{len(times)} timed forwards of a batch-{Bs} slice of the workload (median), torch {torch.__version__} " \
+                     f"CPU fp32, {torch.get_num_threads()} threads", med * 1e3, Bs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, sample, ms, Bs = cpu_port_throughput(steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample_batch": Bs, "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from dpmn_b200 import _lib
+    from dpmn_b200.pipeline import DPMNHotPath
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the hot path has no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    assert lib.dpmn_check_device() == 0
+
+    model = DPMNHotPath(precision=args.precision)
+    pg, cm = synth_weights(2)
+    for k, m in enumerate(model.pgrm):
+        sd = m.state_dict()
+        m.load_state_dict({n: (torch.from_numpy(pg[k][n]) if n in pg[k] else v) for n, v in sd.items()}, strict=True)
+    model.cmm.load_state_dict({n: torch.from_numpy(np.asarray(cm[n])) for n in model.cmm.state_dict()}, strict=True)
+    model = model.to(dev).eval()
+
+    B = BATCH
+    n_sets = 4   # rotate input sets; the per-step working set (workspaces ~0.7 GB) is far larger than the 126 MB L2
+    host_sets, dev_sets = [], []
+    for s in range(n_sets):
+        psn, p1, p2 = synth_inputs(1000 * rank + s, B)
+        hs = (torch.from_numpy(psn).pin_memory(), [torch.from_numpy(a).pin_memory() for a in p1],
+              [torch.from_numpy(a).pin_memory() for a in p2])
+        host_sets.append(hs)
+        dev_sets.append((hs[0].to(dev), [a.to(dev) for a in hs[1]], [a.to(dev) for a in hs[2]]))
+    h2d_bytes = sum(t.numel() * 4 for t in [host_sets[0][0]] + host_sets[0][1] + host_sets[0][2])
+    out_host = torch.empty((B, 3, 32, 128), dtype=torch.float32).pin_memory()
+    d2h_bytes = out_host.numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_resident(i):
+        return model(*dev_sets[i % n_sets])
+
+    def step_e2e(i):
+        hs = host_sets[i % n_sets]
+        psn = hs[0].to(dev, non_blocking=True)
+        p1 = [a.to(dev, non_blocking=True) for a in hs[1]]
+        p2 = [a.to(dev, non_blocking=True) for a in hs[2]]
+        y = model(psn, p1, p2)
+        out_host.copy_(y, non_blocking=True)
+        return y
+
+    with torch.no_grad():
+        # ---------- value: inputs resident in HBM
+        for i in range(args.warmup):
+            step_resident(i)
+        barrier()
+        launches0 = lib.dpmn_launch_count()
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step_resident(i)
+        e1.record()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        launches = lib.dpmn_launch_count() - launches0
+        clk = clocks.stop() if rank == 0 else None
+        # ---------- e2e: pinned host buffers, H2D + D2H inside the timed region
+        for i in range(min(args.warmup, 3)):
+            step_e2e(i)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step_e2e(i)
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        # ---------- per-kernel-class timing (roofline leg), outside the throughput regions
+        prof = None
+        if rank == 0:
+            lib.dpmn_profile_enable(1)
+            n_prof = 2
+            for i in range(n_prof):
+                step_resident(i)
+            torch.cuda.synchronize()
+            import ctypes as C
+            cap = 20000
+            tags, nk, ms = (C.c_int32 * cap)(), (C.c_int32 * cap)(), (C.c_float * cap)()
+            n = lib.dpmn_profile_collect(tags, nk, ms, cap)
+            lib.dpmn_profile_enable(0)
+            agg = {}
+            for j in range(n):
+                name = lib.dpmn_profile_tag_name(tags[j]).decode()
+                a = agg.setdefault(name, [0.0, 0])
+                a[0] += ms[j] / n_prof
+                a[1] += nk[j]
+            prof = {k: {"ms_per_step": v[0], "launches_per_step": v[1] // n_prof} for k, v in agg.items()}
+
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step / 1e3)
+    e2e_val = B * world / (ms_e2e / args.steps / 1e3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if peaks else "fallback"
+    dom = max((k for k in prof if k in FLOPS_IMG), key=lambda k: prof[k]["ms_per_step"])
+    dom_ms = prof[dom]["ms_per_step"]
+    achieved = FLOPS_IMG[dom] * B / (dom_ms / 1e3) / 1e12
+    total_prof_ms = sum(v["ms_per_step"] for v in prof.values())
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": achieved / tensor_peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": dom_ms / total_prof_ms,
+                "launches_per_step": prof[dom]["launches_per_step"],
+                "avg_launch_ms": dom_ms / max(1, prof[dom]["launches_per_step"]),
+                "whole_step_tflops": FLOPS_IMG["total"] * B / (ms_step / 1e3) / 1e12,
+                "by_kernel_ms": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, sample, _, _ = cpu_port_throughput(budget_s=15.0)
+        cpu = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"replicas x{world} (no collective: inference)",
+                       "l2": f"inputs rotate over {n_sets} sets; per-step working set (activations/workspace) >> 126 MB L2"},
+            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--precision", default=os.environ.get("DPMN_PRECISION", "fp32"))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,123 @@
+"""ctypes binding of libdpmn_b200.so (include/dpmn_b200.h).
+
+The shared library is the product: there is NO fallback.  If it is missing or does not export the
+symbols of the header, importing the compute modules raises.  Structs mirror the header field by field
+and are verified against `dpmn_abi_sizeof` at load time.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdpmn_b200.so")
+
+MAX_GROUPS, MAX_MIX, MAX_BLOCKS = 4, 8, 2
+PREC = {"fp32": 0, "f32": 0, "fp16": 1, "f16": 1, "bf16": 2}
+ERRORS = {-1: "DPMN_E_ARG (null pointer / inconsistent sizes)",
+          -2: "DPMN_E_UNSUPPORTED (configuration outside this build or that the reference cannot run)",
+          -3: "DPMN_E_WORKSPACE (workspace too small)",
+          -4: "DPMN_E_DEVICE (not an sm_100 device)"}
+
+fp = C.c_void_p   # device pointers travel as integers
+
+
+class BlockWeights(C.Structure):
+    _fields_ = ([(n, fp) for n in ("norm1_q_w", "norm1_q_b", "norm1_kv_w", "norm1_kv_b")]
+                + [("rpb_table", fp * MAX_GROUPS)]
+                + [(n, fp) for n in ("q_w", "q_b", "kv_w", "kv_b", "sk_proj_w", "sk_proj_b", "sk_fc1_w", "sk_fc1_b",
+                                     "sk_fc2_w", "sk_fc2_b", "sk_head_w", "sk_head_b", "norm2_w", "norm2_b",
+                                     "fc1_w", "fc1_b", "fc2_w", "fc2_b", "dw_w", "dw_b", "pw_w", "pw_b")])
+
+
+class PgrmDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32), ("patch", C.c_int32),
+                ("q_chans", C.c_int32), ("embed_dim", C.c_int32), ("num_heads", C.c_int32),
+                ("n_groups", C.c_int32), ("window", C.c_int32 * MAX_GROUPS), ("mlp_hidden", C.c_int32),
+                ("hidden_size", C.c_int32), ("precision", C.c_int32), ("n_mix", C.c_int32),
+                ("x_q_batch_stride", C.c_int64), ("x_kv_batch_stride", C.c_int64),
+                ("prior_fusion_w", fp), ("prior_fusion_b", fp), ("pe_w", fp), ("pe_b", fp),
+                ("pe_norm_w", fp), ("pe_norm_b", fp),
+                ("blocks", BlockWeights * MAX_BLOCKS),
+                ("head0_w", fp), ("head0_b", fp), ("head1_w", fp), ("head1_b", fp),
+                ("mix_weight", fp * MAX_MIX), ("mix_input", fp * MAX_MIX),
+                ("mix_input_batch_stride", C.c_int64 * MAX_MIX)]
+
+
+class Bn(C.Structure):
+    _fields_ = [("w", fp), ("b", fp), ("running_mean", fp), ("running_var", fp)]
+
+
+class CmmStage(C.Structure):
+    _fields_ = [("conv_a_w", fp), ("conv_a_b", fp), ("bn_a", Bn), ("conv_b_w", fp), ("conv_b_b", fp), ("bn_b", Bn)]
+
+
+class CmmDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32), ("c_img", C.c_int32),
+                ("cnum", C.c_int32), ("precision", C.c_int32), ("training", C.c_int32),
+                ("update_running_stats", C.c_int32),
+                ("x1_batch_stride", C.c_int64), ("x2_batch_stride", C.c_int64),
+                ("en1_w", fp * 2), ("en1_b", fp * 2),
+                ("enc", (CmmStage * 4) * 2),
+                ("en6_w", fp * 2), ("en6_b", fp * 2),
+                ("fc1_w", fp), ("fc1_b", fp), ("fc2_w", fp), ("fc2_b", fp),
+                ("de6_w", fp), ("de6_b", fp), ("de6_bn", Bn),
+                ("dec", CmmStage * 4),
+                ("de1_w", fp), ("de1_b", fp)]
+
+
+# every symbol include/dpmn_b200.h declares: (restype, argtypes)
+_i32, _sz, _vp = C.c_int32, C.c_size_t, C.c_void_p
+SYMBOLS = {
+    "dpmn_version": (C.c_char_p, []),
+    "dpmn_check_device": (C.c_int, []),
+    "dpmn_abi_sizeof": (_sz, [_i32]),
+    "dpmn_launch_count": (C.c_uint64, []),
+    "dpmn_profile_enable": (C.c_int, [_i32]),
+    "dpmn_profile_collect": (_i32, [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(C.c_float), _i32]),
+    "dpmn_profile_tag_name": (C.c_char_p, [_i32]),
+    "dpmn_pgrm_workspace_bytes": (_sz, [C.POINTER(PgrmDesc)]),
+    "dpmn_pgrm_forward": (C.c_int, [C.POINTER(PgrmDesc), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dpmn_pgrm_forward_probe": (C.c_int, [C.POINTER(PgrmDesc), _vp, _vp, _vp, _vp, _sz, _vp,
+                                          C.POINTER(_vp * MAX_BLOCKS), C.POINTER(_vp * MAX_BLOCKS)]),
+    "dpmn_window_attn_forward": (C.c_int, [_vp, _vp, _vp, C.POINTER(_vp * MAX_GROUPS), _i32, _i32, _i32, _i32, _i32,
+                                           _i32, C.POINTER(_i32 * MAX_GROUPS), C.POINTER(_i32 * MAX_GROUPS), _i32,
+                                           _vp, _sz, _vp]),
+    "dpmn_window_attn_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "dpmn_cmm_workspace_bytes": (_sz, [C.POINTER(CmmDesc)]),
+    "dpmn_cmm_forward": (C.c_int, [C.POINTER(CmmDesc), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dpmn_gemm_nt": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "dpmn_gemm_nt_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and type the C-ABI library.  Raises if it is absent or incomplete: no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"dpmn_b200: {LIB_PATH} is missing.  Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C dpmn_b200/csrc`).  There is no CPU or PyTorch fallback for the hot path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)   # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    for which, st in enumerate((BlockWeights, PgrmDesc, Bn, CmmStage, CmmDesc)):
+        got = lib.dpmn_abi_sizeof(which)
+        if got != C.sizeof(st):
+            raise RuntimeError(f"dpmn_b200: ABI mismatch for {st.__name__}: library {got} B, binding {C.sizeof(st)} B")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise RuntimeError(f"{what}: {ERRORS.get(rc, rc)}")
+    raise RuntimeError(f"{what}: CUDA error {rc}")

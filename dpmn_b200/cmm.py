@@ -1,0 +1,126 @@
+"""Drop-in `ComplementationModulationModule`: the reference's constructor, forward signature and state_dict
+schema (/root/reference/model/cmm.py:80-161) over the libdpmn_b200 C-ABI.  No PyTorch/CPU compute path."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .pgrm import ParamTree, workspace
+from .schema import cmm_schema
+
+
+def _initial_value(name: str, shape) -> torch.Tensor:
+    """torch defaults, which is all the reference uses for this module (no custom init in cmm.py):
+    kaiming_uniform(a=sqrt(5)) conv/linear weights, U(+-1/sqrt(fan_in)) biases, BN (1, 0, mean 0, var 1)."""
+    leaf = name.rsplit(".", 1)[-1]
+    if leaf == "num_batches_tracked":
+        return torch.zeros((), dtype=torch.long)
+    t = torch.empty(tuple(shape), dtype=torch.float32)
+    if leaf in ("running_mean",):
+        return t.zero_()
+    if leaf in ("running_var",):
+        return t.fill_(1.0)
+    if len(shape) >= 2:
+        return nn.init.kaiming_uniform_(t, a=math.sqrt(5))
+    return t   # 1-D: resolved by the caller (needs the sibling weight's fan-in)
+
+
+class ComplementationModulationModule(ParamTree):
+    """cmm.py:80-81 signature.  Extra keyword `precision` as in `PGRM`."""
+
+    def __init__(self, c_img=3, norm='batch', act_en='leaky_relu', act_de='relu', cnum=64, precision="fp32"):
+        super().__init__()
+        if norm != 'batch' or act_en != 'leaky_relu' or act_de != 'relu':
+            raise NotImplementedError("dpmn_b200 CMM implements the configuration DPMN instantiates "
+                                      "(norm='batch', act_en='leaky_relu', act_de='relu'; super_resolution.py:72)")
+        self.c_img, self.cnum, self.precision = int(c_img), int(cnum), precision
+        schema = cmm_schema(self.c_img, self.cnum)
+        shapes = {n: s for n, s, _ in schema}
+        for name, shape, kind in schema:
+            leaf = name.rsplit(".", 1)[-1]
+            v = _initial_value(name, shape)
+            if len(shape) == 1 and kind == "param":
+                stem = name.rsplit(".", 1)[0]
+                wshape = shapes[stem + ".weight"]
+                if len(wshape) == 1:          # BatchNorm affine
+                    v = v.fill_(1.0) if leaf == "weight" else v.zero_()
+                else:                         # conv / linear bias: fan_in of the sibling weight
+                    fan_in = 1
+                    for s in wshape[1:]:
+                        fan_in *= s
+                    bound = 1.0 / math.sqrt(fan_in)
+                    v = v.uniform_(-bound, bound)
+            self.attach(name, v, kind)
+        _lib.load()
+
+    def _ptr(self, name: str) -> int:
+        t = self.fetch(name)
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError(f"dpmn_b200 CMM: {name} must be a contiguous fp32 CUDA tensor (got {t.device}, "
+                               f"{t.dtype}); there is no CPU path")
+        return t.data_ptr()
+
+    def _bn(self, dst: _lib.Bn, stem: str):
+        dst.w, dst.b = self._ptr(stem + ".weight"), self._ptr(stem + ".bias")
+        dst.running_mean, dst.running_var = self._ptr(stem + ".running_mean"), self._ptr(stem + ".running_var")
+
+    def _stage(self, dst: _lib.CmmStage, stem: str):
+        dst.conv_a_w, dst.conv_a_b = self._ptr(stem + "1.weight"), self._ptr(stem + "1.bias")
+        self._bn(dst.bn_a, stem + "2")
+        dst.conv_b_w, dst.conv_b_b = self._ptr(stem + "4.weight"), self._ptr(stem + "4.bias")
+        self._bn(dst.bn_b, stem + "5")
+
+    def _descriptor(self, B, H, W) -> _lib.CmmDesc:
+        d = _lib.CmmDesc()
+        d.batch, d.img_h, d.img_w, d.c_img, d.cnum = B, H, W, self.c_img, self.cnum
+        d.precision = _lib.PREC[self.precision]
+        d.training = int(self.training)
+        d.update_running_stats = int(self.training)
+        for br in (0, 1):
+            d.en1_w[br], d.en1_b[br] = self._ptr(f"en_1_{br + 1}.weight"), self._ptr(f"en_1_{br + 1}.bias")
+            for l, lvl in enumerate((2, 3, 4, 5)):
+                self._stage(d.enc[br][l], f"en_{lvl}_{br + 1}.encode.")
+            d.en6_w[br], d.en6_b[br] = self._ptr(f"en_6_{br + 1}.1.weight"), self._ptr(f"en_6_{br + 1}.1.bias")
+        d.fc1_w, d.fc1_b = self._ptr("fc_1.weight"), self._ptr("fc_1.bias")
+        d.fc2_w, d.fc2_b = self._ptr("fc_2.weight"), self._ptr("fc_2.bias")
+        d.de6_w, d.de6_b = self._ptr("de_6.1.weight"), self._ptr("de_6.1.bias")
+        self._bn(d.de6_bn, "de_6.2")
+        for i, lvl in enumerate((5, 4, 3, 2)):
+            self._stage(d.dec[i], f"de_{lvl}.decode.")
+        d.de1_w, d.de1_b = self._ptr("de_1.1.weight"), self._ptr("de_1.1.bias")
+        return d
+
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        for n, t in (("x1", x1), ("x2", x2)):
+            if not t.is_cuda:
+                raise RuntimeError(f"dpmn_b200 CMM: {n} is on {t.device}; the hot path only exists on CUDA")
+            if t.dtype != torch.float32 or t.dim() != 4 or t.shape[1] != self.c_img:
+                raise ValueError(f"dpmn_b200 CMM: {n} must be fp32 (B,{self.c_img},H,W), got {t.dtype} {tuple(t.shape)}")
+        if x1.shape != x2.shape:
+            raise ValueError("CMM.forward: x1 and x2 must have the same shape")
+        x1, x2 = x1.contiguous(), x2.contiguous()
+        B, _, H, W = x1.shape
+        if self.training and B * (H // 32) * (W // 32) == 1:
+            # nn.BatchNorm2d raises for a single value per channel in training mode
+            raise ValueError("Expected more than 1 value per channel when training")
+        d = self._descriptor(B, H, W)
+        dev = x1.device
+        with torch.cuda.device(dev):
+            nbytes = lib.dpmn_cmm_workspace_bytes(C.byref(d))
+            if nbytes == 0:
+                raise RuntimeError("dpmn_cmm_workspace_bytes: configuration rejected (image sides must be multiples of 32)")
+            ws = workspace(dev, nbytes)
+            out = torch.empty_like(x1)
+            rc = lib.dpmn_cmm_forward(C.byref(d), x1.data_ptr(), x2.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "dpmn_cmm_forward")
+        if self.training:
+            for name, buf in self.named_buffers():
+                if name.endswith("num_batches_tracked"):
+                    buf += 1
+        return out

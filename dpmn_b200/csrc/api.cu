@@ -1,0 +1,544 @@
+// C-ABI of libdpmn_b200 (include/dpmn_b200.h): argument checking, workspace carving and the launch
+// sequences of PGRM.forward (pgrm.py:546-565) and ComplementationModulationModule.forward (cmm.py:120-161).
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/dpmn_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace dpmn;
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+
+// Optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream around every
+// kernel launch, tagged by kernel class.  Off by default; never active inside a timed throughput region.
+enum KTag { T_PATCH_EMBED = 0, T_LAYERNORM, T_GEMM, T_WINDOW_ATTN, T_SK_GATE, T_DWCONV, T_HEAD, T_CONV, T_BN,
+            T_SE_GATE, T_COUNT };
+const char* const kTagNames[T_COUNT] = {"patch_embed", "layernorm", "gemm", "window_attn", "sk_gate",
+                                        "dwconv", "head", "conv", "bn_affine", "se_gate"};
+struct ProfRec { int tag; int n; cudaEvent_t e0, e1; };
+bool g_prof = false;
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_recs;
+
+struct ProfScope {
+  bool on; ProfRec r; cudaStream_t st;
+  ProfScope(int tag, int n, cudaStream_t s) : on(g_prof), st(s) {
+    if (!on) return;
+    r.tag = tag; r.n = n;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.e1, st);
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    g_recs.push_back(r);
+  }
+};
+
+#define DPMN_RUN(tag, expr, n_kernels)       \
+  do {                                       \
+    int _rc;                                 \
+    {                                        \
+      ProfScope _ps(tag, n_kernels, st);     \
+      _rc = (expr);                          \
+    }                                        \
+    if (_rc != 0) return _rc;                \
+    g_launches.fetch_add(n_kernels);         \
+  } while (0)
+
+struct Bump {
+  char* base;
+  size_t off = 0, cap;
+  Bump(void* p, size_t c) : base((char*)p), cap(c) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* r = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+};
+
+struct PgrmWs {
+  float *tq, *tkv, *ln, *q, *kv, *attn, *colsum, *wb, *bias_b, *h, *dt, *t1;
+  size_t bytes;
+};
+
+PgrmWs carve_pgrm(const dpmn_pgrm_desc* d, void* ws) {
+  const size_t B = d->batch, C = d->embed_dim, hid = d->mlp_hidden;
+  const size_t L = (size_t)(d->img_h / d->patch) * (d->img_w / d->patch);
+  Bump b(ws, (size_t)-1);
+  PgrmWs w;
+  w.tq = b.take<float>(B * L * C);
+  w.tkv = b.take<float>(B * L * C);
+  w.ln = b.take<float>(B * L * C);
+  w.q = b.take<float>(B * L * C);
+  w.kv = b.take<float>(B * L * 2 * C);
+  w.attn = b.take<float>(B * L * C);
+  w.colsum = b.take<float>(B * ((L + kSimtTileM - 1) / kSimtTileM) * C);
+  w.wb = b.take<float>(B * C * C);
+  w.bias_b = b.take<float>(B * C);
+  w.h = b.take<float>(B * L * hid);
+  w.dt = b.take<float>(B * L * hid);
+  w.t1 = b.take<float>(B * L * 16);
+  w.bytes = b.off + 256;
+  return w;
+}
+
+int check_pgrm(const dpmn_pgrm_desc* d) {
+  if (!d) return DPMN_E_ARG;
+  if (d->batch < 1 || d->patch < 1 || d->img_h % d->patch || d->img_w % d->patch) return DPMN_E_ARG;
+  if (d->n_groups < 1 || d->n_groups > DPMN_MAX_GROUPS) return DPMN_E_ARG;
+  if (d->embed_dim % d->n_groups || d->num_heads % d->n_groups) return DPMN_E_ARG;
+  if ((d->embed_dim / d->n_groups) % (d->num_heads / d->n_groups)) return DPMN_E_ARG;
+  if (d->q_chans != 2 && d->q_chans != 3) return DPMN_E_ARG;
+  if (d->q_chans == 2 && (!d->prior_fusion_w || !d->prior_fusion_b)) return DPMN_E_ARG;
+  if (d->n_mix < 1 || d->n_mix > DPMN_MAX_MIX) return DPMN_E_ARG;
+  if (d->precision != DPMN_PREC_F32) return DPMN_E_UNSUPPORTED;
+  const int H = d->img_h / d->patch, W = d->img_w / d->patch;
+  const int mn = H < W ? H : W;
+  for (int g = 0; g < d->n_groups; ++g) {
+    const int ws = d->window[g];
+    // a window larger than min(H, W) is clamped by the reference but its bias table keeps the configured
+    // size, so the reference's own forward raises (pgrm.py:127-151,234-236)
+    if (ws < 1 || ws > mn) return DPMN_E_UNSUPPORTED;
+    if (H % ws || W % ws) return DPMN_E_UNSUPPORTED;   // the reference's pad path cannot run
+  }
+  if (d->embed_dim % 32 || d->mlp_hidden % 32) return DPMN_E_UNSUPPORTED;
+  return 0;
+}
+
+int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_kv, float* out, void* workspace,
+                      size_t workspace_bytes, void* stream, float* const* attn_core, float* const* block_out) {
+  int rc = check_pgrm(d);
+  if (rc) return rc;
+  if (!x_q || !x_kv || !out || !workspace) return DPMN_E_ARG;
+  const PgrmWs w = carve_pgrm(d, workspace);
+  if (workspace_bytes < w.bytes) return DPMN_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  const int B = d->batch, C = d->embed_dim, hid = d->mlp_hidden, G = d->n_groups;
+  const int H = d->img_h / d->patch, W = d->img_w / d->patch, L = H * W;
+  const int rows = B * L;
+  const long long plane = (long long)d->img_h * d->img_w;
+  const long long xq_bs = d->x_q_batch_stride ? d->x_q_batch_stride : (long long)d->q_chans * plane;
+  const long long xkv_bs = d->x_kv_batch_stride ? d->x_kv_batch_stride : 3LL * plane;
+
+  // K0: both streams share the patch-embed weights (pgrm.py:549-550)
+  DPMN_RUN(T_PATCH_EMBED, launch_patch_embed(x_q, xq_bs, d->q_chans, d->q_chans == 2 ? d->prior_fusion_w : nullptr,
+                              d->prior_fusion_b, d->pe_w, d->pe_b, d->pe_norm_w, d->pe_norm_b, w.tq, B, d->img_h,
+                              d->img_w, d->patch, C, st), 1);
+  DPMN_RUN(T_PATCH_EMBED, launch_patch_embed(x_kv, xkv_bs, 3, nullptr, nullptr, d->pe_w, d->pe_b, d->pe_norm_w, d->pe_norm_b,
+                              w.tkv, B, d->img_h, d->img_w, d->patch, C, st), 1);
+
+  for (int blk = 0; blk < DPMN_MAX_BLOCKS; ++blk) {
+    const dpmn_block_weights& bw = d->blocks[blk];
+    // ---- K1: LayerNorms + q / kv projections (pgrm.py:322-323,188,194)
+    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tq, bw.norm1_q_w, bw.norm1_q_b, w.ln, DT_F32, rows, C, st), 1);
+    {
+      GemmSimtArgs g;
+      g.A = w.ln; g.lda = C; g.Bm = bw.q_w; g.ldb = C; g.C = w.q; g.ldc = C;
+      g.M = rows; g.N = C; g.K = C; g.bias = bw.q_b; g.bias_mode = 1;
+      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+    }
+    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm1_kv_w, bw.norm1_kv_b, w.ln, DT_F32, rows, C, st), 1);
+    {
+      GemmSimtArgs g;
+      g.A = w.ln; g.lda = C; g.Bm = bw.kv_w; g.ldb = C; g.C = w.kv; g.ldc = 2 * C;
+      g.M = rows; g.N = 2 * C; g.K = C; g.bias = bw.kv_b; g.bias_mode = 1;
+      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+    }
+    // ---- K2: windowed attention core (pgrm.py:197-268)
+    {
+      AttnArgs a;
+      a.q = w.q; a.kv = w.kv; a.out = w.attn; a.io_type = DT_F32;
+      a.q_ld = C; a.kv_ld = 2 * C; a.v_off = C; a.out_ld = C;
+      a.B = B; a.H = H; a.W = W; a.C = C; a.n_groups = G; a.heads_per_group = d->num_heads / G;
+      const int mn = H < W ? H : W;
+      for (int g = 0; g < G; ++g) {
+        a.table[g] = bw.rpb_table[g];
+        a.window[g] = d->window[g];
+        a.shift[g] = (blk % 2 == 0 || mn <= d->window[g]) ? 0 : d->window[g] / 2;   // pgrm.py:148-150,362
+      }
+      DPMN_RUN(T_WINDOW_ATTN, launch_window_attn_simt(a, st), G);
+    }
+    if (attn_core && attn_core[blk])
+      DPMN_CUDA_TRY(cudaMemcpyAsync(attn_core[blk], w.attn, (size_t)rows * C * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, st));
+    // ---- K3: SK gate (pgrm.py:79-96): pass 1 pooled GELU(proj), fold, pass 2 per-image GEMM + residual
+    const int tiles = (L + kSimtTileM - 1) / kSimtTileM;
+    {
+      GemmSimtArgs g;
+      g.A = w.attn; g.a_bs = (long long)L * C; g.lda = C; g.Bm = bw.sk_proj_w; g.ldb = C;
+      g.M = L; g.N = C; g.K = C; g.batch = B; g.bias = bw.sk_proj_b; g.bias_mode = 1; g.act = 1;
+      g.colsum = w.colsum;
+      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+    }
+    DPMN_RUN(T_SK_GATE, launch_sk_gate(w.colsum, tiles, L, bw.sk_proj_w, bw.sk_proj_b, bw.sk_fc1_w, bw.sk_fc1_b, bw.sk_fc2_w,
+                            bw.sk_fc2_b, bw.sk_head_w, bw.sk_head_b, w.wb, DT_F32, w.bias_b, B, C, G, st), 1);
+    {
+      GemmSimtArgs g;   // x_kv = shortcut + attn (pgrm.py:329), in place on the kv stream
+      g.A = w.attn; g.a_bs = (long long)L * C; g.lda = C; g.Bm = w.wb; g.b_bs = (long long)C * C; g.ldb = C;
+      g.C = w.tkv; g.c_bs = (long long)L * C; g.ldc = C; g.M = L; g.N = C; g.K = C; g.batch = B;
+      g.bias = w.bias_b; g.bias_bs = C; g.bias_mode = 1; g.residual = w.tkv;
+      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+    }
+    // ---- K4: norm2 + Mlp (pgrm.py:330, 29-41)
+    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm2_w, bw.norm2_b, w.ln, DT_F32, rows, C, st), 1);
+    {
+      GemmSimtArgs g;   // fc1 + GELU
+      g.A = w.ln; g.lda = C; g.Bm = bw.fc1_w; g.ldb = C; g.C = w.h; g.ldc = hid;
+      g.M = rows; g.N = hid; g.K = C; g.bias = bw.fc1_b; g.bias_mode = 1; g.act = 1;
+      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+    }
+    DPMN_RUN(T_DWCONV, launch_dwconv(w.h, w.dt, DT_F32, bw.dw_w, bw.dw_b, B, L, hid, st), 1);
+    {
+      GemmSimtArgs g;   // pointwise conv: per image (hid x hid) * (hid x L), written (hid, L) = the raw view
+      g.A = bw.pw_w; g.lda = hid; g.Bm = w.dt; g.b_bs = (long long)L * hid; g.ldb = hid;
+      g.C = w.h; g.c_bs = (long long)L * hid; g.ldc = L; g.M = hid; g.N = L; g.K = hid; g.batch = B;
+      g.bias = bw.pw_b; g.bias_mode = 2;
+      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+    }
+    {
+      GemmSimtArgs g;   // fc2 on the raw (L, hid) view + residual, in place on the kv stream
+      g.A = w.h; g.lda = hid; g.Bm = bw.fc2_w; g.ldb = hid; g.C = w.tkv; g.ldc = C;
+      g.M = rows; g.N = C; g.K = hid; g.bias = bw.fc2_b; g.bias_mode = 1; g.residual = w.tkv;
+      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+    }
+    if (block_out && block_out[blk])
+      DPMN_CUDA_TRY(cudaMemcpyAsync(block_out[blk], w.tkv, (size_t)rows * C * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, st));
+  }
+
+  // ---- K5: head (pgrm.py:559-564)
+  const int hp = d->hidden_size * d->patch * d->patch;
+  DPMN_RUN(T_HEAD, launch_head_conv1(w.tkv, d->head0_w, d->head0_b, w.t1, B, H, W, C, hp, st), 1);
+  MixArgs mix;
+  mix.n_mix = d->n_mix;
+  for (int i = 0; i < d->n_mix; ++i) {
+    if (!d->mix_weight[i] || (i > 0 && !d->mix_input[i])) return DPMN_E_ARG;
+    mix.w[i] = d->mix_weight[i];
+    mix.in[i] = d->mix_input[i];
+    mix.in_bs[i] = d->mix_input_batch_stride[i] ? d->mix_input_batch_stride[i] : (long long)d->hidden_size * plane;
+  }
+  DPMN_RUN(T_HEAD, launch_head_conv2_mix(w.t1, d->head1_w, d->head1_b, out, B, H, W, d->hidden_size, d->patch, mix, st), 1);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct CmmWs {
+  float* o[2][6];        // encoder outputs o1..o6 per branch (raw conv outputs)
+  float* mid[2][4];      // EncodeBlock intermediates
+  float* o_sc[2][6];     // BN affine of o2..o5 (index 1..4), nullptr otherwise
+  float* o_sh[2][6];
+  float* mid_sc[2][4];
+  float* mid_sh[2][4];
+  float* z;              // gated bottleneck (B, 16c, h/32, w/32)
+  float* d6; float *d6_sc, *d6_sh;
+  float* dmid[4]; float *dmid_sc[4], *dmid_sh[4];
+  float* dout[4]; float *dout_sc[4], *dout_sh[4];
+  size_t bytes;
+};
+
+CmmWs carve_cmm(const dpmn_cmm_desc* d, void* ws) {
+  const size_t B = d->batch, c = d->cnum, H = d->img_h, W = d->img_w;
+  const size_t ch_o[6] = {c, 2 * c, 4 * c, 8 * c, 8 * c, 8 * c};
+  Bump b(ws, (size_t)-1);
+  CmmWs w;
+  memset(&w, 0, sizeof(w));
+  for (int br = 0; br < 2; ++br) {
+    for (int l = 0; l < 6; ++l) {
+      const size_t hw = (H >> l) * (W >> l);
+      w.o[br][l] = b.take<float>(B * ch_o[l] * hw);
+      if (l >= 1 && l <= 4) {
+        w.o_sc[br][l] = b.take<float>(ch_o[l]);
+        w.o_sh[br][l] = b.take<float>(ch_o[l]);
+      }
+    }
+    for (int l = 0; l < 4; ++l) {   // EncodeBlock l+2: conv_a keeps ch_o[l] channels at half resolution
+      const size_t hw = (H >> (l + 1)) * (W >> (l + 1));
+      w.mid[br][l] = b.take<float>(B * ch_o[l] * hw);
+      w.mid_sc[br][l] = b.take<float>(ch_o[l]);
+      w.mid_sh[br][l] = b.take<float>(ch_o[l]);
+    }
+  }
+  w.z = b.take<float>(B * 16 * c * (H >> 5) * (W >> 5));
+  w.d6 = b.take<float>(B * 8 * c * (H >> 4) * (W >> 4));
+  w.d6_sc = b.take<float>(8 * c);
+  w.d6_sh = b.take<float>(8 * c);
+  const size_t ch_d[4] = {8 * c, 4 * c, 2 * c, c};   // de_5, de_4, de_3, de_2 output channels
+  for (int i = 0; i < 4; ++i) {
+    const size_t hw_in = (H >> (4 - i)) * (W >> (4 - i));
+    w.dmid[i] = b.take<float>(B * ch_d[i] * hw_in);
+    w.dmid_sc[i] = b.take<float>(ch_d[i]);
+    w.dmid_sh[i] = b.take<float>(ch_d[i]);
+    w.dout[i] = b.take<float>(B * ch_d[i] * hw_in * 4);
+    w.dout_sc[i] = b.take<float>(ch_d[i]);
+    w.dout_sh[i] = b.take<float>(ch_d[i]);
+  }
+  w.bytes = b.off + 256;
+  return w;
+}
+
+int bn_affine(const dpmn_cmm_desc* d, const dpmn_bn& bn, const float* x, int ch, int hw, float* sc, float* sh,
+              cudaStream_t st) {
+  if (!bn.w || !bn.b || !bn.running_mean || !bn.running_var) return DPMN_E_ARG;
+  return launch_bn_affine(x, d->batch, ch, hw, bn.w, bn.b, bn.running_mean, bn.running_var, d->training,
+                          d->training && d->update_running_stats, 1e-5f, sc, sh, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dpmn_version(void) { return "dpmn_b200 0.1 (sm_100a)"; }
+
+int dpmn_check_device(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return DPMN_E_DEVICE;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return DPMN_E_DEVICE;
+  return major == 10 ? 0 : DPMN_E_DEVICE;
+}
+
+uint64_t dpmn_launch_count(void) { return g_launches.load(); }
+
+int dpmn_profile_enable(int32_t on) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  for (auto& r : g_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_recs.clear();
+  g_prof = on != 0;
+  return 0;
+}
+
+int32_t dpmn_profile_collect(int32_t* tags, int32_t* n_kernels, float* ms, int32_t cap) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  int32_t n = 0;
+  for (auto& r : g_recs) {
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) return -1;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) return -1;
+    if (n < cap) { tags[n] = r.tag; n_kernels[n] = r.n; ms[n] = t; ++n; }
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_recs.clear();
+  return n;
+}
+
+const char* dpmn_profile_tag_name(int32_t tag) { return (tag >= 0 && tag < T_COUNT) ? kTagNames[tag] : ""; }
+
+size_t dpmn_abi_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(dpmn_block_weights);
+    case 1: return sizeof(dpmn_pgrm_desc);
+    case 2: return sizeof(dpmn_bn);
+    case 3: return sizeof(dpmn_cmm_stage);
+    case 4: return sizeof(dpmn_cmm_desc);
+  }
+  return 0;
+}
+
+size_t dpmn_pgrm_workspace_bytes(const dpmn_pgrm_desc* d) {
+  if (check_pgrm(d)) return 0;
+  return carve_pgrm(d, nullptr).bytes;
+}
+
+int dpmn_pgrm_forward(const dpmn_pgrm_desc* d, const float* x_q, const float* x_kv, float* out, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return pgrm_forward_impl(d, x_q, x_kv, out, workspace, workspace_bytes, stream, nullptr, nullptr);
+}
+
+int dpmn_pgrm_forward_probe(const dpmn_pgrm_desc* d, const float* x_q, const float* x_kv, float* out,
+                            void* workspace, size_t workspace_bytes, void* stream,
+                            float* const attn_core[DPMN_MAX_BLOCKS], float* const block_out[DPMN_MAX_BLOCKS]) {
+  return pgrm_forward_impl(d, x_q, x_kv, out, workspace, workspace_bytes, stream, attn_core, block_out);
+}
+
+size_t dpmn_window_attn_workspace_bytes(int32_t, int32_t, int32_t, int32_t) { return 256; }
+
+int dpmn_window_attn_forward(const void* q, const void* kv, void* out, const float* const rpb_table[DPMN_MAX_GROUPS],
+                             int32_t batch, int32_t grid_h, int32_t grid_w, int32_t embed_dim, int32_t num_heads,
+                             int32_t n_groups, const int32_t window[DPMN_MAX_GROUPS],
+                             const int32_t shift[DPMN_MAX_GROUPS], int32_t precision, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (!q || !kv || !out || !rpb_table || !window || !shift) return DPMN_E_ARG;
+  if (n_groups < 1 || n_groups > DPMN_MAX_GROUPS || batch < 1) return DPMN_E_ARG;
+  if (embed_dim % n_groups || num_heads % n_groups) return DPMN_E_ARG;
+  if (precision < DPMN_PREC_F32 || precision > DPMN_PREC_BF16) return DPMN_E_ARG;
+  AttnArgs a;
+  a.q = q; a.kv = kv; a.out = out; a.io_type = (DType)precision;
+  a.q_ld = embed_dim; a.kv_ld = 2 * embed_dim; a.v_off = embed_dim; a.out_ld = embed_dim;
+  a.B = batch; a.H = grid_h; a.W = grid_w; a.C = embed_dim; a.n_groups = n_groups;
+  a.heads_per_group = num_heads / n_groups;
+  for (int g = 0; g < n_groups; ++g) {
+    if (!rpb_table[g]) return DPMN_E_ARG;
+    if (shift[g] < 0 || shift[g] >= window[g]) return DPMN_E_ARG;
+    a.table[g] = rpb_table[g];
+    a.window[g] = window[g];
+    a.shift[g] = shift[g];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  DPMN_RUN(T_WINDOW_ATTN, launch_window_attn_simt(a, st), n_groups);
+  return 0;
+}
+
+size_t dpmn_gemm_nt_workspace_bytes(int32_t, int32_t, int32_t, int32_t) { return 256; }
+
+int dpmn_gemm_nt(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                 int32_t precision, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (!A || !B || !C || M < 1 || N < 1 || K < 1) return DPMN_E_ARG;
+  if (precision != DPMN_PREC_F32) return DPMN_E_UNSUPPORTED;
+  GemmSimtArgs g;
+  g.A = A; g.lda = K; g.Bm = B; g.ldb = K; g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K;
+  g.bias = bias; g.bias_mode = bias ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+  return 0;
+}
+
+static int check_cmm(const dpmn_cmm_desc* d) {
+  if (!d) return DPMN_E_ARG;
+  if (d->batch < 1 || d->c_img < 1 || d->cnum < 1) return DPMN_E_ARG;
+  if (d->img_h % 32 || d->img_w % 32 || d->img_h < 32 || d->img_w < 32) return DPMN_E_UNSUPPORTED;
+  if (d->precision != DPMN_PREC_F32) return DPMN_E_UNSUPPORTED;
+  return 0;
+}
+
+size_t dpmn_cmm_workspace_bytes(const dpmn_cmm_desc* d) {
+  if (check_cmm(d)) return 0;
+  return carve_cmm(d, nullptr).bytes;
+}
+
+int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, float* out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  int rc = check_cmm(d);
+  if (rc) return rc;
+  if (!x1 || !x2 || !out || !workspace) return DPMN_E_ARG;
+  const CmmWs w = carve_cmm(d, workspace);
+  if (workspace_bytes < w.bytes) return DPMN_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = d->batch, c = d->cnum, H = d->img_h, W = d->img_w;
+  const int ch_o[6] = {c, 2 * c, 4 * c, 8 * c, 8 * c, 8 * c};
+  const float* xin[2] = {x1, x2};
+
+  // ---- encoders (cmm.py:121-133)
+  for (int br = 0; br < 2; ++br) {
+    {
+      ConvArgs a;   // en_1: conv3x3 c_img -> cnum, no activation before, no BN after
+      a.n_seg = 1; a.in[0] = xin[br]; a.seg_ch[0] = d->c_img;
+      const long long bs = br == 0 ? d->x1_batch_stride : d->x2_batch_stride;
+      if (bs != 0 && bs != (long long)d->c_img * H * W) return DPMN_E_UNSUPPORTED;
+      a.w = d->en1_w[br]; a.bias = d->en1_b[br]; a.out = w.o[br][0];
+      a.B = B; a.Cin = d->c_img; a.H = H; a.W = W; a.Cout = c; a.Ho = H; a.Wo = W; a.k = 3; a.stride = 1; a.pad = 1;
+      DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+    }
+    for (int l = 0; l < 4; ++l) {
+      const dpmn_cmm_stage& s = d->enc[br][l];
+      const int hi = H >> l, wi = W >> l, ho = hi / 2, wo = wi / 2;
+      {
+        ConvArgs a;   // LeakyReLU(0.2) -> conv4x4 stride 2 dilation 2 pad 3 (cmm.py:41-44)
+        a.n_seg = 1; a.in[0] = w.o[br][l]; a.seg_ch[0] = ch_o[l];
+        a.in_scale[0] = w.o_sc[br][l]; a.in_shift[0] = w.o_sh[br][l]; a.in_act = 1;
+        a.w = s.conv_a_w; a.bias = s.conv_a_b; a.out = w.mid[br][l];
+        a.B = B; a.Cin = ch_o[l]; a.H = hi; a.W = wi; a.Cout = ch_o[l]; a.Ho = ho; a.Wo = wo;
+        a.k = 4; a.stride = 2; a.pad = 3; a.dil = 2;
+        DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+      }
+      DPMN_RUN(T_BN, bn_affine(d, s.bn_a, w.mid[br][l], ch_o[l], ho * wo, w.mid_sc[br][l], w.mid_sh[br][l], st), 1);
+      {
+        ConvArgs a;   // LeakyReLU -> conv3x3 (cmm.py:46-49)
+        a.n_seg = 1; a.in[0] = w.mid[br][l]; a.seg_ch[0] = ch_o[l];
+        a.in_scale[0] = w.mid_sc[br][l]; a.in_shift[0] = w.mid_sh[br][l]; a.in_act = 1;
+        a.w = s.conv_b_w; a.bias = s.conv_b_b; a.out = w.o[br][l + 1];
+        a.B = B; a.Cin = ch_o[l]; a.H = ho; a.W = wo; a.Cout = ch_o[l + 1]; a.Ho = ho; a.Wo = wo;
+        a.k = 3; a.stride = 1; a.pad = 1;
+        DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+      }
+      DPMN_RUN(T_BN, bn_affine(d, s.bn_b, w.o[br][l + 1], ch_o[l + 1], ho * wo, w.o_sc[br][l + 1], w.o_sh[br][l + 1], st), 1);
+    }
+    {
+      ConvArgs a;   // en_6: LeakyReLU -> conv4x4 stride 2 pad 1 (cmm.py:91-93)
+      const int hi = H >> 4, wi = W >> 4;
+      a.n_seg = 1; a.in[0] = w.o[br][4]; a.seg_ch[0] = ch_o[4];
+      a.in_scale[0] = w.o_sc[br][4]; a.in_shift[0] = w.o_sh[br][4]; a.in_act = 1;
+      a.w = d->en6_w[br]; a.bias = d->en6_b[br]; a.out = w.o[br][5];
+      a.B = B; a.Cin = ch_o[4]; a.H = hi; a.W = wi; a.Cout = ch_o[5]; a.Ho = hi / 2; a.Wo = wi / 2;
+      a.k = 4; a.stride = 2; a.pad = 1;
+      DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+    }
+  }
+  // ---- SE gate (cmm.py:135-147)
+  const int hb = H >> 5, wb = W >> 5;
+  DPMN_RUN(T_SE_GATE, launch_se_gate(w.o[0][5], w.o[1][5], w.z, d->fc1_w, d->fc1_b, d->fc2_w, d->fc2_b, B, 8 * c, hb * wb,
+                          4 * c, st), 1);
+  // ---- decoder (cmm.py:149-159)
+  {
+    ConvArgs a;   // de_6: ReLU -> convT4x4 stride 2 pad 1 -> BN
+    a.n_seg = 1; a.in[0] = w.z; a.seg_ch[0] = 16 * c; a.in_act = 2;
+    a.w = d->de6_w; a.bias = d->de6_b; a.out = w.d6;
+    a.B = B; a.Cin = 16 * c; a.H = hb; a.W = wb; a.Cout = 8 * c; a.Ho = 2 * hb; a.Wo = 2 * wb;
+    a.k = 4; a.stride = 2; a.pad = 1; a.transposed = 1;
+    DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+    DPMN_RUN(T_BN, bn_affine(d, d->de6_bn, w.d6, 8 * c, 4 * hb * wb, w.d6_sc, w.d6_sh, st), 1);
+  }
+  const float* dprev = w.d6;
+  const float *dprev_sc = w.d6_sc, *dprev_sh = w.d6_sh;
+  int dprev_ch = 8 * c;
+  const int ch_d[4] = {8 * c, 4 * c, 2 * c, c};
+  for (int i = 0; i < 4; ++i) {
+    const dpmn_cmm_stage& s = d->dec[i];
+    const int lvl = 4 - i;                 // skip connection index into o[][]: o5, o4, o3, o2
+    const int hi = H >> lvl, wi = W >> lvl;
+    {
+      ConvArgs a;   // ReLU -> convT3x3 on cat[dec, enc1 skip, enc2 skip] (cmm.py:61-64,150-157)
+      a.n_seg = 3;
+      a.in[0] = dprev; a.seg_ch[0] = dprev_ch; a.in_scale[0] = dprev_sc; a.in_shift[0] = dprev_sh;
+      for (int br = 0; br < 2; ++br) {
+        a.in[1 + br] = w.o[br][lvl]; a.seg_ch[1 + br] = ch_o[lvl];
+        a.in_scale[1 + br] = w.o_sc[br][lvl]; a.in_shift[1 + br] = w.o_sh[br][lvl];
+      }
+      a.in_act = 2;
+      a.w = s.conv_a_w; a.bias = s.conv_a_b; a.out = w.dmid[i];
+      a.B = B; a.Cin = dprev_ch + 2 * ch_o[lvl]; a.H = hi; a.W = wi; a.Cout = ch_d[i]; a.Ho = hi; a.Wo = wi;
+      a.k = 3; a.stride = 1; a.pad = 1; a.transposed = 1;
+      DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+    }
+    DPMN_RUN(T_BN, bn_affine(d, s.bn_a, w.dmid[i], ch_d[i], hi * wi, w.dmid_sc[i], w.dmid_sh[i], st), 1);
+    {
+      ConvArgs a;   // ReLU -> convT4x4 stride 2 pad 1 (cmm.py:66-69)
+      a.n_seg = 1; a.in[0] = w.dmid[i]; a.seg_ch[0] = ch_d[i];
+      a.in_scale[0] = w.dmid_sc[i]; a.in_shift[0] = w.dmid_sh[i]; a.in_act = 2;
+      a.w = s.conv_b_w; a.bias = s.conv_b_b; a.out = w.dout[i];
+      a.B = B; a.Cin = ch_d[i]; a.H = hi; a.W = wi; a.Cout = ch_d[i]; a.Ho = 2 * hi; a.Wo = 2 * wi;
+      a.k = 4; a.stride = 2; a.pad = 1; a.transposed = 1;
+      DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+    }
+    DPMN_RUN(T_BN, bn_affine(d, s.bn_b, w.dout[i], ch_d[i], 4 * hi * wi, w.dout_sc[i], w.dout_sh[i], st), 1);
+    dprev = w.dout[i]; dprev_sc = w.dout_sc[i]; dprev_sh = w.dout_sh[i]; dprev_ch = ch_d[i];
+  }
+  {
+    ConvArgs a;   // de_1: ReLU -> convT3x3 3*cnum -> c_img (cmm.py:113-116,158-159)
+    a.n_seg = 3;
+    a.in[0] = dprev; a.seg_ch[0] = c; a.in_scale[0] = dprev_sc; a.in_shift[0] = dprev_sh;
+    a.in[1] = w.o[0][0]; a.seg_ch[1] = c;
+    a.in[2] = w.o[1][0]; a.seg_ch[2] = c;
+    a.in_act = 2;
+    a.w = d->de1_w; a.bias = d->de1_b; a.out = out;
+    a.B = B; a.Cin = 3 * c; a.H = H; a.W = W; a.Cout = d->c_img; a.Ho = H; a.Wo = W;
+    a.k = 3; a.stride = 1; a.pad = 1; a.transposed = 1;
+    DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+  }
+  return 0;
+}
+
+}  // extern "C"

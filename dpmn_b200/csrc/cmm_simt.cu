@@ -1,0 +1,268 @@
+// SIMT fp32 kernels of the Complementation Modulation Module (exact-arithmetic mode).
+// Behaviour restated from /root/reference/model/cmm.py:10-161 (never copied).
+//
+// Every conv / transposed conv of the U-Net is one implicit GEMM:
+//     out[co, n] = bias[co] + sum_k  Wmat[co, k] * gather(k, n)        M = Cout, N = B*Ho*Wo, K = Cin*k*k
+// where gather() reads the channel-concatenated input, applies the producer's BatchNorm as a per-channel
+// affine and then the consumer's leading activation -- so BN and activations never cost a pass of their own.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dpmn {
+
+constexpr int CM = 64, CN = 64, CK = 16, CPAD = 68;
+
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs p) {
+  __shared__ __align__(16) float As[CK][CPAD];   // weights  [k][co]
+  __shared__ __align__(16) float Bs[CK][CPAD];   // gathered input [k][pixel]
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * CM, n0 = blockIdx.x * CN;
+  const int kk = p.k * p.k;
+  const int K = p.Cin * kk;
+  const int HoWo = p.Ho * p.Wo;
+  const long long Ntot = (long long)p.B * HoWo;
+  const long long HW = (long long)p.H * p.W;
+
+  // B loader: this thread always gathers for pixel (n0 + tid%64), k rows (tid/64) + 4*i
+  const int bn = tid & 63, bk0 = tid >> 6;
+  const long long npix = (long long)n0 + bn;
+  const bool n_ok = npix < Ntot;
+  int pb = 0, oy = 0, ox = 0;
+  if (n_ok) {
+    pb = (int)(npix / HoWo);
+    const int r = (int)(npix - (long long)pb * HoWo);
+    oy = r / p.Wo;
+    ox = r - oy * p.Wo;
+  }
+  // A loader: weight row (tid/16) + 16*i, k column tid%16
+  const int ak = tid & 15, am0 = tid >> 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += CK) {
+    float av[4], bv[4];
+    {
+      const int k = k0 + ak;
+      int ci = 0, tap = 0;
+      if (TRANSPOSED) { ci = k / kk; tap = k - ci * kk; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int co = m0 + am0 + 16 * i;
+        float v = 0.f;
+        if (k < K && co < p.Cout)
+          v = TRANSPOSED ? p.w[((long long)ci * p.Cout + co) * kk + tap] : p.w[(long long)co * K + k];
+        av[i] = v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + bk0 + 4 * i;
+      float v = 0.f;
+      if (n_ok && k < K) {
+        const int ci = k / kk;
+        const int tap = k - ci * kk;
+        const int ky = tap / p.k, kx = tap - ky * p.k;
+        int iy, ix;
+        bool ok;
+        if (TRANSPOSED) {
+          // out[oy] += in[iy] * w[ky]  with  oy = iy*stride - pad + ky
+          const int ty2 = oy + p.pad - ky, tx2 = ox + p.pad - kx;
+          ok = ty2 >= 0 && tx2 >= 0 && (ty2 % p.stride) == 0 && (tx2 % p.stride) == 0;
+          iy = ty2 / p.stride;
+          ix = tx2 / p.stride;
+          ok = ok && iy < p.H && ix < p.W;
+        } else {
+          iy = oy * p.stride - p.pad + ky * p.dil;
+          ix = ox * p.stride - p.pad + kx * p.dil;
+          ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        }
+        if (ok) {
+          int seg = 0, cl = ci;
+          if (p.n_seg > 1 && cl >= p.seg_ch[0]) {
+            cl -= p.seg_ch[0]; seg = 1;
+            if (p.n_seg > 2 && cl >= p.seg_ch[1]) { cl -= p.seg_ch[1]; seg = 2; }
+          }
+          v = p.in[seg][((long long)pb * p.seg_ch[seg] + cl) * HW + (long long)iy * p.W + ix];
+          if (p.in_scale[seg] != nullptr) v = fmaf(v, p.in_scale[seg][cl], p.in_shift[seg][cl]);
+          if (p.in_act == 1) v = v >= 0.f ? v : 0.2f * v;
+          else if (p.in_act == 2) v = fmaxf(v, 0.f);
+        }
+      }
+      bv[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[ak][am0 + 16 * i] = av[i];
+      Bs[bk0 + 4 * i][bn] = bv[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float br[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = m0 + ty * 4 + i;
+    if (co >= p.Cout) continue;
+    const float bb = p.bias ? p.bias[co] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long n = (long long)n0 + tx * 4 + j;
+      if (n >= Ntot) continue;
+      const int b = (int)(n / HoWo);
+      const int r = (int)(n - (long long)b * HoWo);
+      p.out[((long long)b * p.Cout + co) * HoWo + r] = acc[i][j] + bb;
+    }
+  }
+}
+
+int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
+  if (a.n_seg < 1 || a.n_seg > 3) return -1;
+  int cin = 0;
+  for (int i = 0; i < a.n_seg; ++i) cin += a.seg_ch[i];
+  if (cin != a.Cin) return -1;
+  const long long Ntot = (long long)a.B * a.Ho * a.Wo;
+  dim3 grid((unsigned)((Ntot + CN - 1) / CN), (a.Cout + CM - 1) / CM, 1);
+  if (a.transposed) conv_simt_kernel<true><<<grid, 256, 0, st>>>(a);
+  else conv_simt_kernel<false><<<grid, 256, 0, st>>>(a);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// -----------------------------------------------------------------------------------------------------
+// BatchNorm2d -> per-channel (scale, shift).  One CTA per channel; two-pass (mean, then centred second
+// moment) so the batch variance has no cancellation.                                       cmm.py:12
+// -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += red[i];
+  return s;
+}
+
+__global__ void __launch_bounds__(256) bn_affine_kernel(const float* __restrict__ x, int B, int C, int HW,
+                                                        const float* __restrict__ w, const float* __restrict__ b,
+                                                        float* run_mean, float* run_var, int training,
+                                                        int update_running, float eps, float* __restrict__ scale,
+                                                        float* __restrict__ shift) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  float mean, var;
+  if (training) {
+    const long long n = (long long)B * HW;
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < n; i += 256) {
+      const int bb = (int)(i / HW);
+      const int r = (int)(i - (long long)bb * HW);
+      s += x[((long long)bb * C + c) * HW + r];
+    }
+    mean = block_sum_256(s, red) / (float)n;
+    float q = 0.f;
+    for (long long i = threadIdx.x; i < n; i += 256) {
+      const int bb = (int)(i / HW);
+      const int r = (int)(i - (long long)bb * HW);
+      const float d = x[((long long)bb * C + c) * HW + r] - mean;
+      q = fmaf(d, d, q);
+    }
+    const float ss = block_sum_256(q, red);
+    var = ss / (float)n;
+    if (update_running && run_mean != nullptr && threadIdx.x == 0) {
+      const float unbiased = n > 1 ? ss / (float)(n - 1) : var;
+      run_mean[c] = 0.9f * run_mean[c] + 0.1f * mean;
+      run_var[c] = 0.9f * run_var[c] + 0.1f * unbiased;
+    }
+  } else {
+    mean = run_mean[c];
+    var = run_var[c];
+  }
+  if (threadIdx.x == 0) {
+    const float sc = w[c] / sqrtf(var + eps);
+    scale[c] = sc;
+    shift[c] = b[c] - mean * sc;
+  }
+}
+
+int launch_bn_affine(const float* x, int B, int C, int HW, const float* w, const float* b, float* run_mean,
+                     float* run_var, int training, int update_running, float eps, float* scale, float* shift,
+                     cudaStream_t st) {
+  bn_affine_kernel<<<C, 256, 0, st>>>(x, B, C, HW, w, b, run_mean, run_var, training, update_running, eps, scale,
+                                      shift);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// -----------------------------------------------------------------------------------------------------
+// SE gate on the bottleneck                                                           cmm.py:135-147
+// z = cat(z1, z2) (2*Cb channels);  g = sigmoid(fc2(relu(fc1(mean_hw z))));  out = z * g + z
+// One CTA per image.
+// -----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ z1, const float* __restrict__ z2,
+                                                      float* __restrict__ z, const float* __restrict__ fc1_w,
+                                                      const float* __restrict__ fc1_b,
+                                                      const float* __restrict__ fc2_w,
+                                                      const float* __restrict__ fc2_b, int Cb, int hw, int hidden) {
+  extern __shared__ float sm[];
+  const int C2 = 2 * Cb;
+  float* sg = sm;            // [C2] pooled
+  float* sh = sg + C2;       // [hidden]
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C2; c += blockDim.x) {
+    const float* src = c < Cb ? z1 + ((long long)b * Cb + c) * hw : z2 + ((long long)b * Cb + (c - Cb)) * hw;
+    float s = 0.f;
+    for (int i = 0; i < hw; ++i) s += src[i];
+    sg[c] = s / (float)hw;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = warp; j < hidden; j += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C2; c += 32) s = fmaf(fc1_w[(long long)j * C2 + c], sg[c], s);
+    s = warp_sum(s);
+    if (lane == 0) sh[j] = fmaxf(s + fc1_b[j], 0.f);
+  }
+  __syncthreads();
+  for (int c = warp; c < C2; c += nw) {
+    float s = 0.f;
+    for (int j = lane; j < hidden; j += 32) s = fmaf(fc2_w[(long long)c * hidden + j], sh[j], s);
+    s = warp_sum(s);
+    const float g = 1.0f / (1.0f + expf(-(s + fc2_b[c])));
+    const float* src = c < Cb ? z1 + ((long long)b * Cb + c) * hw : z2 + ((long long)b * Cb + (c - Cb)) * hw;
+    for (int i = lane; i < hw; i += 32) {
+      const float v = src[i];
+      z[((long long)b * C2 + c) * hw + i] = fmaf(v, g, v);
+    }
+  }
+}
+
+int launch_se_gate(const float* z1, const float* z2, float* z, const float* fc1_w, const float* fc1_b,
+                   const float* fc2_w, const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * Cb + hidden) * sizeof(float);
+  if (smem > 48 * 1024) return -2;
+  se_gate_kernel<<<B, 256, smem, st>>>(z1, z2, z, fc1_w, fc1_b, fc2_w, fc2_b, Cb, hw, hidden);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dpmn

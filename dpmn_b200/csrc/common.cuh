@@ -1,0 +1,93 @@
+// Shared device helpers for the dpmn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define DPMN_CUDA_TRY(expr)                                   \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return (int)_e;                    \
+  } while (0)
+
+#define DPMN_LAUNCH_CHECK()                                   \
+  do {                                                        \
+    cudaError_t _e = cudaGetLastError();                      \
+    if (_e != cudaSuccess) return (int)_e;                    \
+  } while (0)
+
+namespace dpmn {
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  // nn.GELU() default (exact erf form), pgrm.py:17
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Window-major row p of group (ws, shift) -> original token index (pgrm.py:209-221 roll + partition).
+// p = w*N + n, w = wr*(W/ws) + wc, n = i*ws + j; rolled coords (h', w') = (wr*ws+i, wc*ws+j) read
+// original ((h'+shift) % H, (w'+shift) % W).
+struct WinCoord {
+  int hp, wp;   // rolled coordinates
+  int token;    // original token index
+  int win;      // window index within the image
+  int n;        // index within the window
+};
+
+__device__ __forceinline__ WinCoord window_row_to_token(int p, int H, int W, int ws, int shift) {
+  WinCoord c;
+  const int N = ws * ws;
+  const int nWw = W / ws;
+  c.win = p / N;
+  c.n = p - c.win * N;
+  const int wr = c.win / nWw, wc = c.win - wr * nWw;
+  const int i = c.n / ws, j = c.n - i * ws;
+  c.hp = wr * ws + i;
+  c.wp = wc * ws + j;
+  int ho = c.hp + shift; if (ho >= H) ho -= H;
+  int wo = c.wp + shift; if (wo >= W) wo -= W;
+  c.token = ho * W + wo;
+  return c;
+}
+
+// Inverse: original token -> window-major row of group (ws, shift).
+__device__ __forceinline__ int token_to_window_row(int token, int H, int W, int ws, int shift) {
+  int ho = token / W, wo = token - ho * W;
+  int hp = ho - shift; if (hp < 0) hp += H;
+  int wp = wo - shift; if (wp < 0) wp += W;
+  const int nWw = W / ws;
+  const int win = (hp / ws) * nWw + (wp / ws);
+  const int n = (hp % ws) * ws + (wp % ws);
+  return win * ws * ws + n;
+}
+
+// 3x3 slice label of the shift mask (pgrm.py:157-168) for rolled coordinate (hp, wp).
+__device__ __forceinline__ int shift_region_label(int hp, int wp, int H, int W, int ws, int shift) {
+  const int rh = (hp >= H - ws) + (hp >= H - shift);
+  const int rw = (wp >= W - ws) + (wp >= W - shift);
+  return 3 * rh + rw;
+}
+
+}  // namespace dpmn

@@ -1,0 +1,109 @@
+// Internal launcher interface between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dpmn {
+
+enum DType : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
+inline size_t dtype_size(DType t) { return t == DT_F32 ? 4 : 2; }
+
+// ---- SIMT kernels (pgrm_simt.cu) ------------------------------------------------------------------
+
+// prior_fusion (optional, in_ch == 2) + PatchEmbed conv(k=s=patch) + LayerNorm -> tokens (B, L, C) fp32.
+// x is NCHW with an arbitrary batch stride (elements); channel/row strides are dense.
+int launch_patch_embed(const float* x, long long x_bs, int in_ch, const float* fuse_w, const float* fuse_b,
+                       const float* pe_w, const float* pe_b, const float* ln_w, const float* ln_b, float* tokens,
+                       int B, int img_h, int img_w, int patch, int C, cudaStream_t st);
+
+// LayerNorm over the last dim of (rows, C) fp32 -> out (rows, C) of `out_type`.
+int launch_layernorm(const float* x, const float* w, const float* b, void* out, DType out_type, int rows, int C,
+                     cudaStream_t st);
+
+// C[z][m, n] = epi( sum_k A[z][m, k] * B[z][n, k] ), everything fp32 (the exact-arithmetic mode).
+struct GemmSimtArgs {
+  const float* A = nullptr; long long a_bs = 0; int lda = 0;
+  const float* Bm = nullptr; long long b_bs = 0; int ldb = 0;
+  float* C = nullptr; long long c_bs = 0; int ldc = 0;
+  int M = 0, N = 0, K = 0, batch = 1;
+  const float* bias = nullptr; long long bias_bs = 0; int bias_mode = 0;   // 0 none, 1 per n, 2 per m
+  int act = 0;                               // 0 none, 1 GELU(erf)
+  const float* residual = nullptr;           // fp32, same indexing as C (may alias C)
+  float* colsum = nullptr;                   // if set: no C store; colsum[z][m_tile][n] = sum_rows act(value)
+};
+int launch_gemm_simt(const GemmSimtArgs& a, cudaStream_t st);
+static constexpr int kSimtTileM = 64;
+
+// Windowed attention core, SIMT (any precision of q/kv/out storage).  q (B,L,*) and kv (B,L,*) in token
+// order with row strides q_ld / kv_ld (elements); K channels start at column 0 of a kv row, V channels
+// at column v_off.  out (B,L,C) window-major rows per group (quirk 1, pgrm.py:249,263).
+struct AttnArgs {
+  const void* q = nullptr; const void* kv = nullptr; void* out = nullptr; DType io_type = DT_F32;
+  int q_ld = 0, kv_ld = 0, v_off = 0, out_ld = 0;
+  const float* table[4] = {nullptr, nullptr, nullptr, nullptr};   // ((2*win-1)^2, heads_per_group) each
+  int B = 0, H = 0, W = 0, C = 0, n_groups = 0, heads_per_group = 0;
+  int window[4] = {0, 0, 0, 0}, shift[4] = {0, 0, 0, 0};   // EFFECTIVE windows / shifts
+};
+int launch_window_attn_simt(const AttnArgs& a, cudaStream_t st);
+
+// SK gate (pgrm.py:84-95 folded): from per-tile column sums of GELU(proj(x)) build, per image,
+// Wb = Wp + Wh * diag(softmax_G(fc2(GELU(fc1(mean))))) (C x C) and bias_b = bp + bh.
+int launch_sk_gate(const float* colsum, int tiles_per_image, int L, const float* wp, const float* bp,
+                   const float* w1, const float* b1, const float* w2, const float* b2, const float* wh,
+                   const float* bh, void* wb_out, DType wb_type, float* bias_out, int B, int C, int G,
+                   cudaStream_t st);
+
+// Depthwise 3x3 on the raw (B, hid, side, side) view of h (B, L, hid) + bias + GELU, written transposed
+// as dt (B, L(pixel), hid(channel)).
+int launch_dwconv(const void* h, void* dt, DType io_type, const float* w, const float* b, int B, int L, int hid,
+                  cudaStream_t st);
+
+// PatchUnEmbed + conv3x3 (C -> hp) on token-major x (B, gh, gw, C) -> t1 (B, gh, gw, hp) fp32.
+int launch_head_conv1(const float* x, const float* w, const float* b, float* t1, int B, int gh, int gw, int C,
+                      int hp, cudaStream_t st);
+// conv3x3 (hp -> hp) + LeakyReLU(0.01) + PixelShuffle(patch) + affine mix -> out (B, hs, img_h, img_w).
+struct MixArgs {
+  int n_mix = 1;
+  const float* w[8] = {};
+  const float* in[8] = {};
+  long long in_bs[8] = {};   // batch strides (elements) of the residual inputs
+};
+int launch_head_conv2_mix(const float* t1, const float* w, const float* b, float* out, int B, int gh, int gw,
+                          int hs, int patch, const MixArgs& mix, cudaStream_t st);
+
+// fp32 -> 16-bit conversion of n elements (weights staging for the tensor-core path).
+int launch_convert(const float* src, void* dst, DType dst_type, long long n, cudaStream_t st);
+
+// ---- CMM SIMT kernels (cmm_simt.cu) ------------------------------------------------------------------
+
+// Implicit-GEMM convolution / transposed convolution on NCHW fp32.  The input is the channel-wise
+// concatenation of up to 3 tensors; each may carry a per-channel affine (its producer's BatchNorm,
+// cmm.py:12) that is applied on load, followed by the consumer's leading activation (cmm.py:41,61).
+struct ConvArgs {
+  int n_seg = 1;
+  const float* in[3] = {};         // (B, seg_ch[i], H, W)
+  int seg_ch[3] = {};
+  const float* in_scale[3] = {};   // per channel of the segment, or nullptr (identity)
+  const float* in_shift[3] = {};
+  int in_act = 0;                  // 0 none, 1 LeakyReLU(0.2), 2 ReLU
+  const float* w = nullptr;        // conv: (Cout, Cin, k, k); transposed: (Cin, Cout, k, k)
+  const float* bias = nullptr;     // (Cout)
+  float* out = nullptr;            // (B, Cout, Ho, Wo)
+  int B = 0, Cin = 0, H = 0, W = 0, Cout = 0, Ho = 0, Wo = 0;
+  int k = 3, stride = 1, pad = 1, dil = 1;
+  int transposed = 0;
+};
+int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
+
+// BatchNorm2d as a per-channel affine (scale, shift) of a raw conv output x (B, C, HW):
+// training: biased batch statistics of x (and, if run_mean != nullptr, the momentum-0.1 running update
+// with the unbiased variance, as nn.BatchNorm2d does); eval: running statistics.
+int launch_bn_affine(const float* x, int B, int C, int HW, const float* w, const float* b, float* run_mean,
+                     float* run_var, int training, int update_running, float eps, float* scale, float* shift,
+                     cudaStream_t st);
+
+// SE gate on the concatenated bottleneck (cmm.py:135-147): z (B, 2*Cb, hw) from two (B, Cb, hw) halves.
+int launch_se_gate(const float* z1, const float* z2, float* z, const float* fc1_w, const float* fc1_b,
+                   const float* fc2_w, const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st);
+
+}  // namespace dpmn

@@ -1,0 +1,780 @@
+// SIMT (CUDA-core, fp32-arithmetic) kernels of the PGRM hot path.  These are the exact-arithmetic mode
+// (DPMN_PREC_F32: 1e-5 parity with the reference) and the non-GEMM stages of the tensor-core modes.
+//
+// Reference behaviour restated (never copied) from /root/reference/model/pgrm.py; line numbers per kernel.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dpmn {
+
+// =====================================================================================================
+// K0  prior_fusion (optional) + PatchEmbed conv(k = s = patch) + LayerNorm        pgrm.py:419-426,547-550
+// one warp per token; lane j < in3*p*p holds one (channel, dy, dx) input of the patch conv, every lane
+// owns C/32 output channels.
+// =====================================================================================================
+template <int CPL>   // channels per lane = C / 32
+__global__ void __launch_bounds__(256) patch_embed_kernel(
+    const float* __restrict__ x, long long x_bs, int in_ch, const float* __restrict__ fuse_w,
+    const float* __restrict__ fuse_b, const float* __restrict__ pe_w, const float* __restrict__ pe_b,
+    const float* __restrict__ ln_w, const float* __restrict__ ln_b, float* __restrict__ tokens, int B, int img_h,
+    int img_w, int patch, int n_tokens_total) {
+  constexpr int C = CPL * 32;
+  extern __shared__ float smem[];
+  const int pk = 3 * patch * patch;              // inputs of the patch conv per token (<= 32)
+  float* s_w = smem;                             // [pk][C]  transposed patch-embed weight
+  float* s_fw = s_w + pk * C;                    // [3*2*9]  prior_fusion weight
+  for (int i = threadIdx.x; i < pk * C; i += blockDim.x) {
+    const int k = i / C, c = i - k * C;
+    s_w[i] = pe_w[c * pk + k];
+  }
+  if (fuse_w != nullptr)
+    for (int i = threadIdx.x; i < 54; i += blockDim.x) s_fw[i] = fuse_w[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int gw = img_w / patch, gh = img_h / patch;
+  const int L = gh * gw;
+  const long long plane = (long long)img_h * img_w;
+
+  float bias_r[CPL], lw_r[CPL], lb_r[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    bias_r[i] = pe_b[lane + 32 * i];
+    lw_r[i] = ln_w[lane + 32 * i];
+    lb_r[i] = ln_b[lane + 32 * i];
+  }
+
+  for (int tok = warp; tok < n_tokens_total; tok += n_warps) {
+    const int b = tok / L, t = tok - b * L;
+    const int ty = t / gw, tx = t - ty * gw;
+    // lane j -> (ch, dy, dx) of the conv input
+    float v = 0.f;
+    if (lane < pk) {
+      const int ch = lane / (patch * patch);
+      const int r = lane - ch * patch * patch;
+      const int dy = r / patch, dx = r - dy * patch;
+      const int y = ty * patch + dy, xx = tx * patch + dx;
+      const float* xb = x + (long long)b * x_bs;
+      if (fuse_w == nullptr) {
+        v = xb[ch * plane + (long long)y * img_w + xx];
+      } else {
+        // prior_fusion: conv3x3 pad 1, in_ch (2) -> 3, at full resolution (pgrm.py:471,547-548)
+        float acc = fuse_b[ch];
+        for (int ci = 0; ci < in_ch; ++ci)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int yy = y + ky - 1;
+            if (yy < 0 || yy >= img_h) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int xc = xx + kx - 1;
+              if (xc < 0 || xc >= img_w) continue;
+              acc = fmaf(xb[ci * plane + (long long)yy * img_w + xc], s_fw[(ch * in_ch + ci) * 9 + ky * 3 + kx], acc);
+            }
+          }
+        v = acc;
+      }
+    }
+    float o[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) o[i] = bias_r[i];
+    for (int k = 0; k < pk; ++k) {
+      const float xv = __shfl_sync(0xffffffffu, v, k);
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) o[i] = fmaf(xv, s_w[k * C + lane + 32 * i], o[i]);
+    }
+    // LayerNorm over C (biased variance, eps 1e-5)
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) s += o[i];
+    const float mu = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) { const float d = o[i] - mu; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+    float* dst = tokens + (long long)tok * C;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) dst[lane + 32 * i] = (o[i] - mu) * rstd * lw_r[i] + lb_r[i];
+  }
+}
+
+int launch_patch_embed(const float* x, long long x_bs, int in_ch, const float* fuse_w, const float* fuse_b,
+                       const float* pe_w, const float* pe_b, const float* ln_w, const float* ln_b, float* tokens,
+                       int B, int img_h, int img_w, int patch, int C, cudaStream_t st) {
+  if (C % 32 != 0 || C > 256 || 3 * patch * patch > 32) return -2;
+  const int L = (img_h / patch) * (img_w / patch);
+  const int total = B * L;
+  const int threads = 256;
+  int blocks = (total + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const size_t smem = (size_t)(3 * patch * patch * C + 64) * sizeof(float);
+#define DPMN_PE(CPL_)                                                                                         \
+  patch_embed_kernel<CPL_><<<blocks, threads, smem, st>>>(x, x_bs, in_ch, fuse_w, fuse_b, pe_w, pe_b, ln_w,  \
+                                                          ln_b, tokens, B, img_h, img_w, patch, total)
+  switch (C / 32) {
+    case 1: DPMN_PE(1); break;
+    case 2: DPMN_PE(2); break;
+    case 3: DPMN_PE(3); break;
+    case 4: DPMN_PE(4); break;
+    case 6: DPMN_PE(6); break;
+    case 8: DPMN_PE(8); break;
+    default: return -2;
+  }
+#undef DPMN_PE
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// LayerNorm over rows of (rows, C) fp32; one warp per row.                      pgrm.py:303-304,311,322-323
+// =====================================================================================================
+template <typename OutT, int CPL>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, OutT* __restrict__ out,
+                                                        int rows) {
+  constexpr int C = CPL * 32;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  float wr[CPL], br[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) { wr[i] = w[lane + 32 * i]; br[i] = b[lane + 32 * i]; }
+  for (int r = warp; r < rows; r += n_warps) {
+    const float* src = x + (long long)r * C;
+    float v[CPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) { v[i] = src[lane + 32 * i]; s += v[i]; }
+    const float mu = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) { const float d = v[i] - mu; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+    OutT* dst = out + (long long)r * C;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) dst[lane + 32 * i] = from_f32<OutT>((v[i] - mu) * rstd * wr[i] + br[i]);
+  }
+}
+
+template <typename OutT>
+static int launch_layernorm_t(const float* x, const float* w, const float* b, OutT* out, int rows, int C,
+                              cudaStream_t st) {
+  int blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  switch (C / 32) {
+    case 1: layernorm_kernel<OutT, 1><<<blocks, 256, 0, st>>>(x, w, b, out, rows); break;
+    case 2: layernorm_kernel<OutT, 2><<<blocks, 256, 0, st>>>(x, w, b, out, rows); break;
+    case 3: layernorm_kernel<OutT, 3><<<blocks, 256, 0, st>>>(x, w, b, out, rows); break;
+    case 4: layernorm_kernel<OutT, 4><<<blocks, 256, 0, st>>>(x, w, b, out, rows); break;
+    case 6: layernorm_kernel<OutT, 6><<<blocks, 256, 0, st>>>(x, w, b, out, rows); break;
+    case 8: layernorm_kernel<OutT, 8><<<blocks, 256, 0, st>>>(x, w, b, out, rows); break;
+    default: return -2;
+  }
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_layernorm(const float* x, const float* w, const float* b, void* out, DType out_type, int rows, int C,
+                     cudaStream_t st) {
+  if (C % 32 != 0 || C > 256) return -2;
+  switch (out_type) {
+    case DT_F32: return launch_layernorm_t<float>(x, w, b, (float*)out, rows, C, st);
+    case DT_F16: return launch_layernorm_t<__half>(x, w, b, (__half*)out, rows, C, st);
+    case DT_BF16: return launch_layernorm_t<__nv_bfloat16>(x, w, b, (__nv_bfloat16*)out, rows, C, st);
+  }
+  return -1;
+}
+
+// =====================================================================================================
+// fp32 SIMT GEMM  C[z][m,n] = epi(sum_k A[z][m,k] * B[z][n,k])   (both operands K-contiguous)
+// 64x64 tile, BK 16, 256 threads, 4x4 micro-tile.  Requires K % 4 == 0, lda/ldb % 4 == 0, N % 4 == 0,
+// ldc % 4 == 0 and 16-byte aligned bases.
+// =====================================================================================================
+constexpr int GM = 64, GN = 64, GK = 16, GPAD = 68;
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmSimtArgs p) {
+  __shared__ __align__(16) float As[GK][GPAD];
+  __shared__ __align__(16) float Bs[GK][GPAD];
+  __shared__ float red[16][GN];
+
+  const int z = blockIdx.z;
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  const float* A = p.A + (long long)z * p.a_bs;
+  const float* Bm = p.Bm + (long long)z * p.b_bs;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;   // loader: row within tile, k offset
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const bool a_ok = (m0 + lrow) < p.M, b_ok = (n0 + lrow) < p.N;
+  const float* a_ptr = A + (long long)(m0 + lrow) * p.lda + lk;
+  const float* b_ptr = Bm + (long long)(n0 + lrow) * p.ldb + lk;
+
+  for (int k0 = 0; k0 < p.K; k0 += GK) {
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+    if (a_ok && (k0 + lk) < p.K) av = *reinterpret_cast<const float4*>(a_ptr + k0);
+    if (b_ok && (k0 + lk) < p.K) bv = *reinterpret_cast<const float4*>(b_ptr + k0);
+    __syncthreads();   // previous tile fully consumed
+    As[lk + 0][lrow] = av.x; As[lk + 1][lrow] = av.y; As[lk + 2][lrow] = av.z; As[lk + 3][lrow] = av.w;
+    Bs[lk + 0][lrow] = bv.x; Bs[lk + 1][lrow] = bv.y; Bs[lk + 2][lrow] = bv.z; Bs[lk + 3][lrow] = bv.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float br[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+
+  // epilogue
+  const int n = n0 + tx * 4;
+  const float* bias = p.bias ? p.bias + (long long)z * p.bias_bs : nullptr;
+  float colpart[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M || n >= p.N) continue;
+    float v[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
+    if (p.bias_mode == 1) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias + n);
+      v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+    } else if (p.bias_mode == 2) {
+      const float bb = bias[m];
+      v[0] += bb; v[1] += bb; v[2] += bb; v[3] += bb;
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
+    }
+    if (p.colsum != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) colpart[j] += v[j];
+      continue;
+    }
+    const long long off = (long long)z * p.c_bs + (long long)m * p.ldc + n;
+    if (p.residual != nullptr) {
+      const float4 rr = *reinterpret_cast<const float4*>(p.residual + off);
+      v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+    }
+    *reinterpret_cast<float4*>(p.C + off) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  if (p.colsum != nullptr) {
+    // deterministic in-tile reduction over the 16 row-groups
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[ty][tx * 4 + j] = colpart[j];
+    __syncthreads();
+    if (tid < GN) {
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) s += red[r][tid];
+      const int nn = n0 + tid;
+      if (nn < p.N) p.colsum[((long long)z * gridDim.y + blockIdx.y) * p.N + nn] = s;
+    }
+  }
+}
+
+int launch_gemm_simt(const GemmSimtArgs& a, cudaStream_t st) {
+  if (a.K % 4 || a.lda % 4 || a.ldb % 4 || a.N % 4 || (a.colsum == nullptr && a.ldc % 4)) return -2;
+  dim3 grid((a.N + GN - 1) / GN, (a.M + GM - 1) / GM, a.batch);
+  gemm_simt_kernel<<<grid, 256, 0, st>>>(a);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// K2  windowed multi-head attention core, SIMT                                        pgrm.py:197-268
+// One thread per (window-major row, head).  A CTA covers T = max(128, N) rows = T/N whole windows of
+// one (image, group, head); K and V rows of those windows sit in shared memory (fp32).
+//   S[n,m] = 0.25*<q_n,k_m> + table[idx(n,m), head] + (label_n != label_m ? -100 : 0);  P = softmax_m(S)
+//   out[row p = w*N + n] = sum_m P[n,m] v_m       (window-major rows are kept: quirk 1)
+// =====================================================================================================
+template <typename T, int D>
+__global__ void window_attn_simt_kernel(const T* __restrict__ q, const T* __restrict__ kv, T* __restrict__ out,
+                                        int q_ld, int kv_ld, int v_off, int out_ld,
+                                        const float* __restrict__ table, int hpg, int ch0, int H, int W, int ws,
+                                        int shift, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  const int N = ws * ws;
+  const int L = H * W;
+  const int Tn = blockDim.x;
+  const int units = Tn / N;                  // windows per CTA
+  const int ustride = N * D + 4;             // +4 floats: units of one warp land in different banks
+  float* sK = sm;                            // [units][N][D] (+pad)
+  float* sV = sK + units * ustride;
+  float* sT = sV + units * ustride;          // [(2ws-1)^2] bias column of this head
+  int* sLab = reinterpret_cast<int*>(sT + (2 * ws - 1) * (2 * ws - 1));   // [Tn] shift-mask labels
+
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int row0 = blockIdx.x * Tn;          // first window-major row of this CTA
+  const int t = threadIdx.x;
+  const int p = row0 + t;
+  const int u = t / N, n = t - u * N;
+  const int ch = ch0 + head * D;
+
+  for (int i = t; i < (2 * ws - 1) * (2 * ws - 1); i += Tn) sT[i] = table[i * hpg + head];
+
+  const WinCoord wc = window_row_to_token(p, H, W, ws, shift);
+  sLab[t] = shift > 0 ? shift_region_label(wc.hp, wc.wp, H, W, ws, shift) : 0;
+  const long long tok = (long long)b * L + wc.token;
+  float qr[D];
+  {
+    const T* qp = q + tok * q_ld + ch;
+    const T* kp = kv + tok * kv_ld + ch;
+    const T* vp = kp + v_off;
+    float* dk = sK + u * ustride + n * D;
+    float* dv = sV + u * ustride + n * D;
+#pragma unroll
+    for (int e = 0; e < D; ++e) {
+      qr[e] = to_f32<T>(qp[e]) * scale;      // q * scale first (pgrm.py:230-231)
+      dk[e] = to_f32<T>(kp[e]);
+      dv[e] = to_f32<T>(vp[e]);
+    }
+  }
+  __syncthreads();
+
+  const int i_n = n / ws, j_n = n - i_n * ws;
+  const int my_lab = sLab[t];
+  const float* kbase = sK + u * ustride;
+  const float* vbase = sV + u * ustride;
+  const int* lab = sLab + u * N;
+  const int tw = 2 * ws - 1;
+
+  float mx = -INFINITY, den = 0.f;
+  float o[D];
+#pragma unroll
+  for (int e = 0; e < D; ++e) o[e] = 0.f;
+  int i_m = 0, j_m = 0;
+  for (int m = 0; m < N; ++m) {
+    const float4* k4 = reinterpret_cast<const float4*>(kbase + m * D);
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < D / 4; ++e) {
+      const float4 kk = k4[e];
+      s = fmaf(qr[4 * e + 0], kk.x, s);
+      s = fmaf(qr[4 * e + 1], kk.y, s);
+      s = fmaf(qr[4 * e + 2], kk.z, s);
+      s = fmaf(qr[4 * e + 3], kk.w, s);
+    }
+    s += sT[(i_n - i_m + ws - 1) * tw + (j_n - j_m + ws - 1)];
+    if (lab[m] != my_lab) s += -100.0f;      // pgrm.py:173
+    const float nmx = fmaxf(mx, s);
+    const float corr = expf(mx - nmx);       // 0 on the first key (mx = -inf)
+    const float pexp = expf(s - nmx);
+    den = den * corr + pexp;
+    const float4* v4 = reinterpret_cast<const float4*>(vbase + m * D);
+#pragma unroll
+    for (int e = 0; e < D / 4; ++e) {
+      const float4 vv = v4[e];
+      o[4 * e + 0] = fmaf(pexp, vv.x, o[4 * e + 0] * corr);
+      o[4 * e + 1] = fmaf(pexp, vv.y, o[4 * e + 1] * corr);
+      o[4 * e + 2] = fmaf(pexp, vv.z, o[4 * e + 2] * corr);
+      o[4 * e + 3] = fmaf(pexp, vv.w, o[4 * e + 3] * corr);
+    }
+    mx = nmx;
+    if (++j_m == ws) { j_m = 0; ++i_m; }
+  }
+  const float inv = 1.0f / den;
+  T* op = out + ((long long)b * L + p) * out_ld + ch;
+#pragma unroll
+  for (int e = 0; e < D; ++e) op[e] = from_f32<T>(o[e] * inv);
+}
+
+template <typename T, int D>
+static int launch_attn_group(const AttnArgs& a, int g, cudaStream_t st) {
+  const int ws = a.window[g], N = ws * ws, L = a.H * a.W;
+  const int cg = a.C / a.n_groups;
+  const int Tn = N > 128 ? N : 128;
+  if (Tn > 1024 || L % Tn != 0 || Tn % N != 0) return -2;
+  const int units = Tn / N;
+  const size_t smem = (size_t)(2 * units * (N * D + 4) + (2 * ws - 1) * (2 * ws - 1)) * sizeof(float) +
+                      (size_t)Tn * sizeof(int);
+  auto kern = window_attn_simt_kernel<T, D>;
+  if (smem > 48 * 1024) DPMN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(L / Tn, a.heads_per_group, a.B);
+  kern<<<grid, Tn, smem, st>>>((const T*)a.q, (const T*)a.kv, (T*)a.out, a.q_ld, a.kv_ld, a.v_off, a.out_ld,
+                               a.table[g], a.heads_per_group, g * cg, a.H, a.W, ws, a.shift[g],
+                               1.0f / sqrtf((float)D));
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int launch_attn_t(const AttnArgs& a, cudaStream_t st) {
+  const int cg = a.C / a.n_groups;
+  const int d = cg / a.heads_per_group;
+  for (int g = 0; g < a.n_groups; ++g) {
+    int rc;
+    switch (d) {
+      case 8: rc = launch_attn_group<T, 8>(a, g, st); break;
+      case 16: rc = launch_attn_group<T, 16>(a, g, st); break;
+      case 24: rc = launch_attn_group<T, 24>(a, g, st); break;
+      case 32: rc = launch_attn_group<T, 32>(a, g, st); break;
+      case 48: rc = launch_attn_group<T, 48>(a, g, st); break;
+      case 64: rc = launch_attn_group<T, 64>(a, g, st); break;
+      default: rc = -2;
+    }
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+int launch_window_attn_simt(const AttnArgs& a, cudaStream_t st) {
+  if (a.n_groups < 1 || a.n_groups > 4 || a.C % a.n_groups || (a.C / a.n_groups) % a.heads_per_group) return -1;
+  for (int g = 0; g < a.n_groups; ++g)
+    if (a.window[g] < 1 || a.H % a.window[g] || a.W % a.window[g]) return -2;
+  switch (a.io_type) {
+    case DT_F32: return launch_attn_t<float>(a, st);
+    case DT_F16: return launch_attn_t<__half>(a, st);
+    case DT_BF16: return launch_attn_t<__nv_bfloat16>(a, st);
+  }
+  return -1;
+}
+
+// =====================================================================================================
+// K3  SK gate folding                                                                  pgrm.py:84-95
+// S = mean_L GELU(proj(x));  Z = GELU(fc1 S);  A = softmax_G(view(fc2 Z, (G, cg)));
+// out = proj(x) + proj_head(sum_m A[m] * x_m)  ==  x * (Wp + Wh diag(A))^T + (bp + bh)
+// One CTA per image builds the folded (C x C) weight and bias.
+// =====================================================================================================
+template <typename WT>
+__global__ void __launch_bounds__(256) sk_gate_kernel(const float* __restrict__ colsum, int tiles, int L,
+                                                      const float* __restrict__ wp, const float* __restrict__ bp,
+                                                      const float* __restrict__ w1, const float* __restrict__ b1,
+                                                      const float* __restrict__ w2, const float* __restrict__ b2,
+                                                      const float* __restrict__ wh, const float* __restrict__ bh,
+                                                      WT* __restrict__ wb_out, float* __restrict__ bias_out, int C,
+                                                      int G) {
+  extern __shared__ float sm[];
+  const int cg = C / G, dz = cg / 2;
+  float* sS = sm;          // [C]
+  float* sZ = sS + C;      // [dz]
+  float* sA = sZ + dz;     // [C]  attention vector, index m*cg + j
+  const int b = blockIdx.x, t = threadIdx.x;
+  for (int c = t; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < tiles; ++i) s += colsum[((long long)b * tiles + i) * C + c];
+    sS[c] = s / (float)L;
+  }
+  __syncthreads();
+  for (int j = t; j < dz; j += blockDim.x) {
+    float s = b1[j];
+    for (int c = 0; c < C; ++c) s = fmaf(w1[j * C + c], sS[c], s);
+    sZ[j] = gelu_erf(s);
+  }
+  __syncthreads();
+  for (int c = t; c < C; c += blockDim.x) {
+    float s = b2[c];
+    for (int j = 0; j < dz; ++j) s = fmaf(w2[c * dz + j], sZ[j], s);
+    sA[c] = s;
+  }
+  __syncthreads();
+  for (int j = t; j < cg; j += blockDim.x) {   // softmax over the G groups for channel j
+    float mx = -INFINITY;
+    for (int m = 0; m < G; ++m) mx = fmaxf(mx, sA[m * cg + j]);
+    float den = 0.f;
+    for (int m = 0; m < G; ++m) den += expf(sA[m * cg + j] - mx);
+    for (int m = 0; m < G; ++m) sA[m * cg + j] = expf(sA[m * cg + j] - mx) / den;
+  }
+  __syncthreads();
+  for (int i = t; i < C * C; i += blockDim.x) {
+    const int o = i / C, c = i - o * C;
+    const int j = c % cg;
+    wb_out[(long long)b * C * C + i] = from_f32<WT>(fmaf(wh[o * cg + j], sA[c], wp[i]));
+  }
+  for (int o = t; o < C; o += blockDim.x) bias_out[(long long)b * C + o] = bp[o] + bh[o];
+}
+
+int launch_sk_gate(const float* colsum, int tiles_per_image, int L, const float* wp, const float* bp,
+                   const float* w1, const float* b1, const float* w2, const float* b2, const float* wh,
+                   const float* bh, void* wb_out, DType wb_type, float* bias_out, int B, int C, int G,
+                   cudaStream_t st) {
+  const int cg = C / G;
+  const size_t smem = (size_t)(2 * C + cg / 2 + 8) * sizeof(float);
+  switch (wb_type) {
+    case DT_F32:
+      sk_gate_kernel<float><<<B, 256, smem, st>>>(colsum, tiles_per_image, L, wp, bp, w1, b1, w2, b2, wh, bh,
+                                                  (float*)wb_out, bias_out, C, G);
+      break;
+    case DT_F16:
+      sk_gate_kernel<__half><<<B, 256, smem, st>>>(colsum, tiles_per_image, L, wp, bp, w1, b1, w2, b2, wh, bh,
+                                                   (__half*)wb_out, bias_out, C, G);
+      break;
+    case DT_BF16:
+      sk_gate_kernel<__nv_bfloat16><<<B, 256, smem, st>>>(colsum, tiles_per_image, L, wp, bp, w1, b1, w2, b2, wh,
+                                                          bh, (__nv_bfloat16*)wb_out, bias_out, C, G);
+      break;
+  }
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// K4a  depthwise 3x3 (+bias, GELU) on the RAW view of the hidden tensor                pgrm.py:33-36
+// h is (B, L, hid) row-major; the reference reinterprets each image's L*hid floats as (hid, side, side)
+// with no transpose (quirk 2).  The result is written transposed, dt[b][pixel][channel], so that the
+// pointwise conv is a K-contiguous GEMM operand.
+// CTA = (image, 32 channels, strip of 8 rows); lane = channel for conflict-free smem and coalesced stores.
+// =====================================================================================================
+constexpr int DW_ROWS = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ h, T* __restrict__ dt,
+                                                     const float* __restrict__ w, const float* __restrict__ bias,
+                                                     int L, int hid, int side) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32;
+  const int y0 = blockIdx.x * DW_ROWS;
+  const int rows_in = DW_ROWS + 2;
+  const int cstride = rows_in * side + 1;
+  const T* hb = h + (long long)b * L * hid;
+  // stage rows y0-1 .. y0+DW_ROWS of 32 channel planes (zero outside the plane)
+  for (int i = threadIdx.x; i < 32 * rows_in * side; i += blockDim.x) {
+    const int c = i / (rows_in * side);
+    const int r = i - c * rows_in * side;
+    const int yy = y0 - 1 + r / side;
+    const int xx = r % side;
+    float v = 0.f;
+    if (yy >= 0 && yy < side) v = to_f32<T>(hb[(long long)(c0 + c) * L + yy * side + xx]);
+    sm[c * cstride + r] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = c0 + lane;
+  float wk[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) wk[i] = w[c * 9 + i];
+  const float bb = bias[c];
+  const float* pl = sm + lane * cstride;
+  const int n_pix = DW_ROWS * side;
+  for (int pi = warp; pi < n_pix; pi += 8) {
+    const int yl = pi / side, xx = pi - yl * side;
+    if (y0 + yl >= side) break;
+    float acc = bb;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const float* row = pl + (yl + ky) * side;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xc = xx + kx - 1;
+        if (xc >= 0 && xc < side) acc = fmaf(row[xc], wk[ky * 3 + kx], acc);
+      }
+    }
+    const int pix = (y0 + yl) * side + xx;
+    dt[((long long)b * L + pix) * hid + c] = from_f32<T>(gelu_erf(acc));
+  }
+}
+
+int launch_dwconv(const void* h, void* dt, DType io_type, const float* w, const float* b, int B, int L, int hid,
+                  cudaStream_t st) {
+  int side = (int)(sqrtf((float)L) + 0.5f);
+  if (side * side != L || hid % 32 != 0) return -2;   // the reference's view() needs a perfect square too
+  dim3 grid((side + DW_ROWS - 1) / DW_ROWS, hid / 32, B);
+  const size_t smem = (size_t)32 * ((DW_ROWS + 2) * side + 1) * sizeof(float);
+  if (smem > 200 * 1024) return -2;
+  switch (io_type) {
+    case DT_F32: {
+      auto k = dwconv_kernel<float>;
+      if (smem > 48 * 1024) DPMN_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, 256, smem, st>>>((const float*)h, (float*)dt, w, b, L, hid, side);
+      break;
+    }
+    case DT_F16: {
+      auto k = dwconv_kernel<__half>;
+      if (smem > 48 * 1024) DPMN_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, 256, smem, st>>>((const __half*)h, (__half*)dt, w, b, L, hid, side);
+      break;
+    }
+    case DT_BF16: {
+      auto k = dwconv_kernel<__nv_bfloat16>;
+      if (smem > 48 * 1024) DPMN_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, 256, smem, st>>>((const __nv_bfloat16*)h, (__nv_bfloat16*)dt, w, b, L, hid, side);
+      break;
+    }
+  }
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// K5  head: PatchUnEmbed + conv3x3 (C -> hp)                                           pgrm.py:559-560
+// x is token-major (B, gh, gw, C) == NHWC, which is what PatchUnEmbed's transpose+view describes.
+// One thread per output pixel, all hp (<= 16) outputs in registers; weights in smem as [tap][ci][hp].
+// =====================================================================================================
+constexpr int HP_MAX = 16;
+
+__global__ void __launch_bounds__(128) head_conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ t1,
+                                                         int total, int gh, int gw, int C, int hp) {
+  extern __shared__ __align__(16) float sw[];   // [9][C][HP_MAX]
+  for (int i = threadIdx.x; i < 9 * C * HP_MAX; i += blockDim.x) {
+    const int co = i % HP_MAX;
+    const int ci = (i / HP_MAX) % C;
+    const int tap = i / (HP_MAX * C);
+    sw[i] = co < hp ? w[(co * C + ci) * 9 + tap] : 0.f;
+  }
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int xx = idx % gw;
+  const int yy = (idx / gw) % gh;
+  const int b = idx / (gw * gh);
+  float acc[HP_MAX];
+#pragma unroll
+  for (int j = 0; j < HP_MAX; ++j) acc[j] = j < hp ? bias[j] : 0.f;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int y2 = yy + ky - 1;
+    if (y2 < 0 || y2 >= gh) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int x2 = xx + kx - 1;
+      if (x2 < 0 || x2 >= gw) continue;
+      const float4* src = reinterpret_cast<const float4*>(x + ((long long)(b * gh + y2) * gw + x2) * C);
+      const float* wt = sw + (ky * 3 + kx) * C * HP_MAX;
+      for (int c4 = 0; c4 < C / 4; ++c4) {
+        const float4 v = src[c4];
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4* w4 = reinterpret_cast<const float4*>(wt + (c4 * 4 + u) * HP_MAX);
+#pragma unroll
+          for (int j4 = 0; j4 < HP_MAX / 4; ++j4) {
+            const float4 ww = w4[j4];
+            acc[4 * j4 + 0] = fmaf(vv[u], ww.x, acc[4 * j4 + 0]);
+            acc[4 * j4 + 1] = fmaf(vv[u], ww.y, acc[4 * j4 + 1]);
+            acc[4 * j4 + 2] = fmaf(vv[u], ww.z, acc[4 * j4 + 2]);
+            acc[4 * j4 + 3] = fmaf(vv[u], ww.w, acc[4 * j4 + 3]);
+          }
+        }
+      }
+    }
+  }
+  float* dst = t1 + (long long)idx * HP_MAX;
+#pragma unroll
+  for (int j4 = 0; j4 < HP_MAX / 4; ++j4)
+    *reinterpret_cast<float4*>(dst + 4 * j4) = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
+}
+
+int launch_head_conv1(const float* x, const float* w, const float* b, float* t1, int B, int gh, int gw, int C,
+                      int hp, cudaStream_t st) {
+  if (hp > HP_MAX || C % 4) return -2;
+  const int total = B * gh * gw;
+  const size_t smem = (size_t)9 * C * HP_MAX * sizeof(float);
+  if (smem > 200 * 1024) return -2;
+  if (smem > 48 * 1024)
+    DPMN_CUDA_TRY(cudaFuncSetAttribute(head_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  head_conv1_kernel<<<(total + 127) / 128, 128, smem, st>>>(x, w, b, t1, total, gh, gw, C, hp);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// conv3x3 (hp -> hp) + LeakyReLU(0.01) + PixelShuffle(r) + affine mix                  pgrm.py:560-564
+// t1 is (B, gh, gw, HP_MAX) from head_conv1.  out[b, c, y*r+dy, x*r+dx] = lrelu(conv)[c*r*r + dy*r + dx]
+// * weight_list_0 + sum_{i>=1} residual_i * weight_list_i   (residual_list[0] is never read: quirk 3).
+__global__ void __launch_bounds__(128) head_conv2_mix_kernel(const float* __restrict__ t1,
+                                                             const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ out,
+                                                             int total, int gh, int gw, int hs, int r, MixArgs mix) {
+  __shared__ __align__(16) float sw[9 * HP_MAX * HP_MAX];   // [tap][ci][co]
+  const int hp = hs * r * r;
+  for (int i = threadIdx.x; i < 9 * HP_MAX * HP_MAX; i += blockDim.x) {
+    const int co = i % HP_MAX;
+    const int ci = (i / HP_MAX) % HP_MAX;
+    const int tap = i / (HP_MAX * HP_MAX);
+    sw[i] = (co < hp && ci < hp) ? w[(co * hp + ci) * 9 + tap] : 0.f;
+  }
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int xx = idx % gw;
+  const int yy = (idx / gw) % gh;
+  const int b = idx / (gw * gh);
+  float acc[HP_MAX];
+#pragma unroll
+  for (int j = 0; j < HP_MAX; ++j) acc[j] = j < hp ? bias[j] : 0.f;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int y2 = yy + ky - 1;
+    if (y2 < 0 || y2 >= gh) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int x2 = xx + kx - 1;
+      if (x2 < 0 || x2 >= gw) continue;
+      const float4* src = reinterpret_cast<const float4*>(t1 + ((long long)(b * gh + y2) * gw + x2) * HP_MAX);
+      const float* wt = sw + (ky * 3 + kx) * HP_MAX * HP_MAX;
+#pragma unroll
+      for (int c4 = 0; c4 < HP_MAX / 4; ++c4) {
+        const float4 v = src[c4];
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4* w4 = reinterpret_cast<const float4*>(wt + (c4 * 4 + u) * HP_MAX);
+#pragma unroll
+          for (int j4 = 0; j4 < HP_MAX / 4; ++j4) {
+            const float4 ww = w4[j4];
+            acc[4 * j4 + 0] = fmaf(vv[u], ww.x, acc[4 * j4 + 0]);
+            acc[4 * j4 + 1] = fmaf(vv[u], ww.y, acc[4 * j4 + 1]);
+            acc[4 * j4 + 2] = fmaf(vv[u], ww.z, acc[4 * j4 + 2]);
+            acc[4 * j4 + 3] = fmaf(vv[u], ww.w, acc[4 * j4 + 3]);
+          }
+        }
+      }
+    }
+  }
+  const int img_h = gh * r, img_w = gw * r;
+  const long long plane = (long long)img_h * img_w;
+#pragma unroll
+  for (int j = 0; j < HP_MAX; ++j) {
+    if (j >= hp) break;
+    float v = acc[j];
+    v = v >= 0.f ? v : 0.01f * v;                       // nn.LeakyReLU default slope (pgrm.py:520)
+    const int c = j / (r * r);
+    const int rem = j - c * r * r;
+    const int dy = rem / r, dx = rem - dy * r;
+    const long long pix = (long long)c * plane + (long long)(yy * r + dy) * img_w + (xx * r + dx);
+    float res = v * mix.w[0][pix];
+    for (int i = 1; i < mix.n_mix; ++i)
+      res = fmaf(mix.in[i][(long long)b * mix.in_bs[i] + pix], mix.w[i][pix], res);
+    out[(long long)b * hs * plane + pix] = res;
+  }
+}
+
+int launch_head_conv2_mix(const float* t1, const float* w, const float* b, float* out, int B, int gh, int gw,
+                          int hs, int patch, const MixArgs& mix, cudaStream_t st) {
+  if (hs * patch * patch > HP_MAX || mix.n_mix < 1 || mix.n_mix > 8) return -2;
+  const int total = B * gh * gw;
+  head_conv2_mix_kernel<<<(total + 127) / 128, 128, 0, st>>>(t1, w, b, out, total, gh, gw, hs, patch, mix);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+template <typename T>
+__global__ void convert_kernel(const float* __restrict__ src, T* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = from_f32<T>(src[i]);
+}
+
+int launch_convert(const float* src, void* dst, DType dst_type, long long n, cudaStream_t st) {
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  if (dst_type == DT_F16) convert_kernel<__half><<<(int)blocks, 256, 0, st>>>(src, (__half*)dst, n);
+  else if (dst_type == DT_BF16) convert_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>(src, (__nv_bfloat16*)dst, n);
+  else return -1;
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dpmn

@@ -1,0 +1,190 @@
+/*
+ * dpmn_b200 -- C ABI of the B200-native DPMN hot path (PGRM stack + Complementation Modulation Module).
+ *
+ * The reference (jdfxzzy/DPMN) is pure PyTorch: it has no FFI/plugin layer, its boundary for this path
+ * is the nn.Module ctor + forward signature + state_dict schema.  This header is the
+ * C-ABI a binding sits on; each entry point names the reference interface it replaces:
+ *
+ *   dpmn_pgrm_forward          <- PGRM.forward(x_q, x_kv, residual_list)            model/pgrm.py:546-565
+ *   dpmn_pgrm_forward_probe    <- same, exposing WindowAttention / SwinTransformerBlock outputs
+ *                                                                                   model/pgrm.py:184-271,315-331
+ *   dpmn_window_attn_forward   <- WindowAttention.forward, per-group core           model/pgrm.py:197-268
+ *   dpmn_cmm_forward           <- ComplementationModulationModule.forward(x1, x2)   model/cmm.py:120-161
+ *   dpmn_gemm_nt               <- nn.Linear / 1x1 conv contraction (F.linear)       model/pgrm.py:30,37,39,82,188,194
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = argument error (DPMN_E_*), >0 = a cudaError_t value
+ *   - all pointers are DEVICE pointers; tensors are fp32 in the layouts stated per argument (NCHW images,
+ *     exactly as the reference passes them); image tensors may carry a batch stride (channel-slice views
+ *     such as cascade[:, :3], interfaces/super_resolution.py:196)
+ *   - the library never allocates or frees device memory and never synchronises: the caller passes a
+ *     workspace of at least dpmn_*_workspace_bytes() and a stream (cudaStream_t as void*)
+ *   - weights are read in place in the reference's own state_dict layout; nothing is cached across calls
+ */
+#ifndef DPMN_B200_H
+#define DPMN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPMN_MAX_GROUPS 4   /* window groups per attention (reference default 3: windows 2,4,8) */
+#define DPMN_MAX_MIX 8      /* weight_list_0 .. weight_list_iter (reference uses iter <= 5) */
+#define DPMN_MAX_BLOCKS 2   /* BasicLayer depth is hard-wired to 2 (pgrm.py:506) */
+
+enum {
+  DPMN_OK = 0,
+  DPMN_E_ARG = -1,        /* null pointer / inconsistent sizes */
+  DPMN_E_UNSUPPORTED = -2,/* configuration the reference itself cannot run, or outside this build */
+  DPMN_E_WORKSPACE = -3,  /* workspace too small */
+  DPMN_E_DEVICE = -4      /* not an sm_100 device / driver entry point missing */
+};
+
+/* arithmetic of the GEMM / attention contractions.  Residual stream, LayerNorm statistics, softmax
+ * and all accumulation are fp32 in every mode. */
+enum {
+  DPMN_PREC_F32 = 0,      /* fp32 FFMA everywhere: matches the reference to 1e-5 rel */
+  DPMN_PREC_F16 = 1,      /* fp16 operands on tcgen05 tensor cores, fp32 accumulate: 1e-3 rel */
+  DPMN_PREC_BF16 = 2      /* bf16 operands on tcgen05 tensor cores, fp32 accumulate */
+};
+
+/* one SwinTransformerBlock (pgrm.py:290-331); names follow the state_dict keys under
+ * layers.0.blocks.<b>. ; every pointer is the fp32 tensor in torch's own layout. */
+typedef struct dpmn_block_weights {
+  const float *norm1_q_w, *norm1_q_b, *norm1_kv_w, *norm1_kv_b;       /* (C) */
+  const float *rpb_table[DPMN_MAX_GROUPS];  /* attn.relative_position_bias_table_g ((2ws-1)^2, heads/G) */
+  const float *q_w, *q_b;                   /* attn.q   (C, C), (C) */
+  const float *kv_w, *kv_b;                 /* attn.kv  (2C, C), (2C) */
+  const float *sk_proj_w, *sk_proj_b;       /* attn.sknet.proj       (C, C) */
+  const float *sk_fc1_w, *sk_fc1_b;         /* attn.sknet.fc1        (C/G/2, C) */
+  const float *sk_fc2_w, *sk_fc2_b;         /* attn.sknet.fc2        (C, C/G/2) */
+  const float *sk_head_w, *sk_head_b;       /* attn.sknet.proj_head  (C, C/G) */
+  const float *norm2_w, *norm2_b;           /* (C) */
+  const float *fc1_w, *fc1_b;               /* mlp.fc1 (hid, C) */
+  const float *fc2_w, *fc2_b;               /* mlp.fc2 (C, hid) */
+  const float *dw_w, *dw_b;                 /* mlp.depthwise_conv (hid, 1, 3, 3) */
+  const float *pw_w, *pw_b;                 /* mlp.pointwise_conv (hid, hid, 1, 1) */
+} dpmn_block_weights;
+
+/* one PGRM (pgrm.py:460-565) */
+typedef struct dpmn_pgrm_desc {
+  int32_t batch;            /* B */
+  int32_t img_h, img_w;     /* 32, 128 */
+  int32_t patch;            /* patch_size[iter] (2) */
+  int32_t q_chans;          /* channels of x_q: 2 (prior_fusion runs, pgrm.py:547-548) or 3 */
+  int32_t embed_dim;        /* C (96) */
+  int32_t num_heads;        /* 6 */
+  int32_t n_groups;         /* len(window_size[iter]) */
+  int32_t window[DPMN_MAX_GROUPS];   /* configured windows (2,4,8); clamp/shift rules applied inside */
+  int32_t mlp_hidden;       /* int(C * mlp_ratio) (384) */
+  int32_t hidden_size;      /* output channels (3) */
+  int32_t precision;        /* DPMN_PREC_* */
+  int32_t n_mix;            /* number of terms of the final affine mix = max(1, len(residual_list)) */
+  int64_t x_q_batch_stride; /* elements between images of x_q / x_kv; 0 = dense (chans*img_h*img_w) */
+  int64_t x_kv_batch_stride;
+  const float *prior_fusion_w, *prior_fusion_b;   /* (3,2,3,3),(3) or NULL when q_chans == 3 */
+  const float *pe_w, *pe_b;                       /* patch_embed.proj (C,3,p,p),(C) */
+  const float *pe_norm_w, *pe_norm_b;             /* patch_embed.norm (C) */
+  dpmn_block_weights blocks[DPMN_MAX_BLOCKS];
+  const float *head0_w, *head0_b;                 /* conv_before_upsample.0 (hs*p*p, C, 3, 3) */
+  const float *head1_w, *head1_b;                 /* conv_before_upsample.1 (hs*p*p, hs*p*p, 3, 3) */
+  /* out = head * mix_weight[0] + sum_{i=1}^{n_mix-1} mix_input[i] * mix_weight[i]   (pgrm.py:562-564;
+   * mix_input[0] is never read: the reference skips residual_list[0]) */
+  const float *mix_weight[DPMN_MAX_MIX];          /* weight_list_i (1, hs, img_h, img_w) */
+  const float *mix_input[DPMN_MAX_MIX];           /* residual_list[i] (B, hs, img_h, img_w) */
+  int64_t mix_input_batch_stride[DPMN_MAX_MIX];   /* 0 = dense */
+} dpmn_pgrm_desc;
+
+/* ---- Complementation Modulation Module (cmm.py:80-161) ------------------------------------------- */
+typedef struct dpmn_bn {          /* nn.BatchNorm2d (cmm.py:12), eps 1e-5, momentum 0.1 */
+  const float *w, *b;             /* (ch) */
+  float *running_mean, *running_var;   /* (ch); written only when training && update_running_stats */
+} dpmn_bn;
+
+typedef struct dpmn_cmm_stage {   /* EncodeBlock (cmm.py:38-55) / DecodeBlock (cmm.py:58-77) */
+  const float *conv_a_w, *conv_a_b;    /* index 1: enc conv4x4 s2 d2 p3 (ci,ci) | dec convT3x3 (cin,co) */
+  dpmn_bn bn_a;                        /* index 2 */
+  const float *conv_b_w, *conv_b_b;    /* index 4: enc conv3x3 (co,ci)        | dec convT4x4 s2 (co,co) */
+  dpmn_bn bn_b;                        /* index 5 */
+} dpmn_cmm_stage;
+
+typedef struct dpmn_cmm_desc {
+  int32_t batch;                  /* B */
+  int32_t img_h, img_w;           /* 32, 128 (must be divisible by 32) */
+  int32_t c_img, cnum;            /* 3, 64 */
+  int32_t precision;              /* DPMN_PREC_* */
+  int32_t training;               /* 1: BatchNorm uses batch statistics (module.train()) */
+  int32_t update_running_stats;   /* 1: also apply the momentum update to running_mean/var */
+  int64_t x1_batch_stride, x2_batch_stride;   /* 0 = dense */
+  const float *en1_w[2], *en1_b[2];           /* en_1_{1,2}  conv3x3 (cnum, c_img) */
+  dpmn_cmm_stage enc[2][4];                   /* en_{2..5}_{1,2} */
+  const float *en6_w[2], *en6_b[2];           /* en_6_{1,2}.1 conv4x4 s2 p1 */
+  const float *fc1_w, *fc1_b, *fc2_w, *fc2_b; /* SE gate (4cnum,16cnum), (16cnum,4cnum) */
+  const float *de6_w, *de6_b;                 /* de_6.1 convT4x4 s2 p1 (16cnum, 8cnum) */
+  dpmn_bn de6_bn;                             /* de_6.2 */
+  dpmn_cmm_stage dec[4];                      /* de_5, de_4, de_3, de_2 */
+  const float *de1_w, *de1_b;                 /* de_1.1 convT3x3 (3cnum, c_img) */
+} dpmn_cmm_desc;
+
+const char *dpmn_version(void);
+
+/* 0 if the current device can run this library (compute capability 10.x), else DPMN_E_DEVICE. */
+int dpmn_check_device(void);
+
+/* sizeof() of the descriptor structs as compiled, so a binding can verify its own struct layout:
+ * which = 0 dpmn_block_weights, 1 dpmn_pgrm_desc, 2 dpmn_bn, 3 dpmn_cmm_stage, 4 dpmn_cmm_desc. */
+size_t dpmn_abi_sizeof(int32_t which);
+
+/* number of kernels launched by this library in this process so far (bench.py's gpu_launches). */
+uint64_t dpmn_launch_count(void);
+
+/* Per-launch device timing for the roofline report (bench.py).  While enabled, every kernel launch of
+ * this library is bracketed by CUDA events on its stream; dpmn_profile_collect synchronises on them and
+ * returns up to `cap` records (kernel-class tag, kernels in the record, milliseconds), then clears. */
+int dpmn_profile_enable(int32_t on);
+int32_t dpmn_profile_collect(int32_t *tags, int32_t *n_kernels, float *ms, int32_t cap);
+const char *dpmn_profile_tag_name(int32_t tag);
+
+size_t dpmn_pgrm_workspace_bytes(const dpmn_pgrm_desc *d);
+
+/* PGRM.forward.  x_q (B, q_chans, img_h, img_w), x_kv (B, 3, img_h, img_w), out (B, hidden_size, img_h, img_w). */
+int dpmn_pgrm_forward(const dpmn_pgrm_desc *d, const float *x_q, const float *x_kv, float *out,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* Debug/probe variant: additionally copies per-block tensors out (any pointer may be NULL):
+ * attn_core[b] (B, L, C) the window-major attention output that enters SKConv (fp32),
+ * block_out[b] (B, L, C) the x_kv stream after block b. */
+int dpmn_pgrm_forward_probe(const dpmn_pgrm_desc *d, const float *x_q, const float *x_kv, float *out,
+                            void *workspace, size_t workspace_bytes, void *stream,
+                            float *const attn_core[DPMN_MAX_BLOCKS], float *const block_out[DPMN_MAX_BLOCKS]);
+
+/* Stand-alone windowed attention core of one block (the roofline-sweep kernel).
+ * q (B, L, C), kv (B, L, 2C) are the PROJECTED tensors in token order (fp32, or fp16/bf16 when
+ * precision != F32: then q/kv/out are 16-bit); out (B, L, C) in the reference's window-major row order.
+ * grid_h * grid_w = L.  window[g]/shift[g] are the EFFECTIVE window and cyclic shift of group g. */
+int dpmn_window_attn_forward(const void *q, const void *kv, void *out, const float *const rpb_table[DPMN_MAX_GROUPS],
+                             int32_t batch, int32_t grid_h, int32_t grid_w, int32_t embed_dim, int32_t num_heads,
+                             int32_t n_groups, const int32_t window[DPMN_MAX_GROUPS],
+                             const int32_t shift[DPMN_MAX_GROUPS], int32_t precision,
+                             void *workspace, size_t workspace_bytes, void *stream);
+size_t dpmn_window_attn_workspace_bytes(int32_t batch, int32_t tokens, int32_t embed_dim, int32_t precision);
+
+size_t dpmn_cmm_workspace_bytes(const dpmn_cmm_desc *d);
+
+/* ComplementationModulationModule.forward.  x1, x2 (B, c_img, img_h, img_w) -> out (B, c_img, img_h, img_w). */
+int dpmn_cmm_forward(const dpmn_cmm_desc *d, const float *x1, const float *x2, float *out,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* C (M, N) = A (M, K) * B (N, K)^T + bias (N), fp32 in/out; `precision` picks FFMA or tcgen05 operands.
+ * The contraction every nn.Linear / 1x1 conv of the path reduces to; exported for unit tests. */
+int dpmn_gemm_nt(const float *A, const float *B, const float *bias, float *C, int32_t M, int32_t N, int32_t K,
+                 int32_t precision, void *workspace, size_t workspace_bytes, void *stream);
+size_t dpmn_gemm_nt_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t precision);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPMN_B200_H */

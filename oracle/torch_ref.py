@@ -1,0 +1,181 @@
+"""torch-CPU functional restatement of the reference PGRM / CMM forward (eval or train-BN).
+TEST INFRASTRUCTURE ONLY -- and the CPU baseline `bench.py` times (`cpu_baseline.kind = "port"`).
+
+Why a second oracle: the reference's own CPU path is multi-threaded PyTorch (oneDNN/MKL); the numpy
+oracle (pgrm_oracle.py / cmm_oracle.py) is exact but single-threaded einsum.  This file restates the
+same algorithm with torch ops so that the CPU baseline is timed on the libraries and thread count the
+reference would use on the same host.  /root/reference does not exist on the GPU box, so the
+reference itself cannot be timed there.  Pinned by tests/test_oracle_golden.py against the golden
+fixtures (outputs of the unmodified reference).  Citations: /root/reference/model/pgrm.py, cmm.py.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence
+
+import torch
+import torch.nn.functional as F
+
+
+def _order(H, W, ws, shift):
+    """window-major row -> original token (pgrm.py:209-221,43-52)."""
+    p = torch.arange(H * W)
+    w_idx, n = p // (ws * ws), p % (ws * ws)
+    nWw = W // ws
+    hp = (w_idx // nWw) * ws + n // ws
+    wp = (w_idx % nWw) * ws + n % ws
+    return ((hp + shift) % H) * W + (wp + shift) % W
+
+
+def _rel_index(ws):
+    i, j = torch.arange(ws * ws) // ws, torch.arange(ws * ws) % ws
+    return (i[:, None] - i[None, :] + ws - 1) * (2 * ws - 1) + (j[:, None] - j[None, :] + ws - 1)
+
+
+def _shift_mask(H, W, ws, shift):
+    def region(x, n):
+        return (x >= n - ws).long() + (x >= n - shift).long()
+    lab = 3 * region(torch.arange(H), H)[:, None] + region(torch.arange(W), W)[None, :]
+    lab = lab.view(H // ws, ws, W // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
+    return torch.where(lab[:, None, :] != lab[:, :, None], -100.0, 0.0)
+
+
+def window_attention_core(q, kv, tables, windows, shifts, H, W, hpg):
+    """pgrm.py:197-268 -> (B, L, C) in window-major row order per group (quirk 1)."""
+    B, L, C = q.shape
+    G = len(windows)
+    cg = C // G
+    d = cg // hpg
+    k_all, v_all = kv[..., :C], kv[..., C:]
+    outs = []
+    for g, (ws, sh) in enumerate(zip(windows, shifts)):
+        N = ws * ws
+        nW = L // N
+        order = _order(H, W, ws, sh)
+        sl = slice(g * cg, (g + 1) * cg)
+
+        def part(x):
+            return x[:, order][..., sl].reshape(B, nW, N, hpg, d).permute(0, 1, 3, 2, 4)
+        s = (part(q) * d ** -0.5) @ part(k_all).transpose(-1, -2)
+        bias = tables[g][_rel_index(ws).reshape(-1)].view(N, N, hpg).permute(2, 0, 1)
+        s = s + bias[None, None]
+        if sh > 0:
+            s = s + _shift_mask(H, W, ws, sh)[None, :, None]
+        o = torch.softmax(s, dim=-1) @ part(v_all)
+        outs.append(o.permute(0, 1, 3, 2, 4).reshape(B, L, cg))
+    return torch.cat(outs, dim=-1)
+
+
+def _sk(x, P, pre, G):
+    """SKConv.forward, pgrm.py:79-96, token-major."""
+    B, L, C = x.shape
+    cg = C // G
+    f = F.linear(x, P[pre + "proj.weight"], P[pre + "proj.bias"])
+    s = F.gelu(f).mean(dim=1)
+    z = F.gelu(F.linear(s, P[pre + "fc1.weight"], P[pre + "fc1.bias"]))
+    a = torch.softmax(F.linear(z, P[pre + "fc2.weight"], P[pre + "fc2.bias"]).view(B, G, cg), dim=1)
+    v = (x.view(B, L, G, cg) * a[:, None]).sum(dim=2)
+    return f + F.linear(v, P[pre + "proj_head.weight"], P[pre + "proj_head.bias"])
+
+
+def _mlp(x, P, pre):
+    """Mlp.forward, pgrm.py:29-41, raw views kept (quirk 2)."""
+    B, L, _ = x.shape
+    side = int(math.sqrt(L))
+    h = F.gelu(F.linear(x, P[pre + "fc1.weight"], P[pre + "fc1.bias"]))
+    hid = h.shape[-1]
+    h = h.reshape(B, hid, side, side)
+    h = F.gelu(F.conv2d(h, P[pre + "depthwise_conv.weight"], P[pre + "depthwise_conv.bias"], padding=1, groups=hid))
+    h = F.conv2d(h, P[pre + "pointwise_conv.weight"], P[pre + "pointwise_conv.bias"])
+    return F.linear(h.reshape(B, L, hid), P[pre + "fc2.weight"], P[pre + "fc2.bias"])
+
+
+def _block(tq, tkv, P, pre, blk, windows, H, W, hpg):
+    """SwinTransformerBlock.forward, pgrm.py:315-331 (eval)."""
+    C = tq.shape[-1]
+    G = len(windows)
+    mn = min(H, W)
+    shifts = [0 if (blk % 2 == 0 or mn <= ws) else ws // 2 for ws in windows]
+    wins = [min(ws, mn) for ws in windows]
+    qn = F.layer_norm(tq, (C,), P[pre + "norm1_q.weight"], P[pre + "norm1_q.bias"])
+    kvn = F.layer_norm(tkv, (C,), P[pre + "norm1_kv.weight"], P[pre + "norm1_kv.bias"])
+    q = F.linear(qn, P[pre + "attn.q.weight"], P[pre + "attn.q.bias"])
+    kv = F.linear(kvn, P[pre + "attn.kv.weight"], P[pre + "attn.kv.bias"])
+    tables = [P[pre + f"attn.relative_position_bias_table_{g}"] for g in range(G)]
+    a = window_attention_core(q, kv, tables, wins, shifts, H, W, hpg)
+    y = tkv + _sk(a, P, pre + "attn.sknet.", G)
+    return y + _mlp(F.layer_norm(y, (C,), P[pre + "norm2.weight"], P[pre + "norm2.bias"]), P, pre + "mlp.")
+
+
+def pgrm_forward(P: Dict[str, torch.Tensor], x_q, x_kv, residual_list: Sequence[torch.Tensor], *,
+                 windows=(2, 4, 8), num_heads=6, patch=2):
+    """PGRM.forward, pgrm.py:546-565 (eval mode)."""
+    if x_q.shape[1] == 2:
+        x_q = F.conv2d(x_q, P["prior_fusion.weight"], P["prior_fusion.bias"], padding=1)
+    C = P["patch_embed.proj.weight"].shape[0]
+
+    def embed(x):
+        y = F.conv2d(x, P["patch_embed.proj.weight"], P["patch_embed.proj.bias"], stride=patch)
+        return F.layer_norm(y.flatten(2).transpose(1, 2), (C,), P["patch_embed.norm.weight"], P["patch_embed.norm.bias"])
+    H, W = x_kv.shape[2] // patch, x_kv.shape[3] // patch
+    tq, tkv = embed(x_q), embed(x_kv)
+    G = len(windows)
+    for blk in range(2):
+        tkv = _block(tq, tkv, P, f"layers.0.blocks.{blk}.", blk, windows, H, W, num_heads // G)
+    B = tkv.shape[0]
+    x = tkv.transpose(1, 2).reshape(B, C, H, W)
+    x = F.conv2d(x, P["conv_before_upsample.0.weight"], P["conv_before_upsample.0.bias"], padding=1)
+    x = F.conv2d(x, P["conv_before_upsample.1.weight"], P["conv_before_upsample.1.bias"], padding=1)
+    x = F.pixel_shuffle(F.leaky_relu(x, 0.01), patch)
+    x = x * P["weight_list_0"]
+    for i in range(1, len(residual_list)):   # residual_list[0] skipped (pgrm.py:563)
+        x = x + residual_list[i] * P[f"weight_list_{i}"]
+    return x
+
+
+def _bn(x, P, pre, training):
+    return F.batch_norm(x, None if training else P[pre + ".running_mean"], None if training else P[pre + ".running_var"],
+                        P[pre + ".weight"], P[pre + ".bias"], training=training, eps=1e-5)
+
+
+def cmm_forward(P: Dict[str, torch.Tensor], x1, x2, training: bool = False):
+    """ComplementationModulationModule.forward, cmm.py:120-161."""
+    skips, bott = [], []
+    for br, x in ((1, x1), (2, x2)):
+        o = [F.conv2d(x, P[f"en_1_{br}.weight"], P[f"en_1_{br}.bias"], padding=1)]
+        for lvl in (2, 3, 4, 5):
+            pre = f"en_{lvl}_{br}.encode."
+            t = F.conv2d(F.leaky_relu(o[-1], 0.2), P[pre + "1.weight"], P[pre + "1.bias"], stride=2, padding=3, dilation=2)
+            t = _bn(t, P, pre + "2", training)
+            t = F.conv2d(F.leaky_relu(t, 0.2), P[pre + "4.weight"], P[pre + "4.bias"], padding=1)
+            o.append(_bn(t, P, pre + "5", training))
+        bott.append(F.conv2d(F.leaky_relu(o[-1], 0.2), P[f"en_6_{br}.1.weight"], P[f"en_6_{br}.1.bias"], stride=2, padding=1))
+        skips.append(o)
+    z = torch.cat(bott, dim=1)
+    g = z.mean(dim=(2, 3))
+    g = torch.sigmoid(F.linear(F.relu(F.linear(g, P["fc_1.weight"], P["fc_1.bias"])), P["fc_2.weight"], P["fc_2.bias"]))
+    z = z * g[:, :, None, None] + z
+    d = _bn(F.conv_transpose2d(F.relu(z), P["de_6.1.weight"], P["de_6.1.bias"], stride=2, padding=1), P, "de_6.2", training)
+    for lvl in (5, 4, 3, 2):
+        pre = f"de_{lvl}.decode."
+        cat = torch.cat([d, skips[0][lvl - 1], skips[1][lvl - 1]], dim=1)
+        t = _bn(F.conv_transpose2d(F.relu(cat), P[pre + "1.weight"], P[pre + "1.bias"], stride=1, padding=1), P, pre + "2", training)
+        d = _bn(F.conv_transpose2d(F.relu(t), P[pre + "4.weight"], P[pre + "4.bias"], stride=2, padding=1), P, pre + "5", training)
+    cat = torch.cat([d, skips[0][0], skips[1][0]], dim=1)
+    return F.conv_transpose2d(F.relu(cat), P["de_1.1.weight"], P["de_1.1.bias"], stride=1, padding=1)
+
+
+def hot_path_forward(pgrm_params: List[Dict[str, torch.Tensor]], cmm_params, psn_out, priors_b1, priors_b2,
+                     windows=(2, 4, 8), num_heads=6):
+    """The call-site data flow of interfaces/super_resolution.py:174-265 (inference): two cascades of
+    three PGRMs on the PSN output, then the CMM.  priors_b1[k] (B,2,H,W), priors_b2[k] (B,3,H,W)."""
+    outs = []
+    for branch, priors in ((0, priors_b1), (1, priors_b2)):
+        cascade = psn_out[:, :3]
+        done = []
+        for k in range(3):
+            y = pgrm_forward(pgrm_params[3 * branch + k], priors[k], cascade, done[:k], windows=windows, num_heads=num_heads)
+            done.append(y)
+            cascade = y
+        outs.append(done[-1])
+    return cmm_forward(cmm_params, outs[0], outs[1], training=False)

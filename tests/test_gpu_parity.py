@@ -1,0 +1,197 @@
+"""Parity of the CUDA path (through the nn.Module boundary -> ctypes -> C-ABI -> kernels) with the
+reference.  Ground truth is (i) the golden fixtures minted from the unmodified reference modules and
+(ii) the numpy oracle (itself pinned against the same fixtures) on freshly seeded inputs.
+
+Tolerances (BASELINE.json north_star; metric = max|d| / max|ref|):
+    fp32 arithmetic   1e-5
+    fp16 tensor-core  1e-3
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cmm_oracle, pgrm_oracle
+from oracle import inputs as gen
+from tests.util import (CMM_GOLDEN, PGRM_GOLDEN, build_cmm, build_pgrm, cmm_case, load_golden, pgrm_case, rel_err)
+
+pytestmark = pytest.mark.gpu
+TOL_F32 = 1e-5
+DEV = "cuda"
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("name", PGRM_GOLDEN)
+def test_pgrm_matches_reference_golden(name):
+    z, meta = load_golden(name)
+    cfg, P, x_q, x_kv, res = pgrm_case(meta)
+    m, _ = build_pgrm(meta, DEV)
+    with torch.no_grad():
+        y = m(_t(x_q), _t(x_kv), [_t(r) for r in res])
+    e = rel_err(y.cpu().numpy(), z["out"])
+    print(f"{name}: rel err {e:.3e}")
+    assert y.shape == z["out"].shape
+    assert e < TOL_F32, e
+
+
+@pytest.mark.parametrize("name", ["pgrm_i0_m0", "pgrm_w16_c192"])
+def test_pgrm_stage_probes_match_reference(name):
+    """WindowAttention core (pre-SK, window-major rows: quirk 1) and both SwinTransformerBlock outputs."""
+    z, meta = load_golden(name)
+    cfg, P, x_q, x_kv, res = pgrm_case(meta)
+    m, _ = build_pgrm(meta, DEV)
+    with torch.no_grad():
+        y, cores, blocks = m.forward_probe(_t(x_q), _t(x_kv), [_t(r) for r in res])
+    errs = {}
+    for b in range(2):
+        errs[f"attn_core_b{b}"] = rel_err(cores[b][:1].cpu().numpy(), z[f"attn_core_b{b}"])
+        errs[f"block{b}_out"] = rel_err(blocks[b][:1].cpu().numpy(), z[f"block{b}_out"])
+    print(name, errs)
+    assert max(errs.values()) < TOL_F32, errs
+
+
+@pytest.mark.parametrize("name", CMM_GOLDEN)
+def test_cmm_matches_reference_golden(name):
+    z, meta = load_golden(name)
+    P, x1, x2 = cmm_case(meta)
+    m, _ = build_cmm(meta, DEV)
+    with torch.no_grad():
+        y = m(_t(x1), _t(x2))
+    e = rel_err(y.cpu().numpy(), z["out"])
+    print(f"{name}: rel err {e:.3e}")
+    assert e < TOL_F32, e
+
+
+def test_cmm_train_mode_updates_running_stats_like_batchnorm():
+    z, meta = load_golden("cmm_c8_train")
+    P, x1, x2 = cmm_case(meta)
+    m, _ = build_cmm(meta, DEV)
+    with torch.no_grad():
+        m(_t(x1), _t(x2))
+    sd = m.state_dict()
+    assert int(sd["de_6.2.num_batches_tracked"]) == 1
+    # first encoder BN sees conv4x4(s2,d2,p3)(lrelu(conv3x3(x1))): recompute its batch stats with the oracle pieces
+    o1 = pgrm_oracle.conv2d(x1, P["en_1_1.weight"], P["en_1_1.bias"], pad=1)
+    a = pgrm_oracle.conv2d(np.where(o1 >= 0, o1, 0.2 * o1).astype(np.float32), P["en_2_1.encode.1.weight"],
+                           P["en_2_1.encode.1.bias"], stride=2, pad=3, dil=2)
+    n = a.shape[0] * a.shape[2] * a.shape[3]
+    mean = a.mean(axis=(0, 2, 3))
+    var_unbiased = a.var(axis=(0, 2, 3)) * n / (n - 1)
+    want_mean = 0.9 * P["en_2_1.encode.2.running_mean"] + 0.1 * mean
+    want_var = 0.9 * P["en_2_1.encode.2.running_var"] + 0.1 * var_unbiased
+    assert rel_err(sd["en_2_1.encode.2.running_mean"].cpu().numpy(), want_mean) < 1e-5
+    assert rel_err(sd["en_2_1.encode.2.running_var"].cpu().numpy(), want_var) < 1e-5
+
+
+def test_x_kv_channel_slice_view_is_accepted():
+    """The caller passes cascade[:, :3] of a 4-channel tensor (super_resolution.py:196): batch-strided view."""
+    z, meta = load_golden("pgrm_i0_m0")
+    cfg, P, x_q, x_kv, res = pgrm_case(meta)
+    m, _ = build_pgrm(meta, DEV)
+    four = torch.cat([_t(x_kv), torch.full((x_kv.shape[0], 1, 32, 128), 7.0, device=DEV)], dim=1)
+    view = four[:, :3, :]
+    assert not view.is_contiguous()
+    with torch.no_grad():
+        a = m(_t(x_q), view, [])
+        b = m(_t(x_q), _t(x_kv), [])
+    assert torch.equal(a, b)
+
+
+def test_residual_zero_is_skipped_and_mix_is_affine():
+    """quirk 3 (pgrm.py:563) + linearity of the per-pixel affine mix in the residuals."""
+    z, meta = load_golden("pgrm_i2_m0")
+    cfg, P, x_q, x_kv, res = pgrm_case(meta)
+    m, _ = build_pgrm(meta, DEV)
+    r0, r1 = _t(res[0]), _t(res[1])
+    with torch.no_grad():
+        a = m(_t(x_q), _t(x_kv), [r0, r1])
+        b = m(_t(x_q), _t(x_kv), [r0 * 0 + 123.0, r1])
+        c = m(_t(x_q), _t(x_kv), [r0, r1 * 0])
+    assert torch.equal(a, b)
+    w1 = _t(P["weight_list_1"])
+    assert rel_err((a - c).cpu().numpy(), (r1 * w1).cpu().numpy()) < 1e-6
+
+
+def test_full_batch_48_is_per_image_independent_and_matches_oracle():
+    """BASELINE batch (48/GPU): every image's result is bit-identical to running it alone (PGRM has no
+    cross-image coupling), and two images are checked against the oracle."""
+    z, meta = load_golden("pgrm_i2_m0")
+    cfg, P, _, _, _ = pgrm_case(meta)
+    m, _ = build_pgrm(meta, DEV)
+    B = 48
+    x_q, x_kv = gen.prior_branch1(77, B), gen.image_stream(77, B)
+    res = gen.residuals(77, B, 2)
+    with torch.no_grad():
+        y = m(_t(x_q), _t(x_kv), [_t(r) for r in res])
+        for b in (0, 17, 47):
+            yb = m(_t(x_q[b:b + 1]), _t(x_kv[b:b + 1]), [_t(r[b:b + 1]) for r in res])
+            assert torch.equal(y[b:b + 1], yb), b
+    sel = [5, 40]
+    ref = pgrm_oracle.pgrm_forward(P, x_q[sel], x_kv[sel], [r[sel] for r in res], windows=cfg.window_size)
+    e = rel_err(y[sel].cpu().numpy(), ref)
+    print("B=48 vs oracle:", e)
+    assert e < TOL_F32 * 2, e   # oracle itself is 2e-5 from the reference
+
+
+@pytest.mark.parametrize("windows,shifts,C,heads", [((2, 4, 8), (0, 0, 0), 96, 6), ((2, 4, 8), (1, 2, 4), 96, 6),
+                                                     ((16,), (0,), 192, 6), ((8,), (4,), 96, 6), ((4, 8), (2, 4), 96, 4)])
+def test_window_attention_core_matches_oracle(windows, shifts, C, heads):
+    from dpmn_b200 import window_attention
+    rng = np.random.default_rng(5)
+    B, H, W = 3, 16, 64
+    G = len(windows)
+    q = rng.standard_normal((B, H * W, C)).astype(np.float32)
+    kv = rng.standard_normal((B, H * W, 2 * C)).astype(np.float32)
+    tables = [(0.5 * rng.standard_normal(((2 * ws - 1) ** 2, heads // G))).astype(np.float32) for ws in windows]
+    ref = pgrm_oracle.window_attention_core(q, kv, tables, windows, shifts, H, W, heads // G)
+    out = window_attention(_t(q), _t(kv), [_t(t) for t in tables], (H, W), heads, windows, shifts)
+    e = rel_err(out.cpu().numpy(), ref)
+    print(windows, shifts, e)
+    assert e < TOL_F32, e
+
+
+def test_cmm_batch_48_eval_is_per_image_independent():
+    z, meta = load_golden("cmm_c64_eval")
+    P, _, _ = cmm_case(meta)
+    m, _ = build_cmm(meta, DEV)
+    x1, x2 = gen.image_stream(3, 48, tag=31), gen.image_stream(3, 48, tag=32)
+    with torch.no_grad():
+        y = m(_t(x1), _t(x2))
+        y0 = m(_t(x1[7:8]), _t(x2[7:8]))
+    assert torch.equal(y[7:8], y0)
+    ref = cmm_oracle.cmm_forward(P, x1[7:8], x2[7:8], training=False)
+    assert rel_err(y0.cpu().numpy(), ref) < TOL_F32 * 2
+
+
+def test_gemm_nt_matches_numpy():
+    import ctypes as C
+    from dpmn_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for (M, N, K) in ((1024, 96, 96), (200, 384, 96), (77, 96, 384)):
+        A = rng.standard_normal((M, K)).astype(np.float32)
+        Bm = rng.standard_normal((N, K)).astype(np.float32)
+        bias = rng.standard_normal(N).astype(np.float32)
+        a, b, bi = _t(A), _t(Bm), _t(bias)
+        c = torch.empty((M, N), device=DEV)
+        ws = torch.empty(256, dtype=torch.uint8, device=DEV)
+        rc = lib.dpmn_gemm_nt(a.data_ptr(), b.data_ptr(), bi.data_ptr(), c.data_ptr(), M, N, K, 0, ws.data_ptr(), 256,
+                              torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        ref = A.astype(np.float64) @ Bm.astype(np.float64).T + bias
+        assert rel_err(c.cpu().numpy(), ref) < 1e-6
+
+
+def test_library_was_the_thing_that_ran():
+    from dpmn_b200 import _lib
+    lib = _lib.load()
+    assert lib.dpmn_check_device() == 0
+    before = lib.dpmn_launch_count()
+    z, meta = load_golden("pgrm_w8")
+    cfg, P, x_q, x_kv, res = pgrm_case(meta)
+    m, _ = build_pgrm(meta, DEV)
+    with torch.no_grad():
+        m(_t(x_q), _t(x_kv), [])
+    assert lib.dpmn_launch_count() - before >= 20

@@ -63,3 +63,32 @@ def test_residual_zero_is_skipped():
     a = pgrm_oracle.pgrm_forward(P, x_q[:1], x_kv[:1], [r[:1] for r in res], windows=cfg.window_size)
     b = pgrm_oracle.pgrm_forward(P, x_q[:1], x_kv[:1], [r[:1] for r in res2], windows=cfg.window_size)
     assert np.array_equal(a, b)
+
+
+# ---- the torch-CPU restatement (the timed CPU baseline) is pinned against the same fixtures -------------
+def _torch_params(P):
+    import torch
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in P.items()}
+
+
+@pytest.mark.parametrize("name", PGRM_GOLDEN)
+def test_torch_port_pgrm_matches_reference(name):
+    import torch
+    from oracle import torch_ref
+    z, meta = load_golden(name)
+    cfg, P, x_q, x_kv, res = pgrm_case(meta)
+    with torch.no_grad():
+        y = torch_ref.pgrm_forward(_torch_params(P), torch.from_numpy(x_q), torch.from_numpy(x_kv),
+                                   [torch.from_numpy(r) for r in res], windows=cfg.window_size, num_heads=cfg.num_heads)
+    assert rel_err(y.numpy(), z["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", CMM_GOLDEN)
+def test_torch_port_cmm_matches_reference(name):
+    import torch
+    from oracle import torch_ref
+    z, meta = load_golden(name)
+    P, x1, x2 = cmm_case(meta)
+    with torch.no_grad():
+        y = torch_ref.cmm_forward(_torch_params(P), torch.from_numpy(x1), torch.from_numpy(x2), training=meta["train"])
+    assert rel_err(y.numpy(), z["out"]) < TOL

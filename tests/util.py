@@ -46,3 +46,34 @@ def cmm_case(meta):
 PGRM_GOLDEN = ["pgrm_i0_m0", "pgrm_i2_m0", "pgrm_i3_m1", "pgrm_i5_m1", "pgrm_w2", "pgrm_w4", "pgrm_w8",
                "pgrm_w16_c192", "pgrm_w48_c96_h4"]
 CMM_GOLDEN = ["cmm_c8_eval", "cmm_c8_train", "cmm_c64_eval"]
+
+
+# ---- builders of OUR modules from a golden fixture's meta (GPU tests, bench, smoke) --------------------
+def build_pgrm(meta, device="cuda", precision="fp32"):
+    import torch
+    from dpmn_b200 import PGRM
+    it = meta["iter"]
+    n = it + 1
+    m = PGRM(patch_size=[2] * n, embed_dim=[meta["embed"]] * n, depths=[1] * n, num_heads=[[meta["heads"]]] * n,
+             window_size=[list(meta["window"])] * n, mlp_ratio=[4.] * n, drop_rate=[0.1] * n,
+             attn_drop_rate=[0.1] * n, drop_path_rate=[0.1] * n, iter=it, mode=meta["mode"], hidden_size=3,
+             precision=precision)
+    cfg = PGRMConfig(embed_dim=meta["embed"], num_heads=meta["heads"], window_size=tuple(meta["window"]),
+                     iter=it, mode=meta["mode"])
+    P = synth_params(pgrm_schema(cfg), meta["seed"])
+    sd = m.state_dict()
+    m.load_state_dict({k: (torch.from_numpy(P[k]) if k in P else v) for k, v in sd.items()}, strict=True)
+    return m.to(device).eval(), P
+
+
+def build_cmm(meta, device="cuda", precision="fp32"):
+    import torch
+    from dpmn_b200 import ComplementationModulationModule
+    m = ComplementationModulationModule(cnum=meta["cnum"], precision=precision)
+    P = synth_params(cmm_schema(3, meta["cnum"]), meta["seed"])
+    sd = m.state_dict()
+    assert set(sd) == set(P)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(P[k])) for k in sd}, strict=True)
+    m = m.to(device)
+    m.train(bool(meta.get("train", False)))
+    return m, P

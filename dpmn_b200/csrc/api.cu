@@ -18,9 +18,9 @@ std::atomic<uint64_t> g_launches{0};
 // Optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream around every
 // kernel launch, tagged by kernel class.  Off by default; never active inside a timed throughput region.
 enum KTag { T_PATCH_EMBED = 0, T_LAYERNORM, T_GEMM, T_WINDOW_ATTN, T_SK_GATE, T_DWCONV, T_HEAD, T_CONV, T_BN,
-            T_SE_GATE, T_COUNT };
+            T_SE_GATE, T_CONVERT, T_GEMM_TC, T_COUNT };
 const char* const kTagNames[T_COUNT] = {"patch_embed", "layernorm", "gemm", "window_attn", "sk_gate",
-                                        "dwconv", "head", "conv", "bn_affine", "se_gate"};
+                                        "dwconv", "head", "conv", "bn_affine", "se_gate", "convert", "gemm_tc"};
 struct ProfRec { int tag; int n; cudaEvent_t e0, e1; };
 bool g_prof = false;
 std::mutex g_prof_mu;
@@ -391,18 +391,34 @@ int dpmn_window_attn_forward(const void* q, const void* kv, void* out, const flo
   return 0;
 }
 
-size_t dpmn_gemm_nt_workspace_bytes(int32_t, int32_t, int32_t, int32_t) { return 256; }
+size_t dpmn_gemm_nt_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t precision) {
+  if (precision == DPMN_PREC_F32) return 256;
+  return ((size_t)M * K + (size_t)N * K) * 2 + 1024;
+}
 
 int dpmn_gemm_nt(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
                  int32_t precision, void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   if (!A || !B || !C || M < 1 || N < 1 || K < 1) return DPMN_E_ARG;
-  if (precision != DPMN_PREC_F32) return DPMN_E_UNSUPPORTED;
-  GemmSimtArgs g;
-  g.A = A; g.lda = K; g.Bm = B; g.ldb = K; g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K;
-  g.bias = bias; g.bias_mode = bias ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
-  DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+  if (precision == DPMN_PREC_F32) {
+    GemmSimtArgs g;
+    g.A = A; g.lda = K; g.Bm = B; g.ldb = K; g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K;
+    g.bias = bias; g.bias_mode = bias ? 1 : 0;
+    DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+    return 0;
+  }
+  if (precision != DPMN_PREC_F16 && precision != DPMN_PREC_BF16) return DPMN_E_ARG;
+  if (!workspace || workspace_bytes < dpmn_gemm_nt_workspace_bytes(M, N, K, precision)) return DPMN_E_WORKSPACE;
+  const DType t = (DType)precision;
+  Bump b(workspace, workspace_bytes);
+  uint16_t* a16 = b.take<uint16_t>((size_t)M * K);
+  uint16_t* b16 = b.take<uint16_t>((size_t)N * K);
+  DPMN_RUN(T_CONVERT, launch_convert(A, a16, t, (long long)M * K, st), 1);
+  DPMN_RUN(T_CONVERT, launch_convert(B, b16, t, (long long)N * K, st), 1);
+  GemmTcArgs g;
+  g.A = a16; g.lda = K; g.Bm = b16; g.ldb = K; g.op_type = t; g.C = C; g.ldc = N; g.out_type = DT_F32;
+  g.M = M; g.N = N; g.K = K; g.bias = bias; g.bias_mode = bias ? 1 : 0;
+  DPMN_RUN(T_GEMM_TC, launch_gemm_tc(g, st), 1);
   return 0;
 }
 

@@ -1,0 +1,327 @@
+// tcgen05 GEMM for sm_100a:  C[z][m, n] = epi( sum_k A[z][m, k] * B[z][n, k] )
+//
+// Both operands are K-contiguous 16-bit (fp16 or bf16) matrices in HBM.  Persistent, warp-specialised:
+//   warp 0   TMA producer: 128 x 64 (A) and BN x 64 (B) boxes, 128B-swizzled, 4-stage mbarrier ring
+//   warp 1   MMA issuer: one thread issues tcgen05.mma (M = 128, N = BN, K = 16) into a TMEM accumulator;
+//            two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns), bias / GELU / residual / column-sum, 16-byte stores
+// Every nn.Linear and the 1x1 conv of the PGRM (pgrm.py:30,37,39,82,188,194) run through this kernel in the
+// fp16 / bf16 modes.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace dpmn {
+
+using namespace tc;
+
+constexpr int TBM = 128;       // tile rows (UMMA M)
+constexpr int TBK = 64;        // k-block: 64 x 16-bit = one 128-byte swizzle row
+constexpr int TSTAGES = 4;
+constexpr int TC_THREADS = 192;
+
+struct GemmTcParams {
+  int M, N, K, batch;
+  int m_tiles, n_tiles;
+  int a_zmul, b_zmul;            // 0 when the operand is shared by every batch entry (weights)
+  int fmt;                       // 0 fp16, 1 bf16 (operands)
+  int out_type;                  // DType of C
+  void* C; long long c_bs; int ldc;
+  const float* bias; long long bias_bs; int bias_mode;   // 0 none, 1 per n, 2 per m
+  int act;                       // 0 none, 1 GELU
+  const float* residual;         // fp32, indexed like C (may alias C when C is fp32)
+  float* colsum;                 // if set: no C store; colsum[z][m_tile*4 + quarter][n] = sum over 32 rows
+};
+
+template <int BN>
+struct TcSmem {
+  static constexpr int A_BYTES = TBM * TBK * 2;
+  static constexpr int B_BYTES = BN * TBK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = TSTAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, typename OutT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  using S = TcSmem<BN>;
+  uint8_t* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TSTAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = bars;                    // [TSTAGES]
+  uint64_t* empty_bar = bars + TSTAGES;         // [TSTAGES]
+  uint64_t* tmem_full = bars + 2 * TSTAGES;     // [2]
+  uint64_t* tmem_empty = bars + 2 * TSTAGES + 2;// [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TSTAGES + 4);
+
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (p.K + TBK - 1) / TBK;
+  const int total_tiles = p.batch * p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < TSTAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_blk = t % p.n_tiles;
+        const int m_blk = (t / p.n_tiles) % p.m_tiles;
+        const int z = t / (p.n_tiles * p.m_tiles);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          tma_load_3d(sa, &map_a, &full_bar[stage], kb * TBK, m_blk * TBM, z * p.a_zmul);
+          tma_load_3d(sb, &map_b, &full_bar[stage], kb * TBK, n_blk * BN, z * p.b_zmul);
+          if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(p.fmt, TBM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + stage * S::STAGE_BYTES);
+          const uint64_t da = make_smem_desc_sw128(sa);
+          const uint64_t db = make_smem_desc_sw128(sa + S::A_BYTES);
+          const int k_left = p.K - kb * TBK;
+          const int ksteps = k_left >= TBK ? TBK / 16 : (k_left + 15) / 16;
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16(d_tmem, advance_desc_k(da, k), advance_desc_k(db, k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);            // frees the smem stage once these MMAs have read it
+          if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int n_blk = t % p.n_tiles;
+      const int m_blk = (t / p.n_tiles) % p.m_tiles;
+      const int z = t / (p.n_tiles * p.m_tiles);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int m = m_blk * TBM + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      const float* bias = p.bias ? p.bias + (long long)z * p.bias_bs : nullptr;
+      const float bias_m = (p.bias_mode == 2 && row_ok) ? bias[m] : 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_m;
+        if (p.bias_mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + j < p.N) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias + n0 + j);
+              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+            }
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (p.colsum != nullptr) {
+          // butterfly transpose-reduce over the warp's 32 rows: lane l ends with the sum of column l
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = row_ok ? v[j] : 0.f;
+#pragma unroll
+          for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+            for (int i = 0; i < s; ++i) {
+              const bool up = (lane & s) != 0;
+              const float send = up ? v[i] : v[i + s];
+              const float keep = up ? v[i + s] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+            }
+          }
+          if (n0 + lane < p.N)
+            p.colsum[((long long)z * (p.m_tiles * 4) + m_blk * 4 + quarter) * p.N + n0 + lane] = v[0];
+          continue;
+        }
+        if (!row_ok) continue;
+        const long long off = (long long)z * p.c_bs + (long long)m * p.ldc + n0;
+        if (p.residual != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + j < p.N) {
+              const float4 rr = *reinterpret_cast<const float4*>(p.residual + off + j);
+              v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
+            }
+          }
+        }
+        if constexpr (sizeof(OutT) == 4) {
+          float* dst = reinterpret_cast<float*>(p.C) + off;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (n0 + j < p.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          OutT* dst = reinterpret_cast<OutT*>(p.C) + off;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (n0 + j < p.N) {
+              union { uint4 u; OutT h[8]; } pk;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pk.h[e] = from_f32<OutT>(v[j + e]);
+              *reinterpret_cast<uint4*>(dst + j) = pk.u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  return fn;
+}
+
+int make_tensor_map_16bit(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return -4;
+  cuuint64_t gdims[5]; cuuint64_t gstr[4]; cuuint32_t gbox[5]; cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) { gdims[i] = dims[i]; gbox[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  // fp16 and bf16 move identically through TMA; the element type only matters for OOB fill (zeros either way)
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1000 + (int)r;
+}
+
+static int g_num_sms = 0;
+
+template <int BN, typename OutT>
+static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st) {
+  CUtensorMap map_a, map_b;
+  {
+    const bool batched = a.batch > 1 && a.a_bs != 0;
+    const uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.M, (uint64_t)(batched ? a.batch : 1)};
+    const uint64_t str[2] = {(uint64_t)a.lda * 2, (uint64_t)(batched ? a.a_bs : (long long)a.M * a.lda) * 2};
+    const uint32_t box[3] = {TBK, TBM, 1};
+    int rc = make_tensor_map_16bit(&map_a, a.A, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    const bool batched = a.batch > 1 && a.b_bs != 0;
+    const uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.N, (uint64_t)(batched ? a.batch : 1)};
+    const uint64_t str[2] = {(uint64_t)a.ldb * 2, (uint64_t)(batched ? a.b_bs : (long long)a.N * a.ldb) * 2};
+    const uint32_t box[3] = {TBK, BN, 1};
+    int rc = make_tensor_map_16bit(&map_b, a.Bm, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  GemmTcParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.batch = a.batch;
+  p.m_tiles = (a.M + TBM - 1) / TBM; p.n_tiles = (a.N + BN - 1) / BN;
+  p.a_zmul = (a.batch > 1 && a.a_bs != 0) ? 1 : 0; p.b_zmul = (a.batch > 1 && a.b_bs != 0) ? 1 : 0;
+  p.fmt = a.op_type == DT_BF16 ? 1 : 0; p.out_type = a.out_type;
+  p.C = a.C; p.c_bs = a.c_bs; p.ldc = a.ldc;
+  p.bias = a.bias; p.bias_bs = a.bias_bs; p.bias_mode = a.bias ? a.bias_mode : 0;
+  p.act = a.act; p.residual = a.residual; p.colsum = a.colsum;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    DPMN_CUDA_TRY(cudaGetDevice(&dev));
+    DPMN_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int total = p.batch * p.m_tiles * p.n_tiles;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  auto kern = gemm_tc_kernel<BN, OutT>;
+  constexpr int smem = TcSmem<BN>::TOTAL;
+  static bool attr_set = false;   // per template instantiation
+  if (!attr_set) {
+    DPMN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  kern<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename OutT>
+static int launch_tc_out(const GemmTcArgs& a, cudaStream_t st) {
+  // N tile: the largest of {256, 192, 128, 96, 64, 32} that divides N (fewest wasted columns), else 128 with a tail
+  const int N = a.N;
+  if (N % 256 == 0) return launch_tc_bn<256, OutT>(a, st);
+  if (N % 192 == 0) return launch_tc_bn<192, OutT>(a, st);
+  if (N % 128 == 0) return launch_tc_bn<128, OutT>(a, st);
+  if (N % 96 == 0) return launch_tc_bn<96, OutT>(a, st);
+  if (N % 64 == 0) return launch_tc_bn<64, OutT>(a, st);
+  if (N % 32 == 0) return launch_tc_bn<32, OutT>(a, st);
+  return launch_tc_bn<128, OutT>(a, st);
+}
+
+int launch_gemm_tc(const GemmTcArgs& a, cudaStream_t st) {
+  if (a.op_type != DT_F16 && a.op_type != DT_BF16) return -1;
+  if (a.K % 16 || a.lda % 8 || a.ldb % 8) return -2;                 // 16-byte TMA strides, whole UMMA k-steps
+  if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.Bm)) & 15) return -2;
+  if (a.batch > 1 && ((a.a_bs % 8) || (a.b_bs % 8))) return -2;
+  if (a.colsum == nullptr) {
+    if (a.N % 8 || a.ldc % 8 || (reinterpret_cast<uintptr_t>(a.C) & 15)) return -2;   // 16-byte stores
+  }
+  switch (a.out_type) {
+    case DT_F32: return launch_tc_out<float>(a, st);
+    case DT_F16: return launch_tc_out<__half>(a, st);
+    case DT_BF16: return launch_tc_out<__nv_bfloat16>(a, st);
+  }
+  return -1;
+}
+
+}  // namespace dpmn

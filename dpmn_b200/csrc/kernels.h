@@ -34,6 +34,23 @@ struct GemmSimtArgs {
 int launch_gemm_simt(const GemmSimtArgs& a, cudaStream_t st);
 static constexpr int kSimtTileM = 64;
 
+// tcgen05 GEMM (gemm_tc.cu): same contraction with 16-bit K-contiguous operands (fp16 / bf16), fp32
+// accumulation in TMEM.  a_bs / b_bs == 0 with batch > 1 means the operand is shared by all batch entries.
+// colsum layout: colsum[z][m_tile(128 rows) * 4 + quarter][n].
+struct GemmTcArgs {
+  const void* A = nullptr; long long a_bs = 0; int lda = 0;
+  const void* Bm = nullptr; long long b_bs = 0; int ldb = 0;
+  DType op_type = DT_F16;
+  void* C = nullptr; long long c_bs = 0; int ldc = 0; DType out_type = DT_F32;
+  int M = 0, N = 0, K = 0, batch = 1;
+  const float* bias = nullptr; long long bias_bs = 0; int bias_mode = 0;
+  int act = 0;
+  const float* residual = nullptr;
+  float* colsum = nullptr;
+};
+int launch_gemm_tc(const GemmTcArgs& a, cudaStream_t st);
+static constexpr int kTcTileM = 128;
+
 // Windowed attention core, SIMT (any precision of q/kv/out storage).  q (B,L,*) and kv (B,L,*) in token
 // order with row strides q_ld / kv_ld (elements); K channels start at column 0 of a kv row, V channels
 // at column v_off.  out (B,L,C) window-major rows per group (quirk 1, pgrm.py:249,263).

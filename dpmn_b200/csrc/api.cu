@@ -67,28 +67,72 @@ struct Bump {
   bool ok() const { return off <= cap; }
 };
 
+// One contraction of the PGRM, dispatched on the arithmetic mode: fp32 FFMA tiles or tcgen05 (16-bit operands).
+struct GemmCall {
+  const void* A = nullptr; long long a_bs = 0; int lda = 0;
+  const void* Bm = nullptr; long long b_bs = 0; int ldb = 0;
+  void* C = nullptr; long long c_bs = 0; int ldc = 0; DType out_type = DT_F32;
+  int M = 0, N = 0, K = 0, batch = 1;
+  const float* bias = nullptr; long long bias_bs = 0; int bias_mode = 0;
+  int act = 0;
+  const float* residual = nullptr;
+  float* colsum = nullptr;
+};
+
+int run_gemm(int precision, const GemmCall& c, cudaStream_t st) {
+  if (precision == DPMN_PREC_F32) {
+    GemmSimtArgs g;
+    g.A = (const float*)c.A; g.a_bs = c.a_bs; g.lda = c.lda; g.Bm = (const float*)c.Bm; g.b_bs = c.b_bs; g.ldb = c.ldb;
+    g.C = (float*)c.C; g.c_bs = c.c_bs; g.ldc = c.ldc; g.M = c.M; g.N = c.N; g.K = c.K; g.batch = c.batch;
+    g.bias = c.bias; g.bias_bs = c.bias_bs; g.bias_mode = c.bias_mode; g.act = c.act; g.residual = c.residual;
+    g.colsum = c.colsum;
+    return launch_gemm_simt(g, st);
+  }
+  GemmTcArgs g;
+  g.A = c.A; g.a_bs = c.a_bs; g.lda = c.lda; g.Bm = c.Bm; g.b_bs = c.b_bs; g.ldb = c.ldb; g.op_type = (DType)precision;
+  g.C = c.C; g.c_bs = c.c_bs; g.ldc = c.ldc; g.out_type = c.out_type; g.M = c.M; g.N = c.N; g.K = c.K; g.batch = c.batch;
+  g.bias = c.bias; g.bias_bs = c.bias_bs; g.bias_mode = c.bias_mode; g.act = c.act; g.residual = c.residual;
+  g.colsum = c.colsum;
+  return launch_gemm_tc(g, st);
+}
+
+// weights of one block as the contraction kernels read them: the fp32 tensors themselves (F32 mode) or
+// 16-bit copies staged in the workspace (tensor-core modes)
+struct BlockOperands { const void *q_w, *kv_w, *sk_proj_w, *fc1_w, *fc2_w, *pw_w; };
+
 struct PgrmWs {
-  float *tq, *tkv, *ln, *q, *kv, *attn, *colsum, *wb, *bias_b, *h, *dt, *t1;
+  float *tq, *tkv, *colsum, *bias_b, *t1;
+  void *ln, *q, *kv, *attn, *wb, *h, *dt;      // activation-typed (fp32 or 16-bit)
+  void* w16[DPMN_MAX_BLOCKS][6];               // 16-bit weight copies (tensor-core modes)
   size_t bytes;
 };
 
 PgrmWs carve_pgrm(const dpmn_pgrm_desc* d, void* ws) {
   const size_t B = d->batch, C = d->embed_dim, hid = d->mlp_hidden;
   const size_t L = (size_t)(d->img_h / d->patch) * (d->img_w / d->patch);
+  const size_t es = d->precision == DPMN_PREC_F32 ? 4 : 2;
+  const size_t col_tiles = d->precision == DPMN_PREC_F32 ? (L + kSimtTileM - 1) / kSimtTileM
+                                                          : ((L + kTcTileM - 1) / kTcTileM) * 4;
   Bump b(ws, (size_t)-1);
   PgrmWs w;
+  memset(&w, 0, sizeof(w));
   w.tq = b.take<float>(B * L * C);
   w.tkv = b.take<float>(B * L * C);
-  w.ln = b.take<float>(B * L * C);
-  w.q = b.take<float>(B * L * C);
-  w.kv = b.take<float>(B * L * 2 * C);
-  w.attn = b.take<float>(B * L * C);
-  w.colsum = b.take<float>(B * ((L + kSimtTileM - 1) / kSimtTileM) * C);
-  w.wb = b.take<float>(B * C * C);
+  w.ln = b.take<char>(B * L * C * es);
+  w.q = b.take<char>(B * L * C * es);
+  w.kv = b.take<char>(B * L * 2 * C * es);
+  w.attn = b.take<char>(B * L * C * es);
+  w.colsum = b.take<float>(B * col_tiles * C);
+  w.wb = b.take<char>(B * C * C * es);
   w.bias_b = b.take<float>(B * C);
-  w.h = b.take<float>(B * L * hid);
-  w.dt = b.take<float>(B * L * hid);
+  w.h = b.take<char>(B * L * hid * es);
+  w.dt = b.take<char>(B * L * hid * es);
   w.t1 = b.take<float>(B * L * 16);
+  if (d->precision != DPMN_PREC_F32) {
+    const size_t n[6] = {C * C, 2 * C * C, C * C, hid * C, C * hid, hid * hid};
+    for (int blk = 0; blk < DPMN_MAX_BLOCKS; ++blk)
+      for (int i = 0; i < 6; ++i) w.w16[blk][i] = b.take<char>(n[i] * 2);
+  }
   w.bytes = b.off + 256;
   return w;
 }
@@ -102,7 +146,7 @@ int check_pgrm(const dpmn_pgrm_desc* d) {
   if (d->q_chans != 2 && d->q_chans != 3) return DPMN_E_ARG;
   if (d->q_chans == 2 && (!d->prior_fusion_w || !d->prior_fusion_b)) return DPMN_E_ARG;
   if (d->n_mix < 1 || d->n_mix > DPMN_MAX_MIX) return DPMN_E_ARG;
-  if (d->precision != DPMN_PREC_F32) return DPMN_E_UNSUPPORTED;
+  if (d->precision < DPMN_PREC_F32 || d->precision > DPMN_PREC_BF16) return DPMN_E_ARG;
   const int H = d->img_h / d->patch, W = d->img_w / d->patch;
   const int mn = H < W ? H : W;
   for (int g = 0; g < d->n_groups; ++g) {
@@ -125,12 +169,37 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
   if (workspace_bytes < w.bytes) return DPMN_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
 
+  const int prec = d->precision;
+  const DType at = (DType)prec;                       // storage type of the intermediate activations
+  const int gtag = prec == DPMN_PREC_F32 ? T_GEMM : T_GEMM_TC;
   const int B = d->batch, C = d->embed_dim, hid = d->mlp_hidden, G = d->n_groups;
   const int H = d->img_h / d->patch, W = d->img_w / d->patch, L = H * W;
   const int rows = B * L;
   const long long plane = (long long)d->img_h * d->img_w;
   const long long xq_bs = d->x_q_batch_stride ? d->x_q_batch_stride : (long long)d->q_chans * plane;
   const long long xkv_bs = d->x_kv_batch_stride ? d->x_kv_batch_stride : 3LL * plane;
+
+  // operands of the contractions: fp32 weights in place, or 16-bit copies made now (one launch)
+  BlockOperands ops[DPMN_MAX_BLOCKS];
+  if (prec == DPMN_PREC_F32) {
+    for (int blk = 0; blk < DPMN_MAX_BLOCKS; ++blk) {
+      const dpmn_block_weights& bw = d->blocks[blk];
+      ops[blk] = BlockOperands{bw.q_w, bw.kv_w, bw.sk_proj_w, bw.fc1_w, bw.fc2_w, bw.pw_w};
+    }
+  } else {
+    ConvertBatch cb;
+    const long long n[6] = {(long long)C * C, 2LL * C * C, (long long)C * C, (long long)hid * C, (long long)C * hid,
+                            (long long)hid * hid};
+    for (int blk = 0; blk < DPMN_MAX_BLOCKS; ++blk) {
+      const dpmn_block_weights& bw = d->blocks[blk];
+      const float* src[6] = {bw.q_w, bw.kv_w, bw.sk_proj_w, bw.fc1_w, bw.fc2_w, bw.pw_w};
+      for (int i = 0; i < 6; ++i) {
+        cb.src[cb.count] = src[i]; cb.dst[cb.count] = w.w16[blk][i]; cb.n[cb.count] = n[i]; ++cb.count;
+      }
+      ops[blk] = BlockOperands{w.w16[blk][0], w.w16[blk][1], w.w16[blk][2], w.w16[blk][3], w.w16[blk][4], w.w16[blk][5]};
+    }
+    DPMN_RUN(T_CONVERT, launch_convert_batch(cb, at, st), 1);
+  }
 
   // K0: both streams share the patch-embed weights (pgrm.py:549-550)
   DPMN_RUN(T_PATCH_EMBED, launch_patch_embed(x_q, xq_bs, d->q_chans, d->q_chans == 2 ? d->prior_fusion_w : nullptr,
@@ -141,25 +210,26 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
 
   for (int blk = 0; blk < DPMN_MAX_BLOCKS; ++blk) {
     const dpmn_block_weights& bw = d->blocks[blk];
+    const BlockOperands& op = ops[blk];
     // ---- K1: LayerNorms + q / kv projections (pgrm.py:322-323,188,194)
-    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tq, bw.norm1_q_w, bw.norm1_q_b, w.ln, DT_F32, rows, C, st), 1);
+    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tq, bw.norm1_q_w, bw.norm1_q_b, w.ln, at, rows, C, st), 1);
     {
-      GemmSimtArgs g;
-      g.A = w.ln; g.lda = C; g.Bm = bw.q_w; g.ldb = C; g.C = w.q; g.ldc = C;
+      GemmCall g;
+      g.A = w.ln; g.lda = C; g.Bm = op.q_w; g.ldb = C; g.C = w.q; g.ldc = C; g.out_type = at;
       g.M = rows; g.N = C; g.K = C; g.bias = bw.q_b; g.bias_mode = 1;
-      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+      DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
     }
-    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm1_kv_w, bw.norm1_kv_b, w.ln, DT_F32, rows, C, st), 1);
+    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm1_kv_w, bw.norm1_kv_b, w.ln, at, rows, C, st), 1);
     {
-      GemmSimtArgs g;
-      g.A = w.ln; g.lda = C; g.Bm = bw.kv_w; g.ldb = C; g.C = w.kv; g.ldc = 2 * C;
+      GemmCall g;
+      g.A = w.ln; g.lda = C; g.Bm = op.kv_w; g.ldb = C; g.C = w.kv; g.ldc = 2 * C; g.out_type = at;
       g.M = rows; g.N = 2 * C; g.K = C; g.bias = bw.kv_b; g.bias_mode = 1;
-      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+      DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
     }
     // ---- K2: windowed attention core (pgrm.py:197-268)
     {
       AttnArgs a;
-      a.q = w.q; a.kv = w.kv; a.out = w.attn; a.io_type = DT_F32;
+      a.q = w.q; a.kv = w.kv; a.out = w.attn; a.io_type = at;
       a.q_ld = C; a.kv_ld = 2 * C; a.v_off = C; a.out_ld = C;
       a.B = B; a.H = H; a.W = W; a.C = C; a.n_groups = G; a.heads_per_group = d->num_heads / G;
       const int mn = H < W ? H : W;
@@ -170,48 +240,53 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
       }
       DPMN_RUN(T_WINDOW_ATTN, launch_window_attn_simt(a, st), G);
     }
-    if (attn_core && attn_core[blk])
-      DPMN_CUDA_TRY(cudaMemcpyAsync(attn_core[blk], w.attn, (size_t)rows * C * sizeof(float),
-                                    cudaMemcpyDeviceToDevice, st));
+    if (attn_core && attn_core[blk]) {
+      if (prec == DPMN_PREC_F32) {
+        DPMN_CUDA_TRY(cudaMemcpyAsync(attn_core[blk], w.attn, (size_t)rows * C * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, st));
+      } else {
+        DPMN_RUN(T_CONVERT, launch_widen(w.attn, at, attn_core[blk], (long long)rows * C, st), 1);
+      }
+    }
     // ---- K3: SK gate (pgrm.py:79-96): pass 1 pooled GELU(proj), fold, pass 2 per-image GEMM + residual
-    const int tiles = (L + kSimtTileM - 1) / kSimtTileM;
+    const int tiles = prec == DPMN_PREC_F32 ? (L + kSimtTileM - 1) / kSimtTileM : ((L + kTcTileM - 1) / kTcTileM) * 4;
     {
-      GemmSimtArgs g;
-      g.A = w.attn; g.a_bs = (long long)L * C; g.lda = C; g.Bm = bw.sk_proj_w; g.ldb = C;
+      GemmCall g;
+      g.A = w.attn; g.a_bs = (long long)L * C; g.lda = C; g.Bm = op.sk_proj_w; g.ldb = C;
       g.M = L; g.N = C; g.K = C; g.batch = B; g.bias = bw.sk_proj_b; g.bias_mode = 1; g.act = 1;
       g.colsum = w.colsum;
-      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+      DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
     }
     DPMN_RUN(T_SK_GATE, launch_sk_gate(w.colsum, tiles, L, bw.sk_proj_w, bw.sk_proj_b, bw.sk_fc1_w, bw.sk_fc1_b, bw.sk_fc2_w,
-                            bw.sk_fc2_b, bw.sk_head_w, bw.sk_head_b, w.wb, DT_F32, w.bias_b, B, C, G, st), 1);
+                            bw.sk_fc2_b, bw.sk_head_w, bw.sk_head_b, w.wb, at, w.bias_b, B, C, G, st), 1);
     {
-      GemmSimtArgs g;   // x_kv = shortcut + attn (pgrm.py:329), in place on the kv stream
+      GemmCall g;   // x_kv = shortcut + attn (pgrm.py:329), in place on the fp32 kv stream
       g.A = w.attn; g.a_bs = (long long)L * C; g.lda = C; g.Bm = w.wb; g.b_bs = (long long)C * C; g.ldb = C;
-      g.C = w.tkv; g.c_bs = (long long)L * C; g.ldc = C; g.M = L; g.N = C; g.K = C; g.batch = B;
+      g.C = w.tkv; g.c_bs = (long long)L * C; g.ldc = C; g.out_type = DT_F32; g.M = L; g.N = C; g.K = C; g.batch = B;
       g.bias = w.bias_b; g.bias_bs = C; g.bias_mode = 1; g.residual = w.tkv;
-      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+      DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
     }
     // ---- K4: norm2 + Mlp (pgrm.py:330, 29-41)
-    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm2_w, bw.norm2_b, w.ln, DT_F32, rows, C, st), 1);
+    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm2_w, bw.norm2_b, w.ln, at, rows, C, st), 1);
     {
-      GemmSimtArgs g;   // fc1 + GELU
-      g.A = w.ln; g.lda = C; g.Bm = bw.fc1_w; g.ldb = C; g.C = w.h; g.ldc = hid;
+      GemmCall g;   // fc1 + GELU
+      g.A = w.ln; g.lda = C; g.Bm = op.fc1_w; g.ldb = C; g.C = w.h; g.ldc = hid; g.out_type = at;
       g.M = rows; g.N = hid; g.K = C; g.bias = bw.fc1_b; g.bias_mode = 1; g.act = 1;
-      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+      DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
     }
-    DPMN_RUN(T_DWCONV, launch_dwconv(w.h, w.dt, DT_F32, bw.dw_w, bw.dw_b, B, L, hid, st), 1);
+    DPMN_RUN(T_DWCONV, launch_dwconv(w.h, w.dt, at, bw.dw_w, bw.dw_b, B, L, hid, st), 1);
     {
-      GemmSimtArgs g;   // pointwise conv: per image (hid x hid) * (hid x L), written (hid, L) = the raw view
-      g.A = bw.pw_w; g.lda = hid; g.Bm = w.dt; g.b_bs = (long long)L * hid; g.ldb = hid;
-      g.C = w.h; g.c_bs = (long long)L * hid; g.ldc = L; g.M = hid; g.N = L; g.K = hid; g.batch = B;
+      GemmCall g;   // pointwise conv: per image (hid x hid) * (hid x L), written (hid, L) = the raw view
+      g.A = op.pw_w; g.lda = hid; g.Bm = w.dt; g.b_bs = (long long)L * hid; g.ldb = hid;
+      g.C = w.h; g.c_bs = (long long)L * hid; g.ldc = L; g.out_type = at; g.M = hid; g.N = L; g.K = hid; g.batch = B;
       g.bias = bw.pw_b; g.bias_mode = 2;
-      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+      DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
     }
     {
-      GemmSimtArgs g;   // fc2 on the raw (L, hid) view + residual, in place on the kv stream
-      g.A = w.h; g.lda = hid; g.Bm = bw.fc2_w; g.ldb = hid; g.C = w.tkv; g.ldc = C;
+      GemmCall g;   // fc2 on the raw (L, hid) view + residual, in place on the fp32 kv stream
+      g.A = w.h; g.lda = hid; g.Bm = op.fc2_w; g.ldb = hid; g.C = w.tkv; g.ldc = C; g.out_type = DT_F32;
       g.M = rows; g.N = C; g.K = hid; g.bias = bw.fc2_b; g.bias_mode = 1; g.residual = w.tkv;
-      DPMN_RUN(T_GEMM, launch_gemm_simt(g, st), 1);
+      DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
     }
     if (block_out && block_out[blk])
       DPMN_CUDA_TRY(cudaMemcpyAsync(block_out[blk], w.tkv, (size_t)rows * C * sizeof(float),

@@ -91,6 +91,17 @@ int launch_head_conv2_mix(const float* t1, const float* w, const float* b, float
 // fp32 -> 16-bit conversion of n elements (weights staging for the tensor-core path).
 int launch_convert(const float* src, void* dst, DType dst_type, long long n, cudaStream_t st);
 
+// Several fp32 -> 16-bit conversions in ONE launch (all weights of a PGRM for the tensor-core modes).
+struct ConvertBatch {
+  int count = 0;
+  const float* src[16] = {};
+  void* dst[16] = {};
+  long long n[16] = {};
+};
+int launch_convert_batch(const ConvertBatch& cb, DType dst_type, cudaStream_t st);
+// 16-bit -> fp32 (probe outputs).
+int launch_widen(const void* src, DType src_type, float* dst, long long n, cudaStream_t st);
+
 // ---- CMM SIMT kernels (cmm_simt.cu) ------------------------------------------------------------------
 
 // Implicit-GEMM convolution / transposed convolution on NCHW fp32.  The input is the channel-wise

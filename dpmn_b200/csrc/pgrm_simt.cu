@@ -777,4 +777,40 @@ int launch_convert(const float* src, void* dst, DType dst_type, long long n, cud
   return 0;
 }
 
+template <typename T>
+__global__ void convert_batch_kernel(ConvertBatch cb) {
+  const int seg = blockIdx.y;
+  const float* __restrict__ src = cb.src[seg];
+  T* __restrict__ dst = reinterpret_cast<T*>(cb.dst[seg]);
+  const long long n = cb.n[seg];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = from_f32<T>(src[i]);
+}
+
+int launch_convert_batch(const ConvertBatch& cb, DType dst_type, cudaStream_t st) {
+  if (cb.count < 1 || cb.count > 16) return -1;
+  dim3 grid(64, cb.count);
+  if (dst_type == DT_F16) convert_batch_kernel<__half><<<grid, 256, 0, st>>>(cb);
+  else if (dst_type == DT_BF16) convert_batch_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(cb);
+  else return -1;
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+__global__ void widen_kernel(const T* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = to_f32<T>(src[i]);
+}
+
+int launch_widen(const void* src, DType src_type, float* dst, long long n, cudaStream_t st) {
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (src_type == DT_F16) widen_kernel<__half><<<(int)blocks, 256, 0, st>>>((const __half*)src, dst, n);
+  else if (src_type == DT_BF16) widen_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)src, dst, n);
+  else return -1;
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace dpmn

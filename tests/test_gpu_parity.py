@@ -195,3 +195,47 @@ def test_library_was_the_thing_that_ran():
     with torch.no_grad():
         m(_t(x_q), _t(x_kv), [])
     assert lib.dpmn_launch_count() - before >= 20
+
+
+# ---- tensor-core modes (tcgen05, 16-bit operands, fp32 accumulate) --------------------------------------
+TOL_F16 = 1e-3     # BASELINE.json north_star: "within 1e-3 rel fp16"
+TOL_BF16 = 8e-3    # bf16 carries 8 mantissa bits (3 fewer than fp16); reported, not the headline mode
+
+
+@pytest.mark.parametrize("prec,tol", [("fp16", TOL_F16), ("bf16", TOL_BF16)])
+@pytest.mark.parametrize("name", ["pgrm_i0_m0", "pgrm_i2_m0", "pgrm_i5_m1", "pgrm_w16_c192", "pgrm_w48_c96_h4"])
+def test_pgrm_tensor_core_modes_match_reference(name, prec, tol):
+    z, meta = load_golden(name)
+    cfg, P, x_q, x_kv, res = pgrm_case(meta)
+    m, _ = build_pgrm(meta, DEV, precision=prec)
+    with torch.no_grad():
+        y, cores, blocks = m.forward_probe(_t(x_q), _t(x_kv), [_t(r) for r in res])
+    e = rel_err(y.cpu().numpy(), z["out"])
+    extra = ""
+    if "attn_core_b0" in z.files:
+        extra = " | " + ", ".join(f"{k} {rel_err(t[:1].cpu().numpy(), z[k]):.2e}" for k, t in
+                                  (("attn_core_b0", cores[0]), ("block0_out", blocks[0]),
+                                   ("attn_core_b1", cores[1]), ("block1_out", blocks[1])))
+    print(f"{name} [{prec}]: rel err {e:.3e}{extra}")
+    assert e < tol, e
+
+
+@pytest.mark.parametrize("prec", [1, 2])
+def test_gemm_nt_tensor_core_matches_rounded_operands(prec):
+    import ctypes as C
+    from dpmn_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    tt = torch.float16 if prec == 1 else torch.bfloat16
+    for (M, N, K) in ((1024, 96, 96), (384, 1024, 384), (200, 96, 384), (77, 200, 48)):
+        a = _t(rng.standard_normal((M, K)).astype(np.float32))
+        b = _t(rng.standard_normal((N, K)).astype(np.float32))
+        bi = _t(rng.standard_normal(N).astype(np.float32))
+        c = torch.empty((M, N), device=DEV)
+        nb = lib.dpmn_gemm_nt_workspace_bytes(M, N, K, prec)
+        ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+        rc = lib.dpmn_gemm_nt(a.data_ptr(), b.data_ptr(), bi.data_ptr(), c.data_ptr(), M, N, K, prec, ws.data_ptr(), nb,
+                              torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        ref = a.to(tt).double() @ b.to(tt).double().T + bi.double()
+        assert rel_err(c.cpu().numpy(), ref.cpu().numpy()) < 2e-6   # fp32 accumulation of exactly-rounded operands

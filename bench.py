@@ -33,9 +33,10 @@ WORKLOAD = "DPMN hot path forward: 6xPGRM cascade (b1=b2=3, win 2/4/8, dim 96, 6
            "batch 48/GPU, synthetic PSN output + priors (configs[1] without the frozen TATT backbone)"
 
 # algorithmic FLOPs per image (2*MAC, matmul/conv only; SURVEY.md 8d / BASELINE.md section 3)
-FLOPS_IMG = {"gemm": 6 * 2 * (56_623_104 + 25_165_824 + 460_062_720 - 7_077_888),   # q/kv + SK proj(+fold) + Mlp GEMMs
+_PGRM_GEMM = 6 * 2 * (56_623_104 + 25_165_824 + 460_062_720 - 7_077_888)   # q/kv + SK proj + Mlp GEMMs (dw conv excluded)
+FLOPS_IMG = {"gemm": _PGRM_GEMM, "gemm_tc": _PGRM_GEMM,
              "window_attn": 6 * 2 * 11_010_048,
-             "conv": 4_459_069_440,
+             "conv": 4_459_069_440, "conv_tc": 4_459_069_440 - 14_155_776 * 2 - 42_467_328,   # minus stem / de_1 (own kernels)
              "total": 11_267_776_512}
 
 
@@ -56,6 +57,13 @@ def synth_weights(seed):
     pg = [synth_params(pgrm_schema(PGRMConfig(iter=k, mode=(k >= 3))), seed + k) for k in range(6)]
     cm = synth_params(cmm_schema(3, 64), seed + 50)
     return pg, cm
+
+
+def load_weights(model, pg, cm):
+    for k, m in enumerate(model.pgrm):
+        sd = m.state_dict()
+        m.load_state_dict({n: (torch.from_numpy(pg[k][n]) if n in pg[k] else v) for n, v in sd.items()}, strict=True)
+    model.cmm.load_state_dict({n: torch.from_numpy(np.asarray(cm[n])) for n in model.cmm.state_dict()}, strict=True)
 
 
 class ClockSampler:
@@ -150,10 +158,7 @@ def run_ours(args):
 
     model = DPMNHotPath(precision=args.precision)
     pg, cm = synth_weights(2)
-    for k, m in enumerate(model.pgrm):
-        sd = m.state_dict()
-        m.load_state_dict({n: (torch.from_numpy(pg[k][n]) if n in pg[k] else v) for n, v in sd.items()}, strict=True)
-    model.cmm.load_state_dict({n: torch.from_numpy(np.asarray(cm[n])) for n in model.cmm.state_dict()}, strict=True)
+    load_weights(model, pg, cm)
     model = model.to(dev).eval()
 
     B = BATCH
@@ -292,7 +297,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--precision", default=os.environ.get("DPMN_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("DPMN_PRECISION", "fp16"))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -86,6 +86,8 @@ SYMBOLS = {
     "dpmn_window_attn_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "dpmn_cmm_workspace_bytes": (_sz, [C.POINTER(CmmDesc)]),
     "dpmn_cmm_forward": (C.c_int, [C.POINTER(CmmDesc), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dpmn_cmm_debug_bytes": (_sz, [C.POINTER(CmmDesc), _i32]),
+    "dpmn_cmm_debug_copy": (C.c_int, [C.POINTER(CmmDesc), _vp, _i32, _vp, _sz, _vp]),
     "dpmn_gemm_nt": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
     "dpmn_gemm_nt_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
 }

@@ -18,9 +18,9 @@ std::atomic<uint64_t> g_launches{0};
 // Optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream around every
 // kernel launch, tagged by kernel class.  Off by default; never active inside a timed throughput region.
 enum KTag { T_PATCH_EMBED = 0, T_LAYERNORM, T_GEMM, T_WINDOW_ATTN, T_SK_GATE, T_DWCONV, T_HEAD, T_CONV, T_BN,
-            T_SE_GATE, T_CONVERT, T_GEMM_TC, T_COUNT };
+            T_SE_GATE, T_CONVERT, T_GEMM_TC, T_CONV_TC, T_PREP, T_CONV_STEM, T_COUNT };
 const char* const kTagNames[T_COUNT] = {"patch_embed", "layernorm", "gemm", "window_attn", "sk_gate",
-                                        "dwconv", "head", "conv", "bn_affine", "se_gate", "convert", "gemm_tc"};
+                                        "dwconv", "head", "conv", "bn_affine", "se_gate", "convert", "gemm_tc", "conv_tc", "weight_prep", "conv_stem"};
 struct ProfRec { int tag; int n; cudaEvent_t e0, e1; };
 bool g_prof = false;
 std::mutex g_prof_mu;
@@ -370,6 +370,263 @@ int bn_affine(const dpmn_cmm_desc* d, const dpmn_bn& bn, const float* x, int ch,
                           d->training && d->update_running_stats, 1e-5f, sc, sh, st);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Tensor-core CMM (fp16 / bf16 operands): NHWC 16-bit activations, implicit-GEMM convs on tcgen05.
+struct CmmTcWs {
+  void* e[6];        // e[l], l = 1..5: LeakyReLU'd encoder outputs [2][B][H_l][W_l][C_l]
+  void* mid[6];      // mid[l], l = 2..5: LeakyReLU'd EncodeBlock intermediates [2][B][H_l][W_l][C_{l-1}]
+  void* cat[6];      // cat[l], l = 1..5: ReLU'd decoder input [B][H_l][W_l][Cd_l + 2 C_l]
+  float* z6;         // en_6 outputs [2][B][hw][8c] fp32
+  void* zg;          // ReLU(SE-gated bottleneck) [B][hw][16c]
+  void* dmid[6];     // dmid[l], l = 5..2: ReLU'd DecodeBlock intermediates [B][H_l][W_l][Co_l]
+  float* P;          // de_1 tap products [B*H*W][32]
+  void *w_enc_a[4], *w_enc_b[4], *w_en6, *w_de6, *w_dec_a[4], *w_dec_b[4], *w_de1;
+  float *s_enc_a[4], *t_enc_a[4], *s_enc_b[4], *t_enc_b[4], *t_en6, *s_en6, *s_de6, *t_de6;
+  float *s_dec_a[4], *t_dec_a[4], *s_dec_b[4], *t_dec_b[4];
+  size_t bytes;
+};
+
+struct CmmDims {
+  int B, c, H, W, ci;
+  int Hl(int l) const { return H >> (l - 1); }
+  int Wl(int l) const { return W >> (l - 1); }
+  int Cl(int l) const { return l == 1 ? c : l == 2 ? 2 * c : l == 3 ? 4 * c : 8 * c; }   // encoder channels, l = 1..6
+  int Co(int l) const { return l >= 5 ? 8 * c : l == 4 ? 4 * c : l == 3 ? 2 * c : c; }   // decoder out channels, l = 6..2
+  int Cd(int l) const { return Co(l + 1); }                                               // decoder channels entering cat[l]
+  int Ccat(int l) const { return Cd(l) + 2 * Cl(l); }
+};
+
+CmmTcWs carve_cmm_tc(const dpmn_cmm_desc* d, void* ws) {
+  const CmmDims D{d->batch, d->cnum, d->img_h, d->img_w, d->c_img};
+  const size_t B = D.B;
+  Bump b(ws, (size_t)-1);
+  CmmTcWs w;
+  memset(&w, 0, sizeof(w));
+  for (int l = 1; l <= 5; ++l) {
+    const size_t px = (size_t)D.Hl(l) * D.Wl(l);
+    w.e[l] = b.take<uint16_t>(2 * B * px * D.Cl(l));
+    if (l >= 2) w.mid[l] = b.take<uint16_t>(2 * B * px * D.Cl(l - 1));
+    w.cat[l] = b.take<uint16_t>(B * px * D.Ccat(l));
+    if (l >= 2) w.dmid[l] = b.take<uint16_t>(B * px * D.Co(l));
+  }
+  const size_t hw6 = (size_t)(D.H >> 5) * (D.W >> 5);
+  w.z6 = b.take<float>(2 * B * hw6 * 8 * D.c);
+  w.zg = b.take<uint16_t>(B * hw6 * 16 * D.c);
+  w.P = b.take<float>(B * (size_t)D.H * D.W * 32);
+  for (int l = 1; l <= 4; ++l) {
+    w.w_enc_a[l - 1] = b.take<uint16_t>((size_t)2 * 16 * D.Cl(l) * D.Cl(l));
+    w.w_enc_b[l - 1] = b.take<uint16_t>((size_t)2 * 9 * D.Cl(l + 1) * D.Cl(l));
+    w.s_enc_a[l - 1] = b.take<float>(2 * D.Cl(l)); w.t_enc_a[l - 1] = b.take<float>(2 * D.Cl(l));
+    w.s_enc_b[l - 1] = b.take<float>(2 * D.Cl(l + 1)); w.t_enc_b[l - 1] = b.take<float>(2 * D.Cl(l + 1));
+  }
+  w.w_en6 = b.take<uint16_t>((size_t)2 * 16 * 8 * D.c * 8 * D.c);
+  w.s_en6 = b.take<float>(2 * 8 * D.c); w.t_en6 = b.take<float>(2 * 8 * D.c);
+  w.w_de6 = b.take<uint16_t>((size_t)16 * 8 * D.c * 16 * D.c);
+  w.s_de6 = b.take<float>(8 * D.c); w.t_de6 = b.take<float>(8 * D.c);
+  for (int i = 0; i < 4; ++i) {
+    const int l = 5 - i;
+    w.w_dec_a[i] = b.take<uint16_t>((size_t)9 * D.Co(l) * D.Ccat(l));
+    w.w_dec_b[i] = b.take<uint16_t>((size_t)16 * D.Co(l) * D.Co(l));
+    w.s_dec_a[i] = b.take<float>(D.Co(l)); w.t_dec_a[i] = b.take<float>(D.Co(l));
+    w.s_dec_b[i] = b.take<float>(D.Co(l)); w.t_dec_b[i] = b.take<float>(D.Co(l));
+  }
+  w.w_de1 = b.take<uint16_t>((size_t)32 * 3 * D.c);
+  w.bytes = b.off + 256;
+  return w;
+}
+
+// transposed-conv 4x4 stride 2 pad 1: output parity -> the two kernel taps that hit it and their input shift
+void convt4_taps(ConvTap (&taps)[4][16]) {
+  // oy = 2*iy - 1 + ky:  oy even -> ky 1 (iy = a), ky 3 (iy = a-1);  oy odd -> ky 0 (iy = a+1), ky 2 (iy = a)
+  const int kk[2][2] = {{1, 3}, {0, 2}};
+  const int dd[2][2] = {{0, -1}, {1, 0}};
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      int n = 0;
+      for (int a = 0; a < 2; ++a)
+        for (int bq = 0; bq < 2; ++bq) {
+          ConvTap t{};
+          t.map = 0; t.dy = (int8_t)dd[py][a]; t.dx = (int8_t)dd[px][bq];
+          t.wslice = (int16_t)(kk[py][a] * 4 + kk[px][bq]);
+          taps[py * 2 + px][n++] = t;
+        }
+    }
+}
+
+int cmm_forward_tc(const dpmn_cmm_desc* d, const float* x1, const float* x2, float* out, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st) {
+  if (d->training) return DPMN_E_UNSUPPORTED;   // batch-statistics BatchNorm runs in the fp32 mode only (this build)
+  if (d->cnum % 16 || d->c_img > 3) return DPMN_E_UNSUPPORTED;   // 64-channel k-blocks, whole UMMA k-steps, 9*c_img <= 32
+  const CmmTcWs w = carve_cmm_tc(d, workspace);
+  if (workspace_bytes < w.bytes) return DPMN_E_WORKSPACE;
+  const CmmDims D{d->batch, d->cnum, d->img_h, d->img_w, d->c_img};
+  const DType t = (DType)d->precision;
+  const int B = D.B, c = D.c, H = D.H, W = D.W;
+
+  // ---- stage weights (16-bit, tap-major) and fold bias + eval BatchNorm into (scale, shift)
+  {
+    PrepBatch pb; FoldBatch fb;
+    auto prep = [&](const float* src, void* dst, int Cout, int Cin, int kk, int tr) {
+      pb.seg[pb.count++] = PrepSeg{src, dst, Cout, Cin, kk, tr, Cout};
+    };
+    auto fold = [&](const float* bias, const dpmn_bn* bn, float* sc, float* sh, int C) {
+      fb.seg[fb.count++] = FoldSeg{bias, bn ? bn->w : nullptr, bn ? bn->b : nullptr, bn ? bn->running_mean : nullptr,
+                                   bn ? bn->running_var : nullptr, sc, sh, C};
+    };
+    for (int l = 1; l <= 4; ++l) {
+      const int Ci = D.Cl(l), Cn = D.Cl(l + 1);
+      for (int g = 0; g < 2; ++g) {
+        const dpmn_cmm_stage& s = d->enc[g][l - 1];
+        prep(s.conv_a_w, (uint16_t*)w.w_enc_a[l - 1] + (size_t)g * 16 * Ci * Ci, Ci, Ci, 16, 0);
+        prep(s.conv_b_w, (uint16_t*)w.w_enc_b[l - 1] + (size_t)g * 9 * Cn * Ci, Cn, Ci, 9, 0);
+        fold(s.conv_a_b, &s.bn_a, w.s_enc_a[l - 1] + g * Ci, w.t_enc_a[l - 1] + g * Ci, Ci);
+        fold(s.conv_b_b, &s.bn_b, w.s_enc_b[l - 1] + g * Cn, w.t_enc_b[l - 1] + g * Cn, Cn);
+      }
+    }
+    for (int g = 0; g < 2; ++g) {
+      prep(d->en6_w[g], (uint16_t*)w.w_en6 + (size_t)g * 16 * 64 * c * c, 8 * c, 8 * c, 16, 0);
+      fold(d->en6_b[g], nullptr, w.s_en6 + g * 8 * c, w.t_en6 + g * 8 * c, 8 * c);
+    }
+    prep(d->de6_w, w.w_de6, 8 * c, 16 * c, 16, 1);
+    fold(d->de6_b, &d->de6_bn, w.s_de6, w.t_de6, 8 * c);
+    for (int i = 0; i < 4; ++i) {
+      const int l = 5 - i;
+      const dpmn_cmm_stage& s = d->dec[i];
+      prep(s.conv_a_w, w.w_dec_a[i], D.Co(l), D.Ccat(l), 9, 1);
+      prep(s.conv_b_w, w.w_dec_b[i], D.Co(l), D.Co(l), 16, 1);
+      fold(s.conv_a_b, &s.bn_a, w.s_dec_a[i], w.t_dec_a[i], D.Co(l));
+      fold(s.conv_b_b, &s.bn_b, w.s_dec_b[i], w.t_dec_b[i], D.Co(l));
+    }
+    DPMN_CUDA_TRY(cudaMemsetAsync(w.w_de1, 0, (size_t)32 * 3 * c * 2, st));
+    prep(d->de1_w, w.w_de1, D.ci, 3 * c, 9, 1);
+    DPMN_RUN(T_PREP, launch_prep_weights(pb, t, st), 1);
+    DPMN_RUN(T_PREP, launch_fold_bn(fb, 1e-5f, st), 1);
+  }
+
+  // ---- en_1 (stem, 3 channels: SIMT)
+  DPMN_RUN(T_CONV_STEM, launch_cmm_en1(x1, x2, d->en1_w[0], d->en1_b[0], d->en1_w[1], d->en1_b[1], w.e[1], w.cat[1], t, B, H,
+                                       W, D.ci, c, st), 1);
+
+  // ---- encoders, both branches per launch (G = 2)
+  for (int l = 1; l <= 4; ++l) {
+    const int Hi = D.Hl(l), Wi = D.Wl(l), Ci = D.Cl(l), Cn = D.Cl(l + 1);
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    {
+      ConvTcArgs a;   // LeakyReLU -> conv4x4 s2 d2 p3 -> BN -> (LeakyReLU)          cmm.py:41-45
+      a.op_type = t; a.n_src = 1;
+      a.src[0].base = (const uint16_t*)w.e[l] + ((size_t)Wi + 1) * Ci;   // odd rows / odd columns sub-grid
+      a.src[0].sx = 2LL * Ci; a.src[0].sy = 2LL * Wi * Ci; a.src[0].sb = (long long)Hi * Wi * Ci;
+      a.src[0].sg = (long long)B * Hi * Wi * Ci;
+      a.Cin = Ci; a.Cout = Ci; a.B = B; a.G = 2; a.P = 1; a.Hm = Ho; a.Wm = Wo;
+      a.n_taps = 16;
+      for (int ky = 0; ky < 4; ++ky)
+        for (int kx = 0; kx < 4; ++kx) {
+          ConvTap tp{}; tp.map = 0; tp.dy = (int8_t)(ky - 2); tp.dx = (int8_t)(kx - 2); tp.wslice = (int16_t)(ky * 4 + kx);
+          a.taps[0][ky * 4 + kx] = tp;
+        }
+      a.w = w.w_enc_a[l - 1]; a.n_wslices = 16; a.os = 1; a.Ho = Ho; a.Wo = Wo;
+      a.scale = w.s_enc_a[l - 1]; a.shift = w.t_enc_a[l - 1];
+      a.dst[0].ptr = w.mid[l + 1]; a.dst[0].type = t; a.dst[0].g_stride = (long long)B * Ho * Wo * Ci; a.dst[0].ld = Ci;
+      a.dst[0].act = 1;
+      DPMN_RUN(T_CONV_TC, launch_conv_tc(a, st), 1);
+    }
+    {
+      ConvTcArgs a;   // conv3x3 -> BN; stored LeakyReLU'd for the next stage and ReLU'd for the decoder skip
+      a.op_type = t; a.n_src = 1;
+      a.src[0].base = w.mid[l + 1];
+      a.src[0].sx = Ci; a.src[0].sy = (long long)Wo * Ci; a.src[0].sb = (long long)Ho * Wo * Ci;
+      a.src[0].sg = (long long)B * Ho * Wo * Ci;
+      a.Cin = Ci; a.Cout = Cn; a.B = B; a.G = 2; a.P = 1; a.Hm = Ho; a.Wm = Wo;
+      a.n_taps = 9;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          ConvTap tp{}; tp.map = 0; tp.dy = (int8_t)(ky - 1); tp.dx = (int8_t)(kx - 1); tp.wslice = (int16_t)(ky * 3 + kx);
+          a.taps[0][ky * 3 + kx] = tp;
+        }
+      a.w = w.w_enc_b[l - 1]; a.n_wslices = 9; a.os = 1; a.Ho = Ho; a.Wo = Wo;
+      a.scale = w.s_enc_b[l - 1]; a.shift = w.t_enc_b[l - 1];
+      a.dst[0].ptr = w.e[l + 1]; a.dst[0].type = t; a.dst[0].g_stride = (long long)B * Ho * Wo * Cn; a.dst[0].ld = Cn;
+      a.dst[0].act = 1;
+      a.dst[1].ptr = w.cat[l + 1]; a.dst[1].type = t; a.dst[1].g_stride = 0; a.dst[1].ld = D.Ccat(l + 1);
+      a.dst[1].ch_off = D.Cd(l + 1); a.dst[1].ch_g_off = Cn; a.dst[1].act = 2;
+      DPMN_RUN(T_CONV_TC, launch_conv_tc(a, st), 1);
+    }
+  }
+  const int H5 = D.Hl(5), W5 = D.Wl(5), C5 = 8 * c, H6 = H5 / 2, W6 = W5 / 2;
+  {
+    ConvTcArgs a;   // en_6: LeakyReLU -> conv4x4 s2 p1 (cmm.py:91-93): each tap reads one parity sub-grid
+    a.op_type = t; a.n_src = 4;
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        ConvTcSrc& sc = a.src[py * 2 + px];
+        sc.base = (const uint16_t*)w.e[5] + ((size_t)py * W5 + px) * C5;
+        sc.sx = 2LL * C5; sc.sy = 2LL * W5 * C5; sc.sb = (long long)H5 * W5 * C5; sc.sg = (long long)B * H5 * W5 * C5;
+      }
+    a.Cin = C5; a.Cout = C5; a.B = B; a.G = 2; a.P = 1; a.Hm = H6; a.Wm = W6;
+    a.n_taps = 16;
+    const int par[4] = {1, 0, 1, 0}, sh[4] = {-1, 0, 0, 1};   // iy = 2*oy - 1 + ky
+    for (int ky = 0; ky < 4; ++ky)
+      for (int kx = 0; kx < 4; ++kx) {
+        ConvTap tp{}; tp.map = (int8_t)(par[ky] * 2 + par[kx]); tp.dy = (int8_t)sh[ky]; tp.dx = (int8_t)sh[kx];
+        tp.wslice = (int16_t)(ky * 4 + kx);
+        a.taps[0][ky * 4 + kx] = tp;
+      }
+    a.w = w.w_en6; a.n_wslices = 16; a.os = 1; a.Ho = H6; a.Wo = W6;
+    a.scale = nullptr; a.shift = w.t_en6;
+    a.dst[0].ptr = w.z6; a.dst[0].type = DT_F32; a.dst[0].g_stride = (long long)B * H6 * W6 * C5; a.dst[0].ld = C5;
+    DPMN_RUN(T_CONV_TC, launch_conv_tc(a, st), 1);
+  }
+  DPMN_RUN(T_SE_GATE, launch_se_gate_nhwc(w.z6, w.zg, t, d->fc1_w, d->fc1_b, d->fc2_w, d->fc2_b, B, C5, H6 * W6, 4 * c, st), 1);
+
+  // ---- decoder
+  auto convt4 = [&](const void* src, int Hi, int Wi, int Ci, const void* wt, int Co, const float* sc, const float* sh,
+                    void* dst, int dst_ld) -> int {
+    ConvTcArgs a;   // ReLU'd input -> convT4x4 s2 p1 -> BN -> ReLU into channel 0.. of the next concat buffer
+    a.op_type = t; a.n_src = 1;
+    a.src[0].base = src; a.src[0].sx = Ci; a.src[0].sy = (long long)Wi * Ci; a.src[0].sb = (long long)Hi * Wi * Ci;
+    a.Cin = Ci; a.Cout = Co; a.B = B; a.G = 1; a.P = 4; a.Hm = Hi; a.Wm = Wi;
+    a.n_taps = 4;
+    convt4_taps(a.taps);
+    a.w = wt; a.n_wslices = 16; a.os = 2; a.Ho = 2 * Hi; a.Wo = 2 * Wi;
+    a.scale = sc; a.shift = sh;
+    a.dst[0].ptr = dst; a.dst[0].type = t; a.dst[0].ld = dst_ld; a.dst[0].act = 2;
+    return launch_conv_tc(a, st);
+  };
+  DPMN_RUN(T_CONV_TC, convt4(w.zg, H6, W6, 16 * c, w.w_de6, 8 * c, w.s_de6, w.t_de6, w.cat[5], D.Ccat(5)), 1);
+  for (int i = 0; i < 4; ++i) {
+    const int l = 5 - i;
+    const int Hi = D.Hl(l), Wi = D.Wl(l), Cc = D.Ccat(l), Co = D.Co(l);
+    {
+      ConvTcArgs a;   // convT3x3 s1 p1 on the concat buffer = conv with mirrored taps (cmm.py:62)
+      a.op_type = t; a.n_src = 1;
+      a.src[0].base = w.cat[l]; a.src[0].sx = Cc; a.src[0].sy = (long long)Wi * Cc; a.src[0].sb = (long long)Hi * Wi * Cc;
+      a.Cin = Cc; a.Cout = Co; a.B = B; a.G = 1; a.P = 1; a.Hm = Hi; a.Wm = Wi;
+      a.n_taps = 9;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          ConvTap tp{}; tp.map = 0; tp.dy = (int8_t)(1 - ky); tp.dx = (int8_t)(1 - kx); tp.wslice = (int16_t)(ky * 3 + kx);
+          a.taps[0][ky * 3 + kx] = tp;
+        }
+      a.w = w.w_dec_a[i]; a.n_wslices = 9; a.os = 1; a.Ho = Hi; a.Wo = Wi;
+      a.scale = w.s_dec_a[i]; a.shift = w.t_dec_a[i];
+      a.dst[0].ptr = w.dmid[l]; a.dst[0].type = t; a.dst[0].ld = Co; a.dst[0].act = 2;
+      DPMN_RUN(T_CONV_TC, launch_conv_tc(a, st), 1);
+    }
+    DPMN_RUN(T_CONV_TC, convt4(w.dmid[l], Hi, Wi, Co, w.w_dec_b[i], Co, w.s_dec_b[i], w.t_dec_b[i], w.cat[l - 1],
+                               D.Ccat(l - 1)), 1);
+  }
+  // ---- de_1: 3 output channels -> the 9 taps ride in N (one pass over the concat buffer), then a gather
+  {
+    GemmTcArgs g;
+    g.A = w.cat[1]; g.lda = 3 * c; g.Bm = w.w_de1; g.ldb = 3 * c; g.op_type = t;
+    g.C = w.P; g.ldc = 32; g.out_type = DT_F32; g.M = B * H * W; g.N = 32; g.K = 3 * c;
+    DPMN_RUN(T_GEMM_TC, launch_gemm_tc(g, st), 1);
+    DPMN_RUN(T_CONV_STEM, launch_de1_gather(w.P, 32, d->de1_b, out, B, H, W, D.ci, st), 1);
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -501,13 +758,42 @@ static int check_cmm(const dpmn_cmm_desc* d) {
   if (!d) return DPMN_E_ARG;
   if (d->batch < 1 || d->c_img < 1 || d->cnum < 1) return DPMN_E_ARG;
   if (d->img_h % 32 || d->img_w % 32 || d->img_h < 32 || d->img_w < 32) return DPMN_E_UNSUPPORTED;
-  if (d->precision != DPMN_PREC_F32) return DPMN_E_UNSUPPORTED;
+  if (d->precision < DPMN_PREC_F32 || d->precision > DPMN_PREC_BF16) return DPMN_E_ARG;
   return 0;
 }
 
 size_t dpmn_cmm_workspace_bytes(const dpmn_cmm_desc* d) {
   if (check_cmm(d)) return 0;
+  if (d->precision != DPMN_PREC_F32) return carve_cmm_tc(d, nullptr).bytes;
   return carve_cmm(d, nullptr).bytes;
+}
+
+size_t dpmn_cmm_debug_bytes(const dpmn_cmm_desc* d, int32_t which) {
+  if (check_cmm(d) || d->precision == DPMN_PREC_F32) return 0;
+  const CmmDims D{d->batch, d->cnum, d->img_h, d->img_w, d->c_img};
+  const size_t B = D.B;
+  if (which >= 1 && which <= 5) return 2 * B * D.Hl(which) * D.Wl(which) * D.Cl(which) * 2;
+  if (which >= 12 && which <= 15) { const int l = which - 10; return 2 * B * D.Hl(l) * D.Wl(l) * D.Cl(l - 1) * 2; }
+  if (which >= 21 && which <= 25) { const int l = which - 20; return B * D.Hl(l) * D.Wl(l) * D.Ccat(l) * 2; }
+  if (which >= 32 && which <= 35) { const int l = which - 30; return B * D.Hl(l) * D.Wl(l) * D.Co(l) * 2; }
+  if (which == 40) return 2 * B * (size_t)(D.H >> 5) * (D.W >> 5) * 8 * D.c * 4;
+  if (which == 41) return B * (size_t)(D.H >> 5) * (D.W >> 5) * 16 * D.c * 2;
+  return 0;
+}
+
+int dpmn_cmm_debug_copy(const dpmn_cmm_desc* d, void* workspace, int32_t which, void* dst, size_t dst_bytes, void* stream) {
+  const size_t n = dpmn_cmm_debug_bytes(d, which);
+  if (n == 0 || !workspace || !dst || dst_bytes < n) return DPMN_E_ARG;
+  const CmmTcWs w = carve_cmm_tc(d, workspace);
+  const void* src = nullptr;
+  if (which >= 1 && which <= 5) src = w.e[which];
+  else if (which >= 12 && which <= 15) src = w.mid[which - 10];
+  else if (which >= 21 && which <= 25) src = w.cat[which - 20];
+  else if (which >= 32 && which <= 35) src = w.dmid[which - 30];
+  else if (which == 40) src = w.z6;
+  else if (which == 41) src = w.zg;
+  DPMN_CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
 }
 
 int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, float* out, void* workspace,
@@ -515,6 +801,13 @@ int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, f
   int rc = check_cmm(d);
   if (rc) return rc;
   if (!x1 || !x2 || !out || !workspace) return DPMN_E_ARG;
+  if (d->precision != DPMN_PREC_F32) {
+    for (int br = 0; br < 2; ++br) {
+      const long long bs = br == 0 ? d->x1_batch_stride : d->x2_batch_stride;
+      if (bs != 0 && bs != (long long)d->c_img * d->img_h * d->img_w) return DPMN_E_UNSUPPORTED;
+    }
+    return cmm_forward_tc(d, x1, x2, out, workspace, workspace_bytes, (cudaStream_t)stream);
+  }
   const CmmWs w = carve_cmm(d, workspace);
   if (workspace_bytes < w.bytes) return DPMN_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;

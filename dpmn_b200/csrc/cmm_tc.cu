@@ -1,0 +1,226 @@
+// SIMT helper kernels of the tensor-core CMM path (cmm.py:80-161): weight staging, BatchNorm folding,
+// the 3-channel stem conv, the SE gate on NHWC data and the 3-channel tail of de_1.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dpmn {
+
+// ---- weights: fp32 torch layout -> 16-bit [tap][rows][Cin] --------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) prep_weights_kernel(PrepBatch pb) {
+  const PrepSeg sg = pb.seg[blockIdx.y];
+  const long long n = (long long)sg.kk * sg.rows * sg.Cin;
+  T* dst = reinterpret_cast<T*>(sg.dst);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int ci = (int)(i % sg.Cin);
+    const int co = (int)((i / sg.Cin) % sg.rows);
+    const int tap = (int)(i / ((long long)sg.Cin * sg.rows));
+    float v = 0.f;
+    if (co < sg.Cout)
+      v = sg.transposed ? sg.src[((long long)ci * sg.Cout + co) * sg.kk + tap]
+                        : sg.src[((long long)co * sg.Cin + ci) * sg.kk + tap];
+    dst[i] = from_f32<T>(v);
+  }
+}
+
+int launch_prep_weights(const PrepBatch& pb, DType t, cudaStream_t st) {
+  if (pb.count < 1 || pb.count > 48) return -1;
+  dim3 grid(296, pb.count);
+  if (t == DT_F16) prep_weights_kernel<__half><<<grid, 256, 0, st>>>(pb);
+  else if (t == DT_BF16) prep_weights_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(pb);
+  else return -1;
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- (conv bias, eval BatchNorm) -> (scale, shift):  y = acc * scale + shift -------------------------------
+__global__ void __launch_bounds__(256) fold_bn_kernel(FoldBatch fb, float eps) {
+  const FoldSeg s = fb.seg[blockIdx.y];
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < s.C; c += gridDim.x * blockDim.x) {
+    const float bias = s.bias ? s.bias[c] : 0.f;
+    if (s.bn_w == nullptr) {
+      s.scale[c] = 1.f;
+      s.shift[c] = bias;
+    } else {
+      const float sc = s.bn_w[c] / sqrtf(s.bn_rv[c] + eps);
+      s.scale[c] = sc;
+      s.shift[c] = (bias - s.bn_rm[c]) * sc + s.bn_b[c];
+    }
+  }
+}
+
+int launch_fold_bn(const FoldBatch& fb, float eps, cudaStream_t st) {
+  if (fb.count < 1 || fb.count > 48) return -1;
+  dim3 grid(4, fb.count);
+  fold_bn_kernel<<<grid, 256, 0, st>>>(fb, eps);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- en_1: conv3x3 c_img -> cnum, fp32 NCHW in, two 16-bit NHWC outs -----------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) cmm_en1_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                      const float* __restrict__ w1, const float* __restrict__ b1,
+                                                      const float* __restrict__ w2, const float* __restrict__ b2,
+                                                      T* __restrict__ e1, T* __restrict__ cat1, int B, int H, int W,
+                                                      int c_img, int cnum) {
+  extern __shared__ float sw[];   // [c_img*9][cnum] + bias [cnum]
+  const int g = blockIdx.y;
+  const float* x = g == 0 ? x1 : x2;
+  const float* w = g == 0 ? w1 : w2;
+  const float* bsrc = g == 0 ? b1 : b2;
+  const int K = c_img * 9;
+  for (int i = threadIdx.x; i < K * cnum; i += blockDim.x) {
+    const int co = i % cnum, k = i / cnum;
+    sw[i] = w[co * K + k];
+  }
+  float* sb = sw + K * cnum;
+  for (int i = threadIdx.x; i < cnum; i += blockDim.x) sb[i] = bsrc[i];
+  __syncthreads();
+  const int groups = cnum / 8;
+  const long long total = (long long)B * H * W * groups;
+  const long long HW = (long long)H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % groups);
+    const long long pix = idx / groups;
+    const int xx = (int)(pix % W);
+    const int yy = (int)((pix / W) % H);
+    const int b = (int)(pix / HW);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = sb[cg * 8 + j];
+    for (int ci = 0; ci < c_img; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int y2 = yy + ky - 1;
+        if (y2 < 0 || y2 >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int x2 = xx + kx - 1;
+          if (x2 < 0 || x2 >= W) continue;
+          const float v = x[((long long)b * c_img + ci) * HW + (long long)y2 * W + x2];
+          const float* wr = sw + ((ci * 3 + ky) * 3 + kx) * cnum + cg * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+        }
+      }
+    union { uint4 u; T h[8]; } a, r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a.h[j] = from_f32<T>(acc[j] >= 0.f ? acc[j] : 0.2f * acc[j]);
+      r.h[j] = from_f32<T>(fmaxf(acc[j], 0.f));
+    }
+    *reinterpret_cast<uint4*>(e1 + ((long long)g * B * HW + pix) * cnum + cg * 8) = a.u;
+    *reinterpret_cast<uint4*>(cat1 + pix * (3 * cnum) + cnum * (1 + g) + cg * 8) = r.u;
+  }
+}
+
+int launch_cmm_en1(const float* x1, const float* x2, const float* w1, const float* b1, const float* w2, const float* b2,
+                   void* e1, void* cat1, DType t, int B, int H, int W, int c_img, int cnum, cudaStream_t st) {
+  if (cnum % 8) return -2;
+  const size_t smem = (size_t)(c_img * 9 * cnum + cnum) * sizeof(float);
+  if (smem > 48 * 1024) return -2;
+  dim3 grid(148 * 4, 2);
+  if (t == DT_F16)
+    cmm_en1_kernel<__half><<<grid, 256, smem, st>>>(x1, x2, w1, b1, w2, b2, (__half*)e1, (__half*)cat1, B, H, W, c_img, cnum);
+  else if (t == DT_BF16)
+    cmm_en1_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(x1, x2, w1, b1, w2, b2, (__nv_bfloat16*)e1,
+                                                          (__nv_bfloat16*)cat1, B, H, W, c_img, cnum);
+  else return -1;
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- SE gate on NHWC fp32 halves -----------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) se_gate_nhwc_kernel(const float* __restrict__ z6, T* __restrict__ zg,
+                                                           const float* __restrict__ fc1_w, const float* __restrict__ fc1_b,
+                                                           const float* __restrict__ fc2_w, const float* __restrict__ fc2_b,
+                                                           int B, int Cb, int hw, int hidden) {
+  extern __shared__ float sm[];
+  const int C2 = 2 * Cb;
+  float* sg = sm;
+  float* sh = sg + C2;
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C2; c += blockDim.x) {
+    const int g = c / Cb, cl = c - g * Cb;
+    const float* src = z6 + (((long long)g * B + b) * hw) * Cb + cl;
+    float s = 0.f;
+    for (int i = 0; i < hw; ++i) s += src[(long long)i * Cb];
+    sg[c] = s / (float)hw;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = warp; j < hidden; j += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C2; c += 32) s = fmaf(fc1_w[(long long)j * C2 + c], sg[c], s);
+    s = warp_sum(s);
+    if (lane == 0) sh[j] = fmaxf(s + fc1_b[j], 0.f);
+  }
+  __syncthreads();
+  for (int c = warp; c < C2; c += nw) {
+    float s = 0.f;
+    for (int j = lane; j < hidden; j += 32) s = fmaf(fc2_w[(long long)c * hidden + j], sh[j], s);
+    s = warp_sum(s);
+    const float gate = 1.0f / (1.0f + expf(-(s + fc2_b[c])));
+    const int g = c / Cb, cl = c - g * Cb;
+    for (int i = lane; i < hw; i += 32) {
+      const float v = z6[(((long long)g * B + b) * hw + i) * Cb + cl];
+      zg[((long long)b * hw + i) * C2 + c] = from_f32<T>(fmaxf(fmaf(v, gate, v), 0.f));   // ReLU of de_6 folded in
+    }
+  }
+}
+
+int launch_se_gate_nhwc(const float* z6, void* zg, DType t, const float* fc1_w, const float* fc1_b, const float* fc2_w,
+                        const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * Cb + hidden) * sizeof(float);
+  if (smem > 48 * 1024) return -2;
+  if (t == DT_F16)
+    se_gate_nhwc_kernel<__half><<<B, 256, smem, st>>>(z6, (__half*)zg, fc1_w, fc1_b, fc2_w, fc2_b, B, Cb, hw, hidden);
+  else if (t == DT_BF16)
+    se_gate_nhwc_kernel<__nv_bfloat16><<<B, 256, smem, st>>>(z6, (__nv_bfloat16*)zg, fc1_w, fc1_b, fc2_w, fc2_b, B, Cb,
+                                                             hw, hidden);
+  else return -1;
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- de_1 tail: gather the 9 shifted tap products, NCHW fp32 out ---------------------------------------------
+__global__ void __launch_bounds__(256) de1_gather_kernel(const float* __restrict__ P, int ldp,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                         int H, int W, int c_img) {
+  const long long total = (long long)B * H * W;
+  const long long HW = (long long)H * W;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(pix % W);
+    const int yy = (int)((pix / W) % H);
+    const int b = (int)(pix / HW);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int y2 = yy + 1 - ky;
+      if (y2 < 0 || y2 >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int x2 = xx + 1 - kx;
+        if (x2 < 0 || x2 >= W) continue;
+        const float* src = P + ((long long)b * HW + (long long)y2 * W + x2) * ldp + (ky * 3 + kx) * c_img;
+        for (int co = 0; co < c_img; ++co) acc[co] += src[co];
+      }
+    }
+    for (int co = 0; co < c_img; ++co) out[((long long)b * c_img + co) * HW + (long long)yy * W + xx] = acc[co] + bias[co];
+  }
+}
+
+int launch_de1_gather(const float* P, int ldp, const float* bias, float* out, int B, int H, int W, int c_img,
+                      cudaStream_t st) {
+  if (c_img > 4 || 9 * c_img > ldp) return -2;
+  de1_gather_kernel<<<148 * 8, 256, 0, st>>>(P, ldp, bias, out, B, H, W, c_img);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dpmn

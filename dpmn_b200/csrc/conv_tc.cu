@@ -1,0 +1,324 @@
+// tcgen05 implicit-GEMM convolution for the Complementation Modulation Module (cmm.py:38-118) on sm_100a.
+//
+//   out[pixel, co] = epi( sum_{tap} sum_{ci} X[pixel shifted by tap, ci] * Wt[tap][co][ci] )
+//
+// Activations are NHWC 16-bit.  M = 128 output-grid pixels (a TMA box {64 ch, bw, bh, bb} of the activation
+// tensor per tap, OOB pixels zero-filled = the conv padding), N = BN output channels, K = taps x Cin in
+// 64-channel blocks.  No im2col is ever materialised: every tap is a shifted TMA box load.
+// Strided layers become stride-1 problems on sub-grids of the NHWC tensor (a tensor map with doubled strides):
+//   * conv 4x4 stride 2 dilation 2 pad 3 (cmm.py:44) only reads odd rows/cols -> 4x4 stride-1 conv on that sub-grid
+//   * conv 4x4 stride 2 pad 1 (cmm.py:92): each tap reads one of the 4 parity sub-grids
+//   * convT 4x4 stride 2 pad 1 (cmm.py:67,109): 4 output-parity classes, each a 2x2 stride-1 conv
+//   * convT 3x3 stride 1 pad 1 (cmm.py:62,115): conv with mirrored taps
+// Same warp-specialised pipeline as gemm_tc.cu (TMA warp, MMA warp, 4 epilogue warps, TMEM double buffer).
+// Epilogue: per-channel scale/shift (conv bias + eval BatchNorm folded), then up to two stores with their own
+// activation (LeakyReLU 0.2 for the next encoder stage, ReLU for the decoder skip), 16-bit NHWC or fp32.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+#include <cstring>
+
+namespace dpmn {
+
+using namespace tc;
+
+constexpr int CBM = 128;
+constexpr int CBK = 64;
+constexpr int CSTAGES = 4;
+constexpr int CONV_THREADS = 192;
+
+struct ConvTcParams {
+  int Cin, Cout, B, G, P;            // P output-parity classes (1 or 4)
+  int Hm, Wm;                        // grid the M tiles enumerate (per image)
+  int bw, bh, bb;                    // box: bw*bh*bb == 128
+  int wt, ht, bt, n_tiles;           // tile counts
+  int n_taps;                        // taps per class
+  ConvTap taps[4][16];
+  int os, Ho, Wo;                    // output pixel = (y*os + py, x*os + px) in an (Ho, Wo) grid; class p -> (py, px) = (p>>1, p&1)
+  const float* scale;                // [G][Cout] or nullptr (1)
+  const float* shift;                // [G][Cout] or nullptr (0)
+  ConvTcDest dst[2];
+  int fmt;                           // 0 fp16, 1 bf16
+};
+
+template <int BN>
+struct ConvSmem {
+  static constexpr int A_BYTES = CBM * CBK * 2;
+  static constexpr int B_BYTES = BN * CBK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = CSTAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <typename T>
+__device__ __forceinline__ void store_chunk(const ConvTcDest& d, int g, long long pix, int n0, int ncols, const float (&v)[32]) {
+  // 32 consecutive output channels of one pixel
+  const long long off = (long long)g * d.g_stride + pix * d.ld + d.ch_off + g * d.ch_g_off + n0;
+  float a[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = v[j];
+    if (d.act == 1) x = x >= 0.f ? x : 0.2f * x;
+    else if (d.act == 2) x = fmaxf(x, 0.f);
+    a[j] = x;
+  }
+  if constexpr (sizeof(T) == 4) {
+    float* p = reinterpret_cast<float*>(d.ptr) + off;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      if (j < ncols) *reinterpret_cast<float4*>(p + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+  } else {
+    T* p = reinterpret_cast<T*>(d.ptr) + off;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (j < ncols) {
+        union { uint4 u; T h[8]; } pk;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pk.h[e] = from_f32<T>(a[j + e]);
+        *reinterpret_cast<uint4*>(p + j) = pk.u;
+      }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+               const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  using S = ConvSmem<BN>;
+  uint8_t* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CSTAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + CSTAGES;
+  uint64_t* tmem_full = bars + 2 * CSTAGES;
+  uint64_t* tmem_empty = bars + 2 * CSTAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CSTAGES + 4);
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cblocks = (p.Cin + CBK - 1) / CBK;
+  const int num_kb = p.n_taps * cblocks;
+  const int pix_tiles = p.wt * p.ht * p.bt;
+  const int total_tiles = p.G * p.P * pix_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_w);
+    for (int i = 0; i < CSTAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile index -> (n block, pixel-tile origin, parity class, group); n fastest so neighbours share the A boxes in L2
+#define DPMN_DECODE_TILE(t)                                   \
+  const int n_blk = (t) % p.n_tiles;                          \
+  int _r = (t) / p.n_tiles;                                   \
+  const int w0 = (_r % p.wt) * p.bw; _r /= p.wt;              \
+  const int h0 = (_r % p.ht) * p.bh; _r /= p.ht;              \
+  const int b0 = (_r % p.bt) * p.bb; _r /= p.bt;              \
+  const int cls = _r % p.P;                                   \
+  const int g = _r / p.P;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        DPMN_DECODE_TILE(t)
+        for (int tap = 0; tap < p.n_taps; ++tap) {
+          const ConvTap tp = p.taps[cls][tap];
+          const CUtensorMap* ma = tp.map == 0 ? &map_a0 : tp.map == 1 ? &map_a1 : tp.map == 2 ? &map_a2 : &map_a3;
+          for (int cb = 0; cb < cblocks; ++cb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = tiles + stage * S::STAGE_BYTES;
+            uint8_t* sb = sa + S::A_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+            tma_load_5d(sa, ma, &full_bar[stage], cb * CBK, w0 + tp.dx, h0 + tp.dy, b0, g);
+            tma_load_4d(sb, &map_w, &full_bar[stage], cb * CBK, n_blk * BN, tp.wslice, g);
+            if (++stage == CSTAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(p.fmt, CBM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int cb = kb % cblocks;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + stage * S::STAGE_BYTES);
+          const uint64_t da = make_smem_desc_sw128(sa);
+          const uint64_t db = make_smem_desc_sw128(sa + S::A_BYTES);
+          const int c_left = p.Cin - cb * CBK;
+          const int ksteps = c_left >= CBK ? CBK / 16 : (c_left + 15) / 16;
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16(d_tmem, advance_desc_k(da, k), advance_desc_k(db, k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == CSTAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      DPMN_DECODE_TILE(t)
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int r = quarter * 32 + lane;              // tile row = box element (w fastest, then h, then image)
+      const int wi = r % p.bw;
+      const int hi = (r / p.bw) % p.bh;
+      const int bi = r / (p.bw * p.bh);
+      const int x = w0 + wi, y = h0 + hi, b = b0 + bi;
+      const bool ok = x < p.Wm && y < p.Hm && b < p.B;
+      const long long pix = ((long long)b * p.Ho + (y * p.os + (cls >> 1))) * p.Wo + (x * p.os + (cls & 1));
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), rr);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c0;
+        if (!ok || n0 >= p.Cout) continue;
+        const int ncols = p.Cout - n0 < 32 ? p.Cout - n0 : 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+        if (p.scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncols) {
+              const float4 sc = *reinterpret_cast<const float4*>(p.scale + (long long)g * p.Cout + n0 + j);
+              v[j] *= sc.x; v[j + 1] *= sc.y; v[j + 2] *= sc.z; v[j + 3] *= sc.w;
+            }
+          }
+        }
+        if (p.shift != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncols) {
+              const float4 sh = *reinterpret_cast<const float4*>(p.shift + (long long)g * p.Cout + n0 + j);
+              v[j] += sh.x; v[j + 1] += sh.y; v[j + 2] += sh.z; v[j + 3] += sh.w;
+            }
+          }
+        }
+#pragma unroll
+        for (int di = 0; di < 2; ++di) {
+          const ConvTcDest& d = p.dst[di];
+          if (d.ptr == nullptr) continue;
+          if (d.type == DT_F32) store_chunk<float>(d, g, pix, n0, ncols, v);
+          else if (d.type == DT_F16) store_chunk<__half>(d, g, pix, n0, ncols, v);
+          else store_chunk<__nv_bfloat16>(d, g, pix, n0, ncols, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+#undef DPMN_DECODE_TILE
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host -------------------------------------------------------------------------------------------------
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+template <int BN>
+static int launch_conv_bn(const ConvTcArgs& a, cudaStream_t st) {
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.Cin = a.Cin; p.Cout = a.Cout; p.B = a.B; p.G = a.G; p.P = a.P; p.Hm = a.Hm; p.Wm = a.Wm;
+  p.bw = next_pow2(a.Wm) < CBM ? next_pow2(a.Wm) : CBM;
+  p.bh = next_pow2(a.Hm) < CBM / p.bw ? next_pow2(a.Hm) : CBM / p.bw;
+  p.bb = CBM / (p.bw * p.bh);
+  p.wt = (a.Wm + p.bw - 1) / p.bw; p.ht = (a.Hm + p.bh - 1) / p.bh; p.bt = (a.B + p.bb - 1) / p.bb;
+  p.n_tiles = (a.Cout + BN - 1) / BN;
+  p.n_taps = a.n_taps;
+  for (int c = 0; c < 4; ++c)
+    for (int t = 0; t < 16; ++t) p.taps[c][t] = a.taps[c][t];
+  p.os = a.os; p.Ho = a.Ho; p.Wo = a.Wo; p.scale = a.scale; p.shift = a.shift;
+  p.dst[0] = a.dst[0]; p.dst[1] = a.dst[1];
+  p.fmt = a.op_type == DT_BF16 ? 1 : 0;
+
+  CUtensorMap maps[4];
+  for (int m = 0; m < 4; ++m) {
+    const ConvTcSrc& s = a.src[m < a.n_src ? m : 0];
+    const uint64_t dims[5] = {(uint64_t)a.Cin, (uint64_t)a.Wm, (uint64_t)a.Hm, (uint64_t)a.B, (uint64_t)a.G};
+    const uint64_t str[4] = {(uint64_t)s.sx * 2, (uint64_t)s.sy * 2, (uint64_t)s.sb * 2, (uint64_t)(a.G > 1 ? s.sg : s.sb * a.B) * 2};
+    const uint32_t box[5] = {CBK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bb, 1};
+    int rc = make_tensor_map_16bit(&maps[m], s.base, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  CUtensorMap map_w;
+  {
+    const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.Cout, (uint64_t)a.n_wslices, (uint64_t)a.G};
+    const uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.Cin * a.Cout * 2,
+                             (uint64_t)a.Cin * a.Cout * a.n_wslices * 2};
+    const uint32_t box[4] = {CBK, BN, 1, 1};
+    int rc = make_tensor_map_16bit(&map_w, a.w, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    DPMN_CUDA_TRY(cudaGetDevice(&dev));
+    DPMN_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int total = p.G * p.P * p.wt * p.ht * p.bt * p.n_tiles;
+  const int grid = total < num_sms ? total : num_sms;
+  auto kern = conv_tc_kernel<BN>;
+  constexpr int smem = ConvSmem<BN>::TOTAL;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DPMN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  kern<<<grid, CONV_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], map_w, p);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st) {
+  if (a.op_type != DT_F16 && a.op_type != DT_BF16) return -1;
+  if (a.Cin % 8 || a.Cout % 8 || a.n_src < 1 || a.n_src > 4 || a.n_taps < 1 || a.n_taps > 16) return -2;
+  if (a.P != 1 && a.P != 4) return -2;
+  for (int di = 0; di < 2; ++di)
+    if (a.dst[di].ptr && ((a.dst[di].ld % 8) || (a.dst[di].ch_off % 8) || (a.dst[di].ch_g_off % 8))) return -2;
+  // N tile: small enough that the layer still spreads over the SMs, large enough to amortise the A box
+  const int bw = next_pow2(a.Wm) < CBM ? next_pow2(a.Wm) : CBM;
+  const int bh = next_pow2(a.Hm) < CBM / bw ? next_pow2(a.Hm) : CBM / bw;
+  const int bb = CBM / (bw * bh);
+  const long long pix_tiles = (long long)a.G * a.P * ((a.Wm + bw - 1) / bw) * ((a.Hm + bh - 1) / bh) * ((a.B + bb - 1) / bb);
+  int bn = 128;
+  if (a.Cout <= 32) bn = 32;
+  else if (a.Cout <= 64) bn = 64;
+  else if (pix_tiles * ((a.Cout + 127) / 128) < 148) bn = 64;
+  switch (bn) {
+    case 32: return launch_conv_bn<32>(a, st);
+    case 64: return launch_conv_bn<64>(a, st);
+    default: return launch_conv_bn<128>(a, st);
+  }
+}
+
+}  // namespace dpmn

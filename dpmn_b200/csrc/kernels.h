@@ -134,4 +134,50 @@ int launch_bn_affine(const float* x, int B, int C, int HW, const float* w, const
 int launch_se_gate(const float* z1, const float* z2, float* z, const float* fc1_w, const float* fc1_b,
                    const float* fc2_w, const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st);
 
+// ---- CMM tensor-core kernels (conv_tc.cu, cmm_tc.cu) ----------------------------------------------------
+
+struct ConvTap { int8_t map, dy, dx, pad_; int16_t wslice, pad2_; };   // A-map id, pixel shift, weight slice
+struct ConvTcSrc { const void* base = nullptr; long long sx = 0, sy = 0, sb = 0, sg = 0; };   // element strides
+struct ConvTcDest {
+  void* ptr = nullptr; int type = 0;      // DType of the destination
+  long long g_stride = 0;                 // elements between groups
+  int ld = 0;                             // elements between pixels (channel count of the destination buffer)
+  int ch_off = 0, ch_g_off = 0;           // channel offset = ch_off + g * ch_g_off
+  int act = 0;                            // 0 none, 1 LeakyReLU(0.2), 2 ReLU
+};
+// Implicit-GEMM conv on NHWC 16-bit activations; see conv_tc.cu.  Weights are [G][n_wslices][Cout][Cin] 16-bit.
+struct ConvTcArgs {
+  DType op_type = DT_F16;
+  int n_src = 1; ConvTcSrc src[4];        // the (sub-)grids the taps index; all of extent (Wm, Hm, B, G)
+  int Cin = 0, Cout = 0, B = 0, G = 1, P = 1;
+  int Hm = 0, Wm = 0;
+  int n_taps = 0; ConvTap taps[4][16] = {};
+  const void* w = nullptr; int n_wslices = 0;
+  int os = 1, Ho = 0, Wo = 0;
+  const float* scale = nullptr; const float* shift = nullptr;   // [G][Cout]
+  ConvTcDest dst[2];
+};
+int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st);
+
+// Weight staging for the tensor-core CMM: fp32 conv (Cout,Cin,k,k) / convT (Cin,Cout,k,k) -> 16-bit [k*k][rows][Cin]
+// (rows >= Cout, extra rows zero), and conv bias + eval-BatchNorm folded into per-channel (scale, shift).
+struct PrepSeg { const float* src; void* dst; int Cout, Cin, kk, transposed, rows; };
+struct PrepBatch { int count = 0; PrepSeg seg[48]; };
+int launch_prep_weights(const PrepBatch& pb, DType t, cudaStream_t st);
+struct FoldSeg { const float *bias, *bn_w, *bn_b, *bn_rm, *bn_rv; float *scale, *shift; int C; };
+struct FoldBatch { int count = 0; FoldSeg seg[48]; };
+int launch_fold_bn(const FoldBatch& fb, float eps, cudaStream_t st);
+
+// en_1 (cmm.py:84,95): conv3x3 c_img -> cnum on fp32 NCHW inputs of both branches; writes LeakyReLU(0.2) as
+// e1 [2][B][H][W][cnum] and ReLU into the level-1 concat buffer (B,H,W,3*cnum) at channel cnum*(1+branch).
+int launch_cmm_en1(const float* x1, const float* x2, const float* w1, const float* b1, const float* w2, const float* b2,
+                   void* e1, void* cat1, DType t, int B, int H, int W, int c_img, int cnum, cudaStream_t st);
+// SE gate (cmm.py:135-147) on fp32 NHWC halves z6 [2][B][hw][Cb] -> ReLU(z*g + z) as 16-bit (B, hw, 2*Cb).
+int launch_se_gate_nhwc(const float* z6, void* zg, DType t, const float* fc1_w, const float* fc1_b, const float* fc2_w,
+                        const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st);
+// de_1 tail (cmm.py:113-116): out[b,co,y,x] = bias[co] + sum_taps P[b, y+1-ky, x+1-kx][(ky*3+kx)*c_img + co],
+// P (B*H*W, ldp) fp32 from the tap-in-N GEMM.
+int launch_de1_gather(const float* P, int ldp, const float* bias, float* out, int B, int H, int W, int c_img,
+                      cudaStream_t st);
+
 }  // namespace dpmn

@@ -178,6 +178,14 @@ size_t dpmn_cmm_workspace_bytes(const dpmn_cmm_desc *d);
 int dpmn_cmm_forward(const dpmn_cmm_desc *d, const float *x1, const float *x2, float *out,
                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* Debug: copy one internal activation buffer of the last tensor-core dpmn_cmm_forward out of `workspace`
+ * (tests localise a parity failure to a layer with it).  which: l = 1..5 encoder outputs after LeakyReLU
+ * [2][B][H_l][W_l][C_l]; 10+l (l = 2..5) EncodeBlock intermediates; 20+l (l = 1..5) ReLU'd decoder concat
+ * inputs [B][H_l][W_l][C]; 30+l (l = 2..5) DecodeBlock intermediates; 40 en_6 outputs (fp32); 41 gated bottleneck.
+ * All NHWC, 16-bit in the precision of the descriptor unless noted. */
+size_t dpmn_cmm_debug_bytes(const dpmn_cmm_desc *d, int32_t which);
+int dpmn_cmm_debug_copy(const dpmn_cmm_desc *d, void *workspace, int32_t which, void *dst, size_t dst_bytes, void *stream);
+
 /* C (M, N) = A (M, K) * B (N, K)^T + bias (N), fp32 in/out; `precision` picks FFMA or tcgen05 operands.
  * The contraction every nn.Linear / 1x1 conv of the path reduces to; exported for unit tests. */
 int dpmn_gemm_nt(const float *A, const float *B, const float *bias, float *C, int32_t M, int32_t N, int32_t K,

@@ -138,31 +138,42 @@ def _bn(x, P, pre, training):
                         P[pre + ".weight"], P[pre + ".bias"], training=training, eps=1e-5)
 
 
-def cmm_forward(P: Dict[str, torch.Tensor], x1, x2, training: bool = False):
-    """ComplementationModulationModule.forward, cmm.py:120-161."""
+def cmm_forward(P: Dict[str, torch.Tensor], x1, x2, training: bool = False, return_parts: bool = False):
+    """ComplementationModulationModule.forward, cmm.py:120-161.  With return_parts also the per-layer tensors
+    (post-BatchNorm, pre-activation): o{l}_{br}, mid{l}_{br}, z6_{br}, zgate, d6, dmid{l}, d{l}."""
+    parts = {}
     skips, bott = [], []
     for br, x in ((1, x1), (2, x2)):
         o = [F.conv2d(x, P[f"en_1_{br}.weight"], P[f"en_1_{br}.bias"], padding=1)]
+        parts[f"o1_{br}"] = o[0]
         for lvl in (2, 3, 4, 5):
             pre = f"en_{lvl}_{br}.encode."
             t = F.conv2d(F.leaky_relu(o[-1], 0.2), P[pre + "1.weight"], P[pre + "1.bias"], stride=2, padding=3, dilation=2)
             t = _bn(t, P, pre + "2", training)
+            parts[f"mid{lvl}_{br}"] = t
             t = F.conv2d(F.leaky_relu(t, 0.2), P[pre + "4.weight"], P[pre + "4.bias"], padding=1)
             o.append(_bn(t, P, pre + "5", training))
+            parts[f"o{lvl}_{br}"] = o[-1]
         bott.append(F.conv2d(F.leaky_relu(o[-1], 0.2), P[f"en_6_{br}.1.weight"], P[f"en_6_{br}.1.bias"], stride=2, padding=1))
+        parts[f"z6_{br}"] = bott[-1]
         skips.append(o)
     z = torch.cat(bott, dim=1)
     g = z.mean(dim=(2, 3))
     g = torch.sigmoid(F.linear(F.relu(F.linear(g, P["fc_1.weight"], P["fc_1.bias"])), P["fc_2.weight"], P["fc_2.bias"]))
     z = z * g[:, :, None, None] + z
+    parts["zgate"] = z
     d = _bn(F.conv_transpose2d(F.relu(z), P["de_6.1.weight"], P["de_6.1.bias"], stride=2, padding=1), P, "de_6.2", training)
+    parts["d6"] = d
     for lvl in (5, 4, 3, 2):
         pre = f"de_{lvl}.decode."
         cat = torch.cat([d, skips[0][lvl - 1], skips[1][lvl - 1]], dim=1)
         t = _bn(F.conv_transpose2d(F.relu(cat), P[pre + "1.weight"], P[pre + "1.bias"], stride=1, padding=1), P, pre + "2", training)
+        parts[f"dmid{lvl}"] = t
         d = _bn(F.conv_transpose2d(F.relu(t), P[pre + "4.weight"], P[pre + "4.bias"], stride=2, padding=1), P, pre + "5", training)
+        parts[f"d{lvl}"] = d
     cat = torch.cat([d, skips[0][0], skips[1][0]], dim=1)
-    return F.conv_transpose2d(F.relu(cat), P["de_1.1.weight"], P["de_1.1.bias"], stride=1, padding=1)
+    y = F.conv_transpose2d(F.relu(cat), P["de_1.1.weight"], P["de_1.1.bias"], stride=1, padding=1)
+    return (y, parts) if return_parts else y
 
 
 def hot_path_forward(pgrm_params: List[Dict[str, torch.Tensor]], cmm_params, psn_out, priors_b1, priors_b2,

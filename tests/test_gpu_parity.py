@@ -239,3 +239,51 @@ def test_gemm_nt_tensor_core_matches_rounded_operands(prec):
         assert rc == 0
         ref = a.to(tt).double() @ b.to(tt).double().T + bi.double()
         assert rel_err(c.cpu().numpy(), ref.cpu().numpy()) < 2e-6   # fp32 accumulation of exactly-rounded operands
+
+
+@pytest.mark.parametrize("prec,tol", [("fp16", TOL_F16), ("bf16", TOL_BF16)])
+def test_cmm_tensor_core_modes_match_reference(prec, tol):
+    z, meta = load_golden("cmm_c64_eval")
+    P, x1, x2 = cmm_case(meta)
+    m, _ = build_cmm(meta, DEV, precision=prec)
+    with torch.no_grad():
+        y = m(_t(x1), _t(x2))
+    e = rel_err(y.cpu().numpy(), z["out"])
+    print(f"cmm_c64_eval [{prec}]: rel err {e:.3e}")
+    assert e < tol, e
+
+
+def test_cmm_tensor_core_batch_48_matches_oracle_and_is_per_image_independent():
+    from oracle import torch_ref
+    z, meta = load_golden("cmm_c64_eval")
+    P, _, _ = cmm_case(meta)
+    m, _ = build_cmm(meta, DEV, precision="fp16")
+    x1, x2 = gen.image_stream(3, 48, tag=31), gen.image_stream(3, 48, tag=32)
+    with torch.no_grad():
+        y = m(_t(x1), _t(x2))
+        y0 = m(_t(x1[7:8]), _t(x2[7:8]))
+        Pt = {k: torch.from_numpy(np.asarray(v)) for k, v in P.items()}
+        ref = torch_ref.cmm_forward(Pt, torch.from_numpy(x1[5:9]), torch.from_numpy(x2[5:9]), training=False)
+    assert torch.equal(y[7:8], y0)
+    assert rel_err(y[5:9].cpu().numpy(), ref.numpy()) < TOL_F16
+
+
+def test_full_hot_path_fp16_matches_cpu_port():
+    """6 x PGRM cascade + CMM exactly as bench.py runs it (batch 4 here), against the torch CPU port."""
+    import bench
+    from dpmn_b200.pipeline import DPMNHotPath
+    from oracle import torch_ref
+    pg, cm = bench.synth_weights(2)
+    model = DPMNHotPath(precision="fp16")
+    bench.load_weights(model, pg, cm)
+    model = model.to(DEV).eval()
+    psn, p1, p2 = bench.synth_inputs(5, 4)
+    with torch.no_grad():
+        y = model(_t(psn), [_t(a) for a in p1], [_t(a) for a in p2])
+        ref = torch_ref.hot_path_forward([{k: torch.from_numpy(np.asarray(v)) for k, v in p.items()} for p in pg],
+                                         {k: torch.from_numpy(np.asarray(v)) for k, v in cm.items()},
+                                         torch.from_numpy(psn), [torch.from_numpy(a) for a in p1],
+                                         [torch.from_numpy(a) for a in p2])
+    e = rel_err(y.cpu().numpy(), ref.numpy())
+    print("hot path fp16 vs CPU port:", e)
+    assert e < 2e-3, e   # 7 chained modules; each is within 1e-3 on its own

@@ -18,9 +18,9 @@ std::atomic<uint64_t> g_launches{0};
 // Optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream around every
 // kernel launch, tagged by kernel class.  Off by default; never active inside a timed throughput region.
 enum KTag { T_PATCH_EMBED = 0, T_LAYERNORM, T_GEMM, T_WINDOW_ATTN, T_SK_GATE, T_DWCONV, T_HEAD, T_CONV, T_BN,
-            T_SE_GATE, T_CONVERT, T_GEMM_TC, T_CONV_TC, T_PREP, T_CONV_STEM, T_COUNT };
+            T_SE_GATE, T_CONVERT, T_GEMM_TC, T_CONV_TC, T_PREP, T_CONV_STEM, T_ATTN_TC, T_COUNT };
 const char* const kTagNames[T_COUNT] = {"patch_embed", "layernorm", "gemm", "window_attn", "sk_gate",
-                                        "dwconv", "head", "conv", "bn_affine", "se_gate", "convert", "gemm_tc", "conv_tc", "weight_prep", "conv_stem"};
+                                        "dwconv", "head", "conv", "bn_affine", "se_gate", "convert", "gemm_tc", "conv_tc", "weight_prep", "conv_stem", "window_attn_tc"};
 struct ProfRec { int tag; int n; cudaEvent_t e0, e1; };
 bool g_prof = false;
 std::mutex g_prof_mu;
@@ -211,34 +211,56 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
   for (int blk = 0; blk < DPMN_MAX_BLOCKS; ++blk) {
     const dpmn_block_weights& bw = d->blocks[blk];
     const BlockOperands& op = ops[blk];
-    // ---- K1: LayerNorms + q / kv projections (pgrm.py:322-323,188,194)
-    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tq, bw.norm1_q_w, bw.norm1_q_b, w.ln, at, rows, C, st), 1);
+    // ---- K1 + K2: LayerNorms, q / kv projections, windowed attention core (pgrm.py:322-323,188,194,197-268)
+    AttnArgs a;
+    a.q = w.q; a.kv = w.kv; a.out = w.attn; a.io_type = at;
+    a.q_ld = C; a.kv_ld = 2 * C; a.v_off = C; a.out_ld = C;
+    a.B = B; a.H = H; a.W = W; a.C = C; a.n_groups = G; a.heads_per_group = d->num_heads / G;
     {
-      GemmCall g;
-      g.A = w.ln; g.lda = C; g.Bm = op.q_w; g.ldb = C; g.C = w.q; g.ldc = C; g.out_type = at;
-      g.M = rows; g.N = C; g.K = C; g.bias = bw.q_b; g.bias_mode = 1;
-      DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
-    }
-    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm1_kv_w, bw.norm1_kv_b, w.ln, at, rows, C, st), 1);
-    {
-      GemmCall g;
-      g.A = w.ln; g.lda = C; g.Bm = op.kv_w; g.ldb = C; g.C = w.kv; g.ldc = 2 * C; g.out_type = at;
-      g.M = rows; g.N = 2 * C; g.K = C; g.bias = bw.kv_b; g.bias_mode = 1;
-      DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
-    }
-    // ---- K2: windowed attention core (pgrm.py:197-268)
-    {
-      AttnArgs a;
-      a.q = w.q; a.kv = w.kv; a.out = w.attn; a.io_type = at;
-      a.q_ld = C; a.kv_ld = 2 * C; a.v_off = C; a.out_ld = C;
-      a.B = B; a.H = H; a.W = W; a.C = C; a.n_groups = G; a.heads_per_group = d->num_heads / G;
       const int mn = H < W ? H : W;
       for (int g = 0; g < G; ++g) {
         a.table[g] = bw.rpb_table[g];
         a.window[g] = d->window[g];
         a.shift[g] = (blk % 2 == 0 || mn <= d->window[g]) ? 0 : d->window[g] / 2;   // pgrm.py:148-150,362
       }
+    }
+    AttnTcArgs ta;
+    ta.qw = w.q; ta.kw = w.kv; ta.vw = (const char*)w.kv + (size_t)rows * C * 2; ta.out = w.attn; ta.io_type = at;
+    ta.B = B; ta.H = H; ta.W = W; ta.C = C; ta.n_groups = G; ta.heads_per_group = d->num_heads / G;
+    for (int g = 0; g < G; ++g) { ta.table[g] = a.table[g]; ta.window[g] = a.window[g]; ta.shift[g] = a.shift[g]; }
+    const bool tc_attn = prec != DPMN_PREC_F32 && attn_tc_supported(ta);
+
+    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tq, bw.norm1_q_w, bw.norm1_q_b, w.ln, at, rows, C, st), 1);
+    if (!tc_attn) {
+      GemmCall g;
+      g.A = w.ln; g.lda = C; g.Bm = op.q_w; g.ldb = C; g.C = w.q; g.ldc = C; g.out_type = at;
+      g.M = rows; g.N = C; g.K = C; g.bias = bw.q_b; g.bias_mode = 1;
+      DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
+    } else {
+      GemmTcArgs g;   // projection + roll + window_partition: rows land window-major per group
+      g.A = w.ln; g.lda = C; g.Bm = op.q_w; g.ldb = C; g.op_type = at; g.out_type = at;
+      g.M = rows; g.N = C; g.K = C; g.bias = bw.q_b; g.bias_mode = 1;
+      g.scatter = 1; g.scatter_C = C; g.scatter_G = G; g.scatter_H = H; g.scatter_W = W;
+      for (int i = 0; i < G; ++i) { g.scatter_ws[i] = a.window[i]; g.scatter_shift[i] = a.shift[i]; }
+      g.scatter_dst[0] = w.q;
+      DPMN_RUN(T_GEMM_TC, launch_gemm_tc(g, st), 1);
+    }
+    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm1_kv_w, bw.norm1_kv_b, w.ln, at, rows, C, st), 1);
+    if (!tc_attn) {
+      GemmCall g;
+      g.A = w.ln; g.lda = C; g.Bm = op.kv_w; g.ldb = C; g.C = w.kv; g.ldc = 2 * C; g.out_type = at;
+      g.M = rows; g.N = 2 * C; g.K = C; g.bias = bw.kv_b; g.bias_mode = 1;
+      DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
       DPMN_RUN(T_WINDOW_ATTN, launch_window_attn_simt(a, st), G);
+    } else {
+      GemmTcArgs g;
+      g.A = w.ln; g.lda = C; g.Bm = op.kv_w; g.ldb = C; g.op_type = at; g.out_type = at;
+      g.M = rows; g.N = 2 * C; g.K = C; g.bias = bw.kv_b; g.bias_mode = 1;
+      g.scatter = 1; g.scatter_C = C; g.scatter_G = G; g.scatter_H = H; g.scatter_W = W;
+      for (int i = 0; i < G; ++i) { g.scatter_ws[i] = a.window[i]; g.scatter_shift[i] = a.shift[i]; }
+      g.scatter_dst[0] = const_cast<void*>(ta.kw); g.scatter_dst[1] = const_cast<void*>(ta.vw);
+      DPMN_RUN(T_GEMM_TC, launch_gemm_tc(g, st), 1);
+      DPMN_RUN(T_ATTN_TC, launch_window_attn_tc(ta, st), 1);
     }
     if (attn_core && attn_core[blk]) {
       if (prec == DPMN_PREC_F32) {

@@ -31,6 +31,9 @@ struct GemmTcParams {
   int act;                       // 0 none, 1 GELU
   const float* residual;         // fp32, indexed like C (may alias C when C is fp32)
   float* colsum;                 // if set: no C store; colsum[z][m_tile*4 + quarter][n] = sum over 32 rows
+  int scatter, sc_C, sc_G, sc_H, sc_W, sc_cg;
+  int sc_ws[4], sc_shift[4];
+  void* sc_dst[2];
 };
 
 template <int BN>
@@ -177,6 +180,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           continue;
         }
         if (!row_ok) continue;
+        if (p.scatter) {
+          if constexpr (sizeof(OutT) == 2) {
+            if (n0 < p.N) {
+              const int L = p.sc_H * p.sc_W;
+              const int b = m / L, token = m - b * L;
+              const int which = n0 / p.sc_C, nn = n0 - which * p.sc_C;
+              const int g = nn / p.sc_cg, col = nn - g * p.sc_cg;
+              const int prow = token_to_window_row(token, p.sc_H, p.sc_W, p.sc_ws[g], p.sc_shift[g]);
+              OutT* dst = reinterpret_cast<OutT*>(p.sc_dst[which]) +
+                          (((long long)g * (p.M / L) + b) * L + prow) * p.sc_cg + col;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                union { uint4 u; OutT h[8]; } pk;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) pk.h[e] = from_f32<OutT>(v[j + e]);
+                *reinterpret_cast<uint4*>(dst + j) = pk.u;
+              }
+            }
+          }
+          continue;
+        }
         const long long off = (long long)z * p.c_bs + (long long)m * p.ldc + n0;
         if (p.residual != nullptr) {
 #pragma unroll
@@ -276,6 +300,10 @@ static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st) {
   p.C = a.C; p.c_bs = a.c_bs; p.ldc = a.ldc;
   p.bias = a.bias; p.bias_bs = a.bias_bs; p.bias_mode = a.bias ? a.bias_mode : 0;
   p.act = a.act; p.residual = a.residual; p.colsum = a.colsum;
+  p.scatter = a.scatter; p.sc_C = a.scatter_C; p.sc_G = a.scatter_G; p.sc_H = a.scatter_H; p.sc_W = a.scatter_W;
+  p.sc_cg = a.scatter_G ? a.scatter_C / a.scatter_G : 0;
+  for (int i = 0; i < 4; ++i) { p.sc_ws[i] = a.scatter_ws[i]; p.sc_shift[i] = a.scatter_shift[i]; }
+  p.sc_dst[0] = a.scatter_dst[0]; p.sc_dst[1] = a.scatter_dst[1];
   if (g_num_sms == 0) {
     int dev = 0;
     DPMN_CUDA_TRY(cudaGetDevice(&dev));
@@ -313,7 +341,11 @@ int launch_gemm_tc(const GemmTcArgs& a, cudaStream_t st) {
   if (a.K % 16 || a.lda % 8 || a.ldb % 8) return -2;                 // 16-byte TMA strides, whole UMMA k-steps
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.Bm)) & 15) return -2;
   if (a.batch > 1 && ((a.a_bs % 8) || (a.b_bs % 8))) return -2;
-  if (a.colsum == nullptr) {
+  if (a.scatter) {
+    if (a.out_type == DT_F32 || a.batch != 1 || a.scatter_G < 1 || (a.scatter_C / a.scatter_G) % 32 || a.N % a.scatter_C ||
+        a.M % (a.scatter_H * a.scatter_W))
+      return -2;
+  } else if (a.colsum == nullptr) {
     if (a.N % 8 || a.ldc % 8 || (reinterpret_cast<uintptr_t>(a.C) & 15)) return -2;   // 16-byte stores
   }
   switch (a.out_type) {

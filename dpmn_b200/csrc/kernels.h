@@ -47,6 +47,12 @@ struct GemmTcArgs {
   int act = 0;
   const float* residual = nullptr;
   float* colsum = nullptr;
+  // Window scatter (q / kv projections feeding attn_tc.cu): instead of C, every 32-column chunk of a row is
+  // written to scatter_dst[n / scatter_C] as [group][window-major row][cg] (roll + window_partition,
+  // pgrm.py:209-225, folded into this epilogue).  Rows are tokens of (B, H*W); out_type is the 16-bit type.
+  int scatter = 0, scatter_C = 0, scatter_G = 0, scatter_H = 0, scatter_W = 0;
+  int scatter_ws[4] = {}, scatter_shift[4] = {};
+  void* scatter_dst[2] = {};
 };
 int launch_gemm_tc(const GemmTcArgs& a, cudaStream_t st);
 static constexpr int kTcTileM = 128;
@@ -62,6 +68,16 @@ struct AttnArgs {
   int window[4] = {0, 0, 0, 0}, shift[4] = {0, 0, 0, 0};   // EFFECTIVE windows / shifts
 };
 int launch_window_attn_simt(const AttnArgs& a, cudaStream_t st);
+
+// tcgen05 window attention (attn_tc.cu) on window-major q / k / v: [G][B*L][C/G] 16-bit each.
+struct AttnTcArgs {
+  const void *qw = nullptr, *kw = nullptr, *vw = nullptr; void* out = nullptr; DType io_type = DT_F16;
+  const float* table[4] = {nullptr, nullptr, nullptr, nullptr};
+  int B = 0, H = 0, W = 0, C = 0, n_groups = 0, heads_per_group = 0;
+  int window[4] = {0, 0, 0, 0}, shift[4] = {0, 0, 0, 0};
+};
+bool attn_tc_supported(const AttnTcArgs& a);
+int launch_window_attn_tc(const AttnTcArgs& a, cudaStream_t st);
 
 // SK gate (pgrm.py:84-95 folded): from per-tile column sums of GELU(proj(x)) build, per image,
 // Wb = Wp + Wh * diag(softmax_G(fc2(GELU(fc1(mean))))) (C x C) and bias_b = bp + bh.

@@ -578,10 +578,96 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ h, T*
   }
 }
 
+// 16-bit variant: 64 channels x 8 rows per CTA, 16-byte global loads and stores, sliding 3x3 window in registers.
+// Phase 1 stages the input rows (with halo) as [channel][row][x] in smem (channel stride 161 words: lanes that
+// are consecutive channels hit distinct banks); phase 2 walks each (channel, row) along x; phase 3 writes the
+// transposed tile [pixel][64 channels] with one 128-byte run per pixel.
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv16_kernel(const T* __restrict__ h, T* __restrict__ dt,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       int L, int hid, int side) {
+  static_assert(sizeof(T) == 2, "16-bit storage");
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int rows_in = DW_ROWS + 2;
+  const int cstride = rows_in * side + 2;            // halves; (cstride / 2) odd for side = 32
+  T* s_in = reinterpret_cast<T*>(smraw);             // [64][cstride]
+  T* s_out = s_in + 64 * cstride;                    // [DW_ROWS * side][64]
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, y0 = blockIdx.x * DW_ROWS;
+  const T* hb = h + (long long)b * L * hid;
+  const int vec_per_row = side / 8;
+  const int n_vec = 64 * rows_in * vec_per_row;
+  for (int i = threadIdx.x; i < n_vec; i += 256) {
+    const int xv = i % vec_per_row;
+    const int r = (i / vec_per_row) % rows_in;
+    const int c = i / (vec_per_row * rows_in);
+    const int yy = y0 - 1 + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (yy >= 0 && yy < side) v = *reinterpret_cast<const uint4*>(hb + (long long)(c0 + c) * L + yy * side + xv * 8);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_in + c * cstride + r * side + xv * 8);
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+  }
+  __syncthreads();
+  {
+    const int c = threadIdx.x & 63;
+    float wk[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) wk[i] = w[(c0 + c) * 9 + i];
+    const float bb = bias[c0 + c];
+    for (int row = threadIdx.x >> 6; row < DW_ROWS; row += 4) {
+      if (y0 + row >= side) break;
+      const T* r0 = s_in + c * cstride + row * side;   // input rows row, row+1, row+2 (halo offset -1 applied)
+      const T* r1 = r0 + side;
+      const T* r2 = r1 + side;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;              // column x-1
+      float b0 = to_f32<T>(r0[0]), b1 = to_f32<T>(r1[0]), b2 = to_f32<T>(r2[0]);   // column x
+      for (int x = 0; x < side; ++x) {
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;            // column x+1
+        if (x + 1 < side) { d0 = to_f32<T>(r0[x + 1]); d1 = to_f32<T>(r1[x + 1]); d2 = to_f32<T>(r2[x + 1]); }
+        float acc = bb;
+        acc = fmaf(a0, wk[0], acc); acc = fmaf(b0, wk[1], acc); acc = fmaf(d0, wk[2], acc);
+        acc = fmaf(a1, wk[3], acc); acc = fmaf(b1, wk[4], acc); acc = fmaf(d1, wk[5], acc);
+        acc = fmaf(a2, wk[6], acc); acc = fmaf(b2, wk[7], acc); acc = fmaf(d2, wk[8], acc);
+        s_out[(row * side + x) * 64 + c] = from_f32<T>(gelu_erf(acc));
+        a0 = b0; a1 = b1; a2 = b2; b0 = d0; b1 = d1; b2 = d2;
+      }
+    }
+  }
+  __syncthreads();
+  const int n_out_vec = DW_ROWS * side * 8;            // 8 x 16 B per pixel
+  for (int i = threadIdx.x; i < n_out_vec; i += 256) {
+    const int pix_l = i >> 3, part = i & 7;
+    const int yl = pix_l / side;
+    if (y0 + yl >= side) continue;
+    const int pix = y0 * side + pix_l;
+    *reinterpret_cast<uint4*>(dt + ((long long)b * L + pix) * hid + c0 + part * 8) =
+        *reinterpret_cast<const uint4*>(s_out + pix_l * 64 + part * 8);
+  }
+}
+
+template <typename T>
+static int launch_dwconv16(const void* h, void* dt, const float* w, const float* b, int B, int L, int hid, int side,
+                           cudaStream_t st) {
+  dim3 grid((side + DW_ROWS - 1) / DW_ROWS, hid / 64, B);
+  const size_t smem = (size_t)(64 * ((DW_ROWS + 2) * side + 2) + DW_ROWS * side * 64) * 2;
+  auto k = dwconv16_kernel<T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DPMN_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  k<<<grid, 256, smem, st>>>((const T*)h, (T*)dt, w, b, L, hid, side);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_dwconv(const void* h, void* dt, DType io_type, const float* w, const float* b, int B, int L, int hid,
                   cudaStream_t st) {
   int side = (int)(sqrtf((float)L) + 0.5f);
   if (side * side != L || hid % 32 != 0) return -2;   // the reference's view() needs a perfect square too
+  if (io_type != DT_F32 && hid % 64 == 0 && side % 8 == 0 && side <= 64) {
+    return io_type == DT_F16 ? launch_dwconv16<__half>(h, dt, w, b, B, L, hid, side, st)
+                             : launch_dwconv16<__nv_bfloat16>(h, dt, w, b, B, L, hid, side, st);
+  }
   dim3 grid((side + DW_ROWS - 1) / DW_ROWS, hid / 32, B);
   const size_t smem = (size_t)32 * ((DW_ROWS + 2) * side + 1) * sizeof(float);
   if (smem > 200 * 1024) return -2;

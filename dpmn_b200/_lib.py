@@ -41,7 +41,8 @@ class PgrmDesc(C.Structure):
                 ("blocks", BlockWeights * MAX_BLOCKS),
                 ("head0_w", fp), ("head0_b", fp), ("head1_w", fp), ("head1_b", fp),
                 ("mix_weight", fp * MAX_MIX), ("mix_input", fp * MAX_MIX),
-                ("mix_input_batch_stride", C.c_int64 * MAX_MIX)]
+                ("mix_input_batch_stride", C.c_int64 * MAX_MIX),
+                ("prepared", fp), ("prepared_valid", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class Bn(C.Structure):
@@ -63,7 +64,8 @@ class CmmDesc(C.Structure):
                 ("fc1_w", fp), ("fc1_b", fp), ("fc2_w", fp), ("fc2_b", fp),
                 ("de6_w", fp), ("de6_b", fp), ("de6_bn", Bn),
                 ("dec", CmmStage * 4),
-                ("de1_w", fp), ("de1_b", fp)]
+                ("de1_w", fp), ("de1_b", fp),
+                ("prepared", fp), ("prepared_valid", C.c_int32), ("reserved_", C.c_int32)]
 
 
 # every symbol include/dpmn_b200.h declares: (restype, argtypes)
@@ -77,6 +79,8 @@ SYMBOLS = {
     "dpmn_profile_collect": (_i32, [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(C.c_float), _i32]),
     "dpmn_profile_tag_name": (C.c_char_p, [_i32]),
     "dpmn_pgrm_workspace_bytes": (_sz, [C.POINTER(PgrmDesc)]),
+    "dpmn_pgrm_prepared_bytes": (_sz, [C.POINTER(PgrmDesc)]),
+    "dpmn_cmm_prepared_bytes": (_sz, [C.POINTER(CmmDesc)]),
     "dpmn_pgrm_forward": (C.c_int, [C.POINTER(PgrmDesc), _vp, _vp, _vp, _vp, _sz, _vp]),
     "dpmn_pgrm_forward_probe": (C.c_int, [C.POINTER(PgrmDesc), _vp, _vp, _vp, _vp, _sz, _vp,
                                           C.POINTER(_vp * MAX_BLOCKS), C.POINTER(_vp * MAX_BLOCKS)]),

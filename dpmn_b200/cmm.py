@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .pgrm import ParamTree, workspace
+from .pgrm import ParamTree, PreparedWeights, workspace
 from .schema import cmm_schema
 
 
@@ -55,6 +55,7 @@ class ComplementationModulationModule(ParamTree):
                     bound = 1.0 / math.sqrt(fan_in)
                     v = v.uniform_(-bound, bound)
             self.attach(name, v, kind)
+        self._prepared = PreparedWeights()
         _lib.load()
 
     def _ptr(self, name: str) -> int:
@@ -111,6 +112,7 @@ class ComplementationModulationModule(ParamTree):
         d = self._descriptor(B, H, W)
         dev = x1.device
         with torch.cuda.device(dev):
+            prep_key = self._prepared.attach(self, d, lib.dpmn_cmm_prepared_bytes(C.byref(d)), dev)
             nbytes = lib.dpmn_cmm_workspace_bytes(C.byref(d))
             if nbytes == 0:
                 raise RuntimeError("dpmn_cmm_workspace_bytes: configuration rejected (image sides must be multiples of 32)")
@@ -119,6 +121,7 @@ class ComplementationModulationModule(ParamTree):
             rc = lib.dpmn_cmm_forward(C.byref(d), x1.data_ptr(), x2.data_ptr(), out.data_ptr(), ws.data_ptr(),
                                       ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "dpmn_cmm_forward")
+        self._prepared.key = prep_key
         if self.training:
             for name, buf in self.named_buffers():
                 if name.endswith("num_batches_tracked"):

@@ -103,9 +103,30 @@ struct BlockOperands { const void *q_w, *kv_w, *sk_proj_w, *fc1_w, *fc2_w, *pw_w
 struct PgrmWs {
   float *tq, *tkv, *colsum, *bias_b, *t1;
   void *ln, *q, *kv, *attn, *wb, *h, *dt;      // activation-typed (fp32 or 16-bit)
-  void* w16[DPMN_MAX_BLOCKS][6];               // 16-bit weight copies (tensor-core modes)
+  void* prep;                                  // staged weights when the caller passes no `prepared` buffer
   size_t bytes;
 };
+
+struct PgrmPrep {                              // staged weights of the tensor-core modes
+  void* w16[DPMN_MAX_BLOCKS][6];               // q, kv, sk_proj, fc1, fc2, pw
+  void* head_w;                                // conv_before_upsample.0 as [9][16][C] (rows 12..15 zero)
+  float* head_shift;                           // its bias padded to 16
+  size_t bytes;
+};
+
+PgrmPrep carve_pgrm_prep(const dpmn_pgrm_desc* d, void* base) {
+  const size_t C = d->embed_dim, hid = d->mlp_hidden;
+  Bump b(base, (size_t)-1);
+  PgrmPrep w;
+  memset(&w, 0, sizeof(w));
+  const size_t n[6] = {C * C, 2 * C * C, C * C, hid * C, C * hid, hid * hid};
+  for (int blk = 0; blk < DPMN_MAX_BLOCKS; ++blk)
+    for (int i = 0; i < 6; ++i) w.w16[blk][i] = b.take<char>(n[i] * 2);
+  w.head_w = b.take<char>(9 * 16 * C * 2);
+  w.head_shift = b.take<float>(16);
+  w.bytes = b.off + 256;
+  return w;
+}
 
 PgrmWs carve_pgrm(const dpmn_pgrm_desc* d, void* ws) {
   const size_t B = d->batch, C = d->embed_dim, hid = d->mlp_hidden;
@@ -129,9 +150,7 @@ PgrmWs carve_pgrm(const dpmn_pgrm_desc* d, void* ws) {
   w.dt = b.take<char>(B * L * hid * es);
   w.t1 = b.take<float>(B * L * 16);
   if (d->precision != DPMN_PREC_F32) {
-    const size_t n[6] = {C * C, 2 * C * C, C * C, hid * C, C * hid, hid * hid};
-    for (int blk = 0; blk < DPMN_MAX_BLOCKS; ++blk)
-      for (int i = 0; i < 6; ++i) w.w16[blk][i] = b.take<char>(n[i] * 2);
+    if (d->prepared == nullptr) w.prep = b.take<char>(carve_pgrm_prep(d, nullptr).bytes);
   }
   w.bytes = b.off + 256;
   return w;
@@ -179,14 +198,19 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
   const long long xq_bs = d->x_q_batch_stride ? d->x_q_batch_stride : (long long)d->q_chans * plane;
   const long long xkv_bs = d->x_kv_batch_stride ? d->x_kv_batch_stride : 3LL * plane;
 
-  // operands of the contractions: fp32 weights in place, or 16-bit copies made now (one launch)
+  // operands of the contractions: fp32 weights in place, or staged 16-bit copies
   BlockOperands ops[DPMN_MAX_BLOCKS];
+  PgrmPrep pw;
+  memset(&pw, 0, sizeof(pw));
+  const int hp = d->hidden_size * d->patch * d->patch;
+  const bool tc_head = prec != DPMN_PREC_F32 && hp <= 16 && C % 16 == 0;
   if (prec == DPMN_PREC_F32) {
     for (int blk = 0; blk < DPMN_MAX_BLOCKS; ++blk) {
       const dpmn_block_weights& bw = d->blocks[blk];
       ops[blk] = BlockOperands{bw.q_w, bw.kv_w, bw.sk_proj_w, bw.fc1_w, bw.fc2_w, bw.pw_w};
     }
   } else {
+    pw = carve_pgrm_prep(d, d->prepared ? d->prepared : w.prep);
     ConvertBatch cb;
     const long long n[6] = {(long long)C * C, 2LL * C * C, (long long)C * C, (long long)hid * C, (long long)C * hid,
                             (long long)hid * hid};
@@ -194,11 +218,20 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
       const dpmn_block_weights& bw = d->blocks[blk];
       const float* src[6] = {bw.q_w, bw.kv_w, bw.sk_proj_w, bw.fc1_w, bw.fc2_w, bw.pw_w};
       for (int i = 0; i < 6; ++i) {
-        cb.src[cb.count] = src[i]; cb.dst[cb.count] = w.w16[blk][i]; cb.n[cb.count] = n[i]; ++cb.count;
+        cb.src[cb.count] = src[i]; cb.dst[cb.count] = pw.w16[blk][i]; cb.n[cb.count] = n[i]; ++cb.count;
       }
-      ops[blk] = BlockOperands{w.w16[blk][0], w.w16[blk][1], w.w16[blk][2], w.w16[blk][3], w.w16[blk][4], w.w16[blk][5]};
+      ops[blk] = BlockOperands{pw.w16[blk][0], pw.w16[blk][1], pw.w16[blk][2], pw.w16[blk][3], pw.w16[blk][4], pw.w16[blk][5]};
     }
-    DPMN_RUN(T_CONVERT, launch_convert_batch(cb, at, st), 1);
+    if (!(d->prepared && d->prepared_valid)) {
+      DPMN_RUN(T_CONVERT, launch_convert_batch(cb, at, st), 1);
+      if (tc_head) {
+        PrepBatch pb;
+        pb.seg[pb.count++] = PrepSeg{d->head0_w, pw.head_w, hp, C, 9, 0, 16};
+        DPMN_RUN(T_PREP, launch_prep_weights(pb, at, st), 1);
+        DPMN_CUDA_TRY(cudaMemsetAsync(pw.head_shift, 0, 16 * sizeof(float), st));
+        DPMN_CUDA_TRY(cudaMemcpyAsync(pw.head_shift, d->head0_b, hp * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      }
+    }
   }
 
   // K0: both streams share the patch-embed weights (pgrm.py:549-550)
@@ -316,8 +349,26 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
   }
 
   // ---- K5: head (pgrm.py:559-564)
-  const int hp = d->hidden_size * d->patch * d->patch;
-  DPMN_RUN(T_HEAD, launch_head_conv1(w.tkv, d->head0_w, d->head0_b, w.t1, B, H, W, C, hp, st), 1);
+  if (tc_head) {
+    // conv3x3 C -> hp as a tcgen05 implicit GEMM on a 16-bit copy of the token stream (tokens are NHWC already)
+    DPMN_RUN(T_CONVERT, launch_convert(w.tkv, w.ln, at, (long long)rows * C, st), 1);
+    ConvTcArgs a;
+    a.op_type = at; a.n_src = 1;
+    a.src[0].base = w.ln; a.src[0].sx = C; a.src[0].sy = (long long)W * C; a.src[0].sb = (long long)L * C;
+    a.Cin = C; a.Cout = 16; a.B = B; a.G = 1; a.P = 1; a.Hm = H; a.Wm = W;
+    a.n_taps = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        ConvTap tp{}; tp.map = 0; tp.dy = (int8_t)(ky - 1); tp.dx = (int8_t)(kx - 1); tp.wslice = (int16_t)(ky * 3 + kx);
+        a.taps[0][ky * 3 + kx] = tp;
+      }
+    a.w = pw.head_w; a.n_wslices = 9; a.os = 1; a.Ho = H; a.Wo = W;
+    a.scale = nullptr; a.shift = pw.head_shift;
+    a.dst[0].ptr = w.t1; a.dst[0].type = DT_F32; a.dst[0].ld = 16;
+    DPMN_RUN(T_CONV_TC, launch_conv_tc(a, st), 1);
+  } else {
+    DPMN_RUN(T_HEAD, launch_head_conv1(w.tkv, d->head0_w, d->head0_b, w.t1, B, H, W, C, hp, st), 1);
+  }
   MixArgs mix;
   mix.n_mix = d->n_mix;
   for (int i = 0; i < d->n_mix; ++i) {
@@ -403,6 +454,7 @@ struct CmmTcWs {
   void* zg;          // ReLU(SE-gated bottleneck) [B][hw][16c]
   void* dmid[6];     // dmid[l], l = 5..2: ReLU'd DecodeBlock intermediates [B][H_l][W_l][Co_l]
   float* P;          // de_1 tap products [B*H*W][32]
+  float *pooled, *se_hidden;   // SE gate scratch (B, 16c), (B, 4c)
   void *w_enc_a[4], *w_enc_b[4], *w_en6, *w_de6, *w_dec_a[4], *w_dec_b[4], *w_de1;
   float *s_enc_a[4], *t_enc_a[4], *s_enc_b[4], *t_enc_b[4], *t_en6, *s_en6, *s_de6, *t_de6;
   float *s_dec_a[4], *t_dec_a[4], *s_dec_b[4], *t_dec_b[4];
@@ -419,23 +471,8 @@ struct CmmDims {
   int Ccat(int l) const { return Cd(l) + 2 * Cl(l); }
 };
 
-CmmTcWs carve_cmm_tc(const dpmn_cmm_desc* d, void* ws) {
-  const CmmDims D{d->batch, d->cnum, d->img_h, d->img_w, d->c_img};
-  const size_t B = D.B;
-  Bump b(ws, (size_t)-1);
-  CmmTcWs w;
-  memset(&w, 0, sizeof(w));
-  for (int l = 1; l <= 5; ++l) {
-    const size_t px = (size_t)D.Hl(l) * D.Wl(l);
-    w.e[l] = b.take<uint16_t>(2 * B * px * D.Cl(l));
-    if (l >= 2) w.mid[l] = b.take<uint16_t>(2 * B * px * D.Cl(l - 1));
-    w.cat[l] = b.take<uint16_t>(B * px * D.Ccat(l));
-    if (l >= 2) w.dmid[l] = b.take<uint16_t>(B * px * D.Co(l));
-  }
-  const size_t hw6 = (size_t)(D.H >> 5) * (D.W >> 5);
-  w.z6 = b.take<float>(2 * B * hw6 * 8 * D.c);
-  w.zg = b.take<uint16_t>(B * hw6 * 16 * D.c);
-  w.P = b.take<float>(B * (size_t)D.H * D.W * 32);
+size_t carve_cmm_tc_prep(const CmmDims& D, void* base, CmmTcWs& w) {
+  Bump b(base, (size_t)-1);
   for (int l = 1; l <= 4; ++l) {
     w.w_enc_a[l - 1] = b.take<uint16_t>((size_t)2 * 16 * D.Cl(l) * D.Cl(l));
     w.w_enc_b[l - 1] = b.take<uint16_t>((size_t)2 * 9 * D.Cl(l + 1) * D.Cl(l));
@@ -454,6 +491,35 @@ CmmTcWs carve_cmm_tc(const dpmn_cmm_desc* d, void* ws) {
     w.s_dec_b[i] = b.take<float>(D.Co(l)); w.t_dec_b[i] = b.take<float>(D.Co(l));
   }
   w.w_de1 = b.take<uint16_t>((size_t)32 * 3 * D.c);
+  return b.off + 256;
+}
+
+CmmTcWs carve_cmm_tc(const dpmn_cmm_desc* d, void* ws) {
+  const CmmDims D{d->batch, d->cnum, d->img_h, d->img_w, d->c_img};
+  const size_t B = D.B;
+  Bump b(ws, (size_t)-1);
+  CmmTcWs w;
+  memset(&w, 0, sizeof(w));
+  for (int l = 1; l <= 5; ++l) {
+    const size_t px = (size_t)D.Hl(l) * D.Wl(l);
+    w.e[l] = b.take<uint16_t>(2 * B * px * D.Cl(l));
+    if (l >= 2) w.mid[l] = b.take<uint16_t>(2 * B * px * D.Cl(l - 1));
+    w.cat[l] = b.take<uint16_t>(B * px * D.Ccat(l));
+    if (l >= 2) w.dmid[l] = b.take<uint16_t>(B * px * D.Co(l));
+  }
+  const size_t hw6 = (size_t)(D.H >> 5) * (D.W >> 5);
+  w.z6 = b.take<float>(2 * B * hw6 * 8 * D.c);
+  w.zg = b.take<uint16_t>(B * hw6 * 16 * D.c);
+  w.P = b.take<float>(B * (size_t)D.H * D.W * 32);
+  w.pooled = b.take<float>(B * 16 * D.c);
+  w.se_hidden = b.take<float>(B * 4 * D.c);
+  if (d->prepared != nullptr) {
+    carve_cmm_tc_prep(D, d->prepared, w);
+  } else {
+    char* base = b.take<char>(0);
+    const size_t n = carve_cmm_tc_prep(D, base, w);
+    b.take<char>(n);
+  }
   w.bytes = b.off + 256;
   return w;
 }
@@ -487,7 +553,7 @@ int cmm_forward_tc(const dpmn_cmm_desc* d, const float* x1, const float* x2, flo
   const int B = D.B, c = D.c, H = D.H, W = D.W;
 
   // ---- stage weights (16-bit, tap-major) and fold bias + eval BatchNorm into (scale, shift)
-  {
+  if (!(d->prepared && d->prepared_valid)) {
     PrepBatch pb; FoldBatch fb;
     auto prep = [&](const float* src, void* dst, int Cout, int Cin, int kk, int tr) {
       pb.seg[pb.count++] = PrepSeg{src, dst, Cout, Cin, kk, tr, Cout};
@@ -599,7 +665,8 @@ int cmm_forward_tc(const dpmn_cmm_desc* d, const float* x1, const float* x2, flo
     a.dst[0].ptr = w.z6; a.dst[0].type = DT_F32; a.dst[0].g_stride = (long long)B * H6 * W6 * C5; a.dst[0].ld = C5;
     DPMN_RUN(T_CONV_TC, launch_conv_tc(a, st), 1);
   }
-  DPMN_RUN(T_SE_GATE, launch_se_gate_nhwc(w.z6, w.zg, t, d->fc1_w, d->fc1_b, d->fc2_w, d->fc2_b, B, C5, H6 * W6, 4 * c, st), 1);
+  DPMN_RUN(T_SE_GATE, launch_se_gate_nhwc(w.z6, w.zg, t, d->fc1_w, d->fc1_b, d->fc2_w, d->fc2_b, w.pooled, w.se_hidden, B, C5,
+                                          H6 * W6, 4 * c, st), 3);
 
   // ---- decoder
   auto convt4 = [&](const void* src, int Hi, int Wi, int Ci, const void* wt, int Co, const float* sc, const float* sh,
@@ -705,6 +772,11 @@ size_t dpmn_pgrm_workspace_bytes(const dpmn_pgrm_desc* d) {
   return carve_pgrm(d, nullptr).bytes;
 }
 
+size_t dpmn_pgrm_prepared_bytes(const dpmn_pgrm_desc* d) {
+  if (check_pgrm(d) || d->precision == DPMN_PREC_F32) return 0;
+  return carve_pgrm_prep(d, nullptr).bytes;
+}
+
 int dpmn_pgrm_forward(const dpmn_pgrm_desc* d, const float* x_q, const float* x_kv, float* out, void* workspace,
                       size_t workspace_bytes, void* stream) {
   return pgrm_forward_impl(d, x_q, x_kv, out, workspace, workspace_bytes, stream, nullptr, nullptr);
@@ -788,6 +860,13 @@ size_t dpmn_cmm_workspace_bytes(const dpmn_cmm_desc* d) {
   if (check_cmm(d)) return 0;
   if (d->precision != DPMN_PREC_F32) return carve_cmm_tc(d, nullptr).bytes;
   return carve_cmm(d, nullptr).bytes;
+}
+
+size_t dpmn_cmm_prepared_bytes(const dpmn_cmm_desc* d) {
+  if (check_cmm(d) || d->precision == DPMN_PREC_F32) return 0;
+  const CmmDims D{d->batch, d->cnum, d->img_h, d->img_w, d->c_img};
+  CmmTcWs w;
+  return carve_cmm_tc_prep(D, nullptr, w);
 }
 
 size_t dpmn_cmm_debug_bytes(const dpmn_cmm_desc* d, int32_t which) {

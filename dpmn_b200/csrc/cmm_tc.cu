@@ -134,54 +134,63 @@ int launch_cmm_en1(const float* x1, const float* x2, const float* w1, const floa
 }
 
 // ---- SE gate on NHWC fp32 halves -----------------------------------------------------------------------------
+// Three small launches with one WARP per output so that the 2 x 1 MB of fc weights are read by thousands of
+// warps in parallel instead of 48 latency-bound CTAs.
+__global__ void __launch_bounds__(256) se_pool_kernel(const float* __restrict__ z6, float* __restrict__ pooled, int B,
+                                                      int Cb, int hw) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (b, c) with c in [0, 2*Cb)
+  if (idx >= B * 2 * Cb) return;
+  const int c = idx % (2 * Cb), b = idx / (2 * Cb);
+  const int g = c / Cb, cl = c - g * Cb;
+  const float* src = z6 + (((long long)g * B + b) * hw) * Cb + cl;
+  float s = 0.f;
+  for (int i = 0; i < hw; ++i) s += src[(long long)i * Cb];
+  pooled[idx] = s / (float)hw;
+}
+
+__global__ void __launch_bounds__(256) se_fc1_kernel(const float* __restrict__ pooled, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, float* __restrict__ hid, int B,
+                                                     int C2, int hidden) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * hidden) return;
+  const int j = warp % hidden, b = warp / hidden;
+  float s = 0.f;
+  for (int c = lane; c < C2; c += 32) s = fmaf(w[(long long)j * C2 + c], pooled[(long long)b * C2 + c], s);
+  s = warp_sum(s);
+  if (lane == 0) hid[warp] = fmaxf(s + bias[j], 0.f);
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256) se_gate_nhwc_kernel(const float* __restrict__ z6, T* __restrict__ zg,
-                                                           const float* __restrict__ fc1_w, const float* __restrict__ fc1_b,
-                                                           const float* __restrict__ fc2_w, const float* __restrict__ fc2_b,
-                                                           int B, int Cb, int hw, int hidden) {
-  extern __shared__ float sm[];
+__global__ void __launch_bounds__(256) se_fc2_gate_kernel(const float* __restrict__ z6, const float* __restrict__ hid,
+                                                          const float* __restrict__ w, const float* __restrict__ bias,
+                                                          T* __restrict__ zg, int B, int Cb, int hw, int hidden) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int C2 = 2 * Cb;
-  float* sg = sm;
-  float* sh = sg + C2;
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C2; c += blockDim.x) {
-    const int g = c / Cb, cl = c - g * Cb;
-    const float* src = z6 + (((long long)g * B + b) * hw) * Cb + cl;
-    float s = 0.f;
-    for (int i = 0; i < hw; ++i) s += src[(long long)i * Cb];
-    sg[c] = s / (float)hw;
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int j = warp; j < hidden; j += nw) {
-    float s = 0.f;
-    for (int c = lane; c < C2; c += 32) s = fmaf(fc1_w[(long long)j * C2 + c], sg[c], s);
-    s = warp_sum(s);
-    if (lane == 0) sh[j] = fmaxf(s + fc1_b[j], 0.f);
-  }
-  __syncthreads();
-  for (int c = warp; c < C2; c += nw) {
-    float s = 0.f;
-    for (int j = lane; j < hidden; j += 32) s = fmaf(fc2_w[(long long)c * hidden + j], sh[j], s);
-    s = warp_sum(s);
-    const float gate = 1.0f / (1.0f + expf(-(s + fc2_b[c])));
-    const int g = c / Cb, cl = c - g * Cb;
-    for (int i = lane; i < hw; i += 32) {
-      const float v = z6[(((long long)g * B + b) * hw + i) * Cb + cl];
-      zg[((long long)b * hw + i) * C2 + c] = from_f32<T>(fmaxf(fmaf(v, gate, v), 0.f));   // ReLU of de_6 folded in
-    }
+  if (warp >= B * C2) return;
+  const int c = warp % C2, b = warp / C2;
+  float s = 0.f;
+  for (int j = lane; j < hidden; j += 32) s = fmaf(w[(long long)c * hidden + j], hid[(long long)b * hidden + j], s);
+  s = warp_sum(s);
+  const float gate = 1.0f / (1.0f + expf(-(s + bias[c])));
+  const int g = c / Cb, cl = c - g * Cb;
+  for (int i = lane; i < hw; i += 32) {
+    const float v = z6[(((long long)g * B + b) * hw + i) * Cb + cl];
+    zg[((long long)b * hw + i) * C2 + c] = from_f32<T>(fmaxf(fmaf(v, gate, v), 0.f));   // ReLU of de_6 folded in
   }
 }
 
 int launch_se_gate_nhwc(const float* z6, void* zg, DType t, const float* fc1_w, const float* fc1_b, const float* fc2_w,
-                        const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * Cb + hidden) * sizeof(float);
-  if (smem > 48 * 1024) return -2;
+                        const float* fc2_b, float* pooled, float* hid_buf, int B, int Cb, int hw, int hidden,
+                        cudaStream_t st) {
+  const int C2 = 2 * Cb;
+  se_pool_kernel<<<(B * C2 + 255) / 256, 256, 0, st>>>(z6, pooled, B, Cb, hw);
+  se_fc1_kernel<<<(B * hidden * 32 + 255) / 256, 256, 0, st>>>(pooled, fc1_w, fc1_b, hid_buf, B, C2, hidden);
+  const int blocks = (B * C2 * 32 + 255) / 256;
   if (t == DT_F16)
-    se_gate_nhwc_kernel<__half><<<B, 256, smem, st>>>(z6, (__half*)zg, fc1_w, fc1_b, fc2_w, fc2_b, B, Cb, hw, hidden);
+    se_fc2_gate_kernel<__half><<<blocks, 256, 0, st>>>(z6, hid_buf, fc2_w, fc2_b, (__half*)zg, B, Cb, hw, hidden);
   else if (t == DT_BF16)
-    se_gate_nhwc_kernel<__nv_bfloat16><<<B, 256, smem, st>>>(z6, (__nv_bfloat16*)zg, fc1_w, fc1_b, fc2_w, fc2_b, B, Cb,
-                                                             hw, hidden);
+    se_fc2_gate_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(z6, hid_buf, fc2_w, fc2_b, (__nv_bfloat16*)zg, B, Cb, hw,
+                                                              hidden);
   else return -1;
   DPMN_LAUNCH_CHECK();
   return 0;

@@ -190,7 +190,8 @@ int launch_cmm_en1(const float* x1, const float* x2, const float* w1, const floa
                    void* e1, void* cat1, DType t, int B, int H, int W, int c_img, int cnum, cudaStream_t st);
 // SE gate (cmm.py:135-147) on fp32 NHWC halves z6 [2][B][hw][Cb] -> ReLU(z*g + z) as 16-bit (B, hw, 2*Cb).
 int launch_se_gate_nhwc(const float* z6, void* zg, DType t, const float* fc1_w, const float* fc1_b, const float* fc2_w,
-                        const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st);
+                        const float* fc2_b, float* pooled, float* hid_buf, int B, int Cb, int hw, int hidden,
+                        cudaStream_t st);
 // de_1 tail (cmm.py:113-116): out[b,co,y,x] = bias[co] + sum_taps P[b, y+1-ky, x+1-kx][(ky*3+kx)*c_img + co],
 // P (B*H*W, ldp) fp32 from the tap-in-N GEMM.
 int launch_de1_gather(const float* P, int ldp, const float* bias, float* out, int B, int H, int W, int c_img,

@@ -465,18 +465,24 @@ __global__ void __launch_bounds__(256) sk_gate_kernel(const float* __restrict__ 
   const int b = blockIdx.x, t = threadIdx.x;
   for (int c = t; c < C; c += blockDim.x) {
     float s = 0.f;
+#pragma unroll 8
     for (int i = 0; i < tiles; ++i) s += colsum[((long long)b * tiles + i) * C + c];
     sS[c] = s / (float)L;
   }
   __syncthreads();
-  for (int j = t; j < dz; j += blockDim.x) {
-    float s = b1[j];
-    for (int c = 0; c < C; ++c) s = fmaf(w1[j * C + c], sS[c], s);
-    sZ[j] = gelu_erf(s);
+  {
+    const int lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+    for (int j = warp; j < dz; j += nw) {               // one warp per output: coalesced, parallel loads
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) s = fmaf(w1[j * C + c], sS[c], s);
+      s = warp_sum(s);
+      if (lane == 0) sZ[j] = gelu_erf(s + b1[j]);
+    }
   }
   __syncthreads();
   for (int c = t; c < C; c += blockDim.x) {
     float s = b2[c];
+#pragma unroll 8
     for (int j = 0; j < dz; ++j) s = fmaf(w2[c * dz + j], sZ[j], s);
     sA[c] = s;
   }
@@ -489,12 +495,17 @@ __global__ void __launch_bounds__(256) sk_gate_kernel(const float* __restrict__ 
     for (int m = 0; m < G; ++m) sA[m * cg + j] = expf(sA[m * cg + j] - mx) / den;
   }
   __syncthreads();
-  for (int i = t; i < C * C; i += blockDim.x) {
+  // each of the gridDim.y CTAs of an image writes its slice of the folded weight (the tiny gate above is recomputed)
+  const int per = (C * C + gridDim.y - 1) / gridDim.y;
+  const int i_end = min(C * C, (int)(blockIdx.y + 1) * per);
+#pragma unroll 4
+  for (int i = blockIdx.y * per + t; i < i_end; i += blockDim.x) {
     const int o = i / C, c = i - o * C;
     const int j = c % cg;
     wb_out[(long long)b * C * C + i] = from_f32<WT>(fmaf(wh[o * cg + j], sA[c], wp[i]));
   }
-  for (int o = t; o < C; o += blockDim.x) bias_out[(long long)b * C + o] = bp[o] + bh[o];
+  if (blockIdx.y == 0)
+    for (int o = t; o < C; o += blockDim.x) bias_out[(long long)b * C + o] = bp[o] + bh[o];
 }
 
 int launch_sk_gate(const float* colsum, int tiles_per_image, int L, const float* wp, const float* bp,
@@ -505,15 +516,15 @@ int launch_sk_gate(const float* colsum, int tiles_per_image, int L, const float*
   const size_t smem = (size_t)(2 * C + cg / 2 + 8) * sizeof(float);
   switch (wb_type) {
     case DT_F32:
-      sk_gate_kernel<float><<<B, 256, smem, st>>>(colsum, tiles_per_image, L, wp, bp, w1, b1, w2, b2, wh, bh,
+      sk_gate_kernel<float><<<dim3(B, 4), 256, smem, st>>>(colsum, tiles_per_image, L, wp, bp, w1, b1, w2, b2, wh, bh,
                                                   (float*)wb_out, bias_out, C, G);
       break;
     case DT_F16:
-      sk_gate_kernel<__half><<<B, 256, smem, st>>>(colsum, tiles_per_image, L, wp, bp, w1, b1, w2, b2, wh, bh,
+      sk_gate_kernel<__half><<<dim3(B, 4), 256, smem, st>>>(colsum, tiles_per_image, L, wp, bp, w1, b1, w2, b2, wh, bh,
                                                    (__half*)wb_out, bias_out, C, G);
       break;
     case DT_BF16:
-      sk_gate_kernel<__nv_bfloat16><<<B, 256, smem, st>>>(colsum, tiles_per_image, L, wp, bp, w1, b1, w2, b2, wh,
+      sk_gate_kernel<__nv_bfloat16><<<dim3(B, 4), 256, smem, st>>>(colsum, tiles_per_image, L, wp, bp, w1, b1, w2, b2, wh,
                                                           bh, (__nv_bfloat16*)wb_out, bias_out, C, G);
       break;
   }

@@ -98,6 +98,26 @@ def _initial_value(name: str, shape, cfg: PGRMConfig) -> torch.Tensor:
     return nn.init.trunc_normal_(t, std=.02)   # Linear weight
 
 
+class PreparedWeights:
+    """Cache of the tensor-core modes' staged 16-bit weights (include/dpmn_b200.h `prepared`): re-staged only
+    when a parameter / buffer was modified in place (torch's version counter) or re-allocated."""
+
+    def __init__(self):
+        self.buf = None
+        self.key = None
+
+    def attach(self, module: nn.Module, d, nbytes: int, device):
+        if nbytes == 0:
+            return None
+        key = tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            self.key = None
+        d.prepared = self.buf.data_ptr()
+        d.prepared_valid = int(self.key == key)
+        return key
+
+
 class PGRM(ParamTree):
     """Prior-Guided Refinement Module, signature-compatible with the reference (pgrm.py:462-467).
 
@@ -138,6 +158,7 @@ class PGRM(ParamTree):
                 self.attach(name, torch.from_numpy(shift_mask(H, W, ws_eff[g], sh_eff[g])), "buffer")
             else:
                 raise AssertionError(name)
+        self._prepared = PreparedWeights()
         _lib.load()   # fail at construction, not at first forward, if the CUDA library is absent
 
     # ------------------------------------------------------------------------------------------
@@ -235,6 +256,7 @@ class PGRM(ParamTree):
             d.mix_input_batch_stride[i] = bs
         dev = x_kv.device
         with torch.cuda.device(dev):
+            prep_key = self._prepared.attach(self, d, lib.dpmn_pgrm_prepared_bytes(C.byref(d)), dev)
             nbytes = lib.dpmn_pgrm_workspace_bytes(C.byref(d))
             if nbytes == 0:
                 raise RuntimeError("dpmn_pgrm_workspace_bytes: configuration rejected (see DPMN_E_UNSUPPORTED rules "
@@ -246,6 +268,7 @@ class PGRM(ParamTree):
                 rc = lib.dpmn_pgrm_forward(C.byref(d), x_q.data_ptr(), x_kv.data_ptr(), out.data_ptr(), ws.data_ptr(),
                                            ws.numel(), stream)
                 _lib.check(rc, "dpmn_pgrm_forward")
+                self._prepared.key = prep_key
                 return out
             L, Cc = cfg.tokens, cfg.embed_dim
             cores = [torch.empty((B, L, Cc), dtype=torch.float32, device=dev) for _ in range(2)]
@@ -255,6 +278,7 @@ class PGRM(ParamTree):
             rc = lib.dpmn_pgrm_forward_probe(C.byref(d), x_q.data_ptr(), x_kv.data_ptr(), out.data_ptr(),
                                              ws.data_ptr(), ws.numel(), stream, C.byref(a), C.byref(b))
             _lib.check(rc, "dpmn_pgrm_forward_probe")
+            self._prepared.key = prep_key
             return out, cores, blocks
 
 

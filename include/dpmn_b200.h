@@ -96,6 +96,12 @@ typedef struct dpmn_pgrm_desc {
   const float *mix_weight[DPMN_MAX_MIX];          /* weight_list_i (1, hs, img_h, img_w) */
   const float *mix_input[DPMN_MAX_MIX];           /* residual_list[i] (B, hs, img_h, img_w) */
   int64_t mix_input_batch_stride[DPMN_MAX_MIX];   /* 0 = dense */
+  /* Tensor-core modes stage 16-bit copies of the weights.  prepared == NULL: staged in the workspace on every
+   * call.  Otherwise a caller-owned device buffer of dpmn_pgrm_prepared_bytes(): the call stages into it when
+   * prepared_valid == 0 and reuses it when prepared_valid == 1 (the caller re-validates after the weights change). */
+  void *prepared;
+  int32_t prepared_valid;
+  int32_t reserved_;
 } dpmn_pgrm_desc;
 
 /* ---- Complementation Modulation Module (cmm.py:80-161) ------------------------------------------- */
@@ -127,6 +133,9 @@ typedef struct dpmn_cmm_desc {
   dpmn_bn de6_bn;                             /* de_6.2 */
   dpmn_cmm_stage dec[4];                      /* de_5, de_4, de_3, de_2 */
   const float *de1_w, *de1_b;                 /* de_1.1 convT3x3 (3cnum, c_img) */
+  void *prepared;                             /* as in dpmn_pgrm_desc: staged tap-major 16-bit weights + folded BN */
+  int32_t prepared_valid;
+  int32_t reserved_;
 } dpmn_cmm_desc;
 
 const char *dpmn_version(void);
@@ -149,6 +158,7 @@ int32_t dpmn_profile_collect(int32_t *tags, int32_t *n_kernels, float *ms, int32
 const char *dpmn_profile_tag_name(int32_t tag);
 
 size_t dpmn_pgrm_workspace_bytes(const dpmn_pgrm_desc *d);
+size_t dpmn_pgrm_prepared_bytes(const dpmn_pgrm_desc *d);   /* 0 in the fp32 mode */
 
 /* PGRM.forward.  x_q (B, q_chans, img_h, img_w), x_kv (B, 3, img_h, img_w), out (B, hidden_size, img_h, img_w). */
 int dpmn_pgrm_forward(const dpmn_pgrm_desc *d, const float *x_q, const float *x_kv, float *out,
@@ -173,6 +183,7 @@ int dpmn_window_attn_forward(const void *q, const void *kv, void *out, const flo
 size_t dpmn_window_attn_workspace_bytes(int32_t batch, int32_t tokens, int32_t embed_dim, int32_t precision);
 
 size_t dpmn_cmm_workspace_bytes(const dpmn_cmm_desc *d);
+size_t dpmn_cmm_prepared_bytes(const dpmn_cmm_desc *d);     /* 0 in the fp32 mode */
 
 /* ComplementationModulationModule.forward.  x1, x2 (B, c_img, img_h, img_w) -> out (B, c_img, img_h, img_w). */
 int dpmn_cmm_forward(const dpmn_cmm_desc *d, const float *x1, const float *x2, float *out,

@@ -287,3 +287,29 @@ def test_full_hot_path_fp16_matches_cpu_port():
     e = rel_err(y.cpu().numpy(), ref.numpy())
     print("hot path fp16 vs CPU port:", e)
     assert e < 2e-3, e   # 7 chained modules; each is within 1e-3 on its own
+
+
+def test_prepared_weight_cache_tracks_in_place_updates():
+    """The tensor-core modes cache staged 16-bit weights; an optimizer-style in-place update must invalidate it."""
+    z, meta = load_golden("pgrm_i0_m0")
+    cfg, P, x_q, x_kv, res = pgrm_case(meta)
+    m, _ = build_pgrm(meta, DEV, precision="fp16")
+    with torch.no_grad():
+        a = m(_t(x_q), _t(x_kv), [])
+        b = m(_t(x_q), _t(x_kv), [])          # second call reuses the staged weights
+        assert torch.equal(a, b)
+        m.fetch("layers.0.blocks.0.mlp.fc2.weight").mul_(1.5)
+        c = m(_t(x_q), _t(x_kv), [])
+        m.fetch("layers.0.blocks.0.mlp.fc2.weight").div_(1.5)
+        d = m(_t(x_q), _t(x_kv), [])
+    assert not torch.equal(a, c)
+    assert rel_err(d.cpu().numpy(), a.cpu().numpy()) < 1e-3
+    zc, metac = load_golden("cmm_c64_eval")
+    Pc, x1, x2 = cmm_case(metac)
+    mc, _ = build_cmm(metac, DEV, precision="fp16")
+    with torch.no_grad():
+        a = mc(_t(x1), _t(x2))
+        assert torch.equal(a, mc(_t(x1), _t(x2)))
+        mc.fetch("de_1.1.bias").add_(1.0)
+        c = mc(_t(x1), _t(x2))
+    assert rel_err((c - a).cpu().numpy(), np.ones_like(a.cpu().numpy())) < 1e-3

@@ -77,6 +77,7 @@ struct GemmCall {
   int act = 0;
   const float* residual = nullptr;
   float* colsum = nullptr;
+  int ln_mode = 0; const float* ln_w = nullptr; const float* ln_b = nullptr; void* ln_out = nullptr; DType ln_type = DT_F16;
 };
 
 int run_gemm(int precision, const GemmCall& c, cudaStream_t st) {
@@ -93,6 +94,7 @@ int run_gemm(int precision, const GemmCall& c, cudaStream_t st) {
   g.C = c.C; g.c_bs = c.c_bs; g.ldc = c.ldc; g.out_type = c.out_type; g.M = c.M; g.N = c.N; g.K = c.K; g.batch = c.batch;
   g.bias = c.bias; g.bias_bs = c.bias_bs; g.bias_mode = c.bias_mode; g.act = c.act; g.residual = c.residual;
   g.colsum = c.colsum;
+  g.ln_mode = c.ln_mode; g.ln_w = c.ln_w; g.ln_b = c.ln_b; g.ln_out = c.ln_out; g.ln_type = c.ln_type;
   return launch_gemm_tc(g, st);
 }
 
@@ -103,6 +105,7 @@ struct BlockOperands { const void *q_w, *kv_w, *sk_proj_w, *fc1_w, *fc2_w, *pw_w
 struct PgrmWs {
   float *tq, *tkv, *colsum, *bias_b, *t1;
   void *ln, *q, *kv, *attn, *wb, *h, *dt;      // activation-typed (fp32 or 16-bit)
+  void *lnq[2], *ln2;                          // fused-LayerNorm outputs (tensor-core modes)
   void* prep;                                  // staged weights when the caller passes no `prepared` buffer
   size_t bytes;
 };
@@ -150,6 +153,7 @@ PgrmWs carve_pgrm(const dpmn_pgrm_desc* d, void* ws) {
   w.dt = b.take<char>(B * L * hid * es);
   w.t1 = b.take<float>(B * L * 16);
   if (d->precision != DPMN_PREC_F32) {
+    w.lnq[0] = b.take<char>(B * L * C * 2); w.lnq[1] = b.take<char>(B * L * C * 2); w.ln2 = b.take<char>(B * L * C * 2);
     if (d->prepared == nullptr) w.prep = b.take<char>(carve_pgrm_prep(d, nullptr).bytes);
   }
   w.bytes = b.off + 256;
@@ -234,12 +238,30 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
     }
   }
 
+  // LayerNorm fusion (tensor-core modes, C in {32,64,96,128}): every LayerNorm of the block is produced by the
+  // kernel that produces its input -- the patch embed (norm1_q of both blocks, norm1_kv of block 0) or the
+  // residual GEMM epilogue (norm2; norm1_kv of the next block) -- instead of by a pass of its own.
+  const bool fuse_ln = prec != DPMN_PREC_F32 && gemm_tc_can_fuse_row_output(C);
+
   // K0: both streams share the patch-embed weights (pgrm.py:549-550)
+  if (fuse_ln) {
+    PatchEmbedLn eq;
+    eq.count = 2; eq.type = at;
+    for (int blk = 0; blk < 2; ++blk) { eq.out[blk] = w.lnq[blk]; eq.w[blk] = d->blocks[blk].norm1_q_w; eq.b[blk] = d->blocks[blk].norm1_q_b; }
+    DPMN_RUN(T_PATCH_EMBED, launch_patch_embed(x_q, xq_bs, d->q_chans, d->q_chans == 2 ? d->prior_fusion_w : nullptr,
+                                d->prior_fusion_b, d->pe_w, d->pe_b, d->pe_norm_w, d->pe_norm_b, nullptr, B, d->img_h,
+                                d->img_w, d->patch, C, st, &eq), 1);
+    PatchEmbedLn ek;
+    ek.count = 1; ek.type = at; ek.out[0] = w.ln; ek.w[0] = d->blocks[0].norm1_kv_w; ek.b[0] = d->blocks[0].norm1_kv_b;
+    DPMN_RUN(T_PATCH_EMBED, launch_patch_embed(x_kv, xkv_bs, 3, nullptr, nullptr, d->pe_w, d->pe_b, d->pe_norm_w, d->pe_norm_b,
+                                w.tkv, B, d->img_h, d->img_w, d->patch, C, st, &ek), 1);
+  } else {
   DPMN_RUN(T_PATCH_EMBED, launch_patch_embed(x_q, xq_bs, d->q_chans, d->q_chans == 2 ? d->prior_fusion_w : nullptr,
                               d->prior_fusion_b, d->pe_w, d->pe_b, d->pe_norm_w, d->pe_norm_b, w.tq, B, d->img_h,
                               d->img_w, d->patch, C, st), 1);
   DPMN_RUN(T_PATCH_EMBED, launch_patch_embed(x_kv, xkv_bs, 3, nullptr, nullptr, d->pe_w, d->pe_b, d->pe_norm_w, d->pe_norm_b,
                               w.tkv, B, d->img_h, d->img_w, d->patch, C, st), 1);
+  }
 
   for (int blk = 0; blk < DPMN_MAX_BLOCKS; ++blk) {
     const dpmn_block_weights& bw = d->blocks[blk];
@@ -263,22 +285,23 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
     for (int g = 0; g < G; ++g) { ta.table[g] = a.table[g]; ta.window[g] = a.window[g]; ta.shift[g] = a.shift[g]; }
     const bool tc_attn = prec != DPMN_PREC_F32 && attn_tc_supported(ta);
 
-    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tq, bw.norm1_q_w, bw.norm1_q_b, w.ln, at, rows, C, st), 1);
+    const void* q_in = fuse_ln ? w.lnq[blk] : w.ln;
+    if (!fuse_ln) DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tq, bw.norm1_q_w, bw.norm1_q_b, w.ln, at, rows, C, st), 1);
     if (!tc_attn) {
       GemmCall g;
-      g.A = w.ln; g.lda = C; g.Bm = op.q_w; g.ldb = C; g.C = w.q; g.ldc = C; g.out_type = at;
+      g.A = q_in; g.lda = C; g.Bm = op.q_w; g.ldb = C; g.C = w.q; g.ldc = C; g.out_type = at;
       g.M = rows; g.N = C; g.K = C; g.bias = bw.q_b; g.bias_mode = 1;
       DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
     } else {
       GemmTcArgs g;   // projection + roll + window_partition: rows land window-major per group
-      g.A = w.ln; g.lda = C; g.Bm = op.q_w; g.ldb = C; g.op_type = at; g.out_type = at;
+      g.A = q_in; g.lda = C; g.Bm = op.q_w; g.ldb = C; g.op_type = at; g.out_type = at;
       g.M = rows; g.N = C; g.K = C; g.bias = bw.q_b; g.bias_mode = 1;
       g.scatter = 1; g.scatter_C = C; g.scatter_G = G; g.scatter_H = H; g.scatter_W = W;
       for (int i = 0; i < G; ++i) { g.scatter_ws[i] = a.window[i]; g.scatter_shift[i] = a.shift[i]; }
       g.scatter_dst[0] = w.q;
       DPMN_RUN(T_GEMM_TC, launch_gemm_tc(g, st), 1);
     }
-    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm1_kv_w, bw.norm1_kv_b, w.ln, at, rows, C, st), 1);
+    if (!fuse_ln) DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm1_kv_w, bw.norm1_kv_b, w.ln, at, rows, C, st), 1);
     if (!tc_attn) {
       GemmCall g;
       g.A = w.ln; g.lda = C; g.Bm = op.kv_w; g.ldb = C; g.C = w.kv; g.ldc = 2 * C; g.out_type = at;
@@ -319,13 +342,14 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
       g.A = w.attn; g.a_bs = (long long)L * C; g.lda = C; g.Bm = w.wb; g.b_bs = (long long)C * C; g.ldb = C;
       g.C = w.tkv; g.c_bs = (long long)L * C; g.ldc = C; g.out_type = DT_F32; g.M = L; g.N = C; g.K = C; g.batch = B;
       g.bias = w.bias_b; g.bias_bs = C; g.bias_mode = 1; g.residual = w.tkv;
+      if (fuse_ln) { g.ln_mode = 1; g.ln_w = bw.norm2_w; g.ln_b = bw.norm2_b; g.ln_out = w.ln2; g.ln_type = at; }
       DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
     }
     // ---- K4: norm2 + Mlp (pgrm.py:330, 29-41)
-    DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm2_w, bw.norm2_b, w.ln, at, rows, C, st), 1);
+    if (!fuse_ln) DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm2_w, bw.norm2_b, w.ln, at, rows, C, st), 1);
     {
       GemmCall g;   // fc1 + GELU
-      g.A = w.ln; g.lda = C; g.Bm = op.fc1_w; g.ldb = C; g.C = w.h; g.ldc = hid; g.out_type = at;
+      g.A = fuse_ln ? w.ln2 : w.ln; g.lda = C; g.Bm = op.fc1_w; g.ldb = C; g.C = w.h; g.ldc = hid; g.out_type = at;
       g.M = rows; g.N = hid; g.K = C; g.bias = bw.fc1_b; g.bias_mode = 1; g.act = 1;
       DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
     }
@@ -341,6 +365,14 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
       GemmCall g;   // fc2 on the raw (L, hid) view + residual, in place on the fp32 kv stream
       g.A = w.h; g.lda = hid; g.Bm = op.fc2_w; g.ldb = hid; g.C = w.tkv; g.ldc = C; g.out_type = DT_F32;
       g.M = rows; g.N = C; g.K = hid; g.bias = bw.fc2_b; g.bias_mode = 1; g.residual = w.tkv;
+      if (fuse_ln) {
+        if (blk + 1 < DPMN_MAX_BLOCKS) {   // the next block's norm1_kv
+          g.ln_mode = 1; g.ln_w = d->blocks[blk + 1].norm1_kv_w; g.ln_b = d->blocks[blk + 1].norm1_kv_b;
+        } else {
+          g.ln_mode = 2;                   // 16-bit copy of the final stream for the head conv
+        }
+        g.ln_out = w.ln; g.ln_type = at;
+      }
       DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
     }
     if (block_out && block_out[blk])
@@ -351,7 +383,7 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
   // ---- K5: head (pgrm.py:559-564)
   if (tc_head) {
     // conv3x3 C -> hp as a tcgen05 implicit GEMM on a 16-bit copy of the token stream (tokens are NHWC already)
-    DPMN_RUN(T_CONVERT, launch_convert(w.tkv, w.ln, at, (long long)rows * C, st), 1);
+    if (!fuse_ln) DPMN_RUN(T_CONVERT, launch_convert(w.tkv, w.ln, at, (long long)rows * C, st), 1);
     ConvTcArgs a;
     a.op_type = at; a.n_src = 1;
     a.src[0].base = w.ln; a.src[0].sx = C; a.src[0].sy = (long long)W * C; a.src[0].sb = (long long)L * C;

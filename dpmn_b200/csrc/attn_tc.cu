@@ -25,8 +25,8 @@ using namespace tc;
 
 constexpr int AT_ROWS = 128;
 constexpr int AT_STAGES = 3;
-constexpr int AT_THREADS = 192;
 constexpr int AT_HC = 2;          // heads per unit
+constexpr int AT_THREADS = 64 + AT_HC * 128;   // TMA warp, MMA warp, 4 softmax/epilogue warps per head
 
 struct AttnTcParams {
   int B, H, W, L, C, G, hpg, cg;
@@ -201,8 +201,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(p_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 4 * AT_HC); mbar_init(p_full, 4 * AT_HC); mbar_init(p_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4 * AT_HC); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -283,7 +283,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       if (it > 0) issue_pv(it - 1);
     }
   } else {
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;                       // TMEM lane quarter
+    const int h = (warp - 2) >> 2;                      // this warp set's head within the unit
     const int row = quarter * 32 + lane;
     T* out = reinterpret_cast<T*>(p.out);
     auto epilogue = [&](int j, int u_prev) {
@@ -294,23 +295,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       mbar_wait(&o_full[ob], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
       uint32_t o[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + O_COL0 + (uint32_t)(ob * AT_HC * D), o);
-      uint32_t o2[32];
-      if constexpr (AT_HC * D > 32)
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + O_COL0 + (uint32_t)(ob * AT_HC * D + 32), o2);
+      const uint32_t col = O_COL0 + (uint32_t)(ob * AT_HC * D + h * D);
+      if constexpr (D == 16) tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + col, o);
+      else tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + col, o);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[ob]);
-      T* dst = out + ((long long)tile * AT_ROWS + row) * p.C + g * p.cg + hc * AT_HC * D;
+      T* dst = out + ((long long)tile * AT_ROWS + row) * p.C + g * p.cg + (hc * AT_HC + h) * D;
 #pragma unroll
-      for (int c = 0; c < AT_HC * D; c += 8) {
-        union { uint4 u; T h[8]; } pk;
+      for (int c = 0; c < D; c += 8) {
+        union { uint4 u; T hh[8]; } pk;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int idx = c + e;
-          pk.h[e] = from_f32<T>(__uint_as_float(idx < 32 ? o[idx & 31] : o2[idx & 31]));
-        }
+        for (int e = 0; e < 8; ++e) pk.hh[e] = from_f32<T>(__uint_as_float(o[c + e]));
         *reinterpret_cast<uint4*>(dst + c) = pk.u;
       }
     };
@@ -333,8 +330,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       mbar_wait(s_full, (uint32_t)(it & 1));
       tc_fence_after();
       mbar_wait(p_empty, (uint32_t)((it & 1) ^ 1));
-#pragma unroll
-      for (int h = 0; h < AT_HC; ++h) {
+      {
         const float* tab = s_tab + (g * p.hpg + hc * AT_HC + h) * TAB_STRIDE;
         const uint32_t ts = tmem_base + (uint32_t)(h * 128);
         uint8_t* pt = p_tiles + h * S::P_TILE;

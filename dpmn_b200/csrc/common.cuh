@@ -24,6 +24,18 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// GELU for the 16-bit modes: x * sigmoid(x * q(x^2)) with q fitted to logit(Phi(x)) / x (degree 2 in x^2, max
+// |abs err| 2.5e-5 on the whole real line -- 20x below fp16 rounding at |y| ~ 1).  9 instructions (EX2 + RCP)
+// instead of erff's ~30.  The coefficients carry the factor -log2(e) so that exp() is a bare ex2.
+// The fp32 mode keeps the exact erff form above.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float u = fminf(x * x, 64.0f);
+  float q = fmaf(1.0142650e-3f, u, -1.0677574e-1f);      // -log2e * (-0.00070303491, 0.07401130084)
+  q = fmaf(q, u, -2.3011213f);                            // -log2e * 1.59501575816
+  const float e = exp2f(x * q);
+  return __fdividef(x, 1.0f + e);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -40,6 +52,15 @@ template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// two adjacent 16-bit values (4-byte aligned) -> float2
+template <typename T> __device__ __forceinline__ float2 to_f32x2(const T* p);
+template <> __device__ __forceinline__ float2 to_f32x2<__half>(const __half* p) {
+  return __half22float2(*reinterpret_cast<const __half2*>(p));
+}
+template <> __device__ __forceinline__ float2 to_f32x2<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
 
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }

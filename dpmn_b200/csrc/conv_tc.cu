@@ -24,7 +24,7 @@ using namespace tc;
 
 constexpr int CBM = 128;
 constexpr int CBK = 64;
-constexpr int CSTAGES = 4;
+constexpr int CSTAGES = 3;   // <= 113 KB per CTA so that two CTAs share an SM
 constexpr int CONV_THREADS = 192;
 
 struct ConvTcParams {
@@ -81,7 +81,7 @@ __device__ __forceinline__ void store_chunk(const ConvTcDest& d, int g, long lon
 }
 
 template <int BN>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(CONV_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ ConvTcParams p) {
@@ -189,10 +189,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const long long pix = ((long long)b * p.Ho + (y * p.os + (cls >> 1))) * p.Wo + (x * p.os + (cls & 1));
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int n0 = n_blk * BN + c0;
+        // per-channel scale / shift first, unpredicated (clamped columns): in-order issue must not serialise them
+        float4 sc4[8], sh4[8];
+        if (p.scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sc4[j] = *reinterpret_cast<const float4*>(p.scale + (long long)g * p.Cout + min(n0 + 4 * j, p.Cout - 4));
+        }
+        if (p.shift != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sh4[j] = *reinterpret_cast<const float4*>(p.shift + (long long)g * p.Cout + min(n0 + 4 * j, p.Cout - 4));
+        }
         uint32_t rr[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), rr);
         tmem_ld_wait();
-        const int n0 = n_blk * BN + c0;
         if (!ok || n0 >= p.Cout) continue;
         const int ncols = p.Cout - n0 < 32 ? p.Cout - n0 : 32;
         float v[32];
@@ -200,21 +212,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
         if (p.scale != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-              const float4 sc = *reinterpret_cast<const float4*>(p.scale + (long long)g * p.Cout + n0 + j);
-              v[j] *= sc.x; v[j + 1] *= sc.y; v[j + 2] *= sc.z; v[j + 3] *= sc.w;
-            }
-          }
+          for (int j = 0; j < 8; ++j) { v[4 * j] *= sc4[j].x; v[4 * j + 1] *= sc4[j].y; v[4 * j + 2] *= sc4[j].z; v[4 * j + 3] *= sc4[j].w; }
         }
         if (p.shift != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-              const float4 sh = *reinterpret_cast<const float4*>(p.shift + (long long)g * p.Cout + n0 + j);
-              v[j] += sh.x; v[j + 1] += sh.y; v[j + 2] += sh.z; v[j + 3] += sh.w;
-            }
-          }
+          for (int j = 0; j < 8; ++j) { v[4 * j] += sh4[j].x; v[4 * j + 1] += sh4[j].y; v[4 * j + 2] += sh4[j].z; v[4 * j + 3] += sh4[j].w; }
         }
 #pragma unroll
         for (int di = 0; di < 2; ++di) {
@@ -286,7 +288,7 @@ static int launch_conv_bn(const ConvTcArgs& a, cudaStream_t st) {
     DPMN_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int total = p.G * p.P * p.wt * p.ht * p.bt * p.n_tiles;
-  const int grid = total < num_sms ? total : num_sms;
+  const int grid = total < 2 * num_sms ? total : 2 * num_sms;
   auto kern = conv_tc_kernel<BN>;
   constexpr int smem = ConvSmem<BN>::TOTAL;
   static bool attr_set = false;
@@ -313,7 +315,7 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st) {
   int bn = 128;
   if (a.Cout <= 32) bn = 32;
   else if (a.Cout <= 64) bn = 64;
-  else if (pix_tiles * ((a.Cout + 127) / 128) < 148) bn = 64;
+  else if (pix_tiles * ((a.Cout + 127) / 128) < 2 * 148) bn = 64;
   switch (bn) {
     case 32: return launch_conv_bn<32>(a, st);
     case 64: return launch_conv_bn<64>(a, st);

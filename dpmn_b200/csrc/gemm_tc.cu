@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace dpmn {
 
@@ -17,8 +18,13 @@ using namespace tc;
 
 constexpr int TBM = 128;       // tile rows (UMMA M)
 constexpr int TBK = 64;        // k-block: 64 x 16-bit = one 128-byte swizzle row
-constexpr int TSTAGES = 4;
 constexpr int TC_THREADS = 192;
+// Two CTAs per SM: the epilogue (4 warps, latency-bound loads/stores) of one CTA overlaps the other CTA's work.
+// Shared memory (<= 113 KB per CTA) and TMEM (<= 256 of 512 columns per CTA) are sized per N tile.
+template <int BN> struct TcCfg {
+  static constexpr int STAGES = BN <= 128 ? 3 : 2;
+  static constexpr int ACC = BN <= 128 ? 2 : 1;        // TMEM accumulator stages
+};
 
 struct GemmTcParams {
   int M, N, K, batch;
@@ -31,6 +37,9 @@ struct GemmTcParams {
   int act;                       // 0 none, 1 GELU
   const float* residual;         // fp32, indexed like C (may alias C when C is fp32)
   float* colsum;                 // if set: no C store; colsum[z][m_tile*4 + quarter][n] = sum over 32 rows
+  int ln_mode;                   // second output of the finished row: 0 none, 1 LayerNorm(ln_w, ln_b), 2 copy
+  const float *ln_w, *ln_b;
+  void* ln_out; int ln_type;     // (batch*M, N) rows of ln_type; requires N == BN <= 128
   int scatter, sc_C, sc_G, sc_H, sc_W, sc_cg;
   int sc_ws[4], sc_shift[4];
   void* sc_dst[2];
@@ -41,16 +50,18 @@ struct TcSmem {
   static constexpr int A_BYTES = TBM * TBK * 2;
   static constexpr int B_BYTES = BN * TBK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = TSTAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int TOTAL = TcCfg<BN>::STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, typename OutT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BN, typename OutT, bool LN>
+__global__ void __launch_bounds__(TC_THREADS, LN ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   using S = TcSmem<BN>;
+  constexpr int TSTAGES = TcCfg<BN>::STAGES;
+  constexpr int ACC = TcCfg<BN>::ACC;
   uint8_t* tiles = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TSTAGES * S::STAGE_BYTES);
   uint64_t* full_bar = bars;                    // [TSTAGES]
@@ -59,8 +70,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_empty = bars + 2 * TSTAGES + 2;// [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TSTAGES + 4);
 
-  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
+  constexpr uint32_t TMEM_COLS = (ACC * BN <= 32) ? 32 : (ACC * BN <= 64) ? 64 : (ACC * BN <= 128) ? 128 : 256;
+  static_assert(ACC * BN <= 256, "two co-resident CTAs share the 512 TMEM columns");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + TBK - 1) / TBK;
@@ -122,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -139,27 +150,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool row_ok = m < p.M;
       const float* bias = p.bias ? p.bias + (long long)z * p.bias_bs : nullptr;
       const float bias_m = (p.bias_mode == 2 && row_ok) ? bias[m] : 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      constexpr bool kCanLn = LN;                      // the whole output row passes through one thread
+      float rowbuf[kCanLn ? BN : 1];
+      const int m_ld = row_ok ? m : (p.M - 1);          // clamped row: loads are issued unconditionally
+      auto do_chunk = [&](const int c0) {
+        const int n0 = n_blk * BN + c0;
+        // (1) issue every global load of this chunk first, unpredicated (columns clamped into range), so that the
+        //     in-order issue of the warp does not serialise one L2/DRAM round trip per float4
+        float4 bb[8], rr[8];
+        if (p.bias_mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int nc = min(n0 + 4 * j, p.N - 4);
+            bb[j] = *reinterpret_cast<const float4*>(bias + nc);
+          }
+        }
+        const long long off = (long long)z * p.c_bs + (long long)m * p.ldc + n0;
+        if (p.residual != nullptr) {
+          const long long off_ld = (long long)z * p.c_bs + (long long)m_ld * p.ldc;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int nc = min(n0 + 4 * j, p.N - 4);
+            rr[j] = *reinterpret_cast<const float4*>(p.residual + off_ld + nc);
+          }
+        }
+        // (2) accumulator chunk
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), r);
         tmem_ld_wait();
-        const int n0 = n_blk * BN + c0;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_m;
         if (p.bias_mode == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n0 + j < p.N) {
-              const float4 bb = *reinterpret_cast<const float4*>(bias + n0 + j);
-              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
-            }
-          }
+          for (int j = 0; j < 8; ++j) { v[4 * j] += bb[j].x; v[4 * j + 1] += bb[j].y; v[4 * j + 2] += bb[j].z; v[4 * j + 3] += bb[j].w; }
         }
         if (p.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
         }
         if (p.colsum != nullptr) {
           // butterfly transpose-reduce over the warp's 32 rows: lane l ends with the sum of column l
@@ -177,12 +205,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if (n0 + lane < p.N)
             p.colsum[((long long)z * (p.m_tiles * 4) + m_blk * 4 + quarter) * p.N + n0 + lane] = v[0];
-          continue;
+          return;
         }
-        if (!row_ok) continue;
         if (p.scatter) {
           if constexpr (sizeof(OutT) == 2) {
-            if (n0 < p.N) {
+            if (row_ok && n0 < p.N) {
               const int L = p.sc_H * p.sc_W;
               const int b = m / L, token = m - b * L;
               const int which = n0 / p.sc_C, nn = n0 - which * p.sc_C;
@@ -199,18 +226,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           }
-          continue;
+          return;
         }
-        const long long off = (long long)z * p.c_bs + (long long)m * p.ldc + n0;
         if (p.residual != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n0 + j < p.N) {
-              const float4 rr = *reinterpret_cast<const float4*>(p.residual + off + j);
-              v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
-            }
+          for (int j = 0; j < 8; ++j) { v[4 * j] += rr[j].x; v[4 * j + 1] += rr[j].y; v[4 * j + 2] += rr[j].z; v[4 * j + 3] += rr[j].w; }
+        }
+        if constexpr (kCanLn) {
+          if (p.ln_mode != 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rowbuf[c0 + j] = v[j];   // static index: the chunk loop is fully unrolled
           }
         }
+        if (!row_ok) return;
         if constexpr (sizeof(OutT) == 4) {
           float* dst = reinterpret_cast<float*>(p.C) + off;
 #pragma unroll
@@ -228,11 +256,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
         }
+      };
+      if constexpr (kCanLn) {
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) do_chunk(c0);
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) do_chunk(c0);
       }
+      // the accumulator stage is free as soon as its last chunk has been read
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if constexpr (kCanLn) {
+        // (optional) second output computed from the finished row: LayerNorm of it (the next consumer's norm,
+        // pgrm.py:322-323,330) or a plain narrow copy -- saves a full read+write pass over the token stream
+        if (p.ln_mode != 0 && row_ok) {
+          float mu = 0.f, rstd = 1.f;
+          if (p.ln_mode == 1) {
+            float s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < BN; ++j) s1 += rowbuf[j];
+            mu = s1 * (1.0f / BN);
+            float s2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < BN; ++j) { const float dlt = rowbuf[j] - mu; s2 = fmaf(dlt, dlt, s2); }
+            rstd = rsqrtf(s2 * (1.0f / BN) + 1e-5f);
+          }
+          const long long roff = ((long long)z * p.M + m) * BN;
+#pragma unroll
+          for (int j = 0; j < BN; j += 8) {
+            float y[8];
+            if (p.ln_mode == 1) {
+              const float4 w0 = *reinterpret_cast<const float4*>(p.ln_w + j), w1 = *reinterpret_cast<const float4*>(p.ln_w + j + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(p.ln_b + j), b1 = *reinterpret_cast<const float4*>(p.ln_b + j + 4);
+              const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+              const float bq[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) y[e] = (rowbuf[j + e] - mu) * rstd * ww[e] + bq[e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) y[e] = rowbuf[j + e];
+            }
+            if (p.ln_type == DT_F32) {
+              float* dst = reinterpret_cast<float*>(p.ln_out) + roff + j;
+              *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            } else if (p.ln_type == DT_F16) {
+              union { uint4 u; __half h[8]; } pk;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pk.h[e] = __float2half_rn(y[e]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.ln_out) + roff + j) = pk.u;
+            } else {
+              union { uint4 u; __nv_bfloat16 h[8]; } pk;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pk.h[e] = __float2bfloat16_rn(y[e]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.ln_out) + roff + j) = pk.u;
+            }
+          }
+        }
+      }
+      if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -273,7 +357,7 @@ int make_tensor_map_16bit(CUtensorMap* map, const void* base, int rank, const ui
 
 static int g_num_sms = 0;
 
-template <int BN, typename OutT>
+template <int BN, typename OutT, bool LN>
 static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st) {
   CUtensorMap map_a, map_b;
   {
@@ -300,6 +384,9 @@ static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st) {
   p.C = a.C; p.c_bs = a.c_bs; p.ldc = a.ldc;
   p.bias = a.bias; p.bias_bs = a.bias_bs; p.bias_mode = a.bias ? a.bias_mode : 0;
   p.act = a.act; p.residual = a.residual; p.colsum = a.colsum;
+  p.ln_mode = a.ln_mode; p.ln_w = a.ln_w; p.ln_b = a.ln_b; p.ln_out = a.ln_out; p.ln_type = a.ln_type;
+  if ((a.ln_mode != 0) != LN) return -2;
+  if (a.ln_mode != 0 && (BN > 128 || a.N != BN || a.colsum || a.scatter || !a.ln_out)) return -2;
   p.scatter = a.scatter; p.sc_C = a.scatter_C; p.sc_G = a.scatter_G; p.sc_H = a.scatter_H; p.sc_W = a.scatter_W;
   p.sc_cg = a.scatter_G ? a.scatter_C / a.scatter_G : 0;
   for (int i = 0; i < 4; ++i) { p.sc_ws[i] = a.scatter_ws[i]; p.sc_shift[i] = a.scatter_shift[i]; }
@@ -310,8 +397,10 @@ static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st) {
     DPMN_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int total = p.batch * p.m_tiles * p.n_tiles;
-  const int grid = total < g_num_sms ? total : g_num_sms;
-  auto kern = gemm_tc_kernel<BN, OutT>;
+  static const int env_per_sm = getenv("DPMN_TC_PER_SM") ? atoi(getenv("DPMN_TC_PER_SM")) : 2;
+  const int per_sm = LN ? 1 : (env_per_sm >= 2 ? 2 : 1);
+  const int grid = total < per_sm * g_num_sms ? total : per_sm * g_num_sms;
+  auto kern = gemm_tc_kernel<BN, OutT, LN>;
   constexpr int smem = TcSmem<BN>::TOTAL;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
@@ -327,14 +416,25 @@ template <typename OutT>
 static int launch_tc_out(const GemmTcArgs& a, cudaStream_t st) {
   // N tile: the largest of {256, 192, 128, 96, 64, 32} that divides N (fewest wasted columns), else 128 with a tail
   const int N = a.N;
-  if (N % 256 == 0) return launch_tc_bn<256, OutT>(a, st);
-  if (N % 192 == 0) return launch_tc_bn<192, OutT>(a, st);
-  if (N % 128 == 0) return launch_tc_bn<128, OutT>(a, st);
-  if (N % 96 == 0) return launch_tc_bn<96, OutT>(a, st);
-  if (N % 64 == 0) return launch_tc_bn<64, OutT>(a, st);
-  if (N % 32 == 0) return launch_tc_bn<32, OutT>(a, st);
-  return launch_tc_bn<128, OutT>(a, st);
+  if (a.ln_mode != 0) {
+    if constexpr (sizeof(OutT) == 4) {     // the fused second output exists for the fp32 residual-stream GEMMs
+      if (N == 128) return launch_tc_bn<128, OutT, true>(a, st);
+      if (N == 96) return launch_tc_bn<96, OutT, true>(a, st);
+      if (N == 64) return launch_tc_bn<64, OutT, true>(a, st);
+      if (N == 32) return launch_tc_bn<32, OutT, true>(a, st);
+    }
+    return -2;
+  }
+  if (N % 256 == 0) return launch_tc_bn<256, OutT, false>(a, st);
+  if (N % 192 == 0) return launch_tc_bn<192, OutT, false>(a, st);
+  if (N % 128 == 0) return launch_tc_bn<128, OutT, false>(a, st);
+  if (N % 96 == 0) return launch_tc_bn<96, OutT, false>(a, st);
+  if (N % 64 == 0) return launch_tc_bn<64, OutT, false>(a, st);
+  if (N % 32 == 0) return launch_tc_bn<32, OutT, false>(a, st);
+  return launch_tc_bn<128, OutT, false>(a, st);
 }
+
+bool gemm_tc_can_fuse_row_output(int N) { return N == 32 || N == 64 || N == 96 || N == 128; }
 
 int launch_gemm_tc(const GemmTcArgs& a, cudaStream_t st) {
   if (a.op_type != DT_F16 && a.op_type != DT_BF16) return -1;

@@ -12,9 +12,16 @@ inline size_t dtype_size(DType t) { return t == DT_F32 ? 4 : 2; }
 
 // prior_fusion (optional, in_ch == 2) + PatchEmbed conv(k=s=patch) + LayerNorm -> tokens (B, L, C) fp32.
 // x is NCHW with an arbitrary batch stride (elements); channel/row strides are dense.
+// Optionally also writes up to two further LayerNorms of every token (the consumers' norm1_q / norm1_kv) as
+// (B*L, C) tensors of `type`; `tokens` may then be nullptr (the query stream is only ever read through norm1_q).
+struct PatchEmbedLn {
+  int count = 0; int type = 0;
+  void* out[2] = {}; const float* w[2] = {}; const float* b[2] = {};
+};
 int launch_patch_embed(const float* x, long long x_bs, int in_ch, const float* fuse_w, const float* fuse_b,
                        const float* pe_w, const float* pe_b, const float* ln_w, const float* ln_b, float* tokens,
-                       int B, int img_h, int img_w, int patch, int C, cudaStream_t st);
+                       int B, int img_h, int img_w, int patch, int C, cudaStream_t st,
+                       const PatchEmbedLn* extra = nullptr);
 
 // LayerNorm over the last dim of (rows, C) fp32 -> out (rows, C) of `out_type`.
 int launch_layernorm(const float* x, const float* w, const float* b, void* out, DType out_type, int rows, int C,
@@ -47,6 +54,9 @@ struct GemmTcArgs {
   int act = 0;
   const float* residual = nullptr;
   float* colsum = nullptr;
+  // Second output from the finished row (needs N == the N tile <= 128): ln_mode 1 = LayerNorm(ln_w, ln_b) of the
+  // row, 2 = plain copy; written as (batch*M, N) of ln_type.
+  int ln_mode = 0; const float* ln_w = nullptr; const float* ln_b = nullptr; void* ln_out = nullptr; DType ln_type = DT_F16;
   // Window scatter (q / kv projections feeding attn_tc.cu): instead of C, every 32-column chunk of a row is
   // written to scatter_dst[n / scatter_C] as [group][window-major row][cg] (roll + window_partition,
   // pgrm.py:209-225, folded into this epilogue).  Rows are tokens of (B, H*W); out_type is the 16-bit type.
@@ -55,6 +65,7 @@ struct GemmTcArgs {
   void* scatter_dst[2] = {};
 };
 int launch_gemm_tc(const GemmTcArgs& a, cudaStream_t st);
+bool gemm_tc_can_fuse_row_output(int N);   // ln_mode != 0 is available for these N (fp32 C only)
 static constexpr int kTcTileM = 128;
 
 // Windowed attention core, SIMT (any precision of q/kv/out storage).  q (B,L,*) and kv (B,L,*) in token

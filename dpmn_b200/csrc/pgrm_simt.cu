@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(
     const float* __restrict__ x, long long x_bs, int in_ch, const float* __restrict__ fuse_w,
     const float* __restrict__ fuse_b, const float* __restrict__ pe_w, const float* __restrict__ pe_b,
     const float* __restrict__ ln_w, const float* __restrict__ ln_b, float* __restrict__ tokens, int B, int img_h,
-    int img_w, int patch, int n_tokens_total) {
+    int img_w, int patch, int n_tokens_total, PatchEmbedLn extra) {
   constexpr int C = CPL * 32;
   extern __shared__ float smem[];
   const int pk = 3 * patch * patch;              // inputs of the patch conv per token (<= 32)
@@ -94,16 +94,188 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(
 #pragma unroll
     for (int i = 0; i < CPL; ++i) { const float d = o[i] - mu; q = fmaf(d, d, q); }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+    float tv[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) tv[i] = (o[i] - mu) * rstd * lw_r[i] + lb_r[i];
+    if (tokens != nullptr) {
+      float* dst = tokens + (long long)tok * C;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) dst[lane + 32 * i] = tv[i];
+    }
+    if (extra.count > 0) {
+      // the consumers' own LayerNorms (norm1_q of both blocks / norm1_kv of block 0, pgrm.py:322-323) of the token
+      float s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) s2 += tv[i];
+      const float mu2 = warp_sum(s2) * (1.0f / C);
+      float q2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) { const float d = tv[i] - mu2; q2 = fmaf(d, d, q2); }
+      const float rstd2 = rsqrtf(warp_sum(q2) * (1.0f / C) + 1e-5f);
+      for (int k = 0; k < extra.count; ++k) {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          const int c = lane + 32 * i;
+          const float y = (tv[i] - mu2) * rstd2 * extra.w[k][c] + extra.b[k][c];
+          const long long idx = (long long)tok * C + c;
+          if (extra.type == DT_F32) reinterpret_cast<float*>(extra.out[k])[idx] = y;
+          else if (extra.type == DT_F16) reinterpret_cast<__half*>(extra.out[k])[idx] = __float2half_rn(y);
+          else reinterpret_cast<__nv_bfloat16*>(extra.out[k])[idx] = __float2bfloat16_rn(y);
+        }
+      }
+    }
+  }
+}
+
+// Thread-per-token variant (C = 96, patch 2): all C accumulators of a token live in one thread, so both
+// LayerNorm levels are register-local (no shuffles) and the weights are smem broadcasts.  ~10x fewer issue slots
+// than the warp-per-token kernel above, which remains the generic fallback.
+template <int C>
+__global__ void __launch_bounds__(128) patch_embed_tok_kernel(
+    const float* __restrict__ x, long long x_bs, int in_ch, const float* __restrict__ fuse_w,
+    const float* __restrict__ fuse_b, const float* __restrict__ pe_w, const float* __restrict__ pe_b,
+    const float* __restrict__ ln_w, const float* __restrict__ ln_b, float* __restrict__ tokens, int B, int img_h,
+    int img_w, int n_tokens_total, PatchEmbedLn extra) {
+  __shared__ __align__(16) float s_w[12 * C];      // [k][c]
+  __shared__ __align__(16) float s_aff[6 * C];     // pe bias, ln w, ln b, + up to... (extra affines read from global)
+  __shared__ float s_fw[54 + 3];
+  for (int i = threadIdx.x; i < 12 * C; i += blockDim.x) {
+    const int k = i / C, c = i - k * C;
+    s_w[i] = pe_w[c * 12 + k];
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_aff[i] = pe_b[i]; s_aff[C + i] = ln_w[i]; s_aff[2 * C + i] = ln_b[i]; }
+  if (fuse_w != nullptr)
+    for (int i = threadIdx.x; i < 57; i += blockDim.x) s_fw[i] = i < 54 ? fuse_w[i] : fuse_b[i - 54];
+  __syncthreads();
+  const int tok = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= n_tokens_total) return;
+  const int gw = img_w / 2, gh = img_h / 2, L = gh * gw;
+  const int b = tok / L, t = tok - b * L;
+  const int ty = t / gw, tx = t - ty * gw;
+  const long long plane = (long long)img_h * img_w;
+  const float* xb = x + (long long)b * x_bs;
+  float in[12];   // (ch, dy, dx)
+  if (fuse_w == nullptr) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const float2 v = *reinterpret_cast<const float2*>(xb + ch * plane + (long long)(2 * ty + dy) * img_w + 2 * tx);
+        in[ch * 4 + dy * 2] = v.x; in[ch * 4 + dy * 2 + 1] = v.y;
+      }
+  } else {
+    // prior_fusion conv3x3 pad 1 (in_ch -> 3) at the 2x2 pixels of this token: a 4x4 input patch per channel
+    float patch[2][4][4];
+    for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int yy = 2 * ty - 1 + r;
+#pragma unroll
+        for (int cidx = 0; cidx < 4; ++cidx) {
+          const int xx = 2 * tx - 1 + cidx;
+          patch[ci][r][cidx] = (ci < in_ch && yy >= 0 && yy < img_h && xx >= 0 && xx < img_w)
+                                   ? xb[ci * plane + (long long)yy * img_w + xx] : 0.f;
+        }
+      }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float acc = s_fw[54 + ch];
+          for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx)
+                acc = fmaf(patch[ci][dy + ky][dx + kx], s_fw[(ch * in_ch + ci) * 9 + ky * 3 + kx], acc);
+          in[ch * 4 + dy * 2 + dx] = acc;
+        }
+  }
+  float o[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) o[c] = s_aff[c];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+#pragma unroll
+    for (int c = 0; c < C; c += 4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(&s_w[k * C + c]);
+      o[c] = fmaf(in[k], w4.x, o[c]); o[c + 1] = fmaf(in[k], w4.y, o[c + 1]);
+      o[c + 2] = fmaf(in[k], w4.z, o[c + 2]); o[c + 3] = fmaf(in[k], w4.w, o[c + 3]);
+    }
+  }
+  auto layer_norm_inplace = [&](const float* w, const float* bsrc, bool from_smem) {
+    float s1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) s1 += o[c];
+    const float mu = s1 * (1.0f / C);
+    float s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { const float dlt = o[c] - mu; s2 = fmaf(dlt, dlt, s2); }
+    const float rstd = rsqrtf(s2 * (1.0f / C) + 1e-5f);
+    (void)from_smem;
+#pragma unroll
+    for (int c = 0; c < C; ++c) o[c] = (o[c] - mu) * rstd * w[c] + bsrc[c];
+  };
+  layer_norm_inplace(s_aff + C, s_aff + 2 * C, true);          // patch_embed.norm
+  if (tokens != nullptr) {
     float* dst = tokens + (long long)tok * C;
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) dst[lane + 32 * i] = (o[i] - mu) * rstd * lw_r[i] + lb_r[i];
+    for (int c = 0; c < C; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+  }
+  if (extra.count > 0) {
+    float s1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) s1 += o[c];
+    const float mu = s1 * (1.0f / C);
+    float s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { const float dlt = o[c] - mu; s2 = fmaf(dlt, dlt, s2); }
+    const float rstd = rsqrtf(s2 * (1.0f / C) + 1e-5f);
+    for (int k = 0; k < extra.count; ++k) {
+      const float* w = extra.w[k];
+      const float* bb = extra.b[k];
+      const long long base = (long long)tok * C;
+#pragma unroll
+      for (int c = 0; c < C; c += 8) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = (o[c + e] - mu) * rstd * __ldg(w + c + e) + __ldg(bb + c + e);
+        if (extra.type == DT_F32) {
+          float* dst = reinterpret_cast<float*>(extra.out[k]) + base + c;
+          *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        } else if (extra.type == DT_F16) {
+          union { uint4 u; __half h[8]; } pk;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pk.h[e] = __float2half_rn(y[e]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(extra.out[k]) + base + c) = pk.u;
+        } else {
+          union { uint4 u; __nv_bfloat16 h[8]; } pk;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pk.h[e] = __float2bfloat16_rn(y[e]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(extra.out[k]) + base + c) = pk.u;
+        }
+      }
+    }
   }
 }
 
 int launch_patch_embed(const float* x, long long x_bs, int in_ch, const float* fuse_w, const float* fuse_b,
                        const float* pe_w, const float* pe_b, const float* ln_w, const float* ln_b, float* tokens,
-                       int B, int img_h, int img_w, int patch, int C, cudaStream_t st) {
+                       int B, int img_h, int img_w, int patch, int C, cudaStream_t st, const PatchEmbedLn* extra_in) {
   if (C % 32 != 0 || C > 256 || 3 * patch * patch > 32) return -2;
+  PatchEmbedLn extra;
+  if (extra_in) extra = *extra_in;
+  if (C == 96 && patch == 2 && img_w % 2 == 0 && (x_bs % 2) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
+      (in_ch == 3 || (in_ch == 2 && fuse_w != nullptr))) {
+    const int total_tok = B * (img_h / 2) * (img_w / 2);
+    patch_embed_tok_kernel<96><<<(total_tok + 127) / 128, 128, 0, st>>>(x, x_bs, in_ch, fuse_w, fuse_b, pe_w, pe_b, ln_w,
+                                                                      ln_b, tokens, B, img_h, img_w, total_tok, extra);
+    DPMN_LAUNCH_CHECK();
+    return 0;
+  }
   const int L = (img_h / patch) * (img_w / patch);
   const int total = B * L;
   const int threads = 256;
@@ -112,7 +284,7 @@ int launch_patch_embed(const float* x, long long x_bs, int in_ch, const float* f
   const size_t smem = (size_t)(3 * patch * patch * C + 64) * sizeof(float);
 #define DPMN_PE(CPL_)                                                                                         \
   patch_embed_kernel<CPL_><<<blocks, threads, smem, st>>>(x, x_bs, in_ch, fuse_w, fuse_b, pe_w, pe_b, ln_w,  \
-                                                          ln_b, tokens, B, img_h, img_w, patch, total)
+                                                          ln_b, tokens, B, img_h, img_w, patch, total, extra)
   switch (C / 32) {
     case 1: DPMN_PE(1); break;
     case 2: DPMN_PE(2); break;
@@ -629,17 +801,23 @@ __global__ void __launch_bounds__(256) dwconv16_kernel(const T* __restrict__ h, 
       const T* r0 = s_in + c * cstride + row * side;   // input rows row, row+1, row+2 (halo offset -1 applied)
       const T* r1 = r0 + side;
       const T* r2 = r1 + side;
+      // sliding 3x3 window, two output columns per step (one 32-bit smem load per row per step)
       float a0 = 0.f, a1 = 0.f, a2 = 0.f;              // column x-1
-      float b0 = to_f32<T>(r0[0]), b1 = to_f32<T>(r1[0]), b2 = to_f32<T>(r2[0]);   // column x
-      for (int x = 0; x < side; ++x) {
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f;            // column x+1
-        if (x + 1 < side) { d0 = to_f32<T>(r0[x + 1]); d1 = to_f32<T>(r1[x + 1]); d2 = to_f32<T>(r2[x + 1]); }
-        float acc = bb;
-        acc = fmaf(a0, wk[0], acc); acc = fmaf(b0, wk[1], acc); acc = fmaf(d0, wk[2], acc);
-        acc = fmaf(a1, wk[3], acc); acc = fmaf(b1, wk[4], acc); acc = fmaf(d1, wk[5], acc);
-        acc = fmaf(a2, wk[6], acc); acc = fmaf(b2, wk[7], acc); acc = fmaf(d2, wk[8], acc);
-        s_out[(row * side + x) * 64 + c] = from_f32<T>(gelu_erf(acc));
-        a0 = b0; a1 = b1; a2 = b2; b0 = d0; b1 = d1; b2 = d2;
+      float2 c0 = to_f32x2<T>(r0), c1 = to_f32x2<T>(r1), c2 = to_f32x2<T>(r2);   // columns x, x+1
+      for (int x = 0; x < side; x += 2) {
+        float2 n0 = make_float2(0.f, 0.f), n1 = n0, n2 = n0;                    // columns x+2, x+3
+        if (x + 2 < side) { n0 = to_f32x2<T>(r0 + x + 2); n1 = to_f32x2<T>(r1 + x + 2); n2 = to_f32x2<T>(r2 + x + 2); }
+        float acc0 = bb, acc1 = bb;
+        acc0 = fmaf(a0, wk[0], acc0); acc0 = fmaf(c0.x, wk[1], acc0); acc0 = fmaf(c0.y, wk[2], acc0);
+        acc0 = fmaf(a1, wk[3], acc0); acc0 = fmaf(c1.x, wk[4], acc0); acc0 = fmaf(c1.y, wk[5], acc0);
+        acc0 = fmaf(a2, wk[6], acc0); acc0 = fmaf(c2.x, wk[7], acc0); acc0 = fmaf(c2.y, wk[8], acc0);
+        acc1 = fmaf(c0.x, wk[0], acc1); acc1 = fmaf(c0.y, wk[1], acc1); acc1 = fmaf(n0.x, wk[2], acc1);
+        acc1 = fmaf(c1.x, wk[3], acc1); acc1 = fmaf(c1.y, wk[4], acc1); acc1 = fmaf(n1.x, wk[5], acc1);
+        acc1 = fmaf(c2.x, wk[6], acc1); acc1 = fmaf(c2.y, wk[7], acc1); acc1 = fmaf(n2.x, wk[8], acc1);
+        s_out[(row * side + x) * 64 + c] = from_f32<T>(gelu_fast(acc0));
+        s_out[(row * side + x + 1) * 64 + c] = from_f32<T>(gelu_fast(acc1));
+        a0 = c0.y; a1 = c1.y; a2 = c2.y;
+        c0 = n0; c1 = n1; c2 = n2;
       }
     }
   }

@@ -438,6 +438,7 @@ bool gemm_tc_can_fuse_row_output(int N) { return N == 32 || N == 64 || N == 96 |
 
 int launch_gemm_tc(const GemmTcArgs& a, cudaStream_t st) {
   if (a.op_type != DT_F16 && a.op_type != DT_BF16) return -1;
+  if (a.ln_mode != 0 && gemm_res_ln_supported(a)) return launch_gemm_res_ln(a, st);   // all-TMA residual-stream kernel
   if (a.K % 16 || a.lda % 8 || a.ldb % 8) return -2;                 // 16-byte TMA strides, whole UMMA k-steps
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.Bm)) & 15) return -2;
   if (a.batch > 1 && ((a.a_bs % 8) || (a.b_bs % 8))) return -2;

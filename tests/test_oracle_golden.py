@@ -92,3 +92,48 @@ def test_torch_port_cmm_matches_reference(name):
     with torch.no_grad():
         y = torch_ref.cmm_forward(_torch_params(P), torch.from_numpy(x1), torch.from_numpy(x2), training=meta["train"])
     assert rel_err(y.numpy(), z["out"]) < TOL
+
+
+# ---- backward: autograd through the torch oracle vs the reference's own gradients ------------------------
+import pytest  # noqa: E402
+
+from tests.util import (CMM_GRAD_GOLDEN, PGRM_GRAD_GOLDEN, golden_grad_view, load_golden, rel_err,  # noqa: E402
+                        torch_ref_cmm_grads, torch_ref_pgrm_grads)
+
+
+def _check_grads(z, meta, grads, tol):
+    n = 0
+    for key in z.files:
+        if not key.startswith("g:"):
+            continue
+        name = key[2:]
+        want = z[key]
+        got = grads.get(name)
+        if got is None:   # parameter without gradient in the reference too (unused weight_list_i)
+            assert want.size == 1 and float(np.abs(want).max()) == 0.0, name
+            continue
+        full = meta["full"] or name in ("x_kv", "x1", "x2") or name.startswith("res")
+        got = golden_grad_view(got, full)
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        if float(np.abs(want).max()) == 0.0:
+            assert float(np.abs(got).max()) < 1e-6, name
+        else:
+            assert rel_err(got, want) < tol, (name, rel_err(got, want))
+        n += 1
+    assert n > 10
+
+
+@pytest.mark.parametrize("name", PGRM_GRAD_GOLDEN)
+def test_torch_oracle_pgrm_grads_match_reference(name):
+    z, meta = load_golden(name)
+    y, grads = torch_ref_pgrm_grads(meta)
+    assert rel_err(y, z["out"]) < 2e-5
+    _check_grads(z, meta, grads, 2e-4)
+
+
+@pytest.mark.parametrize("name", CMM_GRAD_GOLDEN)
+def test_torch_oracle_cmm_grads_match_reference(name):
+    z, meta = load_golden(name)
+    y, grads = torch_ref_cmm_grads(meta)
+    assert rel_err(y, z["out"]) < 2e-5
+    _check_grads(z, meta, grads, 2e-4)

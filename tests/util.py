@@ -77,3 +77,56 @@ def build_cmm(meta, device="cuda", precision="fp32"):
     m = m.to(device)
     m.train(bool(meta.get("train", False)))
     return m, P
+
+
+# ---- gradient fixtures (oracle/make_golden_grads.py) -------------------------------------------------------
+PGRM_GRAD_GOLDEN = ["pgrm_i2_m0_grad", "pgrm_i3_m1_grad", "pgrm_i5_m1_grad"]
+CMM_GRAD_GOLDEN = ["cmm_c8_train_grad", "cmm_c8_eval_grad", "cmm_c16_train_grad"]
+GRAD_SAMPLE = 512
+
+
+def grad_seed_out(seed, B):
+    """d loss / d out of the gradient fixtures: loss = sum(out * G), G ~ N(0,1) seeded."""
+    return np.random.default_rng([seed, 77]).standard_normal((B, 3, 32, 128)).astype(np.float32)
+
+
+def golden_grad_view(g, full):
+    """The part of a gradient tensor a fixture stores (everything, or a strided sample of <= 512 entries)."""
+    g = np.asarray(g, dtype=np.float32)
+    if full:
+        return g
+    step = max(1, g.size // GRAD_SAMPLE)
+    return g.reshape(-1)[np.arange(0, g.size, step)[:GRAD_SAMPLE]]
+
+
+def torch_ref_pgrm_grads(meta):
+    """Gradients of the torch-CPU oracle (autograd through oracle/torch_ref.py) for a gradient fixture."""
+    import torch
+    from oracle import torch_ref
+    cfg, P, x_q, x_kv, res = pgrm_case(meta)
+    Pt = {k: torch.from_numpy(v).requires_grad_(True) for k, v in P.items()}
+    xkv = torch.from_numpy(x_kv).requires_grad_(True)
+    rs = [torch.from_numpy(r).requires_grad_(True) for r in res]
+    y = torch_ref.pgrm_forward(Pt, torch.from_numpy(x_q), xkv, rs, windows=cfg.window_size, num_heads=cfg.num_heads)
+    (y * torch.from_numpy(grad_seed_out(meta["seed"], meta["B"]))).sum().backward()
+    out = {k: (v.grad.numpy() if v.grad is not None else None) for k, v in Pt.items()}
+    out["x_kv"] = xkv.grad.numpy()
+    for i, r in enumerate(rs):
+        out[f"res{i}"] = r.grad.numpy() if r.grad is not None else None
+    return y.detach().numpy(), out
+
+
+def torch_ref_cmm_grads(meta):
+    import torch
+    from oracle import torch_ref
+    P, x1, x2 = cmm_case(meta)
+    Pt = {k: torch.from_numpy(np.asarray(v)) for k, v in P.items()}
+    for k, v in Pt.items():
+        if v.dtype == torch.float32 and "running" not in k:
+            v.requires_grad_(True)
+    a, b = torch.from_numpy(x1).requires_grad_(True), torch.from_numpy(x2).requires_grad_(True)
+    y = torch_ref.cmm_forward(Pt, a, b, training=bool(meta["train"]))
+    (y * torch.from_numpy(grad_seed_out(meta["seed"], meta["B"]))).sum().backward()
+    out = {k: v.grad.numpy() for k, v in Pt.items() if v.requires_grad and v.grad is not None}
+    out["x1"], out["x2"] = a.grad.numpy(), b.grad.numpy()
+    return y.detach().numpy(), out

@@ -45,6 +45,18 @@ class PgrmDesc(C.Structure):
                 ("prepared", fp), ("prepared_valid", C.c_int32), ("reserved_", C.c_int32)]
 
 
+class BlockGrads(C.Structure):       # dpmn_block_grads: same fields as dpmn_block_weights
+    _fields_ = list(BlockWeights._fields_)
+
+
+class PgrmGrads(C.Structure):
+    _fields_ = [("prior_fusion_w", fp), ("prior_fusion_b", fp), ("pe_w", fp), ("pe_b", fp),
+                ("pe_norm_w", fp), ("pe_norm_b", fp),
+                ("blocks", BlockGrads * MAX_BLOCKS),
+                ("head0_w", fp), ("head0_b", fp), ("head1_w", fp), ("head1_b", fp),
+                ("mix_weight", fp * MAX_MIX), ("x_kv", fp), ("mix_input", fp * MAX_MIX)]
+
+
 class Bn(C.Structure):
     _fields_ = [("w", fp), ("b", fp), ("running_mean", fp), ("running_var", fp)]
 
@@ -94,6 +106,8 @@ SYMBOLS = {
     "dpmn_cmm_debug_copy": (C.c_int, [C.POINTER(CmmDesc), _vp, _i32, _vp, _sz, _vp]),
     "dpmn_gemm_nt": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
     "dpmn_gemm_nt_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "dpmn_pgrm_backward_workspace_bytes": (_sz, [C.POINTER(PgrmDesc)]),
+    "dpmn_pgrm_backward": (C.c_int, [C.POINTER(PgrmDesc), _vp, _vp, _vp, C.POINTER(PgrmGrads), _vp, _sz, _vp]),
 }
 
 _lib = None
@@ -113,7 +127,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    for which, st in enumerate((BlockWeights, PgrmDesc, Bn, CmmStage, CmmDesc)):
+    for which, st in enumerate((BlockWeights, PgrmDesc, Bn, CmmStage, CmmDesc, BlockGrads, PgrmGrads)):
         got = lib.dpmn_abi_sizeof(which)
         if got != C.sizeof(st):
             raise RuntimeError(f"dpmn_b200: ABI mismatch for {st.__name__}: library {got} B, binding {C.sizeof(st)} B")

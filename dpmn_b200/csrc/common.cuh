@@ -36,6 +36,13 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return __fdividef(x, 1.0f + e);
 }
 
+__device__ __forceinline__ float gelu_grad(float x) {
+  // d/dx [ x * Phi(x) ] = Phi(x) + x * phi(x)
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return fmaf(x, pdf, cdf);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

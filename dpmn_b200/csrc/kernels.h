@@ -131,6 +131,87 @@ int launch_convert_batch(const ConvertBatch& cb, DType dst_type, cudaStream_t st
 // 16-bit -> fp32 (probe outputs).
 int launch_widen(const void* src, DType src_type, float* dst, long long n, cudaStream_t st);
 
+// ---- backward building blocks (bwd_common.cu) -----------------------------------------------------------
+
+// C[z][m*ldc + n] (op)= alpha * sum_k A[z][m*sam + k*sak] * B[z][k*sbk + n*sbn], fp32, any strides.
+// mode 0: store, 1: += (non-atomic), 2: atomicAdd (allows ksplit > 1 and c_bs == 0, i.e. a sum over the batch).
+struct GemmGenArgs {
+  const float* A = nullptr; long long sam = 0, sak = 0, a_bs = 0;
+  const float* B = nullptr; long long sbk = 0, sbn = 0, b_bs = 0;
+  float* C = nullptr; long long ldc = 0, c_bs = 0;
+  int M = 0, N = 0, K = 0, batch = 1, ksplit = 1, mode = 0;
+  float alpha = 1.0f;
+};
+int launch_gemm_gen(const GemmGenArgs& a, cudaStream_t st);
+int launch_colsum(const float* x, long long ld, int rows, int N, float* out, cudaStream_t st);   // out[n] += sum_rows
+int launch_rowsum(const float* x, int rows, int len, int mod, float* out, cudaStream_t st);      // out[row % mod] += sum_j
+int launch_gelu_bwd(float* g, const float* x, long long n, cudaStream_t st);                      // g *= gelu'(x)
+int launch_add(const float* a, const float* b, float* y, long long n, cudaStream_t st);
+int launch_layernorm_bwd(const float* dy, const float* x, const float* w, float* dx, int accumulate, float* dw,
+                         float* db, int rows, int C, cudaStream_t st);
+
+// ---- PGRM backward kernels (pgrm_bwd.cu) ------------------------------------------------------------------
+struct AttnBwdArgs {
+  const float* q = nullptr; const float* kv = nullptr;     // (B, L, C), (B, L, 2C) token order
+  const float* d_attn = nullptr;                           // (B, L, C) window-major rows
+  float* dq = nullptr; float* dkv = nullptr;               // token order, written
+  const float* table[4] = {}; float* d_table[4] = {};      // accumulated
+  int B = 0, H = 0, W = 0, C = 0, n_groups = 0, heads_per_group = 0;
+  int window[4] = {}, shift[4] = {};
+};
+int launch_window_attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
+
+// S = mean_L GELU(F); zpre = fc1 S + b1; a = softmax_G(fc2 GELU(zpre) + b2); Xs = sum_m a_m * A_m
+int launch_sk_train_fwd(const float* F, const float* A, const float* w1, const float* b1, const float* w2,
+                        const float* b2, float* S, float* zpre, float* a, float* Xs, int B, int L, int C, int G,
+                        cudaStream_t st);
+struct SkBwdArgs {
+  float* F = nullptr;                 // in: proj output; out: dF (in place)
+  const float* d_out = nullptr;       // (rows, C)
+  const float* dXs = nullptr;         // (rows, cg)
+  const float* A = nullptr;           // attention output (rows, C)
+  const float* a = nullptr; const float* zpre = nullptr; const float* S = nullptr;
+  const float* w1 = nullptr; const float* w2 = nullptr;
+  float *dw1 = nullptr, *db1 = nullptr, *dw2 = nullptr, *db2 = nullptr;   // accumulated
+  float *da = nullptr, *dS = nullptr;                                     // scratch (B, C)
+  float* dA = nullptr;                // (rows, C) written: dXs * a
+  int B = 0, L = 0, C = 0, G = 0;
+};
+int launch_sk_bwd(const SkBwdArgs& s, cudaStream_t st);
+
+int launch_dwconv_train_fwd(const float* h1pre, float* dtpre, float* dt, const float* w, const float* b, int B, int L,
+                            int hid, cudaStream_t st);
+int launch_dwconv_bwd(const float* d_dt, const float* dtpre, const float* h1pre, const float* w, float* d_h1pre,
+                      float* dw, float* db, int B, int L, int hid, cudaStream_t st);
+
+int launch_patch_embed_bwd(const float* x, long long x_bs, int in_ch, const float* fuse_w, const float* fuse_b,
+                           const float* pe_w, const float* pe_b, const float* ln_w, const float* d_tok, float* d_pe_w,
+                           float* d_pe_b, float* d_ln_w, float* d_ln_b, float* dx3, int B, int img_h, int img_w,
+                           int patch, int C, cudaStream_t st);
+int launch_prior_fusion_wgrad(const float* dx3, const float* xq, long long xq_bs, float* dw, float* db, int B,
+                              int img_h, int img_w, cudaStream_t st);
+
+struct MixBwdArgs {
+  int n_mix = 1;
+  const float* w[8] = {};       // weight_list_i
+  const float* in[8] = {};      // residual_list[i]
+  long long in_bs[8] = {};
+  float* d_w[8] = {};           // accumulated (may be nullptr for i >= 1)
+  float* d_in[8] = {};          // written, dense (B, hs, H, W) (may be nullptr)
+};
+struct HeadBwdArgs {
+  const float* tokens = nullptr;      // final kv stream (B, L, C)
+  const float* t1 = nullptr;          // conv1 output (B, gh, gw, 16)
+  const float *w1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+  const float* d_out = nullptr;       // (B, hs, img_h, img_w)
+  float *dt2 = nullptr, *dt1 = nullptr;    // scratch (B, gh, gw, 16); dt1 zero-filled by the caller
+  float* d_tokens = nullptr;          // (B, L, C) written
+  float *d_w1 = nullptr, *d_b1 = nullptr, *d_w2 = nullptr, *d_b2 = nullptr;   // accumulated
+  MixBwdArgs mix;
+  int B = 0, gh = 0, gw = 0, C = 0, hs = 0, patch = 0;
+};
+int launch_head_bwd(const HeadBwdArgs& h, cudaStream_t st);
+
 // ---- CMM SIMT kernels (cmm_simt.cu) ------------------------------------------------------------------
 
 // Implicit-GEMM convolution / transposed convolution on NCHW fp32.  The input is the channel-wise

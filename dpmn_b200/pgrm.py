@@ -118,6 +118,36 @@ class PreparedWeights:
         return key
 
 
+_BLOCK_FIELDS = (("norm1_q", "norm1_q"), ("norm1_kv", "norm1_kv"), ("norm2", "norm2"), ("q", "attn.q"), ("kv", "attn.kv"),
+                 ("sk_proj", "attn.sknet.proj"), ("sk_fc1", "attn.sknet.fc1"), ("sk_fc2", "attn.sknet.fc2"),
+                 ("sk_head", "attn.sknet.proj_head"), ("fc1", "mlp.fc1"), ("fc2", "mlp.fc2"),
+                 ("dw", "mlp.depthwise_conv"), ("pw", "mlp.pointwise_conv"))
+
+
+class _PGRMFunction(torch.autograd.Function):
+    """Autograd node of PGRM.forward: forward = dpmn_pgrm_forward, backward = dpmn_pgrm_backward (which recomputes
+    the fp32 forward internally, so only the INPUTS are saved).  Differentiable inputs: x_kv, residual_list[1:],
+    every parameter -- the leaves the reference's loss.backward() reaches (super_resolution.py:245-275)."""
+
+    @staticmethod
+    def forward(ctx, module, x_q, x_kv, n_res, *rest):
+        residuals = list(rest[:n_res])
+        with torch.no_grad():
+            out = module._run(x_q, x_kv, residuals, probe=False)
+        ctx.module, ctx.n_res = module, n_res
+        ctx.save_for_backward(x_q, x_kv, *residuals)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x_q, x_kv, *residuals = ctx.saved_tensors
+        m = ctx.module
+        need_xkv = ctx.needs_input_grad[2]
+        need_res = [ctx.needs_input_grad[4 + i] for i in range(ctx.n_res)]
+        d_xkv, d_res, d_params = m._backward(x_q, x_kv, residuals, d_out, need_xkv, need_res)
+        return (None, None, d_xkv, None, *d_res, *d_params)
+
+
 class PGRM(ParamTree):
     """Prior-Guided Refinement Module, signature-compatible with the reference (pgrm.py:462-467).
 
@@ -188,11 +218,7 @@ class PGRM(ParamTree):
         for b in range(cfg.depth):
             pre = f"layers.0.blocks.{b}."
             bw = d.blocks[b]
-            for field, key in (("norm1_q", "norm1_q"), ("norm1_kv", "norm1_kv"), ("norm2", "norm2"),
-                               ("q", "attn.q"), ("kv", "attn.kv"), ("sk_proj", "attn.sknet.proj"),
-                               ("sk_fc1", "attn.sknet.fc1"), ("sk_fc2", "attn.sknet.fc2"),
-                               ("sk_head", "attn.sknet.proj_head"), ("fc1", "mlp.fc1"), ("fc2", "mlp.fc2"),
-                               ("dw", "mlp.depthwise_conv"), ("pw", "mlp.pointwise_conv")):
+            for field, key in _BLOCK_FIELDS:
                 setattr(bw, field + "_w", self._ptr(pre + key + ".weight"))
                 setattr(bw, field + "_b", self._ptr(pre + key + ".bias"))
             for g in range(cfg.groups):
@@ -219,11 +245,88 @@ class PGRM(ParamTree):
     def _check_mode(self):
         if self.training and (self.drop_rate > 0 or self.attn_drop_rate > 0 or max(self.drop_path) > 0):
             raise NotImplementedError(
-                "dpmn_b200.PGRM: train-mode Dropout/DropPath (pgrm.py:248,310) and the backward kernels are not "
-                "part of this build; call .eval() (inference / parity) or construct with all drop rates 0")
+                "dpmn_b200.PGRM: train-mode Dropout/DropPath (pgrm.py:248,310) are not part of this build; "
+                "call .eval() or construct with all drop rates 0 (forward and backward are then exact)")
 
     def forward(self, x_q: torch.Tensor, x_kv: torch.Tensor, residual_list: Sequence[torch.Tensor]):
+        residual_list = list(residual_list)
+        params = [p for _, p in self.named_parameters()]
+        if torch.is_grad_enabled() and (x_kv.requires_grad or any(r.requires_grad for r in residual_list)
+                                        or any(p.requires_grad for p in params)):
+            return _PGRMFunction.apply(self, x_q, x_kv, len(residual_list), *residual_list, *params)
         return self._run(x_q, x_kv, residual_list, probe=False)
+
+    def _backward(self, x_q, x_kv, residuals, d_out, need_xkv=True, need_res=None):
+        """d_out (B, hs, H, W) -> (d x_kv | None, [d residual_i | None], [d param | None in named_parameters order])."""
+        self._check_mode()
+        lib = _lib.load()
+        cfg = self.cfg
+        B = x_q.shape[0]
+        n_mix = max(1, len(residuals))
+        need_res = list(need_res) if need_res is not None else [True] * len(residuals)
+        x_q, q_bs = self._image_arg(x_q, "x_q")
+        x_kv, kv_bs = self._image_arg(x_kv, "x_kv")
+        d = self._descriptor(B, x_q.shape[1], n_mix)
+        d.x_q_batch_stride, d.x_kv_batch_stride = q_bs, kv_bs
+        keep = []
+        for i in range(1, n_mix):
+            r, bs = self._image_arg(residuals[i], f"residual_list[{i}]")
+            keep.append(r)
+            d.mix_input[i] = r.data_ptr()
+            d.mix_input_batch_stride[i] = bs
+        dev = x_kv.device
+        d_out = d_out.contiguous().float()
+        names = [n for n, _ in self.named_parameters()]
+        params = [p for _, p in self.named_parameters()]
+        sizes = [p.numel() for p in params]
+        with torch.cuda.device(dev):
+            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)   # one flat bucket, views per parameter
+            views, off = {}, 0
+            for n, p, sz in zip(names, params, sizes):
+                views[n] = flat[off: off + sz].view_as(p)
+                off += sz
+            g = _lib.PgrmGrads()
+            used = set()
+
+            def gp(name):
+                used.add(name)
+                return views[name].data_ptr()
+            if x_q.shape[1] == 2:
+                g.prior_fusion_w, g.prior_fusion_b = gp("prior_fusion.weight"), gp("prior_fusion.bias")
+            g.pe_w, g.pe_b = gp("patch_embed.proj.weight"), gp("patch_embed.proj.bias")
+            g.pe_norm_w, g.pe_norm_b = gp("patch_embed.norm.weight"), gp("patch_embed.norm.bias")
+            for b in range(cfg.depth):
+                pre = f"layers.0.blocks.{b}."
+                bg = g.blocks[b]
+                for field, key in _BLOCK_FIELDS:
+                    setattr(bg, field + "_w", gp(pre + key + ".weight"))
+                    setattr(bg, field + "_b", gp(pre + key + ".bias"))
+                for gi in range(cfg.groups):
+                    bg.rpb_table[gi] = gp(pre + f"attn.relative_position_bias_table_{gi}")
+            g.head0_w, g.head0_b = gp("conv_before_upsample.0.weight"), gp("conv_before_upsample.0.bias")
+            g.head1_w, g.head1_b = gp("conv_before_upsample.1.weight"), gp("conv_before_upsample.1.bias")
+            for i in range(n_mix):
+                g.mix_weight[i] = gp(f"weight_list_{i}")
+            img = (B, cfg.hidden_size, cfg.img_size[0], cfg.img_size[1])
+            d_xkv = torch.empty((B, 3, cfg.img_size[0], cfg.img_size[1]), dtype=torch.float32, device=dev) if need_xkv else None
+            if d_xkv is not None:
+                g.x_kv = d_xkv.data_ptr()
+            d_res = [None] * len(residuals)
+            for i in range(1, n_mix):    # residual_list[0] never enters the output (pgrm.py:563)
+                if need_res[i]:
+                    d_res[i] = torch.empty(img, dtype=torch.float32, device=dev)
+                    g.mix_input[i] = d_res[i].data_ptr()
+            nbytes = lib.dpmn_pgrm_backward_workspace_bytes(C.byref(d))
+            if nbytes == 0:
+                raise RuntimeError("dpmn_pgrm_backward_workspace_bytes: configuration rejected")
+            ws = workspace(dev, nbytes)
+            rc = lib.dpmn_pgrm_backward(C.byref(d), x_q.data_ptr(), x_kv.data_ptr(), d_out.data_ptr(), C.byref(g),
+                                        ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(rc, "dpmn_pgrm_backward")
+        # parameters the output does not depend on get no gradient, as in the reference (unused weight_list_i,
+        # prior_fusion when x_q already has 3 channels)
+        d_params = [views[n] if (n in used and p.requires_grad) else None for n, p in zip(names, params)]
+        return d_xkv, d_res, d_params
 
     def forward_probe(self, x_q, x_kv, residual_list):
         """forward + the per-block tensors the parity tests compare: (out, attn_core[2], block_out[2])."""

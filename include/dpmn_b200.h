@@ -144,7 +144,8 @@ const char *dpmn_version(void);
 int dpmn_check_device(void);
 
 /* sizeof() of the descriptor structs as compiled, so a binding can verify its own struct layout:
- * which = 0 dpmn_block_weights, 1 dpmn_pgrm_desc, 2 dpmn_bn, 3 dpmn_cmm_stage, 4 dpmn_cmm_desc. */
+ * which = 0 dpmn_block_weights, 1 dpmn_pgrm_desc, 2 dpmn_bn, 3 dpmn_cmm_stage, 4 dpmn_cmm_desc,
+ * 5 dpmn_block_grads, 6 dpmn_pgrm_grads, 7 dpmn_cmm_grads. */
 size_t dpmn_abi_sizeof(int32_t which);
 
 /* number of kernels launched by this library in this process so far (bench.py's gpu_launches). */
@@ -202,6 +203,45 @@ int dpmn_cmm_debug_copy(const dpmn_cmm_desc *d, void *workspace, int32_t which, 
 int dpmn_gemm_nt(const float *A, const float *B, const float *bias, float *C, int32_t M, int32_t N, int32_t K,
                  int32_t precision, void *workspace, size_t workspace_bytes, void *stream);
 size_t dpmn_gemm_nt_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t precision);
+
+
+/* ---- backward (training) --------------------------------------------------------------------------
+ * The reference trains through torch autograd (interfaces/super_resolution.py:245-275: loss.backward(),
+ * per-module clip_grad_norm_, Adam).  These entry points replace autograd's backward of PGRM.forward
+ * (model/pgrm.py:546-565) and ComplementationModulationModule.forward (model/cmm.py:120-161):
+ * given d loss / d out they produce d loss / d (every parameter, x_kv, residual_list[i] | x1, x2).
+ *
+ *   - stateless: the call recomputes the forward internally (fp32), so nothing has to be kept alive between
+ *     dpmn_*_forward and dpmn_*_backward; `desc` and the inputs are the ones given to the forward
+ *   - parameter gradients ACCUMULATE (+=, atomics) into the caller's buffers -- zero them (or the flat gradient
+ *     bucket they live in) once per step; input gradients are WRITTEN, dense (B, ch, img_h, img_w)
+ *   - a NULL gradient pointer for an input skips it; parameter-gradient pointers must all be non-NULL
+ *     (prior_fusion_* only when q_chans == 2, mix_weight[i] for i < n_mix)
+ *   - arithmetic is fp32 in every precision mode of the descriptor (the 16-bit modes only affect forward)
+ *   - eval-mode semantics of Dropout / DropPath (rates 0): the stochastic train-mode paths are not implemented
+ */
+typedef struct dpmn_block_grads {        /* mirrors dpmn_block_weights field by field */
+  float *norm1_q_w, *norm1_q_b, *norm1_kv_w, *norm1_kv_b;
+  float *rpb_table[DPMN_MAX_GROUPS];
+  float *q_w, *q_b, *kv_w, *kv_b;
+  float *sk_proj_w, *sk_proj_b, *sk_fc1_w, *sk_fc1_b, *sk_fc2_w, *sk_fc2_b, *sk_head_w, *sk_head_b;
+  float *norm2_w, *norm2_b;
+  float *fc1_w, *fc1_b, *fc2_w, *fc2_b, *dw_w, *dw_b, *pw_w, *pw_b;
+} dpmn_block_grads;
+
+typedef struct dpmn_pgrm_grads {
+  float *prior_fusion_w, *prior_fusion_b;
+  float *pe_w, *pe_b, *pe_norm_w, *pe_norm_b;
+  dpmn_block_grads blocks[DPMN_MAX_BLOCKS];
+  float *head0_w, *head0_b, *head1_w, *head1_b;
+  float *mix_weight[DPMN_MAX_MIX];       /* d weight_list_i, i < n_mix */
+  float *x_kv;                           /* d x_kv (B, 3, img_h, img_w) or NULL */
+  float *mix_input[DPMN_MAX_MIX];        /* d residual_list[i] (B, hs, img_h, img_w) or NULL; [0] is never touched */
+} dpmn_pgrm_grads;
+
+size_t dpmn_pgrm_backward_workspace_bytes(const dpmn_pgrm_desc *d);
+int dpmn_pgrm_backward(const dpmn_pgrm_desc *d, const float *x_q, const float *x_kv, const float *d_out,
+                       const dpmn_pgrm_grads *grads, void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

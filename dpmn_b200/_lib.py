@@ -80,6 +80,24 @@ class CmmDesc(C.Structure):
                 ("prepared", fp), ("prepared_valid", C.c_int32), ("reserved_", C.c_int32)]
 
 
+class BnGrads(C.Structure):
+    _fields_ = [("w", fp), ("b", fp)]
+
+
+class CmmStageGrads(C.Structure):
+    _fields_ = [("conv_a_w", fp), ("conv_a_b", fp), ("bn_a", BnGrads), ("conv_b_w", fp), ("conv_b_b", fp), ("bn_b", BnGrads)]
+
+
+class CmmGrads(C.Structure):
+    _fields_ = [("en1_w", fp * 2), ("en1_b", fp * 2),
+                ("enc", (CmmStageGrads * 4) * 2),
+                ("en6_w", fp * 2), ("en6_b", fp * 2),
+                ("fc1_w", fp), ("fc1_b", fp), ("fc2_w", fp), ("fc2_b", fp),
+                ("de6_w", fp), ("de6_b", fp), ("de6_bn", BnGrads),
+                ("dec", CmmStageGrads * 4),
+                ("de1_w", fp), ("de1_b", fp), ("x1", fp), ("x2", fp)]
+
+
 # every symbol include/dpmn_b200.h declares: (restype, argtypes)
 _i32, _sz, _vp = C.c_int32, C.c_size_t, C.c_void_p
 SYMBOLS = {
@@ -108,6 +126,8 @@ SYMBOLS = {
     "dpmn_gemm_nt_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "dpmn_pgrm_backward_workspace_bytes": (_sz, [C.POINTER(PgrmDesc)]),
     "dpmn_pgrm_backward": (C.c_int, [C.POINTER(PgrmDesc), _vp, _vp, _vp, C.POINTER(PgrmGrads), _vp, _sz, _vp]),
+    "dpmn_cmm_backward_workspace_bytes": (_sz, [C.POINTER(CmmDesc)]),
+    "dpmn_cmm_backward": (C.c_int, [C.POINTER(CmmDesc), _vp, _vp, _vp, C.POINTER(CmmGrads), _vp, _sz, _vp]),
 }
 
 _lib = None
@@ -127,7 +147,7 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    for which, st in enumerate((BlockWeights, PgrmDesc, Bn, CmmStage, CmmDesc, BlockGrads, PgrmGrads)):
+    for which, st in enumerate((BlockWeights, PgrmDesc, Bn, CmmStage, CmmDesc, BlockGrads, PgrmGrads, CmmGrads)):
         got = lib.dpmn_abi_sizeof(which)
         if got != C.sizeof(st):
             raise RuntimeError(f"dpmn_b200: ABI mismatch for {st.__name__}: library {got} B, binding {C.sizeof(st)} B")

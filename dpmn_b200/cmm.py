@@ -29,6 +29,26 @@ def _initial_value(name: str, shape) -> torch.Tensor:
     return t   # 1-D: resolved by the caller (needs the sibling weight's fan-in)
 
 
+class _CMMFunction(torch.autograd.Function):
+    """Autograd node of CMM.forward: backward = dpmn_cmm_backward (recomputes the fp32 forward internally)."""
+
+    @staticmethod
+    def forward(ctx, module, x1, x2, *params):
+        with torch.no_grad():
+            out = module._forward_impl(x1, x2)
+        ctx.module = module
+        ctx.training = module.training
+        ctx.save_for_backward(x1, x2)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x1, x2 = ctx.saved_tensors
+        d_x1, d_x2, d_params = ctx.module._backward(x1, x2, d_out, ctx.training, ctx.needs_input_grad[1],
+                                                    ctx.needs_input_grad[2])
+        return (None, d_x1, d_x2, *d_params)
+
+
 class ComplementationModulationModule(ParamTree):
     """cmm.py:80-81 signature.  Extra keyword `precision` as in `PGRM`."""
 
@@ -96,6 +116,66 @@ class ComplementationModulationModule(ParamTree):
         return d
 
     def forward(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+        params = [p for _, p in self.named_parameters()]
+        if torch.is_grad_enabled() and (x1.requires_grad or x2.requires_grad or any(p.requires_grad for p in params)):
+            return _CMMFunction.apply(self, x1, x2, *params)
+        return self._forward_impl(x1, x2)
+
+    def _backward(self, x1, x2, d_out, training, need_x1=True, need_x2=True):
+        """d_out (B, c_img, H, W) -> (d x1 | None, d x2 | None, [d param in named_parameters order])."""
+        lib = _lib.load()
+        x1, x2 = x1.contiguous(), x2.contiguous()
+        B, _, H, W = x1.shape
+        d = self._descriptor(B, H, W)
+        d.training = int(training)
+        d.update_running_stats = 0
+        dev = x1.device
+        d_out = d_out.contiguous().float()
+        names = [n for n, _ in self.named_parameters()]
+        params = [p for _, p in self.named_parameters()]
+        with torch.cuda.device(dev):
+            flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+            views, off = {}, 0
+            for n, p in zip(names, params):
+                views[n] = flat[off: off + p.numel()].view_as(p)
+                off += p.numel()
+
+            def gp(name):
+                return views[name].data_ptr()
+
+            def stage(dst, stem):
+                dst.conv_a_w, dst.conv_a_b = gp(stem + "1.weight"), gp(stem + "1.bias")
+                dst.bn_a.w, dst.bn_a.b = gp(stem + "2.weight"), gp(stem + "2.bias")
+                dst.conv_b_w, dst.conv_b_b = gp(stem + "4.weight"), gp(stem + "4.bias")
+                dst.bn_b.w, dst.bn_b.b = gp(stem + "5.weight"), gp(stem + "5.bias")
+            g = _lib.CmmGrads()
+            for br in (0, 1):
+                g.en1_w[br], g.en1_b[br] = gp(f"en_1_{br + 1}.weight"), gp(f"en_1_{br + 1}.bias")
+                for l, lvl in enumerate((2, 3, 4, 5)):
+                    stage(g.enc[br][l], f"en_{lvl}_{br + 1}.encode.")
+                g.en6_w[br], g.en6_b[br] = gp(f"en_6_{br + 1}.1.weight"), gp(f"en_6_{br + 1}.1.bias")
+            g.fc1_w, g.fc1_b, g.fc2_w, g.fc2_b = gp("fc_1.weight"), gp("fc_1.bias"), gp("fc_2.weight"), gp("fc_2.bias")
+            g.de6_w, g.de6_b = gp("de_6.1.weight"), gp("de_6.1.bias")
+            g.de6_bn.w, g.de6_bn.b = gp("de_6.2.weight"), gp("de_6.2.bias")
+            for i, lvl in enumerate((5, 4, 3, 2)):
+                stage(g.dec[i], f"de_{lvl}.decode.")
+            g.de1_w, g.de1_b = gp("de_1.1.weight"), gp("de_1.1.bias")
+            d_x1 = torch.empty_like(x1) if need_x1 else None
+            d_x2 = torch.empty_like(x2) if need_x2 else None
+            if d_x1 is not None:
+                g.x1 = d_x1.data_ptr()
+            if d_x2 is not None:
+                g.x2 = d_x2.data_ptr()
+            nbytes = lib.dpmn_cmm_backward_workspace_bytes(C.byref(d))
+            if nbytes == 0:
+                raise RuntimeError("dpmn_cmm_backward_workspace_bytes: configuration rejected")
+            ws = workspace(dev, nbytes)
+            rc = lib.dpmn_cmm_backward(C.byref(d), x1.data_ptr(), x2.data_ptr(), d_out.data_ptr(), C.byref(g),
+                                       ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "dpmn_cmm_backward")
+        return d_x1, d_x2, [views[n] if p.requires_grad else None for n, p in zip(names, params)]
+
+    def _forward_impl(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
         lib = _lib.load()
         for n, t in (("x1", x1), ("x2", x2)):
             if not t.is_cuda:

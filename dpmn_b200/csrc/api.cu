@@ -754,8 +754,6 @@ int cmm_forward_tc(const dpmn_cmm_desc* d, const float* x1, const float* x2, flo
 
 }  // namespace
 
-#include "api_bwd.inc"
-
 extern "C" {
 
 const char* dpmn_version(void) { return "dpmn_b200 0.1 (sm_100a)"; }
@@ -803,6 +801,7 @@ size_t dpmn_abi_sizeof(int32_t which) {
     case 4: return sizeof(dpmn_cmm_desc);
     case 5: return sizeof(dpmn_block_grads);
     case 6: return sizeof(dpmn_pgrm_grads);
+    case 7: return sizeof(dpmn_cmm_grads);
   }
   return 0;
 }
@@ -1067,3 +1066,5 @@ int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, f
 }
 
 }  // extern "C"
+
+#include "api_bwd.inc"

@@ -1,0 +1,377 @@
+// Backward kernels of the Complementation Modulation Module (fp32 SIMT, sm_100a)       cmm.py:38-161
+//
+// Data gradients of every conv / transposed conv reuse conv_simt_kernel with the roles swapped (the dgrad of a
+// conv is the transposed conv with the same weight tensor and vice versa).  This file adds what is left:
+//   conv_wgrad_simt   dW[co, k] += sum_n dy[co, n] * gather(k, n)   -- the forward's implicit-GEMM operand, so the
+//                     producer's BatchNorm affine, the consumer's activation and the channel concat are applied
+//                     on load exactly as in the forward
+//   bn_act_bwd        sum over consumers of du * act'(bn(y)), BatchNorm backward (batch or running statistics),
+//                     conv-bias gradient; one CTA per channel
+//   se_gate_bwd       the bottleneck gate (cmm.py:135-147)
+// Parity target: the reference's autograd gradients (tests/golden/cmm_*_grad.npz).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dpmn {
+
+constexpr int WM = 64, WN = 64, WK = 16, WPAD = 68;
+
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(ConvArgs p, const float* __restrict__ dy,
+                                                              float* __restrict__ dw, int nsplit) {
+  __shared__ __align__(16) float As[WK][WPAD];   // dy       [pixel][co]
+  __shared__ __align__(16) float Bs[WK][WPAD];   // gathered [pixel][k]
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * WM, k0 = blockIdx.x * WN;
+  const int kk = p.k * p.k;
+  const int K = p.Cin * kk;
+  const int HoWo = p.Ho * p.Wo;
+  const long long Ntot = (long long)p.B * HoWo;
+  const long long HW = (long long)p.H * p.W;
+  const long long chunk = ((Ntot + nsplit - 1) / nsplit + WK - 1) / WK * WK;
+  const long long nbeg = (long long)blockIdx.z * chunk;
+  const long long nend = nbeg + chunk < Ntot ? nbeg + chunk : Ntot;
+
+  // gather loader: fixed k index (tid % 64), pixel rows (tid / 64) + 4 i
+  const int gk = k0 + (tid & 63), gp0 = tid >> 6;
+  const bool k_ok = gk < K;
+  int ci = 0, ky = 0, kx = 0, seg = 0, cl = 0;
+  if (k_ok) {
+    ci = gk / kk;
+    const int tap = gk - ci * kk;
+    ky = tap / p.k; kx = tap - ky * p.k;
+    cl = ci;
+    if (p.n_seg > 1 && cl >= p.seg_ch[0]) {
+      cl -= p.seg_ch[0]; seg = 1;
+      if (p.n_seg > 2 && cl >= p.seg_ch[1]) { cl -= p.seg_ch[1]; seg = 2; }
+    }
+  }
+  const float* src = p.in[seg];
+  const int segC = p.seg_ch[seg];
+  const bool has_aff = p.in_scale[seg] != nullptr;
+  const float sc = (k_ok && has_aff) ? p.in_scale[seg][cl] : 1.f;
+  const float sh = (k_ok && has_aff) ? p.in_shift[seg][cl] : 0.f;
+  // dy loader: pixel (tid % 16), co rows (tid / 16) + 16 i
+  const int ap = tid & 15, am0 = tid >> 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (long long n0 = nbeg; n0 < nend; n0 += WK) {
+    float av[4], bv[4];
+    {
+      const long long n = n0 + ap;
+      int b = 0, r = 0;
+      if (n < nend) { b = (int)(n / HoWo); r = (int)(n - (long long)b * HoWo); }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int co = m0 + am0 + 16 * i;
+        av[i] = (n < nend && co < p.Cout) ? dy[((long long)b * p.Cout + co) * HoWo + r] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long n = n0 + gp0 + 4 * i;
+      float v = 0.f;
+      if (k_ok && n < nend) {
+        const int b = (int)(n / HoWo);
+        const int r = (int)(n - (long long)b * HoWo);
+        const int oy = r / p.Wo, ox = r - oy * p.Wo;
+        int iy, ix;
+        bool ok;
+        if (TRANSPOSED) {
+          const int ty2 = oy + p.pad - ky * p.dil, tx2 = ox + p.pad - kx * p.dil;
+          ok = ty2 >= 0 && tx2 >= 0 && (ty2 % p.stride) == 0 && (tx2 % p.stride) == 0;
+          iy = ty2 / p.stride; ix = tx2 / p.stride;
+          ok = ok && iy < p.H && ix < p.W;
+        } else {
+          iy = oy * p.stride - p.pad + ky * p.dil;
+          ix = ox * p.stride - p.pad + kx * p.dil;
+          ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        }
+        if (ok) {
+          v = src[((long long)b * segC + cl) * HW + (long long)iy * p.W + ix];
+          v = fmaf(v, sc, sh);
+          if (p.in_act == 1) v = v >= 0.f ? v : 0.2f * v;
+          else if (p.in_act == 2) v = fmaxf(v, 0.f);
+        }
+      }
+      bv[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[ap][am0 + 16 * i] = av[i];
+      Bs[gp0 + 4 * i][tid & 63] = bv[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < WK; ++q) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[q][tx * 4]);
+      const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float br[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = m0 + ty * 4 + i;
+    if (co >= p.Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k >= K) continue;
+      long long o;
+      if (TRANSPOSED) { const int c2 = k / kk; o = ((long long)c2 * p.Cout + co) * kk + (k - c2 * kk); }
+      else o = (long long)co * K + k;
+      atomicAdd(dw + o, acc[i][j]);
+    }
+  }
+}
+
+// `a` describes the FORWARD conv (inputs / affines / activation / geometry); dy is d(raw conv output) (B, Cout, Ho, Wo).
+int launch_conv_wgrad_simt(const ConvArgs& a, const float* dy, float* dw, cudaStream_t st) {
+  if (a.n_seg < 1 || a.n_seg > 3) return -1;
+  int cin = 0;
+  for (int i = 0; i < a.n_seg; ++i) cin += a.seg_ch[i];
+  if (cin != a.Cin) return -1;
+  const int K = a.Cin * a.k * a.k;
+  const long long Ntot = (long long)a.B * a.Ho * a.Wo;
+  const int tiles = ((K + WN - 1) / WN) * ((a.Cout + WM - 1) / WM);
+  long long ns = 1184 / tiles;
+  if (ns > Ntot / 64) ns = Ntot / 64;
+  if (ns < 1) ns = 1;
+  if (ns > 512) ns = 512;
+  dim3 grid((K + WN - 1) / WN, (a.Cout + WM - 1) / WM, (unsigned)ns);
+  if (a.transposed) conv_wgrad_simt_kernel<true><<<grid, 256, 0, st>>>(a, dy, dw, (int)ns);
+  else conv_wgrad_simt_kernel<false><<<grid, 256, 0, st>>>(a, dy, dw, (int)ns);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// -----------------------------------------------------------------------------------------------------
+// d(raw conv output y) from the gradients of its consumers' inputs.   bn = sc*y + sh (or y when there is no
+// BatchNorm);  dbn = sum_s du_s * act_s'(bn);  train: dy = sc * (dbn - mean(dbn) - xhat * mean(dbn*xhat));
+// eval: dy = sc * dbn.  d gamma += sum dbn*xhat, d beta += sum dbn, d bias(conv) += sum dy.  One CTA / channel.
+// -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256b(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += red[i];
+  return s;
+}
+
+__device__ __forceinline__ float act_grad(int act, float v) {
+  return act == 1 ? (v >= 0.f ? 1.f : 0.2f) : act == 2 ? (v > 0.f ? 1.f : 0.f) : 1.f;
+}
+
+__global__ void __launch_bounds__(256) bn_act_bwd_kernel(BnBwdArgs p) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  const long long n = (long long)p.B * p.HW;
+  const bool has_bn = p.gamma != nullptr;
+  float mean = 0.f, rstd = 1.f, sc = 1.f, sh = 0.f;
+  if (has_bn) {
+    float var;
+    if (p.training) {
+      float s = 0.f;
+      for (long long i = threadIdx.x; i < n; i += 256) {
+        const int b = (int)(i / p.HW); const int r = (int)(i - (long long)b * p.HW);
+        s += p.y[((long long)b * p.C + c) * p.HW + r];
+      }
+      mean = block_sum_256b(s, red) / (float)n;
+      float q = 0.f;
+      for (long long i = threadIdx.x; i < n; i += 256) {
+        const int b = (int)(i / p.HW); const int r = (int)(i - (long long)b * p.HW);
+        const float d = p.y[((long long)b * p.C + c) * p.HW + r] - mean;
+        q = fmaf(d, d, q);
+      }
+      var = block_sum_256b(q, red) / (float)n;
+    } else {
+      mean = p.run_mean[c]; var = p.run_var[c];
+    }
+    rstd = 1.0f / sqrtf(var + p.eps);
+    sc = p.gamma[c] * rstd;
+    sh = p.beta[c] - mean * sc;
+  }
+  auto dbn_at = [&](int b, int r, float yv) -> float {
+    const float bn = fmaf(yv, sc, sh);
+    float g = 0.f;
+    for (int s = 0; s < p.n_src; ++s)
+      g = fmaf(p.du[s][(long long)b * p.du_bs[s] + (long long)c * p.HW + r], act_grad(p.act[s], bn), g);
+    return g;
+  };
+  float m1 = 0.f, m2 = 0.f;
+  if (has_bn) {
+    float s1 = 0.f, s2 = 0.f;
+    for (long long i = threadIdx.x; i < n; i += 256) {
+      const int b = (int)(i / p.HW); const int r = (int)(i - (long long)b * p.HW);
+      const float yv = p.y[((long long)b * p.C + c) * p.HW + r];
+      const float g = dbn_at(b, r, yv);
+      s1 += g;
+      s2 = fmaf(g, (yv - mean) * rstd, s2);
+    }
+    s1 = block_sum_256b(s1, red);
+    s2 = block_sum_256b(s2, red);
+    if (threadIdx.x == 0) { atomicAdd(p.dgamma + c, s2); atomicAdd(p.dbeta + c, s1); }
+    if (p.training) { m1 = s1 / (float)n; m2 = s2 / (float)n; }
+  }
+  float sb = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 256) {
+    const int b = (int)(i / p.HW); const int r = (int)(i - (long long)b * p.HW);
+    const long long o = ((long long)b * p.C + c) * p.HW + r;
+    const float yv = p.y[o];
+    const float g = dbn_at(b, r, yv);
+    const float d = has_bn ? sc * (g - m1 - (yv - mean) * rstd * m2) : g;
+    p.dy[o] = d;
+    sb += d;
+  }
+  if (p.dbias != nullptr) {
+    sb = block_sum_256b(sb, red);
+    if (threadIdx.x == 0) atomicAdd(p.dbias + c, sb);
+  }
+}
+
+int launch_bn_act_bwd(const BnBwdArgs& a, cudaStream_t st) {
+  if (a.n_src < 1 || a.n_src > 2) return -1;
+  bn_act_bwd_kernel<<<a.C, 256, 0, st>>>(a);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[c] += sum_{b, r} x[(b*C + c)*HW + r]          (bias gradient of a conv whose output gradient is given directly)
+__global__ void __launch_bounds__(256) chan_sum_kernel(const float* __restrict__ x, int B, int C, int HW, float* __restrict__ out) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  const long long n = (long long)B * HW;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 256) {
+    const int b = (int)(i / HW); const int r = (int)(i - (long long)b * HW);
+    s += x[((long long)b * C + c) * HW + r];
+  }
+  s = block_sum_256b(s, red);
+  if (threadIdx.x == 0) atomicAdd(out + c, s);
+}
+
+int launch_chan_sum(const float* x, int B, int C, int HW, float* out, cudaStream_t st) {
+  chan_sum_kernel<<<C, 256, 0, st>>>(x, B, C, HW, out);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// -----------------------------------------------------------------------------------------------------
+// SE gate backward (cmm.py:135-147): z = cat(z1, z2); g0 = mean_hw z; h = relu(fc1 g0 + b1); g = sigmoid(fc2 h + b2);
+// out = z*g + z feeds de_6 through ReLU.  du = d relu(out) (B, 2Cb, hw).  One CTA per image.
+// -----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restrict__ z1, const float* __restrict__ z2,
+                                                          const float* __restrict__ du, const float* __restrict__ fc1_w,
+                                                          const float* __restrict__ fc1_b, const float* __restrict__ fc2_w,
+                                                          const float* __restrict__ fc2_b, float* __restrict__ dz1,
+                                                          float* __restrict__ dz2, float* __restrict__ d_fc1_w,
+                                                          float* __restrict__ d_fc1_b, float* __restrict__ d_fc2_w,
+                                                          float* __restrict__ d_fc2_b, int Cb, int hw, int hidden) {
+  extern __shared__ float sm[];
+  const int C2 = 2 * Cb;
+  float* sg0 = sm;             // [C2] pooled
+  float* sgate = sg0 + C2;     // [C2] sigmoid
+  float* sds = sgate + C2;     // [C2] d (pre-sigmoid)
+  float* sh = sds + C2;        // [hidden] relu(fc1)
+  float* sdh = sh + hidden;    // [hidden] d (pre-relu)
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < C2; c += blockDim.x) {
+    const float* src = c < Cb ? z1 + ((long long)b * Cb + c) * hw : z2 + ((long long)b * Cb + (c - Cb)) * hw;
+    float s = 0.f;
+    for (int i = 0; i < hw; ++i) s += src[i];
+    sg0[c] = s / (float)hw;
+  }
+  __syncthreads();
+  for (int j = warp; j < hidden; j += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C2; c += 32) s = fmaf(fc1_w[(long long)j * C2 + c], sg0[c], s);
+    s = warp_sum(s);
+    if (lane == 0) sh[j] = fmaxf(s + fc1_b[j], 0.f);
+  }
+  __syncthreads();
+  for (int c = warp; c < C2; c += nw) {
+    float s = 0.f;
+    for (int j = lane; j < hidden; j += 32) s = fmaf(fc2_w[(long long)c * hidden + j], sh[j], s);
+    s = warp_sum(s);
+    const float g = 1.0f / (1.0f + expf(-(s + fc2_b[c])));
+    // d gate[c] = sum_hw dout * z, dout = du * [z*(1+g) > 0]
+    const float* src = c < Cb ? z1 + ((long long)b * Cb + c) * hw : z2 + ((long long)b * Cb + (c - Cb)) * hw;
+    float dg = 0.f;
+    for (int i = lane; i < hw; i += 32) {
+      const float v = src[i];
+      const float o = fmaf(v, g, v);
+      if (o > 0.f) dg = fmaf(du[((long long)b * C2 + c) * hw + i], v, dg);
+    }
+    dg = warp_sum(dg);
+    if (lane == 0) {
+      sgate[c] = g;
+      const float ds = dg * g * (1.0f - g);
+      sds[c] = ds;
+      atomicAdd(d_fc2_b + c, ds);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C2 * hidden; i += blockDim.x) {
+    const int c = i / hidden, j = i - c * hidden;
+    atomicAdd(d_fc2_w + i, sds[c] * sh[j]);
+  }
+  for (int j = warp; j < hidden; j += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C2; c += 32) s = fmaf(sds[c], fc2_w[(long long)c * hidden + j], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float d = sh[j] > 0.f ? s : 0.f;
+      sdh[j] = d;
+      atomicAdd(d_fc1_b + j, d);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < hidden * C2; i += blockDim.x) {
+    const int j = i / C2, c = i - j * C2;
+    atomicAdd(d_fc1_w + i, sdh[j] * sg0[c]);
+  }
+  for (int c = warp; c < C2; c += nw) {
+    float s = 0.f;
+    for (int j = lane; j < hidden; j += 32) s = fmaf(sdh[j], fc1_w[(long long)j * C2 + c], s);
+    s = warp_sum(s) / (float)hw;                     // d pooled -> every pixel
+    const float g = sgate[c];
+    const float* src = c < Cb ? z1 + ((long long)b * Cb + c) * hw : z2 + ((long long)b * Cb + (c - Cb)) * hw;
+    float* dst = c < Cb ? dz1 + ((long long)b * Cb + c) * hw : dz2 + ((long long)b * Cb + (c - Cb)) * hw;
+    for (int i = lane; i < hw; i += 32) {
+      const float v = src[i];
+      const float o = fmaf(v, g, v);
+      const float dout = o > 0.f ? du[((long long)b * C2 + c) * hw + i] : 0.f;
+      dst[i] = fmaf(dout, 1.0f + g, s);
+    }
+  }
+}
+
+int launch_se_gate_bwd(const float* z1, const float* z2, const float* du, const float* fc1_w, const float* fc1_b,
+                       const float* fc2_w, const float* fc2_b, float* dz1, float* dz2, float* d_fc1_w, float* d_fc1_b,
+                       float* d_fc2_w, float* d_fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st) {
+  const size_t smem = (size_t)(6 * Cb + 2 * hidden) * sizeof(float);
+  if (smem > 48 * 1024) return -2;
+  se_gate_bwd_kernel<<<B, 256, smem, st>>>(z1, z2, du, fc1_w, fc1_b, fc2_w, fc2_b, dz1, dz2, d_fc1_w, d_fc1_b, d_fc2_w,
+                                           d_fc2_b, Cb, hw, hidden);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dpmn

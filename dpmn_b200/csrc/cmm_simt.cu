@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs p) {
         int iy, ix;
         bool ok;
         if (TRANSPOSED) {
-          // out[oy] += in[iy] * w[ky]  with  oy = iy*stride - pad + ky
-          const int ty2 = oy + p.pad - ky, tx2 = ox + p.pad - kx;
+          // out[oy] += in[iy] * w[ky]  with  oy = iy*stride - pad + ky*dil
+          const int ty2 = oy + p.pad - ky * p.dil, tx2 = ox + p.pad - kx * p.dil;   // dil > 1: dgrad of a dilated conv
           ok = ty2 >= 0 && tx2 >= 0 && (ty2 % p.stride) == 0 && (tx2 % p.stride) == 0;
           iy = ty2 / p.stride;
           ix = tx2 / p.stride;

@@ -244,6 +244,27 @@ int launch_bn_affine(const float* x, int B, int C, int HW, const float* w, const
 int launch_se_gate(const float* z1, const float* z2, float* z, const float* fc1_w, const float* fc1_b,
                    const float* fc2_w, const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st);
 
+// ---- CMM backward kernels (cmm_bwd.cu) ------------------------------------------------------------------
+// weight gradient of the conv described by `a` (the FORWARD ConvArgs): dw += dy (x) gather(inputs); dy (B, Cout, Ho, Wo)
+int launch_conv_wgrad_simt(const ConvArgs& a, const float* dy, float* dw, cudaStream_t st);
+struct BnBwdArgs {
+  const float* y = nullptr;            // raw conv output (B, C, HW)
+  int B = 0, C = 0, HW = 0;
+  const float *gamma = nullptr, *beta = nullptr, *run_mean = nullptr, *run_var = nullptr;   // gamma == nullptr: no BatchNorm
+  int training = 0; float eps = 1e-5f;
+  int n_src = 1;
+  const float* du[2] = {};             // gradient w.r.t. each consumer's (activated) input; channel offset folded in
+  long long du_bs[2] = {};             // batch strides (elements)
+  int act[2] = {};                     // the consumer's activation: 0 none, 1 LeakyReLU(0.2), 2 ReLU
+  float* dy = nullptr;                 // (B, C, HW) written
+  float *dgamma = nullptr, *dbeta = nullptr, *dbias = nullptr;   // accumulated
+};
+int launch_bn_act_bwd(const BnBwdArgs& a, cudaStream_t st);
+int launch_chan_sum(const float* x, int B, int C, int HW, float* out, cudaStream_t st);
+int launch_se_gate_bwd(const float* z1, const float* z2, const float* du, const float* fc1_w, const float* fc1_b,
+                       const float* fc2_w, const float* fc2_b, float* dz1, float* dz2, float* d_fc1_w, float* d_fc1_b,
+                       float* d_fc2_w, float* d_fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st);
+
 // ---- CMM tensor-core kernels (conv_tc.cu, cmm_tc.cu) ----------------------------------------------------
 
 struct ConvTap { int8_t map, dy, dx, pad_; int16_t wslice, pad2_; };   // A-map id, pixel shift, weight slice

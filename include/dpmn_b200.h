@@ -11,6 +11,8 @@
  *   dpmn_window_attn_forward   <- WindowAttention.forward, per-group core           model/pgrm.py:197-268
  *   dpmn_cmm_forward           <- ComplementationModulationModule.forward(x1, x2)   model/cmm.py:120-161
  *   dpmn_gemm_nt               <- nn.Linear / 1x1 conv contraction (F.linear)       model/pgrm.py:30,37,39,82,188,194
+ *   dpmn_pgrm_backward         <- autograd backward of PGRM.forward                 interfaces/super_resolution.py:245-275
+ *   dpmn_cmm_backward          <- autograd backward of the CMM forward              interfaces/super_resolution.py:245-275
  *
  * Conventions
  *   - every function returns int: 0 = ok, <0 = argument error (DPMN_E_*), >0 = a cudaError_t value
@@ -242,6 +244,29 @@ typedef struct dpmn_pgrm_grads {
 size_t dpmn_pgrm_backward_workspace_bytes(const dpmn_pgrm_desc *d);
 int dpmn_pgrm_backward(const dpmn_pgrm_desc *d, const float *x_q, const float *x_kv, const float *d_out,
                        const dpmn_pgrm_grads *grads, void *workspace, size_t workspace_bytes, void *stream);
+
+typedef struct dpmn_bn_grads { float *w, *b; } dpmn_bn_grads;
+typedef struct dpmn_cmm_stage_grads {    /* mirrors dpmn_cmm_stage */
+  float *conv_a_w, *conv_a_b; dpmn_bn_grads bn_a;
+  float *conv_b_w, *conv_b_b; dpmn_bn_grads bn_b;
+} dpmn_cmm_stage_grads;
+typedef struct dpmn_cmm_grads {          /* mirrors the parameters of dpmn_cmm_desc; all pointers required */
+  float *en1_w[2], *en1_b[2];
+  dpmn_cmm_stage_grads enc[2][4];
+  float *en6_w[2], *en6_b[2];
+  float *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+  float *de6_w, *de6_b; dpmn_bn_grads de6_bn;
+  dpmn_cmm_stage_grads dec[4];
+  float *de1_w, *de1_b;
+  float *x1, *x2;                        /* d x1, d x2 (B, c_img, img_h, img_w) or NULL */
+} dpmn_cmm_grads;
+
+/* Backward of ComplementationModulationModule.forward (cmm.py:120-161).  d->training selects batch-statistics
+ * BatchNorm backward (module.train()) or the running-statistics affine (eval()); running stats are never
+ * updated by this call.  x1 / x2 must be dense. */
+size_t dpmn_cmm_backward_workspace_bytes(const dpmn_cmm_desc *d);
+int dpmn_cmm_backward(const dpmn_cmm_desc *d, const float *x1, const float *x2, const float *d_out,
+                      const dpmn_cmm_grads *grads, void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

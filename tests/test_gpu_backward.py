@@ -13,7 +13,10 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-4
 
 
-def _compare(z, meta, grads, tol=TOL):
+NOISE_FLOOR = 1e-2   # see test_cmm_backward_matches_reference
+
+
+def _compare(z, meta, grads, tol=TOL, noise_floor=0.0):
     worst, n = [], 0
     for key in z.files:
         if not key.startswith("g:"):
@@ -28,6 +31,9 @@ def _compare(z, meta, grads, tol=TOL):
         got = golden_grad_view(got, full)
         assert got.shape == want.shape, (name, got.shape, want.shape)
         scale = float(np.abs(want).max())
+        if scale < noise_floor:       # a gradient that is exactly 0 in exact arithmetic: both sides are rounding noise
+            assert float(np.abs(got).max()) < noise_floor, (name, float(np.abs(got).max()))
+            continue
         err = float(np.abs(got - want).max()) if scale == 0.0 else rel_err(got, want)
         worst.append((err, name))
         n += 1
@@ -74,3 +80,21 @@ def test_pgrm_backward_sliced_x_kv_and_accumulation():
     assert rel_err(g[:, :3], 2.0 * z["g:x_kv"]) < TOL
     w = m.get_parameter("layers.0.blocks.1.mlp.fc2.weight").grad.cpu().numpy()
     assert rel_err(golden_grad_view(w, False), 2.0 * z["g:layers.0.blocks.1.mlp.fc2.weight"]) < TOL
+
+
+@pytest.mark.parametrize("name", CMM_GRAD_GOLDEN)
+def test_cmm_backward_matches_reference(name):
+    z, meta = load_golden(name)
+    P, x1, x2 = cmm_case(meta)
+    m, _ = build_cmm(meta, "cuda", precision="fp32")
+    dev = torch.device("cuda")
+    a = torch.from_numpy(x1).to(dev).requires_grad_(True)
+    b = torch.from_numpy(x2).to(dev).requires_grad_(True)
+    y = m(a, b)
+    assert rel_err(y.detach().cpu().numpy(), z["out"]) < 2e-5
+    (y * torch.from_numpy(grad_seed_out(meta["seed"], meta["B"])).to(dev)).sum().backward()
+    grads = {k: p.grad.cpu().numpy() for k, p in m.named_parameters() if p.grad is not None}
+    grads["x1"], grads["x2"] = a.grad.cpu().numpy(), b.grad.cpu().numpy()
+    # a conv bias followed by a train-mode BatchNorm has an exactly-zero true gradient; the reference's own value is
+    # fp32 cancellation noise (<= 4e-4 where real gradients are >= 1), so those are only required to be noise too
+    _compare(z, meta, grads, tol=5e-4 if meta["train"] else TOL, noise_floor=NOISE_FLOOR if meta["train"] else 0.0)

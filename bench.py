@@ -156,22 +156,33 @@ def run_ours(args):
     lib = _lib.load()
     assert lib.dpmn_check_device() == 0
 
-    model = DPMNHotPath(precision=args.precision)
+    train = args.mode == "train"
+    if train:
+        # configs[2]: PGRM forward in the chosen precision; CMM forward fp32 (train-mode BatchNorm); backward fp32
+        model = DPMNHotPath(precision=args.precision, drop=0.0, cmm_precision="fp32")
+    else:
+        model = DPMNHotPath(precision=args.precision)
     pg, cm = synth_weights(2)
     load_weights(model, pg, cm)
-    model = model.to(dev).eval()
+    model = model.to(dev)
+    model.train(train)
+    trainer = None
+    if train:
+        from dpmn_b200.train import HotPathTrainer
+        trainer = HotPathTrainer(model)
 
     B = BATCH
     n_sets = 4   # rotate input sets; the per-step working set (workspaces ~0.7 GB) is far larger than the 126 MB L2
     host_sets, dev_sets = [], []
     for s in range(n_sets):
         psn, p1, p2 = synth_inputs(1000 * rank + s, B)
+        hr = torch.from_numpy(np.random.default_rng([1000 * rank + s, 7]).uniform(0, 1, (B, 4, 32, 128)).astype(np.float32))
         hs = (torch.from_numpy(psn).pin_memory(), [torch.from_numpy(a).pin_memory() for a in p1],
-              [torch.from_numpy(a).pin_memory() for a in p2])
+              [torch.from_numpy(a).pin_memory() for a in p2], hr.pin_memory())
         host_sets.append(hs)
-        dev_sets.append((hs[0].to(dev), [a.to(dev) for a in hs[1]], [a.to(dev) for a in hs[2]]))
-    h2d_bytes = sum(t.numel() * 4 for t in [host_sets[0][0]] + host_sets[0][1] + host_sets[0][2])
-    out_host = torch.empty((B, 3, 32, 128), dtype=torch.float32).pin_memory()
+        dev_sets.append((hs[0].to(dev), [a.to(dev) for a in hs[1]], [a.to(dev) for a in hs[2]], hs[3].to(dev)))
+    h2d_bytes = sum(t.numel() * 4 for t in [host_sets[0][0]] + host_sets[0][1] + host_sets[0][2] + ([host_sets[0][3]] if train else []))
+    out_host = (torch.empty((), dtype=torch.float32) if train else torch.empty((B, 3, 32, 128), dtype=torch.float32)).pin_memory()
     d2h_bytes = out_host.numel() * 4
 
     def barrier():
@@ -187,18 +198,21 @@ def run_ours(args):
         return float(t.item())
 
     def step_resident(i):
-        return model(*dev_sets[i % n_sets])
+        ds = dev_sets[i % n_sets]
+        if train:
+            return trainer.step(*ds)
+        return model(*ds[:3])
 
     def step_e2e(i):
         hs = host_sets[i % n_sets]
         psn = hs[0].to(dev, non_blocking=True)
         p1 = [a.to(dev, non_blocking=True) for a in hs[1]]
         p2 = [a.to(dev, non_blocking=True) for a in hs[2]]
-        y = model(psn, p1, p2)
+        y = trainer.step(psn, p1, p2, hs[3].to(dev, non_blocking=True)) if train else model(psn, p1, p2)
         out_host.copy_(y, non_blocking=True)
         return y
 
-    with torch.no_grad():
+    with torch.set_grad_enabled(train):
         # ---------- value: inputs resident in HBM
         for i in range(args.warmup):
             step_resident(i)
@@ -262,28 +276,44 @@ def run_ours(args):
         pass
     tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if peaks else "fallback"
-    dom = max((k for k in prof if k in FLOPS_IMG), key=lambda k: prof[k]["ms_per_step"])
+    flops_img = dict(FLOPS_IMG)
+    if train:
+        # backward classes: data + weight gradient = 2x the forward contraction FLOPs of the same layers
+        flops_img = {"bwd_gemm": 2 * _PGRM_GEMM, "bwd_conv": 2 * FLOPS_IMG["conv"], "gemm": 2 * _PGRM_GEMM + 0,
+                     "conv": 2 * FLOPS_IMG["conv"], "total": 3 * FLOPS_IMG["total"] + FLOPS_IMG["total"]}
+        # ("gemm"/"conv": fp32 forward recompute inside backward (+ the CMM's own fp32 forward); total = fwd + recompute + bwd)
+    dom = max((k for k in prof if k in flops_img and k != "total"), key=lambda k: prof[k]["ms_per_step"])
     dom_ms = prof[dom]["ms_per_step"]
-    achieved = FLOPS_IMG[dom] * B / (dom_ms / 1e3) / 1e12
+    achieved = flops_img[dom] * B / (dom_ms / 1e3) / 1e12
     total_prof_ms = sum(v["ms_per_step"] for v in prof.values())
-    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+    if train:
+        tensor_peak = 75.0   # B200 fp32 FFMA peak (148 SMs x 128 lanes x 2 x 1.965 GHz): the backward is fp32 SIMT this round
+        peak_src = "nominal fp32 FFMA peak (the backward kernels are fp32 SIMT, not tensor-core, this round)"
+    roofline = {"bound": "tensor" if not train else "fp32-simt", "kernel": dom, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak, "traffic": None, "peak_source": peak_src,
                 "share_of_step": dom_ms / total_prof_ms,
                 "launches_per_step": prof[dom]["launches_per_step"],
                 "avg_launch_ms": dom_ms / max(1, prof[dom]["launches_per_step"]),
-                "whole_step_tflops": FLOPS_IMG["total"] * B / (ms_step / 1e3) / 1e12,
+                "whole_step_tflops": flops_img["total"] * B / (ms_step / 1e3) / 1e12,
                 "by_kernel_ms": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not train:
         v, sample, _, _ = cpu_port_throughput(budget_s=15.0)
         cpu = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
 
-    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+    workload = WORKLOAD if not train else (
+        "DPMN hot path TRAINING step: 6xPGRM cascade + CMM forward (PGRM " + args.precision + ", CMM fp32 train-mode BN), 7 image "
+        "losses, backward through dpmn_pgrm_backward / dpmn_cmm_backward (fp32), flat gradient all-reduce, per-module "
+        "clip 0.25, Adam; 16x64 -> 32x128, batch 48/GPU, synthetic PSN output / priors / HR (configs[2] without the "
+        "frozen TATT backbone, recognisers and distill modules)")
+    line = {"metric": METRIC if not train else "SR images/sec (training step)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"replicas x{world} (no collective: inference)",
+            "config": {"workload": workload, "global_batch": B * world,
+                       "parallelism": f"replicas x{world} (no collective: inference)" if not train else
+                       f"dp{world}: one flat NCCL all-reduce over the 57.2M-parameter fp32 gradient bucket per step",
                        "l2": f"inputs rotate over {n_sets} sets; per-step working set (activations/workspace) >> 126 MB L2"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
@@ -299,6 +329,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--precision", default=os.environ.get("DPMN_PRECISION", "fp16"))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer = BASELINE configs[1] (the headline line); train = configs[2] training step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -46,7 +46,7 @@ class FlatGradBucket:
 
     def allreduce_mean(self, group=None, async_op: bool = False):
         """sum over ranks, then scale by 1/world (the reference averages the loss over the global batch)."""
-        world = dist.get_world_size(group)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
         if world == 1:
             return None
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)

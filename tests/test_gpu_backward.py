@@ -98,3 +98,65 @@ def test_cmm_backward_matches_reference(name):
     # a conv bias followed by a train-mode BatchNorm has an exactly-zero true gradient; the reference's own value is
     # fp32 cancellation noise (<= 4e-4 where real gradients are >= 1), so those are only required to be noise too
     _compare(z, meta, grads, tol=5e-4 if meta["train"] else TOL, noise_floor=NOISE_FLOOR if meta["train"] else 0.0)
+
+
+def test_hot_path_training_step_gradients_vs_oracle():
+    """Whole path (6 PGRM cascade with gradients flowing through x_kv and the residual lists, CMM in train mode,
+    the reference's 7-term image loss): gradients vs autograd through the torch oracle on CPU.  At cnum 64 a CMM
+    forward has ~6M ReLU / LeakyReLU inputs, so a few sit within rounding distance of 0 and their masks may differ
+    between two valid fp32 evaluations (see oracle/make_golden_grads.py); the bar here is therefore a relative L2
+    error of 3e-2 and cosine > 0.999 per tensor -- exact parity is covered by the per-module fixtures above."""
+    import bench
+    from dpmn_b200.pipeline import DPMNHotPath
+    from dpmn_b200.train import HotPathTrainer
+    from oracle import torch_ref
+    B = 2
+    dev = torch.device("cuda")
+    model = DPMNHotPath(precision="fp32", drop=0.0)
+    pg, cm = bench.synth_weights(2)
+    bench.load_weights(model, pg, cm)
+    model = model.to(dev).train()
+    tr = HotPathTrainer(model)
+    psn, p1, p2 = bench.synth_inputs(3, B)
+    hr = np.random.default_rng(9).uniform(0, 1, (B, 4, 32, 128)).astype(np.float32)
+    outs = model.forward_all(torch.from_numpy(psn).to(dev), [torch.from_numpy(a).to(dev) for a in p1],
+                             [torch.from_numpy(a).to(dev) for a in p2])
+    loss = tr.loss(outs, torch.from_numpy(hr).to(dev))
+    loss.backward()
+    # oracle
+    pgt = [{k: torch.from_numpy(np.asarray(v)).requires_grad_(True) for k, v in p.items()} for p in pg]
+    cmt = {k: torch.from_numpy(np.asarray(v)) for k, v in cm.items()}
+    for k, v in cmt.items():
+        if v.dtype == torch.float32 and "running" not in k:
+            v.requires_grad_(True)
+    psn_t = torch.from_numpy(psn)
+    o_outs = []
+    for branch, priors in ((0, p1), (1, p2)):
+        cascade, done = psn_t[:, :3], []
+        for k in range(3):
+            y = torch_ref.pgrm_forward(pgt[3 * branch + k], torch.from_numpy(priors[k]), cascade, done[:k])
+            done.append(y)
+            cascade = y
+        o_outs += done
+    o_outs.append(torch_ref.cmm_forward(cmt, o_outs[2], o_outs[5], training=True))
+    o_loss = tr.loss(o_outs, torch.from_numpy(hr))
+    o_loss.backward()
+    assert abs(float(loss) - float(o_loss)) < 1e-4 * abs(float(o_loss))
+    checked = 0
+    for k, m in enumerate(model.pgrm):
+        for n, p in m.named_parameters():
+            ref = pgt[k][n].grad
+            if ref is None:
+                assert float(p.grad.abs().max()) == 0.0, (k, n)
+                continue
+            a, b = p.grad.cpu().double().flatten(), ref.double().flatten()
+            assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < 3e-2, (k, n)
+            assert float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30)) > 0.999, (k, n)
+            checked += 1
+    for n, p in model.cmm.named_parameters():
+        a, b = p.grad.cpu().double().flatten(), cmt[n].grad.double().flatten()
+        if float(b.abs().max()) < 1e-2:
+            continue
+        assert float((a - b).norm() / b.norm()) < 3e-2, n
+        checked += 1
+    assert checked > 300

@@ -1,0 +1,23 @@
+"""Host-side training logic that needs no GPU: the image loss restatement against the reference's definition."""
+import numpy as np
+import torch
+
+
+def test_image_loss_matches_reference_definition():
+    """ImageLoss(gradient=True, loss_weight=[1,1]) = MSE + L1(gradient_map) (loss/image_loss.py:15-43), written out
+    independently here with explicit shifts."""
+    from dpmn_b200.train import gradient_map, image_loss
+    r = np.random.default_rng(0)
+    a = torch.from_numpy(r.uniform(0, 1, (2, 3, 8, 12)).astype(np.float32))
+    b = torch.from_numpy(r.uniform(0, 1, (2, 3, 8, 12)).astype(np.float32))
+
+    def gmap(x):
+        x = x.numpy().astype(np.float64)
+        rr = np.zeros_like(x); rr[..., :-1] = x[..., 1:]
+        ll = np.zeros_like(x); ll[..., 1:] = x[..., :-1]
+        tt = np.zeros_like(x); tt[..., 1:, :] = x[..., :-1, :]
+        bb = np.zeros_like(x); bb[..., :-1, :] = x[..., 1:, :]
+        return np.sqrt(((rr - ll) * 0.5) ** 2 + ((tt - bb) * 0.5) ** 2 + 1e-6)
+    assert np.allclose(gradient_map(a).numpy(), gmap(a), atol=1e-6)
+    want = ((a.numpy().astype(np.float64) - b.numpy()) ** 2).mean() + np.abs(gmap(a) - gmap(b)).mean()
+    assert abs(float(image_loss(a, b)) - want) < 1e-6

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdpmn_b200.so")
 
 MAX_GROUPS, MAX_MIX, MAX_BLOCKS = 4, 8, 2
+CMM_WORKSPACE_HOLDS_FORWARD = 1
 PREC = {"fp32": 0, "f32": 0, "fp16": 1, "f16": 1, "bf16": 2}
 ERRORS = {-1: "DPMN_E_ARG (null pointer / inconsistent sizes)",
           -2: "DPMN_E_UNSUPPORTED (configuration outside this build or that the reference cannot run)",
@@ -77,7 +78,7 @@ class CmmDesc(C.Structure):
                 ("de6_w", fp), ("de6_b", fp), ("de6_bn", Bn),
                 ("dec", CmmStage * 4),
                 ("de1_w", fp), ("de1_b", fp),
-                ("prepared", fp), ("prepared_valid", C.c_int32), ("reserved_", C.c_int32)]
+                ("prepared", fp), ("prepared_valid", C.c_int32), ("flags", C.c_int32)]
 
 
 class BnGrads(C.Structure):
@@ -118,6 +119,9 @@ SYMBOLS = {
                                            _i32, C.POINTER(_i32 * MAX_GROUPS), C.POINTER(_i32 * MAX_GROUPS), _i32,
                                            _vp, _sz, _vp]),
     "dpmn_window_attn_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "dpmn_window_attn_forward_windowed": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(_vp * MAX_GROUPS), _i32, _i32, _i32, _i32,
+                                                    _i32, _i32, C.POINTER(_i32 * MAX_GROUPS), C.POINTER(_i32 * MAX_GROUPS),
+                                                    _i32, _vp]),
     "dpmn_cmm_workspace_bytes": (_sz, [C.POINTER(CmmDesc)]),
     "dpmn_cmm_forward": (C.c_int, [C.POINTER(CmmDesc), _vp, _vp, _vp, _vp, _sz, _vp]),
     "dpmn_cmm_debug_bytes": (_sz, [C.POINTER(CmmDesc), _i32]),

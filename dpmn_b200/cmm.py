@@ -35,9 +35,14 @@ class _CMMFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x1, x2, *params):
         with torch.no_grad():
-            out = module._forward_impl(x1, x2)
+            # fp32 forward: run it inside a private buffer laid out as the backward's workspace, so that the backward
+            # finds every activation in place and skips its recompute (DPMN_CMM_WORKSPACE_HOLDS_FORWARD)
+            keep = module.precision == "fp32"
+            res = module._forward_impl(x1, x2, keep_workspace=keep)
+            out, ws = res if keep else (res, None)
         ctx.module = module
         ctx.training = module.training
+        ctx.fwd_ws = ws
         ctx.save_for_backward(x1, x2)
         return out
 
@@ -45,7 +50,8 @@ class _CMMFunction(torch.autograd.Function):
     def backward(ctx, d_out):
         x1, x2 = ctx.saved_tensors
         d_x1, d_x2, d_params = ctx.module._backward(x1, x2, d_out, ctx.training, ctx.needs_input_grad[1],
-                                                    ctx.needs_input_grad[2])
+                                                    ctx.needs_input_grad[2], fwd_ws=ctx.fwd_ws)
+        ctx.fwd_ws = None
         return (None, d_x1, d_x2, *d_params)
 
 
@@ -121,7 +127,7 @@ class ComplementationModulationModule(ParamTree):
             return _CMMFunction.apply(self, x1, x2, *params)
         return self._forward_impl(x1, x2)
 
-    def _backward(self, x1, x2, d_out, training, need_x1=True, need_x2=True):
+    def _backward(self, x1, x2, d_out, training, need_x1=True, need_x2=True, fwd_ws=None):
         """d_out (B, c_img, H, W) -> (d x1 | None, d x2 | None, [d param in named_parameters order])."""
         lib = _lib.load()
         x1, x2 = x1.contiguous(), x2.contiguous()
@@ -169,13 +175,17 @@ class ComplementationModulationModule(ParamTree):
             nbytes = lib.dpmn_cmm_backward_workspace_bytes(C.byref(d))
             if nbytes == 0:
                 raise RuntimeError("dpmn_cmm_backward_workspace_bytes: configuration rejected")
-            ws = workspace(dev, nbytes)
+            if fwd_ws is not None and fwd_ws.numel() >= nbytes:
+                ws = fwd_ws
+                d.flags = _lib.CMM_WORKSPACE_HOLDS_FORWARD
+            else:
+                ws = workspace(dev, nbytes)
             rc = lib.dpmn_cmm_backward(C.byref(d), x1.data_ptr(), x2.data_ptr(), d_out.data_ptr(), C.byref(g),
                                        ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "dpmn_cmm_backward")
         return d_x1, d_x2, [views[n] if p.requires_grad else None for n, p in zip(names, params)]
 
-    def _forward_impl(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    def _forward_impl(self, x1: torch.Tensor, x2: torch.Tensor, keep_workspace: bool = False):
         lib = _lib.load()
         for n, t in (("x1", x1), ("x2", x2)):
             if not t.is_cuda:
@@ -196,7 +206,10 @@ class ComplementationModulationModule(ParamTree):
             nbytes = lib.dpmn_cmm_workspace_bytes(C.byref(d))
             if nbytes == 0:
                 raise RuntimeError("dpmn_cmm_workspace_bytes: configuration rejected (image sides must be multiples of 32)")
-            ws = workspace(dev, nbytes)
+            if keep_workspace:
+                ws = torch.empty(int(lib.dpmn_cmm_backward_workspace_bytes(C.byref(d))), dtype=torch.uint8, device=dev)
+            else:
+                ws = workspace(dev, nbytes)
             out = torch.empty_like(x1)
             rc = lib.dpmn_cmm_forward(C.byref(d), x1.data_ptr(), x2.data_ptr(), out.data_ptr(), ws.data_ptr(),
                                       ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
@@ -206,4 +219,4 @@ class ComplementationModulationModule(ParamTree):
             for name, buf in self.named_buffers():
                 if name.endswith("num_batches_tracked"):
                     buf += 1
-        return out
+        return (out, ws) if keep_workspace else out

@@ -406,3 +406,47 @@ def window_attention(q: torch.Tensor, kv: torch.Tensor, tables: List[torch.Tenso
                                           torch.cuda.current_stream(q.device).cuda_stream)
     _lib.check(rc, "dpmn_window_attn_forward")
     return out
+
+
+def window_order(H: int, W: int, ws: int, shift: int) -> torch.Tensor:
+    """window-major row -> original token index of one group (roll + window_partition, pgrm.py:209-221,43-52)."""
+    p = torch.arange(H * W)
+    w_idx, n = p // (ws * ws), p % (ws * ws)
+    nWw = W // ws
+    hp = (w_idx // nWw) * ws + n // ws
+    wp = (w_idx % nWw) * ws + n % ws
+    return ((hp + shift) % H) * W + (wp + shift) % W
+
+
+def to_window_major(x: torch.Tensor, grid, windows: Sequence[int], shifts: Sequence[int]) -> torch.Tensor:
+    """(B, L, C) token order -> [G][B*L][C/G] window-major per group: the layout the projection epilogue writes and
+    `window_attention_windowed` reads.  Host-side helper for tests / the stand-alone sweep (a torch gather)."""
+    B, L, C = x.shape
+    G = len(windows)
+    cg = C // G
+    parts = []
+    for g, (ws, sh) in enumerate(zip(windows, shifts)):
+        order = window_order(grid[0], grid[1], ws, sh).to(x.device)
+        parts.append(x[:, order, g * cg:(g + 1) * cg].reshape(B * L, cg))
+    return torch.stack(parts).contiguous()
+
+
+def window_attention_windowed(qw: torch.Tensor, kw: torch.Tensor, vw: torch.Tensor, tables: List[torch.Tensor], batch: int,
+                              grid, num_heads: int, windows: Sequence[int], shifts: Sequence[int]) -> torch.Tensor:
+    """The tcgen05 window-attention kernel on window-major fp16 / bf16 operands [G][B*L][C/G] -> (B, L, C)."""
+    lib = _lib.load()
+    if not (qw.is_cuda and qw.is_contiguous() and kw.is_contiguous() and vw.is_contiguous()):
+        raise RuntimeError("window_attention_windowed: contiguous CUDA tensors required")
+    prec = {torch.float16: 1, torch.bfloat16: 2}[qw.dtype]
+    G, rows, cg = qw.shape
+    L = grid[0] * grid[1]
+    out = torch.empty((batch, L, G * cg), dtype=qw.dtype, device=qw.device)
+    tabs = (C.c_void_p * _lib.MAX_GROUPS)(*[t.data_ptr() for t in tables])
+    wv = (C.c_int32 * _lib.MAX_GROUPS)(*windows)
+    sv = (C.c_int32 * _lib.MAX_GROUPS)(*shifts)
+    with torch.cuda.device(qw.device):
+        rc = lib.dpmn_window_attn_forward_windowed(qw.data_ptr(), kw.data_ptr(), vw.data_ptr(), out.data_ptr(), C.byref(tabs),
+                                                   batch, grid[0], grid[1], G * cg, num_heads, G, C.byref(wv), C.byref(sv),
+                                                   prec, torch.cuda.current_stream(qw.device).cuda_stream)
+    _lib.check(rc, "dpmn_window_attn_forward_windowed")
+    return out

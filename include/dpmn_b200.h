@@ -137,8 +137,13 @@ typedef struct dpmn_cmm_desc {
   const float *de1_w, *de1_b;                 /* de_1.1 convT3x3 (3cnum, c_img) */
   void *prepared;                             /* as in dpmn_pgrm_desc: staged tap-major 16-bit weights + folded BN */
   int32_t prepared_valid;
-  int32_t reserved_;
+  int32_t flags;                              /* DPMN_CMM_* bits, 0 by default */
 } dpmn_cmm_desc;
+
+/* dpmn_cmm_backward only: `workspace` is the buffer a dpmn_cmm_forward call with precision DPMN_PREC_F32, the same
+ * descriptor (training flag included) and the same x1 / x2 has just filled, and nothing has written to it since --
+ * the backward then skips its internal forward recompute.  The buffer must have dpmn_cmm_backward_workspace_bytes(). */
+#define DPMN_CMM_WORKSPACE_HOLDS_FORWARD 1
 
 const char *dpmn_version(void);
 
@@ -184,6 +189,17 @@ int dpmn_window_attn_forward(const void *q, const void *kv, void *out, const flo
                              const int32_t shift[DPMN_MAX_GROUPS], int32_t precision,
                              void *workspace, size_t workspace_bytes, void *stream);
 size_t dpmn_window_attn_workspace_bytes(int32_t batch, int32_t tokens, int32_t embed_dim, int32_t precision);
+
+/* The same attention core on WINDOW-MAJOR operands -- the layout the fused pipeline feeds it (the q / kv projection
+ * epilogue applies roll + window_partition, pgrm.py:209-225): qw, kw, vw are [n_groups][batch*L][embed_dim/n_groups]
+ * 16-bit, row p of group g = token window_row_to_token(p) of that group's (window, shift).  This is the tcgen05
+ * kernel (attn_tc.cu) itself: precision must be F16 or BF16, windows in {2,4,8}, head_dim 16 or 32, an even number
+ * of heads per group; anything else returns DPMN_E_UNSUPPORTED.  out (batch*L, embed_dim) window-major rows. */
+int dpmn_window_attn_forward_windowed(const void *qw, const void *kw, const void *vw, void *out,
+                                      const float *const rpb_table[DPMN_MAX_GROUPS], int32_t batch, int32_t grid_h,
+                                      int32_t grid_w, int32_t embed_dim, int32_t num_heads, int32_t n_groups,
+                                      const int32_t window[DPMN_MAX_GROUPS], const int32_t shift[DPMN_MAX_GROUPS],
+                                      int32_t precision, void *stream);
 
 size_t dpmn_cmm_workspace_bytes(const dpmn_cmm_desc *d);
 size_t dpmn_cmm_prepared_bytes(const dpmn_cmm_desc *d);     /* 0 in the fp32 mode */

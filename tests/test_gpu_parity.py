@@ -313,3 +313,27 @@ def test_prepared_weight_cache_tracks_in_place_updates():
         mc.fetch("de_1.1.bias").add_(1.0)
         c = mc(_t(x1), _t(x2))
     assert rel_err((c - a).cpu().numpy(), np.ones_like(a.cpu().numpy())) < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,windows,shifted", [(96, [2, 4, 8], True), (96, [8], False), (96, [4], True), (192, [8], True),
+                                               (192, [2], False)])
+def test_window_attention_windowed_tcgen05_matches_simt(C, windows, shifted):
+    """dpmn_window_attn_forward_windowed (the tcgen05 kernel on window-major operands, head_dim 16 and 32) against the
+    fp32 SIMT core on the same values in token order."""
+    import torch
+    from dpmn_b200.pgrm import to_window_major, window_attention, window_attention_windowed
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    B, H, W, heads = 2, 16, 64, 6
+    G = len(windows)
+    shifts = [w // 2 if shifted else 0 for w in windows]
+    q = torch.randn(B, H * W, C, device=dev).half()
+    kv = torch.randn(B, H * W, 2 * C, device=dev).half()
+    tabs = [torch.randn((2 * w - 1) ** 2, heads // G, device=dev) * 0.5 for w in windows]
+    ref = window_attention(q.float(), kv.float(), tabs, (H, W), heads, windows, shifts)
+    qw = to_window_major(q, (H, W), windows, shifts)
+    kw = to_window_major(kv[..., :C].contiguous(), (H, W), windows, shifts)
+    vw = to_window_major(kv[..., C:].contiguous(), (H, W), windows, shifts)
+    out = window_attention_windowed(qw, kw, vw, tabs, B, (H, W), heads, windows, shifts)
+    assert rel_err(out.float().cpu().numpy(), ref.cpu().numpy()) < 2e-3

@@ -203,15 +203,6 @@ def run_ours(args):
             return trainer.step(*ds)
         return model(*ds[:3])
 
-    def step_e2e(i):
-        hs = host_sets[i % n_sets]
-        psn = hs[0].to(dev, non_blocking=True)
-        p1 = [a.to(dev, non_blocking=True) for a in hs[1]]
-        p2 = [a.to(dev, non_blocking=True) for a in hs[2]]
-        y = trainer.step(psn, p1, p2, hs[3].to(dev, non_blocking=True)) if train else model(psn, p1, p2)
-        out_host.copy_(y, non_blocking=True)
-        return y
-
     with torch.set_grad_enabled(train):
         # ---------- value: inputs resident in HBM
         for i in range(args.warmup):
@@ -231,15 +222,32 @@ def run_ours(args):
         launches = lib.dpmn_launch_count() - launches0
         clk = clocks.stop() if rank == 0 else None
         # ---------- e2e: pinned host buffers, H2D + D2H inside the timed region
-        for i in range(min(args.warmup, 3)):
-            step_e2e(i)
+        from dpmn_b200.pipeline import HostFeeder
+        feeder = HostFeeder(dev)
+
+        def run_e2e(n):
+            """n steps from pinned host memory: H2D of step i+1 and D2H of step i-1 overlap the kernels of step i."""
+            def batch(i):
+                hs = host_sets[i % n_sets]
+                return [hs[0], hs[1], hs[2]] + ([hs[3]] if train else [])
+            ticket = feeder.stage(batch(0))
+            for i in range(n):
+                nxt = feeder.stage(batch(i + 1)) if i + 1 < n else None
+                ins = feeder.get(ticket)
+                y = trainer.step(*ins) if train else model(*ins)
+                feeder.release(ticket)
+                feeder.fetch(y, out_host)
+                ticket = nxt
+            feeder.drain()
+        run_e2e(min(args.warmup, 3))
         barrier()
+        t0 = time.perf_counter()
         e0.record()
-        for i in range(args.steps):
-            step_e2e(i)
+        run_e2e(args.steps)          # ends with the last result in host memory (drain)
         e1.record()
         barrier()
-        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
         # ---------- per-kernel-class timing (roofline leg), outside the throughput regions
         prof = None
         if rank == 0:

@@ -57,8 +57,8 @@ struct AttnSmem {
   static constexpr int TILE = AT_ROWS * D * 2;                  // one Q/K/V head tile
   static constexpr int STAGE = AT_HC * 3 * TILE;
   static constexpr int P_TILE = AT_ROWS * 128 * 2;              // 32 KB per head
-  static constexpr int TABLE_FLOATS = 4 * 2 * 256;              // up to 4 groups x 2 heads-of-unit... see below
-  static constexpr int TOTAL = AT_STAGES * STAGE + AT_HC * P_TILE + 1024 + 256 + 4096 * 4;
+  static constexpr int PBUF = D == 16 ? 2 : 1;                  // P double-buffered where shared memory allows
+  static constexpr int TOTAL = AT_STAGES * STAGE + PBUF * AT_HC * P_TILE + 1024 + 256 + 4096 * 4;
 };
 
 template <int WS>
@@ -87,7 +87,8 @@ __device__ __forceinline__ void select_block(const uint32_t (&r)[64], int lane, 
 template <int WS, typename T>
 __device__ __forceinline__ void softmax_row(uint32_t tmem_s, int quarter, int lane, int row, int n, const float* tab,
                                             float scale, bool masked, uint32_t rh_bits, uint32_t rw_bits,
-                                            uint8_t* p_tile) {
+                                            uint8_t* p_tile, uint64_t* s_empty_bar, uint64_t* p_empty_bar,
+                                            uint32_t p_empty_parity, bool full_row) {
   constexpr int N = WS * WS;
   constexpr int TW = 2 * WS - 1;
   // the row's window block sits at columns [blk*N, blk*N + N); a warp's 32 rows share one 32/64-column span
@@ -109,6 +110,10 @@ __device__ __forceinline__ void softmax_row(uint32_t tmem_s, int quarter, int la
     }
     tmem_ld_wait();
   }
+  // the scores are in registers: hand the S accumulator back so the next unit's QK^T overlaps this softmax
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(s_empty_bar);
   float s[N];
   select_block<WS>(r, lane, s);
   const int i_n = n / WS, j_n = n % WS;
@@ -155,14 +160,26 @@ __device__ __forceinline__ void softmax_row(uint32_t tmem_s, int quarter, int la
   }
   const int c_own0 = key0 >> 3;
   uint8_t* row_base = p_tile + (size_t)row * 128;
+  mbar_wait(p_empty_bar, p_empty_parity);          // the P*V that last read this P buffer has retired
+  if (full_row) {
+    // first unit of a window group in this buffer: the zeros outside the row's own window block are (re)written
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    for (int c = 0; c < 16; ++c) {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int q = 0; q < OWN; ++q)
-      if (c == c_own0 + q) v = own[q];
-    const int kb = c >> 3, cc = c & 7;
-    *reinterpret_cast<uint4*>(row_base + kb * (AT_ROWS * 128) + ((cc ^ (row & 7)) << 4)) = v;
+      for (int q = 0; q < OWN; ++q)
+        if (c == c_own0 + q) v = own[q];
+      const int kb = c >> 3, cc = c & 7;
+      *reinterpret_cast<uint4*>(row_base + kb * (AT_ROWS * 128) + ((cc ^ (row & 7)) << 4)) = v;
+    }
+  } else {
+    // same group as the previous unit in this buffer: the block position of every row is unchanged
+#pragma unroll
+    for (int q = 0; q < OWN; ++q) {
+      const int c = c_own0 + q;
+      const int kb = c >> 3, cc = c & 7;
+      *reinterpret_cast<uint4*>(row_base + kb * (AT_ROWS * 128) + ((cc ^ (row & 7)) << 4)) = own[q];
+    }
   }
 }
 
@@ -175,16 +192,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   using S = AttnSmem<D>;
   uint8_t* stages = smem;
   uint8_t* p_tiles = smem + AT_STAGES * S::STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_tiles + AT_HC * S::P_TILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_tiles + S::PBUF * AT_HC * S::P_TILE);
   uint64_t* full_bar = bars;                       // [AT_STAGES]
   uint64_t* empty_bar = bars + AT_STAGES;          // [AT_STAGES]
   uint64_t* s_full = bars + 2 * AT_STAGES;
   uint64_t* s_empty = s_full + 1;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* p_empty = s_full + 3;
-  uint64_t* o_full = s_full + 4;                   // [2]
-  uint64_t* o_empty = s_full + 6;                  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
+  uint64_t* p_full = s_full + 2;                   // [2]
+  uint64_t* p_empty = s_full + 4;                  // [2]
+  uint64_t* o_full = s_full + 6;                   // [2]
+  uint64_t* o_empty = s_full + 8;                  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 10);
+  constexpr int PBUF = S::PBUF;
   float* s_tab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [G][hpg][tab_stride]
   constexpr int TAB_STRIDE = 232;                  // >= (2*8-1)^2 = 225
 
@@ -201,8 +219,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     for (int i = 0; i < AT_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 4 * AT_HC); mbar_init(p_full, 4 * AT_HC); mbar_init(p_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4 * AT_HC); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 4 * AT_HC);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_full[i], 4 * AT_HC); mbar_init(&p_empty[i], 1);
+      mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4 * AT_HC);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -211,10 +232,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+// units are ordered group-major, so a CTA's consecutive units share the window size (the P zero pattern)
 #define DPMN_UNIT(u)                                   \
   const int hc = (u) % p.nhc;                          \
-  const int g = ((u) / p.nhc) % p.G;                   \
-  const int tile = (u) / (p.nhc * p.G);
+  const int tile = ((u) / p.nhc) % p.tiles;            \
+  const int g = (u) / (p.nhc * p.tiles);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -242,14 +264,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       auto issue_pv = [&](int j) {
         const int stage = j % AT_STAGES;
         const int ob = j & 1;
-        mbar_wait(p_full, (uint32_t)(j & 1));
+        const int pb = j % PBUF;
+        mbar_wait(&p_full[pb], (uint32_t)((j / PBUF) & 1));
         mbar_wait(&o_empty[ob], (uint32_t)(((j >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint8_t* st = stages + stage * S::STAGE;
 #pragma unroll
         for (int h = 0; h < AT_HC; ++h) {
           const uint32_t d_o = tmem_base + O_COL0 + (uint32_t)(ob * AT_HC * D + h * D);
-          const uint32_t pa = smem_u32(p_tiles + h * S::P_TILE);
+          const uint32_t pa = smem_u32(p_tiles + (pb * AT_HC + h) * S::P_TILE);
           const uint32_t va = smem_u32(st + (h * 3 + 2) * S::TILE);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {   // 8 k-steps of 16 keys
@@ -259,7 +282,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           }
         }
         umma_commit(&empty_bar[stage]);
-        umma_commit(p_empty);
+        umma_commit(&p_empty[pb]);
         umma_commit(&o_full[ob]);
       };
       int it = 0;
@@ -289,8 +312,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     T* out = reinterpret_cast<T*>(p.out);
     auto epilogue = [&](int j, int u_prev) {
       const int hc = u_prev % p.nhc;
-      const int g = (u_prev / p.nhc) % p.G;
-      const int tile = u_prev / (p.nhc * p.G);
+      const int tile = (u_prev / p.nhc) % p.tiles;
+      const int g = u_prev / (p.nhc * p.tiles);
       const int ob = j & 1;
       mbar_wait(&o_full[ob], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
@@ -312,6 +335,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
     };
     int it = 0, u_prev = -1;
+    int last_g[2] = {-1, -1};                           // group whose zero pattern each P buffer currently holds
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
       DPMN_UNIT(u)
       const int ws = p.ws[g], N = ws * ws, shift = p.shift[g];
@@ -329,19 +353,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       }
       mbar_wait(s_full, (uint32_t)(it & 1));
       tc_fence_after();
-      mbar_wait(p_empty, (uint32_t)((it & 1) ^ 1));
+      const int pb = it % PBUF;
       {
         const float* tab = s_tab + (g * p.hpg + hc * AT_HC + h) * TAB_STRIDE;
         const uint32_t ts = tmem_base + (uint32_t)(h * 128);
-        uint8_t* pt = p_tiles + h * S::P_TILE;
-        if (ws == 8) softmax_row<8, T>(ts, quarter, lane, row, n, tab, p.scale, shift > 0, rh_bits, rw_bits, pt);
-        else if (ws == 4) softmax_row<4, T>(ts, quarter, lane, row, n, tab, p.scale, shift > 0, rh_bits, rw_bits, pt);
-        else softmax_row<2, T>(ts, quarter, lane, row, n, tab, p.scale, shift > 0, rh_bits, rw_bits, pt);
+        uint8_t* pt = p_tiles + (pb * AT_HC + h) * S::P_TILE;
+        uint64_t* pe = &p_empty[pb];
+        const uint32_t pe_par = (uint32_t)(((it / PBUF) & 1) ^ 1);
+        const bool full_row = last_g[pb] != g;
+        last_g[pb] = g;
+        if (ws == 8) softmax_row<8, T>(ts, quarter, lane, row, n, tab, p.scale, shift > 0, rh_bits, rw_bits, pt, s_empty, pe, pe_par, full_row);
+        else if (ws == 4) softmax_row<4, T>(ts, quarter, lane, row, n, tab, p.scale, shift > 0, rh_bits, rw_bits, pt, s_empty, pe, pe_par, full_row);
+        else softmax_row<2, T>(ts, quarter, lane, row, n, tab, p.scale, shift > 0, rh_bits, rw_bits, pt, s_empty, pe, pe_par, full_row);
       }
-      tc_fence_before();
       fence_proxy_async();          // P (generic-proxy stores) must be visible to the tensor core's async proxy
       __syncwarp();
-      if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(p_full); }
+      if (lane == 0) mbar_arrive(&p_full[pb]);
       if (it > 0) epilogue(it - 1, u_prev);
       u_prev = u;
     }

@@ -64,3 +64,70 @@ class DPMNHotPath(nn.Module):
         outs += done
         outs.append(self.cmm(sr1, done[-1]))                           # :265
         return outs
+
+
+class HostFeeder:
+    """Host <-> device staging for callers that hold their batches in (pinned) host memory: inputs of step i+1 are
+    copied on a side stream while step i computes, and the result of step i is read back on another side stream, so
+    PCIe traffic overlaps the kernels instead of serialising with them.  Plumbing only (streams + events)."""
+
+    def __init__(self, device: torch.device, depth: int = 2):
+        self.device = device
+        self.depth = depth
+        self.h2d = torch.cuda.Stream(device)
+        self.d2h = torch.cuda.Stream(device)
+        self.slots = [None] * depth          # device tensors per slot
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.consumed = [None] * depth       # event: the compute that read the slot has been enqueued and finished
+        self.n = 0
+        self.out_done = None
+
+    @staticmethod
+    def _flatten(x):
+        return [x] if torch.is_tensor(x) else [t for y in x for t in HostFeeder._flatten(y)]
+
+    @staticmethod
+    def _rebuild(x, it):
+        return next(it) if torch.is_tensor(x) else [HostFeeder._rebuild(y, it) for y in x]
+
+    def stage(self, host_batch):
+        """Enqueue the H2D copies of a (nested list of) host tensors; returns a ticket for `get`."""
+        slot = self.n % self.depth
+        self.n += 1
+        flat = self._flatten(host_batch)
+        if self.slots[slot] is None or [t.shape for t in self.slots[slot]] != [t.shape for t in flat]:
+            self.slots[slot] = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in flat]
+        with torch.cuda.stream(self.h2d):
+            if self.consumed[slot] is not None:
+                self.h2d.wait_event(self.consumed[slot])       # do not overwrite inputs a running step still reads
+            for dst, src in zip(self.slots[slot], flat):
+                dst.copy_(src, non_blocking=True)
+            self.ready[slot].record(self.h2d)
+        return slot, host_batch
+
+    def get(self, ticket):
+        """Device tensors of a staged batch, ordered after their copies on the current stream."""
+        slot, structure = ticket
+        torch.cuda.current_stream(self.device).wait_event(self.ready[slot])
+        return self._rebuild(structure, iter(self.slots[slot]))
+
+    def release(self, ticket):
+        """Call after the step that consumed the batch has been enqueued."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.consumed[ticket[0]] = ev
+
+    def fetch(self, result: torch.Tensor, host_out: torch.Tensor):
+        """Read a result back into pinned host memory on the D2H stream."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(ev)
+            result.record_stream(self.d2h)
+            host_out.copy_(result, non_blocking=True)
+            self.out_done = torch.cuda.Event()
+            self.out_done.record(self.d2h)
+
+    def drain(self):
+        self.h2d.synchronize()
+        self.d2h.synchronize()

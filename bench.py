@@ -250,9 +250,13 @@ def run_ours(args):
         ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
         # ---------- per-kernel-class timing (roofline leg), outside the throughput regions
         prof = None
+        n_prof = 2
+        if rank != 0 and train and world > 1:
+            for i in range(n_prof):       # the training step contains a collective: every rank has to take part
+                step_resident(i)
+            torch.cuda.synchronize()
         if rank == 0:
             lib.dpmn_profile_enable(1)
-            n_prof = 2
             for i in range(n_prof):
                 step_resident(i)
             torch.cuda.synchronize()

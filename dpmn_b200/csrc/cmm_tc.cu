@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) cmm_en1_kernel(const float* __restrict__ 
                                                       const float* __restrict__ w2, const float* __restrict__ b2,
                                                       T* __restrict__ e1, T* __restrict__ cat1, int B, int H, int W,
                                                       int c_img, int cnum) {
-  extern __shared__ float sw[];   // [c_img*9][cnum] + bias [cnum]
+  extern __shared__ __align__(16) float sw[];   // [c_img*9][cnum] + bias [cnum]
   const int g = blockIdx.y;
   const float* x = g == 0 ? x1 : x2;
   const float* w = g == 0 ? w1 : w2;
@@ -78,48 +78,66 @@ __global__ void __launch_bounds__(256) cmm_en1_kernel(const float* __restrict__ 
   float* sb = sw + K * cnum;
   for (int i = threadIdx.x; i < cnum; i += blockDim.x) sb[i] = bsrc[i];
   __syncthreads();
+  // one thread = two horizontally adjacent pixels x 8 output channels: each 3x3xc_img weight vector (two float4 from
+  // shared memory) feeds 16 FMAs, and the 3 x 4 input patch is loaded once for both pixels
   const int groups = cnum / 8;
-  const long long total = (long long)B * H * W * groups;
+  const int Wp = W / 2;
+  const long long total = (long long)B * H * Wp * groups;
   const long long HW = (long long)H * W;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(idx % groups);
-    const long long pix = idx / groups;
-    const int xx = (int)(pix % W);
-    const int yy = (int)((pix / W) % H);
-    const int b = (int)(pix / HW);
-    float acc[8];
+    const long long pp = idx / groups;
+    const int xp = (int)(pp % Wp);
+    const int yy = (int)((pp / Wp) % H);
+    const int b = (int)(pp / ((long long)Wp * H));
+    const int x0 = 2 * xp;
+    float acc[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sb[cg * 8 + j];
-    for (int ci = 0; ci < c_img; ++ci)
+    for (int j = 0; j < 8; ++j) { acc[0][j] = sb[cg * 8 + j]; acc[1][j] = acc[0][j]; }
+    for (int ci = 0; ci < c_img; ++ci) {
+      const float* xc = x + ((long long)b * c_img + ci) * HW;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int y2 = yy + ky - 1;
         if (y2 < 0 || y2 >= H) continue;
+        const float* xr = xc + (long long)y2 * W;
+        float v[4];
+        v[0] = x0 > 0 ? xr[x0 - 1] : 0.f;
+        v[1] = xr[x0];
+        v[2] = xr[x0 + 1];
+        v[3] = x0 + 2 < W ? xr[x0 + 2] : 0.f;
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const int x2 = xx + kx - 1;
-          if (x2 < 0 || x2 >= W) continue;
-          const float v = x[((long long)b * c_img + ci) * HW + (long long)y2 * W + x2];
-          const float* wr = sw + ((ci * 3 + ky) * 3 + kx) * cnum + cg * 8;
+          const float4* wr = reinterpret_cast<const float4*>(sw + ((ci * 3 + ky) * 3 + kx) * cnum + cg * 8);
+          const float4 wa = wr[0], wb = wr[1];
+          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+          for (int j = 0; j < 8; ++j) {
+            acc[0][j] = fmaf(v[kx], wv[j], acc[0][j]);
+            acc[1][j] = fmaf(v[kx + 1], wv[j], acc[1][j]);
+          }
         }
       }
-    union { uint4 u; T h[8]; } a, r;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      a.h[j] = from_f32<T>(acc[j] >= 0.f ? acc[j] : 0.2f * acc[j]);
-      r.h[j] = from_f32<T>(fmaxf(acc[j], 0.f));
     }
-    *reinterpret_cast<uint4*>(e1 + ((long long)g * B * HW + pix) * cnum + cg * 8) = a.u;
-    *reinterpret_cast<uint4*>(cat1 + pix * (3 * cnum) + cnum * (1 + g) + cg * 8) = r.u;
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      const long long pix = ((long long)b * H + yy) * W + x0 + px;
+      union { uint4 u; T h[8]; } a, r;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a.h[j] = from_f32<T>(acc[px][j] >= 0.f ? acc[px][j] : 0.2f * acc[px][j]);
+        r.h[j] = from_f32<T>(fmaxf(acc[px][j], 0.f));
+      }
+      *reinterpret_cast<uint4*>(e1 + ((long long)g * B * HW + pix) * cnum + cg * 8) = a.u;
+      *reinterpret_cast<uint4*>(cat1 + pix * (3 * cnum) + cnum * (1 + g) + cg * 8) = r.u;
+    }
   }
 }
 
 int launch_cmm_en1(const float* x1, const float* x2, const float* w1, const float* b1, const float* w2, const float* b2,
                    void* e1, void* cat1, DType t, int B, int H, int W, int c_img, int cnum, cudaStream_t st) {
-  if (cnum % 8) return -2;
+  if (cnum % 8 || W % 2) return -2;
   const size_t smem = (size_t)(c_img * 9 * cnum + cnum) * sizeof(float);
   if (smem > 48 * 1024) return -2;
   dim3 grid(148 * 4, 2);

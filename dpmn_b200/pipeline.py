@@ -38,6 +38,8 @@ class DPMNHotPath(nn.Module):
         self.b1, self.b2 = stu_iter_b1, stu_iter_b2
         self.pgrm = nn.ModuleList(build_pgrm_stack(precision, stu_iter_b1, stu_iter_b2, drop))
         self.cmm = ComplementationModulationModule(precision=cmm_precision or precision)
+        self.concurrent_branches = True       # inference: the two PGRM cascades run on two CUDA streams
+        self._streams = None
 
     def forward(self, psn_out: torch.Tensor, priors_b1: Sequence[torch.Tensor], priors_b2: Sequence[torch.Tensor]):
         """psn_out (B,4,32,128) frozen-backbone output; priors_b1[k] (B,2,32,128) rendered-text maps;
@@ -47,20 +49,44 @@ class DPMNHotPath(nn.Module):
     def forward_all(self, psn_out, priors_b1, priors_b2) -> List[torch.Tensor]:
         """All seven images the training loss looks at (super_resolution.py:212,239,267): the six PGRM outputs in
         call order, then the CMM output."""
-        cascade = psn_out[:, :3, :]                       # channel-slice view, super_resolution.py:196
-        done: List[torch.Tensor] = []
-        for k in range(self.b1):
-            y = self.pgrm[k](priors_b1[k], cascade, done[:k])          # :207
-            done.append(y)
-            cascade = y
-        sr1 = done[-1]
-        outs = list(done)
-        cascade = psn_out[:, :3, :]
-        done = []
-        for k in range(self.b1, self.b1 + self.b2):
-            y = self.pgrm[k](priors_b2[k - self.b1], cascade, done[:k - self.b2])   # :234
-            done.append(y)
-            cascade = y
+        def branch(first, count, priors):
+            cascade = psn_out[:, :3, :]                   # channel-slice view, super_resolution.py:196
+            done: List[torch.Tensor] = []
+            for j in range(count):
+                k = first + j
+                # residual_list = the earlier outputs of this branch (super_resolution.py:207,234)
+                y = self.pgrm[k](priors[j], cascade, done[:j])
+                done.append(y)
+                cascade = y
+            return done
+
+        if psn_out.is_cuda and not torch.is_grad_enabled() and self.concurrent_branches:
+            # The two cascades are independent until the CMM (super_resolution.py:174-240): run them on two side
+            # streams so the tail of one branch's kernel overlaps the launch + prologue of the other's.  Workspaces
+            # are per stream (pgrm.workspace), staged weights per module, so nothing is shared between the branches.
+            dev = psn_out.device
+            main = torch.cuda.current_stream(dev)
+            if self._streams is None or self._streams[0].device != dev:
+                self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            start = torch.cuda.Event()
+            start.record(main)
+            results = []
+            for st, (first, count, priors) in zip(self._streams, ((0, self.b1, priors_b1), (self.b1, self.b2, priors_b2))):
+                st.wait_event(start)          # also orders this step after everything the previous step left on `main`
+                with torch.cuda.stream(st):
+                    done = branch(first, count, priors)
+                for t in done:
+                    t.record_stream(main)
+                end = torch.cuda.Event()
+                end.record(st)
+                main.wait_event(end)
+                results.append(done)
+            done1, done = results
+        else:
+            done1 = branch(0, self.b1, priors_b1)
+            done = branch(self.b1, self.b2, priors_b2)
+        sr1 = done1[-1]
+        outs = list(done1)
         outs += done
         outs.append(self.cmm(sr1, done[-1]))                           # :265
         return outs

@@ -152,7 +152,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     lib = _lib.load()
     assert lib.dpmn_check_device() == 0
 
@@ -214,8 +215,16 @@ def run_ours(args):
             clocks.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(args.steps):
-            step_resident(i)
+        if train:
+            for i in range(args.steps):
+                step_resident(i)
+        else:
+            # throughput: batches are submitted back to back (DPMNHotPath.submit keeps them in flight on its own
+            # streams); the timed region ends when the LAST batch's result is complete on the timing stream
+            last = None
+            for i in range(args.steps):
+                _, last = model.submit(*dev_sets[i % n_sets][:3])
+            torch.cuda.current_stream(dev).wait_event(last)
         e1.record()
         barrier()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -234,9 +243,14 @@ def run_ours(args):
             for i in range(n):
                 nxt = feeder.stage(batch(i + 1)) if i + 1 < n else None
                 ins = feeder.get(ticket)
-                y = trainer.step(*ins) if train else model(*ins)
-                feeder.release(ticket)
-                feeder.fetch(y, out_host)
+                if train:
+                    y = trainer.step(*ins)
+                    feeder.release(ticket)
+                    feeder.fetch(y, out_host)
+                else:
+                    y, done = model.submit(*ins)
+                    feeder.release(ticket, after=done)
+                    feeder.fetch(y, out_host, after=done)
                 ticket = nxt
             feeder.drain()
         run_e2e(min(args.warmup, 3))

@@ -88,7 +88,7 @@ template <int WS, typename T>
 __device__ __forceinline__ void softmax_row(uint32_t tmem_s, int quarter, int lane, int row, int n, const float* tab,
                                             float scale, bool masked, uint32_t rh_bits, uint32_t rw_bits,
                                             uint8_t* p_tile, uint64_t* s_empty_bar, uint64_t* p_empty_bar,
-                                            uint32_t p_empty_parity, bool full_row) {
+                                            uint32_t p_empty_parity, bool full_row, float& inv_out) {
   constexpr int N = WS * WS;
   constexpr int TW = 2 * WS - 1;
   // the row's window block sits at columns [blk*N, blk*N + N); a warp's 32 rows share one 32/64-column span
@@ -118,22 +118,38 @@ __device__ __forceinline__ void softmax_row(uint32_t tmem_s, int quarter, int la
   select_block<WS>(r, lane, s);
   const int i_n = n / WS, j_n = n % WS;
   const uint32_t my_h = (rh_bits >> (2 * i_n)) & 3u, my_w = (rw_bits >> (2 * j_n)) & 3u;
+  // Everything is in the log2 domain (`scale` and the table carry log2(e)), so each key costs FMA, max, add, ex2, add.
+  // The shift mask only exists in border windows: a window whose rows / columns all carry the same region label
+  // (the common case) skips it.
+  constexpr uint32_t FIELDS = (1u << (2 * WS)) - 1u;
+  const bool need_mask = masked && ((rh_bits != ((0x55555555u & FIELDS) * my_h)) || (rw_bits != ((0x55555555u & FIELDS) * my_w)));
   float mx = -INFINITY;
+  if (need_mask) {
 #pragma unroll
-  for (int m = 0; m < N; ++m) {
-    const int i_m = m / WS, j_m = m % WS;
-    float v = s[m] * scale + tab[(i_n - i_m + WS - 1) * TW + (j_n - j_m + WS - 1)];
-    if (masked) {
+    for (int m = 0; m < N; ++m) {
+      const int i_m = m / WS, j_m = m % WS;
+      float v = fmaf(s[m], scale, tab[(i_n - i_m + WS - 1) * TW + (j_n - j_m + WS - 1)]);
       const bool diff = (((rh_bits >> (2 * i_m)) & 3u) != my_h) || (((rw_bits >> (2 * j_m)) & 3u) != my_w);
-      v += diff ? -100.0f : 0.0f;                       // pgrm.py:173
+      v += diff ? -144.26950408889634f : 0.0f;          // -100 (pgrm.py:173) * log2(e)
+      s[m] = v;
+      mx = fmaxf(mx, v);
     }
-    s[m] = v;
-    mx = fmaxf(mx, v);
+  } else {
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      const int i_m = m / WS, j_m = m % WS;
+      const float v = fmaf(s[m], scale, tab[(i_n - i_m + WS - 1) * TW + (j_n - j_m + WS - 1)]);
+      s[m] = v;
+      mx = fmaxf(mx, v);
+    }
   }
   float den = 0.f;
 #pragma unroll
-  for (int m = 0; m < N; ++m) { s[m] = __expf(s[m] - mx); den += s[m]; }
-  const float inv = 1.0f / den;
+  for (int m = 0; m < N; ++m) { s[m] = exp2f(s[m] - mx); den += s[m]; }
+  // P is stored UNNORMALISED (values in (0, 1]); the epilogue scales the D outputs of the row by 1/den instead of
+  // the N probabilities here
+  const float inv = 1.0f;
+  inv_out = 1.0f / den;
   // P row: keys [key0, key0 + N) of the tile hold the probabilities, everything else is 0.  The row is
   // 16 x 16-byte chunks (8 keys each), two 64-key k-blocks of 16 KB, chunk index XOR (row & 7) = 128B swizzle.
   const int key0 = (row / N) * N;
@@ -214,7 +230,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int e = i % TAB_STRIDE, gh = i / TAB_STRIDE;
     const int g = gh / p.hpg, h = gh - g * p.hpg;
     const int tw = 2 * p.ws[g] - 1;
-    s_tab[i] = e < tw * tw ? p.table[g][e * p.hpg + h] : 0.f;
+    s_tab[i] = e < tw * tw ? p.table[g][e * p.hpg + h] * 1.4426950408889634f : 0.f;   // log2 domain
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
@@ -310,7 +326,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int h = (warp - 2) >> 2;                      // this warp set's head within the unit
     const int row = quarter * 32 + lane;
     T* out = reinterpret_cast<T*>(p.out);
-    auto epilogue = [&](int j, int u_prev) {
+    auto epilogue = [&](int j, int u_prev, float inv_row) {
       const int hc = u_prev % p.nhc;
       const int tile = (u_prev / p.nhc) % p.tiles;
       const int g = u_prev / (p.nhc * p.tiles);
@@ -330,12 +346,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       for (int c = 0; c < D; c += 8) {
         union { uint4 u; T hh[8]; } pk;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) pk.hh[e] = from_f32<T>(__uint_as_float(o[c + e]));
+        for (int e = 0; e < 8; ++e) pk.hh[e] = from_f32<T>(__uint_as_float(o[c + e]) * inv_row);
         *reinterpret_cast<uint4*>(dst + c) = pk.u;
       }
     };
     int it = 0, u_prev = -1;
     int last_g[2] = {-1, -1};                           // group whose zero pattern each P buffer currently holds
+    float inv_prev = 1.f, inv_cur = 1.f;                // 1 / softmax denominator of this thread's row
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
       DPMN_UNIT(u)
       const int ws = p.ws[g], N = ws * ws, shift = p.shift[g];
@@ -362,17 +379,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const uint32_t pe_par = (uint32_t)(((it / PBUF) & 1) ^ 1);
         const bool full_row = last_g[pb] != g;
         last_g[pb] = g;
-        if (ws == 8) softmax_row<8, T>(ts, quarter, lane, row, n, tab, p.scale, shift > 0, rh_bits, rw_bits, pt, s_empty, pe, pe_par, full_row);
-        else if (ws == 4) softmax_row<4, T>(ts, quarter, lane, row, n, tab, p.scale, shift > 0, rh_bits, rw_bits, pt, s_empty, pe, pe_par, full_row);
-        else softmax_row<2, T>(ts, quarter, lane, row, n, tab, p.scale, shift > 0, rh_bits, rw_bits, pt, s_empty, pe, pe_par, full_row);
+        if (ws == 8) softmax_row<8, T>(ts, quarter, lane, row, n, tab, p.scale, shift > 0, rh_bits, rw_bits, pt, s_empty, pe, pe_par, full_row, inv_cur);
+        else if (ws == 4) softmax_row<4, T>(ts, quarter, lane, row, n, tab, p.scale, shift > 0, rh_bits, rw_bits, pt, s_empty, pe, pe_par, full_row, inv_cur);
+        else softmax_row<2, T>(ts, quarter, lane, row, n, tab, p.scale, shift > 0, rh_bits, rw_bits, pt, s_empty, pe, pe_par, full_row, inv_cur);
       }
       fence_proxy_async();          // P (generic-proxy stores) must be visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[pb]);
-      if (it > 0) epilogue(it - 1, u_prev);
+      if (it > 0) epilogue(it - 1, u_prev, inv_prev);
+      inv_prev = inv_cur;
       u_prev = u;
     }
-    if (it > 0) epilogue(it - 1, u_prev);
+    if (it > 0) epilogue(it - 1, u_prev, inv_prev);
   }
 #undef DPMN_UNIT
 
@@ -393,7 +411,7 @@ static int launch_attn_tc_t(const AttnTcArgs& a, cudaStream_t st) {
   p.cg = a.C / a.n_groups;
   for (int g = 0; g < a.n_groups; ++g) { p.ws[g] = a.window[g]; p.shift[g] = a.shift[g]; p.table[g] = a.table[g]; }
   p.tiles = a.B * p.L / AT_ROWS; p.nhc = a.heads_per_group / AT_HC; p.total_units = p.tiles * p.nhc * p.G;
-  p.out = a.out; p.fmt = a.io_type == DT_BF16 ? 1 : 0; p.scale = 1.0f / sqrtf((float)D);
+  p.out = a.out; p.fmt = a.io_type == DT_BF16 ? 1 : 0; p.scale = 1.4426950408889634f / sqrtf((float)D);   // d^-0.5 * log2(e)
   CUtensorMap maps[3];
   const void* bases[3] = {a.qw, a.kw, a.vw};
   const long long rows = (long long)a.B * p.L;

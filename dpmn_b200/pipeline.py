@@ -61,35 +61,62 @@ class DPMNHotPath(nn.Module):
             return done
 
         if psn_out.is_cuda and not torch.is_grad_enabled() and self.concurrent_branches:
-            # The two cascades are independent until the CMM (super_resolution.py:174-240): run them on two side
-            # streams so the tail of one branch's kernel overlaps the launch + prologue of the other's.  Workspaces
-            # are per stream (pgrm.workspace), staged weights per module, so nothing is shared between the branches.
-            dev = psn_out.device
-            main = torch.cuda.current_stream(dev)
-            if self._streams is None or self._streams[0].device != dev:
-                self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
-            start = torch.cuda.Event()
-            start.record(main)
-            results = []
-            for st, (first, count, priors) in zip(self._streams, ((0, self.b1, priors_b1), (self.b1, self.b2, priors_b2))):
-                st.wait_event(start)          # also orders this step after everything the previous step left on `main`
-                with torch.cuda.stream(st):
-                    done = branch(first, count, priors)
-                for t in done:
-                    t.record_stream(main)
-                end = torch.cuda.Event()
-                end.record(st)
-                main.wait_event(end)
-                results.append(done)
-            done1, done = results
-        else:
-            done1 = branch(0, self.b1, priors_b1)
-            done = branch(self.b1, self.b2, priors_b2)
-        sr1 = done1[-1]
-        outs = list(done1)
-        outs += done
-        outs.append(self.cmm(sr1, done[-1]))                           # :265
-        return outs
+            outs, done = self._submit(psn_out, priors_b1, priors_b2, branch)
+            main = torch.cuda.current_stream(psn_out.device)
+            main.wait_event(done)                 # ordinary stream semantics for the caller: results are ready on `main`
+            for t in outs:
+                t.record_stream(main)
+            return outs
+        done1 = branch(0, self.b1, priors_b1)
+        done = branch(self.b1, self.b2, priors_b2)
+        return list(done1) + list(done) + [self.cmm(done1[-1], done[-1])]                  # :265
+
+    def _submit(self, psn_out, priors_b1, priors_b2, branch):
+        """The two cascades are independent until the CMM (super_resolution.py:174-240): they run on two side streams
+        (the tail of one branch's kernel overlaps the launch + prologue of the other's) and the CMM on a third, so a
+        caller that keeps several batches in flight (`submit`) also overlaps the CMM's small deep layers with the next
+        batch's PGRMs.  Workspaces are per stream (pgrm.workspace) and staged weights per module: nothing is shared."""
+        dev = psn_out.device
+        main = torch.cuda.current_stream(dev)
+        if self._streams is None or self._streams[0].device != dev:
+            self._streams = tuple(torch.cuda.Stream(dev) for _ in range(3))
+        s_cmm = self._streams[2]
+        start = torch.cuda.Event()
+        start.record(main)
+        results = []
+        for st, (first, count, priors) in zip(self._streams[:2], ((0, self.b1, priors_b1), (self.b1, self.b2, priors_b2))):
+            st.wait_event(start)
+            for t in [psn_out] + list(priors):
+                t.record_stream(st)
+            with torch.cuda.stream(st):
+                done = branch(first, count, priors)
+            for t in done:
+                t.record_stream(s_cmm)
+            end = torch.cuda.Event()
+            end.record(st)
+            s_cmm.wait_event(end)
+            results.append(done)
+        with torch.cuda.stream(s_cmm):
+            y = self.cmm(results[0][-1], results[1][-1])                                   # :265
+        finished = torch.cuda.Event()
+        finished.record(s_cmm)
+        return list(results[0]) + list(results[1]) + [y], finished
+
+    @torch.no_grad()
+    def submit(self, psn_out, priors_b1, priors_b2):
+        """Asynchronous inference: enqueue one batch without making the current stream wait for it.  Returns
+        (sr, done): `sr` (B,3,32,128) is valid once the CUDA event `done` has fired -- make the consuming stream
+        `wait_event(done)` (HostFeeder.fetch does).  Batches are processed in submission order."""
+        def branch(first, count, priors):
+            cascade = psn_out[:, :3, :]
+            done: List[torch.Tensor] = []
+            for j in range(count):
+                y = self.pgrm[first + j](priors[j], cascade, done[:j])
+                done.append(y)
+                cascade = y
+            return done
+        outs, finished = self._submit(psn_out, priors_b1, priors_b2, branch)
+        return outs[-1], finished
 
 
 class HostFeeder:
@@ -137,16 +164,21 @@ class HostFeeder:
         torch.cuda.current_stream(self.device).wait_event(self.ready[slot])
         return self._rebuild(structure, iter(self.slots[slot]))
 
-    def release(self, ticket):
-        """Call after the step that consumed the batch has been enqueued."""
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.device))
+    def release(self, ticket, after: torch.cuda.Event = None):
+        """Call after the step that consumed the batch has been enqueued (`after`: the event that marks its end)."""
+        ev = after
+        if ev is None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
         self.consumed[ticket[0]] = ev
 
-    def fetch(self, result: torch.Tensor, host_out: torch.Tensor):
-        """Read a result back into pinned host memory on the D2H stream."""
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.device))
+    def fetch(self, result: torch.Tensor, host_out: torch.Tensor, after: torch.cuda.Event = None):
+        """Read a result back into pinned host memory on the D2H stream, after the event `after` (default: everything
+        enqueued on the current stream so far)."""
+        ev = after
+        if ev is None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.d2h):
             self.d2h.wait_event(ev)
             result.record_stream(self.d2h)

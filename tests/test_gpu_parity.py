@@ -337,3 +337,32 @@ def test_window_attention_windowed_tcgen05_matches_simt(C, windows, shifted):
     vw = to_window_major(kv[..., C:].contiguous(), (H, W), windows, shifts)
     out = window_attention_windowed(qw, kw, vw, tabs, B, (H, W), heads, windows, shifts)
     assert rel_err(out.float().cpu().numpy(), ref.cpu().numpy()) < 2e-3
+
+
+@pytest.mark.gpu
+def test_hot_path_submit_pipelined_equals_sequential():
+    """DPMNHotPath.submit (three internal streams, several batches in flight) must give bit-identical results to the
+    plain sequential forward on the current stream, for every batch, in order."""
+    import bench
+    from dpmn_b200.pipeline import DPMNHotPath
+    dev = torch.device("cuda")
+    model = DPMNHotPath(precision="fp16")
+    pg, cm = bench.synth_weights(2)
+    bench.load_weights(model, pg, cm)
+    model = model.to(dev).eval()
+    batches = []
+    for s in range(4):
+        psn, p1, p2 = bench.synth_inputs(40 + s, 3)
+        batches.append((torch.from_numpy(psn).to(dev), [torch.from_numpy(a).to(dev) for a in p1],
+                        [torch.from_numpy(a).to(dev) for a in p2]))
+    with torch.no_grad():
+        model.concurrent_branches = False
+        ref = [model(*b).clone() for b in batches]
+        model.concurrent_branches = True
+        one = [model(*b).clone() for b in batches]
+        pend = [model.submit(*b) for b in batches]
+        for (y, ev), r in zip(pend, ref):
+            torch.cuda.current_stream().wait_event(ev)
+            assert torch.equal(y, r)
+    for a, r in zip(one, ref):
+        assert torch.equal(a, r)

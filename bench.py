@@ -183,8 +183,8 @@ def run_ours(args):
         host_sets.append(hs)
         dev_sets.append((hs[0].to(dev), [a.to(dev) for a in hs[1]], [a.to(dev) for a in hs[2]], hs[3].to(dev)))
     h2d_bytes = sum(t.numel() * 4 for t in [host_sets[0][0]] + host_sets[0][1] + host_sets[0][2] + ([host_sets[0][3]] if train else []))
-    out_host = (torch.empty((), dtype=torch.float32) if train else torch.empty((B, 3, 32, 128), dtype=torch.float32)).pin_memory()
-    d2h_bytes = out_host.numel() * 4
+    out_host = torch.empty((), dtype=torch.float32).pin_memory()      # training: the loss
+    d2h_bytes = 4 if train else B * 3 * 32 * 128 * 4
 
     def barrier():
         if world > 1:
@@ -208,56 +208,98 @@ def run_ours(args):
         # ---------- value: inputs resident in HBM
         for i in range(args.warmup):
             step_resident(i)
+        graphed = None
+        if not train:
+            from dpmn_b200.pipeline import GraphedHotPath
+            graphed = GraphedHotPath(model, B, dev, slots=2)      # capture once, outside the timed regions
+            for i in range(args.warmup):                          # warm replays
+                graphed.launch(i % 2)
         barrier()
         launches0 = lib.dpmn_launch_count()
         clocks = ClockSampler(local)
         if rank == 0:
             clocks.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        host_enqueue_ms = None
         e0.record()
         if train:
             for i in range(args.steps):
                 step_resident(i)
         else:
-            # throughput: batches are submitted back to back (DPMNHotPath.submit keeps them in flight on its own
-            # streams); the timed region ends when the LAST batch's result is complete on the timing stream
-            last = None
-            for i in range(args.steps):
-                _, last = model.submit(*dev_sets[i % n_sets][:3])
-            torch.cuda.current_stream(dev).wait_event(last)
+            # throughput: each batch = a device-to-device copy of its (HBM-resident) inputs into the slot's static
+            # buffers + one CUDA-graph replay; two slots are in flight, the timed region ends when the last is complete
+            def run_graphed_resident(n):
+                t_host = time.perf_counter()
+                begin = torch.cuda.Event()
+                begin.record(torch.cuda.current_stream(dev))
+                for i in range(n):
+                    slot = graphed.slots[i % 2]
+                    ds = dev_sets[i % n_sets]
+                    slot["stream"].wait_event(begin)
+                    with torch.cuda.stream(slot["stream"]):
+                        slot["psn"].copy_(ds[0], non_blocking=True)
+                        for d_, s_ in zip(slot["p1"] + slot["p2"], ds[1] + ds[2]):
+                            d_.copy_(s_, non_blocking=True)
+                    graphed.launch(i % 2)
+                ms = (time.perf_counter() - t_host) * 1e3 / n
+                for sl in graphed.slots:
+                    torch.cuda.current_stream(dev).wait_event(sl["done"])
+                return ms
+            host_enqueue_ms = run_graphed_resident(args.steps)
         e1.record()
         barrier()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
-        launches = lib.dpmn_launch_count() - launches0
+        launches = (lib.dpmn_launch_count() - launches0) if train else args.steps * graphed.kernels_per_replay
         clk = clocks.stop() if rank == 0 else None
         # ---------- e2e: pinned host buffers, H2D + D2H inside the timed region
         from dpmn_b200.pipeline import HostFeeder
         feeder = HostFeeder(dev)
+        h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        outs_host = [torch.empty((B, 3, 32, 128), dtype=torch.float32).pin_memory() for _ in range(2)]
 
         def run_e2e(n):
             """n steps from pinned host memory: H2D of step i+1 and D2H of step i-1 overlap the kernels of step i."""
-            def batch(i):
-                hs = host_sets[i % n_sets]
-                return [hs[0], hs[1], hs[2]] + ([hs[3]] if train else [])
-            ticket = feeder.stage(batch(0))
-            for i in range(n):
-                nxt = feeder.stage(batch(i + 1)) if i + 1 < n else None
-                ins = feeder.get(ticket)
-                if train:
-                    y = trainer.step(*ins)
+            if train:
+                def batch(i):
+                    hs = host_sets[i % n_sets]
+                    return [hs[0], hs[1], hs[2], hs[3]]
+                ticket = feeder.stage(batch(0))
+                for i in range(n):
+                    nxt = feeder.stage(batch(i + 1)) if i + 1 < n else None
+                    y = trainer.step(*feeder.get(ticket))
                     feeder.release(ticket)
                     feeder.fetch(y, out_host)
-                else:
-                    y, done = model.submit(*ins)
-                    feeder.release(ticket, after=done)
-                    feeder.fetch(y, out_host, after=done)
-                ticket = nxt
-            feeder.drain()
+                    ticket = nxt
+                feeder.drain()
+                return
+            fetched = [None, None]
+            for i in range(n):
+                k = i % 2
+                slot = graphed.slots[k]
+                hs = host_sets[i % n_sets]
+                with torch.cuda.stream(h2d):
+                    if slot["done"] is not None:
+                        h2d.wait_event(slot["done"])          # the previous replay of this slot has read its inputs
+                    slot["psn"].copy_(hs[0], non_blocking=True)
+                    for d_, s_ in zip(slot["p1"] + slot["p2"], hs[1] + hs[2]):
+                        d_.copy_(s_, non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(h2d)
+                if fetched[k] is not None:
+                    slot["stream"].wait_event(fetched[k])     # its previous output has been read back
+                done = graphed.launch(k, after=ready)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(done)
+                    outs_host[k].copy_(slot["out"], non_blocking=True)
+                    fetched[k] = torch.cuda.Event()
+                    fetched[k].record(d2h)
+            h2d.synchronize()
+            d2h.synchronize()
         run_e2e(min(args.warmup, 3))
         barrier()
         t0 = time.perf_counter()
         e0.record()
-        run_e2e(args.steps)          # ends with the last result in host memory (drain)
+        run_e2e(args.steps)          # ends with the last result in host memory
         e1.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
@@ -342,7 +384,7 @@ def run_ours(args):
                        f"dp{world}: one flat NCCL all-reduce over the 57.2M-parameter fp32 gradient bucket per step",
                        "l2": f"inputs rotate over {n_sets} sets; per-step working set (activations/workspace) >> 126 MB L2"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

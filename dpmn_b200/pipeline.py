@@ -64,8 +64,9 @@ class DPMNHotPath(nn.Module):
             outs, done = self._submit(psn_out, priors_b1, priors_b2, branch)
             main = torch.cuda.current_stream(psn_out.device)
             main.wait_event(done)                 # ordinary stream semantics for the caller: results are ready on `main`
-            for t in outs:
-                t.record_stream(main)
+            if not torch.cuda.is_current_stream_capturing():
+                for t in outs:
+                    t.record_stream(main)
             return outs
         done1 = branch(0, self.b1, priors_b1)
         done = branch(self.b1, self.b2, priors_b2)
@@ -86,12 +87,15 @@ class DPMNHotPath(nn.Module):
         results = []
         for st, (first, count, priors) in zip(self._streams[:2], ((0, self.b1, priors_b1), (self.b1, self.b2, priors_b2))):
             st.wait_event(start)
-            for t in [psn_out] + list(priors):
-                t.record_stream(st)
+            capturing = torch.cuda.is_current_stream_capturing()
+            if not capturing:
+                for t in [psn_out] + list(priors):
+                    t.record_stream(st)
             with torch.cuda.stream(st):
                 done = branch(first, count, priors)
-            for t in done:
-                t.record_stream(s_cmm)
+            if not capturing:
+                for t in done:
+                    t.record_stream(s_cmm)
             end = torch.cuda.Event()
             end.record(st)
             s_cmm.wait_event(end)
@@ -117,6 +121,71 @@ class DPMNHotPath(nn.Module):
             return done
         outs, finished = self._submit(psn_out, priors_b1, priors_b2, branch)
         return outs[-1], finished
+
+
+class GraphedHotPath:
+    """Inference through CUDA graphs: the ~170 kernel launches of one forward (three internal streams) are captured
+    once per slot and replayed with one cudaGraphLaunch, which takes the host out of the critical path (enqueueing
+    the launches from Python costs ~3.2 ms per batch, about as much as the GPU needs to run them).
+
+    Each of the `slots` graphs owns static input / output tensors and its own workspaces, and replays on its own
+    stream, so consecutive batches overlap on the GPU exactly as with `DPMNHotPath.submit`.  Usage per batch:
+    write the inputs of slot s (`inputs(s)`, e.g. by H2D copies), `launch(s, after=<event the inputs are ready>)`,
+    read `output(s)` once the returned event has fired; reuse slot s only after that.  Weights are baked in by
+    address: re-capture (`GraphedHotPath(model, ...)`) after loading new weights."""
+
+    def __init__(self, model: DPMNHotPath, batch: int, device: torch.device, slots: int = 2, img=(32, 128)):
+        from . import pgrm as _pgrm
+        self.model, self.device = model, device
+        H, W = img
+        self.slots = []
+        with torch.no_grad():
+            warm = (torch.zeros(batch, 4, H, W, device=device), [torch.zeros(batch, 2, H, W, device=device) for _ in range(model.b1)],
+                    [torch.zeros(batch, 3, H, W, device=device) for _ in range(model.b2)])
+            for _ in range(2):                      # stage the 16-bit weights, set kernel attributes, size workspaces
+                model(*warm)
+            torch.cuda.synchronize(device)
+            for _ in range(slots):
+                psn = torch.zeros(batch, 4, H, W, device=device)
+                p1 = [torch.zeros(batch, 2, H, W, device=device) for _ in range(model.b1)]
+                p2 = [torch.zeros(batch, 3, H, W, device=device) for _ in range(model.b2)]
+                stream = torch.cuda.Stream(device)
+                graph = torch.cuda.CUDAGraph()
+                saved = dict(_pgrm._WORKSPACES)
+                _pgrm._WORKSPACES.clear()           # this graph gets private workspaces (allocated in its own pool)
+                from . import _lib
+                n0 = _lib.load().dpmn_launch_count()
+                try:
+                    with torch.cuda.graph(graph, stream=stream):
+                        out = model(psn, p1, p2)
+                finally:
+                    self.kernels_per_replay = int(_lib.load().dpmn_launch_count() - n0)
+                    _pgrm._WORKSPACES.clear()
+                    _pgrm._WORKSPACES.update(saved)
+                self.slots.append({"psn": psn, "p1": p1, "p2": p2, "out": out, "graph": graph, "stream": stream,
+                                   "done": None})
+        torch.cuda.synchronize(device)
+
+    def inputs(self, slot: int):
+        s = self.slots[slot]
+        return s["psn"], s["p1"], s["p2"]
+
+    def output(self, slot: int) -> torch.Tensor:
+        return self.slots[slot]["out"]
+
+    def launch(self, slot: int, after: torch.cuda.Event = None) -> torch.cuda.Event:
+        s = self.slots[slot]
+        st = s["stream"]
+        if after is None:
+            after = torch.cuda.Event()
+            after.record(torch.cuda.current_stream(self.device))
+        st.wait_event(after)
+        with torch.cuda.stream(st):
+            s["graph"].replay()
+            done = torch.cuda.Event()
+            done.record(st)
+        s["done"] = done
+        return done
 
 
 class HostFeeder:

@@ -366,3 +366,45 @@ def test_hot_path_submit_pipelined_equals_sequential():
             assert torch.equal(y, r)
     for a, r in zip(one, ref):
         assert torch.equal(a, r)
+
+
+@pytest.mark.gpu
+def test_graphed_hot_path_equals_sequential():
+    """GraphedHotPath (CUDA-graph replay, two slots in flight) against the plain forward, bit for bit."""
+    import bench
+    from dpmn_b200.pipeline import DPMNHotPath, GraphedHotPath
+    dev = torch.device("cuda")
+    model = DPMNHotPath(precision="fp16")
+    pg, cm = bench.synth_weights(2)
+    bench.load_weights(model, pg, cm)
+    model = model.to(dev).eval()
+    B = 3
+    batches = []
+    for s in range(5):
+        psn, p1, p2 = bench.synth_inputs(60 + s, B)
+        batches.append((torch.from_numpy(psn).to(dev), [torch.from_numpy(a).to(dev) for a in p1],
+                        [torch.from_numpy(a).to(dev) for a in p2]))
+    with torch.no_grad():
+        ref = [model(*b).clone() for b in batches]
+    g = GraphedHotPath(model, B, dev, slots=2)
+    got = []
+    main = torch.cuda.current_stream()
+    for i, b in enumerate(batches):
+        slot = i % 2
+        if g.slots[slot]["done"] is not None:
+            main.wait_event(g.slots[slot]["done"])
+            got.append(g.output(slot).clone())
+        psn, p1, p2 = g.inputs(slot)
+        psn.copy_(b[0])
+        for d, s_ in zip(p1, b[1]):
+            d.copy_(s_)
+        for d, s_ in zip(p2, b[2]):
+            d.copy_(s_)
+        g.launch(slot)
+    for i in (len(batches) - 2, len(batches) - 1):
+        main.wait_event(g.slots[i % 2]["done"])
+        got.append(g.output(i % 2).clone())
+    torch.cuda.synchronize()
+    assert len(got) == len(ref)
+    for a, r in zip(got, ref):
+        assert torch.equal(a, r)

@@ -53,9 +53,12 @@ struct TcSmem {
   static constexpr int TOTAL = TcCfg<BN>::STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, typename OutT, bool LN>
-__global__ void __launch_bounds__(TC_THREADS, LN ? 1 : 2)
+// EW = epilogue warps (4, or 8: two warps per TMEM lane quarter take alternate CW-column chunks -- the epilogue, not the
+// MMA, bounds these K = 96..384 GEMMs, so more epilogue warps per SM hide more tcgen05.ld / store latency).
+template <int BN, typename OutT, bool LN, int EW = 4>
+__global__ void __launch_bounds__(64 + 32 * EW, LN ? 1 : 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmTcParams p) {
+  constexpr int CW = EW == 8 ? 16 : 32;         // columns per epilogue chunk (8 warps: fewer live registers per thread)
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -81,7 +84,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int i = 0; i < TSTAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EW); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -137,8 +140,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..2+EW-1) =================
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+    const int chunk_first = EW == 8 ? ((warp - 2) >> 2) * CW : 0;
+    constexpr int chunk_step = EW == 8 ? 2 * CW : CW;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % p.n_tiles;
@@ -157,10 +162,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int n0 = n_blk * BN + c0;
         // (1) issue every global load of this chunk first, unpredicated (columns clamped into range), so that the
         //     in-order issue of the warp does not serialise one L2/DRAM round trip per float4
-        float4 bb[8], rr[8];
+        float4 bb[CW / 4], rr[CW / 4];
         if (p.bias_mode == 1) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < CW / 4; ++j) {
             const int nc = min(n0 + 4 * j, p.N - 4);
             bb[j] = *reinterpret_cast<const float4*>(bias + nc);
           }
@@ -169,27 +174,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (p.residual != nullptr) {
           const long long off_ld = (long long)z * p.c_bs + (long long)m_ld * p.ldc;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < CW / 4; ++j) {
             const int nc = min(n0 + 4 * j, p.N - 4);
             rr[j] = *reinterpret_cast<const float4*>(p.residual + off_ld + nc);
           }
         }
         // (2) accumulator chunk
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        if constexpr (CW == 32) tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        else tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), r);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_m;
+        for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]) + bias_m;
         if (p.bias_mode == 1) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { v[4 * j] += bb[j].x; v[4 * j + 1] += bb[j].y; v[4 * j + 2] += bb[j].z; v[4 * j + 3] += bb[j].w; }
+          for (int j = 0; j < CW / 4; ++j) { v[4 * j] += bb[j].x; v[4 * j + 1] += bb[j].y; v[4 * j + 2] += bb[j].z; v[4 * j + 3] += bb[j].w; }
         }
         if (p.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+          for (int j = 0; j < CW; ++j) v[j] = gelu_fast(v[j]);
         }
-        if (p.colsum != nullptr) {
+        if constexpr (CW == 32) if (p.colsum != nullptr) {
           // butterfly transpose-reduce over the warp's 32 rows: lane l ends with the sum of column l
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = row_ok ? v[j] : 0.f;
@@ -218,7 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               OutT* dst = reinterpret_cast<OutT*>(p.sc_dst[which]) +
                           (((long long)g * (p.M / L) + b) * L + prow) * p.sc_cg + col;
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
+              for (int j = 0; j < CW; j += 8) {
                 union { uint4 u; OutT h[8]; } pk;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) pk.h[e] = from_f32<OutT>(v[j + e]);
@@ -230,24 +236,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (p.residual != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { v[4 * j] += rr[j].x; v[4 * j + 1] += rr[j].y; v[4 * j + 2] += rr[j].z; v[4 * j + 3] += rr[j].w; }
+          for (int j = 0; j < CW / 4; ++j) { v[4 * j] += rr[j].x; v[4 * j + 1] += rr[j].y; v[4 * j + 2] += rr[j].z; v[4 * j + 3] += rr[j].w; }
         }
         if constexpr (kCanLn) {
           if (p.ln_mode != 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) rowbuf[c0 + j] = v[j];   // static index: the chunk loop is fully unrolled
+            for (int j = 0; j < CW; ++j) rowbuf[c0 + j] = v[j];   // static index: the chunk loop is fully unrolled
           }
         }
         if (!row_ok) return;
         if constexpr (sizeof(OutT) == 4) {
           float* dst = reinterpret_cast<float*>(p.C) + off;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
+          for (int j = 0; j < CW; j += 4)
             if (n0 + j < p.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {
           OutT* dst = reinterpret_cast<OutT*>(p.C) + off;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
+          for (int j = 0; j < CW; j += 8) {
             if (n0 + j < p.N) {
               union { uint4 u; OutT h[8]; } pk;
 #pragma unroll
@@ -262,7 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int c0 = 0; c0 < BN; c0 += 32) do_chunk(c0);
       } else {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) do_chunk(c0);
+        for (int c0 = chunk_first; c0 < BN; c0 += chunk_step) do_chunk(c0);
       }
       // the accumulator stage is free as soon as its last chunk has been read
       tc_fence_before();
@@ -357,8 +363,12 @@ int make_tensor_map_16bit(CUtensorMap* map, const void* base, int rank, const ui
 
 static int g_num_sms = 0;
 
-template <int BN, typename OutT, bool LN>
+template <int BN, typename OutT, bool LN, int EW = 4>
 static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st) {
+  if constexpr (!LN && EW == 4 && BN % 32 == 0) {
+    static const int env_ew = getenv("DPMN_TC_EPI_WARPS") ? atoi(getenv("DPMN_TC_EPI_WARPS")) : 8;
+    if (env_ew == 8 && a.colsum == nullptr) return launch_tc_bn<BN, OutT, LN, 8>(a, st);
+  }
   CUtensorMap map_a, map_b;
   {
     const bool batched = a.batch > 1 && a.a_bs != 0;
@@ -400,14 +410,14 @@ static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st) {
   static const int env_per_sm = getenv("DPMN_TC_PER_SM") ? atoi(getenv("DPMN_TC_PER_SM")) : 2;
   const int per_sm = LN ? 1 : (env_per_sm >= 2 ? 2 : 1);
   const int grid = total < per_sm * g_num_sms ? total : per_sm * g_num_sms;
-  auto kern = gemm_tc_kernel<BN, OutT, LN>;
+  auto kern = gemm_tc_kernel<BN, OutT, LN, EW>;
   constexpr int smem = TcSmem<BN>::TOTAL;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
     DPMN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  kern<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, p);
+  kern<<<grid, 64 + 32 * EW, smem, st>>>(map_a, map_b, p);
   DPMN_LAUNCH_CHECK();
   return 0;
 }

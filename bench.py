@@ -211,9 +211,10 @@ def run_ours(args):
         graphed = None
         if not train:
             from dpmn_b200.pipeline import GraphedHotPath
-            graphed = GraphedHotPath(model, B, dev, slots=2)      # capture once, outside the timed regions
+            n_slots = int(os.environ.get("DPMN_BENCH_SLOTS", "2"))
+            graphed = GraphedHotPath(model, B, dev, slots=n_slots)      # capture once, outside the timed regions
             for i in range(args.warmup):                          # warm replays
-                graphed.launch(i % 2)
+                graphed.launch(i % n_slots)
         barrier()
         launches0 = lib.dpmn_launch_count()
         clocks = ClockSampler(local)
@@ -233,14 +234,14 @@ def run_ours(args):
                 begin = torch.cuda.Event()
                 begin.record(torch.cuda.current_stream(dev))
                 for i in range(n):
-                    slot = graphed.slots[i % 2]
+                    slot = graphed.slots[i % n_slots]
                     ds = dev_sets[i % n_sets]
                     slot["stream"].wait_event(begin)
                     with torch.cuda.stream(slot["stream"]):
                         slot["psn"].copy_(ds[0], non_blocking=True)
                         for d_, s_ in zip(slot["p1"] + slot["p2"], ds[1] + ds[2]):
                             d_.copy_(s_, non_blocking=True)
-                    graphed.launch(i % 2)
+                    graphed.launch(i % n_slots)
                 ms = (time.perf_counter() - t_host) * 1e3 / n
                 for sl in graphed.slots:
                     torch.cuda.current_stream(dev).wait_event(sl["done"])
@@ -255,7 +256,7 @@ def run_ours(args):
         from dpmn_b200.pipeline import HostFeeder
         feeder = HostFeeder(dev)
         h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        outs_host = [torch.empty((B, 3, 32, 128), dtype=torch.float32).pin_memory() for _ in range(2)]
+        outs_host = [torch.empty((B, 3, 32, 128), dtype=torch.float32).pin_memory() for _ in range(4)]
 
         def run_e2e(n):
             """n steps from pinned host memory: H2D of step i+1 and D2H of step i-1 overlap the kernels of step i."""
@@ -272,9 +273,9 @@ def run_ours(args):
                     ticket = nxt
                 feeder.drain()
                 return
-            fetched = [None, None]
+            fetched = [None] * n_slots
             for i in range(n):
-                k = i % 2
+                k = i % n_slots
                 slot = graphed.slots[k]
                 hs = host_sets[i % n_sets]
                 with torch.cuda.stream(h2d):

@@ -32,8 +32,10 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float u = fminf(x * x, 64.0f);
   float q = fmaf(1.0142650e-3f, u, -1.0677574e-1f);      // -log2e * (-0.00070303491, 0.07401130084)
   q = fmaf(q, u, -2.3011213f);                            // -log2e * 1.59501575816
-  const float e = exp2f(x * q);
-  return __fdividef(x, 1.0f + e);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * q));     // bare MUFU.EX2 (exp2f adds a denormal-range fix-up)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));  // e = +inf -> r = 0 -> x * 0: the x -> -inf limit
+  return x * r;
 }
 
 __device__ __forceinline__ float gelu_grad(float x) {

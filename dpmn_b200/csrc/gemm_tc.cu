@@ -163,11 +163,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // (1) issue every global load of this chunk first, unpredicated (columns clamped into range), so that the
         //     in-order issue of the warp does not serialise one L2/DRAM round trip per float4
         float4 bb[CW / 4], rr[CW / 4];
+        const bool full = n0 + CW <= p.N;                 // whole chunk inside the matrix: no clamps / predicates
         if (p.bias_mode == 1) {
+          if (full) {
 #pragma unroll
-          for (int j = 0; j < CW / 4; ++j) {
-            const int nc = min(n0 + 4 * j, p.N - 4);
-            bb[j] = *reinterpret_cast<const float4*>(bias + nc);
+            for (int j = 0; j < CW / 4; ++j) bb[j] = *reinterpret_cast<const float4*>(bias + n0 + 4 * j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW / 4; ++j) {
+              const int nc = min(n0 + 4 * j, p.N - 4);
+              bb[j] = *reinterpret_cast<const float4*>(bias + nc);
+            }
           }
         }
         const long long off = (long long)z * p.c_bs + (long long)m * p.ldc + n0;
@@ -185,8 +191,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         else tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0), r);
         tmem_ld_wait();
         float v[32];
+        if (p.bias_mode == 2) {
 #pragma unroll
-        for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]) + bias_m;
+          for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]) + bias_m;
+        } else {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+        }
         if (p.bias_mode == 1) {
 #pragma unroll
           for (int j = 0; j < CW / 4; ++j) { v[4 * j] += bb[j].x; v[4 * j + 1] += bb[j].y; v[4 * j + 2] += bb[j].z; v[4 * j + 3] += bb[j].w; }
@@ -249,12 +260,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           float* dst = reinterpret_cast<float*>(p.C) + off;
 #pragma unroll
           for (int j = 0; j < CW; j += 4)
-            if (n0 + j < p.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (full || n0 + j < p.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {
           OutT* dst = reinterpret_cast<OutT*>(p.C) + off;
 #pragma unroll
           for (int j = 0; j < CW; j += 8) {
-            if (n0 + j < p.N) {
+            if (full || n0 + j < p.N) {
               union { uint4 u; OutT h[8]; } pk;
 #pragma unroll
               for (int e = 0; e < 8; ++e) pk.h[e] = from_f32<OutT>(v[j + e]);

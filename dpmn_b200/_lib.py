@@ -43,7 +43,9 @@ class PgrmDesc(C.Structure):
                 ("head0_w", fp), ("head0_b", fp), ("head1_w", fp), ("head1_b", fp),
                 ("mix_weight", fp * MAX_MIX), ("mix_input", fp * MAX_MIX),
                 ("mix_input_batch_stride", C.c_int64 * MAX_MIX),
-                ("prepared", fp), ("prepared_valid", C.c_int32), ("reserved_", C.c_int32)]
+                ("prepared", fp), ("prepared_valid", C.c_int32), ("reserved_", C.c_int32),
+                ("drop_rate", C.c_float), ("attn_drop_rate", C.c_float), ("drop_path_rate", C.c_float * MAX_BLOCKS),
+                ("seed", C.c_uint64)]
 
 
 class BlockGrads(C.Structure):       # dpmn_block_grads: same fields as dpmn_block_weights
@@ -128,6 +130,7 @@ SYMBOLS = {
     "dpmn_cmm_debug_copy": (C.c_int, [C.POINTER(CmmDesc), _vp, _i32, _vp, _sz, _vp]),
     "dpmn_gemm_nt": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
     "dpmn_gemm_nt_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "dpmn_mask_hash": (C.c_uint32, [C.c_uint64, C.c_uint32, C.c_uint64]),
     "dpmn_pgrm_backward_workspace_bytes": (_sz, [C.POINTER(PgrmDesc)]),
     "dpmn_pgrm_backward": (C.c_int, [C.POINTER(PgrmDesc), _vp, _vp, _vp, C.POINTER(PgrmGrads), _vp, _sz, _vp]),
     "dpmn_cmm_backward_workspace_bytes": (_sz, [C.POINTER(CmmDesc)]),

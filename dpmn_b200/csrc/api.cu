@@ -752,6 +752,12 @@ int cmm_forward_tc(const dpmn_cmm_desc* d, const float* x1, const float* x2, flo
   return 0;
 }
 
+// defined in api_bwd.inc (same unnamed namespace): the fp32 training sequence with Dropout / DropPath
+int pgrm_stochastic_forward(const dpmn_pgrm_desc* d, const float* x_q, const float* x_kv, float* out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+bool pgrm_is_stochastic(const dpmn_pgrm_desc* d);
+size_t pgrm_bwd_workspace(const dpmn_pgrm_desc* d);
+
 }  // namespace
 
 extern "C" {
@@ -808,7 +814,9 @@ size_t dpmn_abi_sizeof(int32_t which) {
 
 size_t dpmn_pgrm_workspace_bytes(const dpmn_pgrm_desc* d) {
   if (check_pgrm(d)) return 0;
-  return carve_pgrm(d, nullptr).bytes;
+  const size_t n = carve_pgrm(d, nullptr).bytes;
+  if (pgrm_is_stochastic(d)) { const size_t t = pgrm_bwd_workspace(d); return t > n ? t : n; }
+  return n;
 }
 
 size_t dpmn_pgrm_prepared_bytes(const dpmn_pgrm_desc* d) {
@@ -818,6 +826,7 @@ size_t dpmn_pgrm_prepared_bytes(const dpmn_pgrm_desc* d) {
 
 int dpmn_pgrm_forward(const dpmn_pgrm_desc* d, const float* x_q, const float* x_kv, float* out, void* workspace,
                       size_t workspace_bytes, void* stream) {
+  if (d && pgrm_is_stochastic(d)) return pgrm_stochastic_forward(d, x_q, x_kv, out, workspace, workspace_bytes, stream);
   return pgrm_forward_impl(d, x_q, x_kv, out, workspace, workspace_bytes, stream, nullptr, nullptr);
 }
 

@@ -169,6 +169,37 @@ int launch_add(const float* a, const float* b, float* y, long long n, cudaStream
   return 0;
 }
 
+__global__ void dropout_kernel(float* __restrict__ x, long long n, float p, unsigned long long seed, uint32_t site) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= drop_scale(p, seed, site, (unsigned long long)i);
+}
+
+int launch_dropout(float* x, long long n, float p, unsigned long long seed, uint32_t site, cudaStream_t st) {
+  if (p <= 0.f) return 0;
+  dropout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, p, seed, site);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void branch_combine_kernel(float* __restrict__ dst, const float* __restrict__ base, const float* __restrict__ y,
+                                      long long n, long long per_image, float p_drop, uint32_t site_drop, float p_path,
+                                      uint32_t site_path, unsigned long long seed) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float f = drop_scale(p_drop, seed, site_drop, (unsigned long long)i) *
+                  drop_scale(p_path, seed, site_path, (unsigned long long)(i / per_image));
+  const float v = y[i] * f;
+  dst[i] = base != nullptr ? base[i] + v : v;
+}
+
+int launch_branch_combine(float* dst, const float* base, const float* y, long long n, long long per_image, float p_drop,
+                          uint32_t site_drop, float p_path, uint32_t site_path, unsigned long long seed, cudaStream_t st) {
+  branch_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, base, y, n, per_image, p_drop, site_drop, p_path,
+                                                                    site_path, seed);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
 // =====================================================================================================
 // LayerNorm backward (eps 1e-5, nn.LayerNorm over the last dim).  One warp per row, C <= 256.
 //   xhat = (x - mean) * rstd;  g = dy * w;  dx (+)= rstd * (g - mean(g) - xhat * mean(g * xhat))

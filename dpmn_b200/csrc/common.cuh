@@ -76,6 +76,26 @@ template <> __device__ __forceinline__ float from_f32<float>(float v) { return v
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// Counter-based Bernoulli masks of the train-mode Dropout / DropPath sites (pgrm.py:24,32,40,180,248,310,494,554-555).
+// The reference draws them from torch's Philox stream, which cannot be reproduced outside torch ("parity
+// unpinned"); here every mask element is a pure function of (seed, site, element index) -- splitmix64 finaliser -- so
+// the backward regenerates exactly the masks of the forward and a test can rebuild them in numpy.
+__host__ __device__ __forceinline__ uint32_t dpmn_hash32(unsigned long long seed, uint32_t site, unsigned long long idx) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (idx + 1ULL) + 0xD1B54A32D192ED03ULL * (unsigned long long)(site + 1u);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+// multiplier of element idx: 1/(1-p) if kept, 0 if dropped (1 when p == 0)
+__device__ __forceinline__ float drop_scale(float p, unsigned long long seed, uint32_t site, unsigned long long idx) {
+  if (p <= 0.f) return 1.0f;
+  const float u = (float)(dpmn_hash32(seed, site, idx) >> 8) * (1.0f / 16777216.0f);
+  return u >= p ? 1.0f / (1.0f - p) : 0.0f;
+}
+enum DropSite : uint32_t { SITE_POS_Q = 1, SITE_POS_KV = 2, SITE_BLOCK = 16,   // + 16*blk:
+                           SITE_ATTN = 0, SITE_MLP1 = 1, SITE_MLP2 = 2, SITE_PATH1 = 3, SITE_PATH2 = 4 };
+
 // Window-major row p of group (ws, shift) -> original token index (pgrm.py:209-221 roll + partition).
 // p = w*N + n, w = wr*(W/ws) + wc, n = i*ws + j; rolled coords (h', w') = (wr*ws+i, wc*ws+j) read
 // original ((h'+shift) % H, (w'+shift) % W).

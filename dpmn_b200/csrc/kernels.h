@@ -79,6 +79,7 @@ struct AttnArgs {
   const float* table[4] = {nullptr, nullptr, nullptr, nullptr};   // ((2*win-1)^2, heads_per_group) each
   int B = 0, H = 0, W = 0, C = 0, n_groups = 0, heads_per_group = 0;
   int window[4] = {0, 0, 0, 0}, shift[4] = {0, 0, 0, 0};   // EFFECTIVE windows / shifts
+  float p_drop = 0.f; unsigned long long seed = 0; uint32_t site = 0;   // attn_drop on P (train mode), pgrm.py:248
 };
 int launch_window_attn_simt(const AttnArgs& a, cudaStream_t st);
 
@@ -158,6 +159,7 @@ struct AttnBwdArgs {
   const float* table[4] = {}; float* d_table[4] = {};      // accumulated
   int B = 0, H = 0, W = 0, C = 0, n_groups = 0, heads_per_group = 0;
   int window[4] = {}, shift[4] = {};
+  float p_drop = 0.f; unsigned long long seed = 0; uint32_t site = 0;   // the forward's attn_drop masks
 };
 int launch_window_attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
 
@@ -179,10 +181,19 @@ struct SkBwdArgs {
 };
 int launch_sk_bwd(const SkBwdArgs& s, cudaStream_t st);
 
+// p_drop / seed / site: the Mlp's Dropout after GELU(fc1) (pgrm.py:31-32), applied to the conv INPUT on load
 int launch_dwconv_train_fwd(const float* h1pre, float* dtpre, float* dt, const float* w, const float* b, int B, int L,
-                            int hid, cudaStream_t st);
+                            int hid, float p_drop, unsigned long long seed, uint32_t site, cudaStream_t st);
 int launch_dwconv_bwd(const float* d_dt, const float* dtpre, const float* h1pre, const float* w, float* d_h1pre,
-                      float* dw, float* db, int B, int L, int hid, cudaStream_t st);
+                      float* dw, float* db, int B, int L, int hid, float p_drop, unsigned long long seed, uint32_t site,
+                      cudaStream_t st);
+// x[i] *= drop_scale(p, seed, site, i)                                  (pos_drop, pgrm.py:554-555, and its backward)
+int launch_dropout(float* x, long long n, float p, unsigned long long seed, uint32_t site, cudaStream_t st);
+// dst[i] = (base ? base[i] : 0) + y[i] * drop_scale(p_drop, site_drop, i) * drop_scale(p_path, site_path, i / per_image)
+// -- a residual branch with its Dropout and per-sample DropPath (pgrm.py:40,329-330); with base == nullptr it is the
+// backward of the branch (gradient of y from the gradient of the sum).
+int launch_branch_combine(float* dst, const float* base, const float* y, long long n, long long per_image, float p_drop,
+                          uint32_t site_drop, float p_path, uint32_t site_path, unsigned long long seed, cudaStream_t st);
 
 int launch_patch_embed_bwd(const float* x, long long x_bs, int in_ch, const float* fuse_w, const float* fuse_b,
                            const float* pe_w, const float* pe_b, const float* ln_w, const float* d_tok, float* d_pe_w,

@@ -21,7 +21,8 @@ constexpr int AB_ROWS = 64;
 __global__ void __launch_bounds__(128) window_attn_bwd_kernel(
     const float* __restrict__ q, const float* __restrict__ kv, const float* __restrict__ d_attn,
     float* __restrict__ dq, float* __restrict__ dkv, const float* __restrict__ table, float* __restrict__ d_table,
-    int C, int hpg, int ch0, int D, int H, int W, int ws, int shift, float scale) {
+    int C, int hpg, int ch0, int D, int H, int W, int ws, int shift, float scale, float p_drop, unsigned long long seed,
+    uint32_t site, int g_index, int G) {
   extern __shared__ float sm[];
   const int N = ws * ws, NS = N + 1, L = H * W, DS = D + 1, tw = 2 * ws - 1, TT = tw * tw;
   float* sQ = sm;                       // [64][DS]
@@ -69,6 +70,9 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(
     }
     s = s * scale + sTab[(n / ws - m / ws + ws - 1) * tw + (n % ws - m % ws + ws - 1)];
     if (sLab[r] != sLab[kr]) s += -100.0f;
+    // forward with attn_drop: O = (P o M) V with M in {0, 1/(1-p)}  ->  dP = (dO V^T) o M
+    if (p_drop > 0.f)
+      dp *= drop_scale(p_drop, seed, site, ((((unsigned long long)b * G + g_index) * hpg + head) * L + row0 + r) * N + m);
     sP[r * NS + m] = s;
     sS[r * NS + m] = dp;
   }
@@ -98,7 +102,10 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(
     for (int m = 0; m < N; ++m) {
       aq = fmaf(sS[r * NS + m], sK[(w0 + m) * DS + e], aq);            // dQ[r] = sum_m dS[r,m] K[m]
       ak = fmaf(sS[(w0 + m) * NS + nr], sQ[(w0 + m) * DS + e], ak);    // dK[r] = sum_n dS[n,r] Q[n]
-      av = fmaf(sP[(w0 + m) * NS + nr], sO[(w0 + m) * DS + e], av);    // dV[r] = sum_n P[n,r] dO[n]
+      float pm = sP[(w0 + m) * NS + nr];                               // dV[r] = sum_n (P o M)[n,r] dO[n]
+      if (p_drop > 0.f)
+        pm *= drop_scale(p_drop, seed, site, ((((unsigned long long)b * G + g_index) * hpg + head) * L + row0 + w0 + m) * N + nr);
+      av = fmaf(pm, sO[(w0 + m) * DS + e], av);
     }
     const long long tok = (long long)b * L + sTok[r];
     dq[tok * C + ch + e] = aq * scale;
@@ -127,7 +134,7 @@ int launch_window_attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
     dim3 grid(L / AB_ROWS, a.heads_per_group, a.B);
     window_attn_bwd_kernel<<<grid, 128, smem, st>>>(a.q, a.kv, a.d_attn, a.dq, a.dkv, a.table[g], a.d_table[g], a.C,
                                                     a.heads_per_group, g * cg, D, a.H, a.W, ws, a.shift[g],
-                                                    1.0f / sqrtf((float)D));
+                                                    1.0f / sqrtf((float)D), a.p_drop, a.seed, a.site, g, a.n_groups);
     DPMN_LAUNCH_CHECK();
   }
   return 0;
@@ -315,7 +322,8 @@ constexpr int DWT_ROWS = 8;
 
 __global__ void __launch_bounds__(256) dwconv_train_fwd_kernel(const float* __restrict__ h1pre, float* __restrict__ dtpre,
                                                                float* __restrict__ dt, const float* __restrict__ w,
-                                                               const float* __restrict__ bias, int L, int hid, int side) {
+                                                               const float* __restrict__ bias, int L, int hid, int side,
+                                                               float p_drop, unsigned long long seed, uint32_t site) {
   extern __shared__ float sm[];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, y0 = blockIdx.x * DWT_ROWS;
   const int rows_in = DWT_ROWS + 2;
@@ -326,7 +334,10 @@ __global__ void __launch_bounds__(256) dwconv_train_fwd_kernel(const float* __re
     const int r = i - c * rows_in * side;
     const int yy = y0 - 1 + r / side, xx = r % side;
     float v = 0.f;
-    if (yy >= 0 && yy < side) v = gelu_erf(hb[(long long)(c0 + c) * L + yy * side + xx]);
+    if (yy >= 0 && yy < side) {
+      const long long o = (long long)(c0 + c) * L + yy * side + xx;
+      v = gelu_erf(hb[o]) * drop_scale(p_drop, seed, site, (unsigned long long)b * L * hid + o);   // pgrm.py:31-32
+    }
     sm[c * cstride + r] = v;
   }
   __syncthreads();
@@ -355,14 +366,15 @@ __global__ void __launch_bounds__(256) dwconv_train_fwd_kernel(const float* __re
 }
 
 int launch_dwconv_train_fwd(const float* h1pre, float* dtpre, float* dt, const float* w, const float* b, int B, int L,
-                            int hid, cudaStream_t st) {
+                            int hid, float p_drop, unsigned long long seed, uint32_t site, cudaStream_t st) {
   const int side = (int)(sqrtf((float)L) + 0.5f);
   if (side * side != L || hid % 32 || side % DWT_ROWS) return -2;
   const size_t smem = (size_t)32 * ((DWT_ROWS + 2) * side + 1) * sizeof(float);
   if (smem > 200 * 1024) return -2;
   if (smem > 48 * 1024)
     DPMN_CUDA_TRY(cudaFuncSetAttribute(dwconv_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dwconv_train_fwd_kernel<<<dim3(side / DWT_ROWS, hid / 32, B), 256, smem, st>>>(h1pre, dtpre, dt, w, b, L, hid, side);
+  dwconv_train_fwd_kernel<<<dim3(side / DWT_ROWS, hid / 32, B), 256, smem, st>>>(h1pre, dtpre, dt, w, b, L, hid, side,
+                                                                                p_drop, seed, site);
   DPMN_LAUNCH_CHECK();
   return 0;
 }
@@ -372,7 +384,8 @@ int launch_dwconv_train_fwd(const float* h1pre, float* dtpre, float* dt, const f
 __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict__ d_dt, const float* __restrict__ dtpre,
                                                          const float* __restrict__ h1pre, const float* __restrict__ w,
                                                          float* __restrict__ d_h1pre, float* __restrict__ dw,
-                                                         float* __restrict__ db, int L, int hid, int side) {
+                                                         float* __restrict__ db, int L, int hid, int side, float p_drop,
+                                                         unsigned long long seed, uint32_t site) {
   extern __shared__ float sm[];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, y0 = blockIdx.x * DWT_ROWS;
   const int rows_in = DWT_ROWS + 2;
@@ -396,7 +409,10 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict
     const int r = i - c * rows_in * side;
     const int yy = y0 - 1 + r / side, xx = r % side;
     float v = 0.f;
-    if (yy >= 0 && yy < side) v = gelu_erf(hb[(long long)(c0 + c) * L + yy * side + xx]);
+    if (yy >= 0 && yy < side) {
+      const long long o = (long long)(c0 + c) * L + yy * side + xx;
+      v = gelu_erf(hb[o]) * drop_scale(p_drop, seed, site, (unsigned long long)b * L * hid + o);
+    }
     sH[c * cstride + r] = v;
   }
   __syncthreads();
@@ -416,7 +432,7 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict
         if (xs >= 0 && xs < side) acc = fmaf(g[(yl + 2 - ky) * side + xs], wk[ky * 3 + kx], acc);
       }
     const long long o = (long long)b * L * hid + (long long)(c0 + c) * L + (y0 + yl) * side + xx;
-    d_h1pre[o] = acc * gelu_grad(h1pre[o]);
+    d_h1pre[o] = acc * gelu_grad(h1pre[o]) * drop_scale(p_drop, seed, site, (unsigned long long)o);
   }
   // weight / bias gradient: warp w owns channels 4w .. 4w+3, lanes split the 8 x side positions
   for (int cc = 0; cc < 4; ++cc) {
@@ -449,7 +465,8 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict
 }
 
 int launch_dwconv_bwd(const float* d_dt, const float* dtpre, const float* h1pre, const float* w, float* d_h1pre,
-                      float* dw, float* db, int B, int L, int hid, cudaStream_t st) {
+                      float* dw, float* db, int B, int L, int hid, float p_drop, unsigned long long seed, uint32_t site,
+                      cudaStream_t st) {
   const int side = (int)(sqrtf((float)L) + 0.5f);
   if (side * side != L || hid % 32 || side % DWT_ROWS) return -2;
   const size_t smem = (size_t)2 * 32 * ((DWT_ROWS + 2) * side + 1) * sizeof(float);
@@ -457,7 +474,7 @@ int launch_dwconv_bwd(const float* d_dt, const float* dtpre, const float* h1pre,
   if (smem > 48 * 1024)
     DPMN_CUDA_TRY(cudaFuncSetAttribute(dwconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dwconv_bwd_kernel<<<dim3(side / DWT_ROWS, hid / 32, B), 256, smem, st>>>(d_dt, dtpre, h1pre, w, d_h1pre, dw, db, L, hid,
-                                                                          side);
+                                                                          side, p_drop, seed, site);
   DPMN_LAUNCH_CHECK();
   return 0;
 }

@@ -476,7 +476,8 @@ template <typename T, int D>
 __global__ void window_attn_simt_kernel(const T* __restrict__ q, const T* __restrict__ kv, T* __restrict__ out,
                                         int q_ld, int kv_ld, int v_off, int out_ld,
                                         const float* __restrict__ table, int hpg, int ch0, int H, int W, int ws,
-                                        int shift, float scale) {
+                                        int shift, float scale, float p_drop, unsigned long long seed, uint32_t site,
+                                        int g_index, int G) {
   extern __shared__ __align__(16) float sm[];
   const int N = ws * ws;
   const int L = H * W;
@@ -544,8 +545,11 @@ __global__ void window_attn_simt_kernel(const T* __restrict__ q, const T* __rest
     if (lab[m] != my_lab) s += -100.0f;      // pgrm.py:173
     const float nmx = fmaxf(mx, s);
     const float corr = expf(mx - nmx);       // 0 on the first key (mx = -inf)
-    const float pexp = expf(s - nmx);
+    float pexp = expf(s - nmx);
     den = den * corr + pexp;
+    // attn_drop (pgrm.py:248, train mode): the normalised probability of key m is kept with 1/(1-p) or zeroed
+    if (p_drop > 0.f)
+      pexp *= drop_scale(p_drop, seed, site, ((((unsigned long long)b * G + g_index) * hpg + head) * L + p) * N + m);
     const float4* v4 = reinterpret_cast<const float4*>(vbase + m * D);
 #pragma unroll
     for (int e = 0; e < D / 4; ++e) {
@@ -578,7 +582,7 @@ static int launch_attn_group(const AttnArgs& a, int g, cudaStream_t st) {
   dim3 grid(L / Tn, a.heads_per_group, a.B);
   kern<<<grid, Tn, smem, st>>>((const T*)a.q, (const T*)a.kv, (T*)a.out, a.q_ld, a.kv_ld, a.v_off, a.out_ld,
                                a.table[g], a.heads_per_group, g * cg, a.H, a.W, ws, a.shift[g],
-                               1.0f / sqrtf((float)D));
+                               1.0f / sqrtf((float)D), a.p_drop, a.seed, a.site, g, a.n_groups);
   DPMN_LAUNCH_CHECK();
   return 0;
 }

@@ -132,9 +132,10 @@ class _PGRMFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x_q, x_kv, n_res, *rest):
         residuals = list(rest[:n_res])
+        seed = module._new_seed() if module._stochastic() else None    # train-mode Dropout / DropPath masks
         with torch.no_grad():
-            out = module._run(x_q, x_kv, residuals, probe=False)
-        ctx.module, ctx.n_res = module, n_res
+            out = module._run(x_q, x_kv, residuals, probe=False, seed=seed)
+        ctx.module, ctx.n_res, ctx.seed = module, n_res, seed
         ctx.save_for_backward(x_q, x_kv, *residuals)
         return out
 
@@ -144,7 +145,7 @@ class _PGRMFunction(torch.autograd.Function):
         m = ctx.module
         need_xkv = ctx.needs_input_grad[2]
         need_res = [ctx.needs_input_grad[4 + i] for i in range(ctx.n_res)]
-        d_xkv, d_res, d_params = m._backward(x_q, x_kv, residuals, d_out, need_xkv, need_res)
+        d_xkv, d_res, d_params = m._backward(x_q, x_kv, residuals, d_out, need_xkv, need_res, seed=ctx.seed)
         return (None, None, d_xkv, None, *d_res, *d_params)
 
 
@@ -199,9 +200,21 @@ class PGRM(ParamTree):
                                f"(got {t.device}, {t.dtype}); there is no CPU path")
         return t.data_ptr()
 
-    def _descriptor(self, B: int, q_chans: int, n_mix: int) -> _lib.PgrmDesc:
+    def _stochastic(self) -> bool:
+        """train() with a non-zero Dropout / DropPath rate: the forward then draws masks (fp32 training sequence)."""
+        return self.training and (self.drop_rate > 0 or self.attn_drop_rate > 0 or max(self.drop_path) > 0)
+
+    @staticmethod
+    def _new_seed() -> int:
+        return int(torch.randint(0, 2 ** 62, (1,)).item())     # torch's CPU generator: torch.manual_seed reproduces it
+
+    def _descriptor(self, B: int, q_chans: int, n_mix: int, seed=None) -> _lib.PgrmDesc:
         cfg = self.cfg
         d = _lib.PgrmDesc()
+        if seed is not None:    # pgrm.py:24,180,310,494 -- masks are a function of (seed, site, index), see the header
+            d.drop_rate, d.attn_drop_rate, d.seed = self.drop_rate, self.attn_drop_rate, seed
+            for b, r in enumerate(self.drop_path[:_lib.MAX_BLOCKS]):
+                d.drop_path_rate[b] = r
         d.batch, d.img_h, d.img_w, d.patch = B, cfg.img_size[0], cfg.img_size[1], cfg.patch_size
         d.q_chans, d.embed_dim, d.num_heads, d.n_groups = q_chans, cfg.embed_dim, cfg.num_heads, cfg.groups
         for g, ws in enumerate(cfg.window_size):
@@ -242,12 +255,6 @@ class PGRM(ParamTree):
         t = t.contiguous()
         return t, c * h * w
 
-    def _check_mode(self):
-        if self.training and (self.drop_rate > 0 or self.attn_drop_rate > 0 or max(self.drop_path) > 0):
-            raise NotImplementedError(
-                "dpmn_b200.PGRM: train-mode Dropout/DropPath (pgrm.py:248,310) are not part of this build; "
-                "call .eval() or construct with all drop rates 0 (forward and backward are then exact)")
-
     def forward(self, x_q: torch.Tensor, x_kv: torch.Tensor, residual_list: Sequence[torch.Tensor]):
         residual_list = list(residual_list)
         params = [p for _, p in self.named_parameters()]
@@ -256,9 +263,9 @@ class PGRM(ParamTree):
             return _PGRMFunction.apply(self, x_q, x_kv, len(residual_list), *residual_list, *params)
         return self._run(x_q, x_kv, residual_list, probe=False)
 
-    def _backward(self, x_q, x_kv, residuals, d_out, need_xkv=True, need_res=None):
-        """d_out (B, hs, H, W) -> (d x_kv | None, [d residual_i | None], [d param | None in named_parameters order])."""
-        self._check_mode()
+    def _backward(self, x_q, x_kv, residuals, d_out, need_xkv=True, need_res=None, seed=None):
+        """d_out (B, hs, H, W) -> (d x_kv | None, [d residual_i | None], [d param | None in named_parameters order]).
+        `seed`: the seed of the forward's Dropout / DropPath masks (None = none were drawn)."""
         lib = _lib.load()
         cfg = self.cfg
         B = x_q.shape[0]
@@ -266,7 +273,7 @@ class PGRM(ParamTree):
         need_res = list(need_res) if need_res is not None else [True] * len(residuals)
         x_q, q_bs = self._image_arg(x_q, "x_q")
         x_kv, kv_bs = self._image_arg(x_kv, "x_kv")
-        d = self._descriptor(B, x_q.shape[1], n_mix)
+        d = self._descriptor(B, x_q.shape[1], n_mix, seed=seed)
         d.x_q_batch_stride, d.x_kv_batch_stride = q_bs, kv_bs
         keep = []
         for i in range(1, n_mix):
@@ -332,8 +339,9 @@ class PGRM(ParamTree):
         """forward + the per-block tensors the parity tests compare: (out, attn_core[2], block_out[2])."""
         return self._run(x_q, x_kv, residual_list, probe=True)
 
-    def _run(self, x_q, x_kv, residual_list, probe: bool):
-        self._check_mode()
+    def _run(self, x_q, x_kv, residual_list, probe: bool, seed=None):
+        if seed is None and self._stochastic():
+            seed = self._new_seed()             # train-mode forward outside autograd (torch.no_grad())
         lib = _lib.load()
         cfg = self.cfg
         if x_q.dim() != 4 or x_kv.dim() != 4 or x_q.shape[0] != x_kv.shape[0]:
@@ -347,7 +355,7 @@ class PGRM(ParamTree):
             raise AttributeError(f"PGRM(iter={self.iter}) has no weight_list_{n_mix - 1} (pgrm.py:564)")
         x_q, q_bs = self._image_arg(x_q, "x_q")
         x_kv, kv_bs = self._image_arg(x_kv, "x_kv")
-        d = self._descriptor(B, x_q.shape[1], n_mix)
+        d = self._descriptor(B, x_q.shape[1], n_mix, seed=seed)
         d.x_q_batch_stride, d.x_kv_batch_stride = q_bs, kv_bs
         keep = []
         for i in range(1, n_mix):   # residual_list[0] is skipped by the reference (pgrm.py:563)

@@ -104,6 +104,15 @@ typedef struct dpmn_pgrm_desc {
   void *prepared;
   int32_t prepared_valid;
   int32_t reserved_;
+  /* Train-mode stochastic regularisers (module.train(), pgrm.py:24,32,40 Mlp Dropout; :180,248 attn_drop; :310,329-330
+   * DropPath; :494,554-555 pos_drop).  All rates 0 (the default) = eval semantics.  With a non-zero rate the forward
+   * runs the fp32 training sequence whatever `precision` says and needs dpmn_pgrm_backward_workspace_bytes() of
+   * workspace; dpmn_pgrm_backward given the same rates and seed regenerates the same masks.  Masks are a pure function
+   * of (seed, site, element index) -- NOT torch's Philox stream (the reference's stream cannot be reproduced). */
+  float drop_rate;                           /* drop_rate[iter]: pos_drop and both Mlp dropouts */
+  float attn_drop_rate;                      /* attn_drop_rate[iter] */
+  float drop_path_rate[DPMN_MAX_BLOCKS];     /* dpr slice of this PGRM (pgrm.py:499,512) */
+  uint64_t seed;                             /* fresh per training forward */
 } dpmn_pgrm_desc;
 
 /* ---- Complementation Modulation Module (cmm.py:80-161) ------------------------------------------- */
@@ -256,6 +265,13 @@ typedef struct dpmn_pgrm_grads {
   float *x_kv;                           /* d x_kv (B, 3, img_h, img_w) or NULL */
   float *mix_input[DPMN_MAX_MIX];        /* d residual_list[i] (B, hs, img_h, img_w) or NULL; [0] is never touched */
 } dpmn_pgrm_grads;
+
+/* The hash behind the train-mode masks (host function, no GPU needed): element `idx` of site `site` is kept iff
+ * (dpmn_mask_hash(seed, site, idx) >> 8) * 2^-24 >= rate, and then scaled by 1/(1-rate).  Sites: 1 pos_drop(x_q tokens),
+ * 2 pos_drop(x_kv tokens), 16*(block+1) + {0 attn_drop, 1 Mlp drop after GELU, 2 Mlp drop after fc2, 3 DropPath of the
+ * attention branch, 4 DropPath of the Mlp branch}.  Indices: flat (B,L,C) / (B,L,hidden) element index; DropPath: image
+ * index; attn_drop: ((((b*G + g)*heads_per_group + head)*L + window_major_row)*N + key). */
+uint32_t dpmn_mask_hash(uint64_t seed, uint32_t site, uint64_t idx);
 
 size_t dpmn_pgrm_backward_workspace_bytes(const dpmn_pgrm_desc *d);
 int dpmn_pgrm_backward(const dpmn_pgrm_desc *d, const float *x_q, const float *x_kv, const float *d_out,

@@ -17,6 +17,42 @@ import torch
 import torch.nn.functional as F
 
 
+# ---- train-mode Dropout / DropPath masks: numpy restatement of dpmn_mask_hash (include/dpmn_b200.h) -----------------
+# The reference draws its masks from torch's RNG stream (not reproducible outside torch); the CUDA path derives them
+# from (seed, site, index).  This oracle applies the SAME masks at the reference's Dropout / DropPath sites
+# (pgrm.py:32,40,248,329-330,554-555), so train-mode forward and backward can be checked exactly.
+SITE_POS_Q, SITE_POS_KV, SITE_BLOCK = 1, 2, 16
+SITE_ATTN, SITE_MLP1, SITE_MLP2, SITE_PATH1, SITE_PATH2 = 0, 1, 2, 3, 4
+
+
+def mask_hash(seed: int, site: int, idx):
+    import numpy as np
+    M = np.uint64
+    idx = np.asarray(idx, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = M(seed) + M(0x9E3779B97F4A7C15) * (idx + M(1)) + M(0xD1B54A32D192ED03) * M(site + 1)
+        z = (z ^ (z >> M(30))) * M(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> M(27))) * M(0x94D049BB133111EB)
+        z = z ^ (z >> M(31))
+    return (z >> M(32)).astype(np.uint32)
+
+
+def drop_scale(p: float, seed: int, site: int, idx) -> torch.Tensor:
+    """multiplier per element: 1/(1-p) if kept, 0 if dropped (all ones for p == 0), fp32 like the kernels."""
+    import numpy as np
+    idx = np.asarray(idx, dtype=np.uint64)
+    if p <= 0:
+        return torch.ones(idx.shape, dtype=torch.float32)
+    u = (mask_hash(seed, site, idx) >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    keep = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    return torch.from_numpy(np.where(u >= np.float32(p), keep, np.float32(0.0)).astype(np.float32))
+
+
+def _flat_idx(shape):
+    import numpy as np
+    return np.arange(int(np.prod(shape)), dtype=np.uint64).reshape(shape)
+
+
 def _order(H, W, ws, shift):
     """window-major row -> original token (pgrm.py:209-221,43-52)."""
     p = torch.arange(H * W)
@@ -40,8 +76,8 @@ def _shift_mask(H, W, ws, shift):
     return torch.where(lab[:, None, :] != lab[:, :, None], -100.0, 0.0)
 
 
-def window_attention_core(q, kv, tables, windows, shifts, H, W, hpg):
-    """pgrm.py:197-268 -> (B, L, C) in window-major row order per group (quirk 1)."""
+def window_attention_core(q, kv, tables, windows, shifts, H, W, hpg, drop=None, site=0):
+    """pgrm.py:197-268 -> (B, L, C) in window-major row order per group (quirk 1).  drop = (p, seed): attn_drop masks."""
     B, L, C = q.shape
     G = len(windows)
     cg = C // G
@@ -61,7 +97,14 @@ def window_attention_core(q, kv, tables, windows, shifts, H, W, hpg):
         s = s + bias[None, None]
         if sh > 0:
             s = s + _shift_mask(H, W, ws, sh)[None, :, None]
-        o = torch.softmax(s, dim=-1) @ part(v_all)
+        prob = torch.softmax(s, dim=-1)
+        if drop is not None and drop[0] > 0:                      # attn_drop, pgrm.py:248
+            import numpy as np
+            b_i, w_i, h_i, n_i, m_i = np.meshgrid(np.arange(B), np.arange(nW), np.arange(hpg), np.arange(N), np.arange(N),
+                                                  indexing="ij")
+            idx = ((((b_i * G + g) * hpg + h_i) * L + w_i * N + n_i) * N + m_i).astype(np.uint64)
+            prob = prob * drop_scale(drop[0], drop[1], site, idx)
+        o = prob @ part(v_all)
         outs.append(o.permute(0, 1, 3, 2, 4).reshape(B, L, cg))
     return torch.cat(outs, dim=-1)
 
@@ -78,20 +121,26 @@ def _sk(x, P, pre, G):
     return f + F.linear(v, P[pre + "proj_head.weight"], P[pre + "proj_head.bias"])
 
 
-def _mlp(x, P, pre):
-    """Mlp.forward, pgrm.py:29-41, raw views kept (quirk 2)."""
+def _mlp(x, P, pre, drop=None, site=0):
+    """Mlp.forward, pgrm.py:29-41, raw views kept (quirk 2).  drop = (p, seed): the two Dropout sites."""
     B, L, _ = x.shape
     side = int(math.sqrt(L))
     h = F.gelu(F.linear(x, P[pre + "fc1.weight"], P[pre + "fc1.bias"]))
+    if drop is not None and drop[0] > 0:
+        h = h * drop_scale(drop[0], drop[1], site + SITE_MLP1, _flat_idx(h.shape))
     hid = h.shape[-1]
     h = h.reshape(B, hid, side, side)
     h = F.gelu(F.conv2d(h, P[pre + "depthwise_conv.weight"], P[pre + "depthwise_conv.bias"], padding=1, groups=hid))
     h = F.conv2d(h, P[pre + "pointwise_conv.weight"], P[pre + "pointwise_conv.bias"])
-    return F.linear(h.reshape(B, L, hid), P[pre + "fc2.weight"], P[pre + "fc2.bias"])
+    y = F.linear(h.reshape(B, L, hid), P[pre + "fc2.weight"], P[pre + "fc2.bias"])
+    if drop is not None and drop[0] > 0:
+        y = y * drop_scale(drop[0], drop[1], site + SITE_MLP2, _flat_idx(y.shape))
+    return y
 
 
-def _block(tq, tkv, P, pre, blk, windows, H, W, hpg):
-    """SwinTransformerBlock.forward, pgrm.py:315-331 (eval)."""
+def _block(tq, tkv, P, pre, blk, windows, H, W, hpg, drop=None):
+    """SwinTransformerBlock.forward, pgrm.py:315-331.  drop = dict(seed, drop_rate, attn_drop_rate, drop_path=[..])
+    applies the train-mode masks; None = eval."""
     C = tq.shape[-1]
     G = len(windows)
     mn = min(H, W)
@@ -102,14 +151,26 @@ def _block(tq, tkv, P, pre, blk, windows, H, W, hpg):
     q = F.linear(qn, P[pre + "attn.q.weight"], P[pre + "attn.q.bias"])
     kv = F.linear(kvn, P[pre + "attn.kv.weight"], P[pre + "attn.kv.bias"])
     tables = [P[pre + f"attn.relative_position_bias_table_{g}"] for g in range(G)]
-    a = window_attention_core(q, kv, tables, wins, shifts, H, W, hpg)
-    y = tkv + _sk(a, P, pre + "attn.sknet.", G)
-    return y + _mlp(F.layer_norm(y, (C,), P[pre + "norm2.weight"], P[pre + "norm2.bias"]), P, pre + "mlp.")
+    if drop is None:
+        a = window_attention_core(q, kv, tables, wins, shifts, H, W, hpg)
+        y = tkv + _sk(a, P, pre + "attn.sknet.", G)
+        return y + _mlp(F.layer_norm(y, (C,), P[pre + "norm2.weight"], P[pre + "norm2.bias"]), P, pre + "mlp.")
+    import numpy as np
+    site, seed, B = SITE_BLOCK * (blk + 1), drop["seed"], tq.shape[0]
+    a = window_attention_core(q, kv, tables, wins, shifts, H, W, hpg, drop=(drop["attn_drop_rate"], seed), site=site + SITE_ATTN)
+    path = drop["drop_path"][blk]
+    dp1 = drop_scale(path, seed, site + SITE_PATH1, np.arange(B)).view(B, 1, 1)
+    dp2 = drop_scale(path, seed, site + SITE_PATH2, np.arange(B)).view(B, 1, 1)
+    y = tkv + dp1 * _sk(a, P, pre + "attn.sknet.", G)                                     # pgrm.py:329
+    m = _mlp(F.layer_norm(y, (C,), P[pre + "norm2.weight"], P[pre + "norm2.bias"]), P, pre + "mlp.",
+             drop=(drop["drop_rate"], seed), site=site)
+    return y + dp2 * m                                                                   # pgrm.py:330
 
 
 def pgrm_forward(P: Dict[str, torch.Tensor], x_q, x_kv, residual_list: Sequence[torch.Tensor], *,
-                 windows=(2, 4, 8), num_heads=6, patch=2):
-    """PGRM.forward, pgrm.py:546-565 (eval mode)."""
+                 windows=(2, 4, 8), num_heads=6, patch=2, drop=None):
+    """PGRM.forward, pgrm.py:546-565.  drop=None: eval mode; drop=dict(seed, drop_rate, attn_drop_rate, drop_path):
+    train mode with the CUDA path's masks."""
     if x_q.shape[1] == 2:
         x_q = F.conv2d(x_q, P["prior_fusion.weight"], P["prior_fusion.bias"], padding=1)
     C = P["patch_embed.proj.weight"].shape[0]
@@ -119,9 +180,12 @@ def pgrm_forward(P: Dict[str, torch.Tensor], x_q, x_kv, residual_list: Sequence[
         return F.layer_norm(y.flatten(2).transpose(1, 2), (C,), P["patch_embed.norm.weight"], P["patch_embed.norm.bias"])
     H, W = x_kv.shape[2] // patch, x_kv.shape[3] // patch
     tq, tkv = embed(x_q), embed(x_kv)
+    if drop is not None and drop["drop_rate"] > 0:                                        # pos_drop, pgrm.py:554-555
+        tq = tq * drop_scale(drop["drop_rate"], drop["seed"], SITE_POS_Q, _flat_idx(tq.shape))
+        tkv = tkv * drop_scale(drop["drop_rate"], drop["seed"], SITE_POS_KV, _flat_idx(tkv.shape))
     G = len(windows)
     for blk in range(2):
-        tkv = _block(tq, tkv, P, f"layers.0.blocks.{blk}.", blk, windows, H, W, num_heads // G)
+        tkv = _block(tq, tkv, P, f"layers.0.blocks.{blk}.", blk, windows, H, W, num_heads // G, drop=drop)
     B = tkv.shape[0]
     x = tkv.transpose(1, 2).reshape(B, C, H, W)
     x = F.conv2d(x, P["conv_before_upsample.0.weight"], P["conv_before_upsample.0.bias"], padding=1)

@@ -160,3 +160,66 @@ def test_hot_path_training_step_gradients_vs_oracle():
         assert float((a - b).norm() / b.norm()) < 3e-2, n
         checked += 1
     assert checked > 300
+
+
+@pytest.mark.parametrize("name,rates", [("pgrm_i2_m0_grad", (0.1, 0.1, 0.1)), ("pgrm_i3_m1_grad", (0.2, 0.0, 0.3)),
+                                        ("pgrm_i5_m1_grad", (0.0, 0.15, 0.0))])
+def test_pgrm_train_mode_dropout_droppath_forward_and_backward(name, rates):
+    """module.train() with non-zero drop_rate / attn_drop_rate / drop_path_rate (pgrm.py:32,40,248,
+    329-330,554-555).  The reference's RNG stream cannot be reproduced, so the oracle (oracle/torch_ref.py) applies
+    the masks the CUDA path derives from (seed, site, index) -- restated in numpy -- at the reference's own Dropout /
+    DropPath sites; forward and every gradient must then agree like the eval-mode fixtures do."""
+    from oracle import torch_ref
+    z, meta = load_golden(name)
+    cfg, P, x_q, x_kv, res = pgrm_case(meta)
+    it = meta["iter"]
+    n = it + 1
+    from dpmn_b200 import PGRM
+    drop, attn, path = rates
+    m = PGRM(patch_size=[2] * n, embed_dim=[96] * n, depths=[1] * n, num_heads=[[6]] * n, window_size=[[2, 4, 8]] * n,
+             mlp_ratio=[4.] * n, drop_rate=[drop] * n, attn_drop_rate=[attn] * n, drop_path_rate=[path] * n, iter=it,
+             mode=meta["mode"], hidden_size=3, precision="fp32")
+    sd = m.state_dict()
+    m.load_state_dict({k: (torch.from_numpy(P[k]) if k in P else v) for k, v in sd.items()}, strict=True)
+    dev = torch.device("cuda")
+    m = m.to(dev).train()
+    seed = 123456789 + it
+    m._new_seed = lambda: seed
+    xq = torch.from_numpy(x_q).to(dev)
+    xkv = torch.from_numpy(x_kv).to(dev).requires_grad_(True)
+    rs = [torch.from_numpy(r).to(dev).requires_grad_(True) for r in res]
+    G = torch.from_numpy(grad_seed_out(meta["seed"], meta["B"]))
+    y = m(xq, xkv, rs)
+    (y * G.to(dev)).sum().backward()
+    # oracle with the same masks
+    cfg_drop = dict(seed=seed, drop_rate=drop, attn_drop_rate=attn, drop_path=list(m.drop_path))
+    Pt = {k: torch.from_numpy(v).requires_grad_(True) for k, v in P.items()}
+    oxkv = torch.from_numpy(x_kv).requires_grad_(True)
+    ors = [torch.from_numpy(r).requires_grad_(True) for r in res]
+    oy = torch_ref.pgrm_forward(Pt, torch.from_numpy(x_q), oxkv, ors, windows=cfg.window_size, num_heads=cfg.num_heads,
+                                drop=cfg_drop)
+    (oy * G).sum().backward()
+    assert rel_err(y.detach().cpu().numpy(), oy.detach().numpy()) < 2e-5
+    # the masks really are active: the eval-mode output differs
+    assert rel_err(y.detach().cpu().numpy(), z["out"]) > 1e-3
+    assert rel_err(xkv.grad.cpu().numpy(), oxkv.grad.numpy()) < TOL
+    bad = []
+    for k, p in m.named_parameters():
+        ref = Pt[k].grad
+        if ref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        e = rel_err(p.grad.cpu().numpy(), ref.numpy())
+        if not e < TOL:
+            bad.append((e, k))
+    assert not bad, sorted(bad, reverse=True)[:10]
+    for a, b in zip(rs[1:], ors[1:]):
+        assert rel_err(a.grad.cpu().numpy(), b.grad.numpy()) < TOL
+    # a second forward draws different masks (fresh seed); the same seed reproduces the output bit for bit
+    m._new_seed = lambda: seed + 1
+    with torch.no_grad():
+        y2 = m(xq, xkv.detach(), [r.detach() for r in rs])
+        m._new_seed = lambda: seed
+        y3 = m(xq, xkv.detach(), [r.detach() for r in rs])
+    assert not torch.equal(y2, y.detach())
+    assert torch.equal(y3, y.detach())

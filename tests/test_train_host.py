@@ -21,3 +21,21 @@ def test_image_loss_matches_reference_definition():
     assert np.allclose(gradient_map(a).numpy(), gmap(a), atol=1e-6)
     want = ((a.numpy().astype(np.float64) - b.numpy()) ** 2).mean() + np.abs(gmap(a) - gmap(b)).mean()
     assert abs(float(image_loss(a, b)) - want) < 1e-6
+
+
+def test_numpy_mask_hash_matches_the_library():
+    """oracle/torch_ref.mask_hash restates dpmn_mask_hash (the host-callable hash behind the train-mode Dropout /
+    DropPath masks); no GPU needed."""
+    from dpmn_b200 import _lib
+    from oracle.torch_ref import mask_hash
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        seed = int(rng.integers(0, 2 ** 62))
+        site = int(rng.integers(0, 64))
+        idx = int(rng.integers(0, 2 ** 40))
+        assert int(mask_hash(seed, site, np.array([idx]))[0]) == lib.dpmn_mask_hash(seed, site, idx)
+    # keep fraction of a Bernoulli(0.1) drop
+    h = mask_hash(7, 17, np.arange(200000))
+    u = (h >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    assert abs(float((u >= 0.1).mean()) - 0.9) < 5e-3

@@ -159,8 +159,9 @@ def run_ours(args):
 
     train = args.mode == "train"
     if train:
-        # configs[2]: PGRM forward in the chosen precision; CMM forward fp32 (train-mode BatchNorm); backward fp32
-        model = DPMNHotPath(precision=args.precision, drop=0.0, cmm_precision="fp32")
+        # configs[2]: the three drop rates at the reference's 0.1 (README.md:42) -> every PGRM forward is the fp32
+        # training sequence with Dropout / DropPath masks; CMM forward fp32 (train-mode BatchNorm); backward fp32
+        model = DPMNHotPath(precision=args.precision, drop=args.train_drop, cmm_precision="fp32")
     else:
         model = DPMNHotPath(precision=args.precision)
     pg, cm = synth_weights(2)
@@ -372,7 +373,7 @@ def run_ours(args):
         cpu = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
 
     workload = WORKLOAD if not train else (
-        "DPMN hot path TRAINING step: 6xPGRM cascade + CMM forward (PGRM " + args.precision + ", CMM fp32 train-mode BN), 7 image "
+        "DPMN hot path TRAINING step: 6xPGRM cascade (drop / attn_drop / drop_path " + str(args.train_drop) + ") + CMM forward (train-mode BN), 7 image "
         "losses, backward through dpmn_pgrm_backward / dpmn_cmm_backward (fp32), flat gradient all-reduce, per-module "
         "clip 0.25, Adam; 16x64 -> 32x128, batch 48/GPU, synthetic PSN output / priors / HR (configs[2] without the "
         "frozen TATT backbone, recognisers and distill modules)")
@@ -401,6 +402,7 @@ def main():
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer = BASELINE configs[1] (the headline line); train = configs[2] training step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-drop", type=float, default=0.1, help="drop / attn_drop / drop_path rate of --mode train")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -19,8 +19,8 @@ def build_pgrm_stack(precision: str = "fp32", stu_iter_b1: int = 3, stu_iter_b2:
                      drop: float = 0.1) -> List[PGRM]:
     """generator_init (interfaces/base.py:150-155) for k = 0..5: branch 1 gets the 2-channel rendered-text
     prior (mode=False), branch 2 the 3-channel mask prior (mode=True); hidden_size = 3.  `drop` is the value of
-    --drop_rate / --attn_drop_rate / --drop_path_rate (README.md:42: 0.1); the stochastic train-mode paths are
-    not implemented, so a stack that is to be put in train() must be built with drop=0."""
+    --drop_rate / --attn_drop_rate / --drop_path_rate (README.md:42: 0.1).  In train() with non-zero rates every PGRM
+    forward runs the fp32 training sequence with Dropout / DropPath masks (see include/dpmn_b200.h); eval() ignores them."""
     n = stu_iter_b1 + stu_iter_b2
     mods = []
     for k in range(n):

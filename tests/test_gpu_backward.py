@@ -141,7 +141,7 @@ def test_hot_path_training_step_gradients_vs_oracle():
     o_outs.append(torch_ref.cmm_forward(cmt, o_outs[2], o_outs[5], training=True))
     o_loss = tr.loss(o_outs, torch.from_numpy(hr))
     o_loss.backward()
-    assert abs(float(loss) - float(o_loss)) < 1e-4 * abs(float(o_loss))
+    assert abs(float(loss.detach()) - float(o_loss.detach())) < 1e-4 * abs(float(o_loss.detach()))
     checked = 0
     for k, m in enumerate(model.pgrm):
         for n, p in m.named_parameters():

@@ -314,6 +314,8 @@ def run_ours(args):
                 step_resident(i)
             torch.cuda.synchronize()
         if rank == 0:
+            if not train:
+                model.concurrent_branches = False     # one stream: per-launch event times are not inflated by overlap
             lib.dpmn_profile_enable(1)
             for i in range(n_prof):
                 step_resident(i)
@@ -359,8 +361,11 @@ def run_ours(args):
     if train:
         tensor_peak = 75.0   # B200 fp32 FFMA peak (148 SMs x 128 lanes x 2 x 1.965 GHz): the backward is fp32 SIMT this round
         peak_src = "nominal fp32 FFMA peak (the backward kernels are fp32 SIMT, not tensor-core, this round)"
+    # DRAM bytes per launch of the dominant class from the committed `ncu --set full` capture (mean over its launches in
+    # profiles/r01_ncu_full_fp16_v14.txt: dram__bytes_read.sum + dram__bytes_write.sum; writes mostly stay in the 126 MB L2)
+    traffic = {"gemm_tc": 13.3e6, "conv_tc": None}.get(dom) if not train else None
     roofline = {"bound": "tensor" if not train else "fp32-simt", "kernel": dom, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": achieved / tensor_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / tensor_peak, "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": dom_ms / total_prof_ms,
                 "launches_per_step": prof[dom]["launches_per_step"],
                 "avg_launch_ms": dom_ms / max(1, prof[dom]["launches_per_step"]),

@@ -137,12 +137,152 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(ConvArgs p, const 
   }
 }
 
+// Weight gradient of a stride-2 transposed conv, parity-class form (see conv_simt_t2_kernel): class (py, px) pairs the
+// output pixels of that parity with the taps that are valid for it, so no product multiplies a structural zero.
+// blockIdx.z = class * nsplit + pixel chunk.
+__global__ void __launch_bounds__(256) conv_wgrad_simt_t2_kernel(ConvArgs p, const float* __restrict__ dy,
+                                                                 float* __restrict__ dw, int nsplit) {
+  __shared__ __align__(16) float As[WK][WPAD];
+  __shared__ __align__(16) float Bs[WK][WPAD];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * WM, k0 = blockIdx.x * WN;
+  const int cls = blockIdx.z / nsplit, chunk_id = blockIdx.z - cls * nsplit;
+  const int py = cls >> 1, px = cls & 1;
+  int kys[4], kxs[4], nky = 0, nkx = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (t < p.k && (((py + p.pad + t * p.dil) & 1) == 0)) kys[nky++] = t;
+    if (t < p.k && (((px + p.pad + t * p.dil) & 1) == 0)) kxs[nkx++] = t;
+  }
+  const int nt = nky * nkx;
+  const int kk = p.k * p.k;
+  const int K = p.Cin * nt;
+  if (k0 >= K) return;
+  const int Hq = p.Ho >> 1, Wq = p.Wo >> 1, HqWq = Hq * Wq, HoWo = p.Ho * p.Wo;
+  const long long Ntot = (long long)p.B * HqWq;
+  const long long HW = (long long)p.H * p.W;
+  const long long chunk = ((Ntot + nsplit - 1) / nsplit + WK - 1) / WK * WK;
+  const long long nbeg = (long long)chunk_id * chunk;
+  const long long nend = nbeg + chunk < Ntot ? nbeg + chunk : Ntot;
+
+  const int gk = k0 + (tid & 63), gp0 = tid >> 6;
+  const bool k_ok = gk < K;
+  int ky = 0, kx = 0, seg = 0, cl = 0;
+  if (k_ok) {
+    const int ci = gk / nt, r = gk - ci * nt;
+    const int a = r / nkx;
+    ky = kys[a]; kx = kxs[r - a * nkx];
+    cl = ci;
+    if (p.n_seg > 1 && cl >= p.seg_ch[0]) {
+      cl -= p.seg_ch[0]; seg = 1;
+      if (p.n_seg > 2 && cl >= p.seg_ch[1]) { cl -= p.seg_ch[1]; seg = 2; }
+    }
+  }
+  const float* src = p.in[seg];
+  const int segC = p.seg_ch[seg];
+  const bool has_aff = p.in_scale[seg] != nullptr;
+  const float sc = (k_ok && has_aff) ? p.in_scale[seg][cl] : 1.f;
+  const float sh = (k_ok && has_aff) ? p.in_shift[seg][cl] : 0.f;
+  const int ap = tid & 15, am0 = tid >> 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (long long n0 = nbeg; n0 < nend; n0 += WK) {
+    float av[4], bv[4];
+    {
+      const long long n = n0 + ap;
+      long long o = 0;
+      if (n < nend) {
+        const int b = (int)(n / HqWq);
+        const int r = (int)(n - (long long)b * HqWq);
+        const int qy = r / Wq, qx = r - qy * Wq;
+        o = (long long)b * p.Cout * HoWo + (long long)(2 * qy + py) * p.Wo + 2 * qx + px;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int co = m0 + am0 + 16 * i;
+        av[i] = (n < nend && co < p.Cout) ? dy[o + (long long)co * HoWo] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long n = n0 + gp0 + 4 * i;
+      float v = 0.f;
+      if (k_ok && n < nend) {
+        const int b = (int)(n / HqWq);
+        const int r = (int)(n - (long long)b * HqWq);
+        const int qy = r / Wq, qx = r - qy * Wq;
+        const int ty2 = 2 * qy + py + p.pad - ky * p.dil, tx2 = 2 * qx + px + p.pad - kx * p.dil;
+        const int iy = ty2 >> 1, ix = tx2 >> 1;
+        if (ty2 >= 0 && tx2 >= 0 && iy < p.H && ix < p.W) {
+          v = src[((long long)b * segC + cl) * HW + (long long)iy * p.W + ix];
+          v = fmaf(v, sc, sh);
+          if (p.in_act == 1) v = v >= 0.f ? v : 0.2f * v;
+          else if (p.in_act == 2) v = fmaxf(v, 0.f);
+        }
+      }
+      bv[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[ap][am0 + 16 * i] = av[i];
+      Bs[gp0 + 4 * i][tid & 63] = bv[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < WK; ++q) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[q][tx * 4]);
+      const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float br[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = m0 + ty * 4 + i;
+    if (co >= p.Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k >= K) continue;
+      const int c2 = k / nt, r = k - c2 * nt;
+      const int a = r / nkx;
+      atomicAdd(dw + ((long long)c2 * p.Cout + co) * kk + kys[a] * p.k + kxs[r - a * nkx], acc[i][j]);
+    }
+  }
+}
+
 // `a` describes the FORWARD conv (inputs / affines / activation / geometry); dy is d(raw conv output) (B, Cout, Ho, Wo).
 int launch_conv_wgrad_simt(const ConvArgs& a, const float* dy, float* dw, cudaStream_t st) {
   if (a.n_seg < 1 || a.n_seg > 3) return -1;
   int cin = 0;
   for (int i = 0; i < a.n_seg; ++i) cin += a.seg_ch[i];
   if (cin != a.Cin) return -1;
+  if (a.transposed && a.stride == 2 && a.k <= 4 && a.Ho % 2 == 0 && a.Wo % 2 == 0) {
+    // parity-class form: per class at most Cin * ceil(k/2)^2 (dil 1) or Cin * k^2 (dil 2, one live class) taps
+    const int ntmax = a.dil % 2 == 0 ? a.k * a.k : ((a.k + 1) / 2) * ((a.k + 1) / 2);
+    const int Kc = a.Cin * ntmax;
+    const long long Nc = (long long)a.B * (a.Ho / 2) * (a.Wo / 2);
+    const int tiles_c = ((Kc + WN - 1) / WN) * ((a.Cout + WM - 1) / WM);
+    long long nsp = 1184 / (4 * tiles_c);
+    if (nsp > Nc / 64) nsp = Nc / 64;
+    if (nsp < 1) nsp = 1;
+    if (nsp > 128) nsp = 128;
+    dim3 g2((Kc + WN - 1) / WN, (a.Cout + WM - 1) / WM, (unsigned)(4 * nsp));
+    conv_wgrad_simt_t2_kernel<<<g2, 256, 0, st>>>(a, dy, dw, (int)nsp);
+    DPMN_LAUNCH_CHECK();
+    return 0;
+  }
   const int K = a.Cin * a.k * a.k;
   const long long Ntot = (long long)a.B * a.Ho * a.Wo;
   const int tiles = ((K + WN - 1) / WN) * ((a.Cout + WM - 1) / WM);

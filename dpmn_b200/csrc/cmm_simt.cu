@@ -133,12 +133,139 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs p) {
   }
 }
 
+// Transposed conv with stride 2 (convT 4x4 s2 of the decoder, and the data gradients of the stride-2 encoder convs):
+// in the gather form above 3 of 4 taps of every output pixel hit a non-integer input position and multiply zeros.  Here
+// the output is split into its 4 parity classes (blockIdx.z); a class only enumerates the taps that are valid for it:
+//   (oy + pad - ky*dil) even  <=>  ((py + pad + ky*dil) & 1) == 0          K_eff = Cin * nky * nkx  (a quarter for dil 1;
+// for dil 2 one class carries all taps and the other three are bias-only), N = B * Ho/2 * Wo/2 pixels per class.
+__global__ void __launch_bounds__(256) conv_simt_t2_kernel(ConvArgs p) {
+  __shared__ __align__(16) float As[CK][CPAD];
+  __shared__ __align__(16) float Bs[CK][CPAD];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * CM, n0 = blockIdx.x * CN;
+  const int py = blockIdx.z >> 1, px = blockIdx.z & 1;
+  int kys[4], kxs[4], nky = 0, nkx = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (t < p.k && (((py + p.pad + t * p.dil) & 1) == 0)) kys[nky++] = t;
+    if (t < p.k && (((px + p.pad + t * p.dil) & 1) == 0)) kxs[nkx++] = t;
+  }
+  const int nt = nky * nkx;
+  const int kk = p.k * p.k;
+  const int K = p.Cin * nt;
+  const int Hq = p.Ho >> 1, Wq = p.Wo >> 1;
+  const int HqWq = Hq * Wq;
+  const int HoWo = p.Ho * p.Wo;
+  const long long Ntot = (long long)p.B * HqWq;
+  const long long HW = (long long)p.H * p.W;
+
+  const int bn = tid & 63, bk0 = tid >> 6;
+  const long long npix = (long long)n0 + bn;
+  const bool n_ok = npix < Ntot;
+  int pb = 0, oy = 0, ox = 0;
+  if (n_ok) {
+    pb = (int)(npix / HqWq);
+    const int r = (int)(npix - (long long)pb * HqWq);
+    const int qy = r / Wq;
+    oy = 2 * qy + py;
+    ox = 2 * (r - qy * Wq) + px;
+  }
+  const int ak = tid & 15, am0 = tid >> 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += CK) {
+    float av[4], bv[4];
+    {
+      const int k = k0 + ak;
+      int wofs = 0;
+      if (k < K) {
+        const int ci = k / nt, r = k - ci * nt;
+        const int a = r / nkx, b2 = r - a * nkx;
+        wofs = ci * p.Cout * kk + kys[a] * p.k + kxs[b2];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int co = m0 + am0 + 16 * i;
+        av[i] = (k < K && co < p.Cout) ? p.w[(long long)wofs + (long long)co * kk] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + bk0 + 4 * i;
+      float v = 0.f;
+      if (n_ok && k < K) {
+        const int ci = k / nt, r = k - ci * nt;
+        const int a = r / nkx, b2 = r - a * nkx;
+        const int ty2 = oy + p.pad - kys[a] * p.dil, tx2 = ox + p.pad - kxs[b2] * p.dil;   // even by construction
+        const int iy = ty2 >> 1, ix = tx2 >> 1;
+        if (ty2 >= 0 && tx2 >= 0 && iy < p.H && ix < p.W) {
+          int seg = 0, cl = ci;
+          if (p.n_seg > 1 && cl >= p.seg_ch[0]) {
+            cl -= p.seg_ch[0]; seg = 1;
+            if (p.n_seg > 2 && cl >= p.seg_ch[1]) { cl -= p.seg_ch[1]; seg = 2; }
+          }
+          v = p.in[seg][((long long)pb * p.seg_ch[seg] + cl) * HW + (long long)iy * p.W + ix];
+          if (p.in_scale[seg] != nullptr) v = fmaf(v, p.in_scale[seg][cl], p.in_shift[seg][cl]);
+          if (p.in_act == 1) v = v >= 0.f ? v : 0.2f * v;
+          else if (p.in_act == 2) v = fmaxf(v, 0.f);
+        }
+      }
+      bv[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[ak][am0 + 16 * i] = av[i];
+      Bs[bk0 + 4 * i][bn] = bv[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float br[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = m0 + ty * 4 + i;
+    if (co >= p.Cout) continue;
+    const float bb = p.bias ? p.bias[co] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long n = (long long)n0 + tx * 4 + j;
+      if (n >= Ntot) continue;
+      const int b = (int)(n / HqWq);
+      const int r = (int)(n - (long long)b * HqWq);
+      const int qy = r / Wq, qx = r - qy * Wq;
+      p.out[((long long)b * p.Cout + co) * HoWo + (long long)(2 * qy + py) * p.Wo + 2 * qx + px] = acc[i][j] + bb;
+    }
+  }
+}
+
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
   if (a.n_seg < 1 || a.n_seg > 3) return -1;
   int cin = 0;
   for (int i = 0; i < a.n_seg; ++i) cin += a.seg_ch[i];
   if (cin != a.Cin) return -1;
   const long long Ntot = (long long)a.B * a.Ho * a.Wo;
+  if (a.transposed && a.stride == 2 && a.k <= 4 && a.Ho % 2 == 0 && a.Wo % 2 == 0) {
+    dim3 g2((unsigned)((Ntot / 4 + CN - 1) / CN), (a.Cout + CM - 1) / CM, 4);
+    conv_simt_t2_kernel<<<g2, 256, 0, st>>>(a);
+    DPMN_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid((unsigned)((Ntot + CN - 1) / CN), (a.Cout + CM - 1) / CM, 1);
   if (a.transposed) conv_simt_kernel<true><<<grid, 256, 0, st>>>(a);
   else conv_simt_kernel<false><<<grid, 256, 0, st>>>(a);

@@ -46,7 +46,11 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += CK) {
+  // split-K (deep layers: few output tiles, K = Cin*k*k up to 16384): blockIdx.z takes a K range, atomics combine
+  const int kchunk = ((K + p.ksplit - 1) / p.ksplit + CK - 1) / CK * CK;
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = min(K, kbeg + kchunk);
+  for (int k0 = kbeg; k0 < kend; k0 += CK) {
     float av[4], bv[4];
     {
       const int k = k0 + ak;
@@ -56,7 +60,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs p) {
       for (int i = 0; i < 4; ++i) {
         const int co = m0 + am0 + 16 * i;
         float v = 0.f;
-        if (k < K && co < p.Cout)
+        if (k < kend && co < p.Cout)
           v = TRANSPOSED ? p.w[((long long)ci * p.Cout + co) * kk + tap] : p.w[(long long)co * K + k];
         av[i] = v;
       }
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs p) {
     for (int i = 0; i < 4; ++i) {
       const int k = k0 + bk0 + 4 * i;
       float v = 0.f;
-      if (n_ok && k < K) {
+      if (n_ok && k < kend) {
         const int ci = k / kk;
         const int tap = k - ci * kk;
         const int ky = tap / p.k, kx = tap - ky * p.k;
@@ -121,14 +125,16 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs p) {
   for (int i = 0; i < 4; ++i) {
     const int co = m0 + ty * 4 + i;
     if (co >= p.Cout) continue;
-    const float bb = p.bias ? p.bias[co] : 0.f;
+    const float bb = (p.bias && blockIdx.z == 0) ? p.bias[co] : 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const long long n = (long long)n0 + tx * 4 + j;
       if (n >= Ntot) continue;
       const int b = (int)(n / HoWo);
       const int r = (int)(n - (long long)b * HoWo);
-      p.out[((long long)b * p.Cout + co) * HoWo + r] = acc[i][j] + bb;
+      float* dst = p.out + ((long long)b * p.Cout + co) * HoWo + r;
+      if (p.ksplit == 1) *dst = acc[i][j] + bb;
+      else atomicAdd(dst, acc[i][j] + bb);       // `out` was zero-filled by the launcher
     }
   }
 }
@@ -144,7 +150,8 @@ __global__ void __launch_bounds__(256) conv_simt_t2_kernel(ConvArgs p) {
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * CM, n0 = blockIdx.x * CN;
-  const int py = blockIdx.z >> 1, px = blockIdx.z & 1;
+  const int cls = blockIdx.z / p.ksplit, ks = blockIdx.z - cls * p.ksplit;
+  const int py = cls >> 1, px = cls & 1;
   int kys[4], kxs[4], nky = 0, nkx = 0;
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
@@ -154,6 +161,9 @@ __global__ void __launch_bounds__(256) conv_simt_t2_kernel(ConvArgs p) {
   const int nt = nky * nkx;
   const int kk = p.k * p.k;
   const int K = p.Cin * nt;
+  const int kchunk = ((K + p.ksplit - 1) / p.ksplit + CK - 1) / CK * CK;
+  const int kbeg = ks * kchunk;
+  const int kend = min(K, kbeg + kchunk);
   const int Hq = p.Ho >> 1, Wq = p.Wo >> 1;
   const int HqWq = Hq * Wq;
   const int HoWo = p.Ho * p.Wo;
@@ -179,12 +189,12 @@ __global__ void __launch_bounds__(256) conv_simt_t2_kernel(ConvArgs p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += CK) {
+  for (int k0 = kbeg; k0 < kend; k0 += CK) {
     float av[4], bv[4];
     {
       const int k = k0 + ak;
       int wofs = 0;
-      if (k < K) {
+      if (k < kend) {
         const int ci = k / nt, r = k - ci * nt;
         const int a = r / nkx, b2 = r - a * nkx;
         wofs = ci * p.Cout * kk + kys[a] * p.k + kxs[b2];
@@ -192,14 +202,14 @@ __global__ void __launch_bounds__(256) conv_simt_t2_kernel(ConvArgs p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int co = m0 + am0 + 16 * i;
-        av[i] = (k < K && co < p.Cout) ? p.w[(long long)wofs + (long long)co * kk] : 0.f;
+        av[i] = (k < kend && co < p.Cout) ? p.w[(long long)wofs + (long long)co * kk] : 0.f;
       }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int k = k0 + bk0 + 4 * i;
       float v = 0.f;
-      if (n_ok && k < K) {
+      if (n_ok && k < kend) {
         const int ci = k / nt, r = k - ci * nt;
         const int a = r / nkx, b2 = r - a * nkx;
         const int ty2 = oy + p.pad - kys[a] * p.dil, tx2 = ox + p.pad - kxs[b2] * p.dil;   // even by construction
@@ -241,7 +251,7 @@ __global__ void __launch_bounds__(256) conv_simt_t2_kernel(ConvArgs p) {
   for (int i = 0; i < 4; ++i) {
     const int co = m0 + ty * 4 + i;
     if (co >= p.Cout) continue;
-    const float bb = p.bias ? p.bias[co] : 0.f;
+    const float bb = (p.bias && ks == 0) ? p.bias[co] : 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const long long n = (long long)n0 + tx * 4 + j;
@@ -249,24 +259,40 @@ __global__ void __launch_bounds__(256) conv_simt_t2_kernel(ConvArgs p) {
       const int b = (int)(n / HqWq);
       const int r = (int)(n - (long long)b * HqWq);
       const int qy = r / Wq, qx = r - qy * Wq;
-      p.out[((long long)b * p.Cout + co) * HoWo + (long long)(2 * qy + py) * p.Wo + 2 * qx + px] = acc[i][j] + bb;
+      float* dst = p.out + ((long long)b * p.Cout + co) * HoWo + (long long)(2 * qy + py) * p.Wo + 2 * qx + px;
+      if (p.ksplit == 1) *dst = acc[i][j] + bb;
+      else atomicAdd(dst, acc[i][j] + bb);
     }
   }
 }
 
-int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
+int launch_conv_simt(const ConvArgs& a_in, cudaStream_t st) {
+  ConvArgs a = a_in;
   if (a.n_seg < 1 || a.n_seg > 3) return -1;
   int cin = 0;
   for (int i = 0; i < a.n_seg; ++i) cin += a.seg_ch[i];
   if (cin != a.Cin) return -1;
   const long long Ntot = (long long)a.B * a.Ho * a.Wo;
-  if (a.transposed && a.stride == 2 && a.k <= 4 && a.Ho % 2 == 0 && a.Wo % 2 == 0) {
-    dim3 g2((unsigned)((Ntot / 4 + CN - 1) / CN), (a.Cout + CM - 1) / CM, 4);
+  const bool t2 = a.transposed && a.stride == 2 && a.k <= 4 && a.Ho % 2 == 0 && a.Wo % 2 == 0;
+  const long long n_tiles = t2 ? (Ntot / 4 + CN - 1) / CN * 4 : (Ntot + CN - 1) / CN;
+  const long long ctas = n_tiles * ((a.Cout + CM - 1) / CM);
+  const int K = a.Cin * (t2 ? (a.dil % 2 == 0 ? a.k * a.k : ((a.k + 1) / 2) * ((a.k + 1) / 2)) : a.k * a.k);
+  a.ksplit = 1;
+  if (ctas < 296 && K >= 1024) {       // deep layers: fill the SMs by splitting K (atomics into a zero-filled output)
+    long long ks = 592 / ctas;
+    if (ks > K / 256) ks = K / 256;
+    if (ks > 1) {
+      a.ksplit = (int)ks;
+      DPMN_CUDA_TRY(cudaMemsetAsync(a.out, 0, (size_t)a.B * a.Cout * a.Ho * a.Wo * sizeof(float), st));
+    }
+  }
+  if (t2) {
+    dim3 g2((unsigned)((Ntot / 4 + CN - 1) / CN), (a.Cout + CM - 1) / CM, 4 * a.ksplit);
     conv_simt_t2_kernel<<<g2, 256, 0, st>>>(a);
     DPMN_LAUNCH_CHECK();
     return 0;
   }
-  dim3 grid((unsigned)((Ntot + CN - 1) / CN), (a.Cout + CM - 1) / CM, 1);
+  dim3 grid((unsigned)((Ntot + CN - 1) / CN), (a.Cout + CM - 1) / CM, a.ksplit);
   if (a.transposed) conv_simt_kernel<true><<<grid, 256, 0, st>>>(a);
   else conv_simt_kernel<false><<<grid, 256, 0, st>>>(a);
   DPMN_LAUNCH_CHECK();

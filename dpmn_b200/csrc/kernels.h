@@ -241,6 +241,7 @@ struct ConvArgs {
   int B = 0, Cin = 0, H = 0, W = 0, Cout = 0, Ho = 0, Wo = 0;
   int k = 3, stride = 1, pad = 1, dil = 1;
   int transposed = 0;
+  int ksplit = 1;                  // set by launch_conv_simt: K split over blockIdx.z with atomic accumulation
 };
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 

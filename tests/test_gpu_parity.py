@@ -160,7 +160,9 @@ def test_cmm_batch_48_eval_is_per_image_independent():
     with torch.no_grad():
         y = m(_t(x1), _t(x2))
         y0 = m(_t(x1[7:8]), _t(x2[7:8]))
-    assert torch.equal(y[7:8], y0)
+    # same image alone and inside a batch of 48: equal up to fp32 summation order (the deep layers split K over CTAs
+    # by a batch-size dependent factor and combine with atomics), i.e. no cross-image coupling in eval mode
+    assert rel_err(y[7:8].cpu().numpy(), y0.cpu().numpy()) < 2e-6
     ref = cmm_oracle.cmm_forward(P, x1[7:8], x2[7:8], training=False)
     assert rel_err(y0.cpu().numpy(), ref) < TOL_F32 * 2
 

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libdpmn_b200.so")
 
 MAX_GROUPS, MAX_MIX, MAX_BLOCKS = 4, 8, 2
 CMM_WORKSPACE_HOLDS_FORWARD = 1
+PGRM_WORKSPACE_HOLDS_FORWARD = 1
 PREC = {"fp32": 0, "f32": 0, "fp16": 1, "f16": 1, "bf16": 2}
 ERRORS = {-1: "DPMN_E_ARG (null pointer / inconsistent sizes)",
           -2: "DPMN_E_UNSUPPORTED (configuration outside this build or that the reference cannot run)",
@@ -43,7 +44,7 @@ class PgrmDesc(C.Structure):
                 ("head0_w", fp), ("head0_b", fp), ("head1_w", fp), ("head1_b", fp),
                 ("mix_weight", fp * MAX_MIX), ("mix_input", fp * MAX_MIX),
                 ("mix_input_batch_stride", C.c_int64 * MAX_MIX),
-                ("prepared", fp), ("prepared_valid", C.c_int32), ("reserved_", C.c_int32),
+                ("prepared", fp), ("prepared_valid", C.c_int32), ("flags", C.c_int32),
                 ("drop_rate", C.c_float), ("attn_drop_rate", C.c_float), ("drop_path_rate", C.c_float * MAX_BLOCKS),
                 ("seed", C.c_uint64)]
 

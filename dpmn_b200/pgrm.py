@@ -133,9 +133,13 @@ class _PGRMFunction(torch.autograd.Function):
     def forward(ctx, module, x_q, x_kv, n_res, *rest):
         residuals = list(rest[:n_res])
         seed = module._new_seed() if module._stochastic() else None    # train-mode Dropout / DropPath masks
+        keep_ws = []
         with torch.no_grad():
-            out = module._run(x_q, x_kv, residuals, probe=False, seed=seed)
+            # a stochastic forward is the fp32 training sequence: run it in a private buffer laid out as the backward's
+            # workspace, which then finds every intermediate in place (DPMN_PGRM_WORKSPACE_HOLDS_FORWARD)
+            out = module._run(x_q, x_kv, residuals, probe=False, seed=seed, keep_ws=keep_ws if seed is not None else None)
         ctx.module, ctx.n_res, ctx.seed = module, n_res, seed
+        ctx.fwd_ws = keep_ws[0] if keep_ws else None
         ctx.save_for_backward(x_q, x_kv, *residuals)
         return out
 
@@ -145,7 +149,9 @@ class _PGRMFunction(torch.autograd.Function):
         m = ctx.module
         need_xkv = ctx.needs_input_grad[2]
         need_res = [ctx.needs_input_grad[4 + i] for i in range(ctx.n_res)]
-        d_xkv, d_res, d_params = m._backward(x_q, x_kv, residuals, d_out, need_xkv, need_res, seed=ctx.seed)
+        d_xkv, d_res, d_params = m._backward(x_q, x_kv, residuals, d_out, need_xkv, need_res, seed=ctx.seed,
+                                             fwd_ws=ctx.fwd_ws)
+        ctx.fwd_ws = None
         return (None, None, d_xkv, None, *d_res, *d_params)
 
 
@@ -263,7 +269,7 @@ class PGRM(ParamTree):
             return _PGRMFunction.apply(self, x_q, x_kv, len(residual_list), *residual_list, *params)
         return self._run(x_q, x_kv, residual_list, probe=False)
 
-    def _backward(self, x_q, x_kv, residuals, d_out, need_xkv=True, need_res=None, seed=None):
+    def _backward(self, x_q, x_kv, residuals, d_out, need_xkv=True, need_res=None, seed=None, fwd_ws=None):
         """d_out (B, hs, H, W) -> (d x_kv | None, [d residual_i | None], [d param | None in named_parameters order]).
         `seed`: the seed of the forward's Dropout / DropPath masks (None = none were drawn)."""
         lib = _lib.load()
@@ -326,7 +332,11 @@ class PGRM(ParamTree):
             nbytes = lib.dpmn_pgrm_backward_workspace_bytes(C.byref(d))
             if nbytes == 0:
                 raise RuntimeError("dpmn_pgrm_backward_workspace_bytes: configuration rejected")
-            ws = workspace(dev, nbytes)
+            if fwd_ws is not None and fwd_ws.numel() >= nbytes:
+                ws = fwd_ws
+                d.flags = _lib.PGRM_WORKSPACE_HOLDS_FORWARD
+            else:
+                ws = workspace(dev, nbytes)
             rc = lib.dpmn_pgrm_backward(C.byref(d), x_q.data_ptr(), x_kv.data_ptr(), d_out.data_ptr(), C.byref(g),
                                         ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(rc, "dpmn_pgrm_backward")
@@ -339,7 +349,7 @@ class PGRM(ParamTree):
         """forward + the per-block tensors the parity tests compare: (out, attn_core[2], block_out[2])."""
         return self._run(x_q, x_kv, residual_list, probe=True)
 
-    def _run(self, x_q, x_kv, residual_list, probe: bool, seed=None):
+    def _run(self, x_q, x_kv, residual_list, probe: bool, seed=None, keep_ws=None):
         if seed is None and self._stochastic():
             seed = self._new_seed()             # train-mode forward outside autograd (torch.no_grad())
         lib = _lib.load()
@@ -372,7 +382,11 @@ class PGRM(ParamTree):
             if nbytes == 0:
                 raise RuntimeError("dpmn_pgrm_workspace_bytes: configuration rejected (see DPMN_E_UNSUPPORTED rules "
                                    "in include/dpmn_b200.h)")
-            ws = workspace(dev, nbytes)
+            if keep_ws is not None:
+                ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+                keep_ws.append(ws)
+            else:
+                ws = workspace(dev, nbytes)
             out = torch.empty((B, cfg.hidden_size, cfg.img_size[0], cfg.img_size[1]), dtype=torch.float32, device=dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
             if not probe:

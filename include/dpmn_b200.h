@@ -103,7 +103,7 @@ typedef struct dpmn_pgrm_desc {
    * prepared_valid == 0 and reuses it when prepared_valid == 1 (the caller re-validates after the weights change). */
   void *prepared;
   int32_t prepared_valid;
-  int32_t reserved_;
+  int32_t flags;                             /* DPMN_PGRM_* bits, 0 by default */
   /* Train-mode stochastic regularisers (module.train(), pgrm.py:24,32,40 Mlp Dropout; :180,248 attn_drop; :310,329-330
    * DropPath; :494,554-555 pos_drop).  All rates 0 (the default) = eval semantics.  With a non-zero rate the forward
    * runs the fp32 training sequence whatever `precision` says and needs dpmn_pgrm_backward_workspace_bytes() of
@@ -114,6 +114,11 @@ typedef struct dpmn_pgrm_desc {
   float drop_path_rate[DPMN_MAX_BLOCKS];     /* dpr slice of this PGRM (pgrm.py:499,512) */
   uint64_t seed;                             /* fresh per training forward */
 } dpmn_pgrm_desc;
+
+/* dpmn_pgrm_backward only: `workspace` is the buffer a dpmn_pgrm_forward call with non-zero drop rates (i.e. the fp32
+ * training sequence), the same descriptor, seed and inputs has just filled, untouched since -- the backward then
+ * skips its internal forward recompute. */
+#define DPMN_PGRM_WORKSPACE_HOLDS_FORWARD 1
 
 /* ---- Complementation Modulation Module (cmm.py:80-161) ------------------------------------------- */
 typedef struct dpmn_bn {          /* nn.BatchNorm2d (cmm.py:12), eps 1e-5, momentum 0.1 */

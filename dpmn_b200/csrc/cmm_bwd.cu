@@ -385,8 +385,109 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(BnBwdArgs p) {
   }
 }
 
+// ---- the same computation for layers with few channels and many pixels (C = 64..128 at 32x128 / 16x64: one CTA per
+// channel leaves most SMs idle and each CTA streams 200 K elements three times).  Three fully parallel passes over
+// (channel, pixel chunk) with per-channel atomics into a small scratch: [C][4] = sum(y - ref), sum((y - ref)^2),
+// sum(dbn), sum(dbn * xhat); ref = the channel's first element (a shift that keeps the one-pass variance well
+// conditioned).
+__global__ void __launch_bounds__(256) bn_stats_part_kernel(BnBwdArgs p, float* __restrict__ scratch, int chunk) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  const long long n = (long long)p.B * p.HW;
+  const long long i0 = (long long)blockIdx.y * chunk, i1 = min(n, i0 + chunk);
+  const float ref = p.y[(long long)c * p.HW];
+  float s = 0.f, q = 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const int b = (int)(i / p.HW); const int r = (int)(i - (long long)b * p.HW);
+    const float d = p.y[((long long)b * p.C + c) * p.HW + r] - ref;
+    s += d; q = fmaf(d, d, q);
+  }
+  s = block_sum_256b(s, red);
+  q = block_sum_256b(q, red);
+  if (threadIdx.x == 0) { atomicAdd(scratch + c * 4 + 0, s); atomicAdd(scratch + c * 4 + 1, q); }
+}
+
+__device__ __forceinline__ void bn_channel_affine(const BnBwdArgs& p, const float* scratch, int c, float& mean, float& rstd,
+                                                  float& sc, float& sh) {
+  mean = 0.f; rstd = 1.f; sc = 1.f; sh = 0.f;
+  if (p.gamma == nullptr) return;
+  float var;
+  if (p.training) {
+    const float n = (float)((long long)p.B * p.HW);
+    const float ref = p.y[(long long)c * p.HW];
+    const float ms = scratch[c * 4 + 0] / n;
+    mean = ref + ms;
+    var = fmaxf(scratch[c * 4 + 1] / n - ms * ms, 0.f);
+  } else {
+    mean = p.run_mean[c]; var = p.run_var[c];
+  }
+  rstd = 1.0f / sqrtf(var + p.eps);
+  sc = p.gamma[c] * rstd;
+  sh = p.beta[c] - mean * sc;
+}
+
+template <bool APPLY>   // false: accumulate sum(dbn), sum(dbn*xhat); true: write dy (+ bias gradient)
+__global__ void __launch_bounds__(256) bn_dbn_part_kernel(BnBwdArgs p, float* __restrict__ scratch, int chunk) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  const long long n = (long long)p.B * p.HW;
+  const long long i0 = (long long)blockIdx.y * chunk, i1 = min(n, i0 + chunk);
+  float mean, rstd, sc, sh;
+  bn_channel_affine(p, scratch, c, mean, rstd, sc, sh);
+  const bool has_bn = p.gamma != nullptr;
+  float m1 = 0.f, m2 = 0.f;
+  if (APPLY && has_bn && p.training) { m1 = scratch[c * 4 + 2] / (float)n; m2 = scratch[c * 4 + 3] / (float)n; }
+  float a0 = 0.f, a1 = 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const int b = (int)(i / p.HW); const int r = (int)(i - (long long)b * p.HW);
+    const long long o = ((long long)b * p.C + c) * p.HW + r;
+    const float yv = p.y[o];
+    const float bn = fmaf(yv, sc, sh);
+    float g = 0.f;
+    for (int s = 0; s < p.n_src; ++s)
+      g = fmaf(p.du[s][(long long)b * p.du_bs[s] + (long long)c * p.HW + r], act_grad(p.act[s], bn), g);
+    const float xh = (yv - mean) * rstd;
+    if (APPLY) {
+      const float d = has_bn ? sc * (g - m1 - xh * m2) : g;
+      p.dy[o] = d;
+      a0 += d;
+    } else {
+      a0 += g;
+      a1 = fmaf(g, xh, a1);
+    }
+  }
+  a0 = block_sum_256b(a0, red);
+  if (APPLY) {
+    if (threadIdx.x == 0 && p.dbias != nullptr) atomicAdd(p.dbias + c, a0);
+  } else {
+    a1 = block_sum_256b(a1, red);
+    if (threadIdx.x == 0) { atomicAdd(scratch + c * 4 + 2, a0); atomicAdd(scratch + c * 4 + 3, a1); }
+  }
+}
+
+__global__ void bn_param_grad_kernel(BnBwdArgs p, const float* __restrict__ scratch) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < p.C) { atomicAdd(p.dgamma + c, scratch[c * 4 + 3]); atomicAdd(p.dbeta + c, scratch[c * 4 + 2]); }
+}
+
 int launch_bn_act_bwd(const BnBwdArgs& a, cudaStream_t st) {
   if (a.n_src < 1 || a.n_src > 2) return -1;
+  const long long n = (long long)a.B * a.HW;
+  if (a.scratch != nullptr && a.C <= 256 && n >= 8192) {
+    const int chunk = 8192;
+    const dim3 grid(a.C, (unsigned)((n + chunk - 1) / chunk));
+    DPMN_CUDA_TRY(cudaMemsetAsync(a.scratch, 0, (size_t)a.C * 4 * sizeof(float), st));
+    if (a.gamma != nullptr) {
+      if (a.training) { bn_stats_part_kernel<<<grid, 256, 0, st>>>(a, a.scratch, chunk); DPMN_LAUNCH_CHECK(); }
+      bn_dbn_part_kernel<false><<<grid, 256, 0, st>>>(a, a.scratch, chunk);
+      DPMN_LAUNCH_CHECK();
+      bn_param_grad_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(a, a.scratch);
+      DPMN_LAUNCH_CHECK();
+    }
+    bn_dbn_part_kernel<true><<<grid, 256, 0, st>>>(a, a.scratch, chunk);
+    DPMN_LAUNCH_CHECK();
+    return 0;
+  }
   bn_act_bwd_kernel<<<a.C, 256, 0, st>>>(a);
   DPMN_LAUNCH_CHECK();
   return 0;

@@ -270,6 +270,7 @@ struct BnBwdArgs {
   int act[2] = {};                     // the consumer's activation: 0 none, 1 LeakyReLU(0.2), 2 ReLU
   float* dy = nullptr;                 // (B, C, HW) written
   float *dgamma = nullptr, *dbeta = nullptr, *dbias = nullptr;   // accumulated
+  float* scratch = nullptr;            // >= 4*C floats: enables the multi-CTA-per-channel path for large B*HW
 };
 int launch_bn_act_bwd(const BnBwdArgs& a, cudaStream_t st);
 int launch_chan_sum(const float* x, int B, int C, int HW, float* out, cudaStream_t st);

@@ -16,14 +16,16 @@ namespace dpmn {
 
 constexpr int WM = 64, WN = 64, WK = 16, WPAD = 68;
 
-template <bool TRANSPOSED>
+// MR: output-channel rows per thread (tile = 16*MR channels x 64 k-indices); MR = 1 for Cout <= 16 (de_1: Cout = 3)
+template <bool TRANSPOSED, int MR>
 __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(ConvArgs p, const float* __restrict__ dy,
                                                               float* __restrict__ dw, int nsplit) {
   __shared__ __align__(16) float As[WK][WPAD];   // dy       [pixel][co]
   __shared__ __align__(16) float Bs[WK][WPAD];   // gathered [pixel][k]
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * WM, k0 = blockIdx.x * WN;
+  constexpr int TM = 16 * MR;
+  const int m0 = blockIdx.y * TM, k0 = blockIdx.x * WN;
   const int kk = p.k * p.k;
   const int K = p.Cin * kk;
   const int HoWo = p.Ho * p.Wo;
@@ -55,9 +57,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(ConvArgs p, const 
   // dy loader: pixel (tid % 16), co rows (tid / 16) + 16 i
   const int ap = tid & 15, am0 = tid >> 4;
 
-  float acc[4][4];
+  float acc[MR][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MR; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(ConvArgs p, const 
       int b = 0, r = 0;
       if (n < nend) { b = (int)(n / HoWo); r = (int)(n - (long long)b * HoWo); }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < MR; ++i) {
         const int co = m0 + am0 + 16 * i;
         av[i] = (n < nend && co < p.Cout) ? dy[((long long)b * p.Cout + co) * HoWo + r] : 0.f;
       }
@@ -105,25 +107,31 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(ConvArgs p, const 
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      As[ap][am0 + 16 * i] = av[i];
+      if (i < MR) As[ap][am0 + 16 * i] = av[i];
       Bs[gp0 + 4 * i][tid & 63] = bv[i];
     }
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < WK; ++q) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
+      float ar[MR];
+      if constexpr (MR == 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
+        ar[0] = a4.x; ar[1] = a4.y; ar[2] = a4.z; ar[3] = a4.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < MR; ++i) ar[i] = As[q][ty * MR + i];
+      }
       const float4 b4 = *reinterpret_cast<const float4*>(&Bs[q][tx * 4]);
-      const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
       const float br[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MR; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int co = m0 + ty * 4 + i;
+  for (int i = 0; i < MR; ++i) {
+    const int co = m0 + ty * MR + i;
     if (co >= p.Cout) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -285,14 +293,18 @@ int launch_conv_wgrad_simt(const ConvArgs& a, const float* dy, float* dw, cudaSt
   }
   const int K = a.Cin * a.k * a.k;
   const long long Ntot = (long long)a.B * a.Ho * a.Wo;
-  const int tiles = ((K + WN - 1) / WN) * ((a.Cout + WM - 1) / WM);
+  const int tm = a.Cout <= 16 ? 16 : WM;
+  const int tiles = ((K + WN - 1) / WN) * ((a.Cout + tm - 1) / tm);
   long long ns = 1184 / tiles;
   if (ns > Ntot / 64) ns = Ntot / 64;
   if (ns < 1) ns = 1;
   if (ns > 512) ns = 512;
-  dim3 grid((K + WN - 1) / WN, (a.Cout + WM - 1) / WM, (unsigned)ns);
-  if (a.transposed) conv_wgrad_simt_kernel<true><<<grid, 256, 0, st>>>(a, dy, dw, (int)ns);
-  else conv_wgrad_simt_kernel<false><<<grid, 256, 0, st>>>(a, dy, dw, (int)ns);
+  dim3 grid((K + WN - 1) / WN, (a.Cout + tm - 1) / tm, (unsigned)ns);
+  if (a.Cout <= 16) {
+    if (a.transposed) conv_wgrad_simt_kernel<true, 1><<<grid, 256, 0, st>>>(a, dy, dw, (int)ns);
+    else conv_wgrad_simt_kernel<false, 1><<<grid, 256, 0, st>>>(a, dy, dw, (int)ns);
+  } else if (a.transposed) conv_wgrad_simt_kernel<true, 4><<<grid, 256, 0, st>>>(a, dy, dw, (int)ns);
+  else conv_wgrad_simt_kernel<false, 4><<<grid, 256, 0, st>>>(a, dy, dw, (int)ns);
   DPMN_LAUNCH_CHECK();
   return 0;
 }

@@ -12,14 +12,17 @@ namespace dpmn {
 
 constexpr int CM = 64, CN = 64, CK = 16, CPAD = 68;
 
-template <bool TRANSPOSED>
+// MR = output-channel rows per thread: the tile is (16*MR channels) x 64 pixels.  MR = 1 serves the layers with a handful
+// of output channels (de_1 and the data gradient of en_1: Cout = 3), where a 64-row tile would be 95 % padding.
+template <bool TRANSPOSED, int MR>
 __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs p) {
+  constexpr int TM = 16 * MR;
   __shared__ __align__(16) float As[CK][CPAD];   // weights  [k][co]
   __shared__ __align__(16) float Bs[CK][CPAD];   // gathered input [k][pixel]
 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * CM, n0 = blockIdx.x * CN;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * CN;
   const int kk = p.k * p.k;
   const int K = p.Cin * kk;
   const int HoWo = p.Ho * p.Wo;
@@ -40,9 +43,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs p) {
   // A loader: weight row (tid/16) + 16*i, k column tid%16
   const int ak = tid & 15, am0 = tid >> 4;
 
-  float acc[4][4];
+  float acc[MR][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MR; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs p) {
       int ci = 0, tap = 0;
       if (TRANSPOSED) { ci = k / kk; tap = k - ci * kk; }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < MR; ++i) {
         const int co = m0 + am0 + 16 * i;
         float v = 0.f;
         if (k < kend && co < p.Cout)
@@ -104,26 +107,32 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs p) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      As[ak][am0 + 16 * i] = av[i];
+      if (i < MR) As[ak][am0 + 16 * i] = av[i];
       Bs[bk0 + 4 * i][bn] = bv[i];
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < CK; ++k) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float ar[MR];
+      if constexpr (MR == 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        ar[0] = a4.x; ar[1] = a4.y; ar[2] = a4.z; ar[3] = a4.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < MR; ++i) ar[i] = As[k][ty * MR + i];
+      }
       const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
       const float br[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MR; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
     }
   }
 
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int co = m0 + ty * 4 + i;
+  for (int i = 0; i < MR; ++i) {
+    const int co = m0 + ty * MR + i;
     if (co >= p.Cout) continue;
     const float bb = (p.bias && blockIdx.z == 0) ? p.bias[co] : 0.f;
 #pragma unroll
@@ -292,9 +301,16 @@ int launch_conv_simt(const ConvArgs& a_in, cudaStream_t st) {
     DPMN_LAUNCH_CHECK();
     return 0;
   }
+  if (a.Cout <= 16) {
+    dim3 grid((unsigned)((Ntot + CN - 1) / CN), (a.Cout + 15) / 16, a.ksplit);
+    if (a.transposed) conv_simt_kernel<true, 1><<<grid, 256, 0, st>>>(a);
+    else conv_simt_kernel<false, 1><<<grid, 256, 0, st>>>(a);
+    DPMN_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid((unsigned)((Ntot + CN - 1) / CN), (a.Cout + CM - 1) / CM, a.ksplit);
-  if (a.transposed) conv_simt_kernel<true><<<grid, 256, 0, st>>>(a);
-  else conv_simt_kernel<false><<<grid, 256, 0, st>>>(a);
+  if (a.transposed) conv_simt_kernel<true, 4><<<grid, 256, 0, st>>>(a);
+  else conv_simt_kernel<false, 4><<<grid, 256, 0, st>>>(a);
   DPMN_LAUNCH_CHECK();
   return 0;
 }

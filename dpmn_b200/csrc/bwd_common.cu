@@ -200,6 +200,55 @@ int launch_branch_combine(float* dst, const float* base, const float* y, long lo
   return 0;
 }
 
+// dst[z][c][r] = (T) src[z][r][c]: transposing fp32 -> 16-bit staging of a gradient / activation matrix, so that the
+// weight-gradient contraction over rows becomes a K-contiguous tcgen05 GEMM (gemm_tc.cu).  32 x 32 smem tiles.
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_convert_kernel(const float* __restrict__ src, T* __restrict__ dst, int R,
+                                                                int Cc, long long src_bs, long long dst_bs) {
+  __shared__ float tile[32][33];
+  const int z = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* s = src + (long long)z * src_bs;
+  T* d = dst + (long long)z * dst_bs;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    tile[ty + 8 * i][tx] = (r < R && c < Cc) ? s[(long long)r * Cc + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;
+    if (c < Cc && r < R) d[(long long)c * R + r] = from_f32<T>(tile[tx][ty + 8 * i]);
+  }
+}
+
+int launch_transpose_convert(const float* src, void* dst, DType t, int batch, int R, int Cc, cudaStream_t st) {
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32, batch);
+  const long long bs = (long long)R * Cc;
+  if (t == DT_F16) transpose_convert_kernel<__half><<<grid, 256, 0, st>>>(src, (__half*)dst, R, Cc, bs, bs);
+  else if (t == DT_BF16) transpose_convert_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, (__nv_bfloat16*)dst, R, Cc, bs, bs);
+  else return -1;
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// dst[i] += sum_s partial[s*n + i]      (split-K partial products of the tensor-core weight gradients)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ dst, int S, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int s = 0; s < S; ++s) a += partial[(long long)s * n + i];
+  dst[i] += a;
+}
+
+int launch_reduce_partials(const float* partial, float* dst, int S, long long n, cudaStream_t st) {
+  reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, dst, S, n);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
 // =====================================================================================================
 // LayerNorm backward (eps 1e-5, nn.LayerNorm over the last dim).  One warp per row, C <= 256.
 //   xhat = (x - mean) * rstd;  g = dy * w;  dx (+)= rstd * (g - mean(g) - xhat * mean(g * xhat))

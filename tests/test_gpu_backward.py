@@ -223,3 +223,26 @@ def test_pgrm_train_mode_dropout_droppath_forward_and_backward(name, rates):
         y3 = m(xq, xkv.detach(), [r.detach() for r in rs])
     assert not torch.equal(y2, y.detach())
     assert torch.equal(y3, y.detach())
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 3e-3), ("bf16", 2e-2)])
+def test_pgrm_backward_tensor_core_gemms(precision, tol):
+    """16-bit modes: the Linear / pointwise-conv data and weight gradients run on the tcgen05 GEMM with 16-bit staged
+    operands and fp32 accumulation (everything else of the backward stays fp32).  Bar: 3e-3 (fp16) / 2e-2 (bf16) on
+    max|d| / max|ref| per tensor against the reference's fp32 gradients -- the forward parity bar of the same modes,
+    times the longer contraction (49 152 rows in the weight gradients)."""
+    z, meta = load_golden("pgrm_i2_m0_grad")
+    cfg, P, x_q, x_kv, res = pgrm_case(meta)
+    m, _ = build_pgrm(meta, "cuda", precision=precision)
+    dev = torch.device("cuda")
+    # batch 2 -> rows = 2048 (a multiple of the 512-row split the tensor-core weight gradient needs)
+    xq = torch.from_numpy(x_q).to(dev)
+    xkv = torch.from_numpy(x_kv).to(dev).requires_grad_(True)
+    rs = [torch.from_numpy(r).to(dev).requires_grad_(True) for r in res]
+    y = m(xq, xkv, rs)
+    (y * torch.from_numpy(grad_seed_out(meta["seed"], meta["B"])).to(dev)).sum().backward()
+    grads = {k: (p.grad.cpu().numpy() if p.grad is not None else None) for k, p in m.named_parameters()}
+    grads["x_kv"] = xkv.grad.cpu().numpy()
+    for i, r in enumerate(rs):
+        grads[f"res{i}"] = r.grad.cpu().numpy() if r.grad is not None else None
+    _compare(z, meta, grads, tol=tol)

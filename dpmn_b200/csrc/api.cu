@@ -1,6 +1,7 @@
 // C-ABI of libdpmn_b200 (include/dpmn_b200.h): argument checking, workspace carving and the launch
 // sequences of PGRM.forward (pgrm.py:546-565) and ComplementationModulationModule.forward (cmm.py:120-161).
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>

@@ -160,8 +160,9 @@ def run_ours(args):
     train = args.mode == "train"
     if train:
         # configs[2]: the three drop rates at the reference's 0.1 (README.md:42) -> every PGRM forward is the fp32
-        # training sequence with Dropout / DropPath masks; CMM forward fp32 (train-mode BatchNorm); backward fp32
-        model = DPMNHotPath(precision=args.precision, drop=args.train_drop, cmm_precision="fp32")
+        # training sequence with Dropout / DropPath masks; CMM train-mode BatchNorm; fp32 storage everywhere, the GEMMs and
+        # convs of both modules on tcgen05 with 16-bit staged operands
+        model = DPMNHotPath(precision=args.precision, drop=args.train_drop)
     else:
         model = DPMNHotPath(precision=args.precision)
     pg, cm = synth_weights(2)

@@ -37,7 +37,7 @@ class _CMMFunction(torch.autograd.Function):
         with torch.no_grad():
             # fp32 forward: run it inside a private buffer laid out as the backward's workspace, so that the backward
             # finds every activation in place and skips its recompute (DPMN_CMM_WORKSPACE_HOLDS_FORWARD)
-            keep = module.precision == "fp32"
+            keep = module.precision == "fp32" or module.training   # the fp32-structured forward (see include/dpmn_b200.h)
             res = module._forward_impl(x1, x2, keep_workspace=keep)
             out, ws = res if keep else (res, None)
         ctx.module = module

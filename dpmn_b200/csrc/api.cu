@@ -430,6 +430,7 @@ struct CmmWs {
   float* d6; float *d6_sc, *d6_sh;
   float* dmid[4]; float *dmid_sc[4], *dmid_sh[4];
   float* dout[4]; float *dout_sc[4], *dout_sh[4];
+  ConvTcScratch tc;      // 16-bit modes: the convs of this fp32-structured path run on tcgen05 through an im2col
   size_t bytes;
 };
 
@@ -468,6 +469,18 @@ CmmWs carve_cmm(const dpmn_cmm_desc* d, void* ws) {
     w.dout[i] = b.take<float>(B * ch_d[i] * hw_in * 4);
     w.dout_sc[i] = b.take<float>(ch_d[i]);
     w.dout_sh[i] = b.take<float>(ch_d[i]);
+  }
+  if (d->precision != DPMN_PREC_F32) {
+    const size_t kmax = 27 * c > 16 * c ? 27 * c : 16 * c;              // de_1 (3c x 3x3) and the 4x4 convs at full resolution
+    w.tc.t = (DType)d->precision;
+    w.tc.col_bytes = B * H * W * ((kmax + 15) / 16 * 16) * 2;
+    w.tc.col = b.take<char>(w.tc.col_bytes);
+    w.tc.w16_bytes = (size_t)16 * c * 16 * 8 * c * 2 + 4096;             // de_6: (8c) x (16c * 16)
+    w.tc.w16 = b.take<char>(w.tc.w16_bytes);
+    w.tc.dy16_bytes = B * H * W * 3 * c * 2;                             // widest gradient: de_1's concat input
+    w.tc.dy16 = b.take<char>(w.tc.dy16_bytes);
+    w.tc.part_bytes = (size_t)128 << 20;
+    w.tc.part = b.take<float>(w.tc.part_bytes / 4);
   }
   w.bytes = b.off + 256;
   return w;
@@ -930,7 +943,7 @@ static int check_cmm(const dpmn_cmm_desc* d) {
 
 size_t dpmn_cmm_workspace_bytes(const dpmn_cmm_desc* d) {
   if (check_cmm(d)) return 0;
-  if (d->precision != DPMN_PREC_F32) return carve_cmm_tc(d, nullptr).bytes;
+  if (d->precision != DPMN_PREC_F32 && !d->training) return carve_cmm_tc(d, nullptr).bytes;
   return carve_cmm(d, nullptr).bytes;
 }
 
@@ -969,19 +982,25 @@ int dpmn_cmm_debug_copy(const dpmn_cmm_desc* d, void* workspace, int32_t which, 
   return 0;
 }
 
-int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, float* out, void* workspace,
-                     size_t workspace_bytes, void* stream) {
+// A conv of the fp32-structured CMM path: fp32 FFMA tiles, or (16-bit modes) the tcgen05 GEMM through a 16-bit im2col.
+static int cmm_conv_any(const ConvArgs& a, const ConvTcScratch& tc, bool use_tc, cudaStream_t st) {
+  if (use_tc && conv_tc_im2col_ok(a)) {
+    const int rc = launch_conv_tc_im2col(a, tc, st);
+    if (rc != -3) return rc;           // -3: scratch too small for this layer -> SIMT
+  }
+  return launch_conv_simt(a, st);
+}
+
+// The fp32-structured forward (raw conv outputs + BatchNorm affines kept in the workspace: what the backward reads).
+// It is the fp32 mode, and in the 16-bit modes the train()-mode forward (batch-statistics BatchNorm) and the backward's
+// recompute, with the convs on tensor cores.
+static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const float* x2, float* out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   int rc = check_cmm(d);
   if (rc) return rc;
   if (!x1 || !x2 || !out || !workspace) return DPMN_E_ARG;
-  if (d->precision != DPMN_PREC_F32) {
-    for (int br = 0; br < 2; ++br) {
-      const long long bs = br == 0 ? d->x1_batch_stride : d->x2_batch_stride;
-      if (bs != 0 && bs != (long long)d->c_img * d->img_h * d->img_w) return DPMN_E_UNSUPPORTED;
-    }
-    return cmm_forward_tc(d, x1, x2, out, workspace, workspace_bytes, (cudaStream_t)stream);
-  }
   const CmmWs w = carve_cmm(d, workspace);
+  const bool use_tc = d->precision != DPMN_PREC_F32;
   if (workspace_bytes < w.bytes) return DPMN_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const int B = d->batch, c = d->cnum, H = d->img_h, W = d->img_w;
@@ -997,7 +1016,7 @@ int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, f
       if (bs != 0 && bs != (long long)d->c_img * H * W) return DPMN_E_UNSUPPORTED;
       a.w = d->en1_w[br]; a.bias = d->en1_b[br]; a.out = w.o[br][0];
       a.B = B; a.Cin = d->c_img; a.H = H; a.W = W; a.Cout = c; a.Ho = H; a.Wo = W; a.k = 3; a.stride = 1; a.pad = 1;
-      DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+      DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
     }
     for (int l = 0; l < 4; ++l) {
       const dpmn_cmm_stage& s = d->enc[br][l];
@@ -1009,7 +1028,7 @@ int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, f
         a.w = s.conv_a_w; a.bias = s.conv_a_b; a.out = w.mid[br][l];
         a.B = B; a.Cin = ch_o[l]; a.H = hi; a.W = wi; a.Cout = ch_o[l]; a.Ho = ho; a.Wo = wo;
         a.k = 4; a.stride = 2; a.pad = 3; a.dil = 2;
-        DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+        DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
       }
       DPMN_RUN(T_BN, bn_affine(d, s.bn_a, w.mid[br][l], ch_o[l], ho * wo, w.mid_sc[br][l], w.mid_sh[br][l], st), 1);
       {
@@ -1019,7 +1038,7 @@ int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, f
         a.w = s.conv_b_w; a.bias = s.conv_b_b; a.out = w.o[br][l + 1];
         a.B = B; a.Cin = ch_o[l]; a.H = ho; a.W = wo; a.Cout = ch_o[l + 1]; a.Ho = ho; a.Wo = wo;
         a.k = 3; a.stride = 1; a.pad = 1;
-        DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+        DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
       }
       DPMN_RUN(T_BN, bn_affine(d, s.bn_b, w.o[br][l + 1], ch_o[l + 1], ho * wo, w.o_sc[br][l + 1], w.o_sh[br][l + 1], st), 1);
     }
@@ -1031,7 +1050,7 @@ int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, f
       a.w = d->en6_w[br]; a.bias = d->en6_b[br]; a.out = w.o[br][5];
       a.B = B; a.Cin = ch_o[4]; a.H = hi; a.W = wi; a.Cout = ch_o[5]; a.Ho = hi / 2; a.Wo = wi / 2;
       a.k = 4; a.stride = 2; a.pad = 1;
-      DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+      DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
     }
   }
   // ---- SE gate (cmm.py:135-147)
@@ -1045,7 +1064,7 @@ int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, f
     a.w = d->de6_w; a.bias = d->de6_b; a.out = w.d6;
     a.B = B; a.Cin = 16 * c; a.H = hb; a.W = wb; a.Cout = 8 * c; a.Ho = 2 * hb; a.Wo = 2 * wb;
     a.k = 4; a.stride = 2; a.pad = 1; a.transposed = 1;
-    DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+    DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
     DPMN_RUN(T_BN, bn_affine(d, d->de6_bn, w.d6, 8 * c, 4 * hb * wb, w.d6_sc, w.d6_sh, st), 1);
   }
   const float* dprev = w.d6;
@@ -1068,7 +1087,7 @@ int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, f
       a.w = s.conv_a_w; a.bias = s.conv_a_b; a.out = w.dmid[i];
       a.B = B; a.Cin = dprev_ch + 2 * ch_o[lvl]; a.H = hi; a.W = wi; a.Cout = ch_d[i]; a.Ho = hi; a.Wo = wi;
       a.k = 3; a.stride = 1; a.pad = 1; a.transposed = 1;
-      DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+      DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
     }
     DPMN_RUN(T_BN, bn_affine(d, s.bn_a, w.dmid[i], ch_d[i], hi * wi, w.dmid_sc[i], w.dmid_sh[i], st), 1);
     {
@@ -1078,7 +1097,7 @@ int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, f
       a.w = s.conv_b_w; a.bias = s.conv_b_b; a.out = w.dout[i];
       a.B = B; a.Cin = ch_d[i]; a.H = hi; a.W = wi; a.Cout = ch_d[i]; a.Ho = 2 * hi; a.Wo = 2 * wi;
       a.k = 4; a.stride = 2; a.pad = 1; a.transposed = 1;
-      DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+      DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
     }
     DPMN_RUN(T_BN, bn_affine(d, s.bn_b, w.dout[i], ch_d[i], 4 * hi * wi, w.dout_sc[i], w.dout_sh[i], st), 1);
     dprev = w.dout[i]; dprev_sc = w.dout_sc[i]; dprev_sh = w.dout_sh[i]; dprev_ch = ch_d[i];
@@ -1093,9 +1112,25 @@ int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, f
     a.w = d->de1_w; a.bias = d->de1_b; a.out = out;
     a.B = B; a.Cin = 3 * c; a.H = H; a.W = W; a.Cout = d->c_img; a.Ho = H; a.Wo = W;
     a.k = 3; a.stride = 1; a.pad = 1; a.transposed = 1;
-    DPMN_RUN(T_CONV, launch_conv_simt(a, st), 1);
+    DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
   }
   return 0;
+}
+
+
+int dpmn_cmm_forward(const dpmn_cmm_desc* d, const float* x1, const float* x2, float* out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  int rc = check_cmm(d);
+  if (rc) return rc;
+  if (!x1 || !x2 || !out || !workspace) return DPMN_E_ARG;
+  if (d->precision != DPMN_PREC_F32 && !d->training) {        // eval in a 16-bit mode: the fused NHWC tensor-core path
+    for (int br = 0; br < 2; ++br) {
+      const long long bs = br == 0 ? d->x1_batch_stride : d->x2_batch_stride;
+      if (bs != 0 && bs != (long long)d->c_img * d->img_h * d->img_w) return DPMN_E_UNSUPPORTED;
+    }
+    return cmm_forward_tc(d, x1, x2, out, workspace, workspace_bytes, (cudaStream_t)stream);
+  }
+  return cmm_forward_struct(d, x1, x2, out, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,213 @@
+// CMM convolutions of the TRAINING path on the tcgen05 GEMM (16-bit modes)                    cmm.py:38-161
+//
+// The training forward / backward of the CMM keeps fp32 NCHW tensors (raw conv outputs + BatchNorm affines, see
+// api.cu cmm_forward_struct and api_bwd.inc), so its convs cannot use conv_tc.cu's NHWC TMA boxes.  Instead each conv
+// -- forward, data gradient (= the opposite kind of conv on the same weights) and weight gradient -- is lowered to the
+// NT GEMM of gemm_tc.cu through a 16-bit im2col matrix that one gather kernel writes:
+//     forward / dgrad   out_b (Cout, HoWo) = W16 (Cout, Kp) * col_b (HoWo, Kp)^T           per image, fp32 NCHW output
+//     wgrad             dW (Cout, Kp)     += dy16 (Cout, Ntot) * colT (Kp, Ntot)^T         split over pixel chunks
+// The gather is the B-operand loader of conv_simt_kernel verbatim: channel concat, the producer's BatchNorm affine
+// and the consumer's activation are applied on the way, transposed / strided / dilated geometry included (stride-2
+// transposed convs in plain gather form: the structural zeros cost tensor-core FLOPs, which are not the bottleneck).
+// K = Cin*k*k is padded to Kp (multiple of 16) with zeros on both operands.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dpmn {
+
+__device__ __forceinline__ float conv_gather(const ConvArgs& p, int k, int K, int kk, int b, int oy, int ox, long long HW) {
+  if (k >= K) return 0.f;
+  const int ci = k / kk;
+  const int tap = k - ci * kk;
+  const int ky = tap / p.k, kx = tap - ky * p.k;
+  int iy, ix;
+  bool ok;
+  if (p.transposed) {
+    const int ty2 = oy + p.pad - ky * p.dil, tx2 = ox + p.pad - kx * p.dil;
+    ok = ty2 >= 0 && tx2 >= 0 && (ty2 % p.stride) == 0 && (tx2 % p.stride) == 0;
+    iy = ty2 / p.stride; ix = tx2 / p.stride;
+    ok = ok && iy < p.H && ix < p.W;
+  } else {
+    iy = oy * p.stride - p.pad + ky * p.dil;
+    ix = ox * p.stride - p.pad + kx * p.dil;
+    ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+  }
+  if (!ok) return 0.f;
+  int seg = 0, cl = ci;
+  if (p.n_seg > 1 && cl >= p.seg_ch[0]) {
+    cl -= p.seg_ch[0]; seg = 1;
+    if (p.n_seg > 2 && cl >= p.seg_ch[1]) { cl -= p.seg_ch[1]; seg = 2; }
+  }
+  float v = p.in[seg][((long long)b * p.seg_ch[seg] + cl) * HW + (long long)iy * p.W + ix];
+  if (p.in_scale[seg] != nullptr) v = fmaf(v, p.in_scale[seg][cl], p.in_shift[seg][cl]);
+  if (p.in_act == 1) v = v >= 0.f ? v : 0.2f * v;
+  else if (p.in_act == 2) v = fmaxf(v, 0.f);
+  return v;
+}
+
+// COLT = false: col[n][k] (row length Kp); a 32 (pixels) x 32 (k) tile is gathered with threads along pixels (coalesced
+// reads of the NCHW input) and written with threads along k (coalesced 16-bit rows).
+// COLT = true:  colT[k][n] (row length Npad): threads along pixels for both.
+template <typename T, bool COLT>
+__global__ void __launch_bounds__(256) im2col_kernel(ConvArgs p, T* __restrict__ col, int Kp, long long Npad) {
+  __shared__ float tile[32][33];
+  const int kk = p.k * p.k;
+  const int K = p.Cin * kk;
+  const int HoWo = p.Ho * p.Wo;
+  const long long Ntot = (long long)p.B * HoWo;
+  const long long HW = (long long)p.H * p.W;
+  const long long n0 = (long long)blockIdx.x * 32;
+  const int k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long n = n0 + tx;
+  int b = 0, oy = 0, ox = 0;
+  const bool n_ok = n < Ntot;
+  if (n_ok) {
+    b = (int)(n / HoWo);
+    const int r = (int)(n - (long long)b * HoWo);
+    oy = r / p.Wo; ox = r - oy * p.Wo;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty + 8 * i;
+    const float v = (n_ok && k < Kp) ? conv_gather(p, k, K, kk, b, oy, ox, HW) : 0.f;
+    if (COLT) {
+      if (k < Kp && n < Npad) col[(long long)k * Npad + n] = from_f32<T>(v);
+    } else {
+      tile[ty + 8 * i][tx] = v;
+    }
+  }
+  if (!COLT) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long nn = n0 + ty + 8 * i;
+      const int k = k0 + tx;
+      if (nn < Ntot && k < Kp) col[nn * Kp + k] = from_f32<T>(tile[tx][ty + 8 * i]);
+    }
+  }
+}
+
+// weights -> 16-bit (Cout, Kp) rows, k = ci*kk + tap, zero padded
+template <typename T>
+__global__ void stage_conv_weight_kernel(const float* __restrict__ w, T* __restrict__ dst, int Cout, int Cin, int kk,
+                                         int transposed, int Kp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Cout * Kp) return;
+  const int co = (int)(i / Kp), k = (int)(i - (long long)co * Kp);
+  float v = 0.f;
+  if (k < Cin * kk) {
+    const int ci = k / kk, tap = k - ci * kk;
+    v = transposed ? w[((long long)ci * Cout + co) * kk + tap] : w[(long long)co * Cin * kk + k];
+  }
+  dst[i] = from_f32<T>(v);
+}
+
+// dy (B, C, HW) fp32 -> (C, Npad) 16-bit, n = b*HW + r
+template <typename T>
+__global__ void nchw_to_cn_kernel(const float* __restrict__ src, T* __restrict__ dst, int B, int C, int HW, long long Npad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * C * HW;
+  if (i >= total) return;
+  const int r = (int)(i % HW);
+  const int c = (int)((i / HW) % C);
+  const int b = (int)(i / ((long long)HW * C));
+  dst[(long long)c * Npad + (long long)b * HW + r] = from_f32<T>(src[i]);
+}
+
+// dw (reference layout) += sum_s partial[s][co][k]
+__global__ void reduce_conv_partials_kernel(const float* __restrict__ partial, float* __restrict__ dw, int S, int Cout,
+                                            int Cin, int kk, int transposed, int Kp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = Cin * kk;
+  if (i >= (long long)Cout * K) return;
+  const int co = (int)(i / K), k = (int)(i - (long long)co * K);
+  float a = 0.f;
+  for (int s = 0; s < S; ++s) a += partial[((long long)s * Cout + co) * Kp + k];
+  const int ci = k / kk, tap = k - ci * kk;
+  const long long o = transposed ? ((long long)ci * Cout + co) * kk + tap : (long long)co * K + k;
+  dw[o] += a;
+}
+
+template <typename T>
+static int conv_tc_im2col_t(const ConvArgs& a, const ConvTcScratch& s, cudaStream_t st) {
+  const int kk = a.k * a.k, K = a.Cin * kk, Kp = (K + 15) / 16 * 16;
+  const int HoWo = a.Ho * a.Wo;
+  const long long Ntot = (long long)a.B * HoWo;
+  if ((size_t)Ntot * Kp * 2 > s.col_bytes || (size_t)a.Cout * Kp * 2 > s.w16_bytes) return -3;
+  stage_conv_weight_kernel<T><<<(unsigned)(((long long)a.Cout * Kp + 255) / 256), 256, 0, st>>>(a.w, (T*)s.w16, a.Cout, a.Cin, kk,
+                                                                                            a.transposed, Kp);
+  DPMN_LAUNCH_CHECK();
+  im2col_kernel<T, false><<<dim3((unsigned)((Ntot + 31) / 32), (Kp + 31) / 32), 256, 0, st>>>(a, (T*)s.col, Kp, Ntot);
+  DPMN_LAUNCH_CHECK();
+  GemmTcArgs g;
+  g.A = s.w16; g.a_bs = 0; g.lda = Kp; g.Bm = s.col; g.b_bs = (long long)HoWo * Kp; g.ldb = Kp; g.op_type = s.t;
+  g.C = a.out; g.c_bs = (long long)a.Cout * HoWo; g.ldc = HoWo; g.out_type = DT_F32;
+  g.M = a.Cout; g.N = HoWo; g.K = Kp; g.batch = a.B; g.bias = a.bias; g.bias_mode = a.bias ? 2 : 0;
+  return launch_gemm_tc(g, st);
+}
+
+bool conv_tc_im2col_ok(const ConvArgs& a) {
+  const int HoWo = a.Ho * a.Wo;
+  return HoWo % 8 == 0 && HoWo >= 16 && a.k <= 4;
+}
+
+int launch_conv_tc_im2col(const ConvArgs& a, const ConvTcScratch& s, cudaStream_t st) {
+  if (s.t == DT_F16) return conv_tc_im2col_t<__half>(a, s, st);
+  if (s.t == DT_BF16) return conv_tc_im2col_t<__nv_bfloat16>(a, s, st);
+  return -1;
+}
+
+// pixel-chunk split of the weight gradient: S chunks of `chunk` pixels (multiple of 16), S * chunk == Ntot
+static bool wgrad_split(long long Ntot, long long cout_kp, size_t part_bytes, int& S, long long& chunk) {
+  if (Ntot % 16) return false;
+  long long s = Ntot / 512;
+  if (s > 64) s = 64;
+  const long long cap = (long long)(part_bytes / 4) / cout_kp;
+  if (s > cap) s = cap;
+  if (s < 1) s = 1;
+  while (s > 1 && (Ntot % (s * 16)) != 0) --s;
+  if ((size_t)s * cout_kp * 4 > part_bytes) return false;
+  S = (int)s; chunk = Ntot / s;
+  return true;
+}
+
+bool conv_wgrad_tc_im2col_ok(const ConvArgs& a, const ConvTcScratch& s) {
+  const int kk = a.k * a.k, Kp = (a.Cin * kk + 15) / 16 * 16;
+  const long long Ntot = (long long)a.B * a.Ho * a.Wo;
+  int S; long long chunk;
+  return a.k <= 4 && wgrad_split(Ntot, (long long)a.Cout * Kp, s.part_bytes, S, chunk) && (size_t)Ntot * Kp * 2 <= s.col_bytes &&
+         (size_t)Ntot * a.Cout * 2 <= s.dy16_bytes;
+}
+
+template <typename T>
+static int conv_wgrad_tc_im2col_t(const ConvArgs& a, const float* dy, float* dw, const ConvTcScratch& s, cudaStream_t st) {
+  const int kk = a.k * a.k, K = a.Cin * kk, Kp = (K + 15) / 16 * 16;
+  const int HoWo = a.Ho * a.Wo;
+  const long long Ntot = (long long)a.B * HoWo;
+  int S; long long chunk;
+  if (!wgrad_split(Ntot, (long long)a.Cout * Kp, s.part_bytes, S, chunk)) return -2;
+  const long long total = (long long)a.B * a.Cout * HoWo;
+  nchw_to_cn_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dy, (T*)s.dy16, a.B, a.Cout, HoWo, Ntot);
+  DPMN_LAUNCH_CHECK();
+  im2col_kernel<T, true><<<dim3((unsigned)((Ntot + 31) / 32), (Kp + 31) / 32), 256, 0, st>>>(a, (T*)s.col, Kp, Ntot);
+  DPMN_LAUNCH_CHECK();
+  GemmTcArgs g;       // partial[s] (Cout, Kp) = dy16[:, chunk s] * colT[:, chunk s]^T
+  g.A = s.dy16; g.a_bs = chunk; g.lda = (int)Ntot; g.Bm = s.col; g.b_bs = chunk; g.ldb = (int)Ntot; g.op_type = s.t;
+  g.C = s.part; g.c_bs = (long long)a.Cout * Kp; g.ldc = Kp; g.out_type = DT_F32;
+  g.M = a.Cout; g.N = Kp; g.K = (int)chunk; g.batch = S;
+  int rc = launch_gemm_tc(g, st);
+  if (rc) return rc;
+  reduce_conv_partials_kernel<<<(unsigned)(((long long)a.Cout * K + 255) / 256), 256, 0, st>>>(s.part, dw, S, a.Cout, a.Cin, kk,
+                                                                                          a.transposed, Kp);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_conv_wgrad_tc_im2col(const ConvArgs& a, const float* dy, float* dw, const ConvTcScratch& s, cudaStream_t st) {
+  if (s.t == DT_F16) return conv_wgrad_tc_im2col_t<__half>(a, dy, dw, s, st);
+  if (s.t == DT_BF16) return conv_wgrad_tc_im2col_t<__nv_bfloat16>(a, dy, dw, s, st);
+  return -1;
+}
+
+}  // namespace dpmn

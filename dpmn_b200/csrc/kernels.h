@@ -258,6 +258,19 @@ int launch_bn_affine(const float* x, int B, int C, int HW, const float* w, const
 int launch_se_gate(const float* z1, const float* z2, float* z, const float* fc1_w, const float* fc1_b,
                    const float* fc2_w, const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st);
 
+// ---- CMM training-path convs on the tcgen05 GEMM via a 16-bit im2col (cmm_im2col.cu) -----------------------------
+struct ConvTcScratch {
+  DType t = DT_F16;
+  void* col = nullptr; size_t col_bytes = 0;      // im2col matrix
+  void* w16 = nullptr; size_t w16_bytes = 0;      // staged (Cout, Kp) weights
+  void* dy16 = nullptr; size_t dy16_bytes = 0;    // (Cout, Ntot) output gradient
+  float* part = nullptr; size_t part_bytes = 0;   // split-K partials of the weight gradient
+};
+bool conv_tc_im2col_ok(const ConvArgs& a);
+int launch_conv_tc_im2col(const ConvArgs& a, const ConvTcScratch& s, cudaStream_t st);               // same contract as launch_conv_simt
+bool conv_wgrad_tc_im2col_ok(const ConvArgs& a, const ConvTcScratch& s);
+int launch_conv_wgrad_tc_im2col(const ConvArgs& a, const float* dy, float* dw, const ConvTcScratch& s, cudaStream_t st);
+
 // ---- CMM backward kernels (cmm_bwd.cu) ------------------------------------------------------------------
 // weight gradient of the conv described by `a` (the FORWARD ConvArgs): dw += dy (x) gather(inputs); dy (B, Cout, Ho, Wo)
 int launch_conv_wgrad_simt(const ConvArgs& a, const float* dy, float* dw, cudaStream_t st);

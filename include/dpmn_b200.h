@@ -154,9 +154,11 @@ typedef struct dpmn_cmm_desc {
   int32_t flags;                              /* DPMN_CMM_* bits, 0 by default */
 } dpmn_cmm_desc;
 
-/* dpmn_cmm_backward only: `workspace` is the buffer a dpmn_cmm_forward call with precision DPMN_PREC_F32, the same
- * descriptor (training flag included) and the same x1 / x2 has just filled, and nothing has written to it since --
- * the backward then skips its internal forward recompute.  The buffer must have dpmn_cmm_backward_workspace_bytes(). */
+/* dpmn_cmm_backward only: `workspace` is the buffer a dpmn_cmm_forward call with precision DPMN_PREC_F32 or with
+ * training == 1 (i.e. the fp32-structured forward that keeps raw conv outputs and BatchNorm affines; in the 16-bit modes
+ * its convs run on tcgen05 through a 16-bit im2col), the same descriptor and the same x1 / x2 has just filled, and nothing
+ * has written to it since -- the backward then skips its internal forward recompute.  The buffer must have
+ * dpmn_cmm_backward_workspace_bytes(). */
 #define DPMN_CMM_WORKSPACE_HOLDS_FORWARD 1
 
 const char *dpmn_version(void);

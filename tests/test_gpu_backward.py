@@ -260,3 +260,37 @@ def test_pgrm_backward_tensor_core_gemms(precision, l2_tol, cos_min):
         if not (l2 < l2_tol and cos > cos_min):
             bad.append((l2, cos, key[2:]))
     assert n > 60 and not bad, sorted(bad, reverse=True)[:10]
+
+
+@pytest.mark.parametrize("name", ["cmm_c8_train_grad", "cmm_c16_train_grad", "cmm_c8_eval_grad"])
+def test_cmm_backward_tensor_core_convs(name):
+    """fp16 mode: the convs of the CMM's fp32-structured forward (train-mode BatchNorm), their data gradients and their
+    weight gradients run on the tcgen05 GEMM through a 16-bit im2col (cmm_im2col.cu).  Flip-tolerant metric (the 16-bit
+    forward moves pre-activations past 0 for a few ReLU / LeakyReLU inputs): relative L2 and cosine per tensor."""
+    z, meta = load_golden(name)
+    P, x1, x2 = cmm_case(meta)
+    m, _ = build_cmm(meta, "cuda", precision="fp16")
+    dev = torch.device("cuda")
+    a = torch.from_numpy(x1).to(dev).requires_grad_(True)
+    b = torch.from_numpy(x2).to(dev).requires_grad_(True)
+    y = m(a, b)
+    assert rel_err(y.detach().cpu().numpy(), z["out"]) < 2e-3
+    (y * torch.from_numpy(grad_seed_out(meta["seed"], meta["B"])).to(dev)).sum().backward()
+    grads = {k: p.grad.cpu().numpy() for k, p in m.named_parameters() if p.grad is not None}
+    grads["x1"], grads["x2"] = a.grad.cpu().numpy(), b.grad.cpu().numpy()
+    n, bad = 0, []
+    for key in z.files:
+        if not key.startswith("g:") or key[2:] not in grads:
+            continue
+        name_ = key[2:]
+        full = meta["full"] or name_ in ("x1", "x2")
+        want = z[key].astype(np.float64).ravel()
+        got = golden_grad_view(grads[name_], full).astype(np.float64).ravel()
+        if np.abs(want).max() < NOISE_FLOOR:
+            continue
+        l2 = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+        cos = float(np.dot(got, want) / (np.linalg.norm(got) * np.linalg.norm(want)))
+        n += 1
+        if not (l2 < 5e-2 and cos > 0.998):
+            bad.append((l2, cos, name_))
+    assert n > 40 and not bad, sorted(bad, reverse=True)[:10]

@@ -15,21 +15,25 @@
 
 namespace dpmn {
 
-__device__ __forceinline__ float conv_gather(const ConvArgs& p, int k, int K, int kk, int b, int oy, int ox, long long HW) {
+// KS = kernel size (3 or 4) as a template parameter: k -> (ci, ky, kx) becomes multiply-shift; strides are 1 or 2.
+template <int KS>
+__device__ __forceinline__ float conv_gather(const ConvArgs& p, int k, int K, int b, int oy, int ox, long long HW) {
+  constexpr int kk = KS * KS;
   if (k >= K) return 0.f;
   const int ci = k / kk;
   const int tap = k - ci * kk;
-  const int ky = tap / p.k, kx = tap - ky * p.k;
+  const int ky = tap / KS, kx = tap - ky * KS;
+  const int sh = p.stride >> 1;                       // stride 1 -> 0, stride 2 -> 1
   int iy, ix;
   bool ok;
   if (p.transposed) {
     const int ty2 = oy + p.pad - ky * p.dil, tx2 = ox + p.pad - kx * p.dil;
-    ok = ty2 >= 0 && tx2 >= 0 && (ty2 % p.stride) == 0 && (tx2 % p.stride) == 0;
-    iy = ty2 / p.stride; ix = tx2 / p.stride;
+    ok = ty2 >= 0 && tx2 >= 0 && ((ty2 | tx2) & sh) == 0;
+    iy = ty2 >> sh; ix = tx2 >> sh;
     ok = ok && iy < p.H && ix < p.W;
   } else {
-    iy = oy * p.stride - p.pad + ky * p.dil;
-    ix = ox * p.stride - p.pad + kx * p.dil;
+    iy = (oy << sh) - p.pad + ky * p.dil;
+    ix = (ox << sh) - p.pad + kx * p.dil;
     ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
   }
   if (!ok) return 0.f;
@@ -45,19 +49,20 @@ __device__ __forceinline__ float conv_gather(const ConvArgs& p, int k, int K, in
   return v;
 }
 
-// COLT = false: col[n][k] (row length Kp); a 32 (pixels) x 32 (k) tile is gathered with threads along pixels (coalesced
+// COLT = false: col[n][k] (row length Kp); 32 (pixels) x 32 (k) tiles are gathered with threads along pixels (coalesced
 // reads of the NCHW input) and written with threads along k (coalesced 16-bit rows).
 // COLT = true:  colT[k][n] (row length Npad): threads along pixels for both.
-template <typename T, bool COLT>
+// A CTA walks IM_KT consecutive k-tiles for its 32 pixels, so the pixel -> (image, y, x) decode is paid once.
+constexpr int IM_KT = 8;
+
+template <typename T, bool COLT, int KS>
 __global__ void __launch_bounds__(256) im2col_kernel(ConvArgs p, T* __restrict__ col, int Kp, long long Npad) {
   __shared__ float tile[32][33];
-  const int kk = p.k * p.k;
-  const int K = p.Cin * kk;
+  const int K = p.Cin * KS * KS;
   const int HoWo = p.Ho * p.Wo;
   const long long Ntot = (long long)p.B * HoWo;
   const long long HW = (long long)p.H * p.W;
   const long long n0 = (long long)blockIdx.x * 32;
-  const int k0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long n = n0 + tx;
   int b = 0, oy = 0, ox = 0;
@@ -67,25 +72,40 @@ __global__ void __launch_bounds__(256) im2col_kernel(ConvArgs p, T* __restrict__
     const int r = (int)(n - (long long)b * HoWo);
     oy = r / p.Wo; ox = r - oy * p.Wo;
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int k = k0 + ty + 8 * i;
-    const float v = (n_ok && k < Kp) ? conv_gather(p, k, K, kk, b, oy, ox, HW) : 0.f;
-    if (COLT) {
-      if (k < Kp && n < Npad) col[(long long)k * Npad + n] = from_f32<T>(v);
-    } else {
-      tile[ty + 8 * i][tx] = v;
-    }
-  }
-  if (!COLT) {
-    __syncthreads();
+  for (int kt = 0; kt < IM_KT; ++kt) {
+    const int k0 = (blockIdx.y * IM_KT + kt) * 32;
+    if (k0 >= Kp) break;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const long long nn = n0 + ty + 8 * i;
-      const int k = k0 + tx;
-      if (nn < Ntot && k < Kp) col[nn * Kp + k] = from_f32<T>(tile[tx][ty + 8 * i]);
+      const int k = k0 + ty + 8 * i;
+      const float v = (n_ok && k < Kp) ? conv_gather<KS>(p, k, K, b, oy, ox, HW) : 0.f;
+      if (COLT) {
+        if (k < Kp && n < Npad) col[(long long)k * Npad + n] = from_f32<T>(v);
+      } else {
+        tile[ty + 8 * i][tx] = v;
+      }
+    }
+    if (!COLT) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long nn = n0 + ty + 8 * i;
+        const int k = k0 + tx;
+        if (nn < Ntot && k < Kp) col[nn * Kp + k] = from_f32<T>(tile[tx][ty + 8 * i]);
+      }
+      __syncthreads();
     }
   }
+}
+
+template <typename T, bool COLT>
+static int launch_im2col(const ConvArgs& a, T* col, int Kp, long long Ntot, cudaStream_t st) {
+  const dim3 grid((unsigned)((Ntot + 31) / 32), (Kp + 32 * IM_KT - 1) / (32 * IM_KT));
+  if (a.k == 3) im2col_kernel<T, COLT, 3><<<grid, 256, 0, st>>>(a, col, Kp, Ntot);
+  else if (a.k == 4) im2col_kernel<T, COLT, 4><<<grid, 256, 0, st>>>(a, col, Kp, Ntot);
+  else return -2;
+  DPMN_LAUNCH_CHECK();
+  return 0;
 }
 
 // weights -> 16-bit (Cout, Kp) rows, k = ci*kk + tap, zero padded
@@ -138,8 +158,10 @@ static int conv_tc_im2col_t(const ConvArgs& a, const ConvTcScratch& s, cudaStrea
   stage_conv_weight_kernel<T><<<(unsigned)(((long long)a.Cout * Kp + 255) / 256), 256, 0, st>>>(a.w, (T*)s.w16, a.Cout, a.Cin, kk,
                                                                                             a.transposed, Kp);
   DPMN_LAUNCH_CHECK();
-  im2col_kernel<T, false><<<dim3((unsigned)((Ntot + 31) / 32), (Kp + 31) / 32), 256, 0, st>>>(a, (T*)s.col, Kp, Ntot);
-  DPMN_LAUNCH_CHECK();
+  {
+    const int rc = launch_im2col<T, false>(a, (T*)s.col, Kp, Ntot, st);
+    if (rc) return rc;
+  }
   GemmTcArgs g;
   g.A = s.w16; g.a_bs = 0; g.lda = Kp; g.Bm = s.col; g.b_bs = (long long)HoWo * Kp; g.ldb = Kp; g.op_type = s.t;
   g.C = a.out; g.c_bs = (long long)a.Cout * HoWo; g.ldc = HoWo; g.out_type = DT_F32;
@@ -149,7 +171,7 @@ static int conv_tc_im2col_t(const ConvArgs& a, const ConvTcScratch& s, cudaStrea
 
 bool conv_tc_im2col_ok(const ConvArgs& a) {
   const int HoWo = a.Ho * a.Wo;
-  return HoWo % 8 == 0 && HoWo >= 16 && a.k <= 4;
+  return HoWo % 8 == 0 && HoWo >= 16 && (a.k == 3 || a.k == 4) && (a.stride == 1 || a.stride == 2);
 }
 
 int launch_conv_tc_im2col(const ConvArgs& a, const ConvTcScratch& s, cudaStream_t st) {
@@ -176,7 +198,7 @@ bool conv_wgrad_tc_im2col_ok(const ConvArgs& a, const ConvTcScratch& s) {
   const int kk = a.k * a.k, Kp = (a.Cin * kk + 15) / 16 * 16;
   const long long Ntot = (long long)a.B * a.Ho * a.Wo;
   int S; long long chunk;
-  return a.k <= 4 && wgrad_split(Ntot, (long long)a.Cout * Kp, s.part_bytes, S, chunk) && (size_t)Ntot * Kp * 2 <= s.col_bytes &&
+  return (a.k == 3 || a.k == 4) && (a.stride == 1 || a.stride == 2) && wgrad_split(Ntot, (long long)a.Cout * Kp, s.part_bytes, S, chunk) && (size_t)Ntot * Kp * 2 <= s.col_bytes &&
          (size_t)Ntot * a.Cout * 2 <= s.dy16_bytes;
 }
 
@@ -190,8 +212,10 @@ static int conv_wgrad_tc_im2col_t(const ConvArgs& a, const float* dy, float* dw,
   const long long total = (long long)a.B * a.Cout * HoWo;
   nchw_to_cn_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dy, (T*)s.dy16, a.B, a.Cout, HoWo, Ntot);
   DPMN_LAUNCH_CHECK();
-  im2col_kernel<T, true><<<dim3((unsigned)((Ntot + 31) / 32), (Kp + 31) / 32), 256, 0, st>>>(a, (T*)s.col, Kp, Ntot);
-  DPMN_LAUNCH_CHECK();
+  {
+    const int rc = launch_im2col<T, true>(a, (T*)s.col, Kp, Ntot, st);
+    if (rc) return rc;
+  }
   GemmTcArgs g;       // partial[s] (Cout, Kp) = dy16[:, chunk s] * colT[:, chunk s]^T
   g.A = s.dy16; g.a_bs = chunk; g.lda = (int)Ntot; g.Bm = s.col; g.b_bs = chunk; g.ldb = (int)Ntot; g.op_type = s.t;
   g.C = s.part; g.c_bs = (long long)a.Cout * Kp; g.ldc = Kp; g.out_type = DT_F32;

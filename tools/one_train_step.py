@@ -13,7 +13,7 @@ from dpmn_b200.train import HotPathTrainer  # noqa: E402
 
 drop = float(sys.argv[1]) if len(sys.argv) > 1 else 0.1
 dev = torch.device("cuda:0")
-model = DPMNHotPath(precision="fp16", drop=drop, cmm_precision="fp32")
+model = DPMNHotPath(precision="fp16", drop=drop)
 pg, cm = bench.synth_weights(2)
 bench.load_weights(model, pg, cm)
 model = model.to(dev).train()

@@ -132,6 +132,9 @@ SYMBOLS = {
     "dpmn_gemm_nt": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
     "dpmn_gemm_nt_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "dpmn_mask_hash": (C.c_uint32, [C.c_uint64, C.c_uint32, C.c_uint64]),
+    "dpmn_image_loss": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _i32, _i32, _i32, _i32, C.c_float, C.c_float, C.c_float,
+                                  _vp, _vp, _vp]),
+    "dpmn_to_mask": (C.c_int, [_vp, C.c_int64, _vp, _i32, _i32, _i32, _vp]),
     "dpmn_pgrm_backward_workspace_bytes": (_sz, [C.POINTER(PgrmDesc)]),
     "dpmn_pgrm_backward": (C.c_int, [C.POINTER(PgrmDesc), _vp, _vp, _vp, C.POINTER(PgrmGrads), _vp, _sz, _vp]),
     "dpmn_cmm_backward_workspace_bytes": (_sz, [C.POINTER(CmmDesc)]),

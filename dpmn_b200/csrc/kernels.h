@@ -258,6 +258,13 @@ int launch_bn_affine(const float* x, int B, int C, int HW, const float* w, const
 int launch_se_gate(const float* z1, const float* z2, float* z, const float* fc1_w, const float* fc1_b,
                    const float* fc2_w, const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st);
 
+// ---- neighbours of the hot path (loss_mask.cu) ------------------------------------------------------------------
+// loss[0] += scale * ImageLoss(out, target); d_out (dense (B,C,H,W), may be nullptr) = scale * d ImageLoss / d out
+int launch_image_loss(const float* out, long long out_bs, const float* tgt, long long tgt_bs, int B, int C, int H, int W,
+                      float w_mse, float w_gp, float scale, float* loss, float* d_out, cudaStream_t st);
+// toMask (utils/util.py:27-35) per image: (B,3,H,W) in [0,1] -> inverted binary luma mask on 3 channels, dense
+int launch_to_mask(const float* img, long long img_bs, float* mask, int B, int H, int W, cudaStream_t st);
+
 // ---- CMM training-path convs on the tcgen05 GEMM via a 16-bit im2col (cmm_im2col.cu) -----------------------------
 struct ConvTcScratch {
   DType t = DT_F16;

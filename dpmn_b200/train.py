@@ -4,8 +4,8 @@ Adam(lr 1e-3, betas (0.5, 0.999)) (interfaces/base.py:208-221).  Forward and bac
 libdpmn_b200 (dpmn_*_forward / dpmn_*_backward through the modules' autograd Functions); across ranks the ONLY
 collective is one flat all-reduce over the gradient bucket.
 
-Caller-side pieces kept in torch, exactly where the reference keeps them: the loss (ImageLoss, loss/image_loss.py:
-15-43 -- SURVEY 8f rank 1, not yet a kernel), clip_grad_norm_ and the Adam update.
+The image loss (ImageLoss, loss/image_loss.py:15-43 -- SURVEY 8f rank 1) is one CUDA kernel per term (value + gradient);
+caller-side pieces kept in torch, exactly where the reference keeps them: clip_grad_norm_ and the Adam update.
 Not reproduced: the recogniser / text-rendering loop that produces the priors (out of scope: priors are inputs)
 and the DistillModule terms."""
 from __future__ import annotations
@@ -13,26 +13,67 @@ from __future__ import annotations
 from typing import List, Sequence
 
 import torch
-import torch.nn.functional as F
 
 from .dist import FlatGradBucket
 from .pipeline import DPMNHotPath
 
 
-def gradient_map(x: torch.Tensor) -> torch.Tensor:
-    """GradientPriorLoss.gradient_map, loss/image_loss.py:33-43."""
-    w = x.shape[-1]
-    h = x.shape[-2]
-    r = F.pad(x, (0, 1, 0, 0))[:, :, :, 1:]
-    l = F.pad(x, (1, 0, 0, 0))[:, :, :, :w]
-    t = F.pad(x, (0, 0, 1, 0))[:, :, :h, :]
-    b = F.pad(x, (0, 0, 0, 1))[:, :, 1:, :]
-    return torch.sqrt(((r - l) * 0.5) ** 2 + ((t - b) * 0.5) ** 2 + 1e-6)
+class _ImageLoss(torch.autograd.Function):
+    """ImageLoss value and gradient in one kernel (dpmn_image_loss, csrc/loss_mask.cu)."""
+
+    @staticmethod
+    def forward(ctx, out, target, w_mse, w_gp):
+        from . import _lib
+        lib = _lib.load()
+        if not (out.is_cuda and target.is_cuda and out.dtype == torch.float32 and target.dtype == torch.float32):
+            raise RuntimeError("dpmn_b200.train.image_loss: fp32 CUDA tensors required (there is no CPU path)")
+        B, C, H, W = out.shape
+
+        def arg(t):
+            if t.stride(3) == 1 and t.stride(2) == W and t.stride(1) == H * W:
+                return t, (t.stride(0) if B > 1 else C * H * W)
+            t = t.contiguous()
+            return t, C * H * W
+        o, o_bs = arg(out)
+        t, t_bs = arg(target)
+        loss = torch.zeros((), dtype=torch.float32, device=out.device)
+        d_out = torch.empty((B, C, H, W), dtype=torch.float32, device=out.device) if out.requires_grad else None
+        with torch.cuda.device(out.device):
+            rc = lib.dpmn_image_loss(o.data_ptr(), o_bs, t.data_ptr(), t_bs, B, C, H, W, float(w_mse), float(w_gp), 1.0,
+                                     loss.data_ptr(), d_out.data_ptr() if d_out is not None else None,
+                                     torch.cuda.current_stream(out.device).cuda_stream)
+        _lib.check(rc, "dpmn_image_loss")
+        ctx.d_out = d_out
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d = ctx.d_out
+        ctx.d_out = None
+        return (d * g if d is not None else None), None, None, None
 
 
 def image_loss(out: torch.Tensor, target: torch.Tensor, weight=(1.0, 1.0)) -> torch.Tensor:
-    """ImageLoss(gradient=True, loss_weight=[1, 1]) as main.py constructs it: MSE + L1 of the gradient maps."""
-    return weight[0] * F.mse_loss(out, target) + weight[1] * F.l1_loss(gradient_map(out[:, :3]), gradient_map(target[:, :3]))
+    """ImageLoss(gradient=True, loss_weight=[1, 1]) as interfaces/base.py:132 constructs it: MSE + L1 of the gradient
+    maps (loss/image_loss.py:15-43), value and gradient from one CUDA kernel."""
+    return _ImageLoss.apply(out, target, weight[0], weight[1])
+
+
+def to_mask(images: torch.Tensor) -> torch.Tensor:
+    """toMask (utils/util.py:27-35) for a whole batch on the device: (B, 3, H, W) in [0, 1] -> (B, 3, H, W) in {0, 1}.
+    The reference loops over images through PIL on the host (interfaces/super_resolution.py:220-226)."""
+    from . import _lib
+    lib = _lib.load()
+    if not (images.is_cuda and images.dtype == torch.float32 and images.dim() == 4 and images.shape[1] == 3):
+        raise RuntimeError("dpmn_b200.train.to_mask: a (B, 3, H, W) fp32 CUDA tensor is required")
+    B, _, H, W = images.shape
+    x = images if (images.stride(3) == 1 and images.stride(2) == W and images.stride(1) == H * W) else images.contiguous()
+    bs = x.stride(0) if B > 1 else 3 * H * W
+    mask = torch.empty((B, 3, H, W), dtype=torch.float32, device=images.device)
+    with torch.cuda.device(images.device):
+        rc = lib.dpmn_to_mask(x.data_ptr(), bs, mask.data_ptr(), B, H, W, torch.cuda.current_stream(images.device).cuda_stream)
+    _lib.check(rc, "dpmn_to_mask")
+    return mask
 
 
 class HotPathTrainer:

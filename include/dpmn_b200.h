@@ -307,6 +307,21 @@ size_t dpmn_cmm_backward_workspace_bytes(const dpmn_cmm_desc *d);
 int dpmn_cmm_backward(const dpmn_cmm_desc *d, const float *x1, const float *x2, const float *d_out,
                       const dpmn_cmm_grads *grads, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- the callers' steps on either side of the hot path ------------------------------------------
+ * dpmn_image_loss   <- ImageLoss(gradient=True, loss_weight=[w_mse, w_gp]).forward + its autograd backward
+ *                      loss/image_loss.py:15-43; call sites interfaces/super_resolution.py:212,239,267
+ *   loss[0] += scale * (w_mse * MSE(out, target) + w_gp * L1(gradient_map(out[:, :3]), gradient_map(target[:, :3])));
+ *   d_out (dense (B, C, H, W), or NULL) = scale * d ImageLoss / d out.  out / target (B, C, H, W) fp32 with batch
+ *   strides in elements (0 = dense).  `loss` is accumulated: zero it once for a sum of several terms.
+ * dpmn_to_mask      <- toMask(img) per image, utils/util.py:27-35 (ToPILImage -> convert('L') -> threshold at the mean
+ *                      -> 0 / 255 inverted -> ToTensor -> repeat 3 channels); call site super_resolution.py:220-226
+ *   img (B, 3, H, W) fp32 in [0, 1] (batch stride in elements, 0 = dense) -> mask (B, 3, H, W) fp32 in {0, 1}, bit-exact. */
+int dpmn_image_loss(const float *out, int64_t out_batch_stride, const float *target, int64_t target_batch_stride,
+                    int32_t batch, int32_t chans, int32_t img_h, int32_t img_w, float w_mse, float w_gp, float scale,
+                    float *loss, float *d_out, void *stream);
+int dpmn_to_mask(const float *img, int64_t img_batch_stride, float *mask, int32_t batch, int32_t img_h, int32_t img_w,
+                 void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -254,3 +254,30 @@ def hot_path_forward(pgrm_params: List[Dict[str, torch.Tensor]], cmm_params, psn
             cascade = y
         outs.append(done[-1])
     return cmm_forward(cmm_params, outs[0], outs[1], training=False)
+
+
+# ---- the callers' steps on either side of the hot path ------------------------------------------------
+def gradient_map(x: torch.Tensor) -> torch.Tensor:
+    """GradientPriorLoss.gradient_map, loss/image_loss.py:33-43."""
+    w = x.shape[-1]
+    h = x.shape[-2]
+    r = F.pad(x, (0, 1, 0, 0))[:, :, :, 1:]
+    l = F.pad(x, (1, 0, 0, 0))[:, :, :, :w]
+    t = F.pad(x, (0, 0, 1, 0))[:, :, :h, :]
+    b = F.pad(x, (0, 0, 0, 1))[:, :, 1:, :]
+    return torch.sqrt(((r - l) * 0.5) ** 2 + ((t - b) * 0.5) ** 2 + 1e-6)
+
+
+def image_loss(out: torch.Tensor, target: torch.Tensor, weight=(1.0, 1.0)) -> torch.Tensor:
+    """ImageLoss(gradient=True, loss_weight=weight).forward, loss/image_loss.py:15-24."""
+    return weight[0] * F.mse_loss(out, target) + weight[1] * F.l1_loss(gradient_map(out[:, :3]), gradient_map(target[:, :3]))
+
+
+def to_mask(img):
+    """toMask, utils/util.py:27-35, for one (3, H, W) image in [0, 1]: numpy restatement (uint8 truncation, Pillow's
+    fixed-point ITU-R 601 luma, threshold at the mean luma, inverted, / 255, repeated on 3 channels)."""
+    import numpy as np
+    u8 = (np.asarray(img, dtype=np.float32) * np.float32(255)).astype(np.uint8).astype(np.int64)
+    luma = (u8[0] * 19595 + u8[1] * 38470 + u8[2] * 7471 + 0x8000) >> 16
+    m = np.where(luma * luma.size > luma.sum(), 0.0, 1.0).astype(np.float32)
+    return np.repeat(m[None], 3, axis=0)

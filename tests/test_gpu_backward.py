@@ -139,7 +139,7 @@ def test_hot_path_training_step_gradients_vs_oracle():
             cascade = y
         o_outs += done
     o_outs.append(torch_ref.cmm_forward(cmt, o_outs[2], o_outs[5], training=True))
-    o_loss = tr.loss(o_outs, torch.from_numpy(hr))
+    o_loss = sum(torch_ref.image_loss(o, torch.from_numpy(hr)[:, :3]) * 100 for o in o_outs) / len(o_outs)
     o_loss.backward()
     assert abs(float(loss.detach()) - float(o_loss.detach())) < 1e-4 * abs(float(o_loss.detach()))
     checked = 0
@@ -300,3 +300,25 @@ def test_cmm_backward_tensor_core_convs(name):
         if name_ in ("de_1.1.weight", "de_1.1.bias") and not l2 < 3e-3:
             bad.append((l2, cos, name_))
     assert n > 40 and not bad, sorted(bad, reverse=True)[:10]
+
+
+def test_image_loss_and_to_mask_kernels_match_reference():
+    """dpmn_image_loss (value + gradient in one pass) and dpmn_to_mask (bit-exact integer work) against
+    outputs of the unmodified reference functions."""
+    import os
+    from dpmn_b200.train import image_loss, to_mask
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "neighbors.npz"))
+    dev = torch.device("cuda")
+    for i in range(3):
+        o = torch.from_numpy(z[f"loss{i}_out"]).to(dev).requires_grad_(True)
+        t = torch.from_numpy(z[f"loss{i}_tgt"]).to(dev)
+        v = image_loss(o, t, tuple(float(x) for x in z[f"loss{i}_w"]))
+        (v * 100).backward()
+        assert abs(float(v.detach()) - float(z[f"loss{i}_val"])) < 2e-6 * abs(float(z[f"loss{i}_val"]))
+        assert rel_err(o.grad.cpu().numpy(), z[f"loss{i}_grad"]) < 1e-5
+    # channel-slice view of a 4-channel HR batch (images_hr[:, :3], super_resolution.py:212)
+    four = torch.cat([torch.from_numpy(z["loss0_tgt"]), torch.zeros(3, 1, 32, 128)], dim=1).to(dev)
+    o = torch.from_numpy(z["loss0_out"]).to(dev)
+    assert abs(float(image_loss(o, four[:, :3])) - float(z["loss0_val"])) < 2e-6 * abs(float(z["loss0_val"]))
+    got = to_mask(torch.from_numpy(z["mask_in"]).to(dev)).cpu().numpy()
+    assert np.array_equal(got, z["mask_out"])

@@ -95,13 +95,15 @@ int launch_image_loss(const float* out, long long out_bs, const float* tgt, long
 }
 
 // ---- toMask -------------------------------------------------------------------------------------------------------
-// ToPILImage: byte = (uint8)(x * 255) (truncation; inputs are in [0, 1]); convert('L'): (R*19595 + G*38470 + B*7471 +
+// ToPILImage: byte = (uint8)(x * 255) (truncation; wraps modulo 256 outside [0, 1]); convert('L'): (R*19595 + G*38470 + B*7471 +
 // 0x8000) >> 16; threshold = mean of L over the image; mask = L > thres ? 0 : 255; ToTensor: / 255 -> {0, 1}.
 // One CTA per image: pass 1 luma + integer sum, pass 2 compare L * n > sum (exact integer form of L > mean).
 __device__ __forceinline__ int luma_u8(const float* __restrict__ img, long long plane, int p) {
-  const int r = (int)(unsigned char)(img[p] * 255.0f);
-  const int g = (int)(unsigned char)(img[plane + p] * 255.0f);
-  const int b = (int)(unsigned char)(img[2 * plane + p] * 255.0f);
+  // torch's float -> uint8 cast goes through int64 (c10 TypeCast): out-of-range values wrap modulo 256, as they do
+  // in the reference when a cascade image leaves [0, 1]
+  const int r = (int)(unsigned char)(long long)(img[p] * 255.0f);
+  const int g = (int)(unsigned char)(long long)(img[plane + p] * 255.0f);
+  const int b = (int)(unsigned char)(long long)(img[2 * plane + p] * 255.0f);
   return (r * 19595 + g * 38470 + b * 7471 + 0x8000) >> 16;
 }
 

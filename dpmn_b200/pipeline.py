@@ -48,14 +48,18 @@ class DPMNHotPath(nn.Module):
 
     def forward_all(self, psn_out, priors_b1, priors_b2) -> List[torch.Tensor]:
         """All seven images the training loss looks at (super_resolution.py:212,239,267): the six PGRM outputs in
-        call order, then the CMM output."""
+        call order, then the CMM output.  priors_b2=None: the branch-2 priors are computed from the cascade images
+        with the device toMask, as the reference does on the host."""
+        from .train import to_mask
         def branch(first, count, priors):
             cascade = psn_out[:, :3, :]                   # channel-slice view, super_resolution.py:196
             done: List[torch.Tensor] = []
             for j in range(count):
                 k = first + j
+                # branch 2 without given priors: x_q = toMask(current cascade image), on the device (:218-226)
+                x_q = priors[j] if priors is not None else to_mask(cascade)
                 # residual_list = the earlier outputs of this branch (super_resolution.py:207,234)
-                y = self.pgrm[k](priors[j], cascade, done[:j])
+                y = self.pgrm[k](x_q, cascade, done[:j])
                 done.append(y)
                 cascade = y
             return done
@@ -89,7 +93,7 @@ class DPMNHotPath(nn.Module):
             st.wait_event(start)
             capturing = torch.cuda.is_current_stream_capturing()
             if not capturing:
-                for t in [psn_out] + list(priors):
+                for t in [psn_out] + list(priors or []):
                     t.record_stream(st)
             with torch.cuda.stream(st):
                 done = branch(first, count, priors)

@@ -60,6 +60,7 @@ def main():
     imgs[1] = np.round(imgs[1] * 255) / 255            # exactly representable bytes
     imgs[2, :, :, :64] *= 0.2                           # bimodal
     imgs[3] = 0.5                                       # constant image: nothing is above the mean
+    imgs[4] = r.uniform(-0.3, 1.4, (3, 32, 128)).astype(np.float32)   # a cascade image that left [0, 1]: uint8 wrap-around
     masks = np.concatenate([to_mask(torch.from_numpy(im)).numpy() for im in imgs], axis=0)
     save["mask_in"], save["mask_out"] = imgs, masks.astype(np.float32)
     np.savez_compressed(os.path.join(OUT, "neighbors.npz"), **save)

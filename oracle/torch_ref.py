@@ -277,7 +277,7 @@ def to_mask(img):
     """toMask, utils/util.py:27-35, for one (3, H, W) image in [0, 1]: numpy restatement (uint8 truncation, Pillow's
     fixed-point ITU-R 601 luma, threshold at the mean luma, inverted, / 255, repeated on 3 channels)."""
     import numpy as np
-    u8 = (np.asarray(img, dtype=np.float32) * np.float32(255)).astype(np.uint8).astype(np.int64)
+    u8 = ((np.asarray(img, dtype=np.float32) * np.float32(255)).astype(np.int64) & 255)    # torch: float -> int64 -> uint8 (wraps)
     luma = (u8[0] * 19595 + u8[1] * 38470 + u8[2] * 7471 + 0x8000) >> 16
     m = np.where(luma * luma.size > luma.sum(), 0.0, 1.0).astype(np.float32)
     return np.repeat(m[None], 3, axis=0)

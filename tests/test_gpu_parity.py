@@ -410,3 +410,32 @@ def test_graphed_hot_path_equals_sequential():
     assert len(got) == len(ref)
     for a, r in zip(got, ref):
         assert torch.equal(a, r)
+
+
+@pytest.mark.gpu
+def test_hot_path_with_device_to_mask_priors():
+    """priors_b2=None: branch-2 priors come from dpmn_to_mask on the cascade images (super_resolution.py:218-226);
+    must equal feeding the same masks explicitly, step by step."""
+    import bench
+    from dpmn_b200.pipeline import DPMNHotPath
+    from dpmn_b200.train import to_mask
+    dev = torch.device("cuda")
+    model = DPMNHotPath(precision="fp16")
+    pg, cm = bench.synth_weights(2)
+    bench.load_weights(model, pg, cm)
+    model = model.to(dev).eval()
+    psn, p1, _ = bench.synth_inputs(70, 2)
+    psn_t = torch.from_numpy(psn).to(dev)
+    p1_t = [torch.from_numpy(a).to(dev) for a in p1]
+    with torch.no_grad():
+        outs = model.forward_all(psn_t, p1_t, None)
+        # replay branch 2 by hand
+        cascade, done = psn_t[:, :3], []
+        for j in range(3):
+            y = model.pgrm[3 + j](to_mask(cascade), cascade, done[:j])
+            done.append(y)
+            cascade = y
+    for a, b in zip(outs[3:6], done):
+        assert torch.equal(a, b)
+    m = to_mask(psn_t[:, :3])
+    assert set(np.unique(m.cpu().numpy()).tolist()) <= {0.0, 1.0}

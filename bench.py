@@ -380,9 +380,9 @@ def run_ours(args):
 
     workload = WORKLOAD if not train else (
         "DPMN hot path TRAINING step: 6xPGRM cascade (drop / attn_drop / drop_path " + str(args.train_drop) + ") + CMM forward (train-mode BN), 7 image "
-        "losses, backward through dpmn_pgrm_backward / dpmn_cmm_backward (fp32), flat gradient all-reduce, per-module "
+        "losses + 4 DistillModule terms, backward through dpmn_pgrm_backward / dpmn_cmm_backward (fp32), flat gradient all-reduce, per-module "
         "clip 0.25, Adam; 16x64 -> 32x128, batch 48/GPU, synthetic PSN output / priors / HR (configs[2] without the "
-        "frozen TATT backbone, recognisers and distill modules)")
+        "frozen TATT backbone and recognisers)")
     line = {"metric": METRIC if not train else "SR images/sec (training step)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.precision],

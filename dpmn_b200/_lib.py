@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libdpmn_b200.so")
 
 MAX_GROUPS, MAX_MIX, MAX_BLOCKS = 4, 8, 2
 CMM_WORKSPACE_HOLDS_FORWARD = 1
+DISTILL_WORKSPACE_HOLDS_FORWARD = 1
 PGRM_WORKSPACE_HOLDS_FORWARD = 1
 PREC = {"fp32": 0, "f32": 0, "fp16": 1, "f16": 1, "bf16": 2}
 ERRORS = {-1: "DPMN_E_ARG (null pointer / inconsistent sizes)",
@@ -102,6 +103,18 @@ class CmmGrads(C.Structure):
                 ("de1_w", fp), ("de1_b", fp), ("x1", fp), ("x2", fp)]
 
 
+class DistillDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32), ("training", C.c_int32),
+                ("update_running_stats", C.c_int32), ("flags", C.c_int32), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+                ("deep_batch_stride", C.c_int64), ("shallow_batch_stride", C.c_int64),
+                ("conv_cat_w", fp), ("conv_cat_b", fp), ("bn_1", Bn), ("conv_w", fp), ("conv_b", fp), ("bn_2", Bn)]
+
+
+class DistillGrads(C.Structure):
+    _fields_ = [("conv_cat_w", fp), ("conv_cat_b", fp), ("bn_1", BnGrads), ("conv_w", fp), ("conv_b", fp), ("bn_2", BnGrads),
+                ("x_deep", fp), ("x_shallow", fp)]
+
+
 # every symbol include/dpmn_b200.h declares: (restype, argtypes)
 _i32, _sz, _vp = C.c_int32, C.c_size_t, C.c_void_p
 SYMBOLS = {
@@ -135,6 +148,9 @@ SYMBOLS = {
     "dpmn_image_loss": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _i32, _i32, _i32, _i32, C.c_float, C.c_float, C.c_float,
                                   _vp, _vp, _vp]),
     "dpmn_to_mask": (C.c_int, [_vp, C.c_int64, _vp, _i32, _i32, _i32, _vp]),
+    "dpmn_distill_workspace_bytes": (_sz, [C.POINTER(DistillDesc)]),
+    "dpmn_distill_forward": (C.c_int, [C.POINTER(DistillDesc), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dpmn_distill_backward": (C.c_int, [C.POINTER(DistillDesc), _vp, _vp, _vp, _vp, C.POINTER(DistillGrads), _vp, _sz, _vp]),
     "dpmn_pgrm_backward_workspace_bytes": (_sz, [C.POINTER(PgrmDesc)]),
     "dpmn_pgrm_backward": (C.c_int, [C.POINTER(PgrmDesc), _vp, _vp, _vp, C.POINTER(PgrmGrads), _vp, _sz, _vp]),
     "dpmn_cmm_backward_workspace_bytes": (_sz, [C.POINTER(CmmDesc)]),
@@ -158,7 +174,8 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    for which, st in enumerate((BlockWeights, PgrmDesc, Bn, CmmStage, CmmDesc, BlockGrads, PgrmGrads, CmmGrads)):
+    for which, st in enumerate((BlockWeights, PgrmDesc, Bn, CmmStage, CmmDesc, BlockGrads, PgrmGrads, CmmGrads,
+                                DistillDesc, DistillGrads)):
         got = lib.dpmn_abi_sizeof(which)
         if got != C.sizeof(st):
             raise RuntimeError(f"dpmn_b200: ABI mismatch for {st.__name__}: library {got} B, binding {C.sizeof(st)} B")

@@ -20,12 +20,12 @@ std::atomic<uint64_t> g_launches{0};
 // kernel launch, tagged by kernel class.  Off by default; never active inside a timed throughput region.
 enum KTag { T_PATCH_EMBED = 0, T_LAYERNORM, T_GEMM, T_WINDOW_ATTN, T_SK_GATE, T_DWCONV, T_HEAD, T_CONV, T_BN,
             T_SE_GATE, T_CONVERT, T_GEMM_TC, T_CONV_TC, T_PREP, T_CONV_STEM, T_ATTN_TC,
-            T_BWD_GEMM, T_BWD_GEMM_TC, T_BWD_MISC, T_BWD_LN, T_BWD_SK, T_BWD_ATTN, T_BWD_DWCONV, T_BWD_HEAD, T_BWD_EMBED, T_BWD_CONV, T_BWD_BN, T_LOSS,
+            T_BWD_GEMM, T_BWD_GEMM_TC, T_BWD_MISC, T_BWD_LN, T_BWD_SK, T_BWD_ATTN, T_BWD_DWCONV, T_BWD_HEAD, T_BWD_EMBED, T_BWD_CONV, T_BWD_BN, T_LOSS, T_DISTILL,
             T_COUNT };
 const char* const kTagNames[T_COUNT] = {"patch_embed", "layernorm", "gemm", "window_attn", "sk_gate",
                                         "dwconv", "head", "conv", "bn_affine", "se_gate", "convert", "gemm_tc", "conv_tc", "weight_prep", "conv_stem", "window_attn_tc",
                                         "bwd_gemm", "bwd_gemm_tc", "bwd_misc", "bwd_layernorm", "bwd_sk_gate", "bwd_window_attn", "bwd_dwconv", "bwd_head",
-                                        "bwd_patch_embed", "bwd_conv", "bwd_batchnorm", "loss_mask"};
+                                        "bwd_patch_embed", "bwd_conv", "bwd_batchnorm", "loss_mask", "distill"};
 struct ProfRec { int tag; int n; cudaEvent_t e0, e1; };
 bool g_prof = false;
 std::mutex g_prof_mu;
@@ -822,6 +822,8 @@ size_t dpmn_abi_sizeof(int32_t which) {
     case 5: return sizeof(dpmn_block_grads);
     case 6: return sizeof(dpmn_pgrm_grads);
     case 7: return sizeof(dpmn_cmm_grads);
+    case 8: return sizeof(dpmn_distill_desc);
+    case 9: return sizeof(dpmn_distill_grads);
   }
   return 0;
 }

@@ -265,6 +265,22 @@ int launch_image_loss(const float* out, long long out_bs, const float* tgt, long
 // toMask (utils/util.py:27-35) per image: (B,3,H,W) in [0,1] -> inverted binary luma mask on 3 channels, dense
 int launch_to_mask(const float* img, long long img_bs, float* mask, int B, int H, int W, cudaStream_t st);
 
+// ---- DistillModule (distill.cu; model/distill_module.py:4-31) --------------------------------------------------------
+struct DistillParams {
+  const float *conv_cat_w, *conv_cat_b, *bn1_w, *bn1_b; float *bn1_mean, *bn1_var;
+  const float *conv_w, *conv_b, *bn2_w, *bn2_b; float *bn2_mean, *bn2_var;
+};
+struct DistillGrads { float *conv_cat_w, *conv_cat_b, *bn1_w, *bn1_b, *conv_w, *conv_b, *bn2_w, *bn2_b, *x_deep, *x_shallow; };
+size_t distill_workspace_floats(int B, int H, int W);
+// conv outputs + BatchNorm statistics into ws; feature (B,3,H,W) = a; loss[0] += mean |a - s| (either may be nullptr)
+int launch_distill_forward(const float* xd, long long d_bs, const float* xs, long long s_bs, const DistillParams& w, int B,
+                           int H, int W, int training, int update_running, float eps, float momentum, float* feature,
+                           float* loss, float* ws, cudaStream_t st);
+// ws as the forward left it.  Parameter gradients accumulate; x_deep / x_shallow gradients are written (dense).
+int launch_distill_backward(const float* xd, long long d_bs, const float* xs, long long s_bs, const DistillParams& w, int B,
+                            int H, int W, int training, const float* d_loss, const float* d_feature, const DistillGrads& g,
+                            float* ws, cudaStream_t st);
+
 // ---- CMM training-path convs on the tcgen05 GEMM via a 16-bit im2col (cmm_im2col.cu) -----------------------------
 struct ConvTcScratch {
   DType t = DT_F16;

@@ -6,8 +6,9 @@ collective is one flat all-reduce over the gradient bucket.
 
 The image loss (ImageLoss, loss/image_loss.py:15-43 -- SURVEY 8f rank 1) is one CUDA kernel per term (value + gradient);
 caller-side pieces kept in torch, exactly where the reference keeps them: clip_grad_norm_ and the Adam update.
-Not reproduced: the recogniser / text-rendering loop that produces the priors (out of scope: priors are inputs)
-and the DistillModule terms."""
+The four DistillModule terms (model/distill_module.py; super_resolution.py:245-263 -- SURVEY 8f rank 3) run in
+libdpmn_b200 too (dpmn_b200.distill.DistillModule) and their parameters sit in the same gradient bucket.
+Not reproduced: the recogniser / text-rendering loop that produces the priors (out of scope: priors are inputs)."""
 from __future__ import annotations
 
 from typing import List, Sequence
@@ -77,16 +78,40 @@ def to_mask(images: torch.Tensor) -> torch.Tensor:
 
 
 class HotPathTrainer:
-    def __init__(self, model: DPMNHotPath, lr: float = 1e-3, betas=(0.5, 0.999), clip: float = 0.25, group=None):
+    def __init__(self, model: DPMNHotPath, lr: float = 1e-3, betas=(0.5, 0.999), clip: float = 0.25, group=None,
+                 distill: bool = True):
         self.model, self.clip, self.group = model, clip, group
         self.modules = list(model.pgrm) + [model.cmm]
-        self.bucket = FlatGradBucket(model.parameters())      # p.grad become views of ONE flat fp32 buffer
+        # one DistillModule per adjacent pair of cascade outputs of a branch (super_resolution.py:113-121)
+        self.distill: List[torch.nn.Module] = []
+        if distill:
+            from .distill import DistillModule
+            dev = next(model.parameters()).device
+            with torch.random.fork_rng(devices=[]):            # same initial replicas on every rank
+                torch.manual_seed(20240 + model.b1 * 16 + model.b2)
+                self.distill = [DistillModule().to(dev).train() for _ in range(model.b1 + model.b2 - 2)]
+        params = list(model.parameters()) + [p for m in self.distill for p in m.parameters()]   # base.py:208-221 order
+        self.bucket = FlatGradBucket(params)                   # p.grad become views of ONE flat fp32 buffer
         self.opt = torch.optim.Adam(self.bucket.params, lr=lr, betas=betas)
+
+    def distill_loss(self, outs: Sequence[torch.Tensor]) -> torch.Tensor:
+        """super_resolution.py:245-263: per branch, from the deepest cascade image back to the first; each module
+        compares its fused feature with the next shallower image and hands the feature on."""
+        b1, b2 = self.model.b1, self.model.b2
+        total = outs[0].new_zeros(())
+        for imgs, first in ((outs[:b1], 0), (outs[b1:b1 + b2], b1 - 1)):
+            feature = imgs[-1]
+            for k in range(len(imgs) - 1, 0, -1):
+                l, feature = self.distill[first + k - 1](feature, imgs[k - 1])      # distill_list[k-1] / [k+b1-2]
+                total = total + l.sum() * 100
+        return total
 
     def loss(self, outs: Sequence[torch.Tensor], hr: torch.Tensor) -> torch.Tensor:
         total = outs[0].new_zeros(())
         for o in outs:
             total = total + image_loss(o, hr[:, :3]) * 100        # super_resolution.py:212,239,267
+        if self.distill:
+            total = total + self.distill_loss(outs)                # :253,263
         return total / len(outs)                                   # :268
 
     def step(self, psn_out, priors_b1, priors_b2, hr) -> torch.Tensor:
@@ -97,7 +122,7 @@ class HotPathTrainer:
         loss.backward()
         if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.bucket.allreduce_mean(self.group)
-        for m in self.modules:                                     # super_resolution.py:270-275
+        for m in self.modules + self.distill:                      # super_resolution.py:270-275
             torch.nn.utils.clip_grad_norm_(m.parameters(), self.clip)
         self.opt.step()
         return loss.detach()

@@ -322,6 +322,42 @@ int dpmn_image_loss(const float *out, int64_t out_batch_stride, const float *tar
 int dpmn_to_mask(const float *img, int64_t img_batch_stride, float *mask, int32_t batch, int32_t img_h, int32_t img_w,
                  void *stream);
 
+
+/* ---- DistillModule ----------------------------------------------------------------------------
+ * dpmn_distill_forward  <- DistillModule.forward(x_deep, x_shallow), model/distill_module.py:18-31; call sites
+ *                          interfaces/super_resolution.py:245-263 (4 instances per training step)
+ *   a = ReLU(bn_1(conv_cat_feature(cat[x_deep, x_shallow])));  s = ReLU(bn_2(conv_feature(x_shallow)));
+ *   loss[0] += mean |a - s| (accumulated: zero it once);  feature (B, 3, H, W) dense = a.  Either output may be NULL.
+ *   x_deep / x_shallow (B, 3, H, W) fp32, batch strides in elements (0 = dense).  training = 1: batch statistics
+ *   (+ the momentum update of the running ones when update_running_stats); 0: running statistics.
+ * dpmn_distill_backward <- its autograd backward.  d_loss: DEVICE pointer to the scalar gradient of `loss` (NULL = 0);
+ *   d_feature (B, 3, H, W) dense gradient of `feature` (NULL = 0).  Parameter gradients accumulate into `grads`;
+ *   grads->x_deep / x_shallow (dense, or NULL) are written.  Stateless by default (recomputes the convs); with
+ *   DPMN_DISTILL_WORKSPACE_HOLDS_FORWARD in d->flags the workspace is the one dpmn_distill_forward has just filled for
+ *   the same descriptor and inputs.  Running statistics are never updated by the backward. */
+#define DPMN_DISTILL_WORKSPACE_HOLDS_FORWARD 1
+typedef struct dpmn_distill_desc {
+  int32_t batch, img_h, img_w;
+  int32_t training, update_running_stats, flags;
+  float bn_eps, bn_momentum;                      /* nn.BatchNorm2d defaults: 1e-5, 0.1 */
+  int64_t deep_batch_stride, shallow_batch_stride;
+  const float *conv_cat_w, *conv_cat_b;           /* conv_cat_feature (3, 6, 3, 3), (3) */
+  dpmn_bn bn_1;
+  const float *conv_w, *conv_b;                   /* conv_feature (3, 3, 3, 3), (3) */
+  dpmn_bn bn_2;
+} dpmn_distill_desc;
+typedef struct dpmn_distill_grads {
+  float *conv_cat_w, *conv_cat_b; dpmn_bn_grads bn_1;
+  float *conv_w, *conv_b; dpmn_bn_grads bn_2;
+  float *x_deep, *x_shallow;
+} dpmn_distill_grads;
+size_t dpmn_distill_workspace_bytes(const dpmn_distill_desc *d);
+int dpmn_distill_forward(const dpmn_distill_desc *d, const float *x_deep, const float *x_shallow, float *loss,
+                         float *feature, void *workspace, size_t workspace_bytes, void *stream);
+int dpmn_distill_backward(const dpmn_distill_desc *d, const float *x_deep, const float *x_shallow, const float *d_loss,
+                          const float *d_feature, const dpmn_distill_grads *grads, void *workspace, size_t workspace_bytes,
+                          void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -281,3 +281,37 @@ def to_mask(img):
     luma = (u8[0] * 19595 + u8[1] * 38470 + u8[2] * 7471 + 0x8000) >> 16
     m = np.where(luma * luma.size > luma.sum(), 0.0, 1.0).astype(np.float32)
     return np.repeat(m[None], 3, axis=0)
+
+
+def distill_forward(P: Dict[str, torch.Tensor], x_deep: torch.Tensor, x_shallow: torch.Tensor, training: bool = True,
+                    eps: float = 1e-5):
+    """DistillModule.forward, model/distill_module.py:18-31 -> (loss, feature_cat).  P: the module's state_dict
+    (conv_cat_feature.*, bn_1.*, conv_feature.*, bn_2.*).  training=True: batch statistics (biased variance), the
+    running buffers are not touched here (see distill_running_update)."""
+    def bn(x, stem):
+        if training:
+            mean = x.mean(dim=(0, 2, 3), keepdim=True)
+            var = ((x - mean) ** 2).mean(dim=(0, 2, 3), keepdim=True)
+        else:
+            mean = P[stem + ".running_mean"].view(1, -1, 1, 1)
+            var = P[stem + ".running_var"].view(1, -1, 1, 1)
+        return (x - mean) / torch.sqrt(var + eps) * P[stem + ".weight"].view(1, -1, 1, 1) + P[stem + ".bias"].view(1, -1, 1, 1)
+    u = F.conv2d(torch.cat([x_deep, x_shallow], dim=1), P["conv_cat_feature.weight"], P["conv_cat_feature.bias"], padding=1)
+    a = torch.relu(bn(u, "bn_1"))                                                                    # :19-22
+    v = F.conv2d(x_shallow, P["conv_feature.weight"], P["conv_feature.bias"], padding=1)
+    s = torch.relu(bn(v, "bn_2"))                                                                    # :24-26
+    return (a - s).abs().mean(), a                                                                   # :28,31
+
+
+def distill_running_update(P: Dict[str, torch.Tensor], x_deep, x_shallow, momentum: float = 0.1):
+    """What one train-mode forward does to the BatchNorm buffers (nn.BatchNorm2d: unbiased variance, momentum 0.1)."""
+    out = {}
+    u = F.conv2d(torch.cat([x_deep, x_shallow], dim=1), P["conv_cat_feature.weight"], P["conv_cat_feature.bias"], padding=1)
+    v = F.conv2d(x_shallow, P["conv_feature.weight"], P["conv_feature.bias"], padding=1)
+    for stem, x in (("bn_1", u), ("bn_2", v)):
+        n = x.numel() // x.shape[1]
+        mean = x.mean(dim=(0, 2, 3))
+        var = x.var(dim=(0, 2, 3), unbiased=False) * (n / (n - 1))
+        out[stem + ".running_mean"] = (1 - momentum) * P[stem + ".running_mean"] + momentum * mean
+        out[stem + ".running_var"] = (1 - momentum) * P[stem + ".running_var"] + momentum * var
+    return out

@@ -139,8 +139,24 @@ def test_hot_path_training_step_gradients_vs_oracle():
             cascade = y
         o_outs += done
     o_outs.append(torch_ref.cmm_forward(cmt, o_outs[2], o_outs[5], training=True))
-    o_loss = sum(torch_ref.image_loss(o, torch.from_numpy(hr)[:, :3]) * 100 for o in o_outs) / len(o_outs)
+    # the four DistillModule terms (super_resolution.py:245-263), with the trainer's own distill parameters
+    dps = [{k: (v.detach().cpu().clone().requires_grad_(True) if v.dtype == torch.float32 and "running" not in k
+                else v.detach().cpu().clone()) for k, v in m.state_dict().items()} for m in tr.distill]
+    o_distill = 0
+    for imgs, first in ((o_outs[:3], 0), (o_outs[3:6], 2)):
+        feat = imgs[-1]
+        for k in range(2, 0, -1):
+            l, feat = torch_ref.distill_forward(dps[first + k - 1], feat, imgs[k - 1], training=True)
+            o_distill = o_distill + l * 100
+    o_loss = (sum(torch_ref.image_loss(o, torch.from_numpy(hr)[:, :3]) * 100 for o in o_outs) + o_distill) / len(o_outs)
     o_loss.backward()
+    for j, m in enumerate(tr.distill):
+        for n, p in m.named_parameters():
+            a, b = p.grad.cpu().double().flatten(), dps[j][n].grad.double().flatten()
+            if n in ("conv_cat_feature.bias", "conv_feature.bias"):      # identically zero through a train-mode BatchNorm
+                assert float(a.abs().max()) < 1e-4 and float(b.abs().max()) < 1e-4, (j, n)
+                continue
+            assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < 3e-2, ("distill", j, n)
     assert abs(float(loss.detach()) - float(o_loss.detach())) < 1e-4 * abs(float(o_loss.detach()))
     checked = 0
     for k, m in enumerate(model.pgrm):

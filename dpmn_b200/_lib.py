@@ -148,6 +148,8 @@ SYMBOLS = {
     "dpmn_image_loss": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _i32, _i32, _i32, _i32, C.c_float, C.c_float, C.c_float,
                                   _vp, _vp, _vp]),
     "dpmn_to_mask": (C.c_int, [_vp, C.c_int64, _vp, _i32, _i32, _i32, _vp]),
+    "dpmn_crnn_input": (C.c_int, [_vp, C.c_int64, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dpmn_visionlan_input": (C.c_int, [_vp, C.c_int64, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dpmn_distill_workspace_bytes": (_sz, [C.POINTER(DistillDesc)]),
     "dpmn_distill_forward": (C.c_int, [C.POINTER(DistillDesc), _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dpmn_distill_backward": (C.c_int, [C.POINTER(DistillDesc), _vp, _vp, _vp, _vp, C.POINTER(DistillGrads), _vp, _sz, _vp]),

@@ -95,6 +95,40 @@ __global__ void __launch_bounds__(256) cmm_en1_kernel(const float* __restrict__ 
     float acc[2][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[0][j] = sb[cg * 8 + j]; acc[1][j] = acc[0][j]; }
+    if (c_img == 3) {
+      // all 36 input values first (independent predicated loads in flight together), then the 432 FMAs
+      float v[3][3][4];
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float* xc = x + ((long long)b * 3 + ci) * HW;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int y2 = yy + ky - 1;
+          const bool row_ok = y2 >= 0 && y2 < H;
+          const float* xr = xc + (long long)(row_ok ? y2 : yy) * W;
+          const float2 mid = *reinterpret_cast<const float2*>(xr + x0);
+          v[ci][ky][0] = (row_ok && x0 > 0) ? xr[x0 - 1] : 0.f;
+          v[ci][ky][1] = row_ok ? mid.x : 0.f;
+          v[ci][ky][2] = row_ok ? mid.y : 0.f;
+          v[ci][ky][3] = (row_ok && x0 + 2 < W) ? xr[x0 + 2] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4* wr = reinterpret_cast<const float4*>(sw + ((ci * 3 + ky) * 3 + kx) * cnum + cg * 8);
+            const float4 wa = wr[0], wb = wr[1];
+            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              acc[0][j] = fmaf(v[ci][ky][kx], wv[j], acc[0][j]);
+              acc[1][j] = fmaf(v[ci][ky][kx + 1], wv[j], acc[1][j]);
+            }
+          }
+    } else
     for (int ci = 0; ci < c_img; ++ci) {
       const float* xc = x + ((long long)b * c_img + ci) * HW;
 #pragma unroll

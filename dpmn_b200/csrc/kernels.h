@@ -265,6 +265,12 @@ int launch_image_loss(const float* out, long long out_bs, const float* tgt, long
 // toMask (utils/util.py:27-35) per image: (B,3,H,W) in [0,1] -> inverted binary luma mask on 3 channels, dense
 int launch_to_mask(const float* img, long long img_bs, float* mask, int B, int H, int W, cudaStream_t st);
 
+// ---- recogniser-input resizes (resize.cu; interfaces/base.py:419-425,473-478) ---------------------------------------
+// (B,3,H,W) -> (B,1,OH,OW): bicubic (ATen semantics) + luma.   (B,3,H,W) -> (B,3,OH,OW): uint8 truncation + OpenCV's
+// fixed-point bilinear + / 255, bit-exact.  Batch stride of img in elements; outputs dense.
+int launch_crnn_input(const float* img, long long img_bs, float* out, int B, int H, int W, int OH, int OW, cudaStream_t st);
+int launch_visionlan_input(const float* img, long long img_bs, float* out, int B, int H, int W, int OH, int OW, cudaStream_t st);
+
 // ---- DistillModule (distill.cu; model/distill_module.py:4-31) --------------------------------------------------------
 struct DistillParams {
   const float *conv_cat_w, *conv_cat_b, *bn1_w, *bn1_b; float *bn1_mean, *bn1_var;

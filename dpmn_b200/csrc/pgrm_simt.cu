@@ -262,6 +262,159 @@ __global__ void __launch_bounds__(128) patch_embed_tok_kernel(
   }
 }
 
+// Four lanes per token (C = 96, patch 2): lane `part` owns channels 32 j + 8 part + e (j < 3, e < 8), so every 16-bit
+// output leaves as one 16-byte store per (lane, j) and the four lanes of a token cover a 128-byte line of the fp32 row.
+// 4x the threads of the thread-per-token kernel at ~1/3 of its registers (occupancy was 16 % there); LayerNorm
+// statistics cost two shuffles per sum; with prior fusion each lane computes one of the token's 2x2 fused pixels.
+template <int C>
+__global__ void __launch_bounds__(256) patch_embed_tok4_kernel(
+    const float* __restrict__ x, long long x_bs, int in_ch, const float* __restrict__ fuse_w,
+    const float* __restrict__ fuse_b, const float* __restrict__ pe_w, const float* __restrict__ pe_b,
+    const float* __restrict__ ln_w, const float* __restrict__ ln_b, float* __restrict__ tokens, int B, int img_h,
+    int img_w, int n_tokens_total, PatchEmbedLn extra) {
+  static_assert(C == 96, "channel mapping assumes 3 groups of 32");
+  __shared__ __align__(16) float s_w[12 * C];      // [k][c]
+  __shared__ __align__(16) float s_aff[3 * C];     // pe bias, ln w, ln b
+  __shared__ float s_fw[54 + 3];
+  for (int i = threadIdx.x; i < 12 * C; i += blockDim.x) {
+    const int k = i / C, c = i - k * C;
+    s_w[i] = pe_w[c * 12 + k];
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_aff[i] = pe_b[i]; s_aff[C + i] = ln_w[i]; s_aff[2 * C + i] = ln_b[i]; }
+  if (fuse_w != nullptr)
+    for (int i = threadIdx.x; i < 57; i += blockDim.x) s_fw[i] = i < 54 ? fuse_w[i] : fuse_b[i - 54];
+  __syncthreads();
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int part = gtid & 3;
+  const bool live = (gtid >> 2) < n_tokens_total;
+  const int tok = live ? (gtid >> 2) : n_tokens_total - 1;      // dead lanes shadow the last token (shuffles stay full-warp)
+  const int gw = img_w / 2, gh = img_h / 2, L = gh * gw;
+  const int b = tok / L, t = tok - b * L;
+  const int ty = t / gw, tx = t - ty * gw;
+  const long long plane = (long long)img_h * img_w;
+  const float* xb = x + (long long)b * x_bs;
+  float in[12];   // (ch, dy, dx)
+  if (fuse_w == nullptr) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const float2 v = *reinterpret_cast<const float2*>(xb + ch * plane + (long long)(2 * ty + dy) * img_w + 2 * tx);
+        in[ch * 4 + dy * 2] = v.x; in[ch * 4 + dy * 2 + 1] = v.y;
+      }
+  } else {
+    // prior_fusion conv3x3 pad 1 (in_ch -> 3): this lane's pixel of the token is (2 ty + part / 2, 2 tx + part % 2)
+    const int py = 2 * ty + (part >> 1), px = 2 * tx + (part & 1);
+    float mine[3] = {s_fw[54], s_fw[55], s_fw[56]};
+    for (int ci = 0; ci < 2; ++ci) {
+      if (ci >= in_ch) break;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = py + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = px + kx - 1;
+          const float v = (yy >= 0 && yy < img_h && xx >= 0 && xx < img_w) ? xb[ci * plane + (long long)yy * img_w + xx] : 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) mine[ch] = fmaf(v, s_fw[(ch * in_ch + ci) * 9 + ky * 3 + kx], mine[ch]);
+        }
+      }
+    }
+    const int base_lane = (threadIdx.x & 31) & ~3;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) in[ch * 4 + q] = __shfl_sync(0xffffffffu, mine[ch], base_lane + q);
+  }
+  float o[24];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[j * 8 + e] = s_aff[32 * j + 8 * part + e];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float4 wa = *reinterpret_cast<const float4*>(&s_w[k * C + 32 * j + 8 * part]);
+      const float4 wb = *reinterpret_cast<const float4*>(&s_w[k * C + 32 * j + 8 * part + 4]);
+      float* oo = o + j * 8;
+      oo[0] = fmaf(in[k], wa.x, oo[0]); oo[1] = fmaf(in[k], wa.y, oo[1]);
+      oo[2] = fmaf(in[k], wa.z, oo[2]); oo[3] = fmaf(in[k], wa.w, oo[3]);
+      oo[4] = fmaf(in[k], wb.x, oo[4]); oo[5] = fmaf(in[k], wb.y, oo[5]);
+      oo[6] = fmaf(in[k], wb.z, oo[6]); oo[7] = fmaf(in[k], wb.w, oo[7]);
+    }
+  }
+  auto stats = [&](float& mu, float& rstd) {
+    float s1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 24; ++c) s1 += o[c];
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    mu = s1 * (1.0f / C);
+    float s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 24; ++c) { const float dlt = o[c] - mu; s2 = fmaf(dlt, dlt, s2); }
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+    rstd = rsqrtf(s2 * (1.0f / C) + 1e-5f);
+  };
+  float mu, rstd;
+  stats(mu, rstd);                                              // patch_embed.norm
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = 32 * j + 8 * part + e;
+      o[j * 8 + e] = (o[j * 8 + e] - mu) * rstd * s_aff[C + c] + s_aff[2 * C + c];
+    }
+  if (tokens != nullptr && live) {
+    float* dst = tokens + (long long)tok * C + 8 * part;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      *reinterpret_cast<float4*>(dst + 32 * j) = make_float4(o[j * 8], o[j * 8 + 1], o[j * 8 + 2], o[j * 8 + 3]);
+      *reinterpret_cast<float4*>(dst + 32 * j + 4) = make_float4(o[j * 8 + 4], o[j * 8 + 5], o[j * 8 + 6], o[j * 8 + 7]);
+    }
+  }
+  if (extra.count > 0) {
+    stats(mu, rstd);                                            // the consumers' own LayerNorms of the token
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {                               // static indices: `extra` stays in the constant bank
+      if (k >= extra.count) break;
+      const float* w = extra.w[k];
+      const float* bb = extra.b[k];
+      const long long base = (long long)tok * C + 8 * part;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + 32 * j + 8 * part));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + 32 * j + 8 * part + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bb + 32 * j + 8 * part));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bb + 32 * j + 8 * part + 4));
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = (o[j * 8 + e] - mu) * rstd * wv[e] + bv[e];
+        if (!live) continue;
+        if (extra.type == DT_F32) {
+          float* dst = reinterpret_cast<float*>(extra.out[k]) + base + 32 * j;
+          *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        } else if (extra.type == DT_F16) {
+          union { uint4 u; __half h[8]; } pk;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pk.h[e] = __float2half_rn(y[e]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(extra.out[k]) + base + 32 * j) = pk.u;
+        } else {
+          union { uint4 u; __nv_bfloat16 h[8]; } pk;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pk.h[e] = __float2bfloat16_rn(y[e]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(extra.out[k]) + base + 32 * j) = pk.u;
+        }
+      }
+    }
+  }
+}
+
 int launch_patch_embed(const float* x, long long x_bs, int in_ch, const float* fuse_w, const float* fuse_b,
                        const float* pe_w, const float* pe_b, const float* ln_w, const float* ln_b, float* tokens,
                        int B, int img_h, int img_w, int patch, int C, cudaStream_t st, const PatchEmbedLn* extra_in) {
@@ -271,8 +424,14 @@ int launch_patch_embed(const float* x, long long x_bs, int in_ch, const float* f
   if (C == 96 && patch == 2 && img_w % 2 == 0 && (x_bs % 2) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
       (in_ch == 3 || (in_ch == 2 && fuse_w != nullptr))) {
     const int total_tok = B * (img_h / 2) * (img_w / 2);
-    patch_embed_tok_kernel<96><<<(total_tok + 127) / 128, 128, 0, st>>>(x, x_bs, in_ch, fuse_w, fuse_b, pe_w, pe_b, ln_w,
-                                                                      ln_b, tokens, B, img_h, img_w, total_tok, extra);
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(extra.w[0]) | reinterpret_cast<uintptr_t>(extra.b[0]) |
+                            reinterpret_cast<uintptr_t>(extra.w[1]) | reinterpret_cast<uintptr_t>(extra.b[1])) % 16 == 0;
+    if (aligned16)
+      patch_embed_tok4_kernel<96><<<(total_tok * 4 + 255) / 256, 256, 0, st>>>(x, x_bs, in_ch, fuse_w, fuse_b, pe_w, pe_b, ln_w,
+                                                                               ln_b, tokens, B, img_h, img_w, total_tok, extra);
+    else
+      patch_embed_tok_kernel<96><<<(total_tok + 127) / 128, 128, 0, st>>>(x, x_bs, in_ch, fuse_w, fuse_b, pe_w, pe_b, ln_w,
+                                                                        ln_b, tokens, B, img_h, img_w, total_tok, extra);
     DPMN_LAUNCH_CHECK();
     return 0;
   }

@@ -77,6 +77,37 @@ def to_mask(images: torch.Tensor) -> torch.Tensor:
     return mask
 
 
+def _resize_call(fn_name: str, images: torch.Tensor, out_ch: int, out_hw):
+    from . import _lib
+    lib = _lib.load()
+    if not (images.is_cuda and images.dtype == torch.float32 and images.dim() == 4 and images.shape[1] == 3):
+        raise RuntimeError(f"dpmn_b200.train.{fn_name}: a (B, 3, H, W) fp32 CUDA tensor is required (there is no CPU path)")
+    B, _, H, W = images.shape
+    x = images if (images.stride(3) == 1 and images.stride(2) == W and images.stride(1) == H * W) else images.contiguous()
+    bs = x.stride(0) if B > 1 else 3 * H * W
+    out = torch.empty((B, out_ch, out_hw[0], out_hw[1]), dtype=torch.float32, device=images.device)
+    with torch.cuda.device(images.device):
+        rc = getattr(lib, fn_name)(x.data_ptr(), bs, out.data_ptr(), B, H, W, out_hw[0], out_hw[1],
+                                   torch.cuda.current_stream(images.device).cuda_stream)
+    _lib.check(rc, fn_name)
+    return out
+
+
+def parse_crnn_data(imgs_input: torch.Tensor) -> torch.Tensor:
+    """TextBase.parse_crnn_data (interfaces/base.py:419-425): bicubic resize to (32, 100) + luma in one kernel.
+    (B, 3, H, W) -> (B, 1, 32, 100).  Accepts the channel-slice view images[:, :3] of the call sites."""
+    return _resize_call("dpmn_crnn_input", imgs_input, 1, (32, 100))
+
+
+def parse_visionlan_data(imgs_input: torch.Tensor) -> torch.Tensor:
+    """TextBase.parse_visionlan_data (interfaces/base.py:473-478) for a whole batch on the device: (B, 3, H, W) in [0, 1]
+    -> (B, 3, 64, 256), bit-exact against the reference's per-image ToPILImage -> cv2.resize -> ToTensor round trip.  A
+    single (3, H, W) image (the reference's signature) gives (1, 3, 64, 256) like the reference."""
+    if imgs_input.dim() == 3:
+        imgs_input = imgs_input.unsqueeze(0)
+    return _resize_call("dpmn_visionlan_input", imgs_input, 3, (64, 256))
+
+
 class HotPathTrainer:
     def __init__(self, model: DPMNHotPath, lr: float = 1e-3, betas=(0.5, 0.999), clip: float = 0.25, group=None,
                  distill: bool = True):

@@ -323,6 +323,19 @@ int dpmn_to_mask(const float *img, int64_t img_batch_stride, float *mask, int32_
                  void *stream);
 
 
+/* ---- recogniser-input resizes (second half) ----------------------------------------------------
+ * dpmn_crnn_input      <- TextBase.parse_crnn_data(imgs), interfaces/base.py:419-425; call sites super_resolution.py:159,165
+ *   out (B, 1, out_h, out_w) = luma(F.interpolate(img, (out_h, out_w), mode='bicubic')), luma = 0.299 R + 0.587 G + 0.114 B.
+ *   The reference passes (32, 100).  fp32, within 5e-6 of torch's CPU result (summation order).
+ * dpmn_visionlan_input <- TextBase.parse_visionlan_data(img) for every image of a batch, interfaces/base.py:473-478; call
+ *   site super_resolution.py:177-178: ToPILImage -> cv2.resize(.., (out_w, out_h)) -> ToTensor.  The reference passes
+ *   (256, 64).  out (B, 3, out_h, out_w); integer arithmetic, bit-exact against OpenCV's uint8 INTER_LINEAR.
+ * img (B, 3, H, W) fp32, batch stride in elements (0 = dense). */
+int dpmn_crnn_input(const float *img, int64_t img_batch_stride, float *out, int32_t batch, int32_t img_h, int32_t img_w,
+                    int32_t out_h, int32_t out_w, void *stream);
+int dpmn_visionlan_input(const float *img, int64_t img_batch_stride, float *out, int32_t batch, int32_t img_h, int32_t img_w,
+                         int32_t out_h, int32_t out_w, void *stream);
+
 /* ---- DistillModule ----------------------------------------------------------------------------
  * dpmn_distill_forward  <- DistillModule.forward(x_deep, x_shallow), model/distill_module.py:18-31; call sites
  *                          interfaces/super_resolution.py:245-263 (4 instances per training step)

@@ -315,3 +315,63 @@ def distill_running_update(P: Dict[str, torch.Tensor], x_deep, x_shallow, moment
         out[stem + ".running_mean"] = (1 - momentum) * P[stem + ".running_mean"] + momentum * mean
         out[stem + ".running_var"] = (1 - momentum) * P[stem + ".running_var"] + momentum * var
     return out
+
+
+# ---- recogniser input resizes (interfaces/base.py:419-425,473-478) --------------------------------
+def _cubic_weights(t, A=-0.75):
+    """Keys cubic convolution coefficients as ATen's upsample_bicubic2d uses them (A = -0.75)."""
+    import numpy as np
+    def inner(x):
+        return ((A + 2) * x - (A + 3)) * x * x + 1
+    def outer(x):
+        return ((A * x - 5 * A) * x + 8 * A) * x - 4 * A
+    return np.stack([outer(t + 1), inner(t), inner(1 - t), outer(2 - t)], axis=-1)
+
+
+def parse_crnn_data(imgs, out_hw=(32, 100)):
+    """TextBase.parse_crnn_data, interfaces/base.py:419-425: F.interpolate(imgs, (32, 100), mode='bicubic')
+    (align_corners=False: src = (dst + 0.5) * in/out - 0.5, taps clamped to the image) then 0.299 R + 0.587 G + 0.114 B.
+    numpy restatement; imgs (B, 3, H, W) -> (B, 1, 32, 100)."""
+    import numpy as np
+    x = np.asarray(imgs, dtype=np.float32)
+    B, Ch, H, W = x.shape
+    oh, ow = out_hw
+    def axis(n_in, n_out):
+        src = (np.arange(n_out, dtype=np.float32) + np.float32(0.5)) * np.float32(n_in / n_out) - np.float32(0.5)
+        i0 = np.floor(src)
+        w = _cubic_weights((src - i0).astype(np.float32)).astype(np.float32)            # (n_out, 4)
+        idx = np.clip(i0.astype(np.int64)[:, None] + np.arange(-1, 3)[None, :], 0, n_in - 1)
+        return idx, w
+    iy, wy = axis(H, oh)
+    ix, wx = axis(W, ow)
+    rows = (x[:, :, :, ix] * wx[None, None, None]).sum(-1, dtype=np.float32)            # (B, C, H, ow)
+    out = (rows[:, :, iy, :] * wy[None, None, :, :, None]).sum(3, dtype=np.float32)     # (B, C, oh, ow)
+    return (np.float32(0.299) * out[:, 0:1] + np.float32(0.587) * out[:, 1:2] + np.float32(0.114) * out[:, 2:3]).astype(np.float32)
+
+
+def parse_visionlan_data(img, out_hw=(64, 256)):
+    """TextBase.parse_visionlan_data, interfaces/base.py:473-478, for one (3, H, W) image: ToPILImage (x * 255 truncated
+    to uint8) -> cv2.resize(..., (256, 64)) (INTER_LINEAR on uint8: OpenCV's 11-bit fixed-point bilinear) -> ToTensor
+    (/ 255) -> (1, 3, 64, 256).  Integer restatement, bit-exact against cv2 (opencv-python 4.13 in the build container)."""
+    import numpy as np
+    u8 = ((np.asarray(img, dtype=np.float32) * np.float32(255)).astype(np.int64) & 255)          # (3, H, W)
+    _, sh, sw = u8.shape
+    dh, dw = out_hw
+
+    def coefs(dn, sn, clamp):
+        scale = 1.0 / (dn / float(sn))
+        f = ((np.arange(dn) + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int64)
+        f = (f - s.astype(np.float32)).astype(np.float32)
+        if clamp:                              # columns: the weight collapses onto the border pixel
+            lo, hi = s < 0, s >= sn - 1
+            f[lo | hi] = 0
+            s[lo] = 0
+            s[hi] = sn - 1
+        return s, np.rint((np.float32(1) - f) * np.float32(2048)).astype(np.int64), np.rint(f * np.float32(2048)).astype(np.int64)
+    sx, a0, a1 = coefs(dw, sw, True)
+    sy, b0, b1 = coefs(dh, sh, False)           # rows: indices are clipped instead, the weights stay
+    rows = u8[:, :, sx] * a0 + u8[:, :, np.minimum(sx + 1, sw - 1)] * a1                         # (3, sh, dw), scale 2^11
+    r0, r1 = rows[:, np.clip(sy, 0, sh - 1)], rows[:, np.clip(sy + 1, 0, sh - 1)]
+    out = (((b0[None, :, None] * (r0 >> 4)) >> 16) + ((b1[None, :, None] * (r1 >> 4)) >> 16) + 2) >> 2
+    return (out.astype(np.float32) / np.float32(255))[None]

@@ -39,6 +39,17 @@ FLOPS_IMG = {"gemm": _PGRM_GEMM, "gemm_tc": _PGRM_GEMM,
              "conv": 4_459_069_440, "conv_tc": 4_459_069_440 - 14_155_776 * 2 - 42_467_328,   # minus stem / de_1 (own kernels)
              "total": 11_267_776_512}
 
+# algorithmic HBM bytes per image of the bandwidth-bound kernel classes in the 16-bit inference mode:
+# 16-bit activations (s = 2), fp32 residual stream (r = 4), weights excluded (L2-resident, < 0.6 MB per block).
+_L, _C, _HID = 1024, 96, 384
+BYTES_IMG = {
+    # per block: q (in, out), kv (in, 2 out), SK pooled pass (in), SK output GEMM (in, LN out) and fc2 (LN out) = 10 L*C*s;
+    # the two residual GEMMs read and write the fp32 stream = 4 L*C*r; fc1 out, pointwise in + out, fc2 in = 4 L*hid*s
+    "gemm_tc": 12 * (10 * _L * _C * 2 + 4 * _L * _C * 4 + 4 * _L * _HID * 2),
+    "window_attn_tc": 12 * 4 * _L * _C * 2,          # q, k, v in, out: SURVEY 8d
+    "dwconv": 12 * 2 * _L * _HID * 2,
+}
+
 
 def synth_inputs(seed, B):
     from oracle import inputs as gen
@@ -174,7 +185,7 @@ def run_ours(args):
         from dpmn_b200.train import HotPathTrainer
         trainer = HotPathTrainer(model)
 
-    B = BATCH
+    B = args.batch
     n_sets = 4   # rotate input sets; the per-step working set (workspaces ~0.7 GB) is far larger than the 126 MB L2
     host_sets, dev_sets = [], []
     for s in range(n_sets):
@@ -372,16 +383,29 @@ def run_ours(args):
                 "avg_launch_ms": dom_ms / max(1, prof[dom]["launches_per_step"]),
                 "whole_step_tflops": flops_img["total"] * B / (ms_step / 1e3) / 1e12,
                 "by_kernel_ms": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
+    if not train and dom in BYTES_IMG:
+        # The dominant class is bandwidth-bound by arithmetic intensity (FLOPs / algorithmic bytes below the ridge
+        # tensor_peak / hbm_peak): its roofline is the HBM one.  achieved = algorithmic bytes per launch / launch time.
+        hbm_peak = peaks.get("hbm_gbs", 6500.0)
+        ai = flops_img[dom] / BYTES_IMG[dom]
+        if ai < tensor_peak * 1e12 / (hbm_peak * 1e9):
+            gbs = BYTES_IMG[dom] * B / (dom_ms / 1e3) / 1e9
+            roofline.update({"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                             "peak_source": ("measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback"),
+                             "algorithmic_bytes_per_launch": BYTES_IMG[dom] * B / max(1, prof[dom]["launches_per_step"]),
+                             "arithmetic_intensity_flop_per_byte": ai,
+                             "tensor_view": {"achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                                             "frac": achieved / tensor_peak}})
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline and not train:
         v, sample, _, _ = cpu_port_throughput(budget_s=15.0)
         cpu = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
 
-    workload = WORKLOAD if not train else (
+    workload = WORKLOAD.replace("batch 48/GPU", f"batch {B}/GPU") if not train else (
         "DPMN hot path TRAINING step: 6xPGRM cascade (drop / attn_drop / drop_path " + str(args.train_drop) + ") + CMM forward (train-mode BN), 7 image "
         "losses + 4 DistillModule terms, backward through dpmn_pgrm_backward / dpmn_cmm_backward (fp32), flat gradient all-reduce, per-module "
-        "clip 0.25, Adam; 16x64 -> 32x128, batch 48/GPU, synthetic PSN output / priors / HR (configs[2] without the "
+        "clip 0.25, Adam; 16x64 -> 32x128, batch " + str(B) + "/GPU, synthetic PSN output / priors / HR (configs[2] without the "
         "frozen TATT backbone and recognisers)")
     line = {"metric": METRIC if not train else "SR images/sec (training step)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -408,6 +432,7 @@ def main():
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer = BASELINE configs[1] (the headline line); train = configs[2] training step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU per step (48 = configs[1]/[2]; 64 = configs[3])")
     ap.add_argument("--train-drop", type=float, default=0.1, help="drop / attn_drop / drop_path rate of --mode train")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

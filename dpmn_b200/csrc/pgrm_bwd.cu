@@ -365,10 +365,82 @@ __global__ void __launch_bounds__(256) dwconv_train_fwd_kernel(const float* __re
   }
 }
 
+// SIDE = 32 fast path of the two kernels around here: compile-time index arithmetic (the generic kernels spend a third of
+// their issue slots on runtime div / mod), 16 channels per CTA so that three CTAs share an SM, the input halo tile loaded
+// with 16-byte accesses, and -- in the backward -- erf evaluated ONCE per element of h1pre for both GELU(h) (weight
+// gradient) and GELU'(h) (data gradient), with the dropout hash evaluated once as well.
+constexpr int DWF_CH = 16;
+
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  g = x * cdf;
+  dg = fmaf(x, pdf, cdf);
+}
+
+template <int SIDE>
+__global__ void __launch_bounds__(256) dwconv_train_fwd_fast_kernel(const float* __restrict__ h1pre, float* __restrict__ dtpre,
+                                                                    float* __restrict__ dt, const float* __restrict__ w,
+                                                                    const float* __restrict__ bias, int hid, float p_drop,
+                                                                    unsigned long long seed, uint32_t site) {
+  constexpr int L = SIDE * SIDE, ROWS_IN = DWT_ROWS + 2, CSTRIDE = ROWS_IN * SIDE + 2;   // even stride: see the store below
+  __shared__ float sm[DWF_CH * CSTRIDE];
+  const int b = blockIdx.z, c0 = blockIdx.y * DWF_CH, y0 = blockIdx.x * DWT_ROWS;
+  const float* hb = h1pre + (long long)b * L * hid;
+  constexpr int VEC_ROW = SIDE / 4, N_VEC = DWF_CH * ROWS_IN * VEC_ROW;
+  for (int i = threadIdx.x; i < N_VEC; i += 256) {
+    const int xv = i % VEC_ROW, r = (i / VEC_ROW) % ROWS_IN, c = i / (VEC_ROW * ROWS_IN);
+    const int yy = y0 - 1 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yy >= 0 && yy < SIDE) {
+      const long long o = (long long)(c0 + c) * L + yy * SIDE + xv * 4;
+      const float4 hv = *reinterpret_cast<const float4*>(hb + o);
+      const unsigned long long e = (unsigned long long)b * L * hid + o;
+      v.x = gelu_erf(hv.x) * drop_scale(p_drop, seed, site, e);                                   // pgrm.py:31-32
+      v.y = gelu_erf(hv.y) * drop_scale(p_drop, seed, site, e + 1);
+      v.z = gelu_erf(hv.z) * drop_scale(p_drop, seed, site, e + 2);
+      v.w = gelu_erf(hv.w) * drop_scale(p_drop, seed, site, e + 3);
+    }
+    float* dst = sm + c * CSTRIDE + r * SIDE + xv * 4;
+    *reinterpret_cast<float2*>(dst) = make_float2(v.x, v.y);
+    *reinterpret_cast<float2*>(dst + 2) = make_float2(v.z, v.w);
+  }
+  __syncthreads();
+  // lane -> (channel = lane & 15, pixel parity = lane >> 4): a half-warp writes 64 contiguous bytes of a pixel's channels
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cl = lane & 15, c = c0 + cl;
+  float wk[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) wk[i] = w[c * 9 + i];
+  const float bb = bias[c];
+  const float* pl = sm + cl * CSTRIDE;
+#pragma unroll 2
+  for (int pi = warp * 2 + (lane >> 4); pi < DWT_ROWS * SIDE; pi += 16) {
+    const int yl = pi / SIDE, xx = pi % SIDE;
+    float acc = bb;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xc = xx + kx - 1;
+        if (xc >= 0 && xc < SIDE) acc = fmaf(pl[(yl + ky) * SIDE + xc], wk[ky * 3 + kx], acc);
+      }
+    const long long o = ((long long)b * L + (y0 + yl) * SIDE + xx) * hid + c;
+    dtpre[o] = acc;
+    dt[o] = gelu_erf(acc);
+  }
+}
+
 int launch_dwconv_train_fwd(const float* h1pre, float* dtpre, float* dt, const float* w, const float* b, int B, int L,
                             int hid, float p_drop, unsigned long long seed, uint32_t site, cudaStream_t st) {
   const int side = (int)(sqrtf((float)L) + 0.5f);
   if (side * side != L || hid % 32 || side % DWT_ROWS) return -2;
+  if (side == 32 && hid % DWF_CH == 0 && (reinterpret_cast<uintptr_t>(h1pre) & 15) == 0) {
+    dwconv_train_fwd_fast_kernel<32><<<dim3(32 / DWT_ROWS, hid / DWF_CH, B), 256, 0, st>>>(h1pre, dtpre, dt, w, b, hid, p_drop,
+                                                                                          seed, site);
+    DPMN_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = (size_t)32 * ((DWT_ROWS + 2) * side + 1) * sizeof(float);
   if (smem > 200 * 1024) return -2;
   if (smem > 48 * 1024)
@@ -464,11 +536,125 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict
   }
 }
 
+template <int SIDE>
+__global__ void __launch_bounds__(256) dwconv_bwd_fast_kernel(const float* __restrict__ d_dt, const float* __restrict__ dtpre,
+                                                              const float* __restrict__ h1pre, const float* __restrict__ w,
+                                                              float* __restrict__ d_h1pre, float* __restrict__ dw,
+                                                              float* __restrict__ db, int hid, float p_drop,
+                                                              unsigned long long seed, uint32_t site) {
+  constexpr int L = SIDE * SIDE, ROWS_IN = DWT_ROWS + 2, CSTRIDE = ROWS_IN * SIDE + 2, DSTRIDE = DWT_ROWS * SIDE;
+  extern __shared__ float sm[];
+  float* sG = sm;                              // [16][CSTRIDE]  g = d_dt * GELU'(dtpre), one halo row each side
+  float* sH = sG + DWF_CH * CSTRIDE;           // [16][CSTRIDE]  GELU(h1pre) * dropout scale, same rows
+  float* sD = sH + DWF_CH * CSTRIDE;           // [16][DSTRIDE]  GELU'(h1pre) * dropout scale, interior rows
+  const int b = blockIdx.z, c0 = blockIdx.y * DWF_CH, y0 = blockIdx.x * DWT_ROWS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    // g: pixel-major global; a half-warp reads the 16 channels of one pixel (64 contiguous bytes)
+    const int cl = lane & 15;
+    for (int r = warp * 2 + (lane >> 4); r < ROWS_IN * SIDE; r += 16) {
+      const int yy = y0 - 1 + r / SIDE, xx = r % SIDE;
+      float v = 0.f;
+      if (yy >= 0 && yy < SIDE) {
+        const long long o = ((long long)b * L + yy * SIDE + xx) * hid + c0 + cl;
+        v = d_dt[o] * gelu_grad(dtpre[o]);
+      }
+      sG[cl * CSTRIDE + r] = v;                // even CSTRIDE: the two half-warps (r, r + 1) land on disjoint banks
+    }
+  }
+  const float* hb = h1pre + (long long)b * L * hid;
+  constexpr int VEC_ROW = SIDE / 4, N_VEC = DWF_CH * ROWS_IN * VEC_ROW;
+  for (int i = threadIdx.x; i < N_VEC; i += 256) {
+    const int xv = i % VEC_ROW, r = (i / VEC_ROW) % ROWS_IN, c = i / (VEC_ROW * ROWS_IN);
+    const int yy = y0 - 1 + r;
+    float gl[4] = {0.f, 0.f, 0.f, 0.f}, dg[4] = {0.f, 0.f, 0.f, 0.f};
+    if (yy >= 0 && yy < SIDE) {
+      const long long o = (long long)(c0 + c) * L + yy * SIDE + xv * 4;
+      const float4 hv = *reinterpret_cast<const float4*>(hb + o);
+      const float hx[4] = {hv.x, hv.y, hv.z, hv.w};
+      const unsigned long long e = (unsigned long long)b * L * hid + o;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float sc = drop_scale(p_drop, seed, site, e + k);
+        float g1, d1;
+        gelu_and_grad(hx[k], g1, d1);
+        gl[k] = g1 * sc;
+        dg[k] = d1 * sc;
+      }
+    }
+    float* dh = sH + c * CSTRIDE + r * SIDE + xv * 4;
+    *reinterpret_cast<float2*>(dh) = make_float2(gl[0], gl[1]);
+    *reinterpret_cast<float2*>(dh + 2) = make_float2(gl[2], gl[3]);
+    if (r >= 1 && r <= DWT_ROWS)
+      *reinterpret_cast<float4*>(sD + c * DSTRIDE + (r - 1) * SIDE + xv * 4) = make_float4(dg[0], dg[1], dg[2], dg[3]);
+  }
+  __syncthreads();
+  // data gradient, raw (channel-plane) layout: consecutive threads -> consecutive x
+#pragma unroll 2
+  for (int i = threadIdx.x; i < DWF_CH * DSTRIDE; i += 256) {
+    const int c = i / DSTRIDE, r = i % DSTRIDE;
+    const int yl = r / SIDE, xx = r % SIDE;
+    const float* g = sG + c * CSTRIDE;
+    const float* wk = w + (c0 + c) * 9;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xs = xx - kx + 1;                  // source pixel of g: (y - ky + 1, x - kx + 1)
+        if (xs >= 0 && xs < SIDE) acc = fmaf(g[(yl + 2 - ky) * SIDE + xs], __ldg(wk + ky * 3 + kx), acc);
+      }
+    d_h1pre[(long long)b * L * hid + (long long)(c0 + c) * L + (y0 + yl) * SIDE + xx] = acc * sD[c * DSTRIDE + r];
+  }
+  // weight / bias gradient: warp w owns channels 2w, 2w+1; lanes split the 8 x SIDE positions
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c = warp * 2 + cc;
+    const float* g = sG + c * CSTRIDE + SIDE;          // row y0
+    const float* hh = sH + c * CSTRIDE;
+    float acc[9], sb = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+#pragma unroll 2
+    for (int r = lane; r < DSTRIDE; r += 32) {
+      const int yl = r / SIDE, xx = r % SIDE;
+      const float gv = g[r];
+      sb += gv;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xs = xx + kx - 1;
+          if (xs >= 0 && xs < SIDE) acc[ky * 3 + kx] = fmaf(gv, hh[(yl + ky) * SIDE + xs], acc[ky * 3 + kx]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float v = warp_sum(acc[t]);
+      if (lane == 0) atomicAdd(dw + (c0 + c) * 9 + t, v);
+    }
+    sb = warp_sum(sb);
+    if (lane == 0) atomicAdd(db + c0 + c, sb);
+  }
+}
+
 int launch_dwconv_bwd(const float* d_dt, const float* dtpre, const float* h1pre, const float* w, float* d_h1pre,
                       float* dw, float* db, int B, int L, int hid, float p_drop, unsigned long long seed, uint32_t site,
                       cudaStream_t st) {
   const int side = (int)(sqrtf((float)L) + 0.5f);
   if (side * side != L || hid % 32 || side % DWT_ROWS) return -2;
+  if (side == 32 && hid % DWF_CH == 0 && (reinterpret_cast<uintptr_t>(h1pre) & 15) == 0) {
+    constexpr int fast_smem = (2 * DWF_CH * ((DWT_ROWS + 2) * 32 + 2) + DWF_CH * DWT_ROWS * 32) * (int)sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      DPMN_CUDA_TRY(cudaFuncSetAttribute(dwconv_bwd_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_smem));
+      attr_set = true;
+    }
+    dwconv_bwd_fast_kernel<32><<<dim3(32 / DWT_ROWS, hid / DWF_CH, B), 256, fast_smem, st>>>(d_dt, dtpre, h1pre, w, d_h1pre, dw,
+                                                                                            db, hid, p_drop, seed, site);
+    DPMN_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = (size_t)2 * 32 * ((DWT_ROWS + 2) * side + 1) * sizeof(float);
   if (smem > 200 * 1024) return -2;
   if (smem > 48 * 1024)
@@ -751,7 +937,7 @@ __global__ void mix_res_bwd_kernel(const float* __restrict__ d_out, MixBwdArgs m
 }
 
 // dgrad of a 3x3 conv on NHWC with <= 16 output channels (padded rows of 16): dx[pix][ci] = sum dy[pix - tap][co] w[co][ci][tap]
-__global__ void __launch_bounds__(128) conv3x3_small_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) conv3x3_small_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                                   float* __restrict__ dx, int B, int gh, int gw, int Cin,
                                                                   int Cout, int ldx) {
   extern __shared__ float sw[];           // [tap][co(16)][Cin]
@@ -765,20 +951,26 @@ __global__ void __launch_bounds__(128) conv3x3_small_dgrad_kernel(const float* _
     const int ci = (int)(idx % Cin);
     const long long pixb = idx / Cin;
     const int xx = (int)(pixb % gw), yy = (int)((pixb / gw) % gh), b = (int)(pixb / ((long long)gw * gh));
-    float acc = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent chains (one serial chain of 144 FMAs was latency-bound)
     for (int ky = 0; ky < 3; ++ky) {
       const int y2 = yy - ky + 1;
       if (y2 < 0 || y2 >= gh) continue;
       for (int kx = 0; kx < 3; ++kx) {
         const int x2 = xx - kx + 1;
         if (x2 < 0 || x2 >= gw) continue;
-        const float* src = dy + ((long long)(b * gh + y2) * gw + x2) * HB_PAD;
+        const float4* src = reinterpret_cast<const float4*>(dy + ((long long)(b * gh + y2) * gw + x2) * HB_PAD);
         const float* wt = sw + (ky * 3 + kx) * HB_PAD * Cin + ci;
 #pragma unroll
-        for (int co = 0; co < HB_PAD; ++co) acc = fmaf(src[co], wt[co * Cin], acc);
+        for (int q = 0; q < HB_PAD / 4; ++q) {
+          const float4 g = __ldg(src + q);
+          a0 = fmaf(g.x, wt[(4 * q + 0) * Cin], a0);
+          a1 = fmaf(g.y, wt[(4 * q + 1) * Cin], a1);
+          a2 = fmaf(g.z, wt[(4 * q + 2) * Cin], a2);
+          a3 = fmaf(g.w, wt[(4 * q + 3) * Cin], a3);
+        }
       }
     }
-    dx[pixb * ldx + ci] = acc;
+    dx[pixb * ldx + ci] = (a0 + a1) + (a2 + a3);
   }
 }
 
@@ -847,7 +1039,7 @@ int launch_head_bwd(const HeadBwdArgs& h, cudaStream_t st) {
   DPMN_LAUNCH_CHECK();
   {
     const size_t smem = (size_t)9 * HB_PAD * hp * sizeof(float);   // dt1 columns hp..15 stay zero (memset by the caller)
-    conv3x3_small_dgrad_kernel<<<592, 128, smem, st>>>(h.dt2, h.w2, h.dt1, h.B, h.gh, h.gw, hp, hp, HB_PAD);
+    conv3x3_small_dgrad_kernel<<<592, 256, smem, st>>>(h.dt2, h.w2, h.dt1, h.B, h.gh, h.gw, hp, hp, HB_PAD);
     DPMN_LAUNCH_CHECK();
   }
   // (3) conv1 (C -> hp) backward: weights / bias, then data -> d tokens (B, L, C)
@@ -862,7 +1054,7 @@ int launch_head_bwd(const HeadBwdArgs& h, cudaStream_t st) {
       DPMN_CUDA_TRY(cudaFuncSetAttribute(conv3x3_small_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr = smem;
     }
-    conv3x3_small_dgrad_kernel<<<592, 128, smem, st>>>(h.dt1, h.w1, h.d_tokens, h.B, h.gh, h.gw, h.C, hp, h.C);
+    conv3x3_small_dgrad_kernel<<<592, 256, smem, st>>>(h.dt1, h.w1, h.d_tokens, h.B, h.gh, h.gw, h.C, hp, h.C);
     DPMN_LAUNCH_CHECK();
   }
   return 0;

@@ -291,6 +291,32 @@ def test_full_hot_path_fp16_matches_cpu_port():
     assert e < 2e-3, e   # 7 chained modules; each is within 1e-3 on its own
 
 
+def test_hot_path_batch_64_config4_is_the_same_code_path():
+    """BASELINE configs[3] (TBSRN backbone swap, batch 64/GPU): the PSN only changes the INPUT tensor, so the drop-in check
+    is that the hot path at batch 64 is the batch-48 code path image by image: bit-identical to a batch-4 run of the same
+    images (no cross-image coupling, no batch-size-dependent tiling of any reduction), and within the fp16 bar of the CPU
+    port."""
+    import bench
+    from dpmn_b200.pipeline import DPMNHotPath
+    from oracle import torch_ref
+    pg, cm = bench.synth_weights(2)
+    model = DPMNHotPath(precision="fp16")
+    bench.load_weights(model, pg, cm)
+    model = model.to(DEV).eval()
+    psn, p1, p2 = bench.synth_inputs(11, 64)
+    with torch.no_grad():
+        y = model(_t(psn), [_t(a) for a in p1], [_t(a) for a in p2])
+        sl = slice(59, 63)
+        y4 = model(_t(psn[sl]), [_t(a[sl]) for a in p1], [_t(a[sl]) for a in p2])
+        ref = torch_ref.hot_path_forward([{k: torch.from_numpy(np.asarray(v)) for k, v in p.items()} for p in pg],
+                                         {k: torch.from_numpy(np.asarray(v)) for k, v in cm.items()},
+                                         torch.from_numpy(psn[sl]), [torch.from_numpy(a[sl]) for a in p1],
+                                         [torch.from_numpy(a[sl]) for a in p2])
+    assert y.shape == (64, 3, 32, 128)
+    assert torch.equal(y[sl], y4)
+    assert rel_err(y[sl].cpu().numpy(), ref.numpy()) < 2e-3
+
+
 def test_prepared_weight_cache_tracks_in_place_updates():
     """The tensor-core modes cache staged 16-bit weights; an optimizer-style in-place update must invalidate it."""
     z, meta = load_golden("pgrm_i0_m0")

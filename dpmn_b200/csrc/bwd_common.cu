@@ -256,6 +256,7 @@ int launch_reduce_partials(const float* partial, float* dst, int S, long long n,
 // =====================================================================================================
 constexpr int LNB_CPL = 8;
 
+template <int CPL>       // channels per lane: C <= 32 * CPL (3 for the PGRM's C = 96: no predicated-off slots)
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ w, float* __restrict__ dx,
                                                             int accumulate, float* __restrict__ dw,
@@ -263,19 +264,19 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   __shared__ float red_w[8][256], red_b[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
-  float aw[LNB_CPL], ab[LNB_CPL], wv[LNB_CPL];
+  float aw[CPL], ab[CPL], wv[CPL];
 #pragma unroll
-  for (int i = 0; i < LNB_CPL; ++i) {
+  for (int i = 0; i < CPL; ++i) {
     aw[i] = 0.f; ab[i] = 0.f;
     const int c = lane + 32 * i;
     wv[i] = c < C ? w[c] : 0.f;
   }
   const float invC = 1.0f / (float)C;
   for (int r = gw; r < rows; r += nw) {
-    float xv[LNB_CPL], gv[LNB_CPL];
+    float xv[CPL], gv[CPL];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LNB_CPL; ++i) {
+    for (int i = 0; i < CPL; ++i) {
       const int c = lane + 32 * i;
       xv[i] = c < C ? x[(long long)r * C + c] : 0.f;
       gv[i] = c < C ? dy[(long long)r * C + c] : 0.f;
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     const float mean = warp_sum(s) * invC;
     float v = 0.f;
 #pragma unroll
-    for (int i = 0; i < LNB_CPL; ++i) {
+    for (int i = 0; i < CPL; ++i) {
       const int c = lane + 32 * i;
       const float d = c < C ? xv[i] - mean : 0.f;
       xv[i] = d;
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     const float rstd = rsqrtf(warp_sum(v) * invC + 1e-5f);
     float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LNB_CPL; ++i) {
+    for (int i = 0; i < CPL; ++i) {
       xv[i] *= rstd;                       // xhat
       aw[i] = fmaf(gv[i], xv[i], aw[i]);
       ab[i] += gv[i];
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     m1 = warp_sum(m1) * invC;
     m2 = warp_sum(m2) * invC;
 #pragma unroll
-    for (int i = 0; i < LNB_CPL; ++i) {
+    for (int i = 0; i < CPL; ++i) {
       const int c = lane + 32 * i;
       if (c < C) {
         const float d = rstd * (gv[i] - m1 - xv[i] * m2);
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     }
   }
 #pragma unroll
-  for (int i = 0; i < LNB_CPL; ++i) { red_w[warp][lane + 32 * i] = aw[i]; red_b[warp][lane + 32 * i] = ab[i]; }
+  for (int i = 0; i < CPL; ++i) { red_w[warp][lane + 32 * i] = aw[i]; red_b[warp][lane + 32 * i] = ab[i]; }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += 256) {
     float sw = 0.f, sb = 0.f;
@@ -330,7 +331,8 @@ int launch_layernorm_bwd(const float* dy, const float* x, const float* w, float*
   if (C > 32 * LNB_CPL) return -2;
   int blocks = (rows + 63) / 64;
   if (blocks > 592) blocks = 592;
-  layernorm_bwd_kernel<<<blocks, 256, 0, st>>>(dy, x, w, dx, accumulate, dw, db, rows, C);
+  if (C <= 96) layernorm_bwd_kernel<3><<<blocks, 256, 0, st>>>(dy, x, w, dx, accumulate, dw, db, rows, C);
+  else layernorm_bwd_kernel<LNB_CPL><<<blocks, 256, 0, st>>>(dy, x, w, dx, accumulate, dw, db, rows, C);
   DPMN_LAUNCH_CHECK();
   return 0;
 }

@@ -843,11 +843,115 @@ __global__ void __launch_bounds__(256) sk_gate_kernel(const float* __restrict__ 
     for (int o = t; o < C; o += blockDim.x) bias_out[(long long)b * C + o] = bp[o] + bh[o];
 }
 
+// C = 96, G = 3 (cg 32, dz 16), 256 threads, 4 CTAs per image: the same computation with every parameter load issued
+// before the first barrier.  The generic kernel above is a chain of five phases that each start with a global-memory
+// round trip (column sums -> fc1 rows -> fc2 rows -> proj / proj_head slices): ~15 us of mostly exposed latency for a
+// few kFLOP.  Here the phases only wait on shared memory.
+template <typename WT>
+__global__ void __launch_bounds__(256) sk_gate_c96_kernel(const float* __restrict__ colsum, int tiles, float inv_L,
+                                                          const float* __restrict__ wp, const float* __restrict__ bp,
+                                                          const float* __restrict__ w1, const float* __restrict__ b1,
+                                                          const float* __restrict__ w2, const float* __restrict__ b2,
+                                                          const float* __restrict__ wh, const float* __restrict__ bh,
+                                                          WT* __restrict__ wb_out, float* __restrict__ bias_out) {
+  constexpr int C = 96, CG = 32, DZ = 16, PER = C * C / 4, ITERS = PER / 256;   // 2304 folded weights per CTA, 9 per thread
+  __shared__ float sS[C], sZ[DZ], sA[C];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  // ---- all global loads up front
+  float cs = 0.f;
+  if (t < C) {
+#pragma unroll 8
+    for (int i = 0; i < tiles; ++i) cs += colsum[((long long)b * tiles + i) * C + t];
+  }
+  float r1[2][3];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r1[q][k] = w1[(warp + 8 * q) * C + lane + 32 * k];
+  const float rb1 = b1[warp + 8 * (lane & 1)];
+  float r2[DZ];
+  float rb2 = 0.f;
+  if (t < C) {
+    const float4* src = reinterpret_cast<const float4*>(w2 + t * DZ);
+#pragma unroll
+    for (int q = 0; q < DZ / 4; ++q) {
+      const float4 v = src[q];
+      r2[4 * q] = v.x; r2[4 * q + 1] = v.y; r2[4 * q + 2] = v.z; r2[4 * q + 3] = v.w;
+    }
+    rb2 = b2[t];
+  }
+  float pw[ITERS], ph[ITERS];
+#pragma unroll
+  for (int k = 0; k < ITERS; ++k) {
+    const int i = blockIdx.y * PER + t + 256 * k;
+    const int o = i / C, c = i - o * C;
+    pw[k] = wp[i];
+    ph[k] = wh[o * CG + (c % CG)];
+  }
+  float bias_v = 0.f;
+  if (blockIdx.y == 0 && t < C) bias_v = bp[t] + bh[t];
+  // ---- S = mean_L GELU(proj(x))
+  if (t < C) sS[t] = cs * inv_L;
+  __syncthreads();
+  // ---- Z = GELU(fc1 S): warp w owns outputs w and w + 8
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s = fmaf(r1[q][k], sS[lane + 32 * k], s);
+    s = warp_sum(s);
+    const float bq = __shfl_sync(0xffffffffu, rb1, q);
+    if (lane == 0) sZ[warp + 8 * q] = gelu_erf(s + bq);
+  }
+  __syncthreads();
+  // ---- fc2 and the softmax over the 3 groups
+  if (t < C) {
+    float s = rb2;
+#pragma unroll
+    for (int j = 0; j < DZ; ++j) s = fmaf(r2[j], sZ[j], s);
+    sA[t] = s;
+  }
+  __syncthreads();
+  if (t < CG) {
+    const float a0 = sA[t], a1 = sA[CG + t], a2 = sA[2 * CG + t];
+    const float mx = fmaxf(a0, fmaxf(a1, a2));
+    const float e0 = expf(a0 - mx), e1 = expf(a1 - mx), e2 = expf(a2 - mx);
+    const float den = e0 + e1 + e2;
+    sA[t] = e0 / den; sA[CG + t] = e1 / den; sA[2 * CG + t] = e2 / den;
+  }
+  __syncthreads();
+  // ---- folded weight slice of this CTA: Wp + Wh diag(A)
+#pragma unroll
+  for (int k = 0; k < ITERS; ++k) {
+    const int i = blockIdx.y * PER + t + 256 * k;
+    const int c = i % C;
+    wb_out[(long long)b * C * C + i] = from_f32<WT>(fmaf(ph[k], sA[c], pw[k]));
+  }
+  if (blockIdx.y == 0 && t < C) bias_out[(long long)b * C + t] = bias_v;
+}
+
+template <typename WT>
+static void launch_sk_gate_c96(const float* colsum, int tiles, int L, const float* wp, const float* bp, const float* w1,
+                               const float* b1, const float* w2, const float* b2, const float* wh, const float* bh,
+                               void* wb_out, float* bias_out, int B, cudaStream_t st) {
+  sk_gate_c96_kernel<WT><<<dim3(B, 4), 256, 0, st>>>(colsum, tiles, 1.0f / (float)L, wp, bp, w1, b1, w2, b2, wh, bh,
+                                                     (WT*)wb_out, bias_out);
+}
+
 int launch_sk_gate(const float* colsum, int tiles_per_image, int L, const float* wp, const float* bp,
                    const float* w1, const float* b1, const float* w2, const float* b2, const float* wh,
                    const float* bh, void* wb_out, DType wb_type, float* bias_out, int B, int C, int G,
                    cudaStream_t st) {
   const int cg = C / G;
+  if (C == 96 && G == 3 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0) {
+    switch (wb_type) {
+      case DT_F32: launch_sk_gate_c96<float>(colsum, tiles_per_image, L, wp, bp, w1, b1, w2, b2, wh, bh, wb_out, bias_out, B, st); break;
+      case DT_F16: launch_sk_gate_c96<__half>(colsum, tiles_per_image, L, wp, bp, w1, b1, w2, b2, wh, bh, wb_out, bias_out, B, st); break;
+      case DT_BF16: launch_sk_gate_c96<__nv_bfloat16>(colsum, tiles_per_image, L, wp, bp, w1, b1, w2, b2, wh, bh, wb_out, bias_out, B, st); break;
+    }
+    DPMN_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = (size_t)(2 * C + cg / 2 + 8) * sizeof(float);
   switch (wb_type) {
     case DT_F32:

@@ -370,13 +370,19 @@ def run_ours(args):
     dom_ms = prof[dom]["ms_per_step"]
     achieved = flops_img[dom] * B / (dom_ms / 1e3) / 1e12
     total_prof_ms = sum(v["ms_per_step"] for v in prof.values())
-    if train:
-        tensor_peak = 75.0   # B200 fp32 FFMA peak (148 SMs x 128 lanes x 2 x 1.965 GHz): the backward is fp32 SIMT this round
-        peak_src = "nominal fp32 FFMA peak (the backward kernels are fp32 SIMT, not tensor-core, this round)"
+    train_bound = "tensor"
+    if train and args.precision == "fp32":
+        tensor_peak = 75.0   # B200 fp32 FFMA peak (148 SMs x 128 lanes x 2 x 1.965 GHz): the fp32 mode is all SIMT
+        peak_src = "nominal fp32 FFMA peak (precision fp32: every contraction is an FFMA kernel)"
+        train_bound = "fp32-simt"
+    elif train:
+        # 16-bit modes: the contractions of this class run on tcgen05 through 16-bit staged operands (lin_*_tc, the CMM's
+        # im2col + NT GEMM), so the class -- gathers, staging copies and GEMMs together -- is quoted against the tensor peak
+        peak_src += "; class time includes the im2col gathers / 16-bit staging copies around the tcgen05 GEMMs"
     # DRAM bytes per launch of the dominant class from the committed `ncu --set full` capture (mean over its launches in
     # profiles/r01_ncu_full_fp16_v14.txt: dram__bytes_read.sum + dram__bytes_write.sum; writes mostly stay in the 126 MB L2)
     traffic = {"gemm_tc": 13.3e6, "conv_tc": None}.get(dom) if not train else None
-    roofline = {"bound": "tensor" if not train else "fp32-simt", "kernel": dom, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+    roofline = {"bound": "tensor" if not train else train_bound, "kernel": dom, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak, "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": dom_ms / total_prof_ms,
                 "launches_per_step": prof[dom]["launches_per_step"],

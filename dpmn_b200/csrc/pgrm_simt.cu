@@ -1100,10 +1100,156 @@ __global__ void __launch_bounds__(256) dwconv16_kernel(const T* __restrict__ h, 
   }
 }
 
+// ---- SIDE = 32 form of the 16-bit kernel (the BASELINE geometry: L = 1024 tokens -> 32 x 32 planes) -----------------
+// dwconv16_kernel above is issue-bound (ncu: 73 % of issue slots, 56 instructions per output).  This form
+//   * keeps TWO adjacent channels per thread, so every shared-memory access is one 32-bit word, the nine taps are nine
+//     packed fma.rn.f32x2 (sm_100) and the polynomial part of the GELU is packed too: ~17 instructions per output;
+//   * stages the input tile as [row][x + 1][channel pair] with zero-filled x borders (no bounds tests in the tap loop);
+//     the transposition from the plane layout happens on the way in: lanes holding channels c and c + 1 swap halves with
+//     one shuffle pair and write 32-bit {c, c + 1} words at a 33-word cell pitch (conflict-free);
+//   * writes the result straight to global memory: a warp owns one pixel x 64 channels per store = one 128-byte line.
+// Arithmetic (operation order, rounding, the ex2 / rcp GELU) is that of dwconv16_kernel: results are bit-identical.
+__device__ __forceinline__ unsigned long long f2_pack(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// gelu_fast on a packed pair (same operations as the scalar form in common.cuh)
+__device__ __forceinline__ unsigned long long f2_gelu_fast(unsigned long long x) {
+  float u0, u1;
+  f2_unpack(f2_mul(x, x), u0, u1);
+  const unsigned long long u = f2_pack(fminf(u0, 64.0f), fminf(u1, 64.0f));
+  unsigned long long q = f2_fma(f2_pack(1.0142650e-3f, 1.0142650e-3f), u, f2_pack(-1.0677574e-1f, -1.0677574e-1f));
+  q = f2_fma(q, u, f2_pack(-2.3011213f, -2.3011213f));
+  float t0, t1, e0, e1, r0, r1;
+  f2_unpack(f2_mul(x, q), t0, t1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  float d0, d1;
+  f2_unpack(f2_add(f2_pack(1.0f, 1.0f), f2_pack(e0, e1)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+  return f2_mul(x, f2_pack(r0, r1));
+}
+template <typename T> __device__ __forceinline__ unsigned long long word_to_f2(uint32_t w);
+template <> __device__ __forceinline__ unsigned long long word_to_f2<__half>(uint32_t w) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+  return f2_pack(f.x, f.y);
+}
+template <> __device__ __forceinline__ unsigned long long word_to_f2<__nv_bfloat16>(uint32_t w) {
+  return f2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <typename T> __device__ __forceinline__ uint32_t f2_to_word(unsigned long long v);
+template <> __device__ __forceinline__ uint32_t f2_to_word<__half>(unsigned long long v) {
+  float a, b;
+  f2_unpack(v, a, b);
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t f2_to_word<__nv_bfloat16>(unsigned long long v) {
+  float a, b;
+  f2_unpack(v, a, b);
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+constexpr int DW2_SIDE = 32, DW2_CELLS = DW2_SIDE + 2, DW2_PITCH = 33;     // words per cell: 32 channel pairs + 1 pad
+constexpr int DW2_SMEM_WORDS = (DW_ROWS + 2) * DW2_CELLS * DW2_PITCH;
+
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv16_v2_kernel(const T* __restrict__ h, T* __restrict__ dt,
+                                                          const float* __restrict__ w, const float* __restrict__ bias,
+                                                          int hid) {
+  static_assert(sizeof(T) == 2, "16-bit storage");
+  constexpr int SIDE = DW2_SIDE, L = SIDE * SIDE, ROWS_IN = DW_ROWS + 2;
+  __shared__ uint32_t s_in[DW2_SMEM_WORDS];            // [row][x + 1][pair]
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, y0 = blockIdx.x * DW_ROWS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // zero x borders (cells 0 and SIDE + 1 of every row)
+  for (int i = threadIdx.x; i < ROWS_IN * 2 * 32; i += 256) {
+    const int pr = i & 31, side = (i >> 5) & 1, r = i >> 6;
+    s_in[(r * DW2_CELLS + (side ? SIDE + 1 : 0)) * DW2_PITCH + pr] = 0u;
+  }
+  // plane layout -> [row][x][pair]: lane = (c8 = channel within a group of 8, xv = 8-column vector of the row)
+  {
+    const T* hb = h + (long long)b * L * hid;
+    const int c8 = lane & 7, xv = lane >> 3;
+    const bool odd = (c8 & 1) != 0;
+#pragma unroll 2
+    for (int it = 0; it < (8 * ROWS_IN) / 8; ++it) {
+      const int combo = it * 8 + warp;
+      const int cgrp = combo & 7, r = combo >> 3;
+      const int yy = y0 - 1 + r;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (yy >= 0 && yy < SIDE)
+        v = *reinterpret_cast<const uint4*>(hb + (long long)(c0 + cgrp * 8 + c8) * L + yy * SIDE + xv * 8);
+      const uint32_t send0 = odd ? v.x : v.z, send1 = odd ? v.y : v.w;
+      const uint32_t recv0 = __shfl_xor_sync(0xffffffffu, send0, 1), recv1 = __shfl_xor_sync(0xffffffffu, send1, 1);
+      const uint32_t mine0 = odd ? v.z : v.x, mine1 = odd ? v.w : v.y;
+      const uint32_t a0 = odd ? recv0 : mine0, a1 = odd ? recv1 : mine1;       // even channel of the pair
+      const uint32_t b0 = odd ? mine0 : recv0, b1 = odd ? mine1 : recv1;       // odd channel
+      uint32_t* dst = s_in + (r * DW2_CELLS + 1 + xv * 8 + (odd ? 4 : 0)) * DW2_PITCH + cgrp * 4 + (c8 >> 1);
+      dst[0 * DW2_PITCH] = __byte_perm(a0, b0, 0x5410);
+      dst[1 * DW2_PITCH] = __byte_perm(a0, b0, 0x7632);
+      dst[2 * DW2_PITCH] = __byte_perm(a1, b1, 0x5410);
+      dst[3 * DW2_PITCH] = __byte_perm(a1, b1, 0x7632);
+    }
+  }
+  __syncthreads();
+  // thread = (channel pair = lane, output row = warp): sliding 3 x 3 window along x, two channels per packed operation
+  const int c = c0 + 2 * lane;
+  unsigned long long wk[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) wk[i] = f2_pack(w[c * 9 + i], w[(c + 1) * 9 + i]);
+  const unsigned long long bb = f2_pack(bias[c], bias[c + 1]);
+  const uint32_t* r0 = s_in + ((warp + 0) * DW2_CELLS) * DW2_PITCH + lane;
+  const uint32_t* r1 = r0 + DW2_CELLS * DW2_PITCH;
+  const uint32_t* r2 = r1 + DW2_CELLS * DW2_PITCH;
+  unsigned long long a0 = word_to_f2<T>(r0[0]), a1 = word_to_f2<T>(r1[0]), a2 = word_to_f2<T>(r2[0]);          // column x - 1
+  unsigned long long m0 = word_to_f2<T>(r0[DW2_PITCH]), m1 = word_to_f2<T>(r1[DW2_PITCH]), m2 = word_to_f2<T>(r2[DW2_PITCH]);
+  uint32_t* out = reinterpret_cast<uint32_t*>(dt + ((long long)b * L + (y0 + warp) * SIDE) * hid + c);
+  const int out_step = hid / 2;                        // words per pixel
+#pragma unroll 4
+  for (int x = 0; x < SIDE; ++x) {
+    const unsigned long long n0 = word_to_f2<T>(r0[(x + 2) * DW2_PITCH]), n1 = word_to_f2<T>(r1[(x + 2) * DW2_PITCH]),
+                             n2 = word_to_f2<T>(r2[(x + 2) * DW2_PITCH]);                                           // column x + 1
+    unsigned long long acc = bb;
+    acc = f2_fma(a0, wk[0], acc); acc = f2_fma(m0, wk[1], acc); acc = f2_fma(n0, wk[2], acc);
+    acc = f2_fma(a1, wk[3], acc); acc = f2_fma(m1, wk[4], acc); acc = f2_fma(n1, wk[5], acc);
+    acc = f2_fma(a2, wk[6], acc); acc = f2_fma(m2, wk[7], acc); acc = f2_fma(n2, wk[8], acc);
+    out[(long long)x * out_step] = f2_to_word<T>(f2_gelu_fast(acc));
+    a0 = m0; a1 = m1; a2 = m2;
+    m0 = n0; m1 = n1; m2 = n2;
+  }
+}
+
 template <typename T>
 static int launch_dwconv16(const void* h, void* dt, const float* w, const float* b, int B, int L, int hid, int side,
                            cudaStream_t st) {
   dim3 grid((side + DW_ROWS - 1) / DW_ROWS, hid / 64, B);
+  if (side == DW2_SIDE && (reinterpret_cast<uintptr_t>(h) & 15) == 0 && (reinterpret_cast<uintptr_t>(dt) & 3) == 0) {
+    dwconv16_v2_kernel<T><<<grid, 256, 0, st>>>((const T*)h, (T*)dt, w, b, hid);
+    DPMN_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = (size_t)(64 * ((DW_ROWS + 2) * side + 2) + DW_ROWS * side * 64) * 2;
   auto k = dwconv16_kernel<T>;
   static bool attr_set = false;

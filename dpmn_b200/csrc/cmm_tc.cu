@@ -169,12 +169,108 @@ __global__ void __launch_bounds__(256) cmm_en1_kernel(const float* __restrict__ 
   }
 }
 
+// c_img = 3, W % 4 == 0: four horizontally adjacent pixels x 8 output channels per thread.  The two-pixel kernel above is
+// bound by shared-memory bandwidth (ncu: MIO busy 86 %, one 2 x LDS.128 weight fetch per 16 FMAs); here the same fetch feeds
+// 32 FMAs and the 3 x 3 x 6 input patch is loaded once for all four pixels.
+template <typename T>
+__global__ void __launch_bounds__(128, 4) cmm_en1_p4_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                         const float* __restrict__ w1, const float* __restrict__ b1,
+                                                         const float* __restrict__ w2, const float* __restrict__ b2,
+                                                         T* __restrict__ e1, T* __restrict__ cat1, int B, int H, int W,
+                                                         int cnum) {
+  extern __shared__ __align__(16) float sw[];   // [27][cnum] + bias [cnum]
+  const int g = blockIdx.y;
+  const float* x = g == 0 ? x1 : x2;
+  const float* w = g == 0 ? w1 : w2;
+  const float* bsrc = g == 0 ? b1 : b2;
+  for (int i = threadIdx.x; i < 27 * cnum; i += blockDim.x) {
+    const int co = i % cnum, k = i / cnum;
+    sw[i] = w[co * 27 + k];
+  }
+  float* sb = sw + 27 * cnum;
+  for (int i = threadIdx.x; i < cnum; i += blockDim.x) sb[i] = bsrc[i];
+  __syncthreads();
+  const int groups = cnum / 8;
+  const int Wq = W / 4;
+  const long long total = (long long)B * H * Wq * groups;
+  const long long HW = (long long)H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % groups);
+    const long long pp = idx / groups;
+    const int xq = (int)(pp % Wq);
+    const int yy = (int)((pp / Wq) % H);
+    const int b = (int)(pp / ((long long)Wq * H));
+    const int x0 = 4 * xq;
+    float v[3][3][6];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+      const float* xc = x + ((long long)b * 3 + ci) * HW;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int y2 = yy + ky - 1;
+        const bool row_ok = y2 >= 0 && y2 < H;
+        const float* xr = xc + (long long)(row_ok ? y2 : yy) * W;
+        const float4 mid = *reinterpret_cast<const float4*>(xr + x0);
+        v[ci][ky][0] = (row_ok && x0 > 0) ? xr[x0 - 1] : 0.f;
+        v[ci][ky][1] = row_ok ? mid.x : 0.f;
+        v[ci][ky][2] = row_ok ? mid.y : 0.f;
+        v[ci][ky][3] = row_ok ? mid.z : 0.f;
+        v[ci][ky][4] = row_ok ? mid.w : 0.f;
+        v[ci][ky][5] = (row_ok && x0 + 4 < W) ? xr[x0 + 4] : 0.f;
+      }
+    }
+    float acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float bj = sb[cg * 8 + j];
+      acc[0][j] = bj; acc[1][j] = bj; acc[2][j] = bj; acc[3][j] = bj;
+    }
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4* wr = reinterpret_cast<const float4*>(sw + ((ci * 3 + ky) * 3 + kx) * cnum + cg * 8);
+          const float4 wa = wr[0], wb = wr[1];
+          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+          for (int px = 0; px < 4; ++px)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(v[ci][ky][kx + px], wv[j], acc[px][j]);
+        }
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const long long pix = ((long long)b * H + yy) * W + x0 + px;
+      union { uint4 u; T h[8]; } a, r;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a.h[j] = from_f32<T>(acc[px][j] >= 0.f ? acc[px][j] : 0.2f * acc[px][j]);
+        r.h[j] = from_f32<T>(fmaxf(acc[px][j], 0.f));
+      }
+      *reinterpret_cast<uint4*>(e1 + ((long long)g * B * HW + pix) * cnum + cg * 8) = a.u;
+      *reinterpret_cast<uint4*>(cat1 + pix * (3 * cnum) + cnum * (1 + g) + cg * 8) = r.u;
+    }
+  }
+}
+
 int launch_cmm_en1(const float* x1, const float* x2, const float* w1, const float* b1, const float* w2, const float* b2,
                    void* e1, void* cat1, DType t, int B, int H, int W, int c_img, int cnum, cudaStream_t st) {
   if (cnum % 8 || W % 2) return -2;
   const size_t smem = (size_t)(c_img * 9 * cnum + cnum) * sizeof(float);
   if (smem > 48 * 1024) return -2;
   dim3 grid(148 * 4, 2);
+  if (c_img == 3 && W % 4 == 0 && ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2)) & 15) == 0 &&
+      (t == DT_F16 || t == DT_BF16)) {
+    if (t == DT_F16)
+      cmm_en1_p4_kernel<__half><<<dim3(148 * 8, 2), 128, smem, st>>>(x1, x2, w1, b1, w2, b2, (__half*)e1, (__half*)cat1, B, H, W, cnum);
+    else
+      cmm_en1_p4_kernel<__nv_bfloat16><<<dim3(148 * 8, 2), 128, smem, st>>>(x1, x2, w1, b1, w2, b2, (__nv_bfloat16*)e1,
+                                                               (__nv_bfloat16*)cat1, B, H, W, cnum);
+    DPMN_LAUNCH_CHECK();
+    return 0;
+  }
   if (t == DT_F16)
     cmm_en1_kernel<__half><<<grid, 256, smem, st>>>(x1, x2, w1, b1, w2, b2, (__half*)e1, (__half*)cat1, B, H, W, c_img, cnum);
   else if (t == DT_BF16)

@@ -1193,7 +1193,7 @@ __global__ void __launch_bounds__(256) dwconv16_v2_kernel(const T* __restrict__ 
     const T* hb = h + (long long)b * L * hid;
     const int c8 = lane & 7, xv = lane >> 3;
     const bool odd = (c8 & 1) != 0;
-#pragma unroll 2
+#pragma unroll 5                                     // five 16-byte loads in flight per thread (the stage-in is latency-bound)
     for (int it = 0; it < (8 * ROWS_IN) / 8; ++it) {
       const int combo = it * 8 + warp;
       const int cgrp = combo & 7, r = combo >> 3;

@@ -55,3 +55,51 @@ def test_oracle_image_loss_and_to_mask_match_reference_fixtures():
         assert np.abs(o.grad.numpy() - z[f"loss{i}_grad"]).max() < 1e-6 * np.abs(z[f"loss{i}_grad"]).max()
     for img, want in zip(z["mask_in"], z["mask_out"]):
         assert np.array_equal(to_mask(img), want)
+
+
+def test_distill_chain_follows_the_reference_loop():
+    """HotPathTrainer.distill_loss walks the cascade outputs exactly like interfaces/super_resolution.py:245-263: per branch
+    from the deepest image back, module distill_list[k-1] (branch 1) / distill_list[k+b1-2] (branch 2), x_deep = the feature
+    handed on by the previous module, x_shallow = cascade[k-1].  Host logic only: stand-in modules record their calls."""
+    import types
+    from dpmn_b200.train import HotPathTrainer
+
+    for b1, b2 in ((3, 3), (2, 4)):
+        calls = []
+
+        def make(idx):
+            def module(x_deep, x_shallow):
+                calls.append((idx, x_deep, x_shallow))
+                return torch.tensor(float(idx + 1)), f"feat{idx}"
+            return module
+        outs = [f"b1_{k}" for k in range(b1)] + [f"b2_{k}" for k in range(b2)] + ["cmm"]
+        fake = types.SimpleNamespace(model=types.SimpleNamespace(b1=b1, b2=b2), distill=[make(i) for i in range(b1 + b2 - 2)])
+        # `outs[0].new_zeros(())` is the only tensor method the loop needs from the images
+        class Img(str):
+            def new_zeros(self, shape):
+                return torch.zeros(shape)
+        outs = [Img(o) for o in outs]
+        total = HotPathTrainer.distill_loss(fake, outs)
+        # the reference's loop, written out
+        want, expect_total = [], 0.0
+        feature = outs[b1 - 1]
+        for k in range(b1 - 1, 0, -1):
+            want.append((k - 1, feature, outs[k - 1]))
+            feature = f"feat{k - 1}"
+            expect_total += (k - 1 + 1) * 100
+        feature = outs[b1 + b2 - 1]
+        for k in range(b2 - 1, 0, -1):
+            want.append((k + b1 - 2, feature, outs[b1 + k - 1]))
+            feature = f"feat{k + b1 - 2}"
+            expect_total += (k + b1 - 2 + 1) * 100
+        assert [(i, str(d), str(s)) for i, d, s in calls] == [(i, str(d), str(s)) for i, d, s in want]
+        assert abs(float(total) - expect_total) < 1e-6
+
+
+def test_bench_algorithmic_byte_model_matches_design():
+    """bench.py's BYTES_IMG (the roofline's algorithmic bytes) against the per-block figure DESIGN.md section 5 states."""
+    import bench
+    assert bench.BYTES_IMG["gemm_tc"] == 12 * 6_684_672
+    assert bench.BYTES_IMG["window_attn_tc"] == 12 * 786_432          # SURVEY 8d: 4 * L * C * 2 B per image-block
+    assert bench.FLOPS_IMG["total"] == 11_267_776_512                 # SURVEY 8d: DPMN hot path forward per image
+    assert abs(bench.FLOPS_IMG["gemm_tc"] / bench.BYTES_IMG["gemm_tc"] - 80.0) < 0.5

@@ -46,3 +46,24 @@ def test_cuda_resizes_match_reference_fixtures():
         assert one.shape == (1, 3, 64, 256) and np.array_equal(one[0], got[0])
     with pytest.raises(RuntimeError):
         parse_crnn_data(torch.zeros(1, 3, 16, 64))                    # no CPU path
+
+
+def test_oracle_resizes_against_live_libraries_on_random_shapes():
+    """Beyond the committed fixtures: the numpy restatements against the libraries the reference calls, for random source
+    sizes (up- and down-scaling, odd sizes; out-of-range values are covered by the committed fixture, whose float -> uint8
+    wrap-around does not depend on the host CPU).  Skipped where OpenCV / torchvision are absent."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle.torch_ref import parse_crnn_data, parse_visionlan_data
+    r = np.random.default_rng(77)
+    for _ in range(12):
+        h, w = int(r.integers(5, 90)), int(r.integers(9, 300))
+        img = r.uniform(0, 1, (3, h, w)).astype(np.float32)
+        u8 = (torch.from_numpy(img).mul(255).byte().numpy()).transpose(1, 2, 0)          # ToPILImage: mul(255).byte()
+        want = cv2.resize(np.ascontiguousarray(u8), (256, 64)).transpose(2, 0, 1).astype(np.float32) / np.float32(255)
+        assert np.array_equal(parse_visionlan_data(img)[0], want), (h, w)
+    for _ in range(6):
+        b, h, w = int(r.integers(1, 4)), int(r.integers(8, 70)), int(r.integers(16, 200))
+        x = r.uniform(0, 1, (b, 3, h, w)).astype(np.float32)
+        t = torch.nn.functional.interpolate(torch.from_numpy(x), (32, 100), mode="bicubic")
+        want = (0.299 * t[:, 0:1] + 0.587 * t[:, 1:2] + 0.114 * t[:, 2:3]).numpy()
+        assert np.abs(parse_crnn_data(x) - want).max() < TOL_BICUBIC * np.abs(want).max(), (b, h, w)

@@ -103,3 +103,22 @@ def test_bench_algorithmic_byte_model_matches_design():
     assert bench.BYTES_IMG["window_attn_tc"] == 12 * 786_432          # 4 * L * C * 2 B per image-block
     assert bench.FLOPS_IMG["total"] == 11_267_776_512                 # DPMN hot path forward per image
     assert abs(bench.FLOPS_IMG["gemm_tc"] / bench.BYTES_IMG["gemm_tc"] - 80.0) < 0.5
+
+
+def test_oracle_to_mask_against_live_pillow_on_random_images():
+    """oracle/torch_ref.to_mask against the library calls toMask makes (utils/util.py:27-35: ToPILImage, convert('L'),
+    threshold at the mean, invert, ToTensor, repeat) on fresh random images of several sizes.  Skipped without torchvision."""
+    import pytest
+    tv = pytest.importorskip("torchvision")
+    from torchvision import transforms
+    from oracle.torch_ref import to_mask
+    r = np.random.default_rng(5)
+    for _ in range(10):
+        h, w = int(r.integers(4, 48)), int(r.integers(4, 160))
+        img = r.uniform(0, 1, (3, h, w)).astype(np.float32)
+        if _ % 3 == 0:
+            img[:, :, : w // 2] *= 0.3                         # bimodal: both sides of the mean populated unevenly
+        grey = transforms.ToPILImage()(torch.from_numpy(img)).convert("L")
+        thres = np.array(grey).mean()
+        want = transforms.ToTensor()(grey.point(lambda v: 0 if v > thres else 255)).repeat(3, 1, 1).numpy()
+        assert np.array_equal(to_mask(img), want), (h, w)

@@ -52,7 +52,7 @@ BYTES_IMG = {
 
 
 def synth_inputs(seed, B):
-    from oracle import inputs as gen
+    from dpmn_b200 import synth as gen
     r = np.random.default_rng([seed, 99])
     psn = r.uniform(0, 1, size=(B, 4, 32, 128)).astype(np.float32)
     psn[:, 3] = (psn[:, 3] > 0.5)
@@ -64,7 +64,7 @@ def synth_inputs(seed, B):
 def synth_weights(seed):
     """Deterministic non-trivial weights for the 6 PGRMs + CMM (random-init architecture, BASELINE `data`)."""
     from dpmn_b200.schema import PGRMConfig, cmm_schema, pgrm_schema
-    from oracle.params import synth_params
+    from dpmn_b200.synth import synth_params
     pg = [synth_params(pgrm_schema(PGRMConfig(iter=k, mode=(k >= 3))), seed + k) for k in range(6)]
     cm = synth_params(cmm_schema(3, 64), seed + 50)
     return pg, cm

@@ -119,7 +119,7 @@ class HotPathTrainer:
             from .distill import DistillModule
             dev = next(model.parameters()).device
             with torch.random.fork_rng(devices=[]):            # same initial replicas on every rank
-                torch.manual_seed(20240 + model.b1 * 16 + model.b2)
+                torch.default_generator.manual_seed(20240 + model.b1 * 16 + model.b2)   # CPU generator only
                 self.distill = [DistillModule().to(dev).train() for _ in range(model.b1 + model.b2 - 2)]
         params = list(model.parameters()) + [p for m in self.distill for p in m.parameters()]   # base.py:208-221 order
         self.bucket = FlatGradBucket(params)                   # p.grad become views of ONE flat fp32 buffer

@@ -51,6 +51,31 @@ BYTES_IMG = {
 }
 
 
+def ncu_traffic_per_launch(kernel_class):
+    """Mean dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel class, read from the committed summaries of
+    the `ncu --set full` captures (profiles/*.txt, written by tools/ncu_summary.py); None when the class was not captured."""
+    files = {"gemm_tc": ("r01_ncu_full_fp16_v14.txt", ("gemm_tc_kernel", "gemm_res_ln_kernel")),
+             "conv_tc": ("r01_ncu_full_conv_tc_v21.txt", ("conv_tc_kernel<64>", "conv_tc_kernel<128>")),
+             "dwconv": ("r01_ncu_full_dwconv_v2_en1_v23.txt", ("dwconv16_v2_kernel",)),
+             "window_attn_tc": ("r01_ncu_full_fp16_v14.txt", ("attn_tc_kernel",))}
+    if kernel_class not in files:
+        return None
+    name, kernels = files[kernel_class]
+    try:
+        rows = [l.split() for l in open(os.path.join(ROOT, "profiles", name)) if not l.startswith("#")]
+    except OSError:
+        return None
+    vals = []
+    for r in rows[1:]:
+        line = " ".join(r)
+        if any(k in line for k in kernels):
+            nums = [x for x in r if x.replace(".", "", 1).isdigit()]
+            # columns after the kernel name: time_us, dram_rd_MB, dram_wr_MB, ...
+            if len(nums) >= 4:
+                vals.append((float(nums[2]) + float(nums[3])) * 1e6)
+    return float(np.mean(vals)) if vals else None
+
+
 def synth_inputs(seed, B):
     from dpmn_b200 import synth as gen
     r = np.random.default_rng([seed, 99])
@@ -381,7 +406,7 @@ def run_ours(args):
         peak_src += "; class time includes the im2col gathers / 16-bit staging copies around the tcgen05 GEMMs"
     # DRAM bytes per launch of the dominant class from the committed `ncu --set full` capture (mean over its launches in
     # profiles/r01_ncu_full_fp16_v14.txt: dram__bytes_read.sum + dram__bytes_write.sum; writes mostly stay in the 126 MB L2)
-    traffic = {"gemm_tc": 13.3e6, "conv_tc": None}.get(dom) if not train else None
+    traffic = ncu_traffic_per_launch(dom) if not train else None
     roofline = {"bound": "tensor" if not train else train_bound, "kernel": dom, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                 "frac": achieved / tensor_peak, "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": dom_ms / total_prof_ms,

@@ -122,3 +122,11 @@ def test_oracle_to_mask_against_live_pillow_on_random_images():
         thres = np.array(grey).mean()
         want = transforms.ToTensor()(grey.point(lambda v: 0 if v > thres else 255)).repeat(3, 1, 1).numpy()
         assert np.array_equal(to_mask(img), want), (h, w)
+
+
+def test_roofline_traffic_is_read_from_the_committed_ncu_summaries():
+    import bench
+    t = bench.ncu_traffic_per_launch("gemm_tc")
+    assert t is not None and 5e6 < t < 60e6            # mean DRAM bytes per launch of the PGRM GEMM class (ncu --set full)
+    assert bench.ncu_traffic_per_launch("window_attn_tc") == 28397000.0
+    assert bench.ncu_traffic_per_launch("no_such_class") is None

@@ -1,15 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- SR images/sec of the DPMN hot path (6 x PGRM + CMM forward, batch 48/GPU) on B200.
+"""bench.py -- SR images/sec of the DPMN hot path (6 x PGRM + CMM, batch 48/GPU) on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|fp16|bf16] [--impl ours|reference]
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definitions of every key.
-  value          images/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e            images/s through the public module API from pinned HOST buffers, H2D + D2H inside the timed region
-  roofline       the dominant kernel class, timed per launch with CUDA events by the library's profile hook
-  cpu_baseline   the torch-CPU port of the reference (oracle/torch_ref.py) on this host's cores, bounded sample
---impl reference times that same CPU port as the reference arm (the reference is pure PyTorch and
-/root/reference does not exist on the GPU box; oracle/torch_ref.py is pinned to its outputs).
+  value          inference images/s with inputs resident in HBM (CUDA events, max over ranks)     [BASELINE configs[1]]
+  e2e            the same through the public module API from pinned HOST buffers, H2D + D2H inside the timed region
+  train          BASELINE configs[2] in the same line: HotPathTrainer.step at batch 48/GPU -- forward, 7 image losses +
+                 4 distill terms, backward, the flat NCCL all-reduce of the 228.7 MB gradient bucket (N > 1), clip + Adam;
+                 images/s, ms/step, all-reduce ms (on the communication stream / exposed on the compute stream), by_kernel_ms
+  roofline       SURVEY 8d accounting: the dominant kernel class against the TENSOR roofline (the fused block is
+                 tensor-bound, AI ~ 940 FLOP/B); its DRAM traffic against 8d's minimum bytes; a per-class table with both
+                 fractions (HBM GB/s and TFLOP/s); kernels timed per launch with CUDA events by the library's profile hook
+  parity         the output of the timed configuration diffed against the CPU port on the same inputs (8d)
+  cpu_baseline   the torch-CPU port of the reference (oracle/torch_ref.py) on this host's cores, FULL batch-48 forwards
+--impl reference times that same CPU port as the reference arm (the reference is pure PyTorch and /root/reference does
+not exist on the GPU box; oracle/torch_ref.py is pinned to its outputs), on the same config.
 """
 from __future__ import annotations
 
@@ -28,52 +34,62 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 BATCH = 48
+ALPHA = 0.5          # --alpha of every DPMN run (README.md:42): image_sr = alpha * CMM + (1 - alpha) * PSN image
 METRIC = "SR images/sec"
-WORKLOAD = "DPMN hot path forward: 6xPGRM cascade (b1=b2=3, win 2/4/8, dim 96, 6 heads) + CMM, 16x64 -> 32x128, " \
+WORKLOAD = "DPMN hot path forward: 6xPGRM cascade (b1=b2=3, win 2/4/8, dim 96, 6 heads) + CMM + alpha blend, 16x64 -> 32x128, " \
            "batch 48/GPU, synthetic PSN output + priors (configs[1] without the frozen TATT backbone)"
 
 # algorithmic FLOPs per image (2*MAC, matmul/conv only; SURVEY.md 8d / BASELINE.md section 3)
 _PGRM_GEMM = 6 * 2 * (56_623_104 + 25_165_824 + 460_062_720 - 7_077_888)   # q/kv + SK proj + Mlp GEMMs (dw conv excluded)
+_FC1 = 6 * 2 * 75_497_472                                                  # fc1: 2 * 1024 * 96 * 384 per block
 FLOPS_IMG = {"gemm": _PGRM_GEMM, "gemm_tc": _PGRM_GEMM,
-             "window_attn": 6 * 2 * 11_010_048,
+             "mlp_fc1_dw_tc": _FC1 + 6 * 2 * 7_077_888,                     # fc1 + depthwise 3x3 (fused kernel A)
+             "window_attn": 6 * 2 * 11_010_048, "window_attn_tc": 6 * 2 * 11_010_048,
              "conv": 4_459_069_440, "conv_tc": 4_459_069_440 - 14_155_776 * 2 - 42_467_328,   # minus stem / de_1 (own kernels)
              "total": 11_267_776_512}
 
-# algorithmic HBM bytes per image of the bandwidth-bound kernel classes in the 16-bit inference mode:
-# 16-bit activations (s = 2), fp32 residual stream (r = 4), weights excluded (L2-resident, < 0.6 MB per block).
 _L, _C, _HID = 1024, 96, 384
+# SURVEY 8d minimum HBM bytes per image: a fused block reads x_q, x_kv and writes x_kv = 3 L C s (16-bit, s = 2); the
+# stand-alone attention reads q, k, v and writes out = 4 L C s; the CMM reads two images and writes one (fp32)
+MIN_BYTES_IMG = {"block": 3 * _L * _C * 2, "pgrm_blocks": 12 * 3 * _L * _C * 2, "window_attn_tc": 12 * 4 * _L * _C * 2,
+                 "cmm": 3 * 3 * 32 * 128 * 4}
+# bytes the UNFUSED launch sequence moves per image (every intermediate in and out once): kept so that
+# the distance between what is launched today and 8d's minimum stays visible
 BYTES_IMG = {
-    # per block: q (in, out), kv (in, 2 out), SK pooled pass (in), SK output GEMM (in, LN out) and fc2 (LN out) = 10 L*C*s;
-    # the two residual GEMMs read and write the fp32 stream = 4 L*C*r; fc1 out, pointwise in + out, fc2 in = 4 L*hid*s
     "gemm_tc": 12 * (10 * _L * _C * 2 + 4 * _L * _C * 4 + 4 * _L * _HID * 2),
-    "window_attn_tc": 12 * 4 * _L * _C * 2,          # q, k, v in, out: SURVEY 8d
+    "window_attn_tc": 12 * 4 * _L * _C * 2,
     "dwconv": 12 * 2 * _L * _HID * 2,
+    "mlp_fc1_dw_tc": 12 * (_L * _C * 2 + _L * _HID * 2),
 }
 
 
 def ncu_traffic_per_launch(kernel_class):
     """Mean dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel class, read from the committed summaries of
     the `ncu --set full` captures (profiles/*.txt, written by tools/ncu_summary.py); None when the class was not captured."""
-    files = {"gemm_tc": ("r01_ncu_full_fp16_v14.txt", ("gemm_tc_kernel", "gemm_res_ln_kernel")),
-             "conv_tc": ("r01_ncu_full_conv_tc_v21.txt", ("conv_tc_kernel<64>", "conv_tc_kernel<128>")),
-             "dwconv": ("r01_ncu_full_dwconv_v2_en1_v23.txt", ("dwconv16_v2_kernel",)),
-             "window_attn_tc": ("r01_ncu_full_fp16_v14.txt", ("attn_tc_kernel",))}
+    files = {"gemm_tc": (("r02_ncu_full_block.txt", "r01_ncu_full_fp16_v14.txt"), ("gemm_tc_kernel", "gemm_res_ln_kernel")),
+             "conv_tc": (("r01_ncu_full_conv_tc_v21.txt",), ("conv_tc_kernel<64>", "conv_tc_kernel<128>")),
+             "dwconv": (("r01_ncu_full_dwconv_v2_en1_v23.txt",), ("dwconv16_v2_kernel",)),
+             "mlp_fc1_dw_tc": (("r02_ncu_full_block.txt",), ("mlp_fc1_dw_kernel",)),
+             "window_attn_tc": (("r02_ncu_full_block.txt", "r01_ncu_full_fp16_v14.txt"), ("attn_tc_kernel",))}
     if kernel_class not in files:
         return None
-    name, kernels = files[kernel_class]
-    try:
-        rows = [l.split() for l in open(os.path.join(ROOT, "profiles", name)) if not l.startswith("#")]
-        vals = []
-        for r in rows[1:]:
-            line = " ".join(r)
-            if any(k in line for k in kernels):
-                nums = [x for x in r if x.replace(".", "", 1).isdigit()]
-                # numeric columns: id, time_us, dram_rd_MB, dram_wr_MB, ...
-                if len(nums) >= 4:
-                    vals.append((float(nums[2]) + float(nums[3])) * 1e6)
-        return float(np.mean(vals)) if vals else None
-    except Exception:           # evidence lookup must never take the measurement down
-        return None
+    names, kernels = files[kernel_class]
+    for name in names:
+        try:
+            rows = [l.split() for l in open(os.path.join(ROOT, "profiles", name)) if not l.startswith("#")]
+            vals = []
+            for r in rows[1:]:
+                line = " ".join(r)
+                if any(k in line for k in kernels):
+                    nums = [x for x in r if x.replace(".", "", 1).isdigit()]
+                    # numeric columns: id, time_us, dram_rd_MB, dram_wr_MB, ...
+                    if len(nums) >= 4:
+                        vals.append((float(nums[2]) + float(nums[3])) * 1e6)
+            if vals:
+                return float(np.mean(vals))
+        except Exception:           # evidence lookup must never take the measurement down
+            continue
+    return None
 
 
 def synth_inputs(seed, B):
@@ -103,7 +119,7 @@ def load_weights(model, pg, cm):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed regions (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -113,7 +129,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -136,45 +152,155 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_port_throughput(budget_s=20.0, steps=None, warmup=1):
-    """Time oracle/torch_ref.hot_path_forward on the host cores; returns (images/s, description, ms/step, sample B)."""
+def cpu_port_throughput(B, budget_s=25.0, steps=None, warmup=1, keep_output=False):
+    """Time oracle/torch_ref.hot_path_forward (with the alpha blend) on the host cores at the FULL per-GPU batch; returns
+    (images/s, description, ms/step, output of the last forward | None).  Inputs: synth_inputs(0, B) = rank 0's input set 0."""
     from oracle import torch_ref
     torch.set_num_threads(os.cpu_count() or 1)
     pg, cm = synth_weights(2)
     pg = [{k: torch.from_numpy(np.asarray(v)) for k, v in p.items()} for p in pg]
     cm = {k: torch.from_numpy(np.asarray(v)) for k, v in cm.items()}
-    Bs = 8   # bounded sample of the batch-48 workload (same per-image work; the path has no cross-image coupling)
-    psn, p1, p2 = synth_inputs(1, Bs)
+    psn, p1, p2 = synth_inputs(0, B)
     args = (torch.from_numpy(psn), [torch.from_numpy(a) for a in p1], [torch.from_numpy(a) for a in p2])
-    times = []
+    times, out = [], None
     with torch.no_grad():
         for _ in range(warmup):
-            torch_ref.hot_path_forward(pg, cm, *args)
+            out = torch_ref.hot_path_forward(pg, cm, *args, alpha=ALPHA)
         t_end = time.perf_counter() + budget_s
         n = 0
         while (steps is None and time.perf_counter() < t_end and n < 50) or (steps is not None and n < steps):
             t0 = time.perf_counter()
-            torch_ref.hot_path_forward(pg, cm, *args)
+            out = torch_ref.hot_path_forward(pg, cm, *args, alpha=ALPHA)
             times.append(time.perf_counter() - t0)
             n += 1
     med = float(np.median(times))
-    return Bs / med, f"{len(times)} timed forwards of a batch-{Bs} slice of the workload (median), torch {torch.__version__} " \
-                     f"CPU fp32, {torch.get_num_threads()} threads", med * 1e3, Bs
+    desc = f"{len(times)} timed full forwards of the batch-{B} workload (median; {warmup} warm-up), torch {torch.__version__} " \
+           f"CPU fp32, {torch.get_num_threads()} threads"
+    return B / med, desc, med * 1e3, (out if keep_output else None)
+
+
+def infer_config(B, world):
+    return {"workload": WORKLOAD.replace("batch 48/GPU", f"batch {B}/GPU"), "global_batch": B * world,
+            "parallelism": f"replicas x{world} (inference: no collective; the `train` object carries the dp{world} all-reduce)",
+            "l2": "inputs rotate over 4 sets; per-step working set (activations/workspace) >> 126 MB L2"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, sample, ms, Bs = cpu_port_throughput(steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    B = args.batch
+    val, sample, ms, _ = cpu_port_throughput(B, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample_batch": Bs, "l2": "n/a (CPU)"},
+            "config": infer_config(B, world),
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def collect_profile(lib, n_prof):
+    import ctypes as C
+    cap = 40000
+    tags, nk, ms = (C.c_int32 * cap)(), (C.c_int32 * cap)(), (C.c_float * cap)()
+    n = lib.dpmn_profile_collect(tags, nk, ms, cap)
+    agg = {}
+    for j in range(n):
+        name = lib.dpmn_profile_tag_name(tags[j]).decode()
+        a = agg.setdefault(name, [0.0, 0])
+        a[0] += ms[j] / n_prof
+        a[1] += nk[j]
+    return {k: {"ms_per_step": v[0], "launches_per_step": v[1] // n_prof} for k, v in agg.items()}
+
+
+def run_train_leg(args, dev, world, rank, lib, dev_sets, host_sets, barrier, max_over_ranks, steps, warmup, want_e2e):
+    """BASELINE configs[2]: HotPathTrainer.step at batch B/GPU, the reference's drop rates (0.1), train-mode BatchNorm."""
+    from dpmn_b200.pipeline import DPMNHotPath, HostFeeder
+    from dpmn_b200.train import HotPathTrainer
+    B = args.batch
+    n_sets = len(dev_sets)
+    model = DPMNHotPath(precision=args.precision, drop=args.train_drop)
+    pg, cm = synth_weights(2)
+    load_weights(model, pg, cm)
+    model = model.to(dev).train()
+    trainer = HotPathTrainer(model, overlap=not args.no_overlap)
+    with torch.enable_grad():
+        for i in range(warmup):
+            trainer.step(*dev_sets[i % n_sets])
+        barrier()
+        launches0 = lib.dpmn_launch_count()
+        trainer.timing = {}
+        trainer.collect_timing()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            trainer.step(*dev_sets[i % n_sets])
+        e1.record()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        launches = lib.dpmn_launch_count() - launches0
+        comm_ms = {k: v / steps for k, v in trainer.collect_timing().items()}
+        trainer.timing = None
+        # end to end: pinned host batches, H2D of step i+1 overlaps step i, the loss is read back every step
+        e2e = None
+        if want_e2e:
+            feeder = HostFeeder(dev)
+            out_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+            def run_e2e(n):
+                ticket = feeder.stage(list(host_sets[0]))
+                for i in range(n):
+                    nxt = feeder.stage(list(host_sets[(i + 1) % n_sets])) if i + 1 < n else None
+                    y = trainer.step(*feeder.get(ticket))
+                    feeder.release(ticket)
+                    feeder.fetch(y, out_host)
+                    ticket = nxt
+                feeder.drain()
+            run_e2e(2)
+            barrier()
+            t0 = time.perf_counter()
+            e0.record()
+            run_e2e(steps)
+            e1.record()
+            barrier()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+            h2d = sum(t.numel() * 4 for t in [host_sets[0][0]] + host_sets[0][1] + host_sets[0][2] + [host_sets[0][3]])
+            e2e = {"value": B * world / (ms_e2e / steps / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+        # per-kernel-class timing, outside the throughput regions (every rank takes part: the step has a collective)
+        n_prof = 2
+        if rank == 0:
+            lib.dpmn_profile_enable(1)
+        for i in range(n_prof):
+            trainer.step(*dev_sets[i % n_sets])
+        torch.cuda.synchronize()
+        prof = None
+        if rank == 0:
+            prof = collect_profile(lib, n_prof)
+            lib.dpmn_profile_enable(0)
+    ms_step = ms_total / steps
+    res = {"value": B * world / (ms_step / 1e3), "unit": "images/s", "ms_per_step": ms_step, "steps": steps, "warmup": warmup,
+           "global_batch": B * world, "gpu_launches": int(launches),
+           "parallelism": f"dp{world}: one flat fp32 gradient bucket ({trainer.state.n_params} parameters, "
+                          f"{trainer.state.n_params * 4 / 1e6:.1f} MB), NCCL all-reduce through dpmn_allreduce_bucket"
+                          + ("" if world > 1 else " (N=1: no collective issued)"),
+           "allreduce": {"world": world, "bucket_bytes": trainer.state.flat_grads.numel() * 4,
+                         "overlapped_with_backward": bool(trainer.comm is not None and trainer.overlap),
+                         "ms_per_step": {k: round(v, 4) for k, v in comm_ms.items()}},
+           "optimizer": "fused clip_grad_norm_(0.25 per module) + Adam over the flat buffers (dpmn_clip_adam_step)" if trainer.fused
+                        else "torch clip_grad_norm_ + torch.optim.Adam",
+           "drop_rates": args.train_drop, "e2e": e2e}
+    if prof is not None:
+        res["by_kernel_ms"] = {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])}
+        res["whole_step_tflops"] = 3 * FLOPS_IMG["total"] * B / (ms_step / 1e3) / 1e12    # fwd + 2x bwd algorithmic FLOPs
+    if trainer.comm is not None:
+        trainer.comm.close()
+    del trainer, model
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_ours(args):
@@ -193,23 +319,6 @@ def run_ours(args):
     lib = _lib.load()
     assert lib.dpmn_check_device() == 0
 
-    train = args.mode == "train"
-    if train:
-        # configs[2]: the three drop rates at the reference's 0.1 (README.md:42) -> every PGRM forward is the fp32
-        # training sequence with Dropout / DropPath masks; CMM train-mode BatchNorm; fp32 storage everywhere, the GEMMs and
-        # convs of both modules on tcgen05 with 16-bit staged operands
-        model = DPMNHotPath(precision=args.precision, drop=args.train_drop)
-    else:
-        model = DPMNHotPath(precision=args.precision)
-    pg, cm = synth_weights(2)
-    load_weights(model, pg, cm)
-    model = model.to(dev)
-    model.train(train)
-    trainer = None
-    if train:
-        from dpmn_b200.train import HotPathTrainer
-        trainer = HotPathTrainer(model)
-
     B = args.batch
     n_sets = 4   # rotate input sets; the per-step working set (workspaces ~0.7 GB) is far larger than the 126 MB L2
     host_sets, dev_sets = [], []
@@ -220,9 +329,6 @@ def run_ours(args):
               [torch.from_numpy(a).pin_memory() for a in p2], hr.pin_memory())
         host_sets.append(hs)
         dev_sets.append((hs[0].to(dev), [a.to(dev) for a in hs[1]], [a.to(dev) for a in hs[2]], hs[3].to(dev)))
-    h2d_bytes = sum(t.numel() * 4 for t in [host_sets[0][0]] + host_sets[0][1] + host_sets[0][2] + ([host_sets[0][3]] if train else []))
-    out_host = torch.empty((), dtype=torch.float32).pin_memory()      # training: the loss
-    d2h_bytes = 4 if train else B * 3 * 32 * 128 * 4
 
     def barrier():
         if world > 1:
@@ -236,81 +342,103 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def step_resident(i):
-        ds = dev_sets[i % n_sets]
-        if train:
-            return trainer.step(*ds)
-        return model(*ds[:3])
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
 
-    with torch.set_grad_enabled(train):
-        # ---------- value: inputs resident in HBM
-        for i in range(args.warmup):
-            step_resident(i)
-        graphed = None
-        if not train:
-            from dpmn_b200.pipeline import GraphedHotPath
-            n_slots = int(os.environ.get("DPMN_BENCH_SLOTS", "2"))
-            graphed = GraphedHotPath(model, B, dev, slots=n_slots)      # capture once, outside the timed regions
-            for i in range(args.warmup):                          # warm replays
-                graphed.launch(i % n_slots)
-        barrier()
-        launches0 = lib.dpmn_launch_count()
-        clocks = ClockSampler(local)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    tensor_burst = peaks.get("bf16_tflops", 1640.0)
+    hbm_peak = peaks.get("hbm_gbs", 6500.0)
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    dtype = {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.precision]
+
+    if args.mode == "train":
+        tr = run_train_leg(args, dev, world, rank, lib, dev_sets, host_sets, barrier, max_over_ranks, args.steps, args.warmup, True)
+        clk = clocks.stop() if rank == 0 else None
         if rank == 0:
-            clocks.start()
+            prof = tr.get("by_kernel_ms", {})
+            dom = max((k for k in prof if k.startswith("bwd_conv") or k.startswith("bwd_gemm") or k in ("conv_tc", "gemm_tc", "conv", "gemm")),
+                      key=lambda k: prof[k], default=None)
+            fl = {"bwd_gemm": 2 * _PGRM_GEMM, "bwd_gemm_tc": 2 * _PGRM_GEMM, "bwd_conv": 2 * FLOPS_IMG["conv"],
+                  "conv_tc": 2 * FLOPS_IMG["conv"], "gemm_tc": 2 * _PGRM_GEMM, "conv": 2 * FLOPS_IMG["conv"], "gemm": 2 * _PGRM_GEMM}
+            roof = None
+            if dom:
+                ach = fl[dom] * B / (prof[dom] / 1e3) / 1e12
+                roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
+                        "traffic": None, "peak_source": peak_src + "; class time includes the im2col gathers / 16-bit staging copies",
+                        "whole_step_tflops": tr.get("whole_step_tflops"), "by_kernel_ms": prof}
+            line = {"metric": "SR images/sec (training step)", "value": tr["value"], "unit": "images/s", "n_gpus": world,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": tr["ms_per_step"], "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+                    "config": {"workload": "DPMN hot path TRAINING step (configs[2] without the frozen TATT backbone and recognisers): "
+                                           "6xPGRM (drop rates " + str(args.train_drop) + ") + CMM (train-mode BN), 7 image losses + 4 "
+                                           "DistillModule terms, backward, gradient all-reduce, per-module clip 0.25, Adam; batch "
+                                           + str(B) + "/GPU", "global_batch": B * world, "parallelism": tr["parallelism"],
+                               "l2": "inputs rotate over 4 sets; per-step working set >> 126 MB L2"},
+                    "e2e": tr["e2e"], "gpu_launches": tr["gpu_launches"], "clocks": clk, "roofline": roof, "cpu_baseline": None,
+                    "train": tr}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ================= inference (configs[1]) =================
+    model = DPMNHotPath(precision=args.precision)
+    pg, cm = synth_weights(2)
+    load_weights(model, pg, cm)
+    model = model.to(dev).eval()
+    model.alpha = ALPHA
+    h2d_bytes = sum(t.numel() * 4 for t in [host_sets[0][0]] + host_sets[0][1] + host_sets[0][2])
+    d2h_bytes = B * 3 * 32 * 128 * 4
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            model(*dev_sets[i % n_sets][:3])
+        from dpmn_b200.pipeline import GraphedHotPath
+        n_slots = int(os.environ.get("DPMN_BENCH_SLOTS", "2"))
+        graphed = GraphedHotPath(model, B, dev, slots=n_slots)      # capture once, outside the timed regions
+        for i in range(args.warmup):                                 # warm replays
+            graphed.launch(i % n_slots)
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        host_enqueue_ms = None
+
+        # ---------- value: inputs resident in HBM.  Each batch = a device-to-device copy of its inputs into the slot's static
+        # buffers + one CUDA-graph replay; two slots are in flight, the timed region ends when the last is complete
+        def run_graphed_resident(n):
+            t_host = time.perf_counter()
+            begin = torch.cuda.Event()
+            begin.record(torch.cuda.current_stream(dev))
+            for i in range(n):
+                slot = graphed.slots[i % n_slots]
+                ds = dev_sets[i % n_sets]
+                slot["stream"].wait_event(begin)
+                with torch.cuda.stream(slot["stream"]):
+                    slot["psn"].copy_(ds[0], non_blocking=True)
+                    for d_, s_ in zip(slot["p1"] + slot["p2"], ds[1] + ds[2]):
+                        d_.copy_(s_, non_blocking=True)
+                graphed.launch(i % n_slots)
+            ms = (time.perf_counter() - t_host) * 1e3 / n
+            for sl in graphed.slots:
+                torch.cuda.current_stream(dev).wait_event(sl["done"])
+            return ms
         e0.record()
-        if train:
-            for i in range(args.steps):
-                step_resident(i)
-        else:
-            # throughput: each batch = a device-to-device copy of its (HBM-resident) inputs into the slot's static
-            # buffers + one CUDA-graph replay; two slots are in flight, the timed region ends when the last is complete
-            def run_graphed_resident(n):
-                t_host = time.perf_counter()
-                begin = torch.cuda.Event()
-                begin.record(torch.cuda.current_stream(dev))
-                for i in range(n):
-                    slot = graphed.slots[i % n_slots]
-                    ds = dev_sets[i % n_sets]
-                    slot["stream"].wait_event(begin)
-                    with torch.cuda.stream(slot["stream"]):
-                        slot["psn"].copy_(ds[0], non_blocking=True)
-                        for d_, s_ in zip(slot["p1"] + slot["p2"], ds[1] + ds[2]):
-                            d_.copy_(s_, non_blocking=True)
-                    graphed.launch(i % n_slots)
-                ms = (time.perf_counter() - t_host) * 1e3 / n
-                for sl in graphed.slots:
-                    torch.cuda.current_stream(dev).wait_event(sl["done"])
-                return ms
-            host_enqueue_ms = run_graphed_resident(args.steps)
+        host_enqueue_ms = run_graphed_resident(args.steps)
         e1.record()
         barrier()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
-        launches = (lib.dpmn_launch_count() - launches0) if train else args.steps * graphed.kernels_per_replay
-        clk = clocks.stop() if rank == 0 else None
+        launches = args.steps * graphed.kernels_per_replay
+
         # ---------- e2e: pinned host buffers, H2D + D2H inside the timed region
-        from dpmn_b200.pipeline import HostFeeder
-        feeder = HostFeeder(dev)
         h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         outs_host = [torch.empty((B, 3, 32, 128), dtype=torch.float32).pin_memory() for _ in range(4)]
 
         def run_e2e(n):
             """n steps from pinned host memory: H2D of step i+1 and D2H of step i-1 overlap the kernels of step i."""
-            if train:
-                def batch(i):
-                    hs = host_sets[i % n_sets]
-                    return [hs[0], hs[1], hs[2], hs[3]]
-                ticket = feeder.stage(batch(0))
-                for i in range(n):
-                    nxt = feeder.stage(batch(i + 1)) if i + 1 < n else None
-                    y = trainer.step(*feeder.get(ticket))
-                    feeder.release(ticket)
-                    feeder.fetch(y, out_host)
-                    ticket = nxt
-                feeder.drain()
-                return
             fetched = [None] * n_slots
             for i in range(n):
                 k = i % n_slots
@@ -343,32 +471,39 @@ def run_ours(args):
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
         ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+
+        # ---------- the output of the timed configuration, for the parity diff (rank 0's input set 0 through the graph)
+        timed_out = None
+        if rank == 0:
+            slot = graphed.slots[0]
+            ds = dev_sets[0]
+            with torch.cuda.stream(slot["stream"]):
+                slot["psn"].copy_(ds[0], non_blocking=True)
+                for d_, s_ in zip(slot["p1"] + slot["p2"], ds[1] + ds[2]):
+                    d_.copy_(s_, non_blocking=True)
+            graphed.launch(0).synchronize()
+            timed_out = slot["out"].detach().float().cpu().numpy().copy()
+
         # ---------- per-kernel-class timing (roofline leg), outside the throughput regions
         prof = None
-        n_prof = 2
-        if rank != 0 and train and world > 1:
-            for i in range(n_prof):       # the training step contains a collective: every rank has to take part
-                step_resident(i)
-            torch.cuda.synchronize()
         if rank == 0:
-            if not train:
-                model.concurrent_branches = False     # one stream: per-launch event times are not inflated by overlap
+            n_prof = 2
+            model.concurrent_branches = False     # one stream: per-launch event times are not inflated by overlap
             lib.dpmn_profile_enable(1)
             for i in range(n_prof):
-                step_resident(i)
+                model(*dev_sets[i % n_sets][:3])
             torch.cuda.synchronize()
-            import ctypes as C
-            cap = 20000
-            tags, nk, ms = (C.c_int32 * cap)(), (C.c_int32 * cap)(), (C.c_float * cap)()
-            n = lib.dpmn_profile_collect(tags, nk, ms, cap)
+            prof = collect_profile(lib, n_prof)
             lib.dpmn_profile_enable(0)
-            agg = {}
-            for j in range(n):
-                name = lib.dpmn_profile_tag_name(tags[j]).decode()
-                a = agg.setdefault(name, [0.0, 0])
-                a[0] += ms[j] / n_prof
-                a[1] += nk[j]
-            prof = {k: {"ms_per_step": v[0], "launches_per_step": v[1] // n_prof} for k, v in agg.items()}
+    del graphed
+    torch.cuda.empty_cache()
+
+    # ================= training (configs[2]) in the same line =================
+    train = None
+    if not args.no_train:
+        t_steps = args.train_steps if args.train_steps > 0 else max(3, min(args.steps, 10))
+        train = run_train_leg(args, dev, world, rank, lib, dev_sets, host_sets, barrier, max_over_ranks, t_steps, 3, False)
+    clk = clocks.stop() if rank == 0 else None
 
     ms_step = ms_total / args.steps
     value = B * world / (ms_step / 1e3)
@@ -378,76 +513,81 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)" if peaks else "fallback"
+    # ---------- roofline, SURVEY 8d accounting
     flops_img = dict(FLOPS_IMG)
-    if train:
-        # backward classes: data + weight gradient = 2x the forward contraction FLOPs of the same layers
-        flops_img = {"bwd_gemm": 2 * _PGRM_GEMM, "bwd_conv": 2 * FLOPS_IMG["conv"], "gemm": 2 * _PGRM_GEMM + 0,
-                     "conv": 2 * FLOPS_IMG["conv"], "total": 3 * FLOPS_IMG["total"] + FLOPS_IMG["total"]}
-        # ("gemm"/"conv": fp32 forward recompute inside backward (+ the CMM's own fp32 forward); total = fwd + recompute + bwd)
+    ridge = tensor_peak * 1e12 / (hbm_peak * 1e9)
+    classes = {}
+    for k, v in prof.items():
+        ms_k = v["ms_per_step"]
+        row = {"ms_per_step": round(ms_k, 4), "launches_per_step": v["launches_per_step"]}
+        if k in flops_img:
+            tf = flops_img[k] * B / (ms_k / 1e3) / 1e12
+            row.update({"tflops": round(tf, 2), "tensor_frac_sustained": round(tf / tensor_peak, 4), "tensor_frac_burst": round(tf / tensor_burst, 4)})
+        if k in BYTES_IMG:
+            gb = BYTES_IMG[k] * B / (ms_k / 1e3) / 1e9
+            row.update({"launched_gbs": round(gb, 1), "hbm_frac_of_launched_bytes": round(gb / hbm_peak, 4)})
+        classes[k] = row
+    total_prof_ms = sum(v["ms_per_step"] for v in prof.values())
     dom = max((k for k in prof if k in flops_img and k != "total"), key=lambda k: prof[k]["ms_per_step"])
     dom_ms = prof[dom]["ms_per_step"]
     achieved = flops_img[dom] * B / (dom_ms / 1e3) / 1e12
-    total_prof_ms = sum(v["ms_per_step"] for v in prof.values())
-    train_bound = "tensor"
-    if train and args.precision == "fp32":
-        tensor_peak = 75.0   # B200 fp32 FFMA peak (148 SMs x 128 lanes x 2 x 1.965 GHz): the fp32 mode is all SIMT
-        peak_src = "nominal fp32 FFMA peak (precision fp32: every contraction is an FFMA kernel)"
-        train_bound = "fp32-simt"
-    elif train:
-        # 16-bit modes: the contractions of this class run on tcgen05 through 16-bit staged operands (lin_*_tc, the CMM's
-        # im2col + NT GEMM), so the class -- gathers, staging copies and GEMMs together -- is quoted against the tensor peak
-        peak_src += "; class time includes the im2col gathers / 16-bit staging copies around the tcgen05 GEMMs"
-    # DRAM bytes per launch of the dominant class from the committed `ncu --set full` capture (mean over its launches in
-    # profiles/r01_ncu_full_fp16_v14.txt: dram__bytes_read.sum + dram__bytes_write.sum; writes mostly stay in the 126 MB L2)
-    traffic = ncu_traffic_per_launch(dom) if not train else None
-    roofline = {"bound": "tensor" if not train else train_bound, "kernel": dom, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                "frac": achieved / tensor_peak, "traffic": traffic, "peak_source": peak_src,
-                "share_of_step": dom_ms / total_prof_ms,
-                "launches_per_step": prof[dom]["launches_per_step"],
+    # the PGRM block classes together (every launch between the patch embed and the head) against 8d's fused-block figures
+    block_keys = [k for k in ("gemm_tc", "gemm", "mlp_fc1_dw_tc", "dwconv", "window_attn_tc", "window_attn", "sk_gate", "layernorm") if k in prof]
+    block_ms = sum(prof[k]["ms_per_step"] for k in block_keys)
+    block_flops = 12 * 552_867_840
+    traffic = ncu_traffic_per_launch(dom)
+    traffic_step = None
+    if traffic is not None:
+        traffic_step = traffic * prof[dom]["launches_per_step"]
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": achieved / tensor_peak, "frac_of_burst_peak": achieved / tensor_burst,
+                "traffic": traffic, "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "accounting": "SURVEY 8d: the fused PGRM block is tensor-bound (AI = 552.9 MFLOP / 589 824 B = 937 FLOP/B vs ridge "
+                              f"{ridge:.0f}); achieved = algorithmic FLOPs of the class / its summed launch time",
+                "share_of_step": dom_ms / total_prof_ms, "launches_per_step": prof[dom]["launches_per_step"],
                 "avg_launch_ms": dom_ms / max(1, prof[dom]["launches_per_step"]),
+                "pgrm_blocks": {"classes": block_keys, "ms_per_step": round(block_ms, 4),
+                                "tflops": round(block_flops * B / (block_ms / 1e3) / 1e12, 2),
+                                "tensor_frac_sustained": round(block_flops * B / (block_ms / 1e3) / 1e12 / tensor_peak, 4),
+                                "min_bytes_per_step_8d": MIN_BYTES_IMG["pgrm_blocks"] * B,
+                                "hbm_frac_at_min_bytes": round(MIN_BYTES_IMG["pgrm_blocks"] * B / (block_ms / 1e3) / 1e9 / hbm_peak, 4)},
+                "dram_traffic_per_step": traffic_step,
+                "traffic_over_8d_minimum": (traffic_step / (MIN_BYTES_IMG["pgrm_blocks"] * B)) if traffic_step else None,
+                "unfused_bytes_per_step": BYTES_IMG.get(dom, 0) * B,
                 "whole_step_tflops": flops_img["total"] * B / (ms_step / 1e3) / 1e12,
-                "by_kernel_ms": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
-    if not train and dom in BYTES_IMG:
-        # The dominant class is bandwidth-bound by arithmetic intensity (FLOPs / algorithmic bytes below the ridge
-        # tensor_peak / hbm_peak): its roofline is the HBM one.  achieved = algorithmic bytes per launch / launch time.
-        hbm_peak = peaks.get("hbm_gbs", 6500.0)
-        ai = flops_img[dom] / BYTES_IMG[dom]
-        if ai < tensor_peak * 1e12 / (hbm_peak * 1e9):
-            gbs = BYTES_IMG[dom] * B / (dom_ms / 1e3) / 1e9
-            roofline.update({"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                             "peak_source": ("measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback"),
-                             "algorithmic_bytes_per_launch": BYTES_IMG[dom] * B / max(1, prof[dom]["launches_per_step"]),
-                             "arithmetic_intensity_flop_per_byte": ai,
-                             "tensor_view": {"achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                                             "frac": achieved / tensor_peak}})
+                "whole_step_tensor_frac": flops_img["total"] * B / (ms_step / 1e3) / 1e12 / tensor_peak,
+                "attention": None,
+                "by_kernel_ms": {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])},
+                "classes": classes}
+    if "window_attn_tc" in prof:    # the stand-alone attention is HBM-bound (AI 14 FLOP/B): its own roofline is the HBM one
+        a_ms = prof["window_attn_tc"]["ms_per_step"]
+        gbs = MIN_BYTES_IMG["window_attn_tc"] * B / (a_ms / 1e3) / 1e9
+        roofline["attention"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                 "tflops": FLOPS_IMG["window_attn_tc"] * B / (a_ms / 1e3) / 1e12,
+                                 "traffic": ncu_traffic_per_launch("window_attn_tc"),
+                                 "avg_launch_ms": a_ms / max(1, prof["window_attn_tc"]["launches_per_step"])}
 
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline and not train:
-        v, sample, _, _ = cpu_port_throughput(budget_s=15.0)
+    cpu, parity = None, None
+    if world == 1 and not args.no_cpu_baseline:
+        v, sample, _, ref_out = cpu_port_throughput(B, budget_s=25.0, keep_output=True)
         cpu = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+        if timed_out is not None and ref_out is not None:
+            ref = ref_out.numpy()
+            err = float(np.abs(timed_out - ref).max() / np.abs(ref).max())
+            bar = {"fp32": 1e-4, "fp16": 2e-3, "bf16": 1e-2}[args.precision]
+            parity = {"max_abs_err_over_max_ref": err, "bar": bar, "ok": bool(err < bar),
+                      "what": f"output of the timed CUDA-graph configuration on input set 0 (batch {B}, 6 PGRM + CMM + alpha blend) vs "
+                              "oracle/torch_ref.hot_path_forward on the same inputs and weights (fp32 CPU)"}
+            if not parity["ok"]:
+                print(f"bench.py: PARITY FAILURE in the timed configuration: {err:.3e} >= {bar}", file=sys.stderr)
 
-    workload = WORKLOAD.replace("batch 48/GPU", f"batch {B}/GPU") if not train else (
-        "DPMN hot path TRAINING step: 6xPGRM cascade (drop / attn_drop / drop_path " + str(args.train_drop) + ") + CMM forward (train-mode BN), 7 image "
-        "losses + 4 DistillModule terms, backward through dpmn_pgrm_backward / dpmn_cmm_backward (fp32), flat gradient all-reduce, per-module "
-        "clip 0.25, Adam; 16x64 -> 32x128, batch " + str(B) + "/GPU, synthetic PSN output / priors / HR (configs[2] without the "
-        "frozen TATT backbone and recognisers)")
-    line = {"metric": METRIC if not train else "SR images/sec (training step)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.precision],
-            "data": "synthetic",
-            "config": {"workload": workload, "global_batch": B * world,
-                       "parallelism": f"replicas x{world} (no collective: inference)" if not train else
-                       f"dp{world}: one flat NCCL all-reduce over the 57.2M-parameter fp32 gradient bucket per step",
-                       "l2": f"inputs rotate over {n_sets} sets; per-step working set (activations/workspace) >> 126 MB L2"},
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": infer_config(B, world),
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clk, "roofline": roofline,
+            "cpu_baseline": cpu, "parity": parity, "train": train}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -461,10 +601,13 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("DPMN_PRECISION", "fp16"))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
-                    help="infer = BASELINE configs[1] (the headline line); train = configs[2] training step")
+                    help="infer = BASELINE configs[1] headline line with the configs[2] `train` object inside; train = the training step alone")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the configs[2] training leg of the default line")
+    ap.add_argument("--no-overlap", action="store_true", help="training: all-reduce the whole bucket after the backward (no overlap)")
+    ap.add_argument("--train-steps", type=int, default=0, help="timed training steps of the default line (0 = min(steps, 10))")
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU per step (48 = configs[1]/[2]; 64 = configs[3])")
-    ap.add_argument("--train-drop", type=float, default=0.1, help="drop / attn_drop / drop_path rate of --mode train")
+    ap.add_argument("--train-drop", type=float, default=0.1, help="drop / attn_drop / drop_path rate of the training leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

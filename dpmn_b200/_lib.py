@@ -82,7 +82,9 @@ class CmmDesc(C.Structure):
                 ("de6_w", fp), ("de6_b", fp), ("de6_bn", Bn),
                 ("dec", CmmStage * 4),
                 ("de1_w", fp), ("de1_b", fp),
-                ("prepared", fp), ("prepared_valid", C.c_int32), ("flags", C.c_int32)]
+                ("prepared", fp), ("prepared_valid", C.c_int32), ("flags", C.c_int32),
+                ("blend_input", fp), ("blend_input_batch_stride", C.c_int64), ("blend_alpha", C.c_float),
+                ("reserved_", C.c_int32)]
 
 
 class BnGrads(C.Structure):
@@ -157,6 +159,15 @@ SYMBOLS = {
     "dpmn_pgrm_backward": (C.c_int, [C.POINTER(PgrmDesc), _vp, _vp, _vp, C.POINTER(PgrmGrads), _vp, _sz, _vp]),
     "dpmn_cmm_backward_workspace_bytes": (_sz, [C.POINTER(CmmDesc)]),
     "dpmn_cmm_backward": (C.c_int, [C.POINTER(CmmDesc), _vp, _vp, _vp, C.POINTER(CmmGrads), _vp, _sz, _vp]),
+    "dpmn_nccl_available": (C.c_int, []),
+    "dpmn_nccl_version": (C.c_int, []),
+    "dpmn_nccl_unique_id": (C.c_int, [_vp]),
+    "dpmn_nccl_comm_init": (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp)]),
+    "dpmn_nccl_comm_destroy": (C.c_int, [_vp]),
+    "dpmn_allreduce_bucket": (C.c_int, [_vp, _vp, _sz, _i32, _vp]),
+    "dpmn_clip_adam_workspace_bytes": (_sz, [_i32]),
+    "dpmn_clip_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(C.c_int64), _i32, C.c_float, C.c_float, C.c_float,
+                                      C.c_float, C.c_float, C.c_float, C.c_int64, _vp, _sz, _vp]),
 }
 
 _lib = None
@@ -167,6 +178,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    import torch  # noqa: F401  (first: the library resolves NCCL from the copy torch has already mapped, see optim_nccl.cu)
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             f"dpmn_b200: {LIB_PATH} is missing.  Build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .pgrm import ParamTree, PreparedWeights, workspace
+from .pgrm import ParamTree, PreparedWeights, grad_sink_views, workspace
 from .schema import cmm_schema
 
 
@@ -58,12 +58,13 @@ class _CMMFunction(torch.autograd.Function):
 class ComplementationModulationModule(ParamTree):
     """cmm.py:80-81 signature.  Extra keyword `precision` as in `PGRM`."""
 
-    def __init__(self, c_img=3, norm='batch', act_en='leaky_relu', act_de='relu', cnum=64, precision="fp32"):
+    def __init__(self, c_img=3, norm='batch', act_en='leaky_relu', act_de='relu', cnum=64, precision=None):
         super().__init__()
         if norm != 'batch' or act_en != 'leaky_relu' or act_de != 'relu':
             raise NotImplementedError("dpmn_b200 CMM implements the configuration DPMN instantiates "
                                       "(norm='batch', act_en='leaky_relu', act_de='relu'; super_resolution.py:72)")
-        self.c_img, self.cnum, self.precision = int(c_img), int(cnum), precision
+        from .pgrm import resolve_precision
+        self.c_img, self.cnum, self.precision = int(c_img), int(cnum), resolve_precision(precision)
         schema = cmm_schema(self.c_img, self.cnum)
         shapes = {n: s for n, s, _ in schema}
         for name, shape, kind in schema:
@@ -121,11 +122,16 @@ class ComplementationModulationModule(ParamTree):
         d.de1_w, d.de1_b = self._ptr("de_1.1.weight"), self._ptr("de_1.1.bias")
         return d
 
-    def forward(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor, blend_with: torch.Tensor = None, alpha: float = 0.5) -> torch.Tensor:
+        """cmm.py:120 signature.  Extra keywords (eval / test call sites, super_resolution.py:449,705): with `blend_with`
+        = images_lr_psn[:, :3] the result is alpha * CMM(x1, x2) + (1 - alpha) * blend_with, the blend fused into the kernel
+        that writes the output."""
         params = [p for _, p in self.named_parameters()]
         if torch.is_grad_enabled() and (x1.requires_grad or x2.requires_grad or any(p.requires_grad for p in params)):
-            return _CMMFunction.apply(self, x1, x2, *params)
-        return self._forward_impl(x1, x2)
+            y = _CMMFunction.apply(self, x1, x2, *params)
+            # under autograd the blend stays a torch expression (the reference's own line); the training loss never uses it
+            return y if blend_with is None else alpha * y + (1 - alpha) * blend_with
+        return self._forward_impl(x1, x2, blend_with=blend_with, alpha=alpha)
 
     def _backward(self, x1, x2, d_out, training, need_x1=True, need_x2=True, fwd_ws=None):
         """d_out (B, c_img, H, W) -> (d x1 | None, d x2 | None, [d param in named_parameters order])."""
@@ -139,12 +145,16 @@ class ComplementationModulationModule(ParamTree):
         d_out = d_out.contiguous().float()
         names = [n for n, _ in self.named_parameters()]
         params = [p for _, p in self.named_parameters()]
+        sink = grad_sink_views(self, names, params)
         with torch.cuda.device(dev):
-            flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-            views, off = {}, 0
-            for n, p in zip(names, params):
-                views[n] = flat[off: off + p.numel()].view_as(p)
-                off += p.numel()
+            if sink is not None:
+                views = sink          # accumulate straight into the caller's gradient bucket
+            else:
+                flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+                views, off = {}, 0
+                for n, p in zip(names, params):
+                    views[n] = flat[off: off + p.numel()].view_as(p)
+                    off += p.numel()
 
             def gp(name):
                 return views[name].data_ptr()
@@ -183,9 +193,14 @@ class ComplementationModulationModule(ParamTree):
             rc = lib.dpmn_cmm_backward(C.byref(d), x1.data_ptr(), x2.data_ptr(), d_out.data_ptr(), C.byref(g),
                                        ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "dpmn_cmm_backward")
+        hook = getattr(self, "_after_backward", None)
+        if hook is not None:
+            hook(self)           # e.g. the trainer starts the all-reduce of this module's bucket segment (dpmn_b200.train)
+        if sink is not None:
+            return d_x1, d_x2, [None] * len(params)
         return d_x1, d_x2, [views[n] if p.requires_grad else None for n, p in zip(names, params)]
 
-    def _forward_impl(self, x1: torch.Tensor, x2: torch.Tensor, keep_workspace: bool = False):
+    def _forward_impl(self, x1: torch.Tensor, x2: torch.Tensor, keep_workspace: bool = False, blend_with=None, alpha=0.5):
         lib = _lib.load()
         for n, t in (("x1", x1), ("x2", x2)):
             if not t.is_cuda:
@@ -196,10 +211,17 @@ class ComplementationModulationModule(ParamTree):
             raise ValueError("CMM.forward: x1 and x2 must have the same shape")
         x1, x2 = x1.contiguous(), x2.contiguous()
         B, _, H, W = x1.shape
-        if self.training and B * (H // 32) * (W // 32) == 1:
-            # nn.BatchNorm2d raises for a single value per channel in training mode
-            raise ValueError("Expected more than 1 value per channel when training")
+        # (no BatchNorm of the CMM ever sees a single value per channel: the 1x1 bottleneck en_6 has none, the smallest
+        #  normalised maps are en_5 / de_6 at (H/16, W/16) >= 2x2 -- the reference accepts B = 1 at 32x32, cmm.py:91-93,107-111)
         d = self._descriptor(B, H, W)
+        if blend_with is not None:
+            if not blend_with.is_cuda or blend_with.dtype != torch.float32 or tuple(blend_with.shape) != tuple(x1.shape):
+                raise ValueError(f"dpmn_b200 CMM: blend_with must be an fp32 CUDA tensor of shape {tuple(x1.shape)}")
+            if not (blend_with.stride(3) == 1 and blend_with.stride(2) == W and blend_with.stride(1) == H * W):
+                blend_with = blend_with.contiguous()
+            d.blend_input = blend_with.data_ptr()
+            d.blend_input_batch_stride = blend_with.stride(0) if B > 1 else self.c_img * H * W
+            d.blend_alpha = float(alpha)
         dev = x1.device
         with torch.cuda.device(dev):
             prep_key = self._prepared.attach(self, d, lib.dpmn_cmm_prepared_bytes(C.byref(d)), dev)
@@ -214,7 +236,8 @@ class ComplementationModulationModule(ParamTree):
             rc = lib.dpmn_cmm_forward(C.byref(d), x1.data_ptr(), x2.data_ptr(), out.data_ptr(), ws.data_ptr(),
                                       ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "dpmn_cmm_forward")
-        self._prepared.key = prep_key
+        if not self.training:    # only the eval-mode tensor-core path stages `prepared` (cmm_forward_tc)
+            self._prepared.key = prep_key
         if self.training:
             for name, buf in self.named_buffers():
                 if name.endswith("num_batches_tracked"):

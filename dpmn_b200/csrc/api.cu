@@ -21,11 +21,13 @@ std::atomic<uint64_t> g_launches{0};
 enum KTag { T_PATCH_EMBED = 0, T_LAYERNORM, T_GEMM, T_WINDOW_ATTN, T_SK_GATE, T_DWCONV, T_HEAD, T_CONV, T_BN,
             T_SE_GATE, T_CONVERT, T_GEMM_TC, T_CONV_TC, T_PREP, T_CONV_STEM, T_ATTN_TC,
             T_BWD_GEMM, T_BWD_GEMM_TC, T_BWD_MISC, T_BWD_LN, T_BWD_SK, T_BWD_ATTN, T_BWD_DWCONV, T_BWD_HEAD, T_BWD_EMBED, T_BWD_CONV, T_BWD_BN, T_LOSS, T_DISTILL,
+            T_MLP_A, T_OPTIM,
             T_COUNT };
 const char* const kTagNames[T_COUNT] = {"patch_embed", "layernorm", "gemm", "window_attn", "sk_gate",
                                         "dwconv", "head", "conv", "bn_affine", "se_gate", "convert", "gemm_tc", "conv_tc", "weight_prep", "conv_stem", "window_attn_tc",
                                         "bwd_gemm", "bwd_gemm_tc", "bwd_misc", "bwd_layernorm", "bwd_sk_gate", "bwd_window_attn", "bwd_dwconv", "bwd_head",
-                                        "bwd_patch_embed", "bwd_conv", "bwd_batchnorm", "loss_mask", "distill"};
+                                        "bwd_patch_embed", "bwd_conv", "bwd_batchnorm", "loss_mask", "distill",
+                                        "mlp_fc1_dw_tc", "optimizer"};
 struct ProfRec { int tag; int n; cudaEvent_t e0, e1; };
 bool g_prof = false;
 std::mutex g_prof_mu;
@@ -352,13 +354,19 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
     }
     // ---- K4: norm2 + Mlp (pgrm.py:330, 29-41)
     if (!fuse_ln) DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm2_w, bw.norm2_b, w.ln, at, rows, C, st), 1);
-    {
-      GemmCall g;   // fc1 + GELU
-      g.A = fuse_ln ? w.ln2 : w.ln; g.lda = C; g.Bm = op.fc1_w; g.ldb = C; g.C = w.h; g.ldc = hid; g.out_type = at;
-      g.M = rows; g.N = hid; g.K = C; g.bias = bw.fc1_b; g.bias_mode = 1; g.act = 1;
-      DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
+    static const bool fused_a_on = !(getenv("DPMN_FUSED_MLP_A") && atoi(getenv("DPMN_FUSED_MLP_A")) == 0);
+    if (prec != DPMN_PREC_F32 && fused_a_on && mlp_fc1_dw_supported(C, hid, L)) {
+      // fc1 + GELU + depthwise 3x3 + GELU in one kernel: the hidden tensor never leaves the SM between the two
+      DPMN_RUN(T_MLP_A, launch_mlp_fc1_dw(fuse_ln ? w.ln2 : w.ln, op.fc1_w, bw.fc1_b, bw.dw_w, bw.dw_b, w.dt, B, at, st), 1);
+    } else {
+      {
+        GemmCall g;   // fc1 + GELU
+        g.A = fuse_ln ? w.ln2 : w.ln; g.lda = C; g.Bm = op.fc1_w; g.ldb = C; g.C = w.h; g.ldc = hid; g.out_type = at;
+        g.M = rows; g.N = hid; g.K = C; g.bias = bw.fc1_b; g.bias_mode = 1; g.act = 1;
+        DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
+      }
+      DPMN_RUN(T_DWCONV, launch_dwconv(w.h, w.dt, at, bw.dw_w, bw.dw_b, B, L, hid, st), 1);
     }
-    DPMN_RUN(T_DWCONV, launch_dwconv(w.h, w.dt, at, bw.dw_w, bw.dw_b, B, L, hid, st), 1);
     {
       GemmCall g;   // pointwise conv: per image (hid x hid) * (hid x L), written (hid, L) = the raw view
       g.A = op.pw_w; g.lda = hid; g.Bm = w.dt; g.b_bs = (long long)L * hid; g.ldb = hid;
@@ -761,7 +769,8 @@ int cmm_forward_tc(const dpmn_cmm_desc* d, const float* x1, const float* x2, flo
     g.A = w.cat[1]; g.lda = 3 * c; g.Bm = w.w_de1; g.ldb = 3 * c; g.op_type = t;
     g.C = w.P; g.ldc = 32; g.out_type = DT_F32; g.M = B * H * W; g.N = 32; g.K = 3 * c;
     DPMN_RUN(T_GEMM_TC, launch_gemm_tc(g, st), 1);
-    DPMN_RUN(T_CONV_STEM, launch_de1_gather(w.P, 32, d->de1_b, out, B, H, W, D.ci, st), 1);
+    const long long blend_bs = d->blend_input_batch_stride ? d->blend_input_batch_stride : (long long)D.ci * H * W;
+    DPMN_RUN(T_CONV_STEM, launch_de1_gather(w.P, 32, d->de1_b, out, B, H, W, D.ci, st, d->blend_input, blend_bs, d->blend_alpha), 1);
   }
   return 0;
 }
@@ -1115,6 +1124,11 @@ static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const flo
     a.B = B; a.Cin = 3 * c; a.H = H; a.W = W; a.Cout = d->c_img; a.Ho = H; a.Wo = W;
     a.k = 3; a.stride = 1; a.pad = 1; a.transposed = 1;
     DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
+  }
+  if (d->blend_input != nullptr) {   // alpha * CMM + (1 - alpha) * PSN image (super_resolution.py:449,705)
+    const long long per = (long long)d->c_img * H * W;
+    DPMN_RUN(T_CONV_STEM, launch_alpha_blend(out, d->blend_input, d->blend_input_batch_stride ? d->blend_input_batch_stride : per,
+                                             d->blend_alpha, B, per, st), 1);
   }
   return 0;
 }

@@ -423,20 +423,13 @@ static int launch_attn_tc_t(const AttnTcArgs& a, cudaStream_t st) {
                                    D == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    DPMN_CUDA_TRY(cudaGetDevice(&dev));
-    DPMN_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  DPMN_CUDA_TRY(current_device_sms(&num_sms));
   const int grid = p.total_units < num_sms ? p.total_units : num_sms;
   auto kern = attn_tc_kernel<D, T>;
   constexpr int smem = AttnSmem<D>::TOTAL;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DPMN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr;      // per template instantiation, per device
+  DPMN_CUDA_TRY(attr.smem_attr(kern, smem));
   kern<<<grid, AT_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);
   DPMN_LAUNCH_CHECK();
   return 0;

@@ -347,7 +347,8 @@ int launch_se_gate_nhwc(const float* z6, void* zg, DType t, const float* fc1_w, 
 // ---- de_1 tail: gather the 9 shifted tap products, NCHW fp32 out ---------------------------------------------
 __global__ void __launch_bounds__(256) de1_gather_kernel(const float* __restrict__ P, int ldp,
                                                          const float* __restrict__ bias, float* __restrict__ out, int B,
-                                                         int H, int W, int c_img) {
+                                                         int H, int W, int c_img, const float* __restrict__ blend,
+                                                         long long blend_bs, float alpha) {
   const long long total = (long long)B * H * W;
   const long long HW = (long long)H * W;
   for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
@@ -368,14 +369,35 @@ __global__ void __launch_bounds__(256) de1_gather_kernel(const float* __restrict
         for (int co = 0; co < c_img; ++co) acc[co] += src[co];
       }
     }
-    for (int co = 0; co < c_img; ++co) out[((long long)b * c_img + co) * HW + (long long)yy * W + xx] = acc[co] + bias[co];
+    for (int co = 0; co < c_img; ++co) {
+      float v = acc[co] + bias[co];
+      if (blend != nullptr)      // alpha * CMM + (1 - alpha) * PSN image, super_resolution.py:449,705
+        v = alpha * v + (1.0f - alpha) * blend[(long long)b * blend_bs + (long long)co * HW + (long long)yy * W + xx];
+      out[((long long)b * c_img + co) * HW + (long long)yy * W + xx] = v;
+    }
   }
 }
 
+__global__ void __launch_bounds__(256) alpha_blend_kernel(float* __restrict__ out, const float* __restrict__ blend, long long blend_bs,
+                                                          float alpha, long long per_image, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / per_image, r = i - b * per_image;
+    out[i] = alpha * out[i] + (1.0f - alpha) * blend[b * blend_bs + r];
+  }
+}
+
+int launch_alpha_blend(float* out, const float* blend, long long blend_bs, float alpha, int B, long long per_image, cudaStream_t st) {
+  const long long total = (long long)B * per_image;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  alpha_blend_kernel<<<blocks, 256, 0, st>>>(out, blend, blend_bs, alpha, per_image, total);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_de1_gather(const float* P, int ldp, const float* bias, float* out, int B, int H, int W, int c_img,
-                      cudaStream_t st) {
+                      cudaStream_t st, const float* blend, long long blend_bs, float alpha) {
   if (c_img > 4 || 9 * c_img > ldp) return -2;
-  de1_gather_kernel<<<148 * 8, 256, 0, st>>>(P, ldp, bias, out, B, H, W, c_img);
+  de1_gather_kernel<<<148 * 8, 256, 0, st>>>(P, ldp, bias, out, B, H, W, c_img, blend, blend_bs, alpha);
   DPMN_LAUNCH_CHECK();
   return 0;
 }

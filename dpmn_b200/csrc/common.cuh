@@ -17,7 +17,44 @@
     if (_e != cudaSuccess) return (int)_e;                    \
   } while (0)
 
+#include <atomic>
+
 namespace dpmn {
+
+// ---- per-device launch state (host) --------------------------------------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize and the SM count belong to a DEVICE, not to the process: a process that
+// drives a second GPU must set the attribute there too and size its persistent grids with that GPU's SM count.  One
+// bit per device ordinal (mod 64); the attribute is set BEFORE the bit is published, so a concurrent caller (ctypes
+// releases the GIL) either sees the bit after the attribute exists or sets the attribute itself (idempotent).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  template <typename Kern>
+  cudaError_t smem_attr(Kern kern, int smem_bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ULL << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+  }
+};
+// SM count of the CURRENT device (cached per device ordinal).
+inline cudaError_t current_device_sms(int* sms) {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  int v = cache[dev & 63].load(std::memory_order_relaxed);
+  if (v == 0) {
+    e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    cache[dev & 63].store(v, std::memory_order_relaxed);
+  }
+  *sms = v;
+  return cudaSuccess;
+}
 
 __device__ __forceinline__ float gelu_erf(float x) {
   // nn.GELU() default (exact erf form), pgrm.py:17

@@ -281,21 +281,14 @@ static int launch_conv_bn(const ConvTcArgs& a, cudaStream_t st) {
     int rc = make_tensor_map_16bit(&map_w, a.w, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    DPMN_CUDA_TRY(cudaGetDevice(&dev));
-    DPMN_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  DPMN_CUDA_TRY(current_device_sms(&num_sms));
   const int total = p.G * p.P * p.wt * p.ht * p.bt * p.n_tiles;
   const int grid = total < 2 * num_sms ? total : 2 * num_sms;
   auto kern = conv_tc_kernel<BN>;
   constexpr int smem = ConvSmem<BN>::TOTAL;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DPMN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr;      // per template instantiation, per device
+  DPMN_CUDA_TRY(attr.smem_attr(kern, smem));
   kern<<<grid, CONV_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], map_w, p);
   DPMN_LAUNCH_CHECK();
   return 0;

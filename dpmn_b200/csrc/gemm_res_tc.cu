@@ -286,21 +286,14 @@ static int launch_res_bn(const GemmTcArgs& a, cudaStream_t st) {
   p.a_zmul = (a.batch > 1 && a.a_bs != 0) ? 1 : 0; p.b_zmul = (a.batch > 1 && a.b_bs != 0) ? 1 : 0;
   p.fmt = a.op_type == DT_BF16 ? 1 : 0;
   p.bias = a.bias; p.bias_bs = a.bias_bs; p.ln_mode = a.ln_mode; p.ln_w = a.ln_w; p.ln_b = a.ln_b;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    DPMN_CUDA_TRY(cudaGetDevice(&dev));
-    DPMN_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  DPMN_CUDA_TRY(current_device_sms(&num_sms));
   const int total = p.batch * p.m_tiles;
   const int grid = total < num_sms ? total : num_sms;
   auto kern = gemm_res_ln_kernel<BN, YT>;
   constexpr int smem = ResSmem<BN>::TOTAL;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DPMN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr;      // per template instantiation, per device
+  DPMN_CUDA_TRY(attr.smem_attr(kern, smem));
   kern<<<grid, RTHREADS, smem, st>>>(map_a, map_b, map_r, map_c, map_y, p);
   DPMN_LAUNCH_CHECK();
   return 0;

@@ -372,7 +372,6 @@ int make_tensor_map_16bit(CUtensorMap* map, const void* base, int rank, const ui
   return r == CUDA_SUCCESS ? 0 : 1000 + (int)r;
 }
 
-static int g_num_sms = 0;
 
 template <int BN, typename OutT, bool LN, int EW = 4>
 static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st) {
@@ -412,22 +411,16 @@ static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st) {
   p.sc_cg = a.scatter_G ? a.scatter_C / a.scatter_G : 0;
   for (int i = 0; i < 4; ++i) { p.sc_ws[i] = a.scatter_ws[i]; p.sc_shift[i] = a.scatter_shift[i]; }
   p.sc_dst[0] = a.scatter_dst[0]; p.sc_dst[1] = a.scatter_dst[1];
-  if (g_num_sms == 0) {
-    int dev = 0;
-    DPMN_CUDA_TRY(cudaGetDevice(&dev));
-    DPMN_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int g_num_sms = 0;
+  DPMN_CUDA_TRY(current_device_sms(&g_num_sms));
   const int total = p.batch * p.m_tiles * p.n_tiles;
   static const int env_per_sm = getenv("DPMN_TC_PER_SM") ? atoi(getenv("DPMN_TC_PER_SM")) : 2;
   const int per_sm = LN ? 1 : (env_per_sm >= 2 ? 2 : 1);
   const int grid = total < per_sm * g_num_sms ? total : per_sm * g_num_sms;
   auto kern = gemm_tc_kernel<BN, OutT, LN, EW>;
   constexpr int smem = TcSmem<BN>::TOTAL;
-  static bool attr_set = false;   // per template instantiation
-  if (!attr_set) {
-    DPMN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr;      // per template instantiation, per device
+  DPMN_CUDA_TRY(attr.smem_attr(kern, smem));
   kern<<<grid, 64 + 32 * EW, smem, st>>>(map_a, map_b, p);
   DPMN_LAUNCH_CHECK();
   return 0;

@@ -105,6 +105,12 @@ int launch_sk_gate(const float* colsum, int tiles_per_image, int L, const float*
 int launch_dwconv(const void* h, void* dt, DType io_type, const float* w, const float* b, int B, int L, int hid,
                   cudaStream_t st);
 
+// Mlp front half in one tcgen05 kernel (mlp_fused_a.cu): dt = GELU(dw3x3(raw view of GELU(x16 * w16^T + fc1_b))) written
+// pixel-major (B, L, hid), 16-bit.  x16 (B*L, C), w16 (hid, C) are 16-bit of type t.  Only the production geometry.
+bool mlp_fc1_dw_supported(int C, int hid, int L);
+int launch_mlp_fc1_dw(const void* x16, const void* w16, const float* fc1_b, const float* dw_w, const float* dw_b, void* dt, int B,
+                      DType t, cudaStream_t st);
+
 // PatchUnEmbed + conv3x3 (C -> hp) on token-major x (B, gh, gw, C) -> t1 (B, gh, gw, hp) fp32.
 int launch_head_conv1(const float* x, const float* w, const float* b, float* t1, int B, int gh, int gw, int C,
                       int hp, cudaStream_t st);
@@ -366,7 +372,10 @@ int launch_se_gate_nhwc(const float* z6, void* zg, DType t, const float* fc1_w, 
                         cudaStream_t st);
 // de_1 tail (cmm.py:113-116): out[b,co,y,x] = bias[co] + sum_taps P[b, y+1-ky, x+1-kx][(ky*3+kx)*c_img + co],
 // P (B*H*W, ldp) fp32 from the tap-in-N GEMM.
+// Optional blend (super_resolution.py:449,705): out = alpha * conv + (1 - alpha) * blend[b] (blend == nullptr: none).
 int launch_de1_gather(const float* P, int ldp, const float* bias, float* out, int B, int H, int W, int c_img,
-                      cudaStream_t st);
+                      cudaStream_t st, const float* blend = nullptr, long long blend_bs = 0, float alpha = 1.f);
+// out = alpha * out + (1 - alpha) * blend   (the fp32-structured path's form of the same blend)
+int launch_alpha_blend(float* out, const float* blend, long long blend_bs, float alpha, int B, long long per_image, cudaStream_t st);
 
 }  // namespace dpmn

@@ -1,8 +1,7 @@
-// EXPERIMENTAL DRAFT (round-2 work in progress) -- fc1 + GELU + depthwise 3x3 + GELU of Mlp.forward (pgrm.py:30-36) in ONE
-// kernel.  NOT on any default path: dpmn_pgrm_forward does not call it and include/dpmn_b200.h does not declare it; the
-// only entry is the test hook dpmnx_mlp_fc1_dwconv at the bottom (tests/test_experimental.py, skipped unless
-// DPMN_EXPERIMENTAL=1).  It is compiled with the library so that the draft keeps building, and it has NOT run on
-// hardware yet (the round's GPU budget was spent before it was written) -- treat every line as unverified.
+// fc1 + GELU + depthwise 3x3 + GELU of Mlp.forward (pgrm.py:30-36) in ONE kernel ("kernel A" of DESIGN.md section 9).
+// Called by pgrm_forward_impl (api.cu) in the 16-bit modes for the production geometry (C = 96, hidden 384, 32 x 32 raw
+// view); verified on hardware against the oracle and under compute-sanitizer memcheck
+// (profiles/r02_sanitizer_memcheck_mlp_fused_a.log).  dpmnx_mlp_fc1_dwconv at the bottom is the stand-alone test hook.
 //
 // Why: the PGRM GEMM class is HBM-bound and launch-granular; fc1 writes and the depthwise conv
 // re-reads the 37.7 MB hidden tensor per block.  The raw view of quirk 2 makes the fusion local: a 128-token M-tile of
@@ -273,17 +272,26 @@ int launch_mlp_a(const void* x16, const void* w16, const float* fc1_b, const flo
   }
   MlpAParams p;
   p.tiles = B * (MA_L / MA_ROWS); p.fmt = fmt; p.fc1_b = fc1_b; p.dw_w = dw_w; p.dw_b = dw_b; p.dt = dt;
-  int dev = 0, sms = 0;
-  DPMN_CUDA_TRY(cudaGetDevice(&dev));
-  DPMN_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int sms = 0;
+  DPMN_CUDA_TRY(current_device_sms(&sms));
   auto kern = mlp_fc1_dw_kernel<T>;
-  DPMN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MA_SMEM));
+  static PerDeviceOnce attr;      // per template instantiation, per device
+  DPMN_CUDA_TRY(attr.smem_attr(kern, MA_SMEM));
   kern<<<p.tiles < sms ? p.tiles : sms, MA_THREADS, MA_SMEM, st>>>(map_x, map_w, p);
   DPMN_LAUNCH_CHECK();
   return 0;
 }
 
 }  // namespace
+
+bool mlp_fc1_dw_supported(int C, int hid, int L) { return C == MA_C && hid == MA_HID && L == MA_L; }
+
+int launch_mlp_fc1_dw(const void* x16, const void* w16, const float* fc1_b, const float* dw_w, const float* dw_b, void* dt, int B,
+                      DType t, cudaStream_t st) {
+  if (t == DT_F16) return launch_mlp_a<__half>(x16, w16, fc1_b, dw_w, dw_b, dt, B, 0, st);
+  if (t == DT_BF16) return launch_mlp_a<__nv_bfloat16>(x16, w16, fc1_b, dw_w, dw_b, dt, B, 1, st);
+  return -1;
+}
 
 }  // namespace dpmn
 

@@ -645,11 +645,8 @@ int launch_dwconv_bwd(const float* d_dt, const float* dtpre, const float* h1pre,
   if (side * side != L || hid % 32 || side % DWT_ROWS) return -2;
   if (side == 32 && hid % DWF_CH == 0 && (reinterpret_cast<uintptr_t>(h1pre) & 15) == 0) {
     constexpr int fast_smem = (2 * DWF_CH * ((DWT_ROWS + 2) * 32 + 2) + DWF_CH * DWT_ROWS * 32) * (int)sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      DPMN_CUDA_TRY(cudaFuncSetAttribute(dwconv_bwd_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, fast_smem));
-      attr_set = true;
-    }
+    static PerDeviceOnce attr;
+    DPMN_CUDA_TRY(attr.smem_attr(dwconv_bwd_fast_kernel<32>, fast_smem));
     dwconv_bwd_fast_kernel<32><<<dim3(32 / DWT_ROWS, hid / DWF_CH, B), 256, fast_smem, st>>>(d_dt, dtpre, h1pre, w, d_h1pre, dw,
                                                                                             db, hid, p_drop, seed, site);
     DPMN_LAUNCH_CHECK();

@@ -1252,11 +1252,8 @@ static int launch_dwconv16(const void* h, void* dt, const float* w, const float*
   }
   const size_t smem = (size_t)(64 * ((DW_ROWS + 2) * side + 2) + DW_ROWS * side * 64) * 2;
   auto k = dwconv16_kernel<T>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DPMN_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr;      // per template instantiation, per device
+  DPMN_CUDA_TRY(attr.smem_attr(k, (int)smem));
   k<<<grid, 256, smem, st>>>((const T*)h, (T*)dt, w, b, L, hid, side);
   DPMN_LAUNCH_CHECK();
   return 0;

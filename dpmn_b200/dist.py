@@ -44,16 +44,129 @@ class FlatGradBucket:
     def zero(self):
         self.flat.zero_()
 
-    def allreduce_mean(self, group=None, async_op: bool = False):
-        """sum over ranks, then scale by 1/world (the reference averages the loss over the global batch)."""
+    def allreduce_mean(self, group=None, async_op: bool = False, local_items: int = None, global_items: int = None):
+        """sum over ranks, then scale by 1/world (the reference averages the loss over the global batch).  With uneven
+        shards (`shard_range`) pass the shard sizes: each rank's gradient of its LOCAL mean is weighted by
+        local_items / global_items before the sum, which gives the gradient of the global-batch mean, not a mean of means."""
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         if world == 1:
             return None
+        weighted = local_items is not None and global_items is not None
+        if weighted:
+            self.flat.mul_(float(local_items) / float(global_items))
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         if async_op:
-            return work
-        self.flat.mul_(1.0 / world)
+            return work           # an unweighted async caller scales by 1/world itself once the work has completed
+        if not weighted:
+            self.flat.mul_(1.0 / world)
         return None
+
+
+class FlatTrainState:
+    """Everything the tail of a training step touches, as FLAT fp32 buffers with one contiguous SEGMENT per module:
+    parameters (every `p.data` becomes a view), gradients (`p.grad` views; each module also gets `_grad_sink`, so the C
+    backward accumulates straight into the bucket), and Adam's two moments.  Segment s = [offsets[s], offsets[s+1]).
+
+    Why segments: the reference clips the gradient norm per module (interfaces/super_resolution.py:270-275), and the
+    all-reduce of a module's segment can start as soon as that module's backward has been enqueued -- the CMM (94 % of the
+    bucket) finishes its backward FIRST, so its segment travels over NVLink while the six PGRMs still compute."""
+
+    def __init__(self, modules):
+        """modules: list of nn.Module in segment order."""
+        self.modules = list(modules)
+        per_mod = []
+        for m in self.modules:
+            named = [(n, p) for n, p in m.named_parameters() if p.requires_grad]
+            per_mod.append(named)
+        self.params = [p for named in per_mod for _, p in named]
+        if not self.params:
+            raise ValueError("FlatTrainState: no trainable parameters")
+        dev = self.params[0].device
+        sizes = [sum(p.numel() for _, p in named) for named in per_mod]
+        # every segment starts on a 16-byte boundary (float4 accesses in the fused optimizer, aligned NCCL chunks)
+        self.offsets = [0]
+        for sz in sizes:
+            self.offsets.append(self.offsets[-1] + (sz + 3) // 4 * 4)
+        total = self.offsets[-1]
+        self.flat_params = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grads = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = None          # allocated by the optimizer that uses them
+        self.exp_avg_sq = None
+        self.n_params = sum(sizes)
+        for m, named, start in zip(self.modules, per_mod, self.offsets[:-1]):
+            off = start
+            sink = {}
+            for n, p in named:
+                k = p.numel()
+                self.flat_params[off: off + k].copy_(p.data.reshape(-1))
+                p.data = self.flat_params[off: off + k].view(p.shape)
+                g = self.flat_grads[off: off + k].view(p.shape)
+                if p.grad is not None:
+                    g.copy_(p.grad)
+                p.grad = g
+                sink[n] = g
+                off += k
+            m._grad_sink = sink
+            m._weights_epoch = getattr(m, "_weights_epoch", 0) + 1     # parameter storage moved: re-stage cached weights
+
+    def segment(self, s: int) -> torch.Tensor:
+        return self.flat_grads[self.offsets[s]: self.offsets[s + 1]]
+
+    def zero_grads(self):
+        self.flat_grads.zero_()
+
+    def bump_epoch(self):
+        for m in self.modules:
+            m._weights_epoch = getattr(m, "_weights_epoch", 0) + 1
+
+
+class NcclBucketComm:
+    """The library's own NCCL communicator (dpmn_nccl_comm_init / dpmn_allreduce_bucket in include/dpmn_b200.h): rank 0
+    makes the unique id, the existing torch.distributed group only carries those 128 bytes to the other ranks."""
+
+    def __init__(self, device: torch.device, group=None):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        if not self.lib.dpmn_nccl_available():
+            raise RuntimeError("dpmn_b200: libnccl could not be resolved (dpmn_nccl_available() == 0)")
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        buf = (C.c_char * 128)()
+        if self.rank == 0:
+            _lib.check(self.lib.dpmn_nccl_unique_id(C.cast(buf, C.c_void_p)), "dpmn_nccl_unique_id")
+        box = [bytes(buf)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        idbuf = C.create_string_buffer(box[0], 128)
+        self._comm = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.dpmn_nccl_comm_init(C.cast(idbuf, C.c_void_p), self.world, self.rank, C.byref(self._comm)),
+                       "dpmn_nccl_comm_init")
+        self.device = device
+
+    def allreduce_sum(self, t: torch.Tensor, stream: torch.cuda.Stream):
+        """In-place sum over ranks of a contiguous fp32 / fp16 / bf16 CUDA tensor, enqueued on `stream`."""
+        from . import _lib
+        if not (t.is_cuda and t.is_contiguous()):
+            raise RuntimeError("NcclBucketComm.allreduce_sum: contiguous CUDA tensor required")
+        dt = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[t.dtype]
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dpmn_allreduce_bucket(self._comm, t.data_ptr(), t.numel(), dt, stream.cuda_stream),
+                       "dpmn_allreduce_bucket")
+
+    def close(self):
+        if self._comm:
+            self.lib.dpmn_nccl_comm_destroy(self._comm)
+            self._comm = None
+
+
+def broadcast_module_state(modules, src: int = 0, group=None):
+    """Rank `src`'s parameters and buffers to every rank (what DDP does at construction): replicas must start identical,
+    whatever each rank's RNG state was when it built its modules."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for m in modules:
+        for t in list(m.parameters()) + list(m.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
 
 
 def max_over_ranks(value: float, device) -> float:

@@ -130,11 +130,16 @@ class DistillModule(nn.Module):
         with torch.cuda.device(dev):
             d = self._descriptor(B, H, W, training, False, d_bs, s_bs)
             d.flags = _lib.DISTILL_WORKSPACE_HOLDS_FORWARD
-            flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-            views, off = {}, 0
-            for n, p in zip(names, params):
-                views[n] = flat[off: off + p.numel()].view_as(p)
-                off += p.numel()
+            from .pgrm import grad_sink_views
+            sink = grad_sink_views(self, names, params)
+            if sink is not None:
+                views = sink          # accumulate straight into the caller's gradient bucket
+            else:
+                flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+                views, off = {}, 0
+                for n, p in zip(names, params):
+                    views[n] = flat[off: off + p.numel()].view_as(p)
+                    off += p.numel()
             g = _lib.DistillGrads()
             g.conv_cat_w, g.conv_cat_b = views["conv_cat_feature.weight"].data_ptr(), views["conv_cat_feature.bias"].data_ptr()
             g.conv_w, g.conv_b = views["conv_feature.weight"].data_ptr(), views["conv_feature.bias"].data_ptr()
@@ -151,4 +156,6 @@ class DistillModule(nn.Module):
                                            gf.data_ptr() if gf is not None else None, C.byref(g), ws.data_ptr(), ws.numel(),
                                            torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "dpmn_distill_backward")
+        if sink is not None:
+            return d_deep, d_shallow, [None] * len(params)
         return d_deep, d_shallow, [views[n] if p.requires_grad else None for n, p in zip(names, params)]

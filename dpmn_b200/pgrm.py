@@ -98,6 +98,29 @@ def _initial_value(name: str, shape, cfg: PGRMConfig) -> torch.Tensor:
     return nn.init.trunc_normal_(t, std=.02)   # Linear weight
 
 
+def resolve_precision(precision):
+    """None -> $DPMN_PRECISION -> "fp16" (the fast, 1e-3-parity mode); explicit values are validated."""
+    import os
+    p = precision if precision is not None else os.environ.get("DPMN_PRECISION", "fp16")
+    if p not in _lib.PREC:
+        raise ValueError(f"dpmn_b200: precision must be one of {sorted(_lib.PREC)}, got {p!r}")
+    return p
+
+
+def grad_sink_views(module: nn.Module, names, params):
+    """`module._grad_sink` (set by dpmn_b200.train.FlatTrainState): name -> fp32 view of the caller's flat gradient bucket for
+    EVERY trainable parameter.  The C backward accumulates into its `grads` pointers, so with a sink the gradients land in
+    the bucket directly -- no temporary flat buffer, no autograd AccumulateGrad pass over 57 M elements.  None = off."""
+    sink = getattr(module, "_grad_sink", None)
+    if sink is None:
+        return None
+    for n, p in zip(names, params):
+        v = sink.get(n)
+        if v is None or v.device != p.device or v.numel() != p.numel():
+            return None               # incomplete / stale sink: fall back to the autograd-accumulated path
+    return sink
+
+
 class PreparedWeights:
     """Cache of the tensor-core modes' staged 16-bit weights (include/dpmn_b200.h `prepared`): re-staged only
     when a parameter / buffer was modified in place (torch's version counter) or re-allocated."""
@@ -109,7 +132,10 @@ class PreparedWeights:
     def attach(self, module: nn.Module, d, nbytes: int, device):
         if nbytes == 0:
             return None
-        key = tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+        # `_weights_epoch`: bumped by callers that update the parameters through raw pointers (the fused clip + Adam
+        # kernel of dpmn_b200.train), which torch's version counters cannot see
+        key = (getattr(module, "_weights_epoch", 0),) + tuple(
+            (t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
         if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
             self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
             self.key = None
@@ -159,12 +185,13 @@ class PGRM(ParamTree):
     """Prior-Guided Refinement Module, signature-compatible with the reference (pgrm.py:462-467).
 
     Extra keyword: `precision` in {"fp32", "fp16", "bf16"} selects the arithmetic of the contractions
-    (fp32 = FFMA, 1e-5 parity; fp16/bf16 = tcgen05 tensor cores with fp32 accumulation)."""
+    (fp32 = FFMA, 1e-5 parity; fp16/bf16 = tcgen05 tensor cores with fp32 accumulation, 1e-3 parity).  Default (None): the
+    environment variable DPMN_PRECISION, else "fp16" -- the two-import swap of INTEGRATION.md lands on the tensor-core path."""
 
     def __init__(self, img_size=[32, 128], patch_size=[2], in_chans=3, embed_dim=[96], depths=[1], num_heads=[[6]],
                  window_size=[[2, 4, 8]], mlp_ratio=[4.], qkv_bias=True, qk_scale=None, drop_rate=[0.],
                  attn_drop_rate=[0.], drop_path_rate=[0.1], iter=0, norm_layer=nn.LayerNorm, ape=False,
-                 patch_norm=True, mode=True, use_checkpoint=False, hidden_size=64, precision="fp32", **kwargs):
+                 patch_norm=True, mode=True, use_checkpoint=False, hidden_size=64, precision=None, **kwargs):
         super().__init__()
         if not qkv_bias or qk_scale is not None or ape or not patch_norm or norm_layer is not nn.LayerNorm:
             raise NotImplementedError("dpmn_b200.PGRM supports the configuration DPMN instantiates "
@@ -180,7 +207,7 @@ class PGRM(ParamTree):
         dpr = [float(x) for x in np.linspace(0, drop_path_rate[iter], n)]
         lo = sum(depths[:iter]) * 2
         self.drop_path = dpr[lo: lo + 2] or [0.0]
-        self.precision = precision
+        self.precision = resolve_precision(precision)
         H, W = self.cfg.grid
         for name, shape, kind in pgrm_schema(self.cfg):
             if kind == "param":
@@ -210,9 +237,13 @@ class PGRM(ParamTree):
         """train() with a non-zero Dropout / DropPath rate: the forward then draws masks (fp32 training sequence)."""
         return self.training and (self.drop_rate > 0 or self.attn_drop_rate > 0 or max(self.drop_path) > 0)
 
-    @staticmethod
-    def _new_seed() -> int:
-        return int(torch.randint(0, 2 ** 62, (1,)).item())     # torch's CPU generator: torch.manual_seed reproduces it
+    def _new_seed(self) -> int:
+        """Seed of one forward's Dropout / DropPath masks: torch's CPU generator (torch.manual_seed reproduces it) mixed with
+        `_seed_salt` -- the trainer sets it to the data-parallel rank, so ranks that seeded torch identically (to build
+        identical replicas) still draw different masks for their different shards."""
+        base = int(torch.randint(0, 2 ** 62, (1,)).item())
+        salt = int(getattr(self, "_seed_salt", 0))
+        return (base ^ ((salt * 0x9E3779B97F4A7C15) & (2 ** 62 - 1))) if salt else base
 
     def _descriptor(self, B: int, q_chans: int, n_mix: int, seed=None) -> _lib.PgrmDesc:
         cfg = self.cfg
@@ -292,12 +323,16 @@ class PGRM(ParamTree):
         names = [n for n, _ in self.named_parameters()]
         params = [p for _, p in self.named_parameters()]
         sizes = [p.numel() for p in params]
+        sink = grad_sink_views(self, names, params)
         with torch.cuda.device(dev):
-            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)   # one flat bucket, views per parameter
-            views, off = {}, 0
-            for n, p, sz in zip(names, params, sizes):
-                views[n] = flat[off: off + sz].view_as(p)
-                off += sz
+            if sink is not None:
+                views = sink          # the caller's gradient bucket: dpmn_pgrm_backward accumulates straight into it
+            else:
+                flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)   # one flat bucket, views per parameter
+                views, off = {}, 0
+                for n, p, sz in zip(names, params, sizes):
+                    views[n] = flat[off: off + sz].view_as(p)
+                    off += sz
             g = _lib.PgrmGrads()
             used = set()
 
@@ -342,7 +377,13 @@ class PGRM(ParamTree):
             _lib.check(rc, "dpmn_pgrm_backward")
         # parameters the output does not depend on get no gradient, as in the reference (unused weight_list_i,
         # prior_fusion when x_q already has 3 channels)
-        d_params = [views[n] if (n in used and p.requires_grad) else None for n, p in zip(names, params)]
+        if sink is not None:
+            d_params = [None] * len(params)       # already accumulated in place
+        else:
+            d_params = [views[n] if (n in used and p.requires_grad) else None for n, p in zip(names, params)]
+        hook = getattr(self, "_after_backward", None)
+        if hook is not None:
+            hook(self)
         return d_xkv, d_res, d_params
 
     def forward_probe(self, x_q, x_kv, residual_list):
@@ -393,7 +434,8 @@ class PGRM(ParamTree):
                 rc = lib.dpmn_pgrm_forward(C.byref(d), x_q.data_ptr(), x_kv.data_ptr(), out.data_ptr(), ws.data_ptr(),
                                            ws.numel(), stream)
                 _lib.check(rc, "dpmn_pgrm_forward")
-                self._prepared.key = prep_key
+                if seed is None:     # the stochastic training sequence never stages `prepared`: it must not validate it
+                    self._prepared.key = prep_key
                 return out
             L, Cc = cfg.tokens, cfg.embed_dim
             cores = [torch.empty((B, L, Cc), dtype=torch.float32, device=dev) for _ in range(2)]

@@ -15,7 +15,7 @@ from .pgrm import PGRM
 N_ITER = 6
 
 
-def build_pgrm_stack(precision: str = "fp32", stu_iter_b1: int = 3, stu_iter_b2: int = 3,
+def build_pgrm_stack(precision: str = None, stu_iter_b1: int = 3, stu_iter_b2: int = 3,
                      drop: float = 0.1) -> List[PGRM]:
     """generator_init (interfaces/base.py:150-155) for k = 0..5: branch 1 gets the 2-channel rendered-text
     prior (mode=False), branch 2 the 3-channel mask prior (mode=True); hidden_size = 3.  `drop` is the value of
@@ -32,7 +32,7 @@ def build_pgrm_stack(precision: str = "fp32", stu_iter_b1: int = 3, stu_iter_b2:
 
 
 class DPMNHotPath(nn.Module):
-    def __init__(self, precision: str = "fp32", stu_iter_b1: int = 3, stu_iter_b2: int = 3, drop: float = 0.1,
+    def __init__(self, precision: str = None, stu_iter_b1: int = 3, stu_iter_b2: int = 3, drop: float = 0.1,
                  cmm_precision: str = None):
         super().__init__()
         self.b1, self.b2 = stu_iter_b1, stu_iter_b2
@@ -40,17 +40,25 @@ class DPMNHotPath(nn.Module):
         self.cmm = ComplementationModulationModule(precision=cmm_precision or precision)
         self.concurrent_branches = True       # inference: the two PGRM cascades run on two CUDA streams
         self._streams = None
+        # --alpha of the reference (main.py:66, README.md:42: 0.5): eval / test blend the CMM output with the PSN image
+        # (super_resolution.py:449,705).  None = the plain CMM output (what the training loss looks at).
+        self.alpha = None
 
     def forward(self, psn_out: torch.Tensor, priors_b1: Sequence[torch.Tensor], priors_b2: Sequence[torch.Tensor]):
         """psn_out (B,4,32,128) frozen-backbone output; priors_b1[k] (B,2,32,128) rendered-text maps;
         priors_b2[k] (B,3,32,128) binary masks -> fused SR image (B,3,32,128)."""
         return self.forward_all(psn_out, priors_b1, priors_b2)[-1]
 
-    def forward_all(self, psn_out, priors_b1, priors_b2) -> List[torch.Tensor]:
-        """All seven images the training loss looks at (super_resolution.py:212,239,267): the six PGRM outputs in
-        call order, then the CMM output.  priors_b2=None: the branch-2 priors are computed from the cascade images
-        with the device toMask, as the reference does on the host."""
+    def _cmm_call(self, psn_out, b1_out, b2_out):
+        if self.alpha is None or self.training:
+            return self.cmm(b1_out, b2_out)                                                   # :265
+        return self.cmm(b1_out, b2_out, blend_with=psn_out[:, :3], alpha=self.alpha)          # :448-449, :704-705
+
+    def _branch_fn(self, psn_out):
+        """One cascade of PGRMs (super_resolution.py:174-240) as a closure over the PSN output; shared by forward_all and
+        submit so that both accept priors=None for branch 2 (device toMask of the cascade image, :218-226)."""
         from .train import to_mask
+
         def branch(first, count, priors):
             cascade = psn_out[:, :3, :]                   # channel-slice view, super_resolution.py:196
             done: List[torch.Tensor] = []
@@ -63,6 +71,13 @@ class DPMNHotPath(nn.Module):
                 done.append(y)
                 cascade = y
             return done
+        return branch
+
+    def forward_all(self, psn_out, priors_b1, priors_b2) -> List[torch.Tensor]:
+        """All seven images the training loss looks at (super_resolution.py:212,239,267): the six PGRM outputs in
+        call order, then the CMM output.  priors_b2=None: the branch-2 priors are computed from the cascade images
+        with the device toMask, as the reference does on the host."""
+        branch = self._branch_fn(psn_out)
 
         if psn_out.is_cuda and not torch.is_grad_enabled() and self.concurrent_branches:
             outs, done = self._submit(psn_out, priors_b1, priors_b2, branch)
@@ -74,7 +89,7 @@ class DPMNHotPath(nn.Module):
             return outs
         done1 = branch(0, self.b1, priors_b1)
         done = branch(self.b1, self.b2, priors_b2)
-        return list(done1) + list(done) + [self.cmm(done1[-1], done[-1])]                  # :265
+        return list(done1) + list(done) + [self._cmm_call(psn_out, done1[-1], done[-1])]                  # :265
 
     def _submit(self, psn_out, priors_b1, priors_b2, branch):
         """The two cascades are independent until the CMM (super_resolution.py:174-240): they run on two side streams
@@ -98,14 +113,14 @@ class DPMNHotPath(nn.Module):
             with torch.cuda.stream(st):
                 done = branch(first, count, priors)
             if not capturing:
-                for t in done:
+                for t in list(done) + [psn_out]:      # the CMM stream reads the branch outputs and (alpha blend) the PSN image
                     t.record_stream(s_cmm)
             end = torch.cuda.Event()
             end.record(st)
             s_cmm.wait_event(end)
             results.append(done)
         with torch.cuda.stream(s_cmm):
-            y = self.cmm(results[0][-1], results[1][-1])                                   # :265
+            y = self._cmm_call(psn_out, results[0][-1], results[1][-1])                                   # :265
         finished = torch.cuda.Event()
         finished.record(s_cmm)
         return list(results[0]) + list(results[1]) + [y], finished
@@ -115,15 +130,7 @@ class DPMNHotPath(nn.Module):
         """Asynchronous inference: enqueue one batch without making the current stream wait for it.  Returns
         (sr, done): `sr` (B,3,32,128) is valid once the CUDA event `done` has fired -- make the consuming stream
         `wait_event(done)` (HostFeeder.fetch does).  Batches are processed in submission order."""
-        def branch(first, count, priors):
-            cascade = psn_out[:, :3, :]
-            done: List[torch.Tensor] = []
-            for j in range(count):
-                y = self.pgrm[first + j](priors[j], cascade, done[:j])
-                done.append(y)
-                cascade = y
-            return done
-        outs, finished = self._submit(psn_out, priors_b1, priors_b2, branch)
+        outs, finished = self._submit(psn_out, priors_b1, priors_b2, self._branch_fn(psn_out))
         return outs[-1], finished
 
 

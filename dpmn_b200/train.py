@@ -15,7 +15,6 @@ from typing import List, Sequence
 
 import torch
 
-from .dist import FlatGradBucket
 from .pipeline import DPMNHotPath
 
 
@@ -109,22 +108,121 @@ def parse_visionlan_data(imgs_input: torch.Tensor) -> torch.Tensor:
 
 
 class HotPathTrainer:
+    """One training step of the hot path: forward (6 PGRM + CMM), 7 image losses + the DistillModule terms, backward, the
+    gradient all-reduce, per-module clipping at 0.25 and Adam (interfaces/super_resolution.py:245-278, base.py:208-221).
+
+    Data parallel: one process per GPU, replicas made identical at construction by a broadcast from rank 0,
+    ONE flat fp32 gradient bucket (57.2 M parameters, 228.7 MB) reduced with the library's own NCCL communicator
+    (dpmn_allreduce_bucket) on a side stream.  The bucket is laid out module by module with the CMM first: its backward
+    is the first to finish, so its segment (94 % of the bytes) is reduced while the six PGRMs are still in their
+    backward; the remaining segment follows when the backward ends.  Clip + Adam then run as two kernels over the flat
+    buffers (dpmn_clip_adam_step).  Per-rank BatchNorm statistics, as under the reference's DataParallel (no SyncBN)."""
+
     def __init__(self, model: DPMNHotPath, lr: float = 1e-3, betas=(0.5, 0.999), clip: float = 0.25, group=None,
-                 distill: bool = True):
+                 distill: bool = True, fused_optimizer: bool = None, overlap: bool = True, eps: float = 1e-8):
+        import torch.distributed as dist
+        from .dist import FlatTrainState, NcclBucketComm, broadcast_module_state
         self.model, self.clip, self.group = model, clip, group
-        self.modules = list(model.pgrm) + [model.cmm]
+        self.lr, self.betas, self.eps = lr, betas, eps
+        dev = next(model.parameters()).device
+        self.device = dev
+        self.dist_on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.dist_on else 1
+        self.rank = dist.get_rank(group) if self.dist_on else 0
         # one DistillModule per adjacent pair of cascade outputs of a branch (super_resolution.py:113-121)
         self.distill: List[torch.nn.Module] = []
         if distill:
             from .distill import DistillModule
-            dev = next(model.parameters()).device
-            with torch.random.fork_rng(devices=[]):            # same initial replicas on every rank
+            with torch.random.fork_rng(devices=[]):
                 torch.default_generator.manual_seed(20240 + model.b1 * 16 + model.b2)   # CPU generator only
                 self.distill = [DistillModule().to(dev).train() for _ in range(model.b1 + model.b2 - 2)]
-        params = list(model.parameters()) + [p for m in self.distill for p in m.parameters()]   # base.py:208-221 order
-        self.bucket = FlatGradBucket(params)                   # p.grad become views of ONE flat fp32 buffer
-        self.opt = torch.optim.Adam(self.bucket.params, lr=lr, betas=betas)
+        self.modules = list(model.pgrm) + [model.cmm]                  # model_list of the reference (clip order)
+        seg_modules = [model.cmm] + list(model.pgrm) + self.distill    # bucket order: the CMM's segment first (see above)
+        broadcast_module_state(seg_modules, src=0, group=group)        # identical replicas whatever each rank's RNG state
+        for m in model.pgrm:
+            m._seed_salt = self.rank                                   # different Dropout / DropPath masks per rank
+        self.state = FlatTrainState(seg_modules)
+        self.bucket = self.state                                       # (name kept for callers of the round-1 interface)
+        cuda = dev.type == "cuda"
+        self.fused = cuda if fused_optimizer is None else bool(fused_optimizer)
+        self.step_count = 0
+        if self.fused:
+            from . import _lib
+            self._lib = _lib.load()
+            self.state.exp_avg = torch.zeros_like(self.state.flat_params)
+            self.state.exp_avg_sq = torch.zeros_like(self.state.flat_params)
+            n_seg = len(seg_modules)
+            self._opt_ws = torch.zeros(int(self._lib.dpmn_clip_adam_workspace_bytes(n_seg)) + 16, dtype=torch.uint8, device=dev)
+            import ctypes as C
+            self._offs = (C.c_int64 * (n_seg + 1))(*self.state.offsets)
+            self.opt = None
+        else:
+            self.opt = torch.optim.Adam(self.state.params, lr=lr, betas=betas, eps=eps)
+        # the collective
+        self.comm, self.comm_stream = None, None
+        self.overlap = overlap
+        self.timing = None               # set to {} to collect all-reduce timings (CUDA events) per step
+        self._events = []
+        if self.dist_on and cuda:
+            self.comm = NcclBucketComm(dev, group)
+            self.comm_stream = torch.cuda.Stream(dev)
+            if overlap:
+                model.cmm._after_backward = self._on_cmm_backward
+        self._cmm_reduced = False
 
+    # ---- collective ---------------------------------------------------------------------------------------------------
+    def _reduce_segment(self, t: torch.Tensor, tag: str):
+        """all-reduce(sum) of a slice of the flat gradient bucket on the communication stream, ordered after everything
+        enqueued on the current stream so far."""
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.comm_stream.wait_event(ready)
+        t0 = t1 = None
+        if self.timing is not None:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(self.comm_stream)
+        self.comm.allreduce_sum(t, self.comm_stream)
+        if self.timing is not None:
+            t1.record(self.comm_stream)
+            self._events.append((tag, t0, t1))
+
+    def _on_cmm_backward(self, module):
+        if self.comm is None or self._cmm_reduced:
+            return
+        self._reduce_segment(self.state.segment(0), "allreduce_cmm_segment")
+        self._cmm_reduced = True
+
+    def _allreduce(self):
+        import torch.distributed as dist
+        st = self.state
+        if self.comm is None:                        # CPU tensors / gloo (the host-logic tests): torch's collective
+            dist.all_reduce(st.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        main = torch.cuda.current_stream(self.device)
+        rest = st.flat_grads[st.offsets[1]:] if self._cmm_reduced else st.flat_grads
+        self._reduce_segment(rest, "allreduce_tail_segment" if self._cmm_reduced else "allreduce_whole_bucket")
+        done = torch.cuda.Event()
+        done.record(self.comm_stream)
+        w0 = w1 = None
+        if self.timing is not None:
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record(main)
+        main.wait_event(done)
+        if self.timing is not None:
+            w1.record(main)
+            self._events.append(("allreduce_exposed_wait", w0, w1))
+
+    def collect_timing(self):
+        """ms per tag, summed over the steps since the last call (needs self.timing = {} before the steps; synchronises)."""
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for tag, a, b in self._events:
+            out[tag] = out.get(tag, 0.0) + a.elapsed_time(b)
+        self._events = []
+        return out
+
+    # ---- loss -----------------------------------------------------------------------------------------------------------
     def distill_loss(self, outs: Sequence[torch.Tensor]) -> torch.Tensor:
         """super_resolution.py:245-263: per branch, from the deepest cascade image back to the first; each module
         compares its fused feature with the next shallower image and hands the feature on."""
@@ -145,15 +243,40 @@ class HotPathTrainer:
             total = total + self.distill_loss(outs)                # :253,263
         return total / len(outs)                                   # :268
 
-    def step(self, psn_out, priors_b1, priors_b2, hr) -> torch.Tensor:
-        """forward + backward + all-reduce + clip + Adam; returns the (local) loss as a 0-d tensor."""
-        self.bucket.zero()
+    # ---- optimizer --------------------------------------------------------------------------------------------------------
+    def _optimizer_step(self):
+        st = self.state
+        self.step_count += 1
+        if not self.fused:
+            if self.world > 1:
+                st.flat_grads.mul_(1.0 / self.world)
+            for m in self.modules + self.distill:                  # super_resolution.py:270-275
+                torch.nn.utils.clip_grad_norm_(m.parameters(), self.clip)
+            self.opt.step()
+            return
+        from . import _lib
+        with torch.cuda.device(self.device):
+            rc = self._lib.dpmn_clip_adam_step(st.flat_params.data_ptr(), st.flat_grads.data_ptr(), st.exp_avg.data_ptr(),
+                                               st.exp_avg_sq.data_ptr(), self._offs, len(st.modules), 1.0 / self.world,
+                                               float(self.clip), float(self.lr), float(self.betas[0]), float(self.betas[1]),
+                                               float(self.eps), self.step_count, self._opt_ws.data_ptr(), self._opt_ws.numel(),
+                                               torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(rc, "dpmn_clip_adam_step")
+        st.bump_epoch()          # parameters changed behind torch's version counters: cached 16-bit weights are stale
+
+    def step(self, psn_out, priors_b1, priors_b2, hr, global_batch: int = None) -> torch.Tensor:
+        """forward + backward + all-reduce + clip + Adam; returns the (local) loss as a 0-d tensor.  `global_batch`: total
+        images over all ranks when the shards are uneven (dist.shard_range) -- each rank's loss is then weighted by
+        local / (global / world), so that the summed gradients / world are those of the global-batch mean."""
+        self.state.zero_grads()
+        self._cmm_reduced = False
         outs = self.model.forward_all(psn_out, priors_b1, priors_b2)
         loss = self.loss(outs, hr)
-        loss.backward()
-        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.bucket.allreduce_mean(self.group)
-        for m in self.modules + self.distill:                      # super_resolution.py:270-275
-            torch.nn.utils.clip_grad_norm_(m.parameters(), self.clip)
-        self.opt.step()
+        w = 1.0
+        if self.world > 1 and global_batch:
+            w = psn_out.shape[0] * self.world / float(global_batch)
+        (loss * w if w != 1.0 else loss).backward()
+        if self.dist_on:
+            self._allreduce()
+        self._optimizer_step()
         return loss.detach()

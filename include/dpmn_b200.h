@@ -152,6 +152,14 @@ typedef struct dpmn_cmm_desc {
   void *prepared;                             /* as in dpmn_pgrm_desc: staged tap-major 16-bit weights + folded BN */
   int32_t prepared_valid;
   int32_t flags;                              /* DPMN_CMM_* bits, 0 by default */
+  /* Optional final blend of the eval / test call sites (interfaces/super_resolution.py:449,705):
+   *   out = blend_alpha * CMM(x1, x2) + (1 - blend_alpha) * blend_input      (blend_input = images_lr_psn[:, :3])
+   * fused into the kernel that writes `out`.  blend_input == NULL (default): plain CMM output.  (B, c_img, H, W) fp32,
+   * batch stride in elements (0 = dense; the call sites pass a channel-slice view of a 4-channel tensor). */
+  const float *blend_input;
+  int64_t blend_input_batch_stride;
+  float blend_alpha;
+  int32_t reserved_;
 } dpmn_cmm_desc;
 
 /* dpmn_cmm_backward only: `workspace` is the buffer a dpmn_cmm_forward call with precision DPMN_PREC_F32 or with
@@ -370,6 +378,32 @@ int dpmn_distill_forward(const dpmn_distill_desc *d, const float *x_deep, const 
 int dpmn_distill_backward(const dpmn_distill_desc *d, const float *x_deep, const float *x_shallow, const float *d_loss,
                           const float *d_feature, const dpmn_distill_grads *grads, void *workspace, size_t workspace_bytes,
                           void *stream);
+
+/* ---- the tail of one data-parallel training step (SURVEY.md 8b proposal, 8e) --------------------------------------------
+ * dpmn_allreduce_bucket <- the gradient reduction of nn.DataParallel(model, device_ids=range(ngpu)), interfaces/base.py:160-162
+ *                          (replicate + scatter + gather onto GPU 0 every iteration in the reference); here: ONE
+ *                          ncclAllReduce(sum) in place over `count` elements of the flat gradient bucket, on `stream`.
+ *   comm: from dpmn_nccl_comm_init (rank 0 makes the 128-byte id with dpmn_nccl_unique_id and ships it to the other ranks
+ *   through any side channel -- dpmn_b200.dist uses the torch.distributed store).  dtype: DPMN_PREC_F32 / F16 / BF16.
+ *   libnccl is resolved with dlopen at the first call (the copy already loaded in the process first); without it every
+ *   function here returns DPMN_E_DEVICE and dpmn_nccl_available() is 0.
+ * dpmn_clip_adam_step   <- torch.nn.utils.clip_grad_norm_(module.parameters(), 0.25) per module, super_resolution.py:270-275,
+ *                          + optimizer_G.step() = Adam(lr, betas=(0.5, 0.999)), interfaces/base.py:208-221, over FLAT fp32
+ *                          buffers (parameters, gradients, exp_avg, exp_avg_sq: same length, 16-byte aligned) in two launches.
+ *   segment_offsets: HOST array of n_segments + 1 element offsets (module boundaries inside the flat buffers; offsets[0] = 0,
+ *   offsets[n] = total; n_segments <= 32): the 2-norm is taken and clipped per segment, as the reference does per module.
+ *   grad_scale multiplies every gradient first (1 / world after a summing all-reduce).  max_norm <= 0: no clipping.
+ *   step: 1-based Adam step count (bias correction).  workspace: dpmn_clip_adam_workspace_bytes(n_segments) device bytes. */
+int dpmn_nccl_available(void);
+int dpmn_nccl_version(void);                                  /* ncclGetVersion(), 0 when unavailable */
+int dpmn_nccl_unique_id(void *id128);                         /* HOST buffer of 128 bytes */
+int dpmn_nccl_comm_init(const void *id128, int32_t world, int32_t rank, void **comm_out);   /* current device */
+int dpmn_nccl_comm_destroy(void *comm);
+int dpmn_allreduce_bucket(void *comm, void *bucket, size_t count, int32_t dtype, void *stream);
+size_t dpmn_clip_adam_workspace_bytes(int32_t n_segments);
+int dpmn_clip_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, const int64_t *segment_offsets,
+                        int32_t n_segments, float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
+                        int64_t step, void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

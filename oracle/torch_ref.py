@@ -241,9 +241,10 @@ def cmm_forward(P: Dict[str, torch.Tensor], x1, x2, training: bool = False, retu
 
 
 def hot_path_forward(pgrm_params: List[Dict[str, torch.Tensor]], cmm_params, psn_out, priors_b1, priors_b2,
-                     windows=(2, 4, 8), num_heads=6):
+                     windows=(2, 4, 8), num_heads=6, alpha=None):
     """The call-site data flow of interfaces/super_resolution.py:174-265 (inference): two cascades of
-    three PGRMs on the PSN output, then the CMM.  priors_b1[k] (B,2,H,W), priors_b2[k] (B,3,H,W)."""
+    three PGRMs on the PSN output, then the CMM.  priors_b1[k] (B,2,H,W), priors_b2[k] (B,3,H,W).
+    alpha: the eval / test blend with the PSN image, super_resolution.py:449,705 (None = plain CMM output)."""
     outs = []
     for branch, priors in ((0, priors_b1), (1, priors_b2)):
         cascade = psn_out[:, :3]
@@ -253,7 +254,8 @@ def hot_path_forward(pgrm_params: List[Dict[str, torch.Tensor]], cmm_params, psn
             done.append(y)
             cascade = y
         outs.append(done[-1])
-    return cmm_forward(cmm_params, outs[0], outs[1], training=False)
+    y = cmm_forward(cmm_params, outs[0], outs[1], training=False)
+    return y if alpha is None else alpha * y + (1 - alpha) * psn_out[:, :3]
 
 
 # ---- the callers' steps on either side of the hot path ------------------------------------------------

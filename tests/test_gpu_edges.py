@@ -75,9 +75,23 @@ def test_reference_error_behaviour():
     c, _ = build_cmm(metac, DEV)
     with pytest.raises(ValueError):
         c(torch.zeros(1, 3, 32, 128, device=DEV), torch.zeros(1, 3, 16, 64, device=DEV))
+
+
+def test_cmm_train_mode_single_32x32_image_runs_like_the_reference():
+    """B = 1 at 32x32 in train(): the reference does NOT raise -- the 1x1 bottleneck (en_6, cmm.py:91-93) has no BatchNorm and
+    the smallest normalised maps (en_5, de_6) are 2x2 = 4 values per channel.  Checked against the oracle (batch statistics)."""
+    from oracle import cmm_oracle
+    zc, metac = load_golden("cmm_c8_train")
+    Pc, _, _ = cmm_case(metac)
+    c, _ = build_cmm(metac, DEV)
     c.train()
-    with pytest.raises(ValueError):                              # nn.BatchNorm2d: one value per channel at the bottleneck
-        c(torch.zeros(1, 3, 32, 32, device=DEV), torch.zeros(1, 3, 32, 32, device=DEV))
+    r = np.random.default_rng(5)
+    x1 = r.uniform(0, 1, (1, 3, 32, 32)).astype(np.float32)
+    x2 = r.uniform(0, 1, (1, 3, 32, 32)).astype(np.float32)
+    with torch.no_grad():
+        y = c(_t(x1), _t(x2))
+    ref = cmm_oracle.cmm_forward(Pc, x1, x2, training=True)
+    assert rel_err(y.cpu().numpy(), ref) < 1e-4
 
 
 def test_c_abi_return_codes_with_device_pointers():

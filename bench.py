@@ -574,7 +574,7 @@ def run_ours(args):
         if timed_out is not None and ref_out is not None:
             ref = ref_out.numpy()
             err = float(np.abs(timed_out - ref).max() / np.abs(ref).max())
-            bar = {"fp32": 1e-4, "fp16": 2e-3, "bf16": 1e-2}[args.precision]
+            bar = {"fp32": 1e-4, "fp16": 1e-3, "bf16": 1e-2}[args.precision]   # BASELINE north_star: 1e-3 rel fp16
             parity = {"max_abs_err_over_max_ref": err, "bar": bar, "ok": bool(err < bar),
                       "what": f"output of the timed CUDA-graph configuration on input set 0 (batch {B}, 6 PGRM + CMM + alpha blend) vs "
                               "oracle/torch_ref.hot_path_forward on the same inputs and weights (fp32 CPU)"}

@@ -71,6 +71,8 @@ class FlatTrainState:
     all-reduce of a module's segment can start as soon as that module's backward has been enqueued -- the CMM (94 % of the
     bucket) finishes its backward FIRST, so its segment travels over NVLink while the six PGRMs still compute."""
 
+    ALIGN = 64          # elements (256 bytes)
+
     def __init__(self, modules):
         """modules: list of nn.Module in segment order."""
         self.modules = list(modules)
@@ -82,17 +84,20 @@ class FlatTrainState:
         if not self.params:
             raise ValueError("FlatTrainState: no trainable parameters")
         dev = self.params[0].device
-        sizes = [sum(p.numel() for _, p in named) for named in per_mod]
-        # every segment starts on a 16-byte boundary (float4 accesses in the fused optimizer, aligned NCCL chunks)
+        # every PARAMETER starts on a 256-byte boundary inside the flat buffers, like a tensor of its own from torch's
+        # allocator would: the kernels read weights with 16-byte vector loads and TMA.  The padding elements stay zero in
+        # all four buffers (zero gradient -> zero moments -> zero update), so norms and the all-reduce are unaffected.
+        A = self.ALIGN
+        sizes = [sum((p.numel() + A - 1) // A * A for _, p in named) for named in per_mod]
         self.offsets = [0]
         for sz in sizes:
-            self.offsets.append(self.offsets[-1] + (sz + 3) // 4 * 4)
+            self.offsets.append(self.offsets[-1] + sz)
         total = self.offsets[-1]
         self.flat_params = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_grads = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = None          # allocated by the optimizer that uses them
         self.exp_avg_sq = None
-        self.n_params = sum(sizes)
+        self.n_params = sum(p.numel() for p in self.params)
         for m, named, start in zip(self.modules, per_mod, self.offsets[:-1]):
             off = start
             sink = {}
@@ -105,7 +110,7 @@ class FlatTrainState:
                     g.copy_(p.grad)
                 p.grad = g
                 sink[n] = g
-                off += k
+                off += (k + A - 1) // A * A
             m._grad_sink = sink
             m._weights_epoch = getattr(m, "_weights_epoch", 0) + 1     # parameter storage moved: re-stage cached weights
 

@@ -74,10 +74,13 @@ def _worker_state(rank, world, port, q):
     same = all(torch.equal(g, gathered[0]) for g in gathered)
     st = FlatTrainState(mods)
     # segments: 16-byte aligned starts, parameters and gradients are views of the flat buffers
-    ok_layout = st.offsets[0] == 0 and all(o % 4 == 0 for o in st.offsets) and st.n_params == 18 + 28 + 14
+    ok_layout = st.offsets[0] == 0 and all(o % 64 == 0 for o in st.offsets) and st.n_params == 18 + 28 + 14
+    ok_layout = ok_layout and all((p.data_ptr() - st.flat_params.data_ptr()) % 256 == 0 and
+                                   (p.grad.data_ptr() - st.flat_grads.data_ptr()) % 256 == 0 for p in st.params)
     p0 = mods[0].weight
     p0.data.fill_(3.0)
-    ok_views = bool(torch.all(st.flat_params[:15] == 3.0)) and p0.grad.data_ptr() == st.flat_grads.data_ptr()
+    ok_views = bool(torch.all(st.flat_params[:15] == 3.0)) and float(st.flat_params[15:64].abs().max()) == 0.0 \
+        and p0.grad.data_ptr() == st.flat_grads.data_ptr()
     ok_sink = set(mods[0]._grad_sink) == {"weight", "bias"} and mods[1]._grad_sink["0.weight"].shape == (7, 3)
     # uneven shards: global batch 5 -> 3 + 2 images; each rank holds the gradient of its LOCAL mean
     lo, hi = shard_range(5, rank, world)

@@ -108,8 +108,12 @@ def test_trainer_fused_tail_equals_the_torch_tail_over_three_steps():
     (l0, w0), (l1, w1) = finals
     assert np.allclose(l0, l1, rtol=2e-4), (l0, l1)
     assert l0[2] < l0[0]                                     # and the step actually trains
+    # Adam's first steps move every weight by ~lr = 1e-3 in the direction sign(g): where a gradient element is within fp32
+    # summation noise of 0 (atomics order differs from run to run) the two runs may legitimately step in opposite directions,
+    # so the bar is statistical per tensor (the exact check of the kernel is the stand-alone test above, 2e-6)
     for n in w0:
-        assert float((w0[n] - w1[n]).abs().max()) < 5e-5, n  # Adam's first steps move every weight by ~lr = 1e-3
+        d = (w0[n] - w1[n]).abs()
+        assert float(d.max()) < 3 * 2e-3 and float(d.mean()) < 5e-5, (n, float(d.max()), float(d.mean()))
 
 
 def test_train_mode_forward_does_not_validate_the_prepared_weight_cache():

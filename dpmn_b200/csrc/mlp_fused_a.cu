@@ -8,15 +8,20 @@
 // fc1's output (128 x 384 values) IS 48 complete 32 x 32 planes of the (384, 32, 32) view (tests/test_mlp_tile_maps.py),
 // so the conv needs nothing from other tiles.
 //
-//   warp 0     TMA: fc1 weight (384 x 96, two 64-column k-blocks, SW128) once per CTA; the A tile (128 x 96) per tile
-//   warp 1     tcgen05.mma: 3 n-blocks of M128 x N128, K = 96 (4 + 2 k-steps) into TMEM columns 0..383
-//   warps 2-9  epilogue: tcgen05.ld 32-column chunks (two warps per lane quarter take alternate chunks), + bias,
-//              gelu_fast, 16-bit, into the plane buffer at flat 384 m + j (plane stride 1026 halves);
-//              named barrier; depthwise 3x3 + GELU out of the plane buffer: warp = plane row, lane = channel pair
-//              (24 of 32 lanes), two x per step, packed fma.rn.f32x2 across the pair, tap order of dwconv16_kernel;
-//              one 96-byte run per pixel into dt (B, 1024, 384); named barrier (plane buffer free again).
-//   The MMAs of tile i + 1 overlap the conv of tile i (TMEM is drained once the epilogue has arrived on tmem_empty).
-// Arithmetic is meant to be bit-identical to gemm_tc (fc1 epilogue) followed by dwconv16_kernel.
+//   warp 0      TMA: fc1 weight (384 x 96, two 64-column k-blocks, SW128) once per CTA; the A tile (128 x 96) per tile
+//   warp 1      tcgen05.mma: 3 n-blocks of M128 x N128, K = 96 (4 + 2 k-steps) into TMEM columns 0..383
+//   warps 2-13  (12 worker warps, 3 per TMEM lane quarter)
+//     phase 1   tcgen05.ld 32-column chunks (a chunk of a token row IS one 32-pixel row of one plane), + bias, GELU with the
+//               polynomial part in packed fma.rn.f32x2, 16-bit, 4 x 8-byte shared stores into the plane buffer
+//               [channel pair][y][plane of the pair][32 pixels] (pair stride 1026 words: conflict-free 8-byte loads);
+//     phase 2   depthwise 3x3 + GELU: thread = (channel pair, two output rows) -- 24 x 16 = 384 items = one per worker
+//               thread -- slides over x in 4-pixel chunks (8-byte loads of the 4 input rows of both planes, converted once,
+//               reused by both output rows and all three kx taps), accumulates the pair in packed fma.rn.f32x2, and writes
+//               one 4-byte (c, c+1) word per pixel into dt (B, 1024, 384): the 24 lanes of a row pair cover 96 contiguous bytes.
+//   The MMAs of tile i + 1 overlap phase 2 of tile i (TMEM is drained once phase 1 has arrived on tmem_empty).
+// Both phases are bound by the two MUFU ops of each GELU (ex2 + rcp; 4 per hidden element = 6.4 us per 128-token tile at
+// 16 MUFU lanes per clock); everything else is sized to hide under that.  Arithmetic per element is that of gemm_tc's fc1
+// epilogue followed by dwconv16_kernel (same GELU form, same tap order).
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -29,15 +34,19 @@ namespace {
 
 constexpr int MA_ROWS = 128, MA_C = 96, MA_HID = 384, MA_SIDE = 32, MA_L = MA_SIDE * MA_SIDE;
 constexpr int MA_PLANES = MA_ROWS * MA_HID / MA_L;         // 48 planes per tile
-constexpr int MA_PWORDS = (MA_L + 2) / 2;                  // 513 words per plane in shared memory (odd: conflict-free lanes)
+constexpr int MA_PAIRS = MA_PLANES / 2;                    // 24 channel pairs
+constexpr int MA_PAIR_WORDS = 2 * MA_L / 2 + 2;            // 1026 words per pair: [y][plane of the pair][16 words] + 2 pad
 constexpr int MA_KTILE = 128 * 128;                        // bytes of one 128-row x 64-column SW128 tile
 constexpr int MA_A_BYTES = 2 * MA_KTILE;                   // K = 96 as two k-blocks (columns 96..127 are TMA zero fill)
 constexpr int MA_W_BYTES = 2 * 3 * MA_KTILE;               // 384 rows x two k-blocks
-constexpr int MA_P_BYTES = MA_PLANES * MA_PWORDS * 4;      // 98 496
-constexpr int MA_THREADS = 64 + 256;
+constexpr int MA_P_BYTES = MA_PAIRS * MA_PAIR_WORDS * 4;   // 98 496
+constexpr int MA_WORKERS = 12;                             // worker warps
+constexpr int MA_WTHREADS = 32 * MA_WORKERS;               // 384 = 24 pairs x 16 row pairs
+constexpr int MA_THREADS = 64 + MA_WTHREADS;
 constexpr int MA_SMEM = MA_W_BYTES + MA_A_BYTES + MA_P_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;   // 230 848 B
 static_assert(MA_SMEM <= 232448, "227 KB of dynamic shared memory per CTA");
 static_assert(MA_PLANES * MA_L == MA_ROWS * MA_HID, "a tile is a whole number of planes");
+static_assert(MA_PAIRS * (MA_SIDE / 2) == MA_WTHREADS, "one (channel pair, row pair) item per worker thread");
 
 struct MlpAParams {
   int tiles;                  // B * 8
@@ -48,20 +57,48 @@ struct MlpAParams {
   void* dt;                   // (B, 1024, 384) 16-bit, pixel-major
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+typedef unsigned long long u64;
 
-__device__ __forceinline__ unsigned long long p2(float x, float y) {
-  unsigned long long r;
+__device__ __forceinline__ void worker_bar_sync() { asm volatile("bar.sync 1, 384;" ::: "memory"); }
+
+__device__ __forceinline__ u64 p2(float x, float y) {
+  u64 r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
   return r;
 }
-__device__ __forceinline__ void u2(unsigned long long v, float& x, float& y) {
+__device__ __forceinline__ void u2(u64 v, float& x, float& y) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
 }
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// gelu_fast (common.cuh) on two values at once: the polynomial in packed f32x2, ex2 / rcp per lane.  Every operation is
+// the .rn form of its scalar counterpart, so the results are bit-identical to gelu_fast.
+__device__ __forceinline__ u64 gelu_fast2(u64 x) {
+  float u0, u1;
+  u2(mul2(x, x), u0, u1);
+  const u64 u = p2(fminf(u0, 64.0f), fminf(u1, 64.0f));
+  u64 q = fma2(p2(1.0142650e-3f, 1.0142650e-3f), u, p2(-1.0677574e-1f, -1.0677574e-1f));
+  q = fma2(q, u, p2(-2.3011213f, -2.3011213f));
+  float z0, z1, e0, e1, r0, r1;
+  u2(mul2(x, q), z0, z1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(z0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(z1));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(1.0f + e0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(1.0f + e1));
+  return mul2(x, p2(r0, r1));
 }
 template <typename T> __device__ __forceinline__ float2 word_f2(uint32_t w);
 template <> __device__ __forceinline__ float2 word_f2<__half>(uint32_t w) {
@@ -79,6 +116,11 @@ template <> __device__ __forceinline__ uint32_t f2_word<__nv_bfloat16>(float a, 
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+template <typename T> __device__ __forceinline__ uint32_t u64_word(u64 v) {
+  float a, b;
+  u2(v, a, b);
+  return f2_word<T>(a, b);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(MA_THREADS, 1)
@@ -87,7 +129,7 @@ mlp_fc1_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_w = smem;                                     // [kb][384 rows x 128 B]
   uint8_t* s_a = s_w + MA_W_BYTES;                         // [kb][128 rows x 128 B]
-  uint32_t* s_pl = reinterpret_cast<uint32_t*>(s_a + MA_A_BYTES);   // [48][513] words = planes of 32 x 32 halves (+2 pad)
+  uint32_t* s_pl = reinterpret_cast<uint32_t*>(s_a + MA_A_BYTES);   // [24 pairs][1026]: [y][plane of the pair][16 words]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_pl) + MA_P_BYTES);
   uint64_t* w_full = bars;
   uint64_t* a_full = bars + 1;
@@ -101,7 +143,7 @@ mlp_fc1_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
     mbar_init(w_full, 1); mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    mbar_init(tmem_full, 1); mbar_init(tmem_empty, 8);
+    mbar_init(tmem_full, 1); mbar_init(tmem_empty, MA_WORKERS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -150,98 +192,120 @@ mlp_fc1_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       }
     }
   } else {
-    // ================= epilogue + depthwise conv (warps 2..9) =================
+    // ================= 12 worker warps: fc1 epilogue, then the depthwise conv =================
     const int quarter = warp & 3;                             // TMEM lane quarter this warp may access
-    const int ew = warp - 2;                                  // 0..7
-    const int half = ew >> 2;                                 // which of the two warps of the quarter
+    const int third = (warp - 2) >> 2;                        // which of the quarter's three warps
     const int m_local = quarter * 32 + lane;
-    T* dt = reinterpret_cast<T*>(p.dt);
+    const int wt = threadIdx.x - 64;                          // 0..383
+    const int pair = wt % MA_PAIRS;                           // channel pair of the tile
+    const int r0 = 2 * (wt / MA_PAIRS);                       // first of this thread's two output rows
+    uint32_t* out_words = reinterpret_cast<uint32_t*>(p.dt);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+      // ---------------- phase 1: hidden = GELU(fc1) of this tile -> planes ----------------
       mbar_wait(tmem_full, (uint32_t)(it & 1));
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = half * 32; c0 < MA_HID; c0 += 64) {
+      for (int c0 = third * 32; c0 < MA_HID; c0 += 96) {
         float4 bb[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(p.fc1_b + c0) + j);
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
         tmem_ld_wait();
-        float v[32];
+        // hidden value (token m, column j) sits at flat 384 m + j of the tile: plane flat / 1024, pixel flat % 1024; the 32
+        // columns of a chunk are exactly one 32-pixel row of that plane (tests/test_mlp_tile_maps.py)
+        const int flat = MA_HID * m_local + c0;
+        const int pl = flat >> 10, y = (flat >> 5) & 31;
+        uint2* dst = reinterpret_cast<uint2*>(s_pl + (pl >> 1) * MA_PAIR_WORDS + y * 32 + (pl & 1) * 16);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          v[4 * j] = __uint_as_float(r[4 * j]) + bb[j].x;
-          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb[j].y;
-          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb[j].z;
-          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb[j].w;
+          const u64 g0 = gelu_fast2(add2(p2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), p2(bb[j].x, bb[j].y)));
+          const u64 g1 = gelu_fast2(add2(p2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), p2(bb[j].z, bb[j].w)));
+          dst[j] = make_uint2(u64_word<T>(g0), u64_word<T>(g1));
         }
-        // hidden value (token m, column j) sits at flat 384 m + j of the tile = plane flat / 1024, offset flat % 1024;
-        // a 32-column chunk never leaves its plane row (tests/test_mlp_tile_maps.py)
-        const int flat = MA_HID * m_local + c0;
-        uint32_t* dst = s_pl + (flat >> 10) * MA_PWORDS + ((flat & (MA_L - 1)) >> 1);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) dst[e] = f2_word<T>(gelu_fast(v[2 * e]), gelu_fast(v[2 * e + 1]));
       }
-      // the accumulator is free as soon as its last chunk has been read: the MMAs of the next tile overlap the conv below
+      // the accumulator is free as soon as its last chunk has been read: the MMAs of the next tile overlap phase 2
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty);
-      epi_bar_sync();                                         // all 48 planes of this tile are complete
+      worker_bar_sync();                                      // all 48 planes of this tile are complete
 
-      if (lane < MA_PLANES / 2) {
+      // ---------------- phase 2: depthwise 3x3 + GELU, item = (pair, rows r0 and r0 + 1) ----------------
+      {
         const int b = tile >> 3, tt = tile & 7;
-        const int c = MA_PLANES * tt + 2 * lane;              // global channel of the pair (c, c + 1)
-        unsigned long long wk[9];
+        const int c = MA_PLANES * tt + 2 * pair;              // global channel of the pair (c, c + 1)
+        u64 wk[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) wk[k] = p2(__ldg(p.dw_w + c * 9 + k), __ldg(p.dw_w + (c + 1) * 9 + k));
-        const unsigned long long bias = p2(__ldg(p.dw_b + c), __ldg(p.dw_b + c + 1));
-        const uint32_t* pl0 = s_pl + (2 * lane) * MA_PWORDS;
-        const uint32_t* pl1 = pl0 + MA_PWORDS;
+        const u64 bias = p2(__ldg(p.dw_b + c), __ldg(p.dw_b + c + 1));
+        const uint32_t* base = s_pl + pair * MA_PAIR_WORDS;
+        // the four input rows r0 - 1 .. r0 + 2 (rows outside the plane contribute zeros)
+        const bool ok[4] = {r0 > 0, true, true, r0 + 2 < MA_SIDE};
+        const uint32_t* rowp[4] = {base + (r0 > 0 ? r0 - 1 : r0) * 32, base + r0 * 32, base + (r0 + 1) * 32,
+                                   base + (r0 + 2 < MA_SIDE ? r0 + 2 : r0 + 1) * 32};
+        u64 cur[4][4], left[4];
+        uint2 na[4], nb[4];                                   // raw words of the next 4-pixel chunk, planes a / b
+        auto load_raw = [&](int j) {
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            na[rr] = *reinterpret_cast<const uint2*>(rowp[rr] + 2 * j);
+            nb[rr] = *reinterpret_cast<const uint2*>(rowp[rr] + 16 + 2 * j);
+          }
+        };
+        auto convert = [&]() {
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            if (ok[rr]) {
+              const float2 a0 = word_f2<T>(na[rr].x), a1 = word_f2<T>(na[rr].y);
+              const float2 b0 = word_f2<T>(nb[rr].x), b1 = word_f2<T>(nb[rr].y);
+              cur[rr][0] = p2(a0.x, b0.x); cur[rr][1] = p2(a0.y, b0.y); cur[rr][2] = p2(a1.x, b1.x); cur[rr][3] = p2(a1.y, b1.y);
+            } else {
+              cur[rr][0] = cur[rr][1] = cur[rr][2] = cur[rr][3] = 0ULL;
+            }
+          }
+        };
+        load_raw(0);
+        convert();
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) left[rr] = 0ULL;
+        // word index of (pixel (r0, 0), channel pair c) in dt viewed as 32-bit words: ((b * 1024 + y * 32 + x) * 384 + c) / 2
+        uint32_t* out0 = out_words + ((long long)b * MA_L + r0 * MA_SIDE) * (MA_HID / 2) + (c >> 1);
 #pragma unroll 1
-        for (int y = ew; y < MA_SIDE; y += 8) {
-          // rows y - 1, y, y + 1 of both planes; a row outside the plane contributes zeros
-          const bool ok0 = y > 0, ok2 = y + 1 < MA_SIDE;
-          const uint32_t* ra[3] = {pl0 + (ok0 ? y - 1 : y) * 16, pl0 + y * 16, pl0 + (ok2 ? y + 1 : y) * 16};
-          const uint32_t* rb[3] = {pl1 + (ok0 ? y - 1 : y) * 16, pl1 + y * 16, pl1 + (ok2 ? y + 1 : y) * 16};
-          const bool okr[3] = {ok0, true, ok2};
-          unsigned long long pm1[3], p0[3], p1[3];
+        for (int j = 0; j < MA_SIDE / 4; ++j) {
+          u64 right[4];
+          if (j + 1 < MA_SIDE / 4) {
+            load_raw(j + 1);
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            const float2 fa = okr[ky] ? word_f2<T>(ra[ky][0]) : make_float2(0.f, 0.f);
-            const float2 fb = okr[ky] ? word_f2<T>(rb[ky][0]) : make_float2(0.f, 0.f);
-            pm1[ky] = p2(0.f, 0.f);
-            p0[ky] = p2(fa.x, fb.x);
-            p1[ky] = p2(fa.y, fb.y);
+            for (int rr = 0; rr < 4; ++rr)
+              right[rr] = ok[rr] ? p2(word_f2<T>(na[rr].x).x, word_f2<T>(nb[rr].x).x) : 0ULL;
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) right[rr] = 0ULL;
           }
-          uint32_t* out = reinterpret_cast<uint32_t*>(dt + ((long long)b * MA_L + y * MA_SIDE) * MA_HID + c);
-#pragma unroll 2
-          for (int xw = 0; xw < MA_SIDE / 2; ++xw) {
-            unsigned long long n0[3], n1[3];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              float2 fa = make_float2(0.f, 0.f), fb = fa;
-              if (okr[ky] && xw + 1 < MA_SIDE / 2) { fa = word_f2<T>(ra[ky][xw + 1]); fb = word_f2<T>(rb[ky][xw + 1]); }
-              n0[ky] = p2(fa.x, fb.x);
-              n1[ky] = p2(fa.y, fb.y);
+          for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+              u64 acc = bias;
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {               // tap order of dwconv16_kernel: ky outer, kx inner
+                const int rr = o + ky;
+                const u64 vl = i == 0 ? left[rr] : cur[rr][i == 0 ? 0 : i - 1];
+                const u64 vr = i == 3 ? right[rr] : cur[rr][i == 3 ? 3 : i + 1];
+                acc = fma2(vl, wk[3 * ky], acc);
+                acc = fma2(cur[rr][i], wk[3 * ky + 1], acc);
+                acc = fma2(vr, wk[3 * ky + 2], acc);
+              }
+              out0[((long long)o * MA_SIDE + 4 * j + i) * (MA_HID / 2)] = u64_word<T>(gelu_fast2(acc));
             }
-            unsigned long long acc_a = bias, acc_b = bias;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              acc_a = fma2(pm1[ky], wk[3 * ky], acc_a); acc_a = fma2(p0[ky], wk[3 * ky + 1], acc_a); acc_a = fma2(p1[ky], wk[3 * ky + 2], acc_a);
-              acc_b = fma2(p0[ky], wk[3 * ky], acc_b); acc_b = fma2(p1[ky], wk[3 * ky + 1], acc_b); acc_b = fma2(n0[ky], wk[3 * ky + 2], acc_b);
-            }
-            float a0, a1, b0, b1;
-            u2(acc_a, a0, a1);
-            u2(acc_b, b0, b1);
-            out[(long long)(2 * xw) * (MA_HID / 2)] = f2_word<T>(gelu_fast(a0), gelu_fast(a1));
-            out[(long long)(2 * xw + 1) * (MA_HID / 2)] = f2_word<T>(gelu_fast(b0), gelu_fast(b1));
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) { pm1[ky] = p1[ky]; p0[ky] = n0[ky]; p1[ky] = n1[ky]; }
           }
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) left[rr] = cur[rr][3];
+          if (j + 1 < MA_SIDE / 4) convert();
         }
       }
-      epi_bar_sync();                                         // the plane buffer may be overwritten by the next tile
+      worker_bar_sync();                                      // the plane buffer may be overwritten by the next tile
     }
   }
 

@@ -53,6 +53,39 @@ def _flat_idx(shape):
     return np.arange(int(np.prod(shape)), dtype=np.uint64).reshape(shape)
 
 
+# ---- emulation of the 16-bit tensor-core modes' operand rounding (tests only) -----------------------------------------
+# In the fp16 / bf16 modes the CUDA path rounds both OPERANDS of every tensor-core contraction to 16 bits and accumulates in
+# fp32; everything else (LayerNorm, softmax, BatchNorm statistics, activations, the residual stream) stays fp32.  With
+# OPERAND_ROUND set, the contractions below round their operands the same way (straight-through: the rounding is invisible
+# to autograd, exactly like the CUDA backward, which differentiates the fp32 formulas), so this oracle reproduces the
+# 16-bit forward -- and therefore its ReLU / LeakyReLU / Dropout masks -- to fp32 accumulation order.  Gradient tests of
+# the 16-bit modes compare against THIS evaluation: what is left is the rounding of the backward's own operands.
+OPERAND_ROUND = None          # None | torch.float16 | torch.bfloat16
+
+
+class operand_rounding:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global OPERAND_ROUND
+        self.prev, OPERAND_ROUND = OPERAND_ROUND, self.dtype
+
+    def __exit__(self, *exc):
+        global OPERAND_ROUND
+        OPERAND_ROUND = self.prev
+
+
+def _r(x, on=True):
+    if OPERAND_ROUND is None or not on:
+        return x
+    return x + (x.detach().to(OPERAND_ROUND).to(x.dtype) - x.detach())
+
+
+def _linear_tc(x, w, b):
+    return F.linear(_r(x), _r(w), b)
+
+
 def _order(H, W, ws, shift):
     """window-major row -> original token (pgrm.py:209-221,43-52)."""
     p = torch.arange(H * W)
@@ -113,26 +146,26 @@ def _sk(x, P, pre, G):
     """SKConv.forward, pgrm.py:79-96, token-major."""
     B, L, C = x.shape
     cg = C // G
-    f = F.linear(x, P[pre + "proj.weight"], P[pre + "proj.bias"])
+    f = _linear_tc(x, P[pre + "proj.weight"], P[pre + "proj.bias"])
     s = F.gelu(f).mean(dim=1)
     z = F.gelu(F.linear(s, P[pre + "fc1.weight"], P[pre + "fc1.bias"]))
     a = torch.softmax(F.linear(z, P[pre + "fc2.weight"], P[pre + "fc2.bias"]).view(B, G, cg), dim=1)
     v = (x.view(B, L, G, cg) * a[:, None]).sum(dim=2)
-    return f + F.linear(v, P[pre + "proj_head.weight"], P[pre + "proj_head.bias"])
+    return f + _linear_tc(v, P[pre + "proj_head.weight"], P[pre + "proj_head.bias"])
 
 
 def _mlp(x, P, pre, drop=None, site=0):
     """Mlp.forward, pgrm.py:29-41, raw views kept (quirk 2).  drop = (p, seed): the two Dropout sites."""
     B, L, _ = x.shape
     side = int(math.sqrt(L))
-    h = F.gelu(F.linear(x, P[pre + "fc1.weight"], P[pre + "fc1.bias"]))
+    h = F.gelu(_linear_tc(x, P[pre + "fc1.weight"], P[pre + "fc1.bias"]))
     if drop is not None and drop[0] > 0:
         h = h * drop_scale(drop[0], drop[1], site + SITE_MLP1, _flat_idx(h.shape))
     hid = h.shape[-1]
     h = h.reshape(B, hid, side, side)
     h = F.gelu(F.conv2d(h, P[pre + "depthwise_conv.weight"], P[pre + "depthwise_conv.bias"], padding=1, groups=hid))
-    h = F.conv2d(h, P[pre + "pointwise_conv.weight"], P[pre + "pointwise_conv.bias"])
-    y = F.linear(h.reshape(B, L, hid), P[pre + "fc2.weight"], P[pre + "fc2.bias"])
+    h = F.conv2d(_r(h), _r(P[pre + "pointwise_conv.weight"]), P[pre + "pointwise_conv.bias"])
+    y = _linear_tc(h.reshape(B, L, hid), P[pre + "fc2.weight"], P[pre + "fc2.bias"])
     if drop is not None and drop[0] > 0:
         y = y * drop_scale(drop[0], drop[1], site + SITE_MLP2, _flat_idx(y.shape))
     return y
@@ -148,8 +181,8 @@ def _block(tq, tkv, P, pre, blk, windows, H, W, hpg, drop=None):
     wins = [min(ws, mn) for ws in windows]
     qn = F.layer_norm(tq, (C,), P[pre + "norm1_q.weight"], P[pre + "norm1_q.bias"])
     kvn = F.layer_norm(tkv, (C,), P[pre + "norm1_kv.weight"], P[pre + "norm1_kv.bias"])
-    q = F.linear(qn, P[pre + "attn.q.weight"], P[pre + "attn.q.bias"])
-    kv = F.linear(kvn, P[pre + "attn.kv.weight"], P[pre + "attn.kv.bias"])
+    q = _linear_tc(qn, P[pre + "attn.q.weight"], P[pre + "attn.q.bias"])
+    kv = _linear_tc(kvn, P[pre + "attn.kv.weight"], P[pre + "attn.kv.bias"])
     tables = [P[pre + f"attn.relative_position_bias_table_{g}"] for g in range(G)]
     if drop is None:
         a = window_attention_core(q, kv, tables, wins, shifts, H, W, hpg)
@@ -168,7 +201,7 @@ def _block(tq, tkv, P, pre, blk, windows, H, W, hpg, drop=None):
 
 
 def pgrm_forward(P: Dict[str, torch.Tensor], x_q, x_kv, residual_list: Sequence[torch.Tensor], *,
-                 windows=(2, 4, 8), num_heads=6, patch=2, drop=None):
+                 windows=(2, 4, 8), num_heads=6, patch=2, drop=None, parts=None):
     """PGRM.forward, pgrm.py:546-565.  drop=None: eval mode; drop=dict(seed, drop_rate, attn_drop_rate, drop_path):
     train mode with the CUDA path's masks."""
     if x_q.shape[1] == 2:
@@ -190,6 +223,8 @@ def pgrm_forward(P: Dict[str, torch.Tensor], x_q, x_kv, residual_list: Sequence[
     x = tkv.transpose(1, 2).reshape(B, C, H, W)
     x = F.conv2d(x, P["conv_before_upsample.0.weight"], P["conv_before_upsample.0.bias"], padding=1)
     x = F.conv2d(x, P["conv_before_upsample.1.weight"], P["conv_before_upsample.1.bias"], padding=1)
+    if parts is not None:
+        parts["head_pre"] = x                 # LeakyReLU input (B, hs * patch^2, H, W): tests mask out elements next to 0
     x = F.pixel_shuffle(F.leaky_relu(x, 0.01), patch)
     x = x * P["weight_list_0"]
     for i in range(1, len(residual_list)):   # residual_list[0] skipped (pgrm.py:563)
@@ -202,23 +237,42 @@ def _bn(x, P, pre, training):
                         P[pre + ".weight"], P[pre + ".bias"], training=training, eps=1e-5)
 
 
+def _tc_conv_ok(ho, wo):
+    """conv_tc_im2col_ok (csrc/cmm_im2col.cu): which convs of the fp32-structured CMM path run on the tensor cores."""
+    return (ho * wo) % 8 == 0 and ho * wo >= 16
+
+
+def _conv(x, w, b, **kw):
+    y = F.conv2d(x, w, b, **kw)
+    if OPERAND_ROUND is None or not _tc_conv_ok(y.shape[2], y.shape[3]):
+        return y
+    return F.conv2d(_r(x), _r(w), b, **kw)
+
+
+def _convT(x, w, b, **kw):
+    y = F.conv_transpose2d(x, w, b, **kw)
+    if OPERAND_ROUND is None or not _tc_conv_ok(y.shape[2], y.shape[3]):
+        return y
+    return F.conv_transpose2d(_r(x), _r(w), b, **kw)
+
+
 def cmm_forward(P: Dict[str, torch.Tensor], x1, x2, training: bool = False, return_parts: bool = False):
     """ComplementationModulationModule.forward, cmm.py:120-161.  With return_parts also the per-layer tensors
     (post-BatchNorm, pre-activation): o{l}_{br}, mid{l}_{br}, z6_{br}, zgate, d6, dmid{l}, d{l}."""
     parts = {}
     skips, bott = [], []
     for br, x in ((1, x1), (2, x2)):
-        o = [F.conv2d(x, P[f"en_1_{br}.weight"], P[f"en_1_{br}.bias"], padding=1)]
+        o = [_conv(x, P[f"en_1_{br}.weight"], P[f"en_1_{br}.bias"], padding=1)]
         parts[f"o1_{br}"] = o[0]
         for lvl in (2, 3, 4, 5):
             pre = f"en_{lvl}_{br}.encode."
-            t = F.conv2d(F.leaky_relu(o[-1], 0.2), P[pre + "1.weight"], P[pre + "1.bias"], stride=2, padding=3, dilation=2)
+            t = _conv(F.leaky_relu(o[-1], 0.2), P[pre + "1.weight"], P[pre + "1.bias"], stride=2, padding=3, dilation=2)
             t = _bn(t, P, pre + "2", training)
             parts[f"mid{lvl}_{br}"] = t
-            t = F.conv2d(F.leaky_relu(t, 0.2), P[pre + "4.weight"], P[pre + "4.bias"], padding=1)
+            t = _conv(F.leaky_relu(t, 0.2), P[pre + "4.weight"], P[pre + "4.bias"], padding=1)
             o.append(_bn(t, P, pre + "5", training))
             parts[f"o{lvl}_{br}"] = o[-1]
-        bott.append(F.conv2d(F.leaky_relu(o[-1], 0.2), P[f"en_6_{br}.1.weight"], P[f"en_6_{br}.1.bias"], stride=2, padding=1))
+        bott.append(_conv(F.leaky_relu(o[-1], 0.2), P[f"en_6_{br}.1.weight"], P[f"en_6_{br}.1.bias"], stride=2, padding=1))
         parts[f"z6_{br}"] = bott[-1]
         skips.append(o)
     z = torch.cat(bott, dim=1)
@@ -226,17 +280,17 @@ def cmm_forward(P: Dict[str, torch.Tensor], x1, x2, training: bool = False, retu
     g = torch.sigmoid(F.linear(F.relu(F.linear(g, P["fc_1.weight"], P["fc_1.bias"])), P["fc_2.weight"], P["fc_2.bias"]))
     z = z * g[:, :, None, None] + z
     parts["zgate"] = z
-    d = _bn(F.conv_transpose2d(F.relu(z), P["de_6.1.weight"], P["de_6.1.bias"], stride=2, padding=1), P, "de_6.2", training)
+    d = _bn(_convT(F.relu(z), P["de_6.1.weight"], P["de_6.1.bias"], stride=2, padding=1), P, "de_6.2", training)
     parts["d6"] = d
     for lvl in (5, 4, 3, 2):
         pre = f"de_{lvl}.decode."
         cat = torch.cat([d, skips[0][lvl - 1], skips[1][lvl - 1]], dim=1)
-        t = _bn(F.conv_transpose2d(F.relu(cat), P[pre + "1.weight"], P[pre + "1.bias"], stride=1, padding=1), P, pre + "2", training)
+        t = _bn(_convT(F.relu(cat), P[pre + "1.weight"], P[pre + "1.bias"], stride=1, padding=1), P, pre + "2", training)
         parts[f"dmid{lvl}"] = t
-        d = _bn(F.conv_transpose2d(F.relu(t), P[pre + "4.weight"], P[pre + "4.bias"], stride=2, padding=1), P, pre + "5", training)
+        d = _bn(_convT(F.relu(t), P[pre + "4.weight"], P[pre + "4.bias"], stride=2, padding=1), P, pre + "5", training)
         parts[f"d{lvl}"] = d
     cat = torch.cat([d, skips[0][0], skips[1][0]], dim=1)
-    y = F.conv_transpose2d(F.relu(cat), P["de_1.1.weight"], P["de_1.1.bias"], stride=1, padding=1)
+    y = _convT(F.relu(cat), P["de_1.1.weight"], P["de_1.1.bias"], stride=1, padding=1)
     return (y, parts) if return_parts else y
 
 

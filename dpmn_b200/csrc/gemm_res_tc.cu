@@ -23,7 +23,7 @@ namespace dpmn {
 
 using namespace tc;
 
-constexpr int RBM = 128, RBK = 64, RSTAGES = 3, RTHREADS = 192;
+constexpr int RBM = 128, RBK = 64, RSTAGES = 2, RTHREADS = 64 + 256 + 32;   // TMA warp, MMA warp, 8 epilogue warps, store warp
 
 struct GemmResParams {
   int M, N, K, batch, m_tiles;
@@ -42,7 +42,11 @@ struct ResSmem {
   static constexpr int CHUNKS = BN / 32;
   static constexpr int C_TILE = RBM * 128;             // 128 rows x 32 fp32, 128B swizzle
   static constexpr int Y_TILE = RBM * 64;              // 128 rows x 32 x 16-bit, 64B swizzle
-  static constexpr int TOTAL = RSTAGES * STAGE + CHUNKS * (C_TILE + Y_TILE) + 1024 + 256;
+  static constexpr int C_BUF = CHUNKS * C_TILE;        // one residual / result tile (in place)
+  static constexpr int Y_BUF = CHUNKS * Y_TILE;
+  static constexpr int STATS = RBM * 2 * 2 * 4;        // per row, per column half: (sum, sum of squares)
+  static constexpr int LNP = 2 * BN * 4;               // LayerNorm weight and bias
+  static constexpr int TOTAL = RSTAGES * STAGE + 2 * C_BUF + 2 * Y_BUF + STATS + LNP + 1024 + 256;
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
@@ -53,7 +57,18 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
+// Pipeline (per CTA, persistent over output tiles; tile i uses residual / result buffer i & 1):
+//   producer   residual tile of tile i -> buffer i & 1 as soon as the TMA store of tile i - 2 has read it out
+//              (res_empty), then the A / B k-blocks through a 2-stage ring
+//   MMA        accumulates tile i into TMEM stage i & 1
+//   epilogue   8 warps = 2 per TMEM lane quarter; the two threads of a row take 48 of its 96 columns each (BN / 2 in
+//              general), add accumulator + bias into the residual tile IN PLACE (swizzled shared memory), exchange their
+//              partial LayerNorm sums through shared memory, write the normalised 16-bit row and arrive on out_ready
+//   store warp one thread issues the TMA stores of both outputs of tile i, waits until they have read shared memory and
+//              hands the buffer back to the producer (res_empty): the residual tile of tile i + 2 is in flight while
+//              tile i + 1 is in its epilogue.
 template <int BN, typename YT>
 __global__ void __launch_bounds__(RTHREADS, 1)
 gemm_res_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -62,17 +77,22 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   using S = ResSmem<BN>;
+  static_assert(BN % 32 == 0 && (BN / 2) % 16 == 0, "column halves are whole 16-column tcgen05.ld chunks");
   uint8_t* tiles = smem;
-  uint8_t* c_stage = smem + RSTAGES * S::STAGE;                 // [CHUNKS][128 x 128 B]
-  uint8_t* y_stage = c_stage + S::CHUNKS * S::C_TILE;           // [CHUNKS][128 x 64 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(y_stage + S::CHUNKS * S::Y_TILE);
+  uint8_t* c_stage = smem + RSTAGES * S::STAGE;                 // [2][CHUNKS][128 x 128 B]
+  uint8_t* y_stage = c_stage + 2 * S::C_BUF;                    // [2][CHUNKS][128 x 64 B]
+  float* s_stat = reinterpret_cast<float*>(y_stage + 2 * S::Y_BUF);   // [128][2 halves][2]
+  float* s_lnw = s_stat + RBM * 4;
+  float* s_lnb = s_lnw + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lnb + BN);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + RSTAGES;
   uint64_t* tmem_full = bars + 2 * RSTAGES;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
-  uint64_t* res_full = tmem_full + 4;
-  uint64_t* res_empty = tmem_full + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 6);
+  uint64_t* res_full = tmem_full + 4;            // [2]
+  uint64_t* res_empty = tmem_full + 6;           // [2]
+  uint64_t* out_ready = tmem_full + 8;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 10);
   constexpr uint32_t TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -83,11 +103,15 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_r);
     tma_prefetch_desc(&map_c); tma_prefetch_desc(&map_y);
     for (int i = 0; i < RSTAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
-    mbar_init(res_full, 1); mbar_init(res_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8);
+      mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 1); mbar_init(&out_ready[i], 8);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (p.ln_mode == 1)
+    for (int i = threadIdx.x; i < BN; i += RTHREADS) { s_lnw[i] = __ldg(p.ln_w + i); s_lnb[i] = __ldg(p.ln_b + i); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -99,12 +123,13 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         const int m_blk = t % p.m_tiles, z = t / p.m_tiles;
+        const int rb = it & 1;
         // residual tile first: it is what the epilogue waits for longest
-        mbar_wait(res_empty, (uint32_t)((it & 1) ^ 1));
-        mbar_arrive_expect_tx(res_full, S::CHUNKS * S::C_TILE);
+        mbar_wait(&res_empty[rb], (uint32_t)(((it >> 1) & 1) ^ 1));
+        mbar_arrive_expect_tx(&res_full[rb], S::C_BUF);
 #pragma unroll
         for (int c = 0; c < S::CHUNKS; ++c)
-          tma_load_3d(c_stage + c * S::C_TILE, &map_r, res_full, c * 32, m_blk * RBM, z);
+          tma_load_3d(c_stage + rb * S::C_BUF + c * S::C_TILE, &map_r, &res_full[rb], c * 32, m_blk * RBM, z);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * S::STAGE;
@@ -141,84 +166,102 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 10) {
+    // ================= store warp =================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int m_blk = t % p.m_tiles, z = t / p.m_tiles;
+        const int rb = it & 1;
+        mbar_wait(&out_ready[rb], (uint32_t)((it >> 1) & 1));
+#pragma unroll
+        for (int c = 0; c < S::CHUNKS; ++c) {
+          tma_store_3d(&map_c, c_stage + rb * S::C_BUF + c * S::C_TILE, c * 32, m_blk * RBM, z);
+          tma_store_3d(&map_y, y_stage + rb * S::Y_BUF + c * S::Y_TILE, c * 32, m_blk * RBM, z);
+        }
+        tma_store_commit();
+        tma_store_wait_read0();                              // both buffers of this tile have been read out
+        mbar_arrive(&res_empty[rb]);
+      }
+    }
   } else {
+    constexpr int HALF = BN / 2;                         // columns per thread
+    constexpr int NQ = HALF / 16;                        // 16-column tcgen05.ld chunks per thread
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;                    // which column half of the row this thread owns
     const int row = quarter * 32 + lane;                 // tile row of this thread
     const int sw128 = (row & 7), sw64 = (row >> 1) & 3;
+    const int col0 = half * HALF;
     int acc = 0; uint32_t acc_phase = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int m_blk = t % p.m_tiles, z = t / p.m_tiles;
+      const int z = t / p.m_tiles;
+      const int rb = it & 1;
       const float* bias = p.bias ? p.bias + (long long)z * p.bias_bs : nullptr;
+      uint8_t* cbuf = c_stage + rb * S::C_BUF;
+      uint8_t* ybuf = y_stage + rb * S::Y_BUF;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      mbar_wait(res_full, (uint32_t)(it & 1));
-      float rowbuf[BN];
+      mbar_wait(&res_full[rb], (uint32_t)((it >> 1) & 1));
+      float rowbuf[HALF];
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int c = 0; c < S::CHUNKS; ++c) {
-        float4 bb[8];
+      for (int q = 0; q < NQ; ++q) {
+        const int n0 = col0 + 16 * q;                    // first column of this 16-column piece
+        float4 bb[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          bb[j] = bias ? *reinterpret_cast<const float4*>(bias + c * 32 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 4; ++j)
+          bb[j] = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + n0), r);
         tmem_ld_wait();
-        uint8_t* crow = c_stage + c * S::C_TILE + row * 128;
+        uint8_t* crow = cbuf + (n0 >> 5) * S::C_TILE + row * 128;
+        const int u0 = (n0 & 31) >> 2;                   // first 16-byte unit of the piece inside the 128-byte row
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4* ptr = reinterpret_cast<float4*>(crow + ((j ^ sw128) << 4));
+        for (int j = 0; j < 4; ++j) {
+          float4* ptr = reinterpret_cast<float4*>(crow + (((u0 + j) ^ sw128) << 4));
           float4 v = *ptr;                                   // residual
           v.x += __uint_as_float(r[4 * j]) + bb[j].x; v.y += __uint_as_float(r[4 * j + 1]) + bb[j].y;
           v.z += __uint_as_float(r[4 * j + 2]) + bb[j].z; v.w += __uint_as_float(r[4 * j + 3]) + bb[j].w;
           *ptr = v;                                          // result in place -> TMA store
-          rowbuf[c * 32 + 4 * j] = v.x; rowbuf[c * 32 + 4 * j + 1] = v.y;
-          rowbuf[c * 32 + 4 * j + 2] = v.z; rowbuf[c * 32 + 4 * j + 3] = v.w;
+          rowbuf[16 * q + 4 * j] = v.x; rowbuf[16 * q + 4 * j + 1] = v.y;
+          rowbuf[16 * q + 4 * j + 2] = v.z; rowbuf[16 * q + 4 * j + 3] = v.w;
+          s1 += (v.x + v.y) + (v.z + v.w);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      // second output
+      // second output: LayerNorm over the whole row (two-pass: mean first, then squared deviations; the two column halves
+      // of a row exchange their partial sums through shared memory behind a 64-thread named barrier per lane quarter)
       float mu = 0.f, rstd = 1.f;
       if (p.ln_mode == 1) {
-        float s1 = 0.f;
+        s_stat[(row * 2 + half) * 2] = s1;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+        mu = (s1 + s_stat[(row * 2 + (half ^ 1)) * 2]) * (1.0f / BN);
 #pragma unroll
-        for (int j = 0; j < BN; ++j) s1 += rowbuf[j];
-        mu = s1 * (1.0f / BN);
-        float s2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < BN; ++j) { const float dlt = rowbuf[j] - mu; s2 = fmaf(dlt, dlt, s2); }
-        rstd = rsqrtf(s2 * (1.0f / BN) + 1e-5f);
+        for (int j = 0; j < HALF; ++j) { const float dlt = rowbuf[j] - mu; s2 = fmaf(dlt, dlt, s2); }
+        s_stat[(row * 2 + half) * 2 + 1] = s2;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+        rstd = rsqrtf((s2 + s_stat[(row * 2 + (half ^ 1)) * 2 + 1]) * (1.0f / BN) + 1e-5f);
       }
 #pragma unroll
-      for (int c = 0; c < S::CHUNKS; ++c) {
-        uint8_t* yrow = y_stage + c * S::Y_TILE + row * 64;
+      for (int g8 = 0; g8 < HALF / 8; ++g8) {
+        const int n0 = col0 + 8 * g8;
+        union { uint4 u; YT h[8]; } pk;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          union { uint4 u; YT h[8]; } pk;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int n = c * 32 + 8 * j + e;
-            float y = rowbuf[n];
-            if (p.ln_mode == 1) y = (y - mu) * rstd * __ldg(p.ln_w + n) + __ldg(p.ln_b + n);
-            pk.h[e] = from_f32<YT>(y);
-          }
-          *reinterpret_cast<uint4*>(yrow + ((j ^ sw64) << 4)) = pk.u;
+        for (int e = 0; e < 8; ++e) {
+          float y = rowbuf[8 * g8 + e];
+          if (p.ln_mode == 1) y = (y - mu) * rstd * s_lnw[n0 + e] + s_lnb[n0 + e];
+          pk.h[e] = from_f32<YT>(y);
         }
+        uint8_t* yrow = ybuf + (n0 >> 5) * S::Y_TILE + row * 64;
+        *reinterpret_cast<uint4*>(yrow + ((((n0 & 31) >> 3) ^ sw64) << 4)) = pk.u;
       }
       fence_proxy_async();                                   // smem writes -> visible to the TMA (async proxy)
-      asm volatile("bar.sync 1, 128;" ::: "memory");         // the 4 epilogue warps
-      if (warp == 2 && lane == 0) {
-#pragma unroll
-        for (int c = 0; c < S::CHUNKS; ++c) {
-          tma_store_3d(&map_c, c_stage + c * S::C_TILE, c * 32, m_blk * RBM, z);
-          tma_store_3d(&map_y, y_stage + c * S::Y_TILE, c * 32, m_blk * RBM, z);
-        }
-        tma_store_commit();
-        tma_store_wait_read0();                              // smem may be overwritten by the next residual tile
-        mbar_arrive(res_empty);
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&out_ready[rb]);            // 8 warps -> the store warp issues this tile's TMA stores
     }
   }
 
@@ -301,7 +344,7 @@ static int launch_res_bn(const GemmTcArgs& a, cudaStream_t st) {
 
 bool gemm_res_ln_supported(const GemmTcArgs& a) {
   if (a.ln_mode == 0 || a.out_type != DT_F32 || a.residual == nullptr || a.ln_out == nullptr) return false;
-  if (a.N != 32 && a.N != 64 && a.N != 96 && a.N != 128) return false;
+  if (a.N != 32 && a.N != 64 && a.N != 96) return false;   // N = 128: two 64 KB fp32 tiles do not fit (generic kernel)
   if (a.ln_type != DT_F16 && a.ln_type != DT_BF16) return false;
   if (a.bias_mode > 1 || a.act != 0 || a.colsum || a.scatter) return false;
   if (a.K % 16 || a.lda % 8 || a.ldb % 8 || a.ldc % 4) return false;
@@ -316,7 +359,6 @@ static int launch_res_y(const GemmTcArgs& a, cudaStream_t st) {
     case 32: return launch_res_bn<32, YT>(a, st);
     case 64: return launch_res_bn<64, YT>(a, st);
     case 96: return launch_res_bn<96, YT>(a, st);
-    case 128: return launch_res_bn<128, YT>(a, st);
   }
   return -2;
 }

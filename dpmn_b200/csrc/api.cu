@@ -293,6 +293,23 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
     const bool tc_attn = prec != DPMN_PREC_F32 && attn_tc_supported(ta);
 
     const void* q_in = fuse_ln ? w.lnq[blk] : w.ln;
+    auto scatter_proj = [&](const void* A, const void* Wt, const float* bias, int N, void* dst0, void* dst1) {
+      GemmTcArgs g;   // projection + roll + window_partition: rows land window-major per group
+      g.A = A; g.lda = C; g.Bm = Wt; g.ldb = C; g.op_type = at; g.out_type = at;
+      g.M = rows; g.N = N; g.K = C; g.bias = bias; g.bias_mode = 1;
+      g.scatter = 1; g.scatter_C = C; g.scatter_G = G; g.scatter_H = H; g.scatter_W = W;
+      for (int i = 0; i < G; ++i) { g.scatter_ws[i] = a.window[i]; g.scatter_shift[i] = a.shift[i]; }
+      g.scatter_dst[0] = dst0; g.scatter_dst[1] = dst1;
+      return g;
+    };
+    static const bool dual_on = !(getenv("DPMN_DUAL_QKV") && atoi(getenv("DPMN_DUAL_QKV")) == 0);
+    if (tc_attn && fuse_ln && dual_on) {
+      // both LayerNorm outputs exist already (patch embed / previous residual GEMM): q and kv projections in ONE launch
+      const GemmTcArgs gq = scatter_proj(q_in, op.q_w, bw.q_b, C, w.q, nullptr);
+      const GemmTcArgs gkv = scatter_proj(w.ln, op.kv_w, bw.kv_b, 2 * C, const_cast<void*>(ta.kw), const_cast<void*>(ta.vw));
+      DPMN_RUN(T_GEMM_TC, launch_gemm_tc_dual(gq, gkv, st), 1);
+      DPMN_RUN(T_ATTN_TC, launch_window_attn_tc(ta, st), 1);
+    } else {
     if (!fuse_ln) DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tq, bw.norm1_q_w, bw.norm1_q_b, w.ln, at, rows, C, st), 1);
     if (!tc_attn) {
       GemmCall g;
@@ -300,12 +317,7 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
       g.M = rows; g.N = C; g.K = C; g.bias = bw.q_b; g.bias_mode = 1;
       DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
     } else {
-      GemmTcArgs g;   // projection + roll + window_partition: rows land window-major per group
-      g.A = q_in; g.lda = C; g.Bm = op.q_w; g.ldb = C; g.op_type = at; g.out_type = at;
-      g.M = rows; g.N = C; g.K = C; g.bias = bw.q_b; g.bias_mode = 1;
-      g.scatter = 1; g.scatter_C = C; g.scatter_G = G; g.scatter_H = H; g.scatter_W = W;
-      for (int i = 0; i < G; ++i) { g.scatter_ws[i] = a.window[i]; g.scatter_shift[i] = a.shift[i]; }
-      g.scatter_dst[0] = w.q;
+      const GemmTcArgs g = scatter_proj(q_in, op.q_w, bw.q_b, C, w.q, nullptr);
       DPMN_RUN(T_GEMM_TC, launch_gemm_tc(g, st), 1);
     }
     if (!fuse_ln) DPMN_RUN(T_LAYERNORM, launch_layernorm(w.tkv, bw.norm1_kv_w, bw.norm1_kv_b, w.ln, at, rows, C, st), 1);
@@ -316,14 +328,10 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
       DPMN_RUN(gtag, run_gemm(prec, g, st), 1);
       DPMN_RUN(T_WINDOW_ATTN, launch_window_attn_simt(a, st), G);
     } else {
-      GemmTcArgs g;
-      g.A = w.ln; g.lda = C; g.Bm = op.kv_w; g.ldb = C; g.op_type = at; g.out_type = at;
-      g.M = rows; g.N = 2 * C; g.K = C; g.bias = bw.kv_b; g.bias_mode = 1;
-      g.scatter = 1; g.scatter_C = C; g.scatter_G = G; g.scatter_H = H; g.scatter_W = W;
-      for (int i = 0; i < G; ++i) { g.scatter_ws[i] = a.window[i]; g.scatter_shift[i] = a.shift[i]; }
-      g.scatter_dst[0] = const_cast<void*>(ta.kw); g.scatter_dst[1] = const_cast<void*>(ta.vw);
+      const GemmTcArgs g = scatter_proj(w.ln, op.kv_w, bw.kv_b, 2 * C, const_cast<void*>(ta.kw), const_cast<void*>(ta.vw));
       DPMN_RUN(T_GEMM_TC, launch_gemm_tc(g, st), 1);
       DPMN_RUN(T_ATTN_TC, launch_window_attn_tc(ta, st), 1);
+    }
     }
     if (attn_core && attn_core[blk]) {
       if (prec == DPMN_PREC_F32) {

@@ -11,6 +11,7 @@
 #include "kernels.h"
 #include "tc_common.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace dpmn {
 
@@ -57,7 +58,12 @@ struct TcSmem {
 // MMA, bounds these K = 96..384 GEMMs, so more epilogue warps per SM hide more tcgen05.ld / store latency).
 template <int BN, typename OutT, bool LN, int EW = 4>
 __global__ void __launch_bounds__(64 + 32 * EW, LN ? 1 : 2)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmTcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
+               const __grid_constant__ GemmTcParams p0, const __grid_constant__ GemmTcParams p1, const int tiles0, const int tiles1) {
+  // Two independent problems may share one launch (tiles [0, tiles0) belong to p0 / map_a / map_b, the rest to p1 / map_a2 /
+  // map_b2): the q and kv projections of a block read different inputs but are otherwise the same small GEMM, and one
+  // persistent launch over both fills the machine better than two (pgrm.py:188,194).  tiles1 == 0: a single problem.
   constexpr int CW = EW == 8 ? 16 : 32;         // columns per epilogue chunk (8 warps: fewer live registers per thread)
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
@@ -77,12 +83,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   static_assert(ACC * BN <= 256, "two co-resident CTAs share the 512 TMEM columns");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = (p.K + TBK - 1) / TBK;
-  const int total_tiles = p.batch * p.m_tiles * p.n_tiles;
+  const int total_tiles = tiles0 + tiles1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (tiles1 > 0) { tma_prefetch_desc(&map_a2); tma_prefetch_desc(&map_b2); }
     for (int i = 0; i < TSTAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EW); }
     fence_barrier_init();
@@ -98,16 +104,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int n_blk = t % p.n_tiles;
-        const int m_blk = (t / p.n_tiles) % p.m_tiles;
-        const int z = t / (p.n_tiles * p.m_tiles);
+        const bool second = t >= tiles0;
+        const GemmTcParams& p = second ? p1 : p0;
+        const CUtensorMap* ma = second ? &map_a2 : &map_a;
+        const CUtensorMap* mb = second ? &map_b2 : &map_b;
+        const int tt = second ? t - tiles0 : t;
+        const int n_blk = tt % p.n_tiles;
+        const int m_blk = (tt / p.n_tiles) % p.m_tiles;
+        const int z = tt / (p.n_tiles * p.m_tiles);
+        const int num_kb = (p.K + TBK - 1) / TBK;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-          tma_load_3d(sa, &map_a, &full_bar[stage], kb * TBK, m_blk * TBM, z * p.a_zmul);
-          tma_load_3d(sb, &map_b, &full_bar[stage], kb * TBK, n_blk * BN, z * p.b_zmul);
+          tma_load_3d(sa, ma, &full_bar[stage], kb * TBK, m_blk * TBM, z * p.a_zmul);
+          tma_load_3d(sb, mb, &full_bar[stage], kb * TBK, n_blk * BN, z * p.b_zmul);
           if (++stage == TSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -115,10 +127,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(p.fmt, TBM, BN);
+      const uint32_t idesc = make_idesc_f16(p0.fmt, TBM, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const GemmTcParams& p = t >= tiles0 ? p1 : p0;
+        const int num_kb = (p.K + TBK - 1) / TBK;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -146,9 +160,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int chunk_step = EW == 8 ? 2 * CW : CW;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int n_blk = t % p.n_tiles;
-      const int m_blk = (t / p.n_tiles) % p.m_tiles;
-      const int z = t / (p.n_tiles * p.m_tiles);
+      const bool second = t >= tiles0;
+      const GemmTcParams& p = second ? p1 : p0;
+      const int tt = second ? t - tiles0 : t;
+      const int n_blk = tt % p.n_tiles;
+      const int m_blk = (tt / p.n_tiles) % p.m_tiles;
+      const int z = tt / (p.n_tiles * p.m_tiles);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int m = m_blk * TBM + quarter * 32 + lane;
@@ -373,30 +390,24 @@ int make_tensor_map_16bit(CUtensorMap* map, const void* base, int rank, const ui
 }
 
 
-template <int BN, typename OutT, bool LN, int EW = 4>
-static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st) {
-  if constexpr (!LN && EW == 4 && BN % 32 == 0) {
-    static const int env_ew = getenv("DPMN_TC_EPI_WARPS") ? atoi(getenv("DPMN_TC_EPI_WARPS")) : 8;
-    if (env_ew == 8 && a.colsum == nullptr) return launch_tc_bn<BN, OutT, LN, 8>(a, st);
-  }
-  CUtensorMap map_a, map_b;
+static int tc_build(const GemmTcArgs& a, int BN, CUtensorMap* map_a, CUtensorMap* map_b, GemmTcParams* pp, bool LN) {
   {
     const bool batched = a.batch > 1 && a.a_bs != 0;
     const uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.M, (uint64_t)(batched ? a.batch : 1)};
     const uint64_t str[2] = {(uint64_t)a.lda * 2, (uint64_t)(batched ? a.a_bs : (long long)a.M * a.lda) * 2};
     const uint32_t box[3] = {TBK, TBM, 1};
-    int rc = make_tensor_map_16bit(&map_a, a.A, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = make_tensor_map_16bit(map_a, a.A, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   {
     const bool batched = a.batch > 1 && a.b_bs != 0;
     const uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.N, (uint64_t)(batched ? a.batch : 1)};
     const uint64_t str[2] = {(uint64_t)a.ldb * 2, (uint64_t)(batched ? a.b_bs : (long long)a.N * a.ldb) * 2};
-    const uint32_t box[3] = {TBK, BN, 1};
-    int rc = make_tensor_map_16bit(&map_b, a.Bm, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    const uint32_t box[3] = {TBK, (uint32_t)BN, 1};
+    int rc = make_tensor_map_16bit(map_b, a.Bm, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  GemmTcParams p;
+  GemmTcParams& p = *pp;
   p.M = a.M; p.N = a.N; p.K = a.K; p.batch = a.batch;
   p.m_tiles = (a.M + TBM - 1) / TBM; p.n_tiles = (a.N + BN - 1) / BN;
   p.a_zmul = (a.batch > 1 && a.a_bs != 0) ? 1 : 0; p.b_zmul = (a.batch > 1 && a.b_bs != 0) ? 1 : 0;
@@ -411,9 +422,34 @@ static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st) {
   p.sc_cg = a.scatter_G ? a.scatter_C / a.scatter_G : 0;
   for (int i = 0; i < 4; ++i) { p.sc_ws[i] = a.scatter_ws[i]; p.sc_shift[i] = a.scatter_shift[i]; }
   p.sc_dst[0] = a.scatter_dst[0]; p.sc_dst[1] = a.scatter_dst[1];
+  return 0;
+}
+
+// `b` (optional): a second problem sharing the launch (same operand / output types and N tile; see the kernel).
+template <int BN, typename OutT, bool LN, int EW = 4>
+static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st, const GemmTcArgs* b = nullptr) {
+  if constexpr (!LN && EW == 4 && BN % 32 == 0) {
+    static const int env_ew = getenv("DPMN_TC_EPI_WARPS") ? atoi(getenv("DPMN_TC_EPI_WARPS")) : 8;
+    if (env_ew == 8 && a.colsum == nullptr && (!b || b->colsum == nullptr)) return launch_tc_bn<BN, OutT, LN, 8>(a, st, b);
+  }
+  CUtensorMap map_a, map_b, map_a2, map_b2;
+  GemmTcParams p, p2;
+  memset(&p2, 0, sizeof(p2));
+  int rc = tc_build(a, BN, &map_a, &map_b, &p, LN);
+  if (rc) return rc;
+  int tiles1 = 0;
+  if (b) {
+    rc = tc_build(*b, BN, &map_a2, &map_b2, &p2, LN);
+    if (rc) return rc;
+    if (p2.fmt != p.fmt) return -2;
+    tiles1 = p2.batch * p2.m_tiles * p2.n_tiles;
+  } else {
+    map_a2 = map_a; map_b2 = map_b;
+  }
   int g_num_sms = 0;
   DPMN_CUDA_TRY(current_device_sms(&g_num_sms));
-  const int total = p.batch * p.m_tiles * p.n_tiles;
+  const int tiles0 = p.batch * p.m_tiles * p.n_tiles;
+  const int total = tiles0 + tiles1;
   static const int env_per_sm = getenv("DPMN_TC_PER_SM") ? atoi(getenv("DPMN_TC_PER_SM")) : 2;
   const int per_sm = LN ? 1 : (env_per_sm >= 2 ? 2 : 1);
   const int grid = total < per_sm * g_num_sms ? total : per_sm * g_num_sms;
@@ -421,7 +457,7 @@ static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st) {
   constexpr int smem = TcSmem<BN>::TOTAL;
   static PerDeviceOnce attr;      // per template instantiation, per device
   DPMN_CUDA_TRY(attr.smem_attr(kern, smem));
-  kern<<<grid, 64 + 32 * EW, smem, st>>>(map_a, map_b, p);
+  kern<<<grid, 64 + 32 * EW, smem, st>>>(map_a, map_b, map_a2, map_b2, p, p2, tiles0, tiles1);
   DPMN_LAUNCH_CHECK();
   return 0;
 }
@@ -446,6 +482,23 @@ static int launch_tc_out(const GemmTcArgs& a, cudaStream_t st) {
   if (N % 64 == 0) return launch_tc_bn<64, OutT, false>(a, st);
   if (N % 32 == 0) return launch_tc_bn<32, OutT, false>(a, st);
   return launch_tc_bn<128, OutT, false>(a, st);
+}
+
+// Two scatter-epilogue projections (q and kv of one block) in one launch; both N must be multiples of 96 or of 32.
+int launch_gemm_tc_dual(const GemmTcArgs& a, const GemmTcArgs& b, cudaStream_t st) {
+  for (const GemmTcArgs* g : {&a, &b}) {
+    if (g->op_type != DT_F16 && g->op_type != DT_BF16) return -1;
+    if (g->ln_mode != 0 || g->colsum != nullptr || g->batch != 1 || !g->scatter) return -2;
+    if (g->K % 16 || g->lda % 8 || g->ldb % 8) return -2;
+    if ((reinterpret_cast<uintptr_t>(g->A) | reinterpret_cast<uintptr_t>(g->Bm)) & 15) return -2;
+    if (g->out_type == DT_F32 || g->scatter_G < 1 || (g->scatter_C / g->scatter_G) % 32 || g->N % g->scatter_C ||
+        g->M % (g->scatter_H * g->scatter_W))
+      return -2;
+  }
+  if (a.op_type != b.op_type || a.out_type != b.out_type) return -2;
+  const bool n96 = a.N % 96 == 0 && b.N % 96 == 0;
+  if (a.out_type == DT_F16) return n96 ? launch_tc_bn<96, __half, false>(a, st, &b) : launch_tc_bn<32, __half, false>(a, st, &b);
+  return n96 ? launch_tc_bn<96, __nv_bfloat16, false>(a, st, &b) : launch_tc_bn<32, __nv_bfloat16, false>(a, st, &b);
 }
 
 bool gemm_tc_can_fuse_row_output(int N) { return N == 32 || N == 64 || N == 96 || N == 128; }

@@ -65,6 +65,7 @@ struct GemmTcArgs {
   void* scatter_dst[2] = {};
 };
 int launch_gemm_tc(const GemmTcArgs& a, cudaStream_t st);
+int launch_gemm_tc_dual(const GemmTcArgs& a, const GemmTcArgs& b, cudaStream_t st);   // two window-scatter projections, one launch
 bool gemm_res_ln_supported(const GemmTcArgs& a);
 int launch_gemm_res_ln(const GemmTcArgs& a, cudaStream_t st);   // gemm_res_tc.cu
 bool gemm_tc_can_fuse_row_output(int N);   // ln_mode != 0 is available for these N (fp32 C only)

@@ -497,6 +497,8 @@ CmmWs carve_cmm(const dpmn_cmm_desc* d, void* ws) {
     w.tc.dy16 = b.take<char>(w.tc.dy16_bytes);
     w.tc.part_bytes = (size_t)128 << 20;
     w.tc.part = b.take<float>(w.tc.part_bytes / 4);
+    w.tc.act_bytes = B * H * W * 3 * c * 2;                              // widest conv input: de_1's concat at full resolution
+    w.tc.act = b.take<char>(w.tc.act_bytes);
   }
   w.bytes = b.off + 256;
   return w;

@@ -535,7 +535,10 @@ __global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restric
                                                           const float* __restrict__ fc2_b, float* __restrict__ dz1,
                                                           float* __restrict__ dz2, float* __restrict__ d_fc1_w,
                                                           float* __restrict__ d_fc1_b, float* __restrict__ d_fc2_w,
-                                                          float* __restrict__ d_fc2_b, int Cb, int hw, int hidden) {
+                                                          float* __restrict__ d_fc2_b, int Cb, int hw, int hidden,
+                                                          float* __restrict__ scratch) {
+  // scratch != nullptr: the per-image factors of the two weight gradients (sds, sh, sdh, sg0) are written there and
+  // se_gate_wgrad_kernel sums the outer products over the batch -- instead of 2 * C2 * hidden atomicAdds per image
   extern __shared__ float sm[];
   const int C2 = 2 * Cb;
   float* sg0 = sm;             // [C2] pooled
@@ -577,13 +580,15 @@ __global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restric
       sgate[c] = g;
       const float ds = dg * g * (1.0f - g);
       sds[c] = ds;
-      atomicAdd(d_fc2_b + c, ds);
+      if (scratch == nullptr) atomicAdd(d_fc2_b + c, ds);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C2 * hidden; i += blockDim.x) {
-    const int c = i / hidden, j = i - c * hidden;
-    atomicAdd(d_fc2_w + i, sds[c] * sh[j]);
+  if (scratch == nullptr) {
+    for (int i = threadIdx.x; i < C2 * hidden; i += blockDim.x) {
+      const int c = i / hidden, j = i - c * hidden;
+      atomicAdd(d_fc2_w + i, sds[c] * sh[j]);
+    }
   }
   for (int j = warp; j < hidden; j += nw) {
     float s = 0.f;
@@ -592,13 +597,19 @@ __global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restric
     if (lane == 0) {
       const float d = sh[j] > 0.f ? s : 0.f;
       sdh[j] = d;
-      atomicAdd(d_fc1_b + j, d);
+      if (scratch == nullptr) atomicAdd(d_fc1_b + j, d);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < hidden * C2; i += blockDim.x) {
-    const int j = i / C2, c = i - j * C2;
-    atomicAdd(d_fc1_w + i, sdh[j] * sg0[c]);
+  if (scratch == nullptr) {
+    for (int i = threadIdx.x; i < hidden * C2; i += blockDim.x) {
+      const int j = i / C2, c = i - j * C2;
+      atomicAdd(d_fc1_w + i, sdh[j] * sg0[c]);
+    }
+  } else {
+    float* row = scratch + (long long)b * (2 * C2 + 2 * hidden);      // [sds C2][sg0 C2][sh hidden][sdh hidden]
+    for (int c = threadIdx.x; c < C2; c += blockDim.x) { row[c] = sds[c]; row[C2 + c] = sg0[c]; }
+    for (int j = threadIdx.x; j < hidden; j += blockDim.x) { row[2 * C2 + j] = sh[j]; row[2 * C2 + hidden + j] = sdh[j]; }
   }
   for (int c = warp; c < C2; c += nw) {
     float s = 0.f;
@@ -616,14 +627,49 @@ __global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restric
   }
 }
 
+// d_fc2_w[c][j] += sum_b sds[b][c] sh[b][j];  d_fc1_w[j][c] += sum_b sdh[b][j] sg0[b][c];  biases likewise
+__global__ void __launch_bounds__(256) se_gate_wgrad_kernel(const float* __restrict__ scratch, float* __restrict__ d_fc1_w,
+                                                            float* __restrict__ d_fc1_b, float* __restrict__ d_fc2_w,
+                                                            float* __restrict__ d_fc2_b, int B, int C2, int hidden) {
+  const int stride = 2 * C2 + 2 * hidden;
+  const long long n_w = (long long)C2 * hidden;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * n_w + C2 + hidden;
+       i += (long long)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    if (i < n_w) {                                    // fc2 weight (C2, hidden)
+      const int c = (int)(i / hidden), j = (int)(i - (long long)c * hidden);
+      for (int b = 0; b < B; ++b) a = fmaf(scratch[(long long)b * stride + c], scratch[(long long)b * stride + 2 * C2 + j], a);
+      d_fc2_w[i] += a;
+    } else if (i < 2 * n_w) {                         // fc1 weight (hidden, C2)
+      const long long k = i - n_w;
+      const int j = (int)(k / C2), c = (int)(k - (long long)j * C2);
+      for (int b = 0; b < B; ++b)
+        a = fmaf(scratch[(long long)b * stride + 2 * C2 + hidden + j], scratch[(long long)b * stride + C2 + c], a);
+      d_fc1_w[k] += a;
+    } else if (i < 2 * n_w + C2) {
+      const int c = (int)(i - 2 * n_w);
+      for (int b = 0; b < B; ++b) a += scratch[(long long)b * stride + c];
+      d_fc2_b[c] += a;
+    } else {
+      const int j = (int)(i - 2 * n_w - C2);
+      for (int b = 0; b < B; ++b) a += scratch[(long long)b * stride + 2 * C2 + hidden + j];
+      d_fc1_b[j] += a;
+    }
+  }
+}
+
 int launch_se_gate_bwd(const float* z1, const float* z2, const float* du, const float* fc1_w, const float* fc1_b,
                        const float* fc2_w, const float* fc2_b, float* dz1, float* dz2, float* d_fc1_w, float* d_fc1_b,
-                       float* d_fc2_w, float* d_fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st) {
+                       float* d_fc2_w, float* d_fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st, float* scratch) {
   const size_t smem = (size_t)(6 * Cb + 2 * hidden) * sizeof(float);
   if (smem > 48 * 1024) return -2;
   se_gate_bwd_kernel<<<B, 256, smem, st>>>(z1, z2, du, fc1_w, fc1_b, fc2_w, fc2_b, dz1, dz2, d_fc1_w, d_fc1_b, d_fc2_w,
-                                           d_fc2_b, Cb, hw, hidden);
+                                           d_fc2_b, Cb, hw, hidden, scratch);
   DPMN_LAUNCH_CHECK();
+  if (scratch != nullptr) {
+    se_gate_wgrad_kernel<<<148 * 4, 256, 0, st>>>(scratch, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, B, 2 * Cb, hidden);
+    DPMN_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -12,6 +12,7 @@
 // K = Cin*k*k is padded to Kp (multiple of 16) with zeros on both operands.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace dpmn {
 
@@ -108,17 +109,160 @@ static int launch_im2col(const ConvArgs& a, T* col, int Kp, long long Ntot, cuda
   return 0;
 }
 
-// weights -> 16-bit (Cout, Kp) rows, k = ci*kk + tap, zero padded
+// ---- fast gather path (Cin % 8 == 0): activate once, then copy ------------------------------------------------------------
+// The element-wise gather above pays ~60 instructions per im2col element (index decode, segment lookup, affine, activation)
+// and every input element is gathered k*k times.  Here the conv input -- channel concat, producer BatchNorm affine and
+// consumer activation applied -- is written ONCE as NHWC 16-bit (act_nhwc_kernel, a tiled transpose of the fp32 NCHW
+// tensors), and the im2col matrix, with K ordered (tap, ci), becomes a copy of whole channel vectors: 16-byte loads and
+// stores, one index decode per (pixel, tap).  Weights are staged in the same (tap, ci) order.
+
+// xa[b][y][x][c] (c over the concatenated channels) = act(affine(in)), 16-bit
+template <typename T>
+__global__ void __launch_bounds__(256) act_nhwc_kernel(ConvArgs p, T* __restrict__ xa) {
+  __shared__ float tile[32][33];
+  const long long HW = (long long)p.H * p.W;
+  const int b = blockIdx.z;
+  const long long hw0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i;
+    const long long hw = hw0 + tx;
+    float v = 0.f;
+    if (c < p.Cin && hw < HW) {
+      int seg = 0, cl = c;
+      if (p.n_seg > 1 && cl >= p.seg_ch[0]) {
+        cl -= p.seg_ch[0]; seg = 1;
+        if (p.n_seg > 2 && cl >= p.seg_ch[1]) { cl -= p.seg_ch[1]; seg = 2; }
+      }
+      v = p.in[seg][((long long)b * p.seg_ch[seg] + cl) * HW + hw];
+      if (p.in_scale[seg] != nullptr) v = fmaf(v, p.in_scale[seg][cl], p.in_shift[seg][cl]);
+      if (p.in_act == 1) v = v >= 0.f ? v : 0.2f * v;
+      else if (p.in_act == 2) v = fmaxf(v, 0.f);
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long hw = hw0 + ty + 8 * i;
+    const int c = c0 + tx;
+    if (hw < HW && c < p.Cin) xa[((long long)b * HW + hw) * p.Cin + c] = from_f32<T>(tile[tx][ty + 8 * i]);
+  }
+}
+
+// input pixel of output pixel (oy, ox) under tap (ky, kx); false = structural zero / padding
+__device__ __forceinline__ bool tap_source(const ConvArgs& p, int oy, int ox, int ky, int kx, int& iy, int& ix) {
+  const int sh = p.stride >> 1;
+  if (p.transposed) {
+    const int ty2 = oy + p.pad - ky * p.dil, tx2 = ox + p.pad - kx * p.dil;
+    if (ty2 < 0 || tx2 < 0 || ((ty2 | tx2) & sh) != 0) return false;
+    iy = ty2 >> sh; ix = tx2 >> sh;
+    return iy < p.H && ix < p.W;
+  }
+  iy = (oy << sh) - p.pad + ky * p.dil;
+  ix = (ox << sh) - p.pad + kx * p.dil;
+  return iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+}
+
+// col[n][tap * Cin + ci]: one warp per output pixel at a time, lanes over (tap, 8-channel vector)
+template <typename T, int KS>
+__global__ void __launch_bounds__(256) im2col_nhwc_kernel(ConvArgs p, const T* __restrict__ xa, T* __restrict__ col, int Kp,
+                                                          long long Ntot) {
+  constexpr int kk = KS * KS;
+  const int HoWo = p.Ho * p.Wo;
+  const int vec = p.Cin >> 3;                         // 16-byte vectors per channel row
+  const int items = kk * vec;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * 8;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  for (long long n = warp0; n < Ntot; n += nwarps) {
+    const int b = (int)(n / HoWo);
+    const int r = (int)(n - (long long)b * HoWo);
+    const int oy = r / p.Wo, ox = r - oy * p.Wo;
+    uint4* dst = reinterpret_cast<uint4*>(col + n * Kp);
+    for (int it = lane; it < items; it += 32) {
+      const int tap = it / vec, v = it - tap * vec;
+      const int ky = tap / KS, kx = tap - ky * KS;
+      int iy, ix;
+      uint4 val = zero;
+      if (tap_source(p, oy, ox, ky, kx, iy, ix))
+        val = __ldg(reinterpret_cast<const uint4*>(xa + (((long long)b * p.H + iy) * p.W + ix) * p.Cin) + v);
+      dst[it] = val;
+    }
+    // K is padded to a multiple of 16 elements = 2 vectors (only when kk * Cin is an odd multiple of 8)
+    if (lane == 0 && items * 8 < Kp) dst[items] = zero;
+  }
+}
+
+// colT[tap * Cin + ci][n] (row length Npad): 64 pixels x 64 channels per CTA per tap through a shared-memory transpose
+template <typename T, int KS>
+__global__ void __launch_bounds__(256) im2colT_nhwc_kernel(ConvArgs p, const T* __restrict__ xa, T* __restrict__ colT,
+                                                           long long Npad, long long Ntot) {
+  __shared__ uint32_t tile[64][33];                   // [pixel][channel pair]
+  const int HoWo = p.Ho * p.Wo;
+  const long long n0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const int tap = blockIdx.z;
+  const int ky = tap / KS, kx = tap - ky * KS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // phase 1: warp w reads pixels n0 + w, w + 8, ...: 64 channels = 32 words per pixel (one 128-byte line)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int pl = warp + 8 * i;
+    const long long n = n0 + pl;
+    uint32_t v = 0u;
+    if (n < Ntot && c0 + 2 * lane < p.Cin) {
+      const int b = (int)(n / HoWo);
+      const int r = (int)(n - (long long)b * HoWo);
+      const int oy = r / p.Wo, ox = r - oy * p.Wo;
+      int iy, ix;
+      if (tap_source(p, oy, ox, ky, kx, iy, ix))
+        v = __ldg(reinterpret_cast<const uint32_t*>(xa + (((long long)b * p.H + iy) * p.W + ix) * p.Cin + c0) + lane);
+    }
+    tile[pl][lane] = v;
+  }
+  __syncthreads();
+  // phase 2: warp w writes channels c0 + 8 w .. + 7; lane = pixel pair -> 4-byte stores, 128 contiguous bytes per row
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int cl = 8 * warp + j;                      // channel within the tile
+    if (c0 + cl >= p.Cin) break;
+    const uint32_t a = tile[2 * lane][cl >> 1], bq = tile[2 * lane + 1][cl >> 1];
+    const uint32_t lo = (cl & 1) ? (a >> 16) : (a & 0xffffu);
+    const uint32_t hi = (cl & 1) ? (bq >> 16) : (bq & 0xffffu);
+    const long long n = n0 + 2 * lane;
+    if (n < Npad) *reinterpret_cast<uint32_t*>(colT + ((long long)tap * p.Cin + c0 + cl) * Npad + n) = lo | (hi << 16);
+  }
+}
+
+static bool nhwc_path_ok(const ConvArgs& a, const ConvTcScratch& s) {
+  static const bool on = !(getenv("DPMN_IM2COL_NHWC") && atoi(getenv("DPMN_IM2COL_NHWC")) == 0);
+  return on && a.Cin % 8 == 0 && s.act != nullptr && (size_t)a.B * a.H * a.W * a.Cin * 2 <= s.act_bytes;
+}
+
+template <typename T>
+static int launch_act_nhwc(const ConvArgs& a, T* xa, cudaStream_t st) {
+  const long long HW = (long long)a.H * a.W;
+  const dim3 grid((unsigned)((HW + 31) / 32), (a.Cin + 31) / 32, a.B);
+  act_nhwc_kernel<T><<<grid, 256, 0, st>>>(a, xa);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// weights -> 16-bit (Cout, Kp) rows, k = ci*kk + tap (tap_major == 0) or tap*Cin + ci (tap_major == 1), zero padded
 template <typename T>
 __global__ void stage_conv_weight_kernel(const float* __restrict__ w, T* __restrict__ dst, int Cout, int Cin, int kk,
-                                         int transposed, int Kp) {
+                                         int transposed, int Kp, int tap_major) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Cout * Kp) return;
   const int co = (int)(i / Kp), k = (int)(i - (long long)co * Kp);
   float v = 0.f;
   if (k < Cin * kk) {
-    const int ci = k / kk, tap = k - ci * kk;
-    v = transposed ? w[((long long)ci * Cout + co) * kk + tap] : w[(long long)co * Cin * kk + k];
+    const int ci = tap_major ? k % Cin : k / kk, tap = tap_major ? k / Cin : k - (k / kk) * kk;
+    v = transposed ? w[((long long)ci * Cout + co) * kk + tap] : w[((long long)co * Cin + ci) * kk + tap];
   }
   dst[i] = from_f32<T>(v);
 }
@@ -137,15 +281,15 @@ __global__ void nchw_to_cn_kernel(const float* __restrict__ src, T* __restrict__
 
 // dw (reference layout) += sum_s partial[s][co][k]
 __global__ void reduce_conv_partials_kernel(const float* __restrict__ partial, float* __restrict__ dw, int S, int Cout,
-                                            int Cin, int kk, int transposed, int Kp) {
+                                            int Cin, int kk, int transposed, int Kp, int tap_major) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int K = Cin * kk;
   if (i >= (long long)Cout * K) return;
   const int co = (int)(i / K), k = (int)(i - (long long)co * K);
   float a = 0.f;
   for (int s = 0; s < S; ++s) a += partial[((long long)s * Cout + co) * Kp + k];
-  const int ci = k / kk, tap = k - ci * kk;
-  const long long o = transposed ? ((long long)ci * Cout + co) * kk + tap : (long long)co * K + k;
+  const int ci = tap_major ? k % Cin : k / kk, tap = tap_major ? k / Cin : k - (k / kk) * kk;
+  const long long o = transposed ? ((long long)ci * Cout + co) * kk + tap : ((long long)co * Cin + ci) * kk + tap;
   dw[o] += a;
 }
 
@@ -155,10 +299,18 @@ static int conv_tc_im2col_t(const ConvArgs& a, const ConvTcScratch& s, cudaStrea
   const int HoWo = a.Ho * a.Wo;
   const long long Ntot = (long long)a.B * HoWo;
   if ((size_t)Ntot * Kp * 2 > s.col_bytes || (size_t)a.Cout * Kp * 2 > s.w16_bytes) return -3;
+  const bool fast = nhwc_path_ok(a, s);
   stage_conv_weight_kernel<T><<<(unsigned)(((long long)a.Cout * Kp + 255) / 256), 256, 0, st>>>(a.w, (T*)s.w16, a.Cout, a.Cin, kk,
-                                                                                            a.transposed, Kp);
+                                                                                            a.transposed, Kp, fast ? 1 : 0);
   DPMN_LAUNCH_CHECK();
-  {
+  if (fast) {
+    int rc = launch_act_nhwc<T>(a, (T*)s.act, st);
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)((Ntot + 7) / 8 < 148 * 16 ? (Ntot + 7) / 8 : 148 * 16);
+    if (a.k == 3) im2col_nhwc_kernel<T, 3><<<blocks, 256, 0, st>>>(a, (const T*)s.act, (T*)s.col, Kp, Ntot);
+    else im2col_nhwc_kernel<T, 4><<<blocks, 256, 0, st>>>(a, (const T*)s.act, (T*)s.col, Kp, Ntot);
+    DPMN_LAUNCH_CHECK();
+  } else {
     const int rc = launch_im2col<T, false>(a, (T*)s.col, Kp, Ntot, st);
     if (rc) return rc;
   }
@@ -212,7 +364,16 @@ static int conv_wgrad_tc_im2col_t(const ConvArgs& a, const float* dy, float* dw,
   const long long total = (long long)a.B * a.Cout * HoWo;
   nchw_to_cn_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dy, (T*)s.dy16, a.B, a.Cout, HoWo, Ntot);
   DPMN_LAUNCH_CHECK();
-  {
+  const bool fast = nhwc_path_ok(a, s) && Ntot % 2 == 0;
+  if (fast) {
+    int rc = launch_act_nhwc<T>(a, (T*)s.act, st);
+    if (rc) return rc;
+    if (Kp > K) DPMN_CUDA_TRY(cudaMemsetAsync((T*)s.col + (long long)K * Ntot, 0, (size_t)(Kp - K) * Ntot * 2, st));
+    const dim3 grid((unsigned)((Ntot + 63) / 64), (a.Cin + 63) / 64, kk);
+    if (a.k == 3) im2colT_nhwc_kernel<T, 3><<<grid, 256, 0, st>>>(a, (const T*)s.act, (T*)s.col, Ntot, Ntot);
+    else im2colT_nhwc_kernel<T, 4><<<grid, 256, 0, st>>>(a, (const T*)s.act, (T*)s.col, Ntot, Ntot);
+    DPMN_LAUNCH_CHECK();
+  } else {
     const int rc = launch_im2col<T, true>(a, (T*)s.col, Kp, Ntot, st);
     if (rc) return rc;
   }
@@ -223,7 +384,7 @@ static int conv_wgrad_tc_im2col_t(const ConvArgs& a, const float* dy, float* dw,
   int rc = launch_gemm_tc(g, st);
   if (rc) return rc;
   reduce_conv_partials_kernel<<<(unsigned)(((long long)a.Cout * K + 255) / 256), 256, 0, st>>>(s.part, dw, S, a.Cout, a.Cin, kk,
-                                                                                          a.transposed, Kp);
+                                                                                          a.transposed, Kp, fast ? 1 : 0);
   DPMN_LAUNCH_CHECK();
   return 0;
 }

@@ -301,6 +301,7 @@ struct ConvTcScratch {
   void* w16 = nullptr; size_t w16_bytes = 0;      // staged (Cout, Kp) weights
   void* dy16 = nullptr; size_t dy16_bytes = 0;    // (Cout, Ntot) output gradient
   float* part = nullptr; size_t part_bytes = 0;   // split-K partials of the weight gradient
+  void* act = nullptr; size_t act_bytes = 0;      // activated input as NHWC 16-bit (fast gather path, Cin % 8 == 0)
 };
 bool conv_tc_im2col_ok(const ConvArgs& a);
 int launch_conv_tc_im2col(const ConvArgs& a, const ConvTcScratch& s, cudaStream_t st);               // same contract as launch_conv_simt
@@ -327,7 +328,8 @@ int launch_bn_act_bwd(const BnBwdArgs& a, cudaStream_t st);
 int launch_chan_sum(const float* x, int B, int C, int HW, float* out, cudaStream_t st);
 int launch_se_gate_bwd(const float* z1, const float* z2, const float* du, const float* fc1_w, const float* fc1_b,
                        const float* fc2_w, const float* fc2_b, float* dz1, float* dz2, float* d_fc1_w, float* d_fc1_b,
-                       float* d_fc2_w, float* d_fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st);
+                       float* d_fc2_w, float* d_fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st,
+                       float* scratch = nullptr);   // scratch: B * (4 Cb + 2 hidden) floats -> no atomics on the weight gradients
 
 // ---- CMM tensor-core kernels (conv_tc.cu, cmm_tc.cu) ----------------------------------------------------
 

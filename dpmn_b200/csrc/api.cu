@@ -905,6 +905,16 @@ int dpmn_window_attn_forward_windowed(const void* qw, const void* kw, const void
                                       int32_t grid_w, int32_t embed_dim, int32_t num_heads, int32_t n_groups,
                                       const int32_t window[DPMN_MAX_GROUPS], const int32_t shift[DPMN_MAX_GROUPS],
                                       int32_t precision, void* stream) {
+  return dpmn_window_attn_forward_windowed_train(qw, kw, vw, out, rpb_table, batch, grid_h, grid_w, embed_dim, num_heads, n_groups,
+                                                 window, shift, precision, 0.f, 0, 0, stream);
+}
+
+int dpmn_window_attn_forward_windowed_train(const void* qw, const void* kw, const void* vw, void* out,
+                                            const float* const rpb_table[DPMN_MAX_GROUPS], int32_t batch, int32_t grid_h,
+                                            int32_t grid_w, int32_t embed_dim, int32_t num_heads, int32_t n_groups,
+                                            const int32_t window[DPMN_MAX_GROUPS], const int32_t shift[DPMN_MAX_GROUPS],
+                                            int32_t precision, float attn_drop, uint64_t seed, uint32_t site, void* stream) {
+  if (!(attn_drop >= 0.f && attn_drop < 1.f)) return DPMN_E_ARG;
   if (!qw || !kw || !vw || !out || !rpb_table || !window || !shift) return DPMN_E_ARG;
   if (n_groups < 1 || n_groups > DPMN_MAX_GROUPS || batch < 1) return DPMN_E_ARG;
   if (embed_dim % n_groups || num_heads % n_groups) return DPMN_E_ARG;
@@ -917,6 +927,7 @@ int dpmn_window_attn_forward_windowed(const void* qw, const void* kw, const void
     if (shift[g] < 0 || shift[g] >= window[g]) return DPMN_E_ARG;
     a.table[g] = rpb_table[g]; a.window[g] = window[g]; a.shift[g] = shift[g];
   }
+  a.p_drop = attn_drop; a.seed = seed; a.site = site;
   if (!attn_tc_supported(a)) return DPMN_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   DPMN_RUN(T_ATTN_TC, launch_window_attn_tc(a, st), 1);

@@ -1,0 +1,516 @@
+// Fused window attention on tcgen05, second generation (sm_100a)                       pgrm.py:197-268
+//
+// Same contract as attn_tc.cu (window-major 16-bit Qw / Kw / Vw per window group in, window-major rows out -- quirk 1:
+// the reference never applies window_reverse, pgrm.py:249,263), restructured around what the first kernel's ncu
+// capture showed (profiles/r02_ncu_attn_v1_sass.txt): 10 M warp instructions per launch (index arithmetic of the
+// relative-position lookup, block selection, the zero pattern of a 128 x 128 P tile) on 8 softmax warps per SM, one
+// 222 KB CTA per SM, 19 % of HBM.
+//
+//   * M = 64 MMAs.  A unit is still 128 consecutive window-major rows of one group and HC heads, but it is computed
+//     as two 64-row halves: S_half = Q_half K_half^T is a 64 x 64 tile, and the two halves interleave in TMEM (half 0
+//     in lanes 0-15 of every 32-lane quarter, half 1 in lanes 16-31: the M = 64 accumulator layout), so that ONE
+//     32x32b tcgen05.ld still gives every thread one full row.  Windows never straddle a 64-row half (N <= 64), the
+//     score tile has no dead half, the P operand is 64 x 64 (8 KB, was 32 KB) and S needs 64 TMEM columns per head.
+//   * 88-112 KB of shared memory and 256 TMEM columns per CTA -> TWO CTAs per SM (16 softmax warps), each a
+//     TMA warp + MMA warp + 4*HC softmax / epilogue warps over a 3-stage Q/K/V ring.
+//   * Lean softmax: the bias address is `row base - compile-time key offset` into the (2ws-1)^2 table (lanes l and
+//     l + 16 hold the same in-window position -> broadcast, 16 distinct banks otherwise); the shift mask is a 64-bit
+//     key bitmask built once per unit from "is this the last window row / column" (pgrm.py:157-173 in closed form);
+//     log2-domain scores, bare ex2.approx, 3-input max tree, P unnormalised (1/den applied to the D outputs).
+//   * attn_drop (pgrm.py:248, train mode) as a template flag: the kept probabilities are zeroed in P with the
+//     library's counter hash (same element index as the SIMT kernel), 1/(1-p) folded into the row scale.
+//
+// Warp roles per CTA: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2.. : head h = (warp-2)/4,
+// TMEM lane quarter = warp % 4; lane l is row 64*(l/16) + 16*quarter + l%16 of the unit.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+#include <cstring>
+
+namespace dpmn {
+
+using namespace tc;
+
+namespace {
+
+constexpr int A2_ROWS = 128;
+constexpr int A2_TAB_STRIDE = 232;          // >= (2*8-1)^2
+constexpr int A2_TAB_FLOATS = 6 * A2_TAB_STRIDE;
+
+struct Attn2Params {
+  int H, W, L, C, G, hpg, cg;
+  int ws[4], shift[4];
+  int tiles, nhc, total_units;
+  const float* table[4];
+  void* out;
+  int fmt;
+  float scale;                // head_dim^-0.5 * log2(e)
+  float p_drop, keep_inv;
+  unsigned long long seed;
+  uint32_t site;
+};
+
+template <int D>
+__device__ __forceinline__ uint64_t a2_desc_rowD(uint32_t smem_addr) {
+  constexpr uint64_t layout = D == 16 ? 6 : 4;           // SWIZZLE_32B : SWIZZLE_64B
+  constexpr uint64_t sbo = D == 16 ? 256 : 512;          // 8 rows
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
+template <int D, int HC, int STAGES>
+struct A2Smem {
+  static constexpr int TILE = A2_ROWS * D * 2;                  // one Q / K / V head tile
+  static constexpr int STAGE = HC * 3 * TILE;
+  static constexpr int P_HALF = 64 * 128;                       // 64 rows x 64 keys, 16-bit
+  static constexpr int P_BYTES = HC * 2 * P_HALF;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE + P_BYTES + BAR_BYTES + A2_TAB_FLOATS * 4 + 1024;
+};
+
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// Softmax of this thread's row of one head + the write of its P row.  s_addr: TMEM address of the head's S tile at this
+// warp's lane quarter.  row_half = 16*quarter + lane%16 (row within the 64-row half), p_half: the half's P tile.
+// Returns 1 / (softmax denominator [* keep probability]).
+template <int WS, typename T, bool DROP>
+__device__ __forceinline__ float a2_softmax_row(uint32_t s_addr, int quarter, int lane, const float* tab, float scale,
+                                                unsigned long long km, uint8_t* p_half, uint64_t* s_empty_bar,
+                                                uint64_t* p_empty_bar, uint32_t p_empty_parity, bool full_row,
+                                                const Attn2Params& p, unsigned long long drop_base) {
+  constexpr int N = WS * WS;
+  constexpr int TW = 2 * WS - 1;
+  const int r16 = lane & 15;
+  const int row_half = quarter * 16 + r16;
+  float s[N];
+  if constexpr (WS == 8) {
+    uint32_t lo[32], hi[32];
+    tmem_ld_32x32(s_addr, lo);
+    tmem_ld_32x32(s_addr + 32u, hi);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { s[j] = __uint_as_float(lo[j]); s[32 + j] = __uint_as_float(hi[j]); }
+  } else if constexpr (WS == 4) {
+    uint32_t r[32];
+    tmem_ld_32x16(s_addr + (uint32_t)(quarter * 16), r);     // the 16 rows of a quarter are one window: columns [16q, 16q+16)
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s[j] = __uint_as_float(r[j]);
+  } else {
+    uint32_t r[32];
+    tmem_ld_32x16(s_addr + (uint32_t)(quarter * 16), r);     // four 4-row windows per quarter: own block at column 16q + 4*(r16/4)
+    tmem_ld_wait();
+    const int sel = r16 >> 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t v = r[j];
+      v = sel == 1 ? r[4 + j] : v;
+      v = sel == 2 ? r[8 + j] : v;
+      v = sel == 3 ? r[12 + j] : v;
+      s[j] = __uint_as_float(v);
+    }
+  }
+  // the scores are in registers: hand the S accumulator back so the next unit's QK^T overlaps this softmax
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(s_empty_bar);
+
+  const int n = WS == 8 ? row_half : (WS == 4 ? r16 : (r16 & 3));
+  const int i_n = n / WS, j_n = n % WS;
+  const float* tb = tab + (i_n + WS - 1) * TW + (j_n + WS - 1);
+  // log2 domain: `scale` and the table carry log2(e), so each key costs LDS, FFMA, max, FADD, EX2, FADD
+#pragma unroll
+  for (int m = 0; m < N; ++m) s[m] = fmaf(s[m], scale, tb[-((m / WS) * TW + (m % WS))]);
+  if (__any_sync(0xffffffffu, km != 0ull)) {
+    const uint32_t km_lo = (uint32_t)km, km_hi = (uint32_t)(km >> 32);
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      const bool hit = m < 32 ? ((km_lo >> m) & 1u) : ((km_hi >> (m - 32)) & 1u);
+      if (hit) s[m] += -144.26950408889634f;                  // -100 (pgrm.py:173) * log2(e)
+    }
+  }
+  float mx;
+  if constexpr (N >= 16) {
+    float t[N / 4];
+#pragma unroll
+    for (int j = 0; j < N / 4; ++j) t[j] = fmaxf(fmaxf(s[4 * j], s[4 * j + 1]), fmaxf(s[4 * j + 2], s[4 * j + 3]));
+#pragma unroll
+    for (int w = N / 8; w >= 1; w >>= 1) {
+#pragma unroll
+      for (int j = 0; j < w; ++j) t[j] = fmaxf(t[j], t[j + w]);
+    }
+    mx = t[0];
+  } else {
+    mx = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+  }
+  const int swz = row_half & 7;
+  uint8_t* row_base = p_half + (row_half >> 3) * 1024 + swz * 128;
+  mbar_wait(p_empty_bar, p_empty_parity);          // the P*V that last read this P buffer has retired
+  float den = 0.f;
+  if constexpr (WS == 8) {
+    float dpart[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float e[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        e[k] = ex2_fast(s[8 * c + k] - mx);
+        dpart[k & 3] += e[k];
+        if constexpr (DROP) {
+          const float u = (float)(dpmn_hash32(p.seed, p.site, drop_base + (unsigned long long)(8 * c + k)) >> 8) * (1.0f / 16777216.0f);
+          e[k] = u >= p.p_drop ? e[k] : 0.f;
+        }
+      }
+      uint4 v;
+      v.x = pack2<T>(e[0], e[1]); v.y = pack2<T>(e[2], e[3]); v.z = pack2<T>(e[4], e[5]); v.w = pack2<T>(e[6], e[7]);
+      *reinterpret_cast<uint4*>(row_base + ((c ^ swz) << 4)) = v;
+    }
+    den = (dpart[0] + dpart[1]) + (dpart[2] + dpart[3]);
+  } else {
+    float e[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m) {
+      e[m] = ex2_fast(s[m] - mx);
+      den += e[m];
+      if constexpr (DROP) {
+        const float u = (float)(dpmn_hash32(p.seed, p.site, drop_base + (unsigned long long)m) >> 8) * (1.0f / 16777216.0f);
+        e[m] = u >= p.p_drop ? e[m] : 0.f;
+      }
+    }
+    // the row's window block: keys [key0, key0 + N) of the half, everything else of the 64-key row is zero
+    uint4 own[2];
+    int c_own0;
+    if constexpr (WS == 4) {
+      own[0].x = pack2<T>(e[0], e[1]); own[0].y = pack2<T>(e[2], e[3]); own[0].z = pack2<T>(e[4], e[5]); own[0].w = pack2<T>(e[6], e[7]);
+      own[1].x = pack2<T>(e[8], e[9]); own[1].y = pack2<T>(e[10], e[11]); own[1].z = pack2<T>(e[12], e[13]); own[1].w = pack2<T>(e[14], e[15]);
+      c_own0 = 2 * quarter;
+    } else {
+      const uint32_t a = pack2<T>(e[0], e[1]), b = pack2<T>(e[2], e[3]);
+      const bool upper = (r16 >> 2) & 1;              // key0 = 16q + 4*(r16/4): lower or upper half of its 8-key chunk
+      own[0] = upper ? make_uint4(0u, 0u, a, b) : make_uint4(a, b, 0u, 0u);
+      own[1] = make_uint4(0u, 0u, 0u, 0u);
+      c_own0 = 2 * quarter + (r16 >> 3);
+    }
+    constexpr int OWN = WS == 4 ? 2 : 1;
+    if (full_row) {
+      // first unit with this window size in the buffer: the zeros outside the row's own block are (re)written
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int q = 0; q < OWN; ++q)
+          if (c == c_own0 + q) v = own[q];
+        *reinterpret_cast<uint4*>(row_base + ((c ^ swz) << 4)) = v;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < OWN; ++q) *reinterpret_cast<uint4*>(row_base + (((c_own0 + q) ^ swz) << 4)) = own[q];
+    }
+  }
+  return DROP ? p.keep_inv / den : 1.0f / den;
+}
+
+template <int D, int HC, int STAGES, typename T, bool DROP>
+__global__ void __launch_bounds__(64 + HC * 128, 2)
+attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ Attn2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment (128B swizzle atoms) by an offset into the __shared__ array: the pointers keep their address space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  using S = A2Smem<D, HC, STAGES>;
+  constexpr int THREADS = 64 + HC * 128;
+  uint8_t* stages = smem;
+  uint8_t* p_tiles = smem + STAGES * S::STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_tiles + S::P_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;             // [STAGES]
+  uint64_t* s_full = bars + 2 * STAGES;
+  uint64_t* s_empty = s_full + 1;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* p_empty = s_full + 3;
+  uint64_t* o_full = s_full + 4;
+  uint64_t* o_empty = s_full + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
+  float* s_tab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + S::BAR_BYTES);   // [G][hpg][TAB_STRIDE]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = HC == 2 ? 256 : 128;
+  constexpr uint32_t O_COL0 = HC * 64;
+
+  for (int i = threadIdx.x; i < p.G * p.hpg * A2_TAB_STRIDE; i += THREADS) {
+    const int e = i % A2_TAB_STRIDE, gh = i / A2_TAB_STRIDE;
+    const int g = gh / p.hpg, h = gh - g * p.hpg;
+    const int tw = 2 * p.ws[g] - 1;
+    s_tab[i] = e < tw * tw ? p.table[g][e * p.hpg + h] * 1.4426950408889634f : 0.f;   // log2 domain
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 4 * HC);
+    mbar_init(p_full, 4 * HC); mbar_init(p_empty, 1);
+    mbar_init(o_full, 1); mbar_init(o_empty, 4 * HC);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // units are ordered group-major, so a CTA's consecutive units mostly share the window size (the P zero pattern)
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+        const int hc = u % p.nhc, tile = (u / p.nhc) % p.tiles, g = u / (p.nhc * p.tiles);
+        const int stage = it % STAGES;
+        mbar_wait(&empty_bar[stage], (uint32_t)(((it / STAGES) & 1) ^ 1));
+        uint8_t* st = stages + stage * S::STAGE;
+        mbar_arrive_expect_tx(&full_bar[stage], S::STAGE);
+#pragma unroll
+        for (int h = 0; h < HC; ++h) {
+          const int ch = (hc * HC + h) * D;
+          tma_load_3d(st + (h * 3 + 0) * S::TILE, &map_q, &full_bar[stage], ch, tile * A2_ROWS, g);
+          tma_load_3d(st + (h * 3 + 1) * S::TILE, &map_k, &full_bar[stage], ch, tile * A2_ROWS, g);
+          tma_load_3d(st + (h * 3 + 2) * S::TILE, &map_v, &full_bar[stage], ch, tile * A2_ROWS, g);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(p.fmt, 64, 64);
+      const uint32_t idesc_o = make_idesc_f16(p.fmt, 64, D) | (1u << 16);   // B operand (V) is MN-major
+      auto issue_pv = [&](int j) {
+        const int stage = j % STAGES;
+        mbar_wait(p_full, (uint32_t)(j & 1));
+        mbar_wait(o_empty, (uint32_t)((j & 1) ^ 1));
+        tc_fence_after();
+        const uint8_t* st = stages + stage * S::STAGE;
+#pragma unroll
+        for (int h = 0; h < HC; ++h) {
+          const uint32_t va = smem_u32(st + (h * 3 + 2) * S::TILE);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t d_o = tmem_base + O_COL0 + (uint32_t)(h * D) + ((uint32_t)(16 * t) << 16);
+            const uint64_t da0 = make_smem_desc_sw128(smem_u32(p_tiles + (h * 2 + t) * S::P_HALF));
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)       // 4 k-steps of 16 keys
+              umma_f16(d_o, advance_desc_k(da0, ks), a2_desc_rowD<D>(va + (uint32_t)((t * 64 + ks * 16) * D * 2)), idesc_o,
+                       ks ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(p_empty);
+        umma_commit(o_full);
+      };
+      int it = 0;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+        const int stage = it % STAGES;
+        mbar_wait(&full_bar[stage], (uint32_t)((it / STAGES) & 1));
+        mbar_wait(s_empty, (uint32_t)((it & 1) ^ 1));
+        tc_fence_after();
+        const uint8_t* st = stages + stage * S::STAGE;
+#pragma unroll
+        for (int h = 0; h < HC; ++h) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const uint64_t dq = a2_desc_rowD<D>(smem_u32(st + (h * 3 + 0) * S::TILE) + (uint32_t)(t * 64 * D * 2));
+            const uint64_t dk = a2_desc_rowD<D>(smem_u32(st + (h * 3 + 1) * S::TILE) + (uint32_t)(t * 64 * D * 2));
+            const uint32_t d_s = tmem_base + (uint32_t)(h * 64) + ((uint32_t)(16 * t) << 16);
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k)
+              umma_f16(d_s, advance_desc_k(dq, k), advance_desc_k(dk, k), idesc_s, k ? 1u : 0u);
+          }
+        }
+        umma_commit(s_full);
+        if (it > 0) issue_pv(it - 1);
+      }
+      if (it > 0) issue_pv(it - 1);
+    }
+  } else {
+    const int quarter = warp & 3;                       // TMEM lane quarter
+    const int h = (warp - 2) >> 2;                      // this warp set's head within the unit
+    const int half = lane >> 4, r16 = lane & 15;
+    const int row = half * 64 + quarter * 16 + r16;     // row within the unit
+    T* out = reinterpret_cast<T*>(p.out);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    auto epilogue = [&](int j, int u_prev, float inv_row) {
+      const int hc = u_prev % p.nhc, tile = (u_prev / p.nhc) % p.tiles, g = u_prev / (p.nhc * p.tiles);
+      mbar_wait(o_full, (uint32_t)(j & 1));
+      tc_fence_after();
+      uint32_t o[32];
+      const uint32_t col = O_COL0 + (uint32_t)(h * D);
+      if constexpr (D == 16) tmem_ld_32x16(lane_addr + col, o);
+      else tmem_ld_32x32(lane_addr + col, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      T* dst = out + ((long long)tile * A2_ROWS + row) * p.C + g * p.cg + (hc * HC + h) * D;
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        uint4 v;
+        v.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_row, __uint_as_float(o[c + 1]) * inv_row);
+        v.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_row, __uint_as_float(o[c + 3]) * inv_row);
+        v.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_row, __uint_as_float(o[c + 5]) * inv_row);
+        v.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_row, __uint_as_float(o[c + 7]) * inv_row);
+        *reinterpret_cast<uint4*>(dst + c) = v;
+      }
+    };
+    int it = 0, u_prev = -1;
+    int last_ws = -1;                                   // window size whose zero pattern the P buffer currently holds
+    float inv_prev = 1.f, inv_cur = 1.f;                // 1 / softmax denominator of this thread's row
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+      const int hc = u % p.nhc, tile = (u / p.nhc) % p.tiles, g = u / (p.nhc * p.tiles);
+      const int ws = p.ws[g], N = ws * ws, shift = p.shift[g];
+      const int grow = tile * A2_ROWS + row;            // window-major row in [0, B*L)
+      const int b_img = grow / p.L;
+      const int p_img = grow - b_img * p.L;
+      const int w_idx = p_img / N, n = p_img - w_idx * N;
+      // shift mask (pgrm.py:157-173) in closed form: rolled rows / columns carry region label 0 except in the LAST window
+      // row / column, where positions >= ws - shift carry 2 and the others 1; keys whose label differs get -100.
+      unsigned long long km = 0ull;
+      if (shift > 0) {
+        const int nWw = p.W / ws, nWin = p.L / N;
+        const int i_n = n / ws, j_n = n - i_n * ws;
+        const int cut = ws - shift;
+        if (w_idx >= nWin - nWw) {                      // last window row
+          const unsigned long long lowrows = (1ull << (cut * ws)) - 1ull;
+          const unsigned long long all = N == 64 ? ~0ull : ((1ull << N) - 1ull);
+          km |= i_n >= cut ? lowrows : (all & ~lowrows);
+        }
+        if (w_idx % nWw == nWw - 1) {                   // last window column
+          const unsigned long long rep = ws == 8 ? 0x0101010101010101ull : (ws == 4 ? 0x1111ull : 0x5ull);
+          const unsigned long long lowcols = (1ull << cut) - 1ull;
+          const unsigned long long allc = (1ull << ws) - 1ull;
+          km |= (j_n >= cut ? lowcols : (allc & ~lowcols)) * rep;
+        }
+      }
+      const int head = hc * HC + h;
+      const unsigned long long drop_base =
+          DROP ? ((((unsigned long long)b_img * p.G + g) * p.hpg + head) * p.L + p_img) * (unsigned long long)N : 0ull;
+      mbar_wait(s_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      {
+        const float* tab = s_tab + (g * p.hpg + head) * A2_TAB_STRIDE;
+        const uint32_t s_addr = lane_addr + (uint32_t)(h * 64);
+        uint8_t* ph = p_tiles + (h * 2 + half) * S::P_HALF;
+        const uint32_t pe_par = (uint32_t)((it & 1) ^ 1);
+        const bool full_row = last_ws != ws;
+        last_ws = ws;
+        if (ws == 8) inv_cur = a2_softmax_row<8, T, DROP>(s_addr, quarter, lane, tab, p.scale, km, ph, s_empty, p_empty, pe_par, full_row, p, drop_base);
+        else if (ws == 4) inv_cur = a2_softmax_row<4, T, DROP>(s_addr, quarter, lane, tab, p.scale, km, ph, s_empty, p_empty, pe_par, full_row, p, drop_base);
+        else inv_cur = a2_softmax_row<2, T, DROP>(s_addr, quarter, lane, tab, p.scale, km, ph, s_empty, p_empty, pe_par, full_row, p, drop_base);
+      }
+      fence_proxy_async();          // P (generic-proxy stores) must be visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (it > 0) epilogue(it - 1, u_prev, inv_prev);
+      inv_prev = inv_cur;
+      u_prev = u;
+    }
+    if (it > 0) epilogue(it - 1, u_prev, inv_prev);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+// ---- host ---------------------------------------------------------------------------------------------------
+template <int D, int HC, int STAGES, typename T, bool DROP>
+static int launch_attn2_t(const AttnTcArgs& a, cudaStream_t st) {
+  Attn2Params p;
+  memset(&p, 0, sizeof(p));
+  p.H = a.H; p.W = a.W; p.L = a.H * a.W; p.C = a.C; p.G = a.n_groups; p.hpg = a.heads_per_group;
+  p.cg = a.C / a.n_groups;
+  for (int g = 0; g < a.n_groups; ++g) { p.ws[g] = a.window[g]; p.shift[g] = a.shift[g]; p.table[g] = a.table[g]; }
+  p.tiles = a.B * p.L / A2_ROWS; p.nhc = a.heads_per_group / HC; p.total_units = p.tiles * p.nhc * p.G;
+  p.out = a.out; p.fmt = a.io_type == DT_BF16 ? 1 : 0; p.scale = 1.4426950408889634f / sqrtf((float)D);   // d^-0.5 * log2(e)
+  p.p_drop = a.p_drop; p.keep_inv = a.p_drop > 0.f ? 1.0f / (1.0f - a.p_drop) : 1.0f; p.seed = a.seed; p.site = a.site;
+  CUtensorMap maps[3];
+  const void* bases[3] = {a.qw, a.kw, a.vw};
+  const long long rows = (long long)a.B * p.L;
+  for (int i = 0; i < 3; ++i) {
+    const uint64_t dims[3] = {(uint64_t)p.cg, (uint64_t)rows, (uint64_t)p.G};
+    const uint64_t str[2] = {(uint64_t)p.cg * 2, (uint64_t)rows * p.cg * 2};
+    const uint32_t box[3] = {(uint32_t)D, A2_ROWS, 1};
+    int rc = make_tensor_map_16bit(&maps[i], bases[i], 3, dims, str, box,
+                                   D == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  int num_sms = 0;
+  DPMN_CUDA_TRY(current_device_sms(&num_sms));
+  const int grid = p.total_units < 2 * num_sms ? p.total_units : 2 * num_sms;
+  auto kern = attn2_tc_kernel<D, HC, STAGES, T, DROP>;
+  constexpr int smem = A2Smem<D, HC, STAGES>::TOTAL;
+  static_assert(smem <= 115712, "two CTAs per SM");
+  static PerDeviceOnce attr;      // per template instantiation, per device
+  DPMN_CUDA_TRY(attr.smem_attr(kern, smem));
+  kern<<<grid, 64 + HC * 128, smem, st>>>(maps[0], maps[1], maps[2], p);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+bool attn2_tc_supported(const AttnTcArgs& a) {
+  if (a.io_type != DT_F16 && a.io_type != DT_BF16) return false;
+  if (a.n_groups < 1 || a.n_groups > 4 || a.C % a.n_groups) return false;
+  const int cg = a.C / a.n_groups;
+  if (a.heads_per_group < 1 || cg % a.heads_per_group) return false;
+  const int d = cg / a.heads_per_group;
+  if (d != 16 && d != 32) return false;
+  if ((a.H * a.W) % A2_ROWS) return false;
+  if (a.n_groups * a.heads_per_group * A2_TAB_STRIDE > A2_TAB_FLOATS) return false;
+  if (a.p_drop < 0.f || a.p_drop >= 1.f) return false;
+  for (int g = 0; g < a.n_groups; ++g) {
+    const int ws = a.window[g];
+    if (ws != 2 && ws != 4 && ws != 8) return false;
+    if (a.H % ws || a.W % ws) return false;
+    if (a.shift[g] < 0 || a.shift[g] >= ws) return false;
+  }
+  return true;
+}
+
+template <typename T>
+static int launch_attn2_dtype(const AttnTcArgs& a, cudaStream_t st) {
+  const int d = a.C / a.n_groups / a.heads_per_group;
+  const bool drop = a.p_drop > 0.f;
+  if (d == 16 && a.heads_per_group % 2 == 0)
+    return drop ? launch_attn2_t<16, 2, 3, T, true>(a, st) : launch_attn2_t<16, 2, 3, T, false>(a, st);
+  if (d == 16) return drop ? launch_attn2_t<16, 1, 3, T, true>(a, st) : launch_attn2_t<16, 1, 3, T, false>(a, st);
+  return drop ? launch_attn2_t<32, 1, 3, T, true>(a, st) : launch_attn2_t<32, 1, 3, T, false>(a, st);
+}
+
+int launch_window_attn2_tc(const AttnTcArgs& a, cudaStream_t st) {
+  if (!attn2_tc_supported(a)) return -2;
+  return a.io_type == DT_F16 ? launch_attn2_dtype<__half>(a, st) : launch_attn2_dtype<__nv_bfloat16>(a, st);
+}
+
+}  // namespace dpmn

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
+#include <cstdlib>
 #include <cstring>
 
 namespace dpmn {
@@ -435,7 +436,13 @@ static int launch_attn_tc_t(const AttnTcArgs& a, cudaStream_t st) {
   return 0;
 }
 
-bool attn_tc_supported(const AttnTcArgs& a) {
+static bool attn_v1_forced() {
+  static const bool v1 = getenv("DPMN_ATTN_V1") && atoi(getenv("DPMN_ATTN_V1")) != 0;
+  return v1;
+}
+
+static bool attn_v1_supported(const AttnTcArgs& a) {
+  if (a.p_drop > 0.f) return false;
   if (a.io_type != DT_F16 && a.io_type != DT_BF16) return false;
   if (a.n_groups < 1 || a.n_groups > 4 || a.C % a.n_groups) return false;
   const int cg = a.C / a.n_groups;
@@ -453,8 +460,14 @@ bool attn_tc_supported(const AttnTcArgs& a) {
   return true;
 }
 
+bool attn_tc_supported(const AttnTcArgs& a) {
+  if (!attn_v1_forced() && attn2_tc_supported(a)) return true;
+  return attn_v1_supported(a);
+}
+
 int launch_window_attn_tc(const AttnTcArgs& a, cudaStream_t st) {
-  if (!attn_tc_supported(a)) return -2;
+  if (!attn_v1_forced() && attn2_tc_supported(a)) return launch_window_attn2_tc(a, st);
+  if (!attn_v1_supported(a)) return -2;
   const int d = a.C / a.n_groups / a.heads_per_group;
   if (d == 16) {
     return a.io_type == DT_F16 ? launch_attn_tc_t<16, __half>(a, st) : launch_attn_tc_t<16, __nv_bfloat16>(a, st);

@@ -90,9 +90,12 @@ struct AttnTcArgs {
   const float* table[4] = {nullptr, nullptr, nullptr, nullptr};
   int B = 0, H = 0, W = 0, C = 0, n_groups = 0, heads_per_group = 0;
   int window[4] = {0, 0, 0, 0}, shift[4] = {0, 0, 0, 0};
+  float p_drop = 0.f; unsigned long long seed = 0; uint32_t site = 0;   // attn_drop (train mode), attn2_tc.cu only
 };
 bool attn_tc_supported(const AttnTcArgs& a);
-int launch_window_attn_tc(const AttnTcArgs& a, cudaStream_t st);
+int launch_window_attn_tc(const AttnTcArgs& a, cudaStream_t st);      // dispatches to attn2_tc.cu unless DPMN_ATTN_V1=1
+bool attn2_tc_supported(const AttnTcArgs& a);                           // attn2_tc.cu: M = 64 tiles, two CTAs per SM
+int launch_window_attn2_tc(const AttnTcArgs& a, cudaStream_t st);
 
 // SK gate (pgrm.py:84-95 folded): from per-tile column sums of GELU(proj(x)) build, per image,
 // Wb = Wp + Wh * diag(softmax_G(fc2(GELU(fc1(mean))))) (C x C) and bias_b = bp + bh.

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import List, Sequence
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -496,8 +496,10 @@ def to_window_major(x: torch.Tensor, grid, windows: Sequence[int], shifts: Seque
 
 
 def window_attention_windowed(qw: torch.Tensor, kw: torch.Tensor, vw: torch.Tensor, tables: List[torch.Tensor], batch: int,
-                              grid, num_heads: int, windows: Sequence[int], shifts: Sequence[int]) -> torch.Tensor:
-    """The tcgen05 window-attention kernel on window-major fp16 / bf16 operands [G][B*L][C/G] -> (B, L, C)."""
+                              grid, num_heads: int, windows: Sequence[int], shifts: Sequence[int],
+                              drop: Optional[Tuple[float, int, int]] = None) -> torch.Tensor:
+    """The tcgen05 window-attention kernel on window-major fp16 / bf16 operands [G][B*L][C/G] -> (B, L, C).
+    drop = (attn_drop rate, seed, site): train-mode attn_drop (pgrm.py:248) with the library's counter-hash masks."""
     lib = _lib.load()
     if not (qw.is_cuda and qw.is_contiguous() and kw.is_contiguous() and vw.is_contiguous()):
         raise RuntimeError("window_attention_windowed: contiguous CUDA tensors required")
@@ -509,8 +511,10 @@ def window_attention_windowed(qw: torch.Tensor, kw: torch.Tensor, vw: torch.Tens
     wv = (C.c_int32 * _lib.MAX_GROUPS)(*windows)
     sv = (C.c_int32 * _lib.MAX_GROUPS)(*shifts)
     with torch.cuda.device(qw.device):
-        rc = lib.dpmn_window_attn_forward_windowed(qw.data_ptr(), kw.data_ptr(), vw.data_ptr(), out.data_ptr(), C.byref(tabs),
-                                                   batch, grid[0], grid[1], G * cg, num_heads, G, C.byref(wv), C.byref(sv),
-                                                   prec, torch.cuda.current_stream(qw.device).cuda_stream)
-    _lib.check(rc, "dpmn_window_attn_forward_windowed")
+        p_drop, seed, site = drop if drop is not None else (0.0, 0, 0)
+        rc = lib.dpmn_window_attn_forward_windowed_train(qw.data_ptr(), kw.data_ptr(), vw.data_ptr(), out.data_ptr(),
+                                                         C.byref(tabs), batch, grid[0], grid[1], G * cg, num_heads, G,
+                                                         C.byref(wv), C.byref(sv), prec, float(p_drop), int(seed), int(site),
+                                                         torch.cuda.current_stream(qw.device).cuda_stream)
+    _lib.check(rc, "dpmn_window_attn_forward_windowed_train")
     return out

@@ -217,13 +217,21 @@ size_t dpmn_window_attn_workspace_bytes(int32_t batch, int32_t tokens, int32_t e
 /* The same attention core on WINDOW-MAJOR operands -- the layout the fused pipeline feeds it (the q / kv projection
  * epilogue applies roll + window_partition, pgrm.py:209-225): qw, kw, vw are [n_groups][batch*L][embed_dim/n_groups]
  * 16-bit, row p of group g = token window_row_to_token(p) of that group's (window, shift).  This is the tcgen05
- * kernel (attn_tc.cu) itself: precision must be F16 or BF16, windows in {2,4,8}, head_dim 16 or 32, an even number
- * of heads per group; anything else returns DPMN_E_UNSUPPORTED.  out (batch*L, embed_dim) window-major rows. */
+ * kernel (attn2_tc.cu; attn_tc.cu with DPMN_ATTN_V1=1) itself: precision must be F16 or BF16, windows in {2,4,8},
+ * head_dim 16 or 32; anything else returns DPMN_E_UNSUPPORTED.  out (batch*L, embed_dim) window-major rows. */
 int dpmn_window_attn_forward_windowed(const void *qw, const void *kw, const void *vw, void *out,
                                       const float *const rpb_table[DPMN_MAX_GROUPS], int32_t batch, int32_t grid_h,
                                       int32_t grid_w, int32_t embed_dim, int32_t num_heads, int32_t n_groups,
                                       const int32_t window[DPMN_MAX_GROUPS], const int32_t shift[DPMN_MAX_GROUPS],
                                       int32_t precision, void *stream);
+/* Train-mode form (WindowAttention.attn_drop, model/pgrm.py:180,248): each softmax probability is kept with probability
+ * 1 - attn_drop and scaled by 1/(1 - attn_drop), inside the same kernel.  The mask of element (b, g, head-in-group, window-major
+ * row p, key m) is dpmn_mask_hash(seed, site, ((((b*G + g)*heads_per_group + head)*L + p)*N + m)) (see dpmn_mask_hash). */
+int dpmn_window_attn_forward_windowed_train(const void *qw, const void *kw, const void *vw, void *out,
+                                            const float *const rpb_table[DPMN_MAX_GROUPS], int32_t batch, int32_t grid_h,
+                                            int32_t grid_w, int32_t embed_dim, int32_t num_heads, int32_t n_groups,
+                                            const int32_t window[DPMN_MAX_GROUPS], const int32_t shift[DPMN_MAX_GROUPS],
+                                            int32_t precision, float attn_drop, uint64_t seed, uint32_t site, void *stream);
 
 size_t dpmn_cmm_workspace_bytes(const dpmn_cmm_desc *d);
 size_t dpmn_cmm_prepared_bytes(const dpmn_cmm_desc *d);     /* 0 in the fp32 mode */

@@ -345,7 +345,8 @@ def test_prepared_weight_cache_tracks_in_place_updates():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("C,windows,shifted", [(96, [2, 4, 8], True), (96, [8], False), (96, [4], True), (192, [8], True),
-                                               (192, [2], False)])
+                                               (192, [2], False), (96, [2], True), (96, [8], True), (96, [2, 4, 8], False),
+                                               (192, [4], True), (96, [4, 8], True), (192, [2, 4, 8], True)])
 def test_window_attention_windowed_tcgen05_matches_simt(C, windows, shifted):
     """dpmn_window_attn_forward_windowed (the tcgen05 kernel on window-major operands, head_dim 16 and 32) against the
     fp32 SIMT core on the same values in token order."""
@@ -365,6 +366,63 @@ def test_window_attention_windowed_tcgen05_matches_simt(C, windows, shifted):
     vw = to_window_major(kv[..., C:].contiguous(), (H, W), windows, shifts)
     out = window_attention_windowed(qw, kw, vw, tabs, B, (H, W), heads, windows, shifts)
     assert rel_err(out.float().cpu().numpy(), ref.cpu().numpy()) < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+@pytest.mark.parametrize("C,windows,B,shifts", [(96, [2, 4, 8], 3, [1, 2, 4]), (96, [8], 1, [3]), (96, [4], 2, [1]),
+                                                (192, [8], 2, [4]), (96, [2, 4, 8], 5, [0, 0, 0]), (96, [4, 8], 2, [2, 5])])
+def test_attn2_tcgen05_against_the_oracle_core(dtype, C, windows, B, shifts):
+    """attn2_tc.cu (M = 64 tiles, two CTAs per SM) against the torch restatement of pgrm.py:197-268 on the same 16-bit
+    operand values: odd batch counts (persistent-loop tails), arbitrary shifts (the closed-form shift mask is not tied to
+    ws // 2), odd heads per group (one head per unit), both 16-bit types.  Bar: 1e-3 fp16 (north_star), 4e-3 bf16 (P and the
+    output are rounded to 8 mantissa bits)."""
+    import torch
+    from dpmn_b200.pgrm import to_window_major, window_attention_windowed
+    from oracle import torch_ref
+    dev = torch.device("cuda")
+    torch.manual_seed(11)
+    td = torch.float16 if dtype == "fp16" else torch.bfloat16
+    H, W, heads = 16, 64, 6
+    G = len(windows)
+    q = torch.randn(B, H * W, C, device=dev).to(td)
+    kv = torch.randn(B, H * W, 2 * C, device=dev).to(td)
+    tabs = [torch.randn((2 * w - 1) ** 2, heads // G, device=dev) * 0.5 for w in windows]
+    ref = torch_ref.window_attention_core(q.float().cpu(), kv.float().cpu(), [t.cpu() for t in tabs], windows, shifts, H, W,
+                                          heads // G)
+    qw = to_window_major(q, (H, W), windows, shifts)
+    kw = to_window_major(kv[..., :C].contiguous(), (H, W), windows, shifts)
+    vw = to_window_major(kv[..., C:].contiguous(), (H, W), windows, shifts)
+    out = window_attention_windowed(qw, kw, vw, tabs, B, (H, W), heads, windows, shifts)
+    assert rel_err(out.float().cpu().numpy(), ref.numpy()) < (1e-3 if dtype == "fp16" else 4e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,windows", [(96, [2, 4, 8]), (192, [8]), (96, [4, 8])])
+def test_attn2_attn_drop_masks_match_the_oracle(C, windows):
+    """Train-mode attn_drop (pgrm.py:248) inside the tcgen05 kernel: the oracle applies the SAME counter-hash masks
+    (dpmn_mask_hash over (b, group, head, row, key)) to its softmax; with p = 0.3 a wrong mask index moves the output by O(1)."""
+    import torch
+    from dpmn_b200.pgrm import to_window_major, window_attention_windowed
+    from oracle import torch_ref
+    dev = torch.device("cuda")
+    torch.manual_seed(5)
+    B, H, W, heads = 2, 16, 64, 6
+    G = len(windows)
+    shifts = [w // 2 for w in windows]
+    q = torch.randn(B, H * W, C, device=dev).half()
+    kv = torch.randn(B, H * W, 2 * C, device=dev).half()
+    tabs = [torch.randn((2 * w - 1) ** 2, heads // G, device=dev) * 0.5 for w in windows]
+    p, seed, site = 0.3, 0x1234567, 16
+    ref = torch_ref.window_attention_core(q.float().cpu(), kv.float().cpu(), [t.cpu() for t in tabs], windows, shifts, H, W,
+                                          heads // G, drop=(p, seed), site=site)
+    qw = to_window_major(q, (H, W), windows, shifts)
+    kw = to_window_major(kv[..., :C].contiguous(), (H, W), windows, shifts)
+    vw = to_window_major(kv[..., C:].contiguous(), (H, W), windows, shifts)
+    out = window_attention_windowed(qw, kw, vw, tabs, B, (H, W), heads, windows, shifts, drop=(p, seed, site))
+    assert rel_err(out.float().cpu().numpy(), ref.numpy()) < 1e-3
+    plain = window_attention_windowed(qw, kw, vw, tabs, B, (H, W), heads, windows, shifts)
+    assert rel_err(plain.float().cpu().numpy(), ref.numpy()) > 5e-2      # the masks do something
 
 
 @pytest.mark.gpu

@@ -38,17 +38,33 @@ constexpr int A2_TAB_STRIDE = 232;          // >= (2*8-1)^2
 constexpr int A2_TAB_FLOATS = 6 * A2_TAB_STRIDE;
 
 struct Attn2Params {
-  int H, W, L, C, G, hpg, cg;
+  int L, C, G, hpg, cg;
   int ws[4], shift[4];
+  int order[4];                     // group of the gi-th run of units: window sizes descending, the heavy units first
+  int upg;                          // units per group = tiles * nhc
   int tiles, nhc, total_units;
+  int tpi; uint32_t tpi_magic;      // 128-row tiles per image, ceil(2^32 / tpi)
+  // shift mask (pgrm.py:157-173) per group: windows per window row and its division magic, first window of the last
+  // window row, key bitmasks of "key row < ws - shift" / "key column < ws - shift" (replicated over rows), all N keys
+  int nww[4]; uint32_t nww_magic[4]; int lastrow_w0[4]; int cut[4];
+  unsigned long long rows_lo[4], cols_lo[4], all_keys[4];
   const float* table[4];
   void* out;
   int fmt;
-  float scale;                // head_dim^-0.5 * log2(e)
+  float scale;                      // head_dim^-0.5 * log2(e)
   float p_drop, keep_inv;
   unsigned long long seed;
   uint32_t site;
 };
+
+// unit u -> (group, 128-row tile, head chunk); warp-uniform
+__device__ __forceinline__ void a2_decode(const Attn2Params& p, int u, int& g, int& tile, int& hc) {
+  const int gi = (u >= p.upg) + (u >= 2 * p.upg) + (u >= 3 * p.upg);
+  const int r = u - gi * p.upg;
+  g = p.order[gi];
+  if (p.nhc == 1) { tile = r; hc = 0; }
+  else { tile = r / p.nhc; hc = r - tile * p.nhc; }
+}
 
 template <int D>
 __device__ __forceinline__ uint64_t a2_desc_rowD(uint32_t smem_addr) {
@@ -93,13 +109,13 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
 }
 
 // Softmax of this thread's row of one head + the write of its P row.  s_addr: TMEM address of the head's S tile at this
-// warp's lane quarter.  row_half = 16*quarter + lane%16 (row within the 64-row half), p_half: the half's P tile.
-// Returns 1 / (softmax denominator [* keep probability]).
+// warp's lane quarter.  row_half = 16*quarter + lane%16 (row within the 64-row half), p_half: the half's P tile,
+// w_idx: the row's window within its image.  Returns 1 / (softmax denominator [* keep probability]).
 template <int WS, typename T, bool DROP>
-__device__ __forceinline__ float a2_softmax_row(uint32_t s_addr, int quarter, int lane, const float* tab, float scale,
-                                                unsigned long long km, uint8_t* p_half, uint64_t* s_empty_bar,
-                                                uint64_t* p_empty_bar, uint32_t p_empty_parity, bool full_row,
-                                                const Attn2Params& p, unsigned long long drop_base) {
+__device__ __forceinline__ float a2_softmax_row(uint32_t s_addr, int quarter, int lane, const float* tab, int g, int w_idx,
+                                                uint8_t* p_half, uint64_t* s_empty_bar, uint64_t* p_empty_bar,
+                                                uint32_t p_empty_parity, bool full_row, const Attn2Params& p,
+                                                unsigned long long drop_base) {
   constexpr int N = WS * WS;
   constexpr int TW = 2 * WS - 1;
   const int r16 = lane & 15;
@@ -139,6 +155,17 @@ __device__ __forceinline__ float a2_softmax_row(uint32_t s_addr, int quarter, in
 
   const int n = WS == 8 ? row_half : (WS == 4 ? r16 : (r16 & 3));
   const int i_n = n / WS, j_n = n % WS;
+  const float scale = p.scale;
+  // shift mask in closed form: rolled rows / columns carry region label 0 except in the LAST window row / column, where
+  // positions >= ws - shift carry 2 and the others 1 (pgrm.py:157-168); keys whose label differs from the row's get -100
+  unsigned long long km = 0ull;
+  if (p.shift[g] > 0) {
+    const int cut = p.cut[g];
+    if (w_idx >= p.lastrow_w0[g]) km |= i_n >= cut ? p.rows_lo[g] : (p.all_keys[g] ^ p.rows_lo[g]);
+    const int nww = p.nww[g];
+    const int wq = (int)__umulhi((uint32_t)w_idx, p.nww_magic[g]);
+    if (w_idx - wq * nww == nww - 1) km |= j_n >= cut ? p.cols_lo[g] : (p.all_keys[g] ^ p.cols_lo[g]);
+  }
   const float* tb = tab + (i_n + WS - 1) * TW + (j_n + WS - 1);
   // log2 domain: `scale` and the table carry log2(e), so each key costs LDS, FFMA, max, FADD, EX2, FADD
 #pragma unroll
@@ -240,7 +267,6 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   // 1024-byte alignment (128B swizzle atoms) by an offset into the __shared__ array: the pointers keep their address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   using S = A2Smem<D, HC, STAGES>;
-  constexpr int THREADS = 64 + HC * 128;
   uint8_t* stages = smem;
   uint8_t* p_tiles = smem + STAGES * S::STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(p_tiles + S::P_BYTES);
@@ -259,21 +285,61 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   constexpr uint32_t TMEM_COLS = HC == 2 ? 256 : 128;
   constexpr uint32_t O_COL0 = HC * 64;
 
-  for (int i = threadIdx.x; i < p.G * p.hpg * A2_TAB_STRIDE; i += THREADS) {
-    const int e = i % A2_TAB_STRIDE, gh = i / A2_TAB_STRIDE;
-    const int g = gh / p.hpg, h = gh - g * p.hpg;
-    const int tw = 2 * p.ws[g] - 1;
-    s_tab[i] = e < tw * tw ? p.table[g][e * p.hpg + h] * 1.4426950408889634f : 0.f;   // log2 domain
+  // Prologue, three roles at once: warp 0 initialises the barriers and immediately puts the first STAGES units' Q / K / V
+  // in flight; warp 1 allocates TMEM; the softmax warps stage the bias tables (all loads issued before the first store).
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      mbar_init(s_full, 1); mbar_init(s_empty, 4 * HC);
+      mbar_init(p_full, 4 * HC); mbar_init(p_empty, 1);
+      mbar_init(o_full, 1); mbar_init(o_empty, 4 * HC);
+      fence_barrier_init();
+    }
+  } else if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  } else {
+    constexpr int NT = HC * 128;
+    const int t = threadIdx.x - 64;
+    float v[6];
+#pragma unroll
+    for (int gh = 0; gh < 6; ++gh) {
+      v[gh] = 0.f;
+      if (gh < p.G * p.hpg) {
+        const int g = gh / p.hpg, h = gh - g * p.hpg;
+        const int tw2 = (2 * p.ws[g] - 1) * (2 * p.ws[g] - 1);
+        if (t < tw2) v[gh] = p.table[g][t * p.hpg + h];
+      }
+    }
+#pragma unroll
+    for (int gh = 0; gh < 6; ++gh)
+      if (gh < p.G * p.hpg && t < A2_TAB_STRIDE) s_tab[gh * A2_TAB_STRIDE + t] = v[gh] * 1.4426950408889634f;   // log2 domain
+    if constexpr (NT < A2_TAB_STRIDE) {      // one head per unit: 128 threads, the 15 x 15 table of an 8-window needs a second pass
+      for (int gh = 0; gh < p.G * p.hpg; ++gh) {
+        const int g = gh / p.hpg, h = gh - g * p.hpg;
+        const int tw2 = (2 * p.ws[g] - 1) * (2 * p.ws[g] - 1);
+        for (int e = t + NT; e < tw2; e += NT) s_tab[gh * A2_TAB_STRIDE + e] = p.table[g][e * p.hpg + h] * 1.4426950408889634f;
+      }
+    }
   }
+  auto tma_unit = [&](int u, int it) {
+    int g, tile, hc;
+    a2_decode(p, u, g, tile, hc);
+    const int stage = it % STAGES;
+    uint8_t* st = stages + stage * S::STAGE;
+    mbar_arrive_expect_tx(&full_bar[stage], S::STAGE);
+#pragma unroll
+    for (int h = 0; h < HC; ++h) {
+      const int ch = (hc * HC + h) * D;
+      tma_load_3d(st + (h * 3 + 0) * S::TILE, &map_q, &full_bar[stage], ch, tile * A2_ROWS, g);
+      tma_load_3d(st + (h * 3 + 1) * S::TILE, &map_k, &full_bar[stage], ch, tile * A2_ROWS, g);
+      tma_load_3d(st + (h * 3 + 2) * S::TILE, &map_v, &full_bar[stage], ch, tile * A2_ROWS, g);
+    }
+  };
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 4 * HC);
-    mbar_init(p_full, 4 * HC); mbar_init(p_empty, 1);
-    mbar_init(o_full, 1); mbar_init(o_empty, 4 * HC);
-    fence_barrier_init();
+    int it = 0;
+    for (int u = blockIdx.x; u < p.total_units && it < STAGES; u += gridDim.x, ++it) tma_unit(u, it);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -282,20 +348,10 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   // units are ordered group-major, so a CTA's consecutive units mostly share the window size (the P zero pattern)
   if (warp == 0) {
     if (lane == 0) {
-      int it = 0;
-      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
-        const int hc = u % p.nhc, tile = (u / p.nhc) % p.tiles, g = u / (p.nhc * p.tiles);
-        const int stage = it % STAGES;
-        mbar_wait(&empty_bar[stage], (uint32_t)(((it / STAGES) & 1) ^ 1));
-        uint8_t* st = stages + stage * S::STAGE;
-        mbar_arrive_expect_tx(&full_bar[stage], S::STAGE);
-#pragma unroll
-        for (int h = 0; h < HC; ++h) {
-          const int ch = (hc * HC + h) * D;
-          tma_load_3d(st + (h * 3 + 0) * S::TILE, &map_q, &full_bar[stage], ch, tile * A2_ROWS, g);
-          tma_load_3d(st + (h * 3 + 1) * S::TILE, &map_k, &full_bar[stage], ch, tile * A2_ROWS, g);
-          tma_load_3d(st + (h * 3 + 2) * S::TILE, &map_v, &full_bar[stage], ch, tile * A2_ROWS, g);
-        }
+      int it = STAGES;
+      for (int u = blockIdx.x + STAGES * gridDim.x; u < p.total_units; u += gridDim.x, ++it) {
+        mbar_wait(&empty_bar[it % STAGES], (uint32_t)(((it / STAGES) & 1) ^ 1));
+        tma_unit(u, it);
       }
     }
   } else if (warp == 1) {
@@ -356,8 +412,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int row = half * 64 + quarter * 16 + r16;     // row within the unit
     T* out = reinterpret_cast<T*>(p.out);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    auto epilogue = [&](int j, int u_prev, float inv_row) {
-      const int hc = u_prev % p.nhc, tile = (u_prev / p.nhc) % p.tiles, g = u_prev / (p.nhc * p.tiles);
+    auto epilogue = [&](int j, T* dst, float inv_row) {
       mbar_wait(o_full, (uint32_t)(j & 1));
       tc_fence_after();
       uint32_t o[32];
@@ -368,7 +423,6 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
-      T* dst = out + ((long long)tile * A2_ROWS + row) * p.C + g * p.cg + (hc * HC + h) * D;
 #pragma unroll
       for (int c = 0; c < D; c += 8) {
         uint4 v;
@@ -379,38 +433,19 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         *reinterpret_cast<uint4*>(dst + c) = v;
       }
     };
-    int it = 0, u_prev = -1;
+    int it = 0;
     int last_ws = -1;                                   // window size whose zero pattern the P buffer currently holds
     float inv_prev = 1.f, inv_cur = 1.f;                // 1 / softmax denominator of this thread's row
+    T* dst_prev = nullptr;
+    T* const out_row = out + (long long)row * p.C + h * D;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
-      const int hc = u % p.nhc, tile = (u / p.nhc) % p.tiles, g = u / (p.nhc * p.tiles);
-      const int ws = p.ws[g], N = ws * ws, shift = p.shift[g];
-      const int grow = tile * A2_ROWS + row;            // window-major row in [0, B*L)
-      const int b_img = grow / p.L;
-      const int p_img = grow - b_img * p.L;
-      const int w_idx = p_img / N, n = p_img - w_idx * N;
-      // shift mask (pgrm.py:157-173) in closed form: rolled rows / columns carry region label 0 except in the LAST window
-      // row / column, where positions >= ws - shift carry 2 and the others 1; keys whose label differs get -100.
-      unsigned long long km = 0ull;
-      if (shift > 0) {
-        const int nWw = p.W / ws, nWin = p.L / N;
-        const int i_n = n / ws, j_n = n - i_n * ws;
-        const int cut = ws - shift;
-        if (w_idx >= nWin - nWw) {                      // last window row
-          const unsigned long long lowrows = (1ull << (cut * ws)) - 1ull;
-          const unsigned long long all = N == 64 ? ~0ull : ((1ull << N) - 1ull);
-          km |= i_n >= cut ? lowrows : (all & ~lowrows);
-        }
-        if (w_idx % nWw == nWw - 1) {                   // last window column
-          const unsigned long long rep = ws == 8 ? 0x0101010101010101ull : (ws == 4 ? 0x1111ull : 0x5ull);
-          const unsigned long long lowcols = (1ull << cut) - 1ull;
-          const unsigned long long allc = (1ull << ws) - 1ull;
-          km |= (j_n >= cut ? lowcols : (allc & ~lowcols)) * rep;
-        }
-      }
+      int g, tile, hc;
+      a2_decode(p, u, g, tile, hc);
+      const int ws = p.ws[g];
+      const int b_img = (int)__umulhi((uint32_t)tile, p.tpi_magic);
+      const int p_img = (tile - b_img * p.tpi) * A2_ROWS + row;          // window-major row within the image
       const int head = hc * HC + h;
-      const unsigned long long drop_base =
-          DROP ? ((((unsigned long long)b_img * p.G + g) * p.hpg + head) * p.L + p_img) * (unsigned long long)N : 0ull;
+      T* dst = out_row + (long long)tile * (A2_ROWS * p.C) + g * p.cg + hc * (HC * D);
       mbar_wait(s_full, (uint32_t)(it & 1));
       tc_fence_after();
       {
@@ -420,18 +455,21 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t pe_par = (uint32_t)((it & 1) ^ 1);
         const bool full_row = last_ws != ws;
         last_ws = ws;
-        if (ws == 8) inv_cur = a2_softmax_row<8, T, DROP>(s_addr, quarter, lane, tab, p.scale, km, ph, s_empty, p_empty, pe_par, full_row, p, drop_base);
-        else if (ws == 4) inv_cur = a2_softmax_row<4, T, DROP>(s_addr, quarter, lane, tab, p.scale, km, ph, s_empty, p_empty, pe_par, full_row, p, drop_base);
-        else inv_cur = a2_softmax_row<2, T, DROP>(s_addr, quarter, lane, tab, p.scale, km, ph, s_empty, p_empty, pe_par, full_row, p, drop_base);
+        unsigned long long drop_base = 0ull;
+        if constexpr (DROP)
+          drop_base = ((((unsigned long long)b_img * p.G + g) * p.hpg + head) * p.L + p_img) * (unsigned long long)(ws * ws);
+        if (ws == 8) inv_cur = a2_softmax_row<8, T, DROP>(s_addr, quarter, lane, tab, g, p_img >> 6, ph, s_empty, p_empty, pe_par, full_row, p, drop_base);
+        else if (ws == 4) inv_cur = a2_softmax_row<4, T, DROP>(s_addr, quarter, lane, tab, g, p_img >> 4, ph, s_empty, p_empty, pe_par, full_row, p, drop_base);
+        else inv_cur = a2_softmax_row<2, T, DROP>(s_addr, quarter, lane, tab, g, p_img >> 2, ph, s_empty, p_empty, pe_par, full_row, p, drop_base);
       }
       fence_proxy_async();          // P (generic-proxy stores) must be visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      if (it > 0) epilogue(it - 1, u_prev, inv_prev);
+      if (it > 0) epilogue(it - 1, dst_prev, inv_prev);
       inv_prev = inv_cur;
-      u_prev = u;
+      dst_prev = dst;
     }
-    if (it > 0) epilogue(it - 1, u_prev, inv_prev);
+    if (it > 0) epilogue(it - 1, dst_prev, inv_prev);
   }
 
   tc_fence_before();
@@ -449,10 +487,22 @@ template <int D, int HC, int STAGES, typename T, bool DROP>
 static int launch_attn2_t(const AttnTcArgs& a, cudaStream_t st) {
   Attn2Params p;
   memset(&p, 0, sizeof(p));
-  p.H = a.H; p.W = a.W; p.L = a.H * a.W; p.C = a.C; p.G = a.n_groups; p.hpg = a.heads_per_group;
+  p.L = a.H * a.W; p.C = a.C; p.G = a.n_groups; p.hpg = a.heads_per_group;
   p.cg = a.C / a.n_groups;
-  for (int g = 0; g < a.n_groups; ++g) { p.ws[g] = a.window[g]; p.shift[g] = a.shift[g]; p.table[g] = a.table[g]; }
-  p.tiles = a.B * p.L / A2_ROWS; p.nhc = a.heads_per_group / HC; p.total_units = p.tiles * p.nhc * p.G;
+  p.tiles = a.B * p.L / A2_ROWS; p.nhc = a.heads_per_group / HC; p.upg = p.tiles * p.nhc; p.total_units = p.upg * p.G;
+  p.tpi = p.L / A2_ROWS; p.tpi_magic = (uint32_t)((0x100000000ull + p.tpi - 1) / p.tpi);
+  for (int g = 0; g < a.n_groups; ++g) {
+    const int ws = a.window[g], N = ws * ws, cut = ws - a.shift[g];
+    p.ws[g] = ws; p.shift[g] = a.shift[g]; p.table[g] = a.table[g]; p.order[g] = g; p.cut[g] = cut;
+    p.nww[g] = a.W / ws; p.nww_magic[g] = (uint32_t)((0x100000000ull + p.nww[g] - 1) / p.nww[g]);
+    p.lastrow_w0[g] = p.L / N - p.nww[g];
+    const unsigned long long rep = ws == 8 ? 0x0101010101010101ull : (ws == 4 ? 0x1111ull : 0x5ull);
+    p.all_keys[g] = N == 64 ? ~0ull : ((1ull << N) - 1ull);
+    p.rows_lo[g] = cut * ws >= 64 ? ~0ull : (1ull << (cut * ws)) - 1ull;   // (only read when shift >= 1)
+    p.cols_lo[g] = ((1ull << cut) - 1ull) * rep & p.all_keys[g];
+  }
+  for (int i = 1; i < a.n_groups; ++i)                          // heaviest (largest window) groups first
+    for (int j = i; j > 0 && p.ws[p.order[j]] > p.ws[p.order[j - 1]]; --j) { const int t = p.order[j]; p.order[j] = p.order[j - 1]; p.order[j - 1] = t; }
   p.out = a.out; p.fmt = a.io_type == DT_BF16 ? 1 : 0; p.scale = 1.4426950408889634f / sqrtf((float)D);   // d^-0.5 * log2(e)
   p.p_drop = a.p_drop; p.keep_inv = a.p_drop > 0.f ? 1.0f / (1.0f - a.p_drop) : 1.0f; p.seed = a.seed; p.site = a.site;
   CUtensorMap maps[3];

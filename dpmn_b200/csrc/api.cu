@@ -290,7 +290,7 @@ int pgrm_forward_impl(const dpmn_pgrm_desc* d, const float* x_q, const float* x_
     ta.qw = w.q; ta.kw = w.kv; ta.vw = (const char*)w.kv + (size_t)rows * C * 2; ta.out = w.attn; ta.io_type = at;
     ta.B = B; ta.H = H; ta.W = W; ta.C = C; ta.n_groups = G; ta.heads_per_group = d->num_heads / G;
     for (int g = 0; g < G; ++g) { ta.table[g] = a.table[g]; ta.window[g] = a.window[g]; ta.shift[g] = a.shift[g]; }
-    const bool tc_attn = prec != DPMN_PREC_F32 && attn_tc_supported(ta);
+    const bool tc_attn = prec != DPMN_PREC_F32 && attn_tc_supported(ta) && (C / G) % 32 == 0;   // the projection epilogue scatters 32-column chunks per group
 
     const void* q_in = fuse_ln ? w.lnq[blk] : w.ln;
     auto scatter_proj = [&](const void* A, const void* Wt, const float* bias, int N, void* dst0, void* dst1) {

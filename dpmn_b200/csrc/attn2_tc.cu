@@ -38,7 +38,8 @@ constexpr int A2_TAB_STRIDE = 232;          // >= (2*8-1)^2
 constexpr int A2_TAB_FLOATS = 6 * A2_TAB_STRIDE;
 
 struct Attn2Params {
-  int L, C, G, hpg, cg;
+  int L, C, G, hpg, cg, G_all;       // G groups in this launch (local index g) out of G_all
+  int gid[4];                       // actual group index of local group g: TMA z coordinate, output channels, dropout index
   int ws[4], shift[4];
   int order[4];                     // group of the gi-th run of units: window sizes descending, the heavy units first
   int upg;                          // units per group = tiles * nhc
@@ -331,9 +332,9 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
     for (int h = 0; h < HC; ++h) {
       const int ch = (hc * HC + h) * D;
-      tma_load_3d(st + (h * 3 + 0) * S::TILE, &map_q, &full_bar[stage], ch, tile * A2_ROWS, g);
-      tma_load_3d(st + (h * 3 + 1) * S::TILE, &map_k, &full_bar[stage], ch, tile * A2_ROWS, g);
-      tma_load_3d(st + (h * 3 + 2) * S::TILE, &map_v, &full_bar[stage], ch, tile * A2_ROWS, g);
+      tma_load_3d(st + (h * 3 + 0) * S::TILE, &map_q, &full_bar[stage], ch, tile * A2_ROWS, p.gid[g]);
+      tma_load_3d(st + (h * 3 + 1) * S::TILE, &map_k, &full_bar[stage], ch, tile * A2_ROWS, p.gid[g]);
+      tma_load_3d(st + (h * 3 + 2) * S::TILE, &map_v, &full_bar[stage], ch, tile * A2_ROWS, p.gid[g]);
     }
   };
   if (warp == 0 && lane == 0) {
@@ -445,7 +446,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int b_img = (int)__umulhi((uint32_t)tile, p.tpi_magic);
       const int p_img = (tile - b_img * p.tpi) * A2_ROWS + row;          // window-major row within the image
       const int head = hc * HC + h;
-      T* dst = out_row + (long long)tile * (A2_ROWS * p.C) + g * p.cg + hc * (HC * D);
+      T* dst = out_row + (long long)tile * (A2_ROWS * p.C) + p.gid[g] * p.cg + hc * (HC * D);
       mbar_wait(s_full, (uint32_t)(it & 1));
       tc_fence_after();
       {
@@ -457,7 +458,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         last_ws = ws;
         unsigned long long drop_base = 0ull;
         if constexpr (DROP)
-          drop_base = ((((unsigned long long)b_img * p.G + g) * p.hpg + head) * p.L + p_img) * (unsigned long long)(ws * ws);
+          drop_base = ((((unsigned long long)b_img * p.G_all + p.gid[g]) * p.hpg + head) * p.L + p_img) * (unsigned long long)(ws * ws);
         if (ws == 8) inv_cur = a2_softmax_row<8, T, DROP>(s_addr, quarter, lane, tab, g, p_img >> 6, ph, s_empty, p_empty, pe_par, full_row, p, drop_base);
         else if (ws == 4) inv_cur = a2_softmax_row<4, T, DROP>(s_addr, quarter, lane, tab, g, p_img >> 4, ph, s_empty, p_empty, pe_par, full_row, p, drop_base);
         else inv_cur = a2_softmax_row<2, T, DROP>(s_addr, quarter, lane, tab, g, p_img >> 2, ph, s_empty, p_empty, pe_par, full_row, p, drop_base);
@@ -480,20 +481,298 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   }
 }
 
+
+// =====================================================================================================================
+// Window 16 (N = 256 keys; the clamp case of pgrm.py:148-150 on the 16 x 64 grid, configs[4] of the sweep).
+// Unit = 128 query rows (half a window) of ONE head; keys / values = the whole 256-row window.  S = Q K^T is two
+// M64 x N256 MMAs (256 TMEM columns, halves interleaved by lanes as above), P is 2 halves x 4 key blocks of 64 x 64
+// (64 KB), O = P V accumulates over the four key blocks.  A row's 256 scores do not fit in registers: the softmax warps
+// read S twice (pass 1: row maximum; pass 2: exp, sum, P), 32 columns at a time.  Shift 0 only (a 16-window on this
+// grid is never shifted); one CTA per SM (512 TMEM columns).
+// =====================================================================================================================
+constexpr int W16_TAB_STRIDE = 964;        // >= 31 * 31
+constexpr int W16_MAX_HEADS = 6;
+
+struct AttnW16Params {
+  int L, C, hpg, cg, n_g, G_all;
+  int gid[4];                       // actual group index: TMA z coordinate, output channel offset, dropout index
+  int tiles, upg, total_units;      // units = n_g * tiles * hpg, head fastest
+  int tpi; uint32_t tpi_magic;
+  const float* table[4];
+  void* out;
+  int fmt;
+  float scale, p_drop, keep_inv;
+  unsigned long long seed;
+  uint32_t site;
+};
+
+template <int D, int STAGES>
+struct W16Smem {
+  static constexpr int Q_TILE = 128 * D * 2, KV_TILE = 256 * D * 2;
+  static constexpr int STAGE = Q_TILE + 2 * KV_TILE;
+  static constexpr int P_BLK = 64 * 128;                        // 64 rows x 64 keys
+  static constexpr int P_BYTES = 2 * 4 * P_BLK;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE + P_BYTES + BAR_BYTES + W16_MAX_HEADS * W16_TAB_STRIDE * 4 + 1024;
+};
+
+template <int D, int STAGES, typename T, bool DROP>
+__global__ void __launch_bounds__(192, 1)
+attn2_w16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AttnW16Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  using S = W16Smem<D, STAGES>;
+  uint8_t* stages = smem;
+  uint8_t* p_tiles = smem + STAGES * S::STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_tiles + S::P_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* s_full = bars + 2 * STAGES;
+  uint64_t* s_empty = s_full + 1;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* p_empty = s_full + 3;
+  uint64_t* o_full = s_full + 4;
+  uint64_t* o_empty = s_full + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
+  float* s_tab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + S::BAR_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 512, O_COL0 = 256;
+
+  auto decode = [&](int u, int& gi, int& tile, int& head) {
+    gi = (u >= p.upg) + (u >= 2 * p.upg) + (u >= 3 * p.upg);
+    const int r = u - gi * p.upg;
+    tile = r / p.hpg;
+    head = r - tile * p.hpg;
+  };
+  auto tma_unit = [&](int u, int it) {
+    int gi, tile, head;
+    decode(u, gi, tile, head);
+    const int stage = it % STAGES;
+    uint8_t* st = stages + stage * S::STAGE;
+    mbar_arrive_expect_tx(&full_bar[stage], S::STAGE);
+    tma_load_3d(st, &map_q, &full_bar[stage], head * D, tile * 128, p.gid[gi]);
+    tma_load_3d(st + S::Q_TILE, &map_k, &full_bar[stage], head * D, (tile >> 1) * 256, p.gid[gi]);
+    tma_load_3d(st + S::Q_TILE + S::KV_TILE, &map_v, &full_bar[stage], head * D, (tile >> 1) * 256, p.gid[gi]);
+  };
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      mbar_init(s_full, 1); mbar_init(s_empty, 4);
+      mbar_init(p_full, 4); mbar_init(p_empty, 1);
+      mbar_init(o_full, 1); mbar_init(o_empty, 4);
+      fence_barrier_init();
+      int it = 0;
+      for (int u = blockIdx.x; u < p.total_units && it < STAGES; u += gridDim.x, ++it) tma_unit(u, it);
+    }
+  } else if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+  } else {
+    const int t = threadIdx.x - 64;
+    for (int gh = 0; gh < p.n_g * p.hpg; ++gh) {
+      const int gi = gh / p.hpg, h = gh - gi * p.hpg;
+      for (int e = t; e < 961; e += 128) s_tab[gh * W16_TAB_STRIDE + e] = p.table[gi][e * p.hpg + h] * 1.4426950408889634f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = STAGES;
+      for (int u = blockIdx.x + STAGES * gridDim.x; u < p.total_units; u += gridDim.x, ++it) {
+        mbar_wait(&empty_bar[it % STAGES], (uint32_t)(((it / STAGES) & 1) ^ 1));
+        tma_unit(u, it);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(p.fmt, 64, 256);
+      const uint32_t idesc_o = make_idesc_f16(p.fmt, 64, D) | (1u << 16);   // B operand (V) is MN-major
+      auto issue_pv = [&](int j) {
+        const int stage = j % STAGES;
+        mbar_wait(p_full, (uint32_t)(j & 1));
+        mbar_wait(o_empty, (uint32_t)((j & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t va = smem_u32(stages + stage * S::STAGE + S::Q_TILE + S::KV_TILE);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t d_o = tmem_base + O_COL0 + ((uint32_t)(16 * t) << 16);
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            const uint64_t da0 = make_smem_desc_sw128(smem_u32(p_tiles + (t * 4 + kb) * S::P_BLK));
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_f16(d_o, advance_desc_k(da0, ks), a2_desc_rowD<D>(va + (uint32_t)((kb * 64 + ks * 16) * D * 2)), idesc_o,
+                       (kb | ks) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(p_empty);
+        umma_commit(o_full);
+      };
+      int it = 0;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+        const int stage = it % STAGES;
+        mbar_wait(&full_bar[stage], (uint32_t)((it / STAGES) & 1));
+        mbar_wait(s_empty, (uint32_t)((it & 1) ^ 1));
+        tc_fence_after();
+        const uint8_t* st = stages + stage * S::STAGE;
+        const uint64_t dk = a2_desc_rowD<D>(smem_u32(st + S::Q_TILE));
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint64_t dq = a2_desc_rowD<D>(smem_u32(st) + (uint32_t)(t * 64 * D * 2));
+          const uint32_t d_s = tmem_base + ((uint32_t)(16 * t) << 16);
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k) umma_f16(d_s, advance_desc_k(dq, k), advance_desc_k(dk, k), idesc_s, k ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        if (it > 0) issue_pv(it - 1);
+      }
+      if (it > 0) issue_pv(it - 1);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int half = lane >> 4, r16 = lane & 15;
+    const int row_half = quarter * 16 + r16;
+    const int row = half * 64 + row_half;
+    const int swz = row_half & 7;
+    T* out = reinterpret_cast<T*>(p.out);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* const prow = p_tiles + half * 4 * S::P_BLK + (row_half >> 3) * 1024 + swz * 128;
+    auto epilogue = [&](int j, T* dst, float inv_row) {
+      mbar_wait(o_full, (uint32_t)(j & 1));
+      tc_fence_after();
+      uint32_t o[32];
+      if constexpr (D == 16) tmem_ld_32x16(lane_addr + O_COL0, o);
+      else tmem_ld_32x32(lane_addr + O_COL0, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        uint4 v;
+        v.x = pack2<T>(__uint_as_float(o[c + 0]) * inv_row, __uint_as_float(o[c + 1]) * inv_row);
+        v.y = pack2<T>(__uint_as_float(o[c + 2]) * inv_row, __uint_as_float(o[c + 3]) * inv_row);
+        v.z = pack2<T>(__uint_as_float(o[c + 4]) * inv_row, __uint_as_float(o[c + 5]) * inv_row);
+        v.w = pack2<T>(__uint_as_float(o[c + 6]) * inv_row, __uint_as_float(o[c + 7]) * inv_row);
+        *reinterpret_cast<uint4*>(dst + c) = v;
+      }
+    };
+    int it = 0;
+    float inv_prev = 1.f;
+    T* dst_prev = nullptr;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+      int gi, tile, head;
+      decode(u, gi, tile, head);
+      const int n = (tile & 1) * 128 + row;                  // position within the 16 x 16 window
+      const int i_n = n >> 4, j_n = n & 15;
+      const float* tb = s_tab + (gi * p.hpg + head) * W16_TAB_STRIDE + (i_n + 15) * 31 + (j_n + 15);
+      T* dst = out + ((long long)tile * 128 + row) * p.C + p.gid[gi] * p.cg + head * D;
+      unsigned long long drop_base = 0ull;
+      if constexpr (DROP) {
+        const int b_img = (int)__umulhi((uint32_t)tile, p.tpi_magic);
+        const int p_img = (tile - b_img * p.tpi) * 128 + row;
+        drop_base = ((((unsigned long long)b_img * p.G_all + p.gid[gi]) * p.hpg + head) * p.L + p_img) * 256ull;
+      }
+      const float scale = p.scale;
+      mbar_wait(s_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {                          // pass 1: row maximum
+        uint32_t r[32];
+        tmem_ld_32x32(lane_addr + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        const float* tc_ = tb - c * 62;                      // keys 32c .. 32c+31 = window rows 2c, 2c+1
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int m = 0; m < 32; ++m) m4[m & 3] = fmaxf(m4[m & 3], fmaf(__uint_as_float(r[m]), scale, tc_[-((m >> 4) * 31 + (m & 15))]));
+        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      }
+      mbar_wait(p_empty, (uint32_t)((it & 1) ^ 1));          // the P*V that last read the P buffer has retired
+      float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {                          // pass 2: exp, sum, P
+        uint32_t r[32];
+        tmem_ld_32x32(lane_addr + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        const float* tc_ = tb - c * 62;
+        uint8_t* blk = prow + (c >> 1) * S::P_BLK;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float e[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int m = q * 8 + k;
+            e[k] = ex2_fast(fmaf(__uint_as_float(r[m]), scale, tc_[-((m >> 4) * 31 + (m & 15))]) - mx);
+            d4[k & 3] += e[k];
+            if constexpr (DROP) {
+              const float uu = (float)(dpmn_hash32(p.seed, p.site, drop_base + (unsigned long long)(c * 32 + m)) >> 8) * (1.0f / 16777216.0f);
+              e[k] = uu >= p.p_drop ? e[k] : 0.f;
+            }
+          }
+          uint4 v;
+          v.x = pack2<T>(e[0], e[1]); v.y = pack2<T>(e[2], e[3]); v.z = pack2<T>(e[4], e[5]); v.w = pack2<T>(e[6], e[7]);
+          const int cc = (c & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(blk + ((cc ^ swz) << 4)) = v;
+        }
+      }
+      // S has been read twice: hand the accumulator back, publish P
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(p_full); }
+      const float den = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+      if (it > 0) epilogue(it - 1, dst_prev, inv_prev);
+      inv_prev = DROP ? p.keep_inv / den : 1.0f / den;
+      dst_prev = dst;
+    }
+    if (it > 0) epilogue(it - 1, dst_prev, inv_prev);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 }  // namespace
 
 // ---- host ---------------------------------------------------------------------------------------------------
+static int attn2_maps(const AttnTcArgs& a, int D, int kv_rows, CUtensorMap* maps) {
+  const void* bases[3] = {a.qw, a.kw, a.vw};
+  const int cg = a.C / a.n_groups;
+  const long long rows = (long long)a.B * a.H * a.W;
+  for (int i = 0; i < 3; ++i) {
+    const uint64_t dims[3] = {(uint64_t)cg, (uint64_t)rows, (uint64_t)a.n_groups};
+    const uint64_t str[2] = {(uint64_t)cg * 2, (uint64_t)rows * cg * 2};
+    const uint32_t box[3] = {(uint32_t)D, (uint32_t)(i == 0 ? A2_ROWS : kv_rows), 1};
+    int rc = make_tensor_map_16bit(&maps[i], bases[i], 3, dims, str, box,
+                                   D == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// groups with windows 2 / 4 / 8
 template <int D, int HC, int STAGES, typename T, bool DROP>
 static int launch_attn2_t(const AttnTcArgs& a, cudaStream_t st) {
   Attn2Params p;
   memset(&p, 0, sizeof(p));
-  p.L = a.H * a.W; p.C = a.C; p.G = a.n_groups; p.hpg = a.heads_per_group;
+  p.L = a.H * a.W; p.C = a.C; p.G_all = a.n_groups; p.hpg = a.heads_per_group;
   p.cg = a.C / a.n_groups;
-  p.tiles = a.B * p.L / A2_ROWS; p.nhc = a.heads_per_group / HC; p.upg = p.tiles * p.nhc; p.total_units = p.upg * p.G;
-  p.tpi = p.L / A2_ROWS; p.tpi_magic = (uint32_t)((0x100000000ull + p.tpi - 1) / p.tpi);
-  for (int g = 0; g < a.n_groups; ++g) {
-    const int ws = a.window[g], N = ws * ws, cut = ws - a.shift[g];
-    p.ws[g] = ws; p.shift[g] = a.shift[g]; p.table[g] = a.table[g]; p.order[g] = g; p.cut[g] = cut;
+  for (int ga = 0; ga < a.n_groups; ++ga) {
+    if (a.window[ga] > 8) continue;
+    const int g = p.G++;
+    const int ws = a.window[ga], N = ws * ws, cut = ws - a.shift[ga];
+    p.gid[g] = ga; p.ws[g] = ws; p.shift[g] = a.shift[ga]; p.table[g] = a.table[ga]; p.order[g] = g; p.cut[g] = cut;
     p.nww[g] = a.W / ws; p.nww_magic[g] = (uint32_t)((0x100000000ull + p.nww[g] - 1) / p.nww[g]);
     p.lastrow_w0[g] = p.L / N - p.nww[g];
     const unsigned long long rep = ws == 8 ? 0x0101010101010101ull : (ws == 4 ? 0x1111ull : 0x5ull);
@@ -501,21 +780,15 @@ static int launch_attn2_t(const AttnTcArgs& a, cudaStream_t st) {
     p.rows_lo[g] = cut * ws >= 64 ? ~0ull : (1ull << (cut * ws)) - 1ull;   // (only read when shift >= 1)
     p.cols_lo[g] = ((1ull << cut) - 1ull) * rep & p.all_keys[g];
   }
-  for (int i = 1; i < a.n_groups; ++i)                          // heaviest (largest window) groups first
+  if (p.G == 0) return 0;
+  p.tiles = a.B * p.L / A2_ROWS; p.nhc = a.heads_per_group / HC; p.upg = p.tiles * p.nhc; p.total_units = p.upg * p.G;
+  p.tpi = p.L / A2_ROWS; p.tpi_magic = (uint32_t)((0x100000000ull + p.tpi - 1) / p.tpi);
+  for (int i = 1; i < p.G; ++i)                                 // heaviest (largest window) groups first
     for (int j = i; j > 0 && p.ws[p.order[j]] > p.ws[p.order[j - 1]]; --j) { const int t = p.order[j]; p.order[j] = p.order[j - 1]; p.order[j - 1] = t; }
   p.out = a.out; p.fmt = a.io_type == DT_BF16 ? 1 : 0; p.scale = 1.4426950408889634f / sqrtf((float)D);   // d^-0.5 * log2(e)
   p.p_drop = a.p_drop; p.keep_inv = a.p_drop > 0.f ? 1.0f / (1.0f - a.p_drop) : 1.0f; p.seed = a.seed; p.site = a.site;
   CUtensorMap maps[3];
-  const void* bases[3] = {a.qw, a.kw, a.vw};
-  const long long rows = (long long)a.B * p.L;
-  for (int i = 0; i < 3; ++i) {
-    const uint64_t dims[3] = {(uint64_t)p.cg, (uint64_t)rows, (uint64_t)p.G};
-    const uint64_t str[2] = {(uint64_t)p.cg * 2, (uint64_t)rows * p.cg * 2};
-    const uint32_t box[3] = {(uint32_t)D, A2_ROWS, 1};
-    int rc = make_tensor_map_16bit(&maps[i], bases[i], 3, dims, str, box,
-                                   D == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc) return rc;
-  }
+  if (int rc = attn2_maps(a, D, A2_ROWS, maps)) return rc;
   int num_sms = 0;
   DPMN_CUDA_TRY(current_device_sms(&num_sms));
   const int grid = p.total_units < 2 * num_sms ? p.total_units : 2 * num_sms;
@@ -529,6 +802,35 @@ static int launch_attn2_t(const AttnTcArgs& a, cudaStream_t st) {
   return 0;
 }
 
+// groups with window 16
+template <int D, typename T, bool DROP>
+static int launch_attn2_w16_t(const AttnTcArgs& a, cudaStream_t st) {
+  AttnW16Params p;
+  memset(&p, 0, sizeof(p));
+  p.L = a.H * a.W; p.C = a.C; p.G_all = a.n_groups; p.hpg = a.heads_per_group; p.cg = a.C / a.n_groups;
+  for (int ga = 0; ga < a.n_groups; ++ga)
+    if (a.window[ga] == 16) { p.gid[p.n_g] = ga; p.table[p.n_g] = a.table[ga]; ++p.n_g; }
+  if (p.n_g == 0) return 0;
+  p.tiles = a.B * p.L / 128; p.upg = p.tiles * p.hpg; p.total_units = p.upg * p.n_g;
+  p.tpi = p.L / 128; p.tpi_magic = (uint32_t)((0x100000000ull + p.tpi - 1) / p.tpi);
+  p.out = a.out; p.fmt = a.io_type == DT_BF16 ? 1 : 0; p.scale = 1.4426950408889634f / sqrtf((float)D);
+  p.p_drop = a.p_drop; p.keep_inv = a.p_drop > 0.f ? 1.0f / (1.0f - a.p_drop) : 1.0f; p.seed = a.seed; p.site = a.site;
+  CUtensorMap maps[3];
+  if (int rc = attn2_maps(a, D, 256, maps)) return rc;
+  int num_sms = 0;
+  DPMN_CUDA_TRY(current_device_sms(&num_sms));
+  const int grid = p.total_units < num_sms ? p.total_units : num_sms;
+  constexpr int STAGES = 2;
+  auto kern = attn2_w16_kernel<D, STAGES, T, DROP>;
+  constexpr int smem = W16Smem<D, STAGES>::TOTAL;
+  static_assert(smem <= 232448, "shared memory per CTA");
+  static PerDeviceOnce attr;
+  DPMN_CUDA_TRY(attr.smem_attr(kern, smem));
+  kern<<<grid, 192, smem, st>>>(maps[0], maps[1], maps[2], p);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
 bool attn2_tc_supported(const AttnTcArgs& a) {
   if (a.io_type != DT_F16 && a.io_type != DT_BF16) return false;
   if (a.n_groups < 1 || a.n_groups > 4 || a.C % a.n_groups) return false;
@@ -537,14 +839,18 @@ bool attn2_tc_supported(const AttnTcArgs& a) {
   const int d = cg / a.heads_per_group;
   if (d != 16 && d != 32) return false;
   if ((a.H * a.W) % A2_ROWS) return false;
-  if (a.n_groups * a.heads_per_group * A2_TAB_STRIDE > A2_TAB_FLOATS) return false;
   if (a.p_drop < 0.f || a.p_drop >= 1.f) return false;
+  int n_small = 0, n_16 = 0;
   for (int g = 0; g < a.n_groups; ++g) {
     const int ws = a.window[g];
-    if (ws != 2 && ws != 4 && ws != 8) return false;
+    if (ws != 2 && ws != 4 && ws != 8 && ws != 16) return false;
     if (a.H % ws || a.W % ws) return false;
     if (a.shift[g] < 0 || a.shift[g] >= ws) return false;
+    if (ws == 16) { if (a.shift[g] != 0 || (a.H * a.W) % 256) return false; ++n_16; }   // a 16-window is only supported unshifted
+    else ++n_small;
   }
+  if (n_small * a.heads_per_group * A2_TAB_STRIDE > A2_TAB_FLOATS) return false;
+  if (n_16 * a.heads_per_group > W16_MAX_HEADS) return false;
   return true;
 }
 
@@ -552,10 +858,14 @@ template <typename T>
 static int launch_attn2_dtype(const AttnTcArgs& a, cudaStream_t st) {
   const int d = a.C / a.n_groups / a.heads_per_group;
   const bool drop = a.p_drop > 0.f;
+  int rc;
   if (d == 16 && a.heads_per_group % 2 == 0)
-    return drop ? launch_attn2_t<16, 2, 3, T, true>(a, st) : launch_attn2_t<16, 2, 3, T, false>(a, st);
-  if (d == 16) return drop ? launch_attn2_t<16, 1, 3, T, true>(a, st) : launch_attn2_t<16, 1, 3, T, false>(a, st);
-  return drop ? launch_attn2_t<32, 1, 3, T, true>(a, st) : launch_attn2_t<32, 1, 3, T, false>(a, st);
+    rc = drop ? launch_attn2_t<16, 2, 3, T, true>(a, st) : launch_attn2_t<16, 2, 3, T, false>(a, st);
+  else if (d == 16) rc = drop ? launch_attn2_t<16, 1, 3, T, true>(a, st) : launch_attn2_t<16, 1, 3, T, false>(a, st);
+  else rc = drop ? launch_attn2_t<32, 1, 3, T, true>(a, st) : launch_attn2_t<32, 1, 3, T, false>(a, st);
+  if (rc) return rc;
+  if (d == 16) return drop ? launch_attn2_w16_t<16, T, true>(a, st) : launch_attn2_w16_t<16, T, false>(a, st);
+  return drop ? launch_attn2_w16_t<32, T, true>(a, st) : launch_attn2_w16_t<32, T, false>(a, st);
 }
 
 int launch_window_attn2_tc(const AttnTcArgs& a, cudaStream_t st) {

@@ -338,6 +338,7 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
   };
   if (warp == 0 && lane == 0) {
+    pdl_wait();                                        // Q / K / V are the predecessor's outputs
     int it = 0;
     for (int u = blockIdx.x; u < p.total_units && it < STAGES; u += gridDim.x, ++it) tma_unit(u, it);
   }
@@ -345,6 +346,8 @@ attn2_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   // units are ordered group-major, so a CTA's consecutive units mostly share the window size (the P zero pattern)
   if (warp == 0) {
@@ -563,6 +566,7 @@ attn2_w16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       mbar_init(p_full, 4); mbar_init(p_empty, 1);
       mbar_init(o_full, 1); mbar_init(o_empty, 4);
       fence_barrier_init();
+      pdl_wait();
       int it = 0;
       for (int u = blockIdx.x; u < p.total_units && it < STAGES; u += gridDim.x, ++it) tma_unit(u, it);
     }
@@ -579,6 +583,8 @@ attn2_w16_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -797,7 +803,7 @@ static int launch_attn2_t(const AttnTcArgs& a, cudaStream_t st) {
   static_assert(smem <= 115712, "two CTAs per SM");
   static PerDeviceOnce attr;      // per template instantiation, per device
   DPMN_CUDA_TRY(attr.smem_attr(kern, smem));
-  kern<<<grid, 64 + HC * 128, smem, st>>>(maps[0], maps[1], maps[2], p);
+  DPMN_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(64 + HC * 128), smem, st, maps[0], maps[1], maps[2], p));
   DPMN_LAUNCH_CHECK();
   return 0;
 }
@@ -826,7 +832,7 @@ static int launch_attn2_w16_t(const AttnTcArgs& a, cudaStream_t st) {
   static_assert(smem <= 232448, "shared memory per CTA");
   static PerDeviceOnce attr;
   DPMN_CUDA_TRY(attr.smem_attr(kern, smem));
-  kern<<<grid, 192, smem, st>>>(maps[0], maps[1], maps[2], p);
+  DPMN_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(192), smem, st, maps[0], maps[1], maps[2], p));
   DPMN_LAUNCH_CHECK();
   return 0;
 }

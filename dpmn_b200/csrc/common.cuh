@@ -18,6 +18,7 @@
   } while (0)
 
 #include <atomic>
+#include <cstdlib>
 
 namespace dpmn {
 
@@ -54,6 +55,26 @@ inline cudaError_t current_device_sms(int* sms) {
   }
   *sms = v;
   return cudaSuccess;
+}
+
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait / pdl_trigger in tc_common.cuh).  Only kernels
+// whose every predecessor-dependent access sits behind pdl_wait() may be launched this way.  Opt-in (DPMN_PDL=1): measured
+// on B200 (profiles/r02_pdl_ab.md) it shortens back-to-back launches of one stream (stand-alone attention 7.2 -> 6.0 us at
+// batch 8) but LENGTHENS the three-stream, two-slot graph of the pipelined forward (2.48 -> 2.59 ms per batch): the
+// pre-launched CTAs hold shared memory that the other streams' kernels would have used.
+inline bool pdl_enabled() {
+  static const bool on = getenv("DPMN_PDL") && atoi(getenv("DPMN_PDL")) != 0;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 __device__ __forceinline__ float gelu_erf(float x) {

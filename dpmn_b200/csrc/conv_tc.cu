@@ -115,6 +115,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // everything above overlapped the predecessor's tail; its outputs are visible from here on
+  pdl_trigger();
 
   // tile index -> (n block, pixel-tile origin, parity class, group); n fastest so neighbours share the A boxes in L2
 #define DPMN_DECODE_TILE(t)                                   \
@@ -289,7 +291,7 @@ static int launch_conv_bn(const ConvTcArgs& a, cudaStream_t st) {
   constexpr int smem = ConvSmem<BN>::TOTAL;
   static PerDeviceOnce attr;      // per template instantiation, per device
   DPMN_CUDA_TRY(attr.smem_attr(kern, smem));
-  kern<<<grid, CONV_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], map_w, p);
+  DPMN_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(CONV_THREADS), smem, st, maps[0], maps[1], maps[2], maps[3], map_w, p));
   DPMN_LAUNCH_CHECK();
   return 0;
 }

@@ -116,6 +116,8 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // everything above overlapped the predecessor's tail; its outputs are visible from here on
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -337,7 +339,7 @@ static int launch_res_bn(const GemmTcArgs& a, cudaStream_t st) {
   constexpr int smem = ResSmem<BN>::TOTAL;
   static PerDeviceOnce attr;      // per template instantiation, per device
   DPMN_CUDA_TRY(attr.smem_attr(kern, smem));
-  kern<<<grid, RTHREADS, smem, st>>>(map_a, map_b, map_r, map_c, map_y, p);
+  DPMN_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(RTHREADS), smem, st, map_a, map_b, map_r, map_c, map_y, p));
   DPMN_LAUNCH_CHECK();
   return 0;
 }

@@ -98,6 +98,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // everything above overlapped the predecessor's tail; its outputs are visible from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -457,7 +459,7 @@ static int launch_tc_bn(const GemmTcArgs& a, cudaStream_t st, const GemmTcArgs* 
   constexpr int smem = TcSmem<BN>::TOTAL;
   static PerDeviceOnce attr;      // per template instantiation, per device
   DPMN_CUDA_TRY(attr.smem_attr(kern, smem));
-  kern<<<grid, 64 + 32 * EW, smem, st>>>(map_a, map_b, map_a2, map_b2, p, p2, tiles0, tiles1);
+  DPMN_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(64 + 32 * EW), smem, st, map_a, map_b, map_a2, map_b2, p, p2, tiles0, tiles1));
   DPMN_LAUNCH_CHECK();
   return 0;
 }

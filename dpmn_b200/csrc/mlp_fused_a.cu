@@ -151,6 +151,8 @@ mlp_fc1_dw_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // everything above overlapped the predecessor's tail; its outputs are visible from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -341,7 +343,7 @@ int launch_mlp_a(const void* x16, const void* w16, const float* fc1_b, const flo
   auto kern = mlp_fc1_dw_kernel<T>;
   static PerDeviceOnce attr;      // per template instantiation, per device
   DPMN_CUDA_TRY(attr.smem_attr(kern, MA_SMEM));
-  kern<<<p.tiles < sms ? p.tiles : sms, MA_THREADS, MA_SMEM, st>>>(map_x, map_w, p);
+  DPMN_CUDA_TRY(launch_pdl(kern, dim3(p.tiles < sms ? p.tiles : sms), dim3(MA_THREADS), MA_SMEM, st, map_x, map_w, p));
   DPMN_LAUNCH_CHECK();
   return 0;
 }

@@ -857,6 +857,8 @@ __global__ void __launch_bounds__(256) sk_gate_c96_kernel(const float* __restric
   constexpr int C = 96, CG = 32, DZ = 16, PER = C * C / 4, ITERS = PER / 256;   // 2304 folded weights per CTA, 9 per thread
   __shared__ float sS[C], sZ[DZ], sA[C];
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  asm volatile("griddepcontrol.wait;" ::: "memory");                 // PDL (tc_common.cuh): colsum is the predecessor's output
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // ---- all global loads up front
   float cs = 0.f;
   if (t < C) {
@@ -934,8 +936,8 @@ template <typename WT>
 static void launch_sk_gate_c96(const float* colsum, int tiles, int L, const float* wp, const float* bp, const float* w1,
                                const float* b1, const float* w2, const float* b2, const float* wh, const float* bh,
                                void* wb_out, float* bias_out, int B, cudaStream_t st) {
-  sk_gate_c96_kernel<WT><<<dim3(B, 4), 256, 0, st>>>(colsum, tiles, 1.0f / (float)L, wp, bp, w1, b1, w2, b2, wh, bh,
-                                                     (WT*)wb_out, bias_out);
+  launch_pdl(sk_gate_c96_kernel<WT>, dim3(B, 4), dim3(256), 0, st, colsum, tiles, 1.0f / (float)L, wp, bp, w1, b1, w2, b2, wh, bh,
+             (WT*)wb_out, bias_out);
 }
 
 int launch_sk_gate(const float* colsum, int tiles_per_image, int L, const float* wp, const float* bp,

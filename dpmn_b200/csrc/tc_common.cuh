@@ -60,6 +60,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// A kernel launched with launch_pdl (common.cuh) may start while its stream predecessor is still running: everything
+// before pdl_wait() (barrier initialisation, TMEM allocation, descriptor prefetch, staging of WEIGHTS) overlaps the
+// predecessor's tail; pdl_wait() returns once the predecessor grid has completed and its writes are visible.
+// pdl_trigger() lets the NEXT kernel of the stream do the same with us; it is issued after our own wait, so at most one
+// dependent grid is ever pre-launched.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- TMA ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -172,8 +172,12 @@ struct AttnBwdArgs {
   int B = 0, H = 0, W = 0, C = 0, n_groups = 0, heads_per_group = 0;
   int window[4] = {}, shift[4] = {};
   float p_drop = 0.f; unsigned long long seed = 0; uint32_t site = 0;   // the forward's attn_drop masks
+  int round16 = 0;                                         // 1 fp16 / 2 bf16: the forward was the tcgen05 kernel (16-bit q, k, v, P)
 };
 int launch_window_attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
+// fp32 token-order q (rows, C) / kv (rows, 2C) -> window-major 16-bit [G][rows][C/G] operands of the tcgen05 attention
+int launch_window_scatter16(const float* q, const float* kv, void* qw, void* kw, void* vw, DType t, int B, int H, int W, int C,
+                            int G, const int* ws, const int* shift, cudaStream_t st);
 
 // S = mean_L GELU(F); zpre = fc1 S + b1; a = softmax_G(fc2 GELU(zpre) + b2); Xs = sum_m a_m * A_m
 int launch_sk_train_fwd(const float* F, const float* A, const float* w1, const float* b1, const float* w2,

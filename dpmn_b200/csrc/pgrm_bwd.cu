@@ -22,7 +22,10 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(
     const float* __restrict__ q, const float* __restrict__ kv, const float* __restrict__ d_attn,
     float* __restrict__ dq, float* __restrict__ dkv, const float* __restrict__ table, float* __restrict__ d_table,
     int C, int hpg, int ch0, int D, int H, int W, int ws, int shift, float scale, float p_drop, unsigned long long seed,
-    uint32_t site, int g_index, int G) {
+    uint32_t site, int g_index, int G, int rnd) {
+  // rnd (1 fp16, 2 bf16): the forward ran on the tcgen05 kernel, which read q / k / v as 16-bit values and rounded the
+  // unnormalised probabilities to 16 bits (attn2_tc.cu); P is recomputed from the same rounded values here
+  auto r16 = [rnd](float x) { return rnd == 1 ? __half2float(__float2half_rn(x)) : (rnd == 2 ? __bfloat162float(__float2bfloat16_rn(x)) : x); };
   extern __shared__ float sm[];
   const int N = ws * ws, NS = N + 1, L = H * W, DS = D + 1, tw = 2 * ws - 1, TT = tw * tw;
   float* sQ = sm;                       // [64][DS]
@@ -52,9 +55,9 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(
   for (int i = tid; i < AB_ROWS * D; i += 128) {
     const int r = i / D, e = i - r * D;
     const long long tok = (long long)b * L + sTok[r];
-    sQ[r * DS + e] = q[tok * C + ch + e];
-    sK[r * DS + e] = kv[tok * 2 * C + ch + e];
-    sV[r * DS + e] = kv[tok * 2 * C + C + ch + e];
+    sQ[r * DS + e] = r16(q[tok * C + ch + e]);
+    sK[r * DS + e] = r16(kv[tok * 2 * C + ch + e]);
+    sV[r * DS + e] = r16(kv[tok * 2 * C + C + ch + e]);
     sO[r * DS + e] = d_attn[((long long)b * L + row0 + r) * C + ch + e];
   }
   __syncthreads();
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(
     float mx = -INFINITY;
     for (int m = 0; m < N; ++m) mx = fmaxf(mx, pr[m]);
     float den = 0.f;
-    for (int m = 0; m < N; ++m) { const float e = expf(pr[m] - mx); pr[m] = e; den += e; }
+    for (int m = 0; m < N; ++m) { const float e = expf(pr[m] - mx); pr[m] = r16(e); den += e; }
     const float inv = 1.0f / den;
     float dot = 0.f;
     for (int m = 0; m < N; ++m) { pr[m] *= inv; dot = fmaf(pr[m], dr[m], dot); }
@@ -134,7 +137,7 @@ int launch_window_attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
     dim3 grid(L / AB_ROWS, a.heads_per_group, a.B);
     window_attn_bwd_kernel<<<grid, 128, smem, st>>>(a.q, a.kv, a.d_attn, a.dq, a.dkv, a.table[g], a.d_table[g], a.C,
                                                     a.heads_per_group, g * cg, D, a.H, a.W, ws, a.shift[g],
-                                                    1.0f / sqrtf((float)D), a.p_drop, a.seed, a.site, g, a.n_groups);
+                                                    1.0f / sqrtf((float)D), a.p_drop, a.seed, a.site, g, a.n_groups, a.round16);
     DPMN_LAUNCH_CHECK();
   }
   return 0;
@@ -1054,6 +1057,66 @@ int launch_head_bwd(const HeadBwdArgs& h, cudaStream_t st) {
     conv3x3_small_dgrad_kernel<<<592, 256, smem, st>>>(h.dt1, h.w1, h.d_tokens, h.B, h.gh, h.gw, h.C, hp, h.C);
     DPMN_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+// =====================================================================================================================
+// Training forward, 16-bit modes: fp32 token-order q (rows, C) / kv (rows, 2C) -> the window-major 16-bit operands
+// [G][rows][cg] of the tcgen05 attention kernel (roll + window_partition, pgrm.py:209-225).  One thread per 8 channels
+// of one window-major row: 3 x 32-byte reads, 3 x 16-byte writes.
+// =====================================================================================================================
+struct ScatterGeom { int ws[4], shift[4]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) window_scatter16_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                               T* __restrict__ qw, T* __restrict__ kw, T* __restrict__ vw,
+                                                               long long rows, int L, int H, int W, int C, int G,
+                                                               ScatterGeom geo) {
+  const int cg = C / G, c8 = cg / 8;
+  const long long total = (long long)G * rows * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c8);
+    const long long rp = i / c8;
+    const long long p = rp % rows;
+    const int g = (int)(rp / rows);
+    const long long b = p / L;
+    const int p_img = (int)(p - b * L);
+    const int tok = window_row_to_token(p_img, H, W, geo.ws[g], geo.shift[g]).token;
+    const long long src_row = b * L + tok;
+    const int c = g * cg + ch * 8;
+    const float4* sq = reinterpret_cast<const float4*>(q + src_row * C + c);
+    const float4* sk = reinterpret_cast<const float4*>(kv + src_row * 2 * C + c);
+    const float4* sv = reinterpret_cast<const float4*>(kv + src_row * 2 * C + C + c);
+    const float4 a0 = sq[0], a1 = sq[1], k0 = sk[0], k1 = sk[1], v0 = sv[0], v1 = sv[1];
+    auto pack = [](const float4& x, const float4& y) {
+      union { uint4 u; T h[8]; } o;
+      o.h[0] = from_f32<T>(x.x); o.h[1] = from_f32<T>(x.y); o.h[2] = from_f32<T>(x.z); o.h[3] = from_f32<T>(x.w);
+      o.h[4] = from_f32<T>(y.x); o.h[5] = from_f32<T>(y.y); o.h[6] = from_f32<T>(y.z); o.h[7] = from_f32<T>(y.w);
+      return o.u;
+    };
+    const long long dst = ((long long)g * rows + p) * cg + ch * 8;
+    *reinterpret_cast<uint4*>(qw + dst) = pack(a0, a1);
+    *reinterpret_cast<uint4*>(kw + dst) = pack(k0, k1);
+    *reinterpret_cast<uint4*>(vw + dst) = pack(v0, v1);
+  }
+}
+
+int launch_window_scatter16(const float* q, const float* kv, void* qw, void* kw, void* vw, DType t, int B, int H, int W, int C,
+                            int G, const int* ws, const int* shift, cudaStream_t st) {
+  if (t != DT_F16 && t != DT_BF16) return -2;
+  if (G < 1 || G > 4 || C % G || (C / G) % 8) return -2;
+  ScatterGeom geo;
+  for (int g = 0; g < 4; ++g) { geo.ws[g] = g < G ? ws[g] : 1; geo.shift[g] = g < G ? shift[g] : 0; }
+  const int L = H * W;
+  const long long rows = (long long)B * L;
+  const long long total = (long long)G * rows * (C / G / 8);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (t == DT_F16)
+    window_scatter16_kernel<__half><<<blocks, 256, 0, st>>>(q, kv, (__half*)qw, (__half*)kw, (__half*)vw, rows, L, H, W, C, G, geo);
+  else
+    window_scatter16_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(q, kv, (__nv_bfloat16*)qw, (__nv_bfloat16*)kw,
+                                                                   (__nv_bfloat16*)vw, rows, L, H, W, C, G, geo);
+  DPMN_LAUNCH_CHECK();
   return 0;
 }
 

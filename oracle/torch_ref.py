@@ -125,19 +125,34 @@ def window_attention_core(q, kv, tables, windows, shifts, H, W, hpg, drop=None, 
 
         def part(x):
             return x[:, order][..., sl].reshape(B, nW, N, hpg, d).permute(0, 1, 3, 2, 4)
-        s = (part(q) * d ** -0.5) @ part(k_all).transpose(-1, -2)
+        # OPERAND_ROUND (16-bit training emulation): the tcgen05 kernel reads q, k, v as 16-bit values, rounds the
+        # UNNORMALISED probabilities exp(s - max) to 16 bits for the P V product, divides by the fp32 row sum afterwards and
+        # stores a 16-bit result (csrc/attn2_tc.cu)
+        qg, kg, vg = _r(part(q)), _r(part(k_all)), _r(part(v_all))
+        s = (qg * d ** -0.5) @ kg.transpose(-1, -2)
         bias = tables[g][_rel_index(ws).reshape(-1)].view(N, N, hpg).permute(2, 0, 1)
         s = s + bias[None, None]
         if sh > 0:
             s = s + _shift_mask(H, W, ws, sh)[None, :, None]
-        prob = torch.softmax(s, dim=-1)
+        keep = None
         if drop is not None and drop[0] > 0:                      # attn_drop, pgrm.py:248
             import numpy as np
             b_i, w_i, h_i, n_i, m_i = np.meshgrid(np.arange(B), np.arange(nW), np.arange(hpg), np.arange(N), np.arange(N),
                                                   indexing="ij")
             idx = ((((b_i * G + g) * hpg + h_i) * L + w_i * N + n_i) * N + m_i).astype(np.uint64)
-            prob = prob * drop_scale(drop[0], drop[1], site, idx)
-        o = prob @ part(v_all)
+            keep = drop_scale(drop[0], drop[1], site, idx)
+        if OPERAND_ROUND is None:
+            prob = torch.softmax(s, dim=-1)
+            if keep is not None:
+                prob = prob * keep
+            o = prob @ vg
+        else:
+            e = torch.exp(s - s.amax(dim=-1, keepdim=True).detach())
+            den = e.sum(dim=-1, keepdim=True)
+            e = _r(e)
+            if keep is not None:
+                e = e * keep
+            o = _r((e @ vg) / den)
         outs.append(o.permute(0, 1, 3, 2, 4).reshape(B, L, cg))
     return torch.cat(outs, dim=-1)
 

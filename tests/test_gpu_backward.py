@@ -241,7 +241,7 @@ def test_pgrm_train_mode_dropout_droppath_forward_and_backward(name, rates):
     assert torch.equal(y3, y.detach())
 
 
-@pytest.mark.parametrize("precision,l2_tol,cos_min", [("fp16", 3e-2, 0.999), ("bf16", 1e-1, 0.99)])
+@pytest.mark.parametrize("precision,l2_tol,cos_min", [("fp16", 5e-2, 0.999), ("bf16", 1e-1, 0.99)])
 def test_pgrm_backward_tensor_core_gemms(precision, l2_tol, cos_min):
     """16-bit modes: the GEMMs of the training forward sequence and every Linear / pointwise-conv data and weight
     gradient run on the tcgen05 GEMM with 16-bit staged operands and fp32 accumulation (the rest of the backward stays
@@ -249,7 +249,11 @@ def test_pgrm_backward_tensor_core_gemms(precision, l2_tol, cos_min):
     LeakyReLU(0.01) inputs that sit next to 0 -- each flip changes that element's derivative 100-fold (measured: the
     same gradients are within 3e-3 max-norm when only the backward GEMMs are 16-bit, and individual tensors move by up
     to 8e-2 max-norm once a forward GEMM is, whichever GEMM it is).  The bar is therefore the flip-tolerant one of the
-    whole-path test: relative L2 error and cosine per gradient tensor against the reference's fp32 gradients."""
+    whole-path test: relative L2 error and cosine per gradient tensor against the reference's fp32 gradients.
+    (With the attention core on the tcgen05 kernel as well -- 16-bit q / k / v / P -- the 12-element bias gradient of the
+    head's second conv, a plain sum over those LeakyReLU derivatives, sits at 3.3e-2; every other tensor is below 3e-2.  The
+    TIGHT check of the 16-bit backward is test_pgrm_16bit_gradients_against_the_same_arithmetic_oracle below, where the
+    flips are excluded by construction.)"""
     z, meta = load_golden("pgrm_i2_m0_grad")
     cfg, P, x_q, x_kv, res = pgrm_case(meta)
     m, _ = build_pgrm(meta, "cuda", precision=precision)
@@ -324,14 +328,16 @@ def _l2_cos(got, want):
     return float(np.linalg.norm(got - want) / max(nw, 1e-30)), float(np.dot(got, want) / max(np.linalg.norm(got) * nw, 1e-30))
 
 
-@pytest.mark.parametrize("precision,fwd_tol,l2_tol", [("fp16", 5e-4, 2e-3), ("bf16", 4e-3, 1.6e-2)])
+@pytest.mark.parametrize("precision,fwd_tol,l2_tol", [("fp16", 5e-4, 2e-3), ("bf16", 4e-3, 2e-2)])
 def test_pgrm_16bit_gradients_against_the_same_arithmetic_oracle(precision, fwd_tol, l2_tol):
     """the loose 16-bit gradient bars compared a 16-bit forward with the reference's fp32 one, so every
     LeakyReLU / Dropout mask that flipped showed up as gradient error.  Here the oracle evaluates the SAME forward
     arithmetic -- operands of the tensor-core contractions rounded to 16 bits, fp32 everywhere else, the CUDA path's
     Dropout / DropPath masks (oracle/torch_ref.operand_rounding) -- so forward and masks coincide and what is measured is
     the backward itself: its 16-bit staged operands (relative rounding 2^-11 fp16 / 2^-8 bf16 per element, averaged over
-    K >= 96 terms).  Bars: relative L2 < 2e-3 (fp16) per gradient tensor, cosine > 0.9999."""
+    K >= 96 terms).  Bars: relative L2 < 2e-3 (fp16) per gradient tensor, cosine > 0.9999.  Since the attention core of the
+    16-bit training forward runs on the tcgen05 kernel (16-bit q / k / v / P, attn_drop inside the kernel), the oracle rounds
+    those operands too and the backward recomputes P from the rounded values: measured fp16 1.4e-3, bf16 1.6e-2."""
     from oracle import torch_ref
     z, meta = load_golden("pgrm_i2_m0_grad")
     cfg, P, x_q, x_kv, res = pgrm_case(meta)

@@ -484,6 +484,69 @@ def run_ours(args):
             graphed.launch(0).synchronize()
             timed_out = slot["out"].detach().float().cpu().numpy().copy()
 
+        # ---------- "PSN included" (SURVEY 8d config 2): the frozen TATT backbone in front of the hot path.  Per batch: TATT
+        # (torch / cuDNN operators replayed from a CUDA graph, dpmn_b200/psn.py) on the LR images + text prior -> its output is
+        # the hot path's image stream -> the hot-path graph.  Both run on the slot's stream; two slots are in flight.
+        psn_obj = None
+        if not args.no_psn:
+            from dpmn_b200.psn import TATT
+            from dpmn_b200.synth import synth_value
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            tatt = TATT()
+            tatt.load_state_dict({k: (v if k.endswith("pe.pe") else torch.from_numpy(np.asarray(synth_value(90, k, tuple(v.shape)))).to(v.dtype).reshape(v.shape))
+                                  for k, v in tatt.state_dict().items()}, strict=True)
+            tatt = tatt.to(dev)
+            lr_sets = []
+            for s in range(n_sets):
+                r = np.random.default_rng([1000 * rank + s, 41])
+                lr = r.uniform(0, 1, size=(B, 4, 16, 64)).astype(np.float32)
+                lr[:, 3] = lr[:, 3] > 0.5
+                tp = torch.softmax(torch.from_numpy(r.standard_normal((B, 37, 1, 26)).astype(np.float32)), dim=1)
+                lr_sets.append((torch.from_numpy(lr).to(dev), tp.to(dev)))
+
+            def run_with_psn(n, with_hot_path=True):
+                begin = torch.cuda.Event()
+                begin.record(torch.cuda.current_stream(dev))
+                for i in range(n):
+                    k = i % n_slots
+                    slot = graphed.slots[k]
+                    ds = dev_sets[i % n_sets]
+                    slot["stream"].wait_event(begin)
+                    with torch.cuda.stream(slot["stream"]):
+                        sr, _ = tatt.graphed(*lr_sets[i % n_sets], slot=k)
+                        if with_hot_path:
+                            slot["psn"].copy_(sr, non_blocking=True)
+                            for d_, s_ in zip(slot["p1"] + slot["p2"], ds[1] + ds[2]):
+                                d_.copy_(s_, non_blocking=True)
+                        else:
+                            slot["done"] = torch.cuda.Event()
+                            slot["done"].record(slot["stream"])
+                    if with_hot_path:
+                        graphed.launch(k)
+                for sl in graphed.slots:
+                    torch.cuda.current_stream(dev).wait_event(sl["done"])
+            run_with_psn(4)
+            run_with_psn(4, False)
+            barrier()
+            n_psn = max(10, args.steps // 2)
+            e0.record()
+            run_with_psn(n_psn, False)
+            e1.record()
+            barrier()
+            ms_psn = max_over_ranks(e0.elapsed_time(e1)) / n_psn
+            e0.record()
+            run_with_psn(n_psn)
+            e1.record()
+            barrier()
+            ms_both = max_over_ranks(e0.elapsed_time(e1)) / n_psn
+            psn_obj = {"model": "TATT = TSRN_TL_TRANS(scale 2, 5 SRBs, TP interpreter), frozen, eval, fp32 (TF32 off): torch / cuDNN "
+                                "operators replayed from a CUDA graph (dpmn_b200/psn.py; parity vs the reference: tests/test_psn.py)",
+                       "psn_ms_per_batch": ms_psn, "ms_per_step_psn_included": ms_both,
+                       "value_psn_included": B * world / (ms_both / 1e3), "unit": "images/s", "steps": n_psn,
+                       "inputs": "LR images U[0,1) (B,4,16,64) with a {0,1} mask channel + text prior softmax(N(0,1)) (B,37,1,26), resident"}
+            del tatt
+
         # ---------- per-kernel-class timing (roofline leg), outside the throughput regions
         prof = None
         if rank == 0:
@@ -587,7 +650,7 @@ def run_ours(args):
             "config": infer_config(B, world),
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clk, "roofline": roofline,
-            "cpu_baseline": cpu, "parity": parity, "train": train}
+            "cpu_baseline": cpu, "parity": parity, "psn": psn_obj, "train": train}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -603,6 +666,7 @@ def main():
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer = BASELINE configs[1] headline line with the configs[2] `train` object inside; train = the training step alone")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-psn", action="store_true", help="skip the 'PSN included' leg (frozen TATT backbone in front of the hot path)")
     ap.add_argument("--no-train", action="store_true", help="skip the configs[2] training leg of the default line")
     ap.add_argument("--no-overlap", action="store_true", help="training: all-reduce the whole bucket after the backward (no overlap)")
     ap.add_argument("--train-steps", type=int, default=0, help="timed training steps of the default line (0 = min(steps, 10))")

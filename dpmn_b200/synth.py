@@ -61,8 +61,10 @@ def synth_value(seed: int, name: str, shape: Tuple[int, ...]) -> np.ndarray:
         return 0.5 * n
     if name.startswith("weight_list_"):
         return (1.0 + 0.2 * n).astype(np.float32)
-    if leaf == "bias":
+    if leaf == "bias" or leaf.startswith("bias_") or leaf.endswith("_bias"):     # incl. GRU bias_ih_l0, MHA in_proj_bias
         return 0.05 * n
+    if shape == (1,):                # PReLU slope (torch default 0.25)
+        return (0.25 + 0.05 * n).astype(np.float32)
     if len(shape) == 1:              # LayerNorm / BatchNorm scale
         return (1.0 + 0.1 * n).astype(np.float32)
     if "depthwise_conv" in name:

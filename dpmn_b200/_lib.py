@@ -143,6 +143,10 @@ SYMBOLS = {
     "dpmn_window_attn_forward_windowed_train": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(_vp * MAX_GROUPS), _i32, _i32, _i32, _i32,
                                                           _i32, _i32, C.POINTER(_i32 * MAX_GROUPS), C.POINTER(_i32 * MAX_GROUPS),
                                                           _i32, C.c_float, C.c_uint64, C.c_uint32, _vp]),
+    "dpmn_window_attn_backward_windowed": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp * MAX_GROUPS),
+                                                     C.POINTER(_vp * MAX_GROUPS), _i32, _i32, _i32, _i32, _i32, _i32,
+                                                     C.POINTER(_i32 * MAX_GROUPS), C.POINTER(_i32 * MAX_GROUPS), _i32,
+                                                     C.c_float, C.c_uint64, C.c_uint32, _vp]),
     "dpmn_cmm_workspace_bytes": (_sz, [C.POINTER(CmmDesc)]),
     "dpmn_cmm_forward": (C.c_int, [C.POINTER(CmmDesc), _vp, _vp, _vp, _vp, _sz, _vp]),
     "dpmn_cmm_debug_bytes": (_sz, [C.POINTER(CmmDesc), _i32]),

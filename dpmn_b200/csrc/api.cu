@@ -934,6 +934,31 @@ int dpmn_window_attn_forward_windowed_train(const void* qw, const void* kw, cons
   return 0;
 }
 
+int dpmn_window_attn_backward_windowed(const void* qw, const void* kw, const void* vw, const void* d_out16, float* dq, float* dkv,
+                                       const float* const rpb_table[DPMN_MAX_GROUPS], float* const d_rpb_table[DPMN_MAX_GROUPS],
+                                       int32_t batch, int32_t grid_h, int32_t grid_w, int32_t embed_dim, int32_t num_heads,
+                                       int32_t n_groups, const int32_t window[DPMN_MAX_GROUPS], const int32_t shift[DPMN_MAX_GROUPS],
+                                       int32_t precision, float attn_drop, uint64_t seed, uint32_t site, void* stream) {
+  if (!qw || !kw || !vw || !d_out16 || !dq || !dkv || !rpb_table || !d_rpb_table || !window || !shift) return DPMN_E_ARG;
+  if (n_groups < 1 || n_groups > DPMN_MAX_GROUPS || batch < 1) return DPMN_E_ARG;
+  if (embed_dim % n_groups || num_heads % n_groups) return DPMN_E_ARG;
+  if (!(attn_drop >= 0.f && attn_drop < 1.f)) return DPMN_E_ARG;
+  if (precision != DPMN_PREC_F16 && precision != DPMN_PREC_BF16) return DPMN_E_UNSUPPORTED;
+  AttnBwdTcArgs a;
+  a.qw = qw; a.kw = kw; a.vw = vw; a.d_out16 = d_out16; a.dq = dq; a.dkv = dkv; a.io_type = (DType)precision;
+  a.B = batch; a.H = grid_h; a.W = grid_w; a.C = embed_dim; a.n_groups = n_groups; a.heads_per_group = num_heads / n_groups;
+  a.p_drop = attn_drop; a.seed = seed; a.site = site;
+  for (int g = 0; g < n_groups; ++g) {
+    if (!rpb_table[g] || !d_rpb_table[g]) return DPMN_E_ARG;
+    if (shift[g] < 0 || shift[g] >= window[g]) return DPMN_E_ARG;
+    a.table[g] = rpb_table[g]; a.d_table[g] = d_rpb_table[g]; a.window[g] = window[g]; a.shift[g] = shift[g];
+  }
+  if (!attn_bwd_tc_supported(a)) return DPMN_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  DPMN_RUN(T_BWD_ATTN, launch_window_attn_bwd_tc(a, st), 1);
+  return 0;
+}
+
 size_t dpmn_gemm_nt_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t precision) {
   if (precision == DPMN_PREC_F32) return 256;
   return ((size_t)M * K + (size_t)N * K) * 2 + 1024;

@@ -175,6 +175,19 @@ struct AttnBwdArgs {
   int round16 = 0;                                         // 1 fp16 / 2 bf16: the forward was the tcgen05 kernel (16-bit q, k, v, P)
 };
 int launch_window_attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
+// tcgen05 backward of the attention core (attn2_bwd_tc.cu): window-major 16-bit qw / kw / vw [G][rows][C/G] as the forward
+// read them, d_out16 (rows, C) 16-bit window-major rows; dq (rows, C), dkv (rows, 2C) fp32 in TOKEN order (written),
+// d_table[g] accumulated.  Windows 2 / 4 / 8, head_dim 16 / 32.
+struct AttnBwdTcArgs {
+  const void *qw = nullptr, *kw = nullptr, *vw = nullptr, *d_out16 = nullptr; DType io_type = DT_F16;
+  float* dq = nullptr; float* dkv = nullptr;
+  const float* table[4] = {}; float* d_table[4] = {};
+  int B = 0, H = 0, W = 0, C = 0, n_groups = 0, heads_per_group = 0;
+  int window[4] = {}, shift[4] = {};
+  float p_drop = 0.f; unsigned long long seed = 0; uint32_t site = 0;
+};
+bool attn_bwd_tc_supported(const AttnBwdTcArgs& a);
+int launch_window_attn_bwd_tc(const AttnBwdTcArgs& a, cudaStream_t st);
 // fp32 token-order q (rows, C) / kv (rows, 2C) -> window-major 16-bit [G][rows][C/G] operands of the tcgen05 attention
 int launch_window_scatter16(const float* q, const float* kv, void* qw, void* kw, void* vw, DType t, int B, int H, int W, int C,
                             int G, const int* ws, const int* shift, cudaStream_t st);

@@ -518,3 +518,33 @@ def window_attention_windowed(qw: torch.Tensor, kw: torch.Tensor, vw: torch.Tens
                                                          torch.cuda.current_stream(qw.device).cuda_stream)
     _lib.check(rc, "dpmn_window_attn_forward_windowed_train")
     return out
+
+
+def window_attention_windowed_backward(qw: torch.Tensor, kw: torch.Tensor, vw: torch.Tensor, d_out: torch.Tensor,
+                                       tables: List[torch.Tensor], batch: int, grid, num_heads: int, windows: Sequence[int],
+                                       shifts: Sequence[int], drop: Optional[Tuple[float, int, int]] = None):
+    """Backward of `window_attention_windowed` on tcgen05: d_out (B, L, C) 16-bit in the output's window-major row order ->
+    (dq (B, L, C), dkv (B, L, 2C)) fp32 in token order, and the list of relative-position-table gradients."""
+    lib = _lib.load()
+    for t in (qw, kw, vw, d_out):
+        if not (t.is_cuda and t.is_contiguous()):
+            raise RuntimeError("window_attention_windowed_backward: contiguous CUDA tensors required")
+    prec = {torch.float16: 1, torch.bfloat16: 2}[qw.dtype]
+    G, rows, cg = qw.shape
+    L = grid[0] * grid[1]
+    dq = torch.empty((batch, L, G * cg), dtype=torch.float32, device=qw.device)
+    dkv = torch.empty((batch, L, 2 * G * cg), dtype=torch.float32, device=qw.device)
+    dtabs = [torch.zeros_like(t) for t in tables]
+    tabs = (C.c_void_p * _lib.MAX_GROUPS)(*[t.data_ptr() for t in tables])
+    dts = (C.c_void_p * _lib.MAX_GROUPS)(*[t.data_ptr() for t in dtabs])
+    wv = (C.c_int32 * _lib.MAX_GROUPS)(*windows)
+    sv = (C.c_int32 * _lib.MAX_GROUPS)(*shifts)
+    p_drop, seed, site = drop if drop is not None else (0.0, 0, 0)
+    with torch.cuda.device(qw.device):
+        rc = lib.dpmn_window_attn_backward_windowed(qw.data_ptr(), kw.data_ptr(), vw.data_ptr(), d_out.data_ptr(), dq.data_ptr(),
+                                                    dkv.data_ptr(), C.byref(tabs), C.byref(dts), batch, grid[0], grid[1], G * cg,
+                                                    num_heads, G, C.byref(wv), C.byref(sv), prec, float(p_drop), int(seed), int(site),
+                                                    torch.cuda.current_stream(qw.device).cuda_stream)
+    _lib.check(rc, "dpmn_window_attn_backward_windowed")
+    return dq, dkv, dtabs
+

@@ -233,6 +233,16 @@ int dpmn_window_attn_forward_windowed_train(const void *qw, const void *kw, cons
                                             const int32_t window[DPMN_MAX_GROUPS], const int32_t shift[DPMN_MAX_GROUPS],
                                             int32_t precision, float attn_drop, uint64_t seed, uint32_t site, void *stream);
 
+/* Backward of the same core on tcgen05 (attn2_bwd_tc.cu): d_out16 (batch*L, embed_dim) 16-bit, the gradient of `out` in its
+ * window-major row order; writes dq (batch*L, embed_dim) and dkv (batch*L, 2*embed_dim) fp32 in TOKEN order (the gradients of
+ * the projected q / kv tensors, roll + window_partition undone) and ACCUMULATES d_rpb_table[g] ((2ws-1)^2, heads/G) fp32.
+ * Scores are recomputed from qw / kw; attn_drop / seed / site must be the forward's.  Windows in {2,4,8}. */
+int dpmn_window_attn_backward_windowed(const void *qw, const void *kw, const void *vw, const void *d_out16, float *dq, float *dkv,
+                                       const float *const rpb_table[DPMN_MAX_GROUPS], float *const d_rpb_table[DPMN_MAX_GROUPS],
+                                       int32_t batch, int32_t grid_h, int32_t grid_w, int32_t embed_dim, int32_t num_heads,
+                                       int32_t n_groups, const int32_t window[DPMN_MAX_GROUPS], const int32_t shift[DPMN_MAX_GROUPS],
+                                       int32_t precision, float attn_drop, uint64_t seed, uint32_t site, void *stream);
+
 size_t dpmn_cmm_workspace_bytes(const dpmn_cmm_desc *d);
 size_t dpmn_cmm_prepared_bytes(const dpmn_cmm_desc *d);     /* 0 in the fp32 mode */
 

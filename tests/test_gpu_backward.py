@@ -415,3 +415,38 @@ def test_image_loss_and_to_mask_kernels_match_reference():
     assert abs(float(image_loss(o, four[:, :3])) - float(z["loss0_val"])) < 2e-6 * abs(float(z["loss0_val"]))
     got = to_mask(torch.from_numpy(z["mask_in"]).to(dev)).cpu().numpy()
     assert np.array_equal(got, z["mask_out"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,windows,B,shifts,p_drop", [(96, [2, 4, 8], 2, [1, 2, 4], 0.0), (96, [2, 4, 8], 3, [1, 2, 4], 0.2),
+                                                        (192, [8], 2, [4], 0.0), (192, [4], 1, [2], 0.3), (96, [4, 8], 2, [0, 3], 0.1),
+                                                        (96, [2], 1, [0], 0.0)])
+def test_attention_backward_tcgen05_against_autograd_of_the_oracle_core(C, windows, B, shifts, p_drop):
+    """attn2_bwd_tc.cu (five tcgen05 contractions per 64-row half: S, dP, dQ, dK, dV; bias-table gradient through shared-memory
+    atomics) against torch autograd through the oracle's restatement of pgrm.py:197-268 on the same 16-bit operand values and
+    the same attn_drop masks.  The kernel rounds dO, dS and P o M to fp16 operands: bar 4e-3 relative L2 per tensor."""
+    from dpmn_b200.pgrm import to_window_major, window_attention_windowed_backward
+    from oracle import torch_ref
+    dev = torch.device("cuda")
+    torch.manual_seed(21)
+    H, W, heads = 16, 64, 6
+    G = len(windows)
+    q = torch.randn(B, H * W, C).half()
+    kv = torch.randn(B, H * W, 2 * C).half()
+    tabs = [torch.randn((2 * w - 1) ** 2, heads // G) * 0.5 for w in windows]
+    d_out = (torch.randn(B, H * W, C) * 0.1).half()
+    qf, kvf = q.float().requires_grad_(True), kv.float().requires_grad_(True)
+    tf = [t.clone().requires_grad_(True) for t in tabs]
+    seed, site = 99, 32
+    out = torch_ref.window_attention_core(qf, kvf, tf, windows, shifts, H, W, heads // G,
+                                          drop=(p_drop, seed) if p_drop > 0 else None, site=site)
+    (out * d_out.float()).sum().backward()
+    qw = to_window_major(q.to(dev), (H, W), windows, shifts)
+    kw = to_window_major(kv[..., :C].contiguous().to(dev), (H, W), windows, shifts)
+    vw = to_window_major(kv[..., C:].contiguous().to(dev), (H, W), windows, shifts)
+    dq, dkv, dt = window_attention_windowed_backward(qw, kw, vw, d_out.to(dev), [t.to(dev) for t in tabs], B, (H, W), heads, windows,
+                                                     shifts, drop=(p_drop, seed, site) if p_drop > 0 else None)
+    for name, got, want in [("dq", dq, qf.grad), ("dkv", dkv, kvf.grad)] + [(f"dtable{g}", dt[g], tf[g].grad) for g in range(G)]:
+        l2, cos = _l2_cos(got.cpu().numpy(), want.numpy())
+        assert l2 < 4e-3 and cos > 0.9999, (name, l2, cos)
+

@@ -78,12 +78,13 @@ struct B2Smem {
   static constexpr int OP_TILE = 64 * 128;                      // 64 x 64 16-bit operand tile
   static constexpr int OP_BYTES = HC * 2 * 3 * OP_TILE;         // [head][half][dS, dS^T, Pd^T]
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = B2_STAGES * STAGE + OP_BYTES + BAR_BYTES + 2 * B2_TAB_FLOATS * 4 + 1024;
+  static constexpr int ACC_FLOATS = 64 * 64;                    // per head: bias-gradient accumulators of the current window size
+  static constexpr int TOTAL = B2_STAGES * STAGE + OP_BYTES + BAR_BYTES + 2 * B2_TAB_FLOATS * 4 + HC * ACC_FLOATS * 4 + 1024;
 };
 
 // One row of one head: recompute P, form dS, write the three operand tiles, accumulate the bias-table gradient.
 template <int WS, typename T, bool DROP>
-__device__ __forceinline__ void b2_row(uint32_t s_addr, int quarter, int lane, const float* tab, float* dtab, int g, int w_idx,
+__device__ __forceinline__ void b2_row(uint32_t s_addr, int quarter, int lane, const float* tab, float* acc, int g, int w_idx,
                                        uint8_t* tiles_half, uint64_t* s_empty_bar, uint64_t* ds_empty_bar, uint32_t ds_empty_parity,
                                        bool full, const AttnBwd2Params& p, unsigned long long drop_base) {
   constexpr int N = WS * WS;
@@ -174,13 +175,25 @@ __device__ __forceinline__ void b2_row(uint32_t s_addr, int quarter, int lane, c
     delta = fmaf(s[m], dp[m], delta);
   }
   // dS (kept in dp[]), the bias-table gradient, and Pd = P o M (kept in s[])
-  float* dtb = dtab + tb0;
+  // d table[idx(n, m)] += dS[n, m]: a shared-memory atomic per score would cost ~2 LSU cycles per lane (measured: 130 of the
+  // kernel's 143 us).  Instead the lanes that hold the same in-window position n first add up through shuffles, and ONE of them
+  // adds into a plain accumulator acc[.][m][n] that no other thread touches (per warp for windows 2 / 4, where every quarter
+  // holds the same n); the accumulators are folded into the table bins once per run of equal window sizes (b2_flush).
 #pragma unroll
   for (int m = 0; m < N; ++m) {
     const float ds = s[m] * (dp[m] - delta);
     if constexpr (DROP) s[m] *= ((kept >> m) & 1ull) ? p.keep_inv : 0.f;
     dp[m] = ds;
-    atomicAdd(dtb - ((m / WS) * TW + (m % WS)), ds);
+    float a = ds + __shfl_xor_sync(0xffffffffu, ds, 16);      // the other half's row with the same n
+    if constexpr (WS == 2) {
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      if (lane < 4) acc[quarter * 16 + m * 4 + n] += a;
+    } else if constexpr (WS == 4) {
+      if (lane < 16) acc[quarter * 256 + m * 16 + n] += a;
+    } else {
+      if (lane < 16) acc[m * 64 + n] += a;
+    }
   }
 
   // ---- operand tiles of this half: [0] dS row-major, [1] dS^T, [2] Pd^T; 64 x 64, 128-byte rows, 128B swizzle
@@ -231,6 +244,20 @@ __device__ __forceinline__ void b2_row(uint32_t s_addr, int quarter, int lane, c
   }
 }
 
+// Fold one head's accumulators (window size ws) into its table-gradient bins and clear them.  Called by the head's 128
+// threads between two named-barrier syncs; t = thread index within the head.
+__device__ __forceinline__ void b2_flush(float* acc, float* dtab, int ws, int t) {
+  const int N = ws * ws, tw = 2 * ws - 1;
+  const int total = ws == 8 ? 64 * 64 : 4 * N * N;           // [m][n] for window 8, [quarter][m][n] otherwise
+  for (int e = t; e < total; e += 128) {
+    const int r = ws == 8 ? e : e % (N * N);
+    const int m = r / N, n = r - m * N;
+    const float v = acc[e];
+    acc[e] = 0.f;
+    if (v != 0.f) atomicAdd(dtab + (n / ws - m / ws + ws - 1) * tw + (n % ws - m % ws + ws - 1), v);
+  }
+}
+
 template <int D, int HC, typename T, bool DROP>
 // (10 warps put three on one SM sub-partition: 16384 / 96 = 170 registers per thread is the hardware ceiling for HC = 2)
 __global__ void __launch_bounds__(64 + HC * 128, 1)
@@ -256,6 +283,7 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
   float* s_tab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + S::BAR_BYTES);   // [G][hpg][TAB_STRIDE]
   float* s_dtab = s_tab + B2_TAB_FLOATS;
+  float* s_acc = s_dtab + B2_TAB_FLOATS;           // [HC][64 * 64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = HC == 2 ? 512 : 256;
@@ -264,7 +292,7 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   auto decode = [&](int u, int& g, int& tile, int& hc) {
     g = (u >= p.upg) + (u >= 2 * p.upg) + (u >= 3 * p.upg);
     const int r = u - g * p.upg;
-    if (p.nhc == 1) { tile = r; hc = 0; } else { tile = r / p.nhc; hc = r - tile * p.nhc; }
+    if (p.nhc == 1) { tile = r; hc = 0; } else { hc = r / p.tiles; tile = r - hc * p.tiles; }   // head-chunk major: long runs of one (group, head)
   };
   auto tma_unit = [&](int u, int it) {
     int g, tile, hc;
@@ -306,6 +334,7 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       s_tab[i] = v;
       s_dtab[i] = 0.f;
     }
+    for (int i = threadIdx.x - 64; i < HC * S::ACC_FLOATS; i += THREADS - 64) s_acc[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -416,7 +445,7 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                                                          __uint_as_float(o[2][c + 2]), __uint_as_float(o[2][c + 3]));
       }
     };
-    int it = 0, last_ws = -1;
+    int it = 0, last_ws = -1, last_gh = -1;
     long long tok_prev = 0;
     int ch_prev = 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
@@ -431,19 +460,25 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       unsigned long long drop_base = 0ull;
       if constexpr (DROP)
         drop_base = ((((unsigned long long)b_img * p.G + g) * p.hpg + head) * p.L + p_img) * (unsigned long long)(ws * ws);
+      float* acc = s_acc + h * S::ACC_FLOATS;
+      if (last_gh >= 0 && last_gh != g * p.hpg + head) {       // the (group, head) changed: fold its accumulators into its bins
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
+        b2_flush(acc, s_dtab + last_gh * B2_TAB_STRIDE, last_ws, threadIdx.x - 64 - h * 128);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
+      }
+      last_gh = g * p.hpg + head;
       mbar_wait(s_full, (uint32_t)(it & 1));
       tc_fence_after();
       {
         const float* tab = s_tab + (g * p.hpg + head) * B2_TAB_STRIDE;
-        float* dtab = s_dtab + (g * p.hpg + head) * B2_TAB_STRIDE;
         const uint32_t s_addr = lane_addr + (uint32_t)(h * 128);
         uint8_t* th = op_tiles + (h * 2 + half) * 3 * S::OP_TILE;
         const uint32_t par = (uint32_t)((it & 1) ^ 1);
         const bool full = last_ws != ws;
         last_ws = ws;
-        if (ws == 8) b2_row<8, T, DROP>(s_addr, quarter, lane, tab, dtab, g, p_img >> 6, th, s_empty, ds_empty, par, full, p, drop_base);
-        else if (ws == 4) b2_row<4, T, DROP>(s_addr, quarter, lane, tab, dtab, g, p_img >> 4, th, s_empty, ds_empty, par, full, p, drop_base);
-        else b2_row<2, T, DROP>(s_addr, quarter, lane, tab, dtab, g, p_img >> 2, th, s_empty, ds_empty, par, full, p, drop_base);
+        if (ws == 8) b2_row<8, T, DROP>(s_addr, quarter, lane, tab, acc, g, p_img >> 6, th, s_empty, ds_empty, par, full, p, drop_base);
+        else if (ws == 4) b2_row<4, T, DROP>(s_addr, quarter, lane, tab, acc, g, p_img >> 4, th, s_empty, ds_empty, par, full, p, drop_base);
+        else b2_row<2, T, DROP>(s_addr, quarter, lane, tab, acc, g, p_img >> 2, th, s_empty, ds_empty, par, full, p, drop_base);
       }
       fence_proxy_async();
       __syncwarp();
@@ -453,6 +488,10 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       ch_prev = ch;
     }
     if (it > 0) epilogue(it - 1, tok_prev, ch_prev);
+    if (last_gh >= 0) {
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
+      b2_flush(s_acc + h * S::ACC_FLOATS, s_dtab + last_gh * B2_TAB_STRIDE, last_ws, threadIdx.x - 64 - h * 128);
+    }
   }
 
   tc_fence_before();

@@ -19,7 +19,7 @@ for line in out.splitlines():
     if m:
         if cur is not None:
             rows.append((cur, cnt, total))
-        cur = names[fi].split("(")[0].replace("void ", "").replace("dpmn::", "").replace("<unnamed>::", "")
+        cur = names[fi].replace("(anonymous namespace)::", "").split("(")[0].replace("void ", "").replace("dpmn::", "").replace("<unnamed>::", "")
         fi += 1
         cnt, total = collections.Counter(), 0
         continue

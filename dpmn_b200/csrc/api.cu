@@ -615,6 +615,8 @@ int cmm_forward_tc(const dpmn_cmm_desc* d, const float* x1, const float* x2, flo
   if (d->training) return DPMN_E_UNSUPPORTED;   // batch-statistics BatchNorm runs in the fp32 mode only (this build)
   if (d->cnum % 16 || d->c_img > 3) return DPMN_E_UNSUPPORTED;   // 64-channel k-blocks, whole UMMA k-steps, 9*c_img <= 32
   const CmmTcWs w = carve_cmm_tc(d, workspace);
+  // split-K scratch of the deep layers: the de_1 tap-product buffer, which is only written by the last GEMM of the forward
+  const size_t sk_floats = (size_t)d->batch * d->img_h * d->img_w * 32;
   if (workspace_bytes < w.bytes) return DPMN_E_WORKSPACE;
   const CmmDims D{d->batch, d->cnum, d->img_h, d->img_w, d->c_img};
   const DType t = (DType)d->precision;
@@ -670,7 +672,7 @@ int cmm_forward_tc(const dpmn_cmm_desc* d, const float* x1, const float* x2, flo
     const int Ho = Hi / 2, Wo = Wi / 2;
     {
       ConvTcArgs a;   // LeakyReLU -> conv4x4 s2 d2 p3 -> BN -> (LeakyReLU)          cmm.py:41-45
-      a.op_type = t; a.n_src = 1;
+      a.splitk_ws = w.P; a.splitk_floats = sk_floats; a.op_type = t; a.n_src = 1;
       a.src[0].base = (const uint16_t*)w.e[l] + ((size_t)Wi + 1) * Ci;   // odd rows / odd columns sub-grid
       a.src[0].sx = 2LL * Ci; a.src[0].sy = 2LL * Wi * Ci; a.src[0].sb = (long long)Hi * Wi * Ci;
       a.src[0].sg = (long long)B * Hi * Wi * Ci;
@@ -689,7 +691,7 @@ int cmm_forward_tc(const dpmn_cmm_desc* d, const float* x1, const float* x2, flo
     }
     {
       ConvTcArgs a;   // conv3x3 -> BN; stored LeakyReLU'd for the next stage and ReLU'd for the decoder skip
-      a.op_type = t; a.n_src = 1;
+      a.splitk_ws = w.P; a.splitk_floats = sk_floats; a.op_type = t; a.n_src = 1;
       a.src[0].base = w.mid[l + 1];
       a.src[0].sx = Ci; a.src[0].sy = (long long)Wo * Ci; a.src[0].sb = (long long)Ho * Wo * Ci;
       a.src[0].sg = (long long)B * Ho * Wo * Ci;
@@ -712,7 +714,7 @@ int cmm_forward_tc(const dpmn_cmm_desc* d, const float* x1, const float* x2, flo
   const int H5 = D.Hl(5), W5 = D.Wl(5), C5 = 8 * c, H6 = H5 / 2, W6 = W5 / 2;
   {
     ConvTcArgs a;   // en_6: LeakyReLU -> conv4x4 s2 p1 (cmm.py:91-93): each tap reads one parity sub-grid
-    a.op_type = t; a.n_src = 4;
+    a.splitk_ws = w.P; a.splitk_floats = sk_floats; a.op_type = t; a.n_src = 4;
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
         ConvTcSrc& sc = a.src[py * 2 + px];
@@ -740,7 +742,7 @@ int cmm_forward_tc(const dpmn_cmm_desc* d, const float* x1, const float* x2, flo
   auto convt4 = [&](const void* src, int Hi, int Wi, int Ci, const void* wt, int Co, const float* sc, const float* sh,
                     void* dst, int dst_ld) -> int {
     ConvTcArgs a;   // ReLU'd input -> convT4x4 s2 p1 -> BN -> ReLU into channel 0.. of the next concat buffer
-    a.op_type = t; a.n_src = 1;
+    a.splitk_ws = w.P; a.splitk_floats = sk_floats; a.op_type = t; a.n_src = 1;
     a.src[0].base = src; a.src[0].sx = Ci; a.src[0].sy = (long long)Wi * Ci; a.src[0].sb = (long long)Hi * Wi * Ci;
     a.Cin = Ci; a.Cout = Co; a.B = B; a.G = 1; a.P = 4; a.Hm = Hi; a.Wm = Wi;
     a.n_taps = 4;
@@ -756,7 +758,7 @@ int cmm_forward_tc(const dpmn_cmm_desc* d, const float* x1, const float* x2, flo
     const int Hi = D.Hl(l), Wi = D.Wl(l), Cc = D.Ccat(l), Co = D.Co(l);
     {
       ConvTcArgs a;   // convT3x3 s1 p1 on the concat buffer = conv with mirrored taps (cmm.py:62)
-      a.op_type = t; a.n_src = 1;
+      a.splitk_ws = w.P; a.splitk_floats = sk_floats; a.op_type = t; a.n_src = 1;
       a.src[0].base = w.cat[l]; a.src[0].sx = Cc; a.src[0].sy = (long long)Wi * Cc; a.src[0].sb = (long long)Hi * Wi * Cc;
       a.Cin = Cc; a.Cout = Co; a.B = B; a.G = 1; a.P = 1; a.Hm = Hi; a.Wm = Wi;
       a.n_taps = 9;

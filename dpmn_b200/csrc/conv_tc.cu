@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
+#include <cstdlib>
 #include <cstring>
 
 namespace dpmn {
@@ -39,6 +40,9 @@ struct ConvTcParams {
   const float* shift;                // [G][Cout] or nullptr (0)
   ConvTcDest dst[2];
   int fmt;                           // 0 fp16, 1 bf16
+  int ksplit, kb_per;                // split-K: slices and k-blocks per slice (ksplit == 1: none)
+  float* part;                       // [ksplit][G][npix][Cout] fp32 partial sums
+  long long npix;                    // B * Ho * Wo
 };
 
 template <int BN>
@@ -101,7 +105,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int cblocks = (p.Cin + CBK - 1) / CBK;
   const int num_kb = p.n_taps * cblocks;
   const int pix_tiles = p.wt * p.ht * p.bt;
-  const int total_tiles = p.G * p.P * pix_tiles * p.n_tiles;
+  const int total_tiles = p.G * p.P * pix_tiles * p.n_tiles * p.ksplit;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -120,8 +124,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   // tile index -> (n block, pixel-tile origin, parity class, group); n fastest so neighbours share the A boxes in L2
 #define DPMN_DECODE_TILE(t)                                   \
-  const int n_blk = (t) % p.n_tiles;                          \
-  int _r = (t) / p.n_tiles;                                   \
+  const int ks = (t) % p.ksplit;                              \
+  const int kb0 = ks * p.kb_per;                              \
+  const int kb1 = kb0 + p.kb_per < num_kb ? kb0 + p.kb_per : num_kb;   \
+  const int n_blk = ((t) / p.ksplit) % p.n_tiles;             \
+  int _r = (t) / (p.ksplit * p.n_tiles);                      \
   const int w0 = (_r % p.wt) * p.bw; _r /= p.wt;              \
   const int h0 = (_r % p.ht) * p.bh; _r /= p.ht;              \
   const int b0 = (_r % p.bt) * p.bb; _r /= p.bt;              \
@@ -133,18 +140,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         DPMN_DECODE_TILE(t)
-        for (int tap = 0; tap < p.n_taps; ++tap) {
+        int tap = kb0 / cblocks, cb = kb0 - tap * cblocks;
+        for (int kb = kb0; kb < kb1; ++kb) {
           const ConvTap tp = p.taps[cls][tap];
           const CUtensorMap* ma = tp.map == 0 ? &map_a0 : tp.map == 1 ? &map_a1 : tp.map == 2 ? &map_a2 : &map_a3;
-          for (int cb = 0; cb < cblocks; ++cb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = tiles + stage * S::STAGE_BYTES;
-            uint8_t* sb = sa + S::A_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-            tma_load_5d(sa, ma, &full_bar[stage], cb * CBK, w0 + tp.dx, h0 + tp.dy, b0, g);
-            tma_load_4d(sb, &map_w, &full_bar[stage], cb * CBK, n_blk * BN, tp.wslice, g);
-            if (++stage == CSTAGES) { stage = 0; phase ^= 1; }
-          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          tma_load_5d(sa, ma, &full_bar[stage], cb * CBK, w0 + tp.dx, h0 + tp.dy, b0, g);
+          tma_load_4d(sb, &map_w, &full_bar[stage], cb * CBK, n_blk * BN, tp.wslice, g);
+          if (++stage == CSTAGES) { stage = 0; phase ^= 1; }
+          if (++cb == cblocks) { cb = 0; ++tap; }
         }
       }
     }
@@ -154,10 +161,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int kb0 = (t % p.ksplit) * p.kb_per;
+        const int kb1 = kb0 + p.kb_per < num_kb ? kb0 + p.kb_per : num_kb;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           const int cb = kb % cblocks;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -167,7 +176,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const int c_left = p.Cin - cb * CBK;
           const int ksteps = c_left >= CBK ? CBK / 16 : (c_left + 15) / 16;
           for (int k = 0; k < ksteps; ++k)
-            umma_f16(d_tmem, advance_desc_k(da, k), advance_desc_k(db, k), idesc, (kb | k) ? 1u : 0u);
+            umma_f16(d_tmem, advance_desc_k(da, k), advance_desc_k(db, k), idesc, ((kb - kb0) | k) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == CSTAGES) { stage = 0; phase ^= 1; }
         }
@@ -212,6 +221,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+        if (p.ksplit > 1) {                             // raw partial sums; conv_splitk_reduce_kernel applies the epilogue
+          float* pp = p.part + (((long long)ks * p.G + g) * p.npix + pix) * p.Cout + n0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (j < ncols) *reinterpret_cast<float4*>(pp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          continue;
+        }
         if (p.scale != nullptr) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { v[4 * j] *= sc4[j].x; v[4 * j + 1] *= sc4[j].y; v[4 * j + 2] *= sc4[j].z; v[4 * j + 3] *= sc4[j].w; }
@@ -242,6 +258,67 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Split-K second pass: out[g, pix, c] = epi( sum_ks part[ks, g, pix, c] ), slices added in order (deterministic); 8 channels
+// per thread, the same scale / shift / dual-destination epilogue as the fused path.
+struct SplitKReduceParams {
+  const float* part; int ksplit, G, Cout; long long npix;
+  const float* scale; const float* shift;
+  ConvTcDest dst[2];
+};
+__global__ void __launch_bounds__(256) conv_splitk_reduce_kernel(const SplitKReduceParams p) {
+  const int c8 = p.Cout / 8;
+  const long long total = (long long)p.G * p.npix * c8;
+  const long long slice = (long long)p.G * p.npix * p.Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8) * 8;
+    const long long gp = i / c8;
+    const long long pix = gp % p.npix;
+    const int g = (int)(gp / p.npix);
+    const float* src = p.part + gp * p.Cout + c;
+    float v[8];
+    {
+      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    for (int ks = 1; ks < p.ksplit; ++ks) {
+      const float4 a = *reinterpret_cast<const float4*>(src + ks * slice), b = *reinterpret_cast<const float4*>(src + ks * slice + 4);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (p.scale != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= p.scale[(long long)g * p.Cout + c + j];
+    }
+    if (p.shift != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += p.shift[(long long)g * p.Cout + c + j];
+    }
+#pragma unroll
+    for (int di = 0; di < 2; ++di) {
+      const ConvTcDest& d = p.dst[di];
+      if (d.ptr == nullptr) continue;
+      float a[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = d.act == 1 ? (v[j] >= 0.f ? v[j] : 0.2f * v[j]) : (d.act == 2 ? fmaxf(v[j], 0.f) : v[j]);
+      const long long off = (long long)g * d.g_stride + pix * d.ld + d.ch_off + g * d.ch_g_off + c;
+      if (d.type == DT_F32) {
+        float* q = reinterpret_cast<float*>(d.ptr) + off;
+        *reinterpret_cast<float4*>(q) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(q + 4) = make_float4(a[4], a[5], a[6], a[7]);
+      } else if (d.type == DT_F16) {
+        union { uint4 u; __half h[8]; } pk;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk.h[j] = __float2half_rn(a[j]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.ptr) + off) = pk.u;
+      } else {
+        union { uint4 u; __nv_bfloat16 h[8]; } pk;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk.h[j] = __float2bfloat16_rn(a[j]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.ptr) + off) = pk.u;
+      }
+    }
   }
 }
 
@@ -285,7 +362,28 @@ static int launch_conv_bn(const ConvTcArgs& a, cudaStream_t st) {
   }
   int num_sms = 0;
   DPMN_CUDA_TRY(current_device_sms(&num_sms));
-  const int total = p.G * p.P * p.wt * p.ht * p.bt * p.n_tiles;
+  const int tiles_mn = p.G * p.P * p.wt * p.ht * p.bt * p.n_tiles;
+  // split-K: only when the (pixel, Cout) tiles cover less than half of the 2-CTA-per-SM grid and the reduction is long
+  p.ksplit = 1; p.npix = (long long)a.B * a.Ho * a.Wo;
+  {
+    // Opt-in (DPMN_CONV_SPLITK=1).  Measured on B200 (profiles/r02_splitk_ab.md): the six deep CMM layers drop from 380 to
+    // ~180 us in a one-stream forward (conv_tc class 1.00 -> 0.80 ms), but the pipelined step does not move (2.49 -> 2.50 ms:
+    // those layers only occupy 32-96 SMs and the other streams' kernels already fill the rest), and a batch-dependent slice
+    // count makes the result depend on the batch size in the last bit (tests pin batch-size invariance).
+    static const bool splitk_on = getenv("DPMN_CONV_SPLITK") && atoi(getenv("DPMN_CONV_SPLITK")) != 0;
+    const int num_kb = a.n_taps * ((a.Cin + CBK - 1) / CBK);
+    if (splitk_on && a.splitk_ws != nullptr && tiles_mn * 2 <= 2 * num_sms && num_kb >= 16) {
+      int ks = (2 * num_sms) / tiles_mn;
+      if (ks > num_kb / 8) ks = num_kb / 8;                       // at least 8 k-blocks per slice
+      const size_t per_slice = (size_t)a.G * p.npix * a.Cout;
+      if ((size_t)ks * per_slice > a.splitk_floats) ks = (int)(a.splitk_floats / per_slice);
+      if (ks >= 2) p.ksplit = ks;
+    }
+    p.kb_per = (num_kb + p.ksplit - 1) / p.ksplit;
+    p.ksplit = (num_kb + p.kb_per - 1) / p.kb_per;                // no empty slice
+    p.part = a.splitk_ws;
+  }
+  const int total = tiles_mn * p.ksplit;
   const int grid = total < 2 * num_sms ? total : 2 * num_sms;
   auto kern = conv_tc_kernel<BN>;
   constexpr int smem = ConvSmem<BN>::TOTAL;
@@ -293,6 +391,15 @@ static int launch_conv_bn(const ConvTcArgs& a, cudaStream_t st) {
   DPMN_CUDA_TRY(attr.smem_attr(kern, smem));
   DPMN_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(CONV_THREADS), smem, st, maps[0], maps[1], maps[2], maps[3], map_w, p));
   DPMN_LAUNCH_CHECK();
+  if (p.ksplit > 1) {
+    SplitKReduceParams r;
+    r.part = p.part; r.ksplit = p.ksplit; r.G = a.G; r.Cout = a.Cout; r.npix = p.npix; r.scale = a.scale; r.shift = a.shift;
+    r.dst[0] = a.dst[0]; r.dst[1] = a.dst[1];
+    const long long items = (long long)a.G * p.npix * (a.Cout / 8);
+    const int blocks = (int)((items + 255) / 256 < 4 * num_sms ? (items + 255) / 256 : 4 * num_sms);
+    conv_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(r);
+    DPMN_LAUNCH_CHECK();
+  }
   return 0;
 }
 

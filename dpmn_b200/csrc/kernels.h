@@ -373,6 +373,10 @@ struct ConvTcArgs {
   int os = 1, Ho = 0, Wo = 0;
   const float* scale = nullptr; const float* shift = nullptr;   // [G][Cout]
   ConvTcDest dst[2];
+  // Split-K scratch (optional): layers whose (pixel tile, Cout tile) grid cannot fill the machine split their taps x Cin
+  // reduction over several CTAs, which write fp32 partial sums [slice][G][B*Ho*Wo][Cout] here; a second kernel adds the
+  // slices in order and applies the epilogue.  nullptr / too small: the layer runs unsplit.
+  float* splitk_ws = nullptr; size_t splitk_floats = 0;
 };
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st);
 

@@ -177,6 +177,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr bool kCanLn = LN;                      // the whole output row passes through one thread
       float rowbuf[kCanLn ? BN : 1];
       const int m_ld = row_ok ? m : (p.M - 1);          // clamped row: loads are issued unconditionally
+      // window scatter: everything that depends on the row only -- image, token, its window-major row in every group (roll +
+      // window_partition, pgrm.py:209-225) -- once per tile instead of once per 16-column chunk (the per-chunk form was
+      // ~1000 instructions per thread and tile, 10 M warp instructions per launch: profiles/r02_ncu_full_block_v4.txt id 1)
+      long long sc_rowbase[4] = {0, 0, 0, 0};           // element offset of (group g, this row) in a scatter destination
+      int sc_which0 = 0, sc_nn0 = 0;
+      if (p.scatter) {
+        const int L = p.sc_H * p.sc_W;
+        const int b = m_ld / L, token = m_ld - b * L;
+        const int ho = token / p.sc_W, wo = token - ho * p.sc_W;
+        const int nimg = p.M / L;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g < p.sc_G) {
+            const int ws = p.sc_ws[g], sh = p.sc_shift[g];
+            int hp = ho - sh; if (hp < 0) hp += p.sc_H;
+            int wp = wo - sh; if (wp < 0) wp += p.sc_W;
+            const int hq = hp / ws, wq = wp / ws;
+            const int prow = (hq * (p.sc_W / ws) + wq) * ws * ws + (hp - hq * ws) * ws + (wp - wq * ws);
+            sc_rowbase[g] = (((long long)g * nimg + b) * L + prow) * p.sc_cg;
+          }
+        }
+        const int nb = n_blk * BN;
+        sc_which0 = nb / p.sc_C;
+        sc_nn0 = nb - sc_which0 * p.sc_C;
+      }
       auto do_chunk = [&](const int c0) {
         const int n0 = n_blk * BN + c0;
         // (1) issue every global load of this chunk first, unpredicated (columns clamped into range), so that the
@@ -246,13 +271,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (p.scatter) {
           if constexpr (sizeof(OutT) == 2) {
             if (row_ok && n0 < p.N) {
-              const int L = p.sc_H * p.sc_W;
-              const int b = m / L, token = m - b * L;
-              const int which = n0 / p.sc_C, nn = n0 - which * p.sc_C;
-              const int g = nn / p.sc_cg, col = nn - g * p.sc_cg;
-              const int prow = token_to_window_row(token, p.sc_H, p.sc_W, p.sc_ws[g], p.sc_shift[g]);
-              OutT* dst = reinterpret_cast<OutT*>(p.sc_dst[which]) +
-                          (((long long)g * (p.M / L) + b) * L + prow) * p.sc_cg + col;
+              int which = sc_which0, nn = sc_nn0 + c0;
+              while (nn >= p.sc_C) { nn -= p.sc_C; ++which; }
+              const int g = (nn >= p.sc_cg) + (nn >= 2 * p.sc_cg) + (nn >= 3 * p.sc_cg);
+              const int col = nn - g * p.sc_cg;
+              const long long rb = g == 0 ? sc_rowbase[0] : (g == 1 ? sc_rowbase[1] : (g == 2 ? sc_rowbase[2] : sc_rowbase[3]));
+              OutT* dst = reinterpret_cast<OutT*>(p.sc_dst[which]) + rb + col;
 #pragma unroll
               for (int j = 0; j < CW; j += 8) {
                 union { uint4 u; OutT h[8]; } pk;

@@ -128,5 +128,6 @@ def test_roofline_traffic_is_read_from_the_committed_ncu_summaries():
     import bench
     t = bench.ncu_traffic_per_launch("gemm_tc")
     assert t is not None and 5e6 < t < 60e6            # mean DRAM bytes per launch of the PGRM GEMM class (ncu --set full)
-    assert bench.ncu_traffic_per_launch("window_attn_tc") == 28397000.0
+    ta = bench.ncu_traffic_per_launch("window_attn_tc")
+    assert ta is not None and 20e6 < ta < 40e6         # attention: ~28 MB of DRAM traffic per launch at batch 48
     assert bench.ncu_traffic_per_launch("no_such_class") is None

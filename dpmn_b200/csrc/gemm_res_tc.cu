@@ -202,6 +202,13 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const float* bias = p.bias ? p.bias + (long long)z * p.bias_bs : nullptr;
       uint8_t* cbuf = c_stage + rb * S::C_BUF;
       uint8_t* ybuf = y_stage + rb * S::Y_BUF;
+      // this thread's bias values: loaded before the waits, so their L2 latency hides behind the MMAs of the tile
+      float4 bb_all[NQ][4];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          bb_all[q][j] = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0 + 16 * q) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       mbar_wait(&res_full[rb], (uint32_t)((it >> 1) & 1));
@@ -210,10 +217,7 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int n0 = col0 + 16 * q;                    // first column of this 16-column piece
-        float4 bb[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          bb[j] = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 (&bb)[4] = bb_all[q];
         uint32_t r[32];
         tmem_ld_32x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + n0), r);
         tmem_ld_wait();

@@ -43,6 +43,7 @@ struct GemmTcParams {
   void* ln_out; int ln_type;     // (batch*M, N) rows of ln_type; requires N == BN <= 128
   int scatter, sc_C, sc_G, sc_H, sc_W, sc_cg;
   int sc_ws[4], sc_shift[4];
+  int sc_pow2, sc_lW, sc_lL, sc_lws[4];   // W, H*W and every window size are powers of two (every DPMN geometry): shifts, no divisions
   void* sc_dst[2];
 };
 
@@ -165,9 +166,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool second = t >= tiles0;
       const GemmTcParams& p = second ? p1 : p0;
       const int tt = second ? t - tiles0 : t;
-      const int n_blk = tt % p.n_tiles;
-      const int m_blk = (tt / p.n_tiles) % p.m_tiles;
-      const int z = tt / (p.n_tiles * p.m_tiles);
+      int n_blk = 0, mz = tt;
+      if (p.n_tiles > 1) { mz = tt / p.n_tiles; n_blk = tt - mz * p.n_tiles; }
+      int z = 0, m_blk = mz;
+      if (p.batch > 1) { z = mz / p.m_tiles; m_blk = mz - z * p.m_tiles; }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int m = m_blk * TBM + quarter * 32 + lane;
@@ -183,23 +185,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       long long sc_rowbase[4] = {0, 0, 0, 0};           // element offset of (group g, this row) in a scatter destination
       int sc_which0 = 0, sc_nn0 = 0;
       if (p.scatter) {
-        const int L = p.sc_H * p.sc_W;
-        const int b = m_ld / L, token = m_ld - b * L;
-        const int ho = token / p.sc_W, wo = token - ho * p.sc_W;
-        const int nimg = p.M / L;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g < p.sc_G) {
-            const int ws = p.sc_ws[g], sh = p.sc_shift[g];
-            int hp = ho - sh; if (hp < 0) hp += p.sc_H;
-            int wp = wo - sh; if (wp < 0) wp += p.sc_W;
-            const int hq = hp / ws, wq = wp / ws;
-            const int prow = (hq * (p.sc_W / ws) + wq) * ws * ws + (hp - hq * ws) * ws + (wp - wq * ws);
-            sc_rowbase[g] = (((long long)g * nimg + b) * L + prow) * p.sc_cg;
-          }
-        }
         const int nb = n_blk * BN;
-        sc_which0 = nb / p.sc_C;
+        if (p.sc_pow2) {
+          const int b = m_ld >> p.sc_lL, token = m_ld & ((1 << p.sc_lL) - 1);
+          const int ho = token >> p.sc_lW, wo = token & (p.sc_W - 1);
+          const int nimg = p.M >> p.sc_lL;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g < p.sc_G) {
+              const int lws = p.sc_lws[g], sh = p.sc_shift[g];
+              int hp = ho - sh; if (hp < 0) hp += p.sc_H;
+              int wp = wo - sh; if (wp < 0) wp += p.sc_W;
+              const int wm = (1 << lws) - 1;
+              const int prow = ((((hp >> lws) << (p.sc_lW - lws)) + (wp >> lws)) << (2 * lws)) + ((hp & wm) << lws) + (wp & wm);
+              sc_rowbase[g] = ((((long long)g * nimg + b) << p.sc_lL) + prow) * p.sc_cg;
+            }
+          }
+          sc_which0 = nb >= p.sc_C ? (nb >= 2 * p.sc_C ? nb / p.sc_C : 1) : 0;
+        } else {
+          const int L = p.sc_H * p.sc_W;
+          const int b = m_ld / L, token = m_ld - b * L;
+          const int ho = token / p.sc_W, wo = token - ho * p.sc_W;
+          const int nimg = p.M / L;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g < p.sc_G) {
+              const int ws = p.sc_ws[g], sh = p.sc_shift[g];
+              int hp = ho - sh; if (hp < 0) hp += p.sc_H;
+              int wp = wo - sh; if (wp < 0) wp += p.sc_W;
+              const int hq = hp / ws, wq = wp / ws;
+              const int prow = (hq * (p.sc_W / ws) + wq) * ws * ws + (hp - hq * ws) * ws + (wp - wq * ws);
+              sc_rowbase[g] = (((long long)g * nimg + b) * L + prow) * p.sc_cg;
+            }
+          }
+          sc_which0 = nb / p.sc_C;
+        }
         sc_nn0 = nb - sc_which0 * p.sc_C;
       }
       auto do_chunk = [&](const int c0) {
@@ -448,6 +468,15 @@ static int tc_build(const GemmTcArgs& a, int BN, CUtensorMap* map_a, CUtensorMap
   p.sc_cg = a.scatter_G ? a.scatter_C / a.scatter_G : 0;
   for (int i = 0; i < 4; ++i) { p.sc_ws[i] = a.scatter_ws[i]; p.sc_shift[i] = a.scatter_shift[i]; }
   p.sc_dst[0] = a.scatter_dst[0]; p.sc_dst[1] = a.scatter_dst[1];
+  p.sc_pow2 = 0; p.sc_lW = p.sc_lL = 0;
+  for (int i = 0; i < 4; ++i) p.sc_lws[i] = 0;
+  if (a.scatter) {
+    auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (v > 0 && (1 << l) == v) ? l : -1; };
+    const int lW = lg(a.scatter_W), lL = lg(a.scatter_H * a.scatter_W);
+    bool ok = lW >= 0 && lL >= 0;
+    for (int i = 0; i < a.scatter_G && i < 4; ++i) { const int l = lg(a.scatter_ws[i]); ok = ok && l >= 0 && l <= lW; if (l >= 0) p.sc_lws[i] = l; }
+    if (ok) { p.sc_pow2 = 1; p.sc_lW = lW; p.sc_lL = lL; }
+  }
   return 0;
 }
 
@@ -501,8 +530,9 @@ static int launch_tc_out(const GemmTcArgs& a, cudaStream_t st) {
     }
     return -2;
   }
-  if (N % 256 == 0) return launch_tc_bn<256, OutT, false>(a, st);
-  if (N % 192 == 0) return launch_tc_bn<192, OutT, false>(a, st);
+  static const int bn_max = getenv("DPMN_TC_BN_MAX") ? atoi(getenv("DPMN_TC_BN_MAX")) : 256;   // A/B switch for the N-tile choice
+  if (N % 256 == 0 && bn_max >= 256) return launch_tc_bn<256, OutT, false>(a, st);
+  if (N % 192 == 0 && bn_max >= 192) return launch_tc_bn<192, OutT, false>(a, st);
   if (N % 128 == 0) return launch_tc_bn<128, OutT, false>(a, st);
   if (N % 96 == 0) return launch_tc_bn<96, OutT, false>(a, st);
   if (N % 64 == 0) return launch_tc_bn<64, OutT, false>(a, st);

@@ -1436,11 +1436,77 @@ __global__ void __launch_bounds__(128) head_conv2_mix_kernel(const float* __rest
   }
 }
 
+// Four lanes per token (hp = hs r^2 = 12: hidden_size 3, PixelShuffle 2): lane q owns output channels 3 q .. 3 q + 2, so a
+// thread runs 324 multiply-adds instead of 2 304 at 4x the threads (the one-thread-per-token kernel above has 2.6 warps per
+// scheduler at batch 48 and is latency-bound at 21 us); weights sit in shared memory as [tap][ci][q] float4 (one LDS.128 per
+// (tap, ci)), the four lanes of a token read the same 48 bytes of t1 per tap (one broadcast transaction).
+__global__ void __launch_bounds__(256) head_conv2_mix4_kernel(const float* __restrict__ t1, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ out,
+                                                              int total, int gh, int gw, int hs, int r, MixArgs mix) {
+  constexpr int HP = 12;
+  __shared__ __align__(16) float4 sw[9 * HP * 4];   // [tap][ci][q] -> (co = 3 q, 3 q + 1, 3 q + 2, -)
+  for (int i = threadIdx.x; i < 9 * HP * 4; i += blockDim.x) {
+    const int q = i & 3, ci = (i >> 2) % HP, tap = i / (4 * HP);
+    sw[i] = make_float4(w[((3 * q) * HP + ci) * 9 + tap], w[((3 * q + 1) * HP + ci) * 9 + tap],
+                        w[((3 * q + 2) * HP + ci) * 9 + tap], 0.f);
+  }
+  __syncthreads();
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = gtid >> 2, q = gtid & 3;
+  if (idx >= total) return;
+  const int xx = idx % gw;
+  const int yy = (idx / gw) % gh;
+  const int b = idx / (gw * gh);
+  float acc[3] = {bias[3 * q], bias[3 * q + 1], bias[3 * q + 2]};
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int y2 = yy + ky - 1;
+    if (y2 < 0 || y2 >= gh) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int x2 = xx + kx - 1;
+      if (x2 < 0 || x2 >= gw) continue;
+      const float4* src = reinterpret_cast<const float4*>(t1 + ((long long)(b * gh + y2) * gw + x2) * HP_MAX);
+      const float4* wt = sw + (ky * 3 + kx) * HP * 4 + q;
+#pragma unroll
+      for (int c4 = 0; c4 < HP / 4; ++c4) {
+        const float4 v = __ldg(src + c4);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 ww = wt[(c4 * 4 + u) * 4];
+          acc[0] = fmaf(vv[u], ww.x, acc[0]); acc[1] = fmaf(vv[u], ww.y, acc[1]); acc[2] = fmaf(vv[u], ww.z, acc[2]);
+        }
+      }
+    }
+  }
+  const int img_h = gh * r, img_w = gw * r;
+  const long long plane = (long long)img_h * img_w;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int j = 3 * q + i;
+    float v = acc[i];
+    v = v >= 0.f ? v : 0.01f * v;                       // nn.LeakyReLU default slope (pgrm.py:520)
+    const int c = j / (r * r);
+    const int rem = j - c * r * r;
+    const int dy = rem / r, dx = rem - dy * r;
+    const long long pix = (long long)c * plane + (long long)(yy * r + dy) * img_w + (xx * r + dx);
+    float res = v * mix.w[0][pix];
+    for (int k = 1; k < mix.n_mix; ++k)
+      res = fmaf(mix.in[k][(long long)b * mix.in_bs[k] + pix], mix.w[k][pix], res);
+    out[(long long)b * hs * plane + pix] = res;
+  }
+}
+
 int launch_head_conv2_mix(const float* t1, const float* w, const float* b, float* out, int B, int gh, int gw,
                           int hs, int patch, const MixArgs& mix, cudaStream_t st) {
   if (hs * patch * patch > HP_MAX || mix.n_mix < 1 || mix.n_mix > 8) return -2;
   const int total = B * gh * gw;
-  head_conv2_mix_kernel<<<(total + 127) / 128, 128, 0, st>>>(t1, w, b, out, total, gh, gw, hs, patch, mix);
+  static const int head_v = getenv("DPMN_HEAD_MIX") ? atoi(getenv("DPMN_HEAD_MIX")) : 4;   // 1: one thread per token (A/B)
+  if (head_v == 4 && hs * patch * patch == 12)
+    head_conv2_mix4_kernel<<<(total * 4 + 255) / 256, 256, 0, st>>>(t1, w, b, out, total, gh, gw, hs, patch, mix);
+  else
+    head_conv2_mix_kernel<<<(total + 127) / 128, 128, 0, st>>>(t1, w, b, out, total, gh, gw, hs, patch, mix);
   DPMN_LAUNCH_CHECK();
   return 0;
 }

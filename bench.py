@@ -401,6 +401,8 @@ def run_ours(args):
             model(*dev_sets[i % n_sets][:3])
         from dpmn_b200.pipeline import GraphedHotPath
         n_slots = int(os.environ.get("DPMN_BENCH_SLOTS", "2"))
+        if os.environ.get("DPMN_BENCH_ONE_STREAM", "0") == "1":       # A/B: one stream per slot instead of three
+            model.concurrent_branches = False
         graphed = GraphedHotPath(model, B, dev, slots=n_slots)      # capture once, outside the timed regions
         for i in range(args.warmup):                                 # warm replays
             graphed.launch(i % n_slots)

@@ -38,7 +38,11 @@ class DPMNHotPath(nn.Module):
         self.b1, self.b2 = stu_iter_b1, stu_iter_b2
         self.pgrm = nn.ModuleList(build_pgrm_stack(precision, stu_iter_b1, stu_iter_b2, drop))
         self.cmm = ComplementationModulationModule(precision=cmm_precision or precision)
-        self.concurrent_branches = True       # inference: the two PGRM cascades run on two CUDA streams
+        self.concurrent_branches = True       # the two PGRM cascades run on two CUDA streams (the CMM on a third)
+        # ... also under autograd (training): every backward node runs on the stream of its forward, so the two cascades'
+        # backwards overlap the same way (DPMN_TRAIN_STREAMS=0: one stream, the A/B switch)
+        import os
+        self.concurrent_train = os.environ.get("DPMN_TRAIN_STREAMS", "1") != "0"
         self._streams = None
         # --alpha of the reference (main.py:66, README.md:42: 0.5): eval / test blend the CMM output with the PSN image
         # (super_resolution.py:449,705).  None = the plain CMM output (what the training loss looks at).
@@ -79,7 +83,7 @@ class DPMNHotPath(nn.Module):
         with the device toMask, as the reference does on the host."""
         branch = self._branch_fn(psn_out)
 
-        if psn_out.is_cuda and not torch.is_grad_enabled() and self.concurrent_branches:
+        if psn_out.is_cuda and self.concurrent_branches and (not torch.is_grad_enabled() or self.concurrent_train):
             outs, done = self._submit(psn_out, priors_b1, priors_b2, branch)
             main = torch.cuda.current_stream(psn_out.device)
             main.wait_event(done)                 # ordinary stream semantics for the caller: results are ready on `main`

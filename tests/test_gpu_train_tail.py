@@ -149,3 +149,48 @@ def test_cmm_alpha_blend_is_the_reference_expression(prec, tol):
         y = c(_t(x1), _t(x2), blend_with=_t(psn)[:, :3], alpha=0.3)
     ref = 0.3 * cmm_oracle.cmm_forward(Pc, x1, x2, training=False) + 0.7 * psn[:, :3]
     assert rel_err(y.cpu().numpy(), ref) < tol
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+def test_two_stream_training_step_gives_the_one_stream_gradients(prec):
+    """DPMNHotPath.concurrent_train: under autograd the two PGRM cascades run on two CUDA streams (every backward node on
+    the stream of its forward).  Same seeds -> same Dropout / DropPath masks, so the seven output images, the loss and the
+    flat gradient bucket must equal the one-stream step's up to the run-to-run noise of the kernels' fp32 atomics (pooled
+    sums, BatchNorm statistics, weight gradients) -- which the 16-bit modes amplify to 16-bit rounding flips.  The control
+    is the one-stream step run twice: the two-stream step may differ from it by no more than that noise (x3) + 1e-6."""
+    import bench
+    from dpmn_b200.pipeline import DPMNHotPath
+    from dpmn_b200.train import HotPathTrainer
+    pg, cm = bench.synth_weights(2)
+    B = 4
+    psn, p1, p2 = bench.synth_inputs(3, B)
+    hr = _t(np.random.default_rng(9).uniform(0, 1, (B, 4, 32, 128)).astype(np.float32))
+    args = (_t(psn), [_t(a) for a in p1], [_t(a) for a in p2], hr)
+    got = []
+    for two_streams in (True, False, False):
+        torch.manual_seed(1234)                                  # the mask seeds come from the CPU generator
+        model = DPMNHotPath(precision=prec, drop=0.1)
+        bench.load_weights(model, pg, cm)
+        model = model.to(DEV).train()
+        model.concurrent_train = two_streams
+        tr = HotPathTrainer(model)
+        tr.state.zero_grads()
+        outs = model.forward_all(*args[:3])
+        loss = tr.loss(outs, hr)
+        loss.backward()
+        torch.cuda.synchronize()
+        got.append((float(loss.detach()), tr.state.flat_grads.detach().clone(), [o.detach().clone() for o in outs]))
+    (l2, g2, o2), (l1, g1, o1), (lc, gc, oc) = got
+
+    def rel(a, b):
+        return float((a - b).abs().max()) / float(b.abs().max())
+    noise_o = max(rel(a, b) for a, b in zip(oc, o1))
+    noise_g = rel(gc, g1)
+    diff_o = max(rel(a, b) for a, b in zip(o2, o1))
+    diff_g = rel(g2, g1)
+    print(f"{prec}: outputs two-vs-one {diff_o:.3e} (control {noise_o:.3e}); gradients {diff_g:.3e} (control {noise_g:.3e}); "
+          f"loss {l2:.7f} / {l1:.7f} / {lc:.7f}")
+    assert float(g1.abs().max()) > 0
+    assert diff_o <= 3 * noise_o + 1e-6
+    assert diff_g <= 3 * noise_g + 2e-4
+    assert abs(l2 - l1) <= 3 * abs(lc - l1) + 1e-6 * abs(l1)

@@ -274,9 +274,12 @@ def run_train_leg(args, dev, world, rank, lib, dev_sets, host_sets, barrier, max
         n_prof = 2
         if rank == 0:
             lib.dpmn_profile_enable(1)
+        two_streams = model.concurrent_train
+        model.concurrent_train = False            # one stream: per-launch event times are not inflated by overlap
         for i in range(n_prof):
             trainer.step(*dev_sets[i % n_sets])
         torch.cuda.synchronize()
+        model.concurrent_train = two_streams
         prof = None
         if rank == 0:
             prof = collect_profile(lib, n_prof)
@@ -292,7 +295,9 @@ def run_train_leg(args, dev, world, rank, lib, dev_sets, host_sets, barrier, max
                          "ms_per_step": {k: round(v, 4) for k, v in comm_ms.items()}},
            "optimizer": "fused clip_grad_norm_(0.25 per module) + Adam over the flat buffers (dpmn_clip_adam_step)" if trainer.fused
                         else "torch clip_grad_norm_ + torch.optim.Adam",
-           "drop_rates": args.train_drop, "e2e": e2e}
+           "drop_rates": args.train_drop, "e2e": e2e,
+           "streams": "the two PGRM cascades (forward and backward) on two CUDA streams, CMM / losses on the main stream"
+                      if model.concurrent_train else "one stream"}
     if prof is not None:
         res["by_kernel_ms"] = {k: round(v["ms_per_step"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])}
         res["whole_step_tflops"] = 3 * FLOPS_IMG["total"] * B / (ms_step / 1e3) / 1e12    # fwd + 2x bwd algorithmic FLOPs

@@ -443,6 +443,7 @@ struct CmmWs {
   float* mid_sc[2][4];
   float* mid_sh[2][4];
   float* z;              // gated bottleneck (B, 16c, h/32, w/32)
+  float* se_h;           // SE gate hidden activations (B, 4c)
   float* d6; float *d6_sc, *d6_sh;
   float* dmid[4]; float *dmid_sc[4], *dmid_sh[4];
   float* dout[4]; float *dout_sc[4], *dout_sh[4];
@@ -473,6 +474,7 @@ CmmWs carve_cmm(const dpmn_cmm_desc* d, void* ws) {
     }
   }
   w.z = b.take<float>(B * 16 * c * (H >> 5) * (W >> 5));
+  w.se_h = b.take<float>(B * 4 * c);
   w.d6 = b.take<float>(B * 8 * c * (H >> 4) * (W >> 4));
   w.d6_sc = b.take<float>(8 * c);
   w.d6_sh = b.take<float>(8 * c);
@@ -1115,7 +1117,7 @@ static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const flo
   // ---- SE gate (cmm.py:135-147)
   const int hb = H >> 5, wb = W >> 5;
   DPMN_RUN(T_SE_GATE, launch_se_gate(w.o[0][5], w.o[1][5], w.z, d->fc1_w, d->fc1_b, d->fc2_w, d->fc2_b, B, 8 * c, hb * wb,
-                          4 * c, st), 1);
+                          4 * c, st, w.se_h), 2);
   // ---- decoder (cmm.py:149-159)
   {
     ConvArgs a;   // de_6: ReLU -> convT4x4 stride 2 pad 1 -> BN

@@ -506,12 +506,14 @@ int launch_bn_act_bwd(const BnBwdArgs& a, cudaStream_t st) {
 }
 
 // out[c] += sum_{b, r} x[(b*C + c)*HW + r]          (bias gradient of a conv whose output gradient is given directly)
+// grid (C, S): the S blocks of a channel split the (b, r) range (de_1 has 3 channels and 48 x 4096 values per channel: one
+// block per channel took 440 us).
 __global__ void __launch_bounds__(256) chan_sum_kernel(const float* __restrict__ x, int B, int C, int HW, float* __restrict__ out) {
   __shared__ float red[8];
   const int c = blockIdx.x;
   const long long n = (long long)B * HW;
   float s = 0.f;
-  for (long long i = threadIdx.x; i < n; i += 256) {
+  for (long long i = (long long)blockIdx.y * 256 + threadIdx.x; i < n; i += 256LL * gridDim.y) {
     const int b = (int)(i / HW); const int r = (int)(i - (long long)b * HW);
     s += x[((long long)b * C + c) * HW + r];
   }
@@ -520,7 +522,12 @@ __global__ void __launch_bounds__(256) chan_sum_kernel(const float* __restrict__
 }
 
 int launch_chan_sum(const float* x, int B, int C, int HW, float* out, cudaStream_t st) {
-  chan_sum_kernel<<<C, 256, 0, st>>>(x, B, C, HW, out);
+  const long long n = (long long)B * HW;
+  long long split = (n + 2047) / 2048;                   // >= 8 values per thread
+  const long long cap = (148 * 8 + C - 1) / C;           // about 8 blocks per SM over all channels
+  if (split > cap) split = cap;
+  if (split < 1) split = 1;
+  chan_sum_kernel<<<dim3(C, (unsigned)split), 256, 0, st>>>(x, B, C, HW, out);
   DPMN_LAUNCH_CHECK();
   return 0;
 }
@@ -658,18 +665,120 @@ __global__ void __launch_bounds__(256) se_gate_wgrad_kernel(const float* __restr
   }
 }
 
+// The backward over many CTAs (the one-CTA-per-image kernel above took 557 us at batch 48).  scratch (floats):
+//   rows   [B][sds C2 | sg0 C2 | sh hidden | sdh hidden]   (what se_gate_wgrad_kernel reads)
+//   sgate  [B][C2]
+//   raw    [B][hidden]   unmasked d(pre-ReLU) sums, accumulated by atomics over 8 channel slices (zeroed first)
+__global__ void __launch_bounds__(256) se_bwd_gate_kernel(const float* __restrict__ z1, const float* __restrict__ z2,
+                                                          const float* __restrict__ du, const float* __restrict__ fc2_w,
+                                                          const float* __restrict__ fc2_b, float* __restrict__ scratch,
+                                                          int B, int Cb, int hw, int hidden) {
+  extern __shared__ float sm[];
+  const int C2 = 2 * Cb, b = blockIdx.x, stride = 2 * C2 + 2 * hidden;
+  float* row = scratch + (long long)b * stride;
+  float* sgate = scratch + (long long)B * stride + (long long)b * C2;
+  for (int j = threadIdx.x; j < hidden; j += blockDim.x) sm[j] = row[2 * C2 + j];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int cc = warp; cc < 64; cc += 8) {
+    const int c = blockIdx.y * 64 + cc;
+    if (c >= C2) break;
+    float s = 0.f;
+    for (int j = lane; j < hidden; j += 32) s = fmaf(fc2_w[(long long)c * hidden + j], sm[j], s);
+    s = warp_sum(s);
+    const float g = 1.0f / (1.0f + expf(-(s + fc2_b[c])));
+    // d gate[c] = sum_hw dout * z, dout = du * [z*(1+g) > 0]
+    const float* src = c < Cb ? z1 + ((long long)b * Cb + c) * hw : z2 + ((long long)b * Cb + (c - Cb)) * hw;
+    float dg = 0.f;
+    for (int i = lane; i < hw; i += 32) {
+      const float v = src[i];
+      const float o = fmaf(v, g, v);
+      if (o > 0.f) dg = fmaf(du[((long long)b * C2 + c) * hw + i], v, dg);
+    }
+    dg = warp_sum(dg);
+    if (lane == 0) { sgate[c] = g; row[c] = dg * g * (1.0f - g); }
+  }
+}
+
+// raw[b][j] += sum over this block's channel slice of sds[b][c] fc2_w[c][j]        grid (B, 8)
+__global__ void __launch_bounds__(256) se_bwd_dh_kernel(const float* __restrict__ fc2_w, float* __restrict__ scratch, int B,
+                                                        int C2, int hidden) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, stride = 2 * C2 + 2 * hidden;
+  const float* row = scratch + (long long)b * stride;
+  float* raw = scratch + (long long)B * (stride + C2) + (long long)b * hidden;
+  const int per = (C2 + gridDim.y - 1) / gridDim.y, c0 = blockIdx.y * per, c1 = min(C2, c0 + per);
+  for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) sm[c - c0] = row[c];
+  __syncthreads();
+  for (int j = threadIdx.x; j < hidden; j += blockDim.x) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int c = c0; c < c1; ++c) s = fmaf(sm[c - c0], fc2_w[(long long)c * hidden + j], s);
+    atomicAdd(raw + j, s);
+  }
+}
+
+// sdh = raw masked by the ReLU; d pooled[c] = sum_j sdh[j] fc1_w[j][c] / hw; dz = dout (1 + g) + d pooled      grid (B, C2 / 256)
+__global__ void __launch_bounds__(256) se_bwd_dz_kernel(const float* __restrict__ z1, const float* __restrict__ z2,
+                                                        const float* __restrict__ du, const float* __restrict__ fc1_w,
+                                                        float* __restrict__ dz1, float* __restrict__ dz2,
+                                                        float* __restrict__ scratch, int B, int Cb, int hw, int hidden) {
+  extern __shared__ float sm[];
+  const int C2 = 2 * Cb, b = blockIdx.x, stride = 2 * C2 + 2 * hidden;
+  float* row = scratch + (long long)b * stride;
+  const float* sgate = scratch + (long long)B * stride + (long long)b * C2;
+  const float* raw = scratch + (long long)B * (stride + C2) + (long long)b * hidden;
+  for (int j = threadIdx.x; j < hidden; j += blockDim.x) {
+    const float d = row[2 * C2 + j] > 0.f ? raw[j] : 0.f;
+    sm[j] = d;
+    if (blockIdx.y == 0) row[2 * C2 + hidden + j] = d;
+  }
+  __syncthreads();
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C2) return;
+  float s = 0.f;
+#pragma unroll 8
+  for (int j = 0; j < hidden; ++j) s = fmaf(sm[j], fc1_w[(long long)j * C2 + c], s);
+  s /= (float)hw;                                    // d pooled -> every pixel
+  const float g = sgate[c];
+  const float* src = c < Cb ? z1 + ((long long)b * Cb + c) * hw : z2 + ((long long)b * Cb + (c - Cb)) * hw;
+  float* dst = c < Cb ? dz1 + ((long long)b * Cb + c) * hw : dz2 + ((long long)b * Cb + (c - Cb)) * hw;
+  for (int i = 0; i < hw; ++i) {
+    const float v = src[i];
+    const float o = fmaf(v, g, v);
+    const float dout = o > 0.f ? du[((long long)b * C2 + c) * hw + i] : 0.f;
+    dst[i] = fmaf(dout, 1.0f + g, s);
+  }
+}
+
+// scratch: B * (3 * 2Cb + 3 * hidden) floats (layout above), or nullptr for the one-CTA-per-image kernel with atomics.
 int launch_se_gate_bwd(const float* z1, const float* z2, const float* du, const float* fc1_w, const float* fc1_b,
                        const float* fc2_w, const float* fc2_b, float* dz1, float* dz2, float* d_fc1_w, float* d_fc1_b,
                        float* d_fc2_w, float* d_fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st, float* scratch) {
   const size_t smem = (size_t)(6 * Cb + 2 * hidden) * sizeof(float);
   if (smem > 48 * 1024) return -2;
+  if (scratch != nullptr) {
+    const int C2 = 2 * Cb, stride = 2 * C2 + 2 * hidden;
+    float* raw = scratch + (long long)B * (stride + C2);
+    DPMN_CUDA_TRY(cudaMemsetAsync(raw, 0, (size_t)B * hidden * sizeof(float), st));
+    // pooled -> rows[.][C2 ..], h -> rows[.][2 C2 ..]
+    const int rc = launch_se_pool_fc1(z1, z2, fc1_w, fc1_b, B, Cb, hw, hidden, scratch + 2 * C2, stride, scratch + C2, stride, st);
+    if (rc) return rc;
+    se_bwd_gate_kernel<<<dim3(B, (C2 + 63) / 64), 256, (size_t)hidden * sizeof(float), st>>>(z1, z2, du, fc2_w, fc2_b, scratch, B, Cb,
+                                                                                           hw, hidden);
+    DPMN_LAUNCH_CHECK();
+    se_bwd_dh_kernel<<<dim3(B, 8), 256, (size_t)((C2 + 7) / 8) * sizeof(float), st>>>(fc2_w, scratch, B, C2, hidden);
+    DPMN_LAUNCH_CHECK();
+    se_bwd_dz_kernel<<<dim3(B, (C2 + 255) / 256), 256, (size_t)hidden * sizeof(float), st>>>(z1, z2, du, fc1_w, dz1, dz2, scratch, B,
+                                                                                           Cb, hw, hidden);
+    DPMN_LAUNCH_CHECK();
+    se_gate_wgrad_kernel<<<148 * 4, 256, 0, st>>>(scratch, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, B, C2, hidden);
+    DPMN_LAUNCH_CHECK();
+    return 0;
+  }
   se_gate_bwd_kernel<<<B, 256, smem, st>>>(z1, z2, du, fc1_w, fc1_b, fc2_w, fc2_b, dz1, dz2, d_fc1_w, d_fc1_b, d_fc2_w,
                                            d_fc2_b, Cb, hw, hidden, scratch);
   DPMN_LAUNCH_CHECK();
-  if (scratch != nullptr) {
-    se_gate_wgrad_kernel<<<148 * 4, 256, 0, st>>>(scratch, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, B, 2 * Cb, hidden);
-    DPMN_LAUNCH_CHECK();
-  }
   return 0;
 }
 

@@ -425,10 +425,79 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
   }
 }
 
+// The same gate over many CTAs (one CTA per image runs 48 CTAs for 2 x 256 K multiply-adds each: 319 us at batch 48):
+// (1) grid (B, hidden / 8): every CTA pools its image (C2 x hw loads) and its 8 warps take one fc1 row each -> h (B, hidden)
+// (2) grid (B, C2 / 64):    h row in shared memory, a warp per channel: fc2 row, sigmoid, z * g + z
+__global__ void __launch_bounds__(256) se_pool_fc1_kernel(const float* __restrict__ z1, const float* __restrict__ z2,
+                                                          const float* __restrict__ fc1_w, const float* __restrict__ fc1_b,
+                                                          int Cb, int hw, int hidden, float* __restrict__ h_out, int h_stride,
+                                                          float* __restrict__ g0_out, int g0_stride) {
+  extern __shared__ float sm[];
+  const int C2 = 2 * Cb, b = blockIdx.x;
+  for (int c = threadIdx.x; c < C2; c += blockDim.x) {
+    const float* src = c < Cb ? z1 + ((long long)b * Cb + c) * hw : z2 + ((long long)b * Cb + (c - Cb)) * hw;
+    float s = 0.f;
+    for (int i = 0; i < hw; ++i) s += src[i];
+    sm[c] = s / (float)hw;
+    if (g0_out != nullptr && blockIdx.y == 0) g0_out[(long long)b * g0_stride + c] = sm[c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.y * 8 + warp;
+  if (j >= hidden) return;
+  float s = 0.f;
+  for (int c = lane; c < C2; c += 32) s = fmaf(fc1_w[(long long)j * C2 + c], sm[c], s);
+  s = warp_sum(s);
+  if (lane == 0) h_out[(long long)b * h_stride + j] = fmaxf(s + fc1_b[j], 0.f);
+}
+
+__global__ void __launch_bounds__(256) se_fc2_gate_fwd_kernel(const float* __restrict__ z1, const float* __restrict__ z2,
+                                                              float* __restrict__ z, const float* __restrict__ fc2_w,
+                                                              const float* __restrict__ fc2_b, const float* __restrict__ h,
+                                                              int h_stride, int Cb, int hw, int hidden) {
+  extern __shared__ float sm[];
+  const int C2 = 2 * Cb, b = blockIdx.x;
+  for (int j = threadIdx.x; j < hidden; j += blockDim.x) sm[j] = h[(long long)b * h_stride + j];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int cc = warp; cc < 64; cc += 8) {
+    const int c = blockIdx.y * 64 + cc;
+    if (c >= C2) break;
+    float s = 0.f;
+    for (int j = lane; j < hidden; j += 32) s = fmaf(fc2_w[(long long)c * hidden + j], sm[j], s);
+    s = warp_sum(s);
+    const float g = 1.0f / (1.0f + expf(-(s + fc2_b[c])));
+    const float* src = c < Cb ? z1 + ((long long)b * Cb + c) * hw : z2 + ((long long)b * Cb + (c - Cb)) * hw;
+    for (int i = lane; i < hw; i += 32) {
+      const float v = src[i];
+      z[((long long)b * C2 + c) * hw + i] = fmaf(v, g, v);
+    }
+  }
+}
+
+int launch_se_pool_fc1(const float* z1, const float* z2, const float* fc1_w, const float* fc1_b, int B, int Cb, int hw,
+                       int hidden, float* h_out, int h_stride, float* g0_out, int g0_stride, cudaStream_t st) {
+  if ((size_t)2 * Cb * sizeof(float) > 48 * 1024) return -2;
+  se_pool_fc1_kernel<<<dim3(B, (hidden + 7) / 8), 256, (size_t)2 * Cb * sizeof(float), st>>>(z1, z2, fc1_w, fc1_b, Cb, hw, hidden,
+                                                                                          h_out, h_stride, g0_out, g0_stride);
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
+// h_scratch: (B, hidden) floats, or nullptr for the one-CTA-per-image kernel.
 int launch_se_gate(const float* z1, const float* z2, float* z, const float* fc1_w, const float* fc1_b,
-                   const float* fc2_w, const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st) {
+                   const float* fc2_w, const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st,
+                   float* h_scratch) {
   const size_t smem = (size_t)(2 * Cb + hidden) * sizeof(float);
   if (smem > 48 * 1024) return -2;
+  if (h_scratch != nullptr) {
+    const int rc = launch_se_pool_fc1(z1, z2, fc1_w, fc1_b, B, Cb, hw, hidden, h_scratch, hidden, nullptr, 0, st);
+    if (rc) return rc;
+    se_fc2_gate_fwd_kernel<<<dim3(B, (2 * Cb + 63) / 64), 256, (size_t)hidden * sizeof(float), st>>>(z1, z2, z, fc2_w, fc2_b,
+                                                                                                   h_scratch, hidden, Cb, hw, hidden);
+    DPMN_LAUNCH_CHECK();
+    return 0;
+  }
   se_gate_kernel<<<B, 256, smem, st>>>(z1, z2, z, fc1_w, fc1_b, fc2_w, fc2_b, Cb, hw, hidden);
   DPMN_LAUNCH_CHECK();
   return 0;

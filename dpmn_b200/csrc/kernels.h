@@ -283,7 +283,11 @@ int launch_bn_affine(const float* x, int B, int C, int HW, const float* w, const
 
 // SE gate on the concatenated bottleneck (cmm.py:135-147): z (B, 2*Cb, hw) from two (B, Cb, hw) halves.
 int launch_se_gate(const float* z1, const float* z2, float* z, const float* fc1_w, const float* fc1_b,
-                   const float* fc2_w, const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st);
+                   const float* fc2_w, const float* fc2_b, int B, int Cb, int hw, int hidden, cudaStream_t st,
+                   float* h_scratch = nullptr);
+// pooled mean (optional output) + relu(fc1) of the SE gate over B x hidden / 8 CTAs (shared by the forward and the backward)
+int launch_se_pool_fc1(const float* z1, const float* z2, const float* fc1_w, const float* fc1_b, int B, int Cb, int hw,
+                       int hidden, float* h_out, int h_stride, float* g0_out, int g0_stride, cudaStream_t st);
 
 // ---- neighbours of the hot path (loss_mask.cu) ------------------------------------------------------------------
 // loss[0] += scale * ImageLoss(out, target); d_out (dense (B,C,H,W), may be nullptr) = scale * d ImageLoss / d out

@@ -60,6 +60,51 @@ struct ProfScope {
     g_launches.fetch_add(n_kernels);         \
   } while (0)
 
+// The CMM's two encoder branches (cmm.py:121-133) are independent chains of small-grid kernels until the SE gate: in the
+// fp32-structured forward and in the backward the second branch runs on a library-owned side stream per device, forked
+// from / joined to the caller's stream by events, so the caller still sees plain stream semantics (everything enqueued by
+// a call is ordered before whatever the caller enqueues next on its stream; works under stream capture as well).  Each
+// branch has its own scratch.  DPMN_CMM_FORK=0: one stream.
+struct BranchFork {
+  cudaStream_t main = nullptr, aux = nullptr;
+  cudaEvent_t ev = nullptr;
+  bool on = false;
+  static cudaStream_t aux_for_device() {
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> g(mu);
+    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
+    return streams[dev];
+  }
+  // the side stream waits for everything enqueued on `m` so far; false: stay on one stream
+  bool begin(cudaStream_t m) {
+    static const bool enabled = !(getenv("DPMN_CMM_FORK") && atoi(getenv("DPMN_CMM_FORK")) == 0);
+    main = m;
+    if (!enabled) return false;
+    aux = aux_for_device();
+    if (!aux || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; return false; }
+    if (cudaEventRecord(ev, main) != cudaSuccess || cudaStreamWaitEvent(aux, ev, 0) != cudaSuccess) {
+      cudaEventDestroy(ev); ev = nullptr;
+      return false;
+    }
+    on = true;
+    return true;
+  }
+  // the caller's stream waits for the side stream
+  cudaError_t end() {
+    if (!on) return cudaSuccess;
+    on = false;
+    cudaError_t e = cudaEventRecord(ev, aux);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(main, ev, 0);
+    cudaEventDestroy(ev);
+    ev = nullptr;
+    return e;
+  }
+  ~BranchFork() { end(); }     // error returns inside the forked region still join
+};
+
 struct Bump {
   char* base;
   size_t off = 0, cap;
@@ -448,6 +493,7 @@ struct CmmWs {
   float* dmid[4]; float *dmid_sc[4], *dmid_sh[4];
   float* dout[4]; float *dout_sc[4], *dout_sh[4];
   ConvTcScratch tc;      // 16-bit modes: the convs of this fp32-structured path run on tcgen05 through an im2col
+  ConvTcScratch tc2;     // the second encoder branch's scratch (it runs on the side stream, BranchFork)
   size_t bytes;
 };
 
@@ -501,6 +547,13 @@ CmmWs carve_cmm(const dpmn_cmm_desc* d, void* ws) {
     w.tc.part = b.take<float>(w.tc.part_bytes / 4);
     w.tc.act_bytes = B * H * W * 3 * c * 2;                              // widest conv input: de_1's concat at full resolution
     w.tc.act = b.take<char>(w.tc.act_bytes);
+    // second branch: same sizes (its data-gradient im2col of EncodeBlock 1 is as wide as the decoder's)
+    w.tc2 = w.tc;
+    w.tc2.col = b.take<char>(w.tc2.col_bytes);
+    w.tc2.w16 = b.take<char>(w.tc2.w16_bytes);
+    w.tc2.dy16 = b.take<char>(w.tc2.dy16_bytes);
+    w.tc2.part = b.take<float>(w.tc2.part_bytes / 4);
+    w.tc2.act = b.take<char>(w.tc2.act_bytes);
   }
   w.bytes = b.off + 256;
   return w;
@@ -1068,8 +1121,13 @@ static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const flo
   const int ch_o[6] = {c, 2 * c, 4 * c, 8 * c, 8 * c, 8 * c};
   const float* xin[2] = {x1, x2};
 
-  // ---- encoders (cmm.py:121-133)
+  // ---- encoders (cmm.py:121-133): branch 2 on the side stream with its own scratch (BranchFork)
+  BranchFork fork;
+  const cudaStream_t st_main = st;
+  const bool forked = fork.begin(st_main);
   for (int br = 0; br < 2; ++br) {
+    st = (br == 1 && forked) ? fork.aux : st_main;                       // DPMN_RUN and the launches below use `st`
+    const ConvTcScratch& tcs = (br == 1 && forked) ? w.tc2 : w.tc;
     {
       ConvArgs a;   // en_1: conv3x3 c_img -> cnum, no activation before, no BN after
       a.n_seg = 1; a.in[0] = xin[br]; a.seg_ch[0] = d->c_img;
@@ -1077,7 +1135,7 @@ static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const flo
       if (bs != 0 && bs != (long long)d->c_img * H * W) return DPMN_E_UNSUPPORTED;
       a.w = d->en1_w[br]; a.bias = d->en1_b[br]; a.out = w.o[br][0];
       a.B = B; a.Cin = d->c_img; a.H = H; a.W = W; a.Cout = c; a.Ho = H; a.Wo = W; a.k = 3; a.stride = 1; a.pad = 1;
-      DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
+      DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, tcs, use_tc, st), 1);
     }
     for (int l = 0; l < 4; ++l) {
       const dpmn_cmm_stage& s = d->enc[br][l];
@@ -1089,7 +1147,7 @@ static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const flo
         a.w = s.conv_a_w; a.bias = s.conv_a_b; a.out = w.mid[br][l];
         a.B = B; a.Cin = ch_o[l]; a.H = hi; a.W = wi; a.Cout = ch_o[l]; a.Ho = ho; a.Wo = wo;
         a.k = 4; a.stride = 2; a.pad = 3; a.dil = 2;
-        DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
+        DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, tcs, use_tc, st), 1);
       }
       DPMN_RUN(T_BN, bn_affine(d, s.bn_a, w.mid[br][l], ch_o[l], ho * wo, w.mid_sc[br][l], w.mid_sh[br][l], st), 1);
       {
@@ -1099,7 +1157,7 @@ static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const flo
         a.w = s.conv_b_w; a.bias = s.conv_b_b; a.out = w.o[br][l + 1];
         a.B = B; a.Cin = ch_o[l]; a.H = ho; a.W = wo; a.Cout = ch_o[l + 1]; a.Ho = ho; a.Wo = wo;
         a.k = 3; a.stride = 1; a.pad = 1;
-        DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
+        DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, tcs, use_tc, st), 1);
       }
       DPMN_RUN(T_BN, bn_affine(d, s.bn_b, w.o[br][l + 1], ch_o[l + 1], ho * wo, w.o_sc[br][l + 1], w.o_sh[br][l + 1], st), 1);
     }
@@ -1111,9 +1169,11 @@ static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const flo
       a.w = d->en6_w[br]; a.bias = d->en6_b[br]; a.out = w.o[br][5];
       a.B = B; a.Cin = ch_o[4]; a.H = hi; a.W = wi; a.Cout = ch_o[5]; a.Ho = hi / 2; a.Wo = wi / 2;
       a.k = 4; a.stride = 2; a.pad = 1;
-      DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
+      DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, tcs, use_tc, st), 1);
     }
   }
+  st = st_main;
+  DPMN_CUDA_TRY(fork.end());
   // ---- SE gate (cmm.py:135-147)
   const int hb = H >> 5, wb = W >> 5;
   DPMN_RUN(T_SE_GATE, launch_se_gate(w.o[0][5], w.o[1][5], w.z, d->fc1_w, d->fc1_b, d->fc2_w, d->fc2_b, B, 8 * c, hb * wb,

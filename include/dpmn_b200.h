@@ -22,6 +22,11 @@
  *   - the library never allocates or frees device memory and never synchronises: the caller passes a
  *     workspace of at least dpmn_*_workspace_bytes() and a stream (cudaStream_t as void*)
  *   - weights are read in place in the reference's own state_dict layout; nothing is cached across calls
+ *   - one exception to "the caller's stream only": dpmn_cmm_backward and the fp32-structured dpmn_cmm_forward run the
+ *     CMM's second encoder branch (independent of the first until the SE gate, cmm.py:121-133) on a library-owned
+ *     non-blocking side stream per device, forked from and joined to the caller's stream by events inside the call.  The
+ *     caller still sees plain stream semantics (the call's work is ordered between what the caller enqueued before and
+ *     after it; legal under stream capture).  DPMN_CMM_FORK=0 in the environment keeps everything on the caller's stream.
  */
 #ifndef DPMN_B200_H
 #define DPMN_B200_H

@@ -234,6 +234,61 @@ int launch_transpose_convert(const float* src, void* dst, DType t, int batch, in
   return 0;
 }
 
+// One pass over a gradient matrix src (R, Cc) fp32 for everything a Linear's backward wants from it (16-bit modes):
+//   copy16 (R, Cc) for the data-gradient GEMM, trans16 (Cc, R) for the weight-gradient GEMM (contraction over rows),
+//   colsum[c] += sum_r src[r][c] for the bias gradient  -- instead of convert + transpose_convert + colsum (three reads).
+// Block = 32 columns x 128 rows (four 32 x 32 shared-memory tiles).
+template <typename T>
+__global__ void __launch_bounds__(256) stage_grad_kernel(const float* __restrict__ src, T* __restrict__ copy16,
+                                                         T* __restrict__ trans16, float* __restrict__ colsum, int R, int Cc) {
+  __shared__ float tile[32][33];
+  __shared__ float red[8][33];
+  const int c0 = blockIdx.x * 32, rb = blockIdx.y * 128;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float cs = 0.f;
+  for (int sub = 0; sub < 4; ++sub) {
+    const int r0 = rb + sub * 32;
+    if (r0 >= R) break;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty + 8 * i, c = c0 + tx;
+      const bool ok = r < R && c < Cc;
+      const float v = ok ? src[(long long)r * Cc + c] : 0.f;
+      tile[ty + 8 * i][tx] = v;
+      cs += v;
+      if (ok && copy16 != nullptr) copy16[(long long)r * Cc + c] = from_f32<T>(v);
+    }
+    __syncthreads();
+    if (trans16 != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;
+        if (c < Cc && r < R) trans16[(long long)c * R + r] = from_f32<T>(tile[tx][ty + 8 * i]);
+      }
+    }
+    __syncthreads();
+  }
+  if (colsum != nullptr) {
+    red[ty][tx] = cs;
+    __syncthreads();
+    if (ty == 0 && c0 + tx < Cc) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][tx];
+      atomicAdd(colsum + c0 + tx, t);
+    }
+  }
+}
+
+int launch_stage_grad(const float* src, void* copy16, void* trans16, float* colsum, DType t, int R, int Cc, cudaStream_t st) {
+  dim3 grid((Cc + 31) / 32, (R + 127) / 128);
+  if (t == DT_F16) stage_grad_kernel<__half><<<grid, 256, 0, st>>>(src, (__half*)copy16, (__half*)trans16, colsum, R, Cc);
+  else if (t == DT_BF16) stage_grad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, (__nv_bfloat16*)copy16, (__nv_bfloat16*)trans16, colsum, R, Cc);
+  else return -1;
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
 // dst[i] += sum_s partial[s*n + i]      (split-K partial products of the tensor-core weight gradients)
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ dst, int S, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -158,7 +158,9 @@ int launch_colsum(const float* x, long long ld, int rows, int N, float* out, cud
 int launch_rowsum(const float* x, int rows, int len, int mod, float* out, cudaStream_t st);      // out[row % mod] += sum_j
 int launch_gelu_bwd(float* g, const float* x, long long n, cudaStream_t st);                      // g *= gelu'(x)
 int launch_add(const float* a, const float* b, float* y, long long n, cudaStream_t st);
-int launch_transpose_convert(const float* src, void* dst, DType t, int batch, int R, int Cc, cudaStream_t st);   // (R,Cc) fp32 -> (Cc,R) 16-bit
+int launch_transpose_convert(const float* src, void* dst, DType t, int batch, int R, int Cc, cudaStream_t st);
+// one pass: 16-bit copy (R, Cc), 16-bit transpose (Cc, R) and column sums (+=) of an fp32 gradient matrix; any output may be null
+int launch_stage_grad(const float* src, void* copy16, void* trans16, float* colsum, DType t, int R, int Cc, cudaStream_t st);   // (R,Cc) fp32 -> (Cc,R) 16-bit
 int launch_reduce_partials(const float* partial, float* dst, int S, long long n, cudaStream_t st);           // dst += sum_s partial[s]
 int launch_layernorm_bwd(const float* dy, const float* x, const float* w, float* dx, int accumulate, float* dw,
                          float* db, int rows, int C, cudaStream_t st);

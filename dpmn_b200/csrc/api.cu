@@ -489,6 +489,7 @@ struct CmmWs {
   float* mid_sh[2][4];
   float* z;              // gated bottleneck (B, 16c, h/32, w/32)
   float* se_h;           // SE gate hidden activations (B, 4c)
+  double* bn_stats[2];   // batch-statistics partial sums (launch_bn_affine), one per stream of the forked encoder section
   float* d6; float *d6_sc, *d6_sh;
   float* dmid[4]; float *dmid_sc[4], *dmid_sh[4];
   float* dout[4]; float *dout_sc[4], *dout_sh[4];
@@ -521,6 +522,7 @@ CmmWs carve_cmm(const dpmn_cmm_desc* d, void* ws) {
   }
   w.z = b.take<float>(B * 16 * c * (H >> 5) * (W >> 5));
   w.se_h = b.take<float>(B * 4 * c);
+  for (int i = 0; i < 2; ++i) w.bn_stats[i] = b.take<double>(bn_stats_scratch_doubles((int)(16 * c)));
   w.d6 = b.take<float>(B * 8 * c * (H >> 4) * (W >> 4));
   w.d6_sc = b.take<float>(8 * c);
   w.d6_sh = b.take<float>(8 * c);
@@ -560,10 +562,10 @@ CmmWs carve_cmm(const dpmn_cmm_desc* d, void* ws) {
 }
 
 int bn_affine(const dpmn_cmm_desc* d, const dpmn_bn& bn, const float* x, int ch, int hw, float* sc, float* sh,
-              cudaStream_t st) {
+              cudaStream_t st, double* stats_scratch) {
   if (!bn.w || !bn.b || !bn.running_mean || !bn.running_var) return DPMN_E_ARG;
   return launch_bn_affine(x, d->batch, ch, hw, bn.w, bn.b, bn.running_mean, bn.running_var, d->training,
-                          d->training && d->update_running_stats, 1e-5f, sc, sh, st);
+                          d->training && d->update_running_stats, 1e-5f, sc, sh, st, stats_scratch);
 }
 
 
@@ -1128,6 +1130,7 @@ static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const flo
   for (int br = 0; br < 2; ++br) {
     st = (br == 1 && forked) ? fork.aux : st_main;                       // DPMN_RUN and the launches below use `st`
     const ConvTcScratch& tcs = (br == 1 && forked) ? w.tc2 : w.tc;
+    double* bnst = w.bn_stats[(br == 1 && forked) ? 1 : 0];
     {
       ConvArgs a;   // en_1: conv3x3 c_img -> cnum, no activation before, no BN after
       a.n_seg = 1; a.in[0] = xin[br]; a.seg_ch[0] = d->c_img;
@@ -1149,7 +1152,7 @@ static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const flo
         a.k = 4; a.stride = 2; a.pad = 3; a.dil = 2;
         DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, tcs, use_tc, st), 1);
       }
-      DPMN_RUN(T_BN, bn_affine(d, s.bn_a, w.mid[br][l], ch_o[l], ho * wo, w.mid_sc[br][l], w.mid_sh[br][l], st), 1);
+      DPMN_RUN(T_BN, bn_affine(d, s.bn_a, w.mid[br][l], ch_o[l], ho * wo, w.mid_sc[br][l], w.mid_sh[br][l], st, bnst), 1);
       {
         ConvArgs a;   // LeakyReLU -> conv3x3 (cmm.py:46-49)
         a.n_seg = 1; a.in[0] = w.mid[br][l]; a.seg_ch[0] = ch_o[l];
@@ -1159,7 +1162,7 @@ static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const flo
         a.k = 3; a.stride = 1; a.pad = 1;
         DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, tcs, use_tc, st), 1);
       }
-      DPMN_RUN(T_BN, bn_affine(d, s.bn_b, w.o[br][l + 1], ch_o[l + 1], ho * wo, w.o_sc[br][l + 1], w.o_sh[br][l + 1], st), 1);
+      DPMN_RUN(T_BN, bn_affine(d, s.bn_b, w.o[br][l + 1], ch_o[l + 1], ho * wo, w.o_sc[br][l + 1], w.o_sh[br][l + 1], st, bnst), 1);
     }
     {
       ConvArgs a;   // en_6: LeakyReLU -> conv4x4 stride 2 pad 1 (cmm.py:91-93)
@@ -1186,7 +1189,7 @@ static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const flo
     a.B = B; a.Cin = 16 * c; a.H = hb; a.W = wb; a.Cout = 8 * c; a.Ho = 2 * hb; a.Wo = 2 * wb;
     a.k = 4; a.stride = 2; a.pad = 1; a.transposed = 1;
     DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
-    DPMN_RUN(T_BN, bn_affine(d, d->de6_bn, w.d6, 8 * c, 4 * hb * wb, w.d6_sc, w.d6_sh, st), 1);
+    DPMN_RUN(T_BN, bn_affine(d, d->de6_bn, w.d6, 8 * c, 4 * hb * wb, w.d6_sc, w.d6_sh, st, w.bn_stats[0]), 1);
   }
   const float* dprev = w.d6;
   const float *dprev_sc = w.d6_sc, *dprev_sh = w.d6_sh;
@@ -1210,7 +1213,7 @@ static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const flo
       a.k = 3; a.stride = 1; a.pad = 1; a.transposed = 1;
       DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
     }
-    DPMN_RUN(T_BN, bn_affine(d, s.bn_a, w.dmid[i], ch_d[i], hi * wi, w.dmid_sc[i], w.dmid_sh[i], st), 1);
+    DPMN_RUN(T_BN, bn_affine(d, s.bn_a, w.dmid[i], ch_d[i], hi * wi, w.dmid_sc[i], w.dmid_sh[i], st, w.bn_stats[0]), 1);
     {
       ConvArgs a;   // ReLU -> convT4x4 stride 2 pad 1 (cmm.py:66-69)
       a.n_seg = 1; a.in[0] = w.dmid[i]; a.seg_ch[0] = ch_d[i];
@@ -1220,7 +1223,7 @@ static int cmm_forward_struct(const dpmn_cmm_desc* d, const float* x1, const flo
       a.k = 4; a.stride = 2; a.pad = 1; a.transposed = 1;
       DPMN_RUN(use_tc ? T_CONV_TC : T_CONV, cmm_conv_any(a, w.tc, use_tc, st), 1);
     }
-    DPMN_RUN(T_BN, bn_affine(d, s.bn_b, w.dout[i], ch_d[i], 4 * hi * wi, w.dout_sc[i], w.dout_sh[i], st), 1);
+    DPMN_RUN(T_BN, bn_affine(d, s.bn_b, w.dout[i], ch_d[i], 4 * hi * wi, w.dout_sc[i], w.dout_sh[i], st, w.bn_stats[0]), 1);
     dprev = w.dout[i]; dprev_sc = w.dout_sc[i]; dprev_sh = w.dout_sh[i]; dprev_ch = ch_d[i];
   }
   {

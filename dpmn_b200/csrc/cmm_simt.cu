@@ -373,9 +373,78 @@ __global__ void __launch_bounds__(256) bn_affine_kernel(const float* __restrict_
   }
 }
 
+// Batch statistics over many CTAs: grid (C, S) accumulates (sum, sum of squares) of a slice in fp64 (one pass; the fp64
+// difference E[x^2] - E[x]^2 keeps the two-pass kernel's accuracy), then one thread per channel finishes.  The one-block-per-
+// channel kernel above runs 64 blocks for the 64-channel layers (49 K - 196 K values each, two passes): 80 us per launch.
+__global__ void __launch_bounds__(256) bn_stats_slices_kernel(const float* __restrict__ x, int B, int C, int HW, int hw_shift,
+                                                              double* __restrict__ part) {
+  __shared__ double red[2][8];
+  const int c = blockIdx.x, S = gridDim.y;
+  const long long n = (long long)B * HW;
+  const long long per = (n + S - 1) / S, i0 = blockIdx.y * per, i1 = i0 + per < n ? i0 + per : n;
+  double s = 0.0, q = 0.0;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const int bb = hw_shift >= 0 ? (int)(i >> hw_shift) : (int)(i / HW);
+    const int r = (int)(i - (long long)bb * HW);
+    const double v = (double)x[((long long)bb * C + c) * HW + r];
+    s += v;
+    q = fma(v, v, q);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = s; red[1][warp] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ts += red[0][k]; tq += red[1][k]; }
+    part[((long long)c * S + blockIdx.y) * 2] = ts;
+    part[((long long)c * S + blockIdx.y) * 2 + 1] = tq;
+  }
+}
+
+__global__ void bn_affine_finish_kernel(const double* __restrict__ part, int S, long long n, int C, const float* __restrict__ w,
+                                        const float* __restrict__ b, float* run_mean, float* run_var, int update_running,
+                                        float eps, float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < S; ++k) { s += part[((long long)c * S + k) * 2]; q += part[((long long)c * S + k) * 2 + 1]; }
+  const double mean_d = s / (double)n;
+  double ss = q - s * mean_d;                            // sum of squared deviations
+  if (ss < 0.0) ss = 0.0;
+  const float mean = (float)mean_d, var = (float)(ss / (double)n);
+  if (update_running && run_mean != nullptr) {
+    const float unbiased = n > 1 ? (float)(ss / (double)(n - 1)) : var;
+    run_mean[c] = 0.9f * run_mean[c] + 0.1f * mean;
+    run_var[c] = 0.9f * run_var[c] + 0.1f * unbiased;
+  }
+  const float sc = w[c] / sqrtf(var + eps);
+  scale[c] = sc;
+  shift[c] = b[c] - mean * sc;
+}
+
+// stats_scratch: BN_STATS_SCRATCH_DOUBLES(C) doubles for the sliced training-statistics path, or nullptr (one block per channel)
 int launch_bn_affine(const float* x, int B, int C, int HW, const float* w, const float* b, float* run_mean,
                      float* run_var, int training, int update_running, float eps, float* scale, float* shift,
-                     cudaStream_t st) {
+                     cudaStream_t st, double* stats_scratch) {
+  if (training && stats_scratch != nullptr) {
+    const long long n = (long long)B * HW;
+    int S = (148 * 4 + C - 1) / C;
+    if (S > BN_STATS_MAX_SLICES) S = BN_STATS_MAX_SLICES;
+    const long long cap = (n + 1023) / 1024;             // at least 4 values per thread
+    if (S > cap) S = (int)cap;
+    if (S < 1) S = 1;
+    int sh = -1;
+    for (int k = 0; k < 31; ++k) if ((1 << k) == HW) sh = k;
+    bn_stats_slices_kernel<<<dim3(C, S), 256, 0, st>>>(x, B, C, HW, sh, stats_scratch);
+    DPMN_LAUNCH_CHECK();
+    bn_affine_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats_scratch, S, n, C, w, b, run_mean, run_var, update_running, eps,
+                                                           scale, shift);
+    DPMN_LAUNCH_CHECK();
+    return 0;
+  }
   bn_affine_kernel<<<C, 256, 0, st>>>(x, B, C, HW, w, b, run_mean, run_var, training, update_running, eps, scale,
                                       shift);
   DPMN_LAUNCH_CHECK();

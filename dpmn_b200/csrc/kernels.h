@@ -279,9 +279,11 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 // BatchNorm2d as a per-channel affine (scale, shift) of a raw conv output x (B, C, HW):
 // training: biased batch statistics of x (and, if run_mean != nullptr, the momentum-0.1 running update
 // with the unbiased variance, as nn.BatchNorm2d does); eval: running statistics.
+constexpr int BN_STATS_MAX_SLICES = 16;
+inline size_t bn_stats_scratch_doubles(int C) { return (size_t)C * BN_STATS_MAX_SLICES * 2; }
 int launch_bn_affine(const float* x, int B, int C, int HW, const float* w, const float* b, float* run_mean,
                      float* run_var, int training, int update_running, float eps, float* scale, float* shift,
-                     cudaStream_t st);
+                     cudaStream_t st, double* stats_scratch = nullptr);
 
 // SE gate on the concatenated bottleneck (cmm.py:135-147): z (B, 2*Cb, hw) from two (B, Cb, hw) halves.
 int launch_se_gate(const float* z1, const float* z2, float* z, const float* fc1_w, const float* fc1_b,

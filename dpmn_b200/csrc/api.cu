@@ -92,6 +92,17 @@ struct BranchFork {
     on = true;
     return true;
   }
+  // the side stream additionally waits for everything enqueued on the caller's stream up to now
+  cudaError_t aux_wait_main() {
+    if (!on) return cudaSuccess;
+    cudaEvent_t e2 = nullptr;
+    cudaError_t e = cudaEventCreateWithFlags(&e2, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    e = cudaEventRecord(e2, main);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(aux, e2, 0);
+    cudaEventDestroy(e2);
+    return e;
+  }
   // the caller's stream waits for the side stream
   cudaError_t end() {
     if (!on) return cudaSuccess;

@@ -69,21 +69,24 @@ struct BranchFork {
   cudaStream_t main = nullptr, aux = nullptr;
   cudaEvent_t ev = nullptr;
   bool on = false;
-  static cudaStream_t aux_for_device() {
+  static cudaStream_t aux_for_device(int slot) {
     static std::mutex mu;
-    static cudaStream_t streams[64] = {};
+    static cudaStream_t streams[64][3] = {};
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || slot < 0 || slot >= 3) return nullptr;
     std::lock_guard<std::mutex> g(mu);
-    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
-    return streams[dev];
+    if (!streams[dev][slot] && cudaStreamCreateWithFlags(&streams[dev][slot], cudaStreamNonBlocking) != cudaSuccess)
+      streams[dev][slot] = nullptr;
+    return streams[dev][slot];
   }
-  // the side stream waits for everything enqueued on `m` so far; false: stay on one stream
-  bool begin(cudaStream_t m) {
+  // the side stream waits for everything enqueued on `m` so far; false: stay on one stream.  slot 0: the CMM's side stream;
+  // 1 / 2: the PGRM backward's (two cascades run their backwards concurrently on two caller streams: one side stream each,
+  // picked by the caller stream's handle)
+  bool begin(cudaStream_t m, int slot = 0) {
     static const bool enabled = !(getenv("DPMN_CMM_FORK") && atoi(getenv("DPMN_CMM_FORK")) == 0);
     main = m;
     if (!enabled) return false;
-    aux = aux_for_device();
+    aux = aux_for_device(slot);
     if (!aux || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { ev = nullptr; return false; }
     if (cudaEventRecord(ev, main) != cudaSuccess || cudaStreamWaitEvent(aux, ev, 0) != cudaSuccess) {
       cudaEventDestroy(ev); ev = nullptr;

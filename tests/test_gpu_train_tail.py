@@ -191,6 +191,10 @@ def test_two_stream_training_step_gives_the_one_stream_gradients(prec):
     print(f"{prec}: outputs two-vs-one {diff_o:.3e} (control {noise_o:.3e}); gradients {diff_g:.3e} (control {noise_g:.3e}); "
           f"loss {l2:.7f} / {l1:.7f} / {lc:.7f}")
     assert float(g1.abs().max()) > 0
-    assert diff_o <= 3 * noise_o + 1e-6
+    # floor: which kernels run next to each other changes the order of fp32 atomics (pooled sums, BatchNorm statistics) even when
+    # two one-stream runs happen to be bit-identical (under compute-sanitizer they are); a 16-bit mode turns that last-bit noise
+    # into 16-bit rounding flips (2^-11 relative per flipped value)
+    floor_o = 1e-6 if prec == "fp32" else 5e-4
+    assert diff_o <= 3 * noise_o + floor_o
     assert diff_g <= 3 * noise_g + 2e-4
     assert abs(l2 - l1) <= 3 * abs(lc - l1) + 1e-6 * abs(l1)

@@ -651,6 +651,17 @@ def run_ours(args):
             if not parity["ok"]:
                 print(f"bench.py: PARITY FAILURE in the timed configuration: {err:.3e} >= {bar}", file=sys.stderr)
 
+    # north_star: images/s "as fraction of the attention-FLOP roofline": what the N GPUs could deliver if the step were nothing but
+    # its window-attention contractions (132.1 MFLOP and, for the HBM-bound stand-alone kernel, 9.4 MB per image)
+    attn_flops_img, attn_bytes_img = FLOPS_IMG["window_attn_tc"], MIN_BYTES_IMG["window_attn_tc"]
+    ips_tensor = world * tensor_peak * 1e12 / attn_flops_img
+    ips_hbm = world * hbm_peak * 1e9 / attn_bytes_img
+    attention_roofline = {"attention_flops_per_image": attn_flops_img, "attention_min_bytes_per_image": attn_bytes_img,
+                          "images_per_s_at_tensor_peak": ips_tensor, "frac_of_attention_flop_roofline": value / ips_tensor,
+                          "images_per_s_at_hbm_peak": ips_hbm, "frac_of_attention_hbm_roofline": value / ips_hbm,
+                          "note": "whole hot-path images/s over the images/s the attention contractions alone would allow on "
+                                  f"{world} GPU(s) at the measured tensor peak / at the measured HBM peak (the stand-alone kernel is HBM-bound)"}
+    roofline["attention_roofline"] = attention_roofline
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": dtype, "data": "synthetic",

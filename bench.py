@@ -66,11 +66,11 @@ BYTES_IMG = {
 def ncu_traffic_per_launch(kernel_class):
     """Mean dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel class, read from the committed summaries of
     the `ncu --set full` captures (profiles/*.txt, written by tools/ncu_summary.py); None when the class was not captured."""
-    files = {"gemm_tc": (("r02_ncu_full_block_v4.txt", "r02_ncu_full_block.txt", "r01_ncu_full_fp16_v14.txt"), ("gemm_tc_kernel", "gemm_res_ln_kernel")),
+    files = {"gemm_tc": (("r02_ncu_full_block_v5.txt", "r02_ncu_full_block_v4.txt", "r02_ncu_full_block.txt", "r01_ncu_full_fp16_v14.txt"), ("gemm_tc_kernel", "gemm_res_ln_kernel")),
              "conv_tc": (("r01_ncu_full_conv_tc_v21.txt",), ("conv_tc_kernel<64>", "conv_tc_kernel<128>")),
              "dwconv": (("r01_ncu_full_dwconv_v2_en1_v23.txt",), ("dwconv16_v2_kernel",)),
-             "mlp_fc1_dw_tc": (("r02_ncu_full_block_v4.txt", "r02_ncu_full_block.txt"), ("mlp_fc1_dw_kernel",)),
-             "window_attn_tc": (("r02_ncu_full_block_v4.txt", "r02_ncu_full_block.txt", "r01_ncu_full_fp16_v14.txt"), ("attn2_tc_kernel", "attn_tc_kernel"))}
+             "mlp_fc1_dw_tc": (("r02_ncu_full_block_v5.txt", "r02_ncu_full_block_v4.txt", "r02_ncu_full_block.txt"), ("mlp_fc1_dw_kernel",)),
+             "window_attn_tc": (("r02_ncu_full_block_v5.txt", "r02_ncu_full_block_v4.txt", "r02_ncu_full_block.txt", "r01_ncu_full_fp16_v14.txt"), ("attn2_tc_kernel", "attn_tc_kernel"))}
     if kernel_class not in files:
         return None
     names, kernels = files[kernel_class]

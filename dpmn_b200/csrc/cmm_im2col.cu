@@ -293,6 +293,53 @@ __global__ void reduce_conv_partials_kernel(const float* __restrict__ partial, f
   dw[o] += a;
 }
 
+// The same for the tap-major k order (k = tap * Cin + ci) through a shared-memory tile of 8 output channels x 32 input channels
+// x all taps: the partials are read along ci (coalesced), dw is written in runs of 32 * kk (reference layout (co, ci, tap))
+// or 8 * kk (transposed-conv layout (ci, co, tap)) consecutive floats.  The flat kernel above writes consecutive threads kk
+// floats apart: every 4-byte read-modify-write of dw costs two 32-byte sectors (1.6 ms per training step over the CMM's
+// 53.6 M weights).
+__global__ void __launch_bounds__(256) reduce_conv_partials_tiled_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                                         int S, int Cout, int Cin, int kk, int transposed, int Kp) {
+  __shared__ float tile[8][16][33];
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ci = ci0 + lane;
+  for (int row = warp; row < 8 * kk; row += 8) {
+    const int co_l = row / kk, tap = row - co_l * kk;
+    const int co = co0 + co_l;
+    float a = 0.f;
+    if (co < Cout && ci < Cin) {
+      const float* src = partial + (long long)co * Kp + (long long)tap * Cin + ci;
+      const long long sstride = (long long)Cout * Kp;
+      for (int sidx = 0; sidx < S; ++sidx) a += src[sidx * sstride];
+    }
+    tile[co_l][tap][lane] = a;
+  }
+  __syncthreads();
+  if (!transposed) {
+    const int n_ci = min(32, Cin - ci0);
+    for (int co_l = 0; co_l < 8; ++co_l) {
+      const int co = co0 + co_l;
+      if (co >= Cout) break;
+      float* dst = dw + ((long long)co * Cin + ci0) * kk;
+      for (int j = threadIdx.x; j < n_ci * kk; j += 256) {
+        const int ci_l = j / kk, tap = j - ci_l * kk;
+        dst[j] += tile[co_l][tap][ci_l];
+      }
+    }
+  } else {
+    const int n_co = min(8, Cout - co0);
+    for (int ci_l = warp; ci_l < 32; ci_l += 8) {
+      if (ci0 + ci_l >= Cin) break;
+      float* dst = dw + ((long long)(ci0 + ci_l) * Cout + co0) * kk;
+      for (int j = lane; j < n_co * kk; j += 32) {
+        const int co_l = j / kk, tap = j - co_l * kk;
+        dst[j] += tile[co_l][tap][ci_l];
+      }
+    }
+  }
+}
+
 template <typename T>
 static int conv_tc_im2col_t(const ConvArgs& a, const ConvTcScratch& s, cudaStream_t st) {
   const int kk = a.k * a.k, K = a.Cin * kk, Kp = (K + 15) / 16 * 16;
@@ -383,8 +430,13 @@ static int conv_wgrad_tc_im2col_t(const ConvArgs& a, const float* dy, float* dw,
   g.M = a.Cout; g.N = Kp; g.K = (int)chunk; g.batch = S;
   int rc = launch_gemm_tc(g, st);
   if (rc) return rc;
-  reduce_conv_partials_kernel<<<(unsigned)(((long long)a.Cout * K + 255) / 256), 256, 0, st>>>(s.part, dw, S, a.Cout, a.Cin, kk,
-                                                                                          a.transposed, Kp, fast ? 1 : 0);
+  static const bool tiled = !(getenv("DPMN_REDUCE_TILED") && atoi(getenv("DPMN_REDUCE_TILED")) == 0);
+  if (tiled && fast && kk <= 16)
+    reduce_conv_partials_tiled_kernel<<<dim3((a.Cin + 31) / 32, (a.Cout + 7) / 8), 256, 0, st>>>(s.part, dw, S, a.Cout, a.Cin, kk,
+                                                                                              a.transposed, Kp);
+  else
+    reduce_conv_partials_kernel<<<(unsigned)(((long long)a.Cout * K + 255) / 256), 256, 0, st>>>(s.part, dw, S, a.Cout, a.Cin, kk,
+                                                                                            a.transposed, Kp, fast ? 1 : 0);
   DPMN_LAUNCH_CHECK();
   return 0;
 }

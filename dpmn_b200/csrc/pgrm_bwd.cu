@@ -3,6 +3,7 @@
 // conv / LeakyReLU / PixelShuffle / affine-mix head.  Parameter gradients ACCUMULATE (atomicAdd) into the caller's
 // buffers; activation gradients are written.  Parity target: the reference's autograd .grad tensors
 // (tests/golden/pgrm_*_grad.npz).
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -937,7 +938,8 @@ __global__ void mix_res_bwd_kernel(const float* __restrict__ d_out, MixBwdArgs m
 }
 
 // dgrad of a 3x3 conv on NHWC with <= 16 output channels (padded rows of 16): dx[pix][ci] = sum dy[pix - tap][co] w[co][ci][tap]
-__global__ void __launch_bounds__(256) conv3x3_small_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+// one input channel per thread: the general form (Cin % 4 != 0)
+__global__ void __launch_bounds__(256) conv3x3_small_dgrad1_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                                   float* __restrict__ dx, int B, int gh, int gw, int Cin,
                                                                   int Cout, int ldx) {
   extern __shared__ float sw[];           // [tap][co(16)][Cin]
@@ -971,6 +973,51 @@ __global__ void __launch_bounds__(256) conv3x3_small_dgrad_kernel(const float* _
       }
     }
     dx[pixb * ldx + ci] = (a0 + a1) + (a2 + a3);
+  }
+}
+
+constexpr int HW_CO_PAD4 = 3;      // dy columns 0..11 carry the hp <= 12 head channels (columns 12..15 are zero padding)
+__global__ void __launch_bounds__(256) conv3x3_small_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                                  float* __restrict__ dx, int B, int gh, int gw, int Cin,
+                                                                  int Cout, int ldx) {
+  extern __shared__ float sw[];           // [tap][co(16)][Cin]
+  for (int i = threadIdx.x; i < 9 * HB_PAD * Cin; i += blockDim.x) {
+    const int ci = i % Cin, co = (i / Cin) % HB_PAD, tap = i / (Cin * HB_PAD);
+    sw[i] = co < Cout ? w[(co * Cin + ci) * 9 + tap] : 0.f;
+  }
+  __syncthreads();
+  // four input channels per thread: one 16-byte weight read and one broadcast dy value feed four multiply-adds (the
+  // one-channel form issued one shared-memory load per multiply-add: 113 us for conv1 at batch 48); Cin % 4 == 0
+  const int Cq = Cin >> 2;
+  const long long total = (long long)B * gh * gw * Cq;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % Cq) * 4;
+    const long long pixb = idx / Cq;
+    const int xx = (int)(pixb % gw), yy = (int)((pixb / gw) % gh), b = (int)(pixb / ((long long)gw * gh));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = make_float4(0.f, 0.f, 0.f, 0.f);   // two chains per channel
+    for (int ky = 0; ky < 3; ++ky) {
+      const int y2 = yy - ky + 1;
+      if (y2 < 0 || y2 >= gh) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int x2 = xx - kx + 1;
+        if (x2 < 0 || x2 >= gw) continue;
+        const float4* src = reinterpret_cast<const float4*>(dy + ((long long)(b * gh + y2) * gw + x2) * HB_PAD);
+        const float* wt = sw + (ky * 3 + kx) * HB_PAD * Cin + ci;
+#pragma unroll
+        for (int q = 0; q < HW_CO_PAD4; ++q) {          // output channels 4 q .. 4 q + 3 (columns >= Cout of dy are zero)
+          const float4 g = __ldg(src + q);
+          const float4 w0 = *reinterpret_cast<const float4*>(wt + (4 * q + 0) * Cin);
+          const float4 w1 = *reinterpret_cast<const float4*>(wt + (4 * q + 1) * Cin);
+          const float4 w2 = *reinterpret_cast<const float4*>(wt + (4 * q + 2) * Cin);
+          const float4 w3 = *reinterpret_cast<const float4*>(wt + (4 * q + 3) * Cin);
+          acc.x = fmaf(g.x, w0.x, acc.x); acc.y = fmaf(g.x, w0.y, acc.y); acc.z = fmaf(g.x, w0.z, acc.z); acc.w = fmaf(g.x, w0.w, acc.w);
+          acc2.x = fmaf(g.y, w1.x, acc2.x); acc2.y = fmaf(g.y, w1.y, acc2.y); acc2.z = fmaf(g.y, w1.z, acc2.z); acc2.w = fmaf(g.y, w1.w, acc2.w);
+          acc.x = fmaf(g.z, w2.x, acc.x); acc.y = fmaf(g.z, w2.y, acc.y); acc.z = fmaf(g.z, w2.z, acc.z); acc.w = fmaf(g.z, w2.w, acc.w);
+          acc2.x = fmaf(g.w, w3.x, acc2.x); acc2.y = fmaf(g.w, w3.y, acc2.y); acc2.z = fmaf(g.w, w3.z, acc2.z); acc2.w = fmaf(g.w, w3.w, acc2.w);
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(dx + pixb * ldx + ci) = make_float4(acc.x + acc2.x, acc.y + acc2.y, acc.z + acc2.z, acc.w + acc2.w);
   }
 }
 
@@ -1019,6 +1066,14 @@ __global__ void __launch_bounds__(128) conv3x3_small_wgrad_kernel(const float* _
   }
 }
 
+static void launch_small_wgrad(const float* dy, const float* x, float* dw, float* db, int B, int gh, int gw, int Cin, int Cout,
+                               int ldx, long long pix, cudaStream_t st) {
+  const int chunk = 128;
+  const unsigned blocks = (unsigned)((pix + chunk - 1) / chunk);
+  if (Cin <= 32) conv3x3_small_wgrad_kernel<<<dim3(blocks, 1), 32, 0, st>>>(dy, x, dw, db, B, gh, gw, Cin, Cout, ldx, chunk);
+  else conv3x3_small_wgrad_kernel<<<dim3(blocks, (Cin + 127) / 128), 128, 0, st>>>(dy, x, dw, db, B, gh, gw, Cin, Cout, ldx, chunk);
+}
+
 int launch_head_bwd(const HeadBwdArgs& h, cudaStream_t st) {
   const int hp = h.hs * h.patch * h.patch;
   if (hp > HW_CO || h.C % 4) return -2;
@@ -1033,18 +1088,16 @@ int launch_head_bwd(const HeadBwdArgs& h, cudaStream_t st) {
     DPMN_LAUNCH_CHECK();
   }
   // (2) conv2 (hp -> hp) backward: weights / bias, then data -> dt1 (B, gh, gw, 16)
-  const int chunk = 128;
-  conv3x3_small_wgrad_kernel<<<dim3((unsigned)((pix + chunk - 1) / chunk), 1), 32, 0, st>>>(h.dt2, h.t1, h.d_w2, h.d_b2, h.B, h.gh,
-                                                                                           h.gw, hp, hp, HB_PAD, chunk);
+  launch_small_wgrad(h.dt2, h.t1, h.d_w2, h.d_b2, h.B, h.gh, h.gw, hp, hp, HB_PAD, pix, st);
   DPMN_LAUNCH_CHECK();
   {
     const size_t smem = (size_t)9 * HB_PAD * hp * sizeof(float);   // dt1 columns hp..15 stay zero (memset by the caller)
-    conv3x3_small_dgrad_kernel<<<592, 256, smem, st>>>(h.dt2, h.w2, h.dt1, h.B, h.gh, h.gw, hp, hp, HB_PAD);
+    if (hp % 4 == 0) conv3x3_small_dgrad_kernel<<<592, 256, smem, st>>>(h.dt2, h.w2, h.dt1, h.B, h.gh, h.gw, hp, hp, HB_PAD);
+    else conv3x3_small_dgrad1_kernel<<<592, 256, smem, st>>>(h.dt2, h.w2, h.dt1, h.B, h.gh, h.gw, hp, hp, HB_PAD);
     DPMN_LAUNCH_CHECK();
   }
   // (3) conv1 (C -> hp) backward: weights / bias, then data -> d tokens (B, L, C)
-  conv3x3_small_wgrad_kernel<<<dim3((unsigned)((pix + chunk - 1) / chunk), (h.C + 127) / 128), 128, 0, st>>>(
-      h.dt1, h.tokens, h.d_w1, h.d_b1, h.B, h.gh, h.gw, h.C, hp, h.C, chunk);
+  launch_small_wgrad(h.dt1, h.tokens, h.d_w1, h.d_b1, h.B, h.gh, h.gw, h.C, hp, h.C, pix, st);
   DPMN_LAUNCH_CHECK();
   {
     const size_t smem = (size_t)9 * HB_PAD * h.C * sizeof(float);

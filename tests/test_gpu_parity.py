@@ -456,12 +456,14 @@ def test_hot_path_submit_pipelined_equals_sequential():
 
 
 @pytest.mark.gpu
-def test_graphed_hot_path_equals_sequential():
-    """GraphedHotPath (CUDA-graph replay, two slots in flight) against the plain forward, bit for bit."""
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+def test_graphed_hot_path_equals_sequential(prec):
+    """GraphedHotPath (CUDA-graph replay, two slots in flight) against the plain forward, bit for bit.  fp32: the CMM's
+    fp32-structured forward forks its second encoder branch onto the library's side stream INSIDE the capture (BranchFork)."""
     import bench
     from dpmn_b200.pipeline import DPMNHotPath, GraphedHotPath
     dev = torch.device("cuda")
-    model = DPMNHotPath(precision="fp16")
+    model = DPMNHotPath(precision=prec)
     pg, cm = bench.synth_weights(2)
     bench.load_weights(model, pg, cm)
     model = model.to(dev).eval()
@@ -494,7 +496,10 @@ def test_graphed_hot_path_equals_sequential():
     torch.cuda.synchronize()
     assert len(got) == len(ref)
     for a, r in zip(got, ref):
-        assert torch.equal(a, r)
+        if prec == "fp16":
+            assert torch.equal(a, r)
+        else:       # the fp32 SIMT convs split K over CTAs with atomics: last-bit run-to-run differences
+            assert float((a - r).abs().max()) <= 2e-6 * float(r.abs().max())
 
 
 @pytest.mark.gpu

@@ -26,6 +26,8 @@ int launch_patch_embed(const float* x, long long x_bs, int in_ch, const float* f
 // LayerNorm over the last dim of (rows, C) fp32 -> out (rows, C) of `out_type`.
 int launch_layernorm(const float* x, const float* w, const float* b, void* out, DType out_type, int rows, int C,
                      cudaStream_t st);
+int launch_layernorm_dual(const float* x, const float* w, const float* b, float* out, void* out16, DType type16, int rows, int C,
+                          cudaStream_t st);
 
 // C[z][m, n] = epi( sum_k A[z][m, k] * B[z][n, k] ), everything fp32 (the exact-arithmetic mode).
 struct GemmSimtArgs {

@@ -461,10 +461,12 @@ int launch_patch_embed(const float* x, long long x_bs, int in_ch, const float* f
 // =====================================================================================================
 // LayerNorm over rows of (rows, C) fp32; one warp per row.                      pgrm.py:303-304,311,322-323
 // =====================================================================================================
+// out2 (optional): a second copy of the normalised row in 16 bits (type2: DT_F16 / DT_BF16) -- the training forward keeps the
+// fp32 row for the backward and feeds the 16-bit one to the tcgen05 GEMM without a convert pass of its own.
 template <typename OutT, int CPL>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, OutT* __restrict__ out,
-                                                        int rows) {
+                                                        int rows, void* __restrict__ out2 = nullptr, int type2 = 0) {
   constexpr int C = CPL * 32;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -485,26 +487,40 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
     OutT* dst = out + (long long)r * C;
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) dst[lane + 32 * i] = from_f32<OutT>((v[i] - mu) * rstd * wr[i] + br[i]);
+    for (int i = 0; i < CPL; ++i) {
+      const float y = (v[i] - mu) * rstd * wr[i] + br[i];
+      dst[lane + 32 * i] = from_f32<OutT>(y);
+      if (out2 != nullptr) {
+        if (type2 == DT_F16) reinterpret_cast<__half*>(out2)[(long long)r * C + lane + 32 * i] = __float2half_rn(y);
+        else reinterpret_cast<__nv_bfloat16*>(out2)[(long long)r * C + lane + 32 * i] = __float2bfloat16_rn(y);
+      }
+    }
   }
 }
 
 template <typename OutT>
 static int launch_layernorm_t(const float* x, const float* w, const float* b, OutT* out, int rows, int C,
-                              cudaStream_t st) {
+                              cudaStream_t st, void* out2 = nullptr, int type2 = 0) {
   int blocks = (rows + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   switch (C / 32) {
-    case 1: layernorm_kernel<OutT, 1><<<blocks, 256, 0, st>>>(x, w, b, out, rows); break;
-    case 2: layernorm_kernel<OutT, 2><<<blocks, 256, 0, st>>>(x, w, b, out, rows); break;
-    case 3: layernorm_kernel<OutT, 3><<<blocks, 256, 0, st>>>(x, w, b, out, rows); break;
-    case 4: layernorm_kernel<OutT, 4><<<blocks, 256, 0, st>>>(x, w, b, out, rows); break;
-    case 6: layernorm_kernel<OutT, 6><<<blocks, 256, 0, st>>>(x, w, b, out, rows); break;
-    case 8: layernorm_kernel<OutT, 8><<<blocks, 256, 0, st>>>(x, w, b, out, rows); break;
+    case 1: layernorm_kernel<OutT, 1><<<blocks, 256, 0, st>>>(x, w, b, out, rows, out2, type2); break;
+    case 2: layernorm_kernel<OutT, 2><<<blocks, 256, 0, st>>>(x, w, b, out, rows, out2, type2); break;
+    case 3: layernorm_kernel<OutT, 3><<<blocks, 256, 0, st>>>(x, w, b, out, rows, out2, type2); break;
+    case 4: layernorm_kernel<OutT, 4><<<blocks, 256, 0, st>>>(x, w, b, out, rows, out2, type2); break;
+    case 6: layernorm_kernel<OutT, 6><<<blocks, 256, 0, st>>>(x, w, b, out, rows, out2, type2); break;
+    case 8: layernorm_kernel<OutT, 8><<<blocks, 256, 0, st>>>(x, w, b, out, rows, out2, type2); break;
     default: return -2;
   }
   DPMN_LAUNCH_CHECK();
   return 0;
+}
+
+// fp32 LayerNorm output + a 16-bit copy of it in one pass (training forward of the 16-bit modes)
+int launch_layernorm_dual(const float* x, const float* w, const float* b, float* out, void* out16, DType type16, int rows, int C,
+                          cudaStream_t st) {
+  if (C % 32 != 0 || C > 256 || (type16 != DT_F16 && type16 != DT_BF16)) return -2;
+  return launch_layernorm_t<float>(x, w, b, out, rows, C, st, out16, (int)type16);
 }
 
 int launch_layernorm(const float* x, const float* w, const float* b, void* out, DType out_type, int rows, int C,

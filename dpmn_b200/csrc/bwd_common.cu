@@ -202,9 +202,11 @@ int launch_branch_combine(float* dst, const float* base, const float* y, long lo
 
 // dst[z][c][r] = (T) src[z][r][c]: transposing fp32 -> 16-bit staging of a gradient / activation matrix, so that the
 // weight-gradient contraction over rows becomes a K-contiguous tcgen05 GEMM (gemm_tc.cu).  32 x 32 smem tiles.
+// copy (optional): the untransposed 16-bit copy of the same matrix, written from the same read
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_convert_kernel(const float* __restrict__ src, T* __restrict__ dst, int R,
-                                                                int Cc, long long src_bs, long long dst_bs) {
+                                                                int Cc, long long src_bs, long long dst_bs,
+                                                                T* __restrict__ copy = nullptr) {
   __shared__ float tile[32][33];
   const int z = blockIdx.z;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -214,7 +216,10 @@ __global__ void __launch_bounds__(256) transpose_convert_kernel(const float* __r
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = r0 + ty + 8 * i, c = c0 + tx;
-    tile[ty + 8 * i][tx] = (r < R && c < Cc) ? s[(long long)r * Cc + c] : 0.f;
+    const bool ok = r < R && c < Cc;
+    const float v = ok ? s[(long long)r * Cc + c] : 0.f;
+    tile[ty + 8 * i][tx] = v;
+    if (ok && copy != nullptr) copy[(long long)z * src_bs + (long long)r * Cc + c] = from_f32<T>(v);
   }
   __syncthreads();
 #pragma unroll
@@ -224,11 +229,12 @@ __global__ void __launch_bounds__(256) transpose_convert_kernel(const float* __r
   }
 }
 
-int launch_transpose_convert(const float* src, void* dst, DType t, int batch, int R, int Cc, cudaStream_t st) {
+int launch_transpose_convert(const float* src, void* dst, DType t, int batch, int R, int Cc, cudaStream_t st, void* copy16) {
   dim3 grid((Cc + 31) / 32, (R + 31) / 32, batch);
   const long long bs = (long long)R * Cc;
-  if (t == DT_F16) transpose_convert_kernel<__half><<<grid, 256, 0, st>>>(src, (__half*)dst, R, Cc, bs, bs);
-  else if (t == DT_BF16) transpose_convert_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, (__nv_bfloat16*)dst, R, Cc, bs, bs);
+  if (t == DT_F16) transpose_convert_kernel<__half><<<grid, 256, 0, st>>>(src, (__half*)dst, R, Cc, bs, bs, (__half*)copy16);
+  else if (t == DT_BF16)
+    transpose_convert_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, (__nv_bfloat16*)dst, R, Cc, bs, bs, (__nv_bfloat16*)copy16);
   else return -1;
   DPMN_LAUNCH_CHECK();
   return 0;

@@ -160,7 +160,8 @@ int launch_colsum(const float* x, long long ld, int rows, int N, float* out, cud
 int launch_rowsum(const float* x, int rows, int len, int mod, float* out, cudaStream_t st);      // out[row % mod] += sum_j
 int launch_gelu_bwd(float* g, const float* x, long long n, cudaStream_t st);                      // g *= gelu'(x)
 int launch_add(const float* a, const float* b, float* y, long long n, cudaStream_t st);
-int launch_transpose_convert(const float* src, void* dst, DType t, int batch, int R, int Cc, cudaStream_t st);
+int launch_transpose_convert(const float* src, void* dst, DType t, int batch, int R, int Cc, cudaStream_t st,
+                             void* copy16 = nullptr);
 // one pass: 16-bit copy (R, Cc), 16-bit transpose (Cc, R) and column sums (+=) of an fp32 gradient matrix; any output may be null
 int launch_stage_grad(const float* src, void* copy16, void* trans16, float* colsum, DType t, int R, int Cc, cudaStream_t st);   // (R,Cc) fp32 -> (Cc,R) 16-bit
 int launch_reduce_partials(const float* partial, float* dst, int S, long long n, cudaStream_t st);           // dst += sum_s partial[s]
@@ -216,7 +217,8 @@ int launch_sk_bwd(const SkBwdArgs& s, cudaStream_t st);
 
 // p_drop / seed / site: the Mlp's Dropout after GELU(fc1) (pgrm.py:31-32), applied to the conv INPUT on load
 int launch_dwconv_train_fwd(const float* h1pre, float* dtpre, float* dt, const float* w, const float* b, int B, int L,
-                            int hid, float p_drop, unsigned long long seed, uint32_t site, cudaStream_t st);
+                            int hid, float p_drop, unsigned long long seed, uint32_t site, cudaStream_t st, void* dt16 = nullptr,
+                            DType type16 = DT_F16);
 int launch_dwconv_bwd(const float* d_dt, const float* dtpre, const float* h1pre, const float* w, float* d_h1pre,
                       float* dw, float* db, int B, int L, int hid, float p_drop, unsigned long long seed, uint32_t site,
                       cudaStream_t st);

@@ -386,7 +386,9 @@ template <int SIDE>
 __global__ void __launch_bounds__(256) dwconv_train_fwd_fast_kernel(const float* __restrict__ h1pre, float* __restrict__ dtpre,
                                                                     float* __restrict__ dt, const float* __restrict__ w,
                                                                     const float* __restrict__ bias, int hid, float p_drop,
-                                                                    unsigned long long seed, uint32_t site) {
+                                                                    unsigned long long seed, uint32_t site,
+                                                                    void* __restrict__ dt16, int type16) {
+  // dt16 (optional): a 16-bit copy of dt, the operand of the pointwise-conv GEMM that follows (no convert pass of its own)
   constexpr int L = SIDE * SIDE, ROWS_IN = DWT_ROWS + 2, CSTRIDE = ROWS_IN * SIDE + 2;   // even stride: see the store below
   __shared__ float sm[DWF_CH * CSTRIDE];
   const int b = blockIdx.z, c0 = blockIdx.y * DWF_CH, y0 = blockIdx.x * DWT_ROWS;
@@ -431,17 +433,24 @@ __global__ void __launch_bounds__(256) dwconv_train_fwd_fast_kernel(const float*
       }
     const long long o = ((long long)b * L + (y0 + yl) * SIDE + xx) * hid + c;
     dtpre[o] = acc;
-    dt[o] = gelu_erf(acc);
+    const float y = gelu_erf(acc);
+    dt[o] = y;
+    if (dt16 != nullptr) {
+      if (type16 == DT_F16) reinterpret_cast<__half*>(dt16)[o] = __float2half_rn(y);
+      else reinterpret_cast<__nv_bfloat16*>(dt16)[o] = __float2bfloat16_rn(y);
+    }
   }
 }
 
 int launch_dwconv_train_fwd(const float* h1pre, float* dtpre, float* dt, const float* w, const float* b, int B, int L,
-                            int hid, float p_drop, unsigned long long seed, uint32_t site, cudaStream_t st) {
+                            int hid, float p_drop, unsigned long long seed, uint32_t site, cudaStream_t st, void* dt16,
+                            DType type16) {
   const int side = (int)(sqrtf((float)L) + 0.5f);
   if (side * side != L || hid % 32 || side % DWT_ROWS) return -2;
+  if (dt16 != nullptr && type16 != DT_F16 && type16 != DT_BF16) return -2;
   if (side == 32 && hid % DWF_CH == 0 && (reinterpret_cast<uintptr_t>(h1pre) & 15) == 0) {
     dwconv_train_fwd_fast_kernel<32><<<dim3(32 / DWT_ROWS, hid / DWF_CH, B), 256, 0, st>>>(h1pre, dtpre, dt, w, b, hid, p_drop,
-                                                                                          seed, site);
+                                                                                          seed, site, dt16, (int)type16);
     DPMN_LAUNCH_CHECK();
     return 0;
   }
@@ -452,6 +461,7 @@ int launch_dwconv_train_fwd(const float* h1pre, float* dtpre, float* dt, const f
   dwconv_train_fwd_kernel<<<dim3(side / DWT_ROWS, hid / 32, B), 256, smem, st>>>(h1pre, dtpre, dt, w, b, L, hid, side,
                                                                                 p_drop, seed, site);
   DPMN_LAUNCH_CHECK();
+  if (dt16 != nullptr) return launch_convert(dt, dt16, type16, (long long)B * L * hid, st);
   return 0;
 }
 

@@ -22,6 +22,15 @@ constexpr int TBK = 64;        // k-block: 64 x 16-bit = one 128-byte swizzle ro
 constexpr int TC_THREADS = 192;
 // Two CTAs per SM: the epilogue (4 warps, latency-bound loads/stores) of one CTA overlaps the other CTA's work.
 // Shared memory (<= 113 KB per CTA) and TMEM (<= 256 of 512 columns per CTA) are sized per N tile.
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 template <int BN> struct TcCfg {
   static constexpr int STAGES = BN <= 128 ? 3 : 2;
   static constexpr int ACC = BN <= 128 ? 2 : 1;        // TMEM accumulator stages
@@ -38,6 +47,7 @@ struct GemmTcParams {
   int act;                       // 0 none, 1 GELU
   const float* residual;         // fp32, indexed like C (may alias C when C is fp32)
   float* colsum;                 // if set: no C store; colsum[z][m_tile*4 + quarter][n] = sum over 32 rows
+  void* out16;                   // fp32 C only: second copy of C in the operand type (fmt), same indexing
   int ln_mode;                   // second output of the finished row: 0 none, 1 LayerNorm(ln_w, ln_b), 2 copy
   const float *ln_w, *ln_b;
   void* ln_out; int ln_type;     // (batch*M, N) rows of ln_type; requires N == BN <= 128
@@ -324,6 +334,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < CW; j += 4)
             if (full || n0 + j < p.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (p.out16 != nullptr) {                           // 16-bit copy of the same values (N % 8 == 0, ldc % 8 == 0: checked on the host)
+#pragma unroll
+            for (int j = 0; j < CW; j += 8) {
+              if (full || n0 + j < p.N) {
+                uint4 pk;
+                if (p.fmt == 0) {
+                  pk.x = pack_f16x2(v[j], v[j + 1]); pk.y = pack_f16x2(v[j + 2], v[j + 3]);
+                  pk.z = pack_f16x2(v[j + 4], v[j + 5]); pk.w = pack_f16x2(v[j + 6], v[j + 7]);
+                } else {
+                  pk.x = pack_bf16x2(v[j], v[j + 1]); pk.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                  pk.z = pack_bf16x2(v[j + 4], v[j + 5]); pk.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                }
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out16) + off + j) = pk;
+              }
+            }
+          }
         } else {
           OutT* dst = reinterpret_cast<OutT*>(p.C) + off;
 #pragma unroll
@@ -461,6 +487,10 @@ static int tc_build(const GemmTcArgs& a, int BN, CUtensorMap* map_a, CUtensorMap
   p.C = a.C; p.c_bs = a.c_bs; p.ldc = a.ldc;
   p.bias = a.bias; p.bias_bs = a.bias_bs; p.bias_mode = a.bias ? a.bias_mode : 0;
   p.act = a.act; p.residual = a.residual; p.colsum = a.colsum;
+  p.out16 = a.out16;
+  if (a.out16 != nullptr && (a.out_type != DT_F32 || a.colsum || a.scatter || a.N % 8 || a.ldc % 8 || (a.batch > 1 && a.c_bs % 8) ||
+                             (reinterpret_cast<uintptr_t>(a.out16) & 15)))
+    return -2;
   p.ln_mode = a.ln_mode; p.ln_w = a.ln_w; p.ln_b = a.ln_b; p.ln_out = a.ln_out; p.ln_type = a.ln_type;
   if ((a.ln_mode != 0) != LN) return -2;
   if (a.ln_mode != 0 && (BN > 128 || a.N != BN || a.colsum || a.scatter || !a.ln_out)) return -2;
@@ -561,6 +591,7 @@ bool gemm_tc_can_fuse_row_output(int N) { return N == 32 || N == 64 || N == 96 |
 
 int launch_gemm_tc(const GemmTcArgs& a, cudaStream_t st) {
   if (a.op_type != DT_F16 && a.op_type != DT_BF16) return -1;
+  if (a.out16 != nullptr && a.ln_mode != 0) return -2;                                  // one second output at a time
   if (a.ln_mode != 0 && gemm_res_ln_supported(a)) return launch_gemm_res_ln(a, st);   // all-TMA residual-stream kernel
   if (a.K % 16 || a.lda % 8 || a.ldb % 8) return -2;                 // 16-byte TMA strides, whole UMMA k-steps
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.Bm)) & 15) return -2;

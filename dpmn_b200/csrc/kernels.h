@@ -56,6 +56,9 @@ struct GemmTcArgs {
   int act = 0;
   const float* residual = nullptr;
   float* colsum = nullptr;
+  // out16 (fp32 C only): a second copy of C in the operand type at the same indices (z * c_bs + m * ldc + n) -- the training
+  // path keeps fp32 activations for the backward and hands the 16-bit copy to the next GEMM without a convert pass
+  void* out16 = nullptr;
   // Second output from the finished row (needs N == the N tile <= 128): ln_mode 1 = LayerNorm(ln_w, ln_b) of the
   // row, 2 = plain copy; written as (batch*M, N) of ln_type.
   int ln_mode = 0; const float* ln_w = nullptr; const float* ln_b = nullptr; void* ln_out = nullptr; DType ln_type = DT_F16;

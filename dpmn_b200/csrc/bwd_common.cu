@@ -295,6 +295,43 @@ int launch_stage_grad(const float* src, void* copy16, void* trans16, float* cols
   return 0;
 }
 
+// Up to 16 small matrices (the weights of one PGRM) transposed + converted in ONE launch: segment = blockIdx.z, the grid's
+// x / y extents cover the largest matrix.  dst[seg][c][r] = (T) src[seg][r][c].
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_convert_batch_kernel(TransposeBatch tb) {
+  __shared__ float tile[32][33];
+  const int seg = blockIdx.z;
+  const int R = tb.R[seg], Cc = tb.C[seg];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  if (r0 >= R || c0 >= Cc) return;                      // uniform per block
+  const float* __restrict__ s = tb.src[seg];
+  T* __restrict__ d = reinterpret_cast<T*>(tb.dst[seg]);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    tile[ty + 8 * i][tx] = (r < R && c < Cc) ? s[(long long)r * Cc + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;
+    if (c < Cc && r < R) d[(long long)c * R + r] = from_f32<T>(tile[tx][ty + 8 * i]);
+  }
+}
+
+int launch_transpose_convert_batch(const TransposeBatch& tb, DType t, cudaStream_t st) {
+  if (tb.count < 1 || tb.count > 16) return -1;
+  int maxR = 0, maxC = 0;
+  for (int i = 0; i < tb.count; ++i) { if (tb.R[i] > maxR) maxR = tb.R[i]; if (tb.C[i] > maxC) maxC = tb.C[i]; }
+  dim3 grid((maxC + 31) / 32, (maxR + 31) / 32, tb.count);
+  if (t == DT_F16) transpose_convert_batch_kernel<__half><<<grid, 256, 0, st>>>(tb);
+  else if (t == DT_BF16) transpose_convert_batch_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(tb);
+  else return -1;
+  DPMN_LAUNCH_CHECK();
+  return 0;
+}
+
 // dst[i] += sum_s partial[s*n + i]      (split-K partial products of the tensor-core weight gradients)
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ dst, int S, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

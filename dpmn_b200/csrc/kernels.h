@@ -144,6 +144,13 @@ struct ConvertBatch {
   long long n[16] = {};
 };
 int launch_convert_batch(const ConvertBatch& cb, DType dst_type, cudaStream_t st);
+struct TransposeBatch {            // dst[i] (C[i], R[i]) 16-bit = transpose of src[i] (R[i], C[i]) fp32
+  int count = 0;
+  const float* src[16] = {};
+  void* dst[16] = {};
+  int R[16] = {}, C[16] = {};
+};
+int launch_transpose_convert_batch(const TransposeBatch& tb, DType t, cudaStream_t st);
 // 16-bit -> fp32 (probe outputs).
 int launch_widen(const void* src, DType src_type, float* dst, long long n, cudaStream_t st);
 

@@ -687,7 +687,7 @@ def main():
     ap.add_argument("--no-psn", action="store_true", help="skip the 'PSN included' leg (frozen TATT backbone in front of the hot path)")
     ap.add_argument("--no-train", action="store_true", help="skip the configs[2] training leg of the default line")
     ap.add_argument("--no-overlap", action="store_true", help="training: all-reduce the whole bucket after the backward (no overlap)")
-    ap.add_argument("--train-steps", type=int, default=0, help="timed training steps of the default line (0 = min(steps, 10))")
+    ap.add_argument("--train-steps", type=int, default=0, help="timed training steps of the default line (0 = min(steps, 20))")
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU per step (48 = configs[1]/[2]; 64 = configs[3])")
     ap.add_argument("--train-drop", type=float, default=0.1, help="drop / attn_drop / drop_path rate of the training leg")
     args = ap.parse_args()

@@ -571,7 +571,7 @@ def run_ours(args):
     # ================= training (configs[2]) in the same line =================
     train = None
     if not args.no_train:
-        t_steps = args.train_steps if args.train_steps > 0 else max(3, min(args.steps, 10))
+        t_steps = args.train_steps if args.train_steps > 0 else max(3, min(args.steps, 20))
         train = run_train_leg(args, dev, world, rank, lib, dev_sets, host_sets, barrier, max_over_ranks, t_steps, 3, False)
     clk = clocks.stop() if rank == 0 else None
 

@@ -131,3 +131,15 @@ def test_roofline_traffic_is_read_from_the_committed_ncu_summaries():
     ta = bench.ncu_traffic_per_launch("window_attn_tc")
     assert ta is not None and 20e6 < ta < 40e6         # attention: ~28 MB of DRAM traffic per launch at batch 48
     assert bench.ncu_traffic_per_launch("no_such_class") is None
+
+
+def test_attention_roofline_constants_match_survey_8d():
+    """north_star's "fraction of the attention-FLOP roofline" (bench roofline.attention_roofline) rests on SURVEY 8d's figures:
+    4 L (C/G) sum ws^2 = 11 010 048 FLOP per image per block, 12 blocks per forward = 132 120 576; stand-alone attention
+    traffic 4 L C s = 786 432 B per image per block in 16 bits."""
+    import bench
+    per_block = 4 * 1024 * 32 * (4 + 16 + 64)
+    assert per_block == 11_010_048
+    assert bench.FLOPS_IMG["window_attn_tc"] == 12 * per_block == 132_120_576
+    assert bench.MIN_BYTES_IMG["window_attn_tc"] == 12 * 786_432
+    assert bench.FLOPS_IMG["total"] == 11_267_776_512          # 6 x 1 134.78 + 4 459.07 MFLOP per image
